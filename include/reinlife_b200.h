@@ -1,0 +1,116 @@
+/*
+ * reinlife_b200.h -- C ABI of libreinlife_b200.so, the B200 (sm_100a) implementation of
+ * ReinLife's data-parallel hot path.  Plain pointers and sizes only; every pointer in a
+ * *_bufs struct is a DEVICE pointer unless the function name ends in _host.  `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  Every entry point returns 0
+ * on success, a negative rl_status otherwise, and never synchronises the stream unless
+ * documented.
+ *
+ * Each entry point names the reference interface (file:line under the reference checkout)
+ * it replaces; INTEGRATION.md shows the ctypes binding a ReinLife maintainer would add.
+ */
+#ifndef REINLIFE_B200_H
+#define REINLIFE_B200_H
+#include <stdint.h>
+#include "rl_rng.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RL_OBS_DIM 153          /* World/environment.py:119,362-370 */
+#define RL_N_ACTIONS 8          /* World/utils.py:4-17 */
+#define RL_FOV 3                /* World/environment.py:353 */
+#define RL_MAX_GENES 32         /* static families: one gene per brain */
+
+/* World/utils.py:20-33 */
+enum rl_entity { RL_EMPTY = 0, RL_FOOD = 1, RL_POISON = 2, RL_AGENT = 3, RL_KIN = 4, RL_SUPER_FOOD = 5 };
+
+/* rl_agent_rec.flags bits (World/entities.py:145-160) */
+#define RL_F_KILLED 1u          /* agent.killed */
+#define RL_F_INTER_KILLED 2u    /* agent.inter_killed (set when victim has the SAME gene, environment.py:696-697) */
+#define RL_F_INTRA_KILLED 4u    /* agent.intra_killed */
+#define RL_F_ATE_SUPER 8u       /* agent.ate_super_food == 1.0 (else -1) */
+#define RL_F_REPRODUCED 16u     /* agent.reproduced */
+#define RL_F_DEAD 32u           /* agent.dead */
+
+enum rl_status {
+    RL_OK = 0,
+    RL_ERR_ARG = -1,            /* bad size / null pointer (reference: AssertionError, World/grid.py:23-24) */
+    RL_ERR_CUDA = -2,           /* a CUDA call failed; rl_last_error() has the text */
+    RL_ERR_UNSUPPORTED = -3
+};
+
+/* One agent, 16 bytes, lists are kept in ROW-MAJOR cell order = the order of
+ * Grid.get_entities (World/grid.py:60-67), which is the reference's agent order everywhere. */
+typedef struct rl_agent_rec {
+    uint16_t cell;              /* i*width + j */
+    int16_t  health;            /* multiple of 10, may be negative (World/environment.py:269,711) */
+    int16_t  age;
+    int16_t  max_age;
+    int32_t  gene;
+    uint8_t  flags;
+    int8_t   action;            /* 0-3 move U/R/D/L, 4-7 attack U/R/D/L, -1 = none yet */
+    uint16_t prev_slot;         /* slot this agent had in the previous `state` list (obs_state row) */
+} rl_agent_rec;
+
+typedef struct rl_world_cfg {
+    int32_t  n_worlds;          /* worlds in this shard */
+    int32_t  height, width;     /* >= 3 (World/grid.py:23-24); height*width <= 65535 */
+    int32_t  n_genes;           /* = len(brains) for static families */
+    int32_t  max_agents;        /* Environment(max_agents) -- a soft cap */
+    int32_t  slot_cap;          /* rows per world in rec/reward/obs buffers (<= height*width) */
+    int32_t  obs_ld;            /* floats per observation row, >= 153, multiple of 4; pad is zero-filled */
+    int32_t  static_families;   /* only 1 is implemented */
+    int32_t  limit_reproduction;
+    int32_t  incentivize_killing;
+    uint64_t seed;
+    int64_t  world_id0;         /* global id of local world 0 (sharding: rank*n_worlds) */
+} rl_world_cfg;
+
+typedef struct rl_world_bufs {
+    uint8_t*      type;         /* [n_worlds, H*W] rl_entity per cell */
+    rl_agent_rec* rec;          /* [n_worlds, slot_cap] current agent list */
+    int32_t*      n_agents;     /* [n_worlds] */
+    float*        reward;       /* [n_worlds, slot_cap] float32(reference reward), written by step */
+    float*        obs_state;    /* [n_worlds, slot_cap, obs_ld] agent.state  (written by reset/update/top_up) */
+    float*        obs_prime;    /* [n_worlds, slot_cap, obs_ld] agent.state_prime (written by step) */
+    int32_t*      gene_count;   /* [n_worlds, n_genes] agents per gene in the current list */
+    int32_t*      status;       /* [n_worlds] sticky bit 0: slot_cap overflow */
+    float*        stats;        /* [n_worlds, n_genes, RL_N_STATS] tracker partials of the last step, may be NULL */
+} rl_world_bufs;
+
+/* per world x gene partial sums over the post-step agent list (Helpers/tracker.py:178-266) */
+enum rl_stat { RL_STAT_COUNT = 0, RL_STAT_AGE_SUM, RL_STAT_REWARD_SUM, RL_STAT_AGE_MAX,
+               RL_STAT_ATTACKS, RL_STAT_KILLS, RL_N_STATS = 8 };
+
+const char* rl_last_error(void);
+int rl_version(void);
+
+/* Environment.reset()  -- World/environment.py:133-158.  Writes type/rec/n_agents/obs_state. */
+int rl_world_reset(const rl_world_cfg* cfg, const rl_world_bufs* bufs, void* stream);
+
+/* Environment.step()   -- World/environment.py:160-186 (_act :258, _attack :652, _prepare_movement :591,
+ * _execute_movement :627, _eat :701, _update_death_status :789, _get_rewards :277, _add_food :763,
+ * _get_observations :313).  Reads rec[].action (set by the act call or by the caller), `t` is the env
+ * step counter (1 for the first step after reset).  Writes type/rec/n_agents/reward/obs_prime. */
+int rl_world_step(const rl_world_cfg* cfg, const rl_world_bufs* bufs, uint64_t t, void* stream);
+
+/* Environment.update_env() -- World/environment.py:188-215 (_reproduce :488, _produce :521,
+ * _remove_dead_agents :795, _get_observations :313, _update_agents_state :784).  Same `t` as the step
+ * it follows.  Writes type/rec/n_agents/obs_state. */
+int rl_world_update(const rl_world_cfg* cfg, const rl_world_bufs* bufs, uint64_t t, void* stream);
+
+/* Saturated-world generator of the benchmark: add agents on random empty cells until
+ * `target` are on the grid (gene U{0..G-1}, health 10*U{1..20}, age U{0..max_age-1}), then observe. */
+int rl_world_top_up(const rl_world_cfg* cfg, const rl_world_bufs* bufs, uint64_t t, int32_t target,
+                    int32_t max_age, void* stream);
+
+/* Environment._get_observations() alone -- World/environment.py:313-375, Grid.fov World/grid.py:90-117.
+ * Writes obs_state (which=0) or obs_prime (which=1) for the current list; does not change the world. */
+int rl_world_observe(const rl_world_cfg* cfg, const rl_world_bufs* bufs, int32_t which, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REINLIFE_B200_H */
