@@ -1,0 +1,92 @@
+"""Device-resident batch of independent ReinLife worlds (SoA tensors in HBM) driven through the C ABI.
+
+One `VecWorld` = `n_worlds` instances of the reference's `Environment` state
+(ReinLife/World/environment.py:133-215), laid out as rl_world_bufs (include/reinlife_b200.h).
+PyTorch is used for device memory and streams only.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+REC_DTYPE = np.dtype([("cell", "<u2"), ("health", "<i2"), ("age", "<i2"), ("max_age", "<i2"),
+                      ("gene", "<i4"), ("flags", "u1"), ("action", "i1"), ("prev_slot", "<u2")])
+
+
+class VecWorld:
+    def __init__(self, n_worlds, height=30, width=30, n_genes=2, max_agents=100, seed=0, world_id0=0,
+                 slot_cap=None, static_families=True, limit_reproduction=False, incentivize_killing=True,
+                 device="cuda", with_stats=False):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.RLError("VecWorld needs a CUDA device: reinlife_b200 has no CPU path")
+        self.n_worlds, self.H, self.W, self.G = n_worlds, height, width, n_genes
+        self.C = height * width
+        self.S = int(slot_cap or self.C)
+        self.ld = _lib.OBS_LD
+        self.cfg = _lib.WorldCfg(n_worlds, height, width, n_genes, max_agents, self.S, self.ld,
+                                 int(static_families), int(limit_reproduction), int(incentivize_killing),
+                                 seed, world_id0)
+        dev = self.device
+        self.type = torch.zeros((n_worlds, self.C), dtype=torch.uint8, device=dev)
+        self.rec = torch.zeros((n_worlds, self.S, 16), dtype=torch.uint8, device=dev)
+        self.n_agents = torch.zeros(n_worlds, dtype=torch.int32, device=dev)
+        self.reward = torch.zeros((n_worlds, self.S), dtype=torch.float32, device=dev)
+        self.obs_state = torch.zeros((n_worlds, self.S, self.ld), dtype=torch.float32, device=dev)
+        self.obs_prime = torch.zeros((n_worlds, self.S, self.ld), dtype=torch.float32, device=dev)
+        self.gene_count = torch.zeros((n_worlds, n_genes), dtype=torch.int32, device=dev)
+        self.status = torch.zeros(n_worlds, dtype=torch.int32, device=dev)
+        self.stats = torch.zeros((n_worlds, n_genes, _lib.N_STATS), dtype=torch.float32, device=dev) if with_stats else None
+        self.bufs = _lib.WorldBufs(self.type.data_ptr(), self.rec.data_ptr(), self.n_agents.data_ptr(),
+                                   self.reward.data_ptr(), self.obs_state.data_ptr(), self.obs_prime.data_ptr(),
+                                   self.gene_count.data_ptr(), self.status.data_ptr(),
+                                   self.stats.data_ptr() if with_stats else None)
+        self.t = 0
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # --- the reference's Environment phases -------------------------------------------------------
+    def reset(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.rl_world_reset(C.byref(self.cfg), C.byref(self.bufs), self._stream()))
+        self.t = 0
+
+    def step(self):
+        self.t += 1
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.rl_world_step(C.byref(self.cfg), C.byref(self.bufs), C.c_uint64(self.t), self._stream()))
+
+    def update(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.rl_world_update(C.byref(self.cfg), C.byref(self.bufs), C.c_uint64(self.t), self._stream()))
+
+    def top_up(self, target, max_age=50):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.rl_world_top_up(C.byref(self.cfg), C.byref(self.bufs), C.c_uint64(self.t),
+                                                C.c_int32(target), C.c_int32(max_age), self._stream()))
+
+    def observe(self, which=0):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.rl_world_observe(C.byref(self.cfg), C.byref(self.bufs), C.c_int32(which), self._stream()))
+
+    # --- host views (tests, trackers) -----------------------------------------------------------
+    def rec_host(self):
+        return self.rec.cpu().numpy().view(REC_DTYPE).reshape(self.n_worlds, self.S)
+
+    def load_host(self, w, typ, rec):
+        """Upload one world's canonical state (cell types + row-major agent list)."""
+        self.type[w] = torch.from_numpy(np.ascontiguousarray(np.asarray(typ, np.uint8).reshape(-1))).to(self.device)
+        n = len(rec)
+        if n:
+            raw = np.ascontiguousarray(rec).view(np.uint8).reshape(n, 16)
+            self.rec[w, :n] = torch.from_numpy(raw.copy()).to(self.device)
+        self.n_agents[w] = n
+
+    def set_actions(self, actions):
+        """actions: int8 tensor/array [n_worlds, <=S] in slot order -> rec[].action."""
+        a = torch.as_tensor(actions, dtype=torch.int8, device=self.device)
+        self.rec[:, :a.shape[1], 13] = a.view(torch.uint8)

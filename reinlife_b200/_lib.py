@@ -1,0 +1,67 @@
+"""ctypes binding of libreinlife_b200.so (include/reinlife_b200.h).
+
+The library is the product: if it is missing or fails to load, importing this module raises --
+there is no CPU fallback anywhere in reinlife_b200.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libreinlife_b200.so")
+
+OBS_DIM = 153
+N_ACTIONS = 8
+OBS_LD = 160           # floats per observation row (640 B: 16-byte vector / TMA friendly); pad is zero
+MAX_GENES = 32
+N_STATS = 8
+
+F_KILLED, F_INTER_KILLED, F_INTRA_KILLED, F_ATE_SUPER, F_REPRODUCED, F_DEAD = 1, 2, 4, 8, 16, 32
+EMPTY, FOOD, POISON, AGENT, KIN, SUPER_FOOD = 0, 1, 2, 3, 4, 5
+
+
+class RLError(RuntimeError):
+    pass
+
+
+class WorldCfg(C.Structure):
+    _fields_ = [("n_worlds", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("n_genes", C.c_int32),
+                ("max_agents", C.c_int32), ("slot_cap", C.c_int32), ("obs_ld", C.c_int32),
+                ("static_families", C.c_int32), ("limit_reproduction", C.c_int32),
+                ("incentivize_killing", C.c_int32), ("seed", C.c_uint64), ("world_id0", C.c_int64)]
+
+
+class WorldBufs(C.Structure):
+    _fields_ = [("type", C.c_void_p), ("rec", C.c_void_p), ("n_agents", C.c_void_p), ("reward", C.c_void_p),
+                ("obs_state", C.c_void_p), ("obs_prime", C.c_void_p), ("gene_count", C.c_void_p),
+                ("status", C.c_void_p), ("stats", C.c_void_p)]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (building it is __graft_entry__.build()'s job)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RLError(f"{LIB_PATH} not found: build it with `python -m reinlife_b200.csrc.build` "
+                      "(nvcc, sm_100a).  reinlife_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.rl_last_error.restype = C.c_char_p
+    lib.rl_version.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RLError(f"libreinlife_b200 error {rc}: {load().rl_last_error().decode()}")
+
+
+def exported_symbols():
+    """Every extern "C" symbol include/reinlife_b200.h declares (used by the CPU-side ABI test)."""
+    import re
+    hdr = os.path.join(_HERE, "..", "include", "reinlife_b200.h")
+    text = open(hdr).read()
+    return sorted(set(re.findall(r"^\s*(?:int|const char\*)\s+(rl_[a-z0-9_]+)\s*\(", text, re.M)))

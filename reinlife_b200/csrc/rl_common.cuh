@@ -1,0 +1,44 @@
+// rl_common.cuh -- shared device helpers for the ReinLife sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/reinlife_b200.h"
+
+#define RL_NONE16 0xFFFFu
+
+extern thread_local char g_rl_err[512];
+int rl_set_err(int code, const char* fmt, ...);
+
+#define RL_CUDA_CHECK(expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return rl_set_err(RL_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                              __FILE__, __LINE__);                                            \
+    } while (0)
+
+#define RL_ARG_CHECK(cond)                                                                    \
+    do {                                                                                      \
+        if (!(cond)) return rl_set_err(RL_ERR_ARG, "argument check failed: %s (%s:%d)", #cond, __FILE__, __LINE__); \
+    } while (0)
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// streaming (write-once) stores: keep obs rows from polluting L1
+__device__ __forceinline__ void st_stream_f4(float4* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ int4 ld_stream_i4(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}

@@ -1,0 +1,706 @@
+// world_kernels.cu -- ReinLife World hot path on sm_100a: one CTA per world, the whole world
+// (cell types + agent attributes) staged in shared memory, all order-dependent reference loops
+// replaced by closed-form gather rules (no atomics on the data path), sequential RNG placements
+// done by warp 0 on ballot-built bitmasks, observations written as full 16-byte-vector rows.
+//
+// Reference semantics: ReinLife/World/environment.py (cited per phase), grid.py:60-117,
+// entities.py:145-248; closed forms: SURVEY.md Appendix A.3-A.6 (validated against the reference
+// through oracle/rl_oracle.c, which keeps the sequential formulation).
+#include "rl_common.cuh"
+
+namespace {
+
+constexpr int WT = 256;         // threads per world
+constexpr int WNW = WT / 32;    // warps per world
+
+__constant__ float c_hratio[41];  // float32(float64(10*(k-20))/200.0): health/max_health for multiples of 10
+
+enum { M_ALIVE = 0, M_NFOOD, M_NPOISON, M_NSUPER, M_NB, M_PRESENT, M_ANY, M_PALL, M_ALIVE_G = 8,
+       M_CNT_G = M_ALIVE_G + RL_MAX_GENES, M_PG = M_CNT_G + RL_MAX_GENES, M_WORDS = M_PG + RL_MAX_GENES };
+
+struct WParams {
+    rl_world_cfg cfg;
+    rl_world_bufs b;
+    uint64_t t;
+    int32_t target, max_age, which;
+    uint32_t magicW;
+};
+
+struct WS {
+    float* rows;        // [WNW][ld] observation staging
+    int32_t* gene;      // [C]
+    uint32_t* pk;       // [C] packed observation planes
+    uint32_t* mask;     // [Cw] empty cells
+    uint32_t* amask;    // [Cw] agent cells / eligible parents
+    uint32_t* wpre;     // [Cw] exclusive popc prefix of amask
+    int32_t* misc;      // [M_WORDS]
+    int16_t *health, *age, *maxage;
+    uint16_t *aslot, *tgt, *src, *cellof;
+    uint8_t *type, *ntype, *flags;
+    int8_t* action;
+};
+
+__host__ __device__ inline size_t ws_bytes(int C, int ld) {
+    size_t Cw = (size_t)(C + 31) / 32;
+    size_t Cp = ((size_t)C + 15) & ~(size_t)15;
+    return sizeof(float) * WNW * ld + 4 * Cp * 2 + 4 * ((Cw + 3) & ~(size_t)3) * 3 + 4 * M_WORDS + 2 * Cp * 7 + Cp * 4;
+}
+
+__device__ inline void ws_carve(WS& s, unsigned char* base, int C, int ld) {
+    size_t Cw = ((size_t)(C + 31) / 32 + 3) & ~(size_t)3;
+    size_t Cp = ((size_t)C + 15) & ~(size_t)15;
+    unsigned char* p = base;
+    s.rows = (float*)p; p += sizeof(float) * WNW * ld;
+    s.gene = (int32_t*)p; p += 4 * Cp;
+    s.pk = (uint32_t*)p; p += 4 * Cp;
+    s.mask = (uint32_t*)p; p += 4 * Cw;
+    s.amask = (uint32_t*)p; p += 4 * Cw;
+    s.wpre = (uint32_t*)p; p += 4 * Cw;
+    s.misc = (int32_t*)p; p += 4 * M_WORDS;
+    s.health = (int16_t*)p; p += 2 * Cp;
+    s.age = (int16_t*)p; p += 2 * Cp;
+    s.maxage = (int16_t*)p; p += 2 * Cp;
+    s.aslot = (uint16_t*)p; p += 2 * Cp;
+    s.tgt = (uint16_t*)p; p += 2 * Cp;
+    s.src = (uint16_t*)p; p += 2 * Cp;
+    s.cellof = (uint16_t*)p; p += 2 * Cp;
+    s.type = p; p += Cp;
+    s.ntype = p; p += Cp;
+    s.flags = p; p += Cp;
+    s.action = (int8_t*)p;
+}
+
+// toroidal neighbour: 0 up (i-1), 1 right (j+1), 2 down (i+1), 3 left (j-1) -- environment.py:601-623
+__device__ __forceinline__ int nbr(int c, int d, int W, int C, uint32_t magicW) {
+    if (d == 0) return c < W ? c + C - W : c - W;
+    if (d == 2) return c + W >= C ? c + W - C : c + W;
+    int i = (int)__umulhi((uint32_t)c, magicW);
+    int j = c - i * W;
+    if (d == 1) return j == W - 1 ? c - (W - 1) : c + 1;
+    return j == 0 ? c + (W - 1) : c - 1;
+}
+
+// ---- warp-0 sequential placement on the empty-cell bitmask (Grid.set_random, grid.py:69-83) ----
+// Returns the cell holding the k-th empty cell in row-major order, k = rl_below(bits, n_empty); -1 if none.
+__device__ int warp_place(uint32_t* mask, int nwords, uint64_t bits) {
+    const int lane = lane_id();
+    const int wpl = (nwords + 31) / 32;
+    const int w0 = lane * wpl, w1 = min(nwords, w0 + wpl);
+    int cnt = 0;
+    for (int wd = w0; wd < w1; ++wd) cnt += __popc(mask[wd]);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return -1;
+    const int k = (int)rl_below(bits, (uint32_t)total);
+    const unsigned bal = __ballot_sync(0xffffffffu, incl > k);
+    const int owner = __ffs(bal) - 1;
+    int cell = -1;
+    if (lane == owner) {
+        int kk = k - (incl - cnt);
+        for (int wd = w0; wd < w1; ++wd) {
+            int p = __popc(mask[wd]);
+            if (kk < p) { cell = wd * 32 + (int)__fns(mask[wd], 0, kk + 1); break; }
+            kk -= p;
+        }
+    }
+    cell = __shfl_sync(0xffffffffu, cell, owner);
+    return cell;
+}
+
+__device__ __forceinline__ void warp_mask_clear(uint32_t* mask, int cell) {
+    if (lane_id() == 0) mask[cell >> 5] &= ~(1u << (cell & 31));
+    __syncwarp();
+}
+
+__device__ __forceinline__ void spawn_agent(WS& s, int cell, int gene, int health, int age) {   // entities.py:145-160
+    if (lane_id() == 0) {
+        s.type[cell] = RL_AGENT;
+        s.health[cell] = (int16_t)health; s.age[cell] = (int16_t)age; s.maxage[cell] = 50;
+        s.gene[cell] = gene; s.flags[cell] = 0; s.action[cell] = -1; s.aslot[cell] = RL_NONE16;
+    }
+    __syncwarp();
+}
+
+// build the empty-cell bitmask of `tarr` (all warps)
+__device__ __forceinline__ void build_empty_mask(const uint8_t* tarr, uint32_t* mask, int C) {
+    const int Cw = (C + 31) / 32;
+    for (int ch = threadIdx.x >> 5; ch < Cw; ch += WNW) {
+        int c = ch * 32 + lane_id();
+        unsigned m = __ballot_sync(0xffffffffu, c < C && tarr[c] == RL_EMPTY);
+        if (lane_id() == 0) mask[ch] = m;
+    }
+}
+
+// load cell types + the agent list into the cell-indexed shared arrays
+template <bool DECAY>
+__device__ __forceinline__ int load_world(const WParams& P, WS& s, int w) {
+    const int C = P.cfg.height * P.cfg.width;
+    const uint8_t* tg = P.b.type + (size_t)w * C;
+    for (int c = threadIdx.x; c < C; c += WT) { s.type[c] = tg[c]; s.aslot[c] = RL_NONE16; }
+    for (int k = threadIdx.x; k < M_WORDS; k += WT) s.misc[k] = 0;
+    const int n = min(P.b.n_agents[w], P.cfg.slot_cap);
+    __syncthreads();
+    const int4* rg = reinterpret_cast<const int4*>(P.b.rec + (size_t)w * P.cfg.slot_cap);
+    for (int sl = threadIdx.x; sl < n; sl += WT) {
+        int4 v = ld_stream_i4(rg + sl);
+        int c = v.x & 0xFFFF;
+        int h = (int16_t)(v.x >> 16), age = (int16_t)(v.y & 0xFFFF), ma = (int16_t)(v.y >> 16);
+        int fl = v.w & 0xFF, act = (int8_t)((v.w >> 8) & 0xFF);
+        if (DECAY) {                                       // _act, environment.py:268-271
+            h = min(200, h - 10);
+            age = min(ma, age + 1);
+            fl &= ~(RL_F_KILLED | RL_F_INTER_KILLED | RL_F_INTRA_KILLED);
+        }
+        s.health[c] = (int16_t)h; s.age[c] = (int16_t)age; s.maxage[c] = (int16_t)ma;
+        s.gene[c] = v.z; s.flags[c] = (uint8_t)fl; s.action[c] = (int8_t)act;
+        s.aslot[c] = (uint16_t)sl; s.cellof[sl] = (uint16_t)c;
+    }
+    __syncthreads();
+    return n;
+}
+
+__device__ __forceinline__ float hratio(int h) {       // float32(health / max_health), environment.py:365,397
+    int k = h / 10;
+    if (k * 10 == h && k >= -20 && k <= 20) return c_hratio[k + 20];
+    return (float)((double)h / 200.0);
+}
+
+// Rebuild the agent list from the final grid `ft` (Grid.get_entities, grid.py:60-67), write
+// type/rec/n_agents(/reward), then Environment._get_observations (environment.py:313-375).
+// src[c] = index into the attribute arrays of the agent standing on cell c.
+template <bool STEP>
+__device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t* ft, float* obs_out) {
+    const int H = P.cfg.height, W = P.cfg.width, C = H * W, Cw = (C + 31) / 32;
+    const int S = P.cfg.slot_cap, ld = P.cfg.obs_ld, G = P.cfg.n_genes;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    uint8_t* tg = P.b.type + (size_t)w * C;
+
+    for (int ch = warp; ch < Cw; ch += WNW) {
+        int c = ch * 32 + lane;
+        bool in = c < C;
+        uint8_t t = in ? ft[c] : (uint8_t)0;
+        unsigned m = __ballot_sync(0xffffffffu, in && t == RL_AGENT);
+        if (lane == 0) s.amask[ch] = m;
+        if (in) tg[c] = t;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int wpl = (Cw + 31) / 32;
+        const int w0 = lane * wpl, w1 = min(Cw, w0 + wpl);
+        int cnt = 0;
+        for (int wd = w0; wd < w1; ++wd) cnt += __popc(s.amask[wd]);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int run = incl - cnt;
+        for (int wd = w0; wd < w1; ++wd) { s.wpre[wd] = run; run += __popc(s.amask[wd]); }
+        if (lane == 31) s.misc[M_NB] = incl;
+        for (int g = lane; g < RL_MAX_GENES; g += 32) s.misc[M_CNT_G + g] = 0;
+    }
+    __syncthreads();
+    const int nB = s.misc[M_NB];
+    const int alive = s.misc[M_ALIVE];
+    rl_agent_rec* rg = P.b.rec + (size_t)w * S;
+    for (int c = threadIdx.x; c < C; c += WT) {
+        uint8_t t = ft[c];
+        uint32_t pk;
+        if (t == RL_AGENT) {
+            const int slot = s.wpre[c >> 5] + __popc(s.amask[c >> 5] & ((1u << (c & 31)) - 1u));
+            const int sc = s.src[c];
+            const int h = s.health[sc], g = s.gene[sc];
+            const unsigned fl = s.flags[sc] & 0x3Fu;
+            pk = (h < 0 ? 2u : 0u) | 4u | ((fl & RL_F_DEAD) ? 8u : 0u) | (((uint32_t)g & 0xFFu) << 4) |
+                 ((uint32_t)(uint16_t)(int16_t)h << 16);
+            atomicAdd(&s.misc[M_CNT_G + (g & (RL_MAX_GENES - 1))], 1);
+            if (slot < S) {
+                s.cellof[slot] = (uint16_t)c;
+                int4 v;
+                v.x = (c & 0xFFFF) | ((int)(uint16_t)(int16_t)h << 16);
+                v.y = ((int)(uint16_t)s.age[sc]) | ((int)(uint16_t)s.maxage[sc] << 16);
+                v.z = g;
+                const unsigned prev = STEP ? (unsigned)s.aslot[sc] : (unsigned)slot;
+                v.w = (int)(fl | (((unsigned)(uint8_t)s.action[sc]) << 8) | (prev << 16));
+                reinterpret_cast<int4*>(rg)[slot] = v;
+                if (STEP) {                                 // _get_rewards, environment.py:291-311
+                    const int kin = max(0, s.misc[M_ALIVE_G + g] - 1);
+                    double r;
+                    if (fl & RL_F_DEAD) r = (double)(kin - alive);
+                    else if (alive == 1) r = 0.0;
+                    else r = (double)kin / (double)alive;
+                    if ((fl & RL_F_KILLED) && P.cfg.incentivize_killing) r += 0.2;
+                    P.b.reward[(size_t)w * S + slot] = (float)r;
+                }
+            }
+        } else {
+            pk = t == RL_FOOD ? 1u : t == RL_SUPER_FOOD ? 2u : t == RL_POISON ? 3u : 0u;   // _get_food :432-446
+        }
+        s.pk[c] = pk;
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        int cg = s.misc[M_CNT_G + threadIdx.x];
+        reinterpret_cast<float*>(s.misc)[M_PG + threadIdx.x] = (float)((double)cg / (double)nB);   // :357
+        if (P.b.gene_count) P.b.gene_count[(size_t)w * G + threadIdx.x] = cg;
+    }
+    if (threadIdx.x == RL_MAX_GENES) {
+        reinterpret_cast<float*>(s.misc)[M_PALL] = (float)((double)nB / (double)P.cfg.max_agents);  // :358
+        P.b.n_agents[w] = min(nB, S);
+        if (nB > S && P.b.status) atomicOr(&P.b.status[w], 1);
+    }
+    __syncthreads();
+
+    // ---- observation rows: one warp per agent, 7x7 toroidal window (Grid.fov, grid.py:90-117) ----
+    const bool float_path = ft[0] == RL_AGENT;   // np.vectorize dtype quirk, SURVEY A.8
+    const float pall = reinterpret_cast<float*>(s.misc)[M_PALL];
+    float* row = s.rows + warp * ld;
+    const int nrow = min(nB, S);
+    for (int sl = warp; sl < nrow; sl += WNW) {
+        const int d = s.cellof[sl];
+        const int i = (int)__umulhi((uint32_t)d, P.magicW), j = d - i * W;
+        const uint32_t me = s.pk[d];
+        const int mygene = (me >> 4) & 0xFF;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int q = lane + 32 * it;
+            if (q < 49) {
+                const int qi = q / 7, qj = q - qi * 7;
+                int r = i + qi - 3, cc = j + qj - 3;
+                r = r < 0 ? r + H : (r >= H ? r - H : r);
+                cc = cc < 0 ? cc + W : (cc >= W ? cc - W : cc);
+                const uint32_t pk = s.pk[r * W + cc];
+                const unsigned fc = pk & 3u;
+                row[q] = fc == 0 ? 0.f : fc == 1 ? .5f : fc == 2 ? 1.f : -1.f;
+                float hv = -1.f, gv = 0.f;
+                if (pk & 4u) {
+                    const int h = (int16_t)(pk >> 16);
+                    hv = float_path ? hratio(h) : (float)(h / 200);           // :396-398
+                    if (pk & 8u) gv = (int)((pk >> 4) & 0xFF) == mygene ? 1.f : -1.f;   // :424-428, :448-456
+                }
+                row[49 + q] = hv;
+                row[98 + q] = gv;
+            }
+        }
+        if (lane < ld - 147) {
+            float v = 0.f;
+            const unsigned fl = s.flags[s.src[d]];
+            if (lane == 0) v = hratio((int16_t)(me >> 16));                   // :365
+            else if (lane == 1) v = (fl & RL_F_REPRODUCED) ? 1.f : 0.f;        // :359
+            else if (lane == 2) v = reinterpret_cast<float*>(s.misc)[M_PG + mygene];
+            else if (lane == 3) v = pall;
+            else if (lane == 4) v = (fl & RL_F_KILLED) ? 1.f : 0.f;            // :369
+            else if (lane == 5) v = (fl & RL_F_ATE_SUPER) ? 1.f : -1.f;        // :370
+            row[147 + lane] = v;
+        }
+        for (int e = 179 + lane; e < ld; e += 32) row[e] = 0.f;
+        __syncwarp();
+        float4* og = reinterpret_cast<float4*>(obs_out + ((size_t)w * S + sl) * ld);
+        for (int v4 = lane; v4 < ld / 4; v4 += 32) st_stream_f4(og + v4, reinterpret_cast<const float4*>(row)[v4]);
+        __syncwarp();
+    }
+}
+
+// =====================================================================================================
+// Environment.step -- environment.py:160-186
+// =====================================================================================================
+__global__ void __launch_bounds__(WT) k_world_step(const WParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int w = blockIdx.x;
+    const int H = P.cfg.height, W = P.cfg.width, C = H * W, Cw = (C + 31) / 32;
+    WS s; ws_carve(s, smem, C, P.cfg.obs_ld);
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
+
+    const int n = load_world<true>(P, s, w);
+
+    // ---- _attack (environment.py:652-699) in closed form + _prepare_movement (:591-625) ----
+    for (int sl = threadIdx.x; sl < n; sl += WT) {
+        const int c = s.cellof[sl];
+        const int a = s.action[c];
+        int h = s.health[c];
+        unsigned fl = s.flags[c];
+        bool hits = false;
+        if (a >= 4 && a <= 7) {
+            const int tc = nbr(c, a - 4, W, C, P.magicW);
+            if (s.type[tc] == RL_AGENT) {
+                hits = true;
+                fl |= RL_F_KILLED | (s.gene[tc] == s.gene[c] ? RL_F_INTER_KILLED : RL_F_INTRA_KILLED);   // :696-699
+            }
+        }
+        int L = -1;   // largest order index (= cell index) among agents that hit me
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int nb = nbr(c, (d + 2) & 3, W, C, P.magicW);      // the cell whose direction-d neighbour is c
+            if (s.type[nb] == RL_AGENT && s.action[nb] == 4 + d) L = max(L, nb);
+        }
+        if (hits) h = (L > c) ? 0 : min(200, (L >= 0 ? 0 : h) + 100);   // entities.py:178-185
+        else if (L >= 0) h = 0;
+        s.health[c] = (int16_t)h;
+        s.flags[c] = (uint8_t)fl;
+        s.tgt[c] = (uint16_t)((a >= 0 && a <= 3) ? nbr(c, a, W, C, P.magicW) : c);
+    }
+    __syncthreads();
+
+    // ---- _execute_movement conflict fixed point (environment.py:637-644, 717-726) ----
+    for (;;) {
+        int any = 0;
+        for (int sl = threadIdx.x; sl < n; sl += WT) {
+            const int c = s.cellof[sl];
+            const int t = s.tgt[c];
+            if (t != c) {
+                int cnt = (s.type[t] == RL_AGENT && s.tgt[t] == t) ? 1 : 0;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const int nb = nbr(t, d, W, C, P.magicW);
+                    cnt += (s.type[nb] == RL_AGENT && s.tgt[nb] == t) ? 1 : 0;
+                }
+                if (cnt > 1) { s.flags[c] |= 0x40u; any = 1; }
+            }
+        }
+        any = __syncthreads_or(any);
+        if (!any) break;
+        for (int sl = threadIdx.x; sl < n; sl += WT) {
+            const int c = s.cellof[sl];
+            if (s.flags[c] & 0x40u) { s.flags[c] &= ~0x40u; s.tgt[c] = (uint16_t)c; }
+        }
+        __syncthreads();
+    }
+
+    // ---- execute: _eat (:701-715) on the pre-move content, vanish rule, new grid ----
+    for (int c = threadIdx.x; c < C; c += WT) {
+        const uint8_t t = s.type[c];
+        if (t == RL_AGENT) {
+            const bool stay = s.tgt[c] == c;
+            s.ntype[c] = stay ? RL_AGENT : RL_EMPTY;
+            s.src[c] = stay ? (uint16_t)c : (uint16_t)RL_NONE16;
+        } else {
+            s.ntype[c] = t;
+            s.src[c] = RL_NONE16;
+        }
+    }
+    for (int sl = threadIdx.x; sl < n; sl += WT) {
+        const int c = s.cellof[sl];
+        const int t = s.tgt[c];
+        if (t != c) {
+            const uint8_t tt = s.type[t];
+            int h = s.health[c];
+            if (tt == RL_FOOD) h = min(200, h + 40);
+            else if (tt == RL_POISON) h = min(200, h - 40);
+            else if (tt == RL_SUPER_FOOD) {
+                h = min(200, h + 40);
+                s.maxage[c] = (int16_t)(int)((double)s.maxage[c] * 1.2);   // :714
+                s.flags[c] |= RL_F_ATE_SUPER;
+            } else if (tt == RL_AGENT && t > c) {
+                s.flags[c] |= 0x80u;   // erased by the later leaver's grid[old] = Empty (:780)
+            }
+            s.health[c] = (int16_t)h;
+        }
+    }
+    __syncthreads();
+    for (int sl = threadIdx.x; sl < n; sl += WT) {
+        const int c = s.cellof[sl];
+        const int t = s.tgt[c];
+        if (t != c && !(s.flags[c] & 0x80u)) { s.ntype[t] = RL_AGENT; s.src[t] = (uint16_t)c; }
+    }
+    // ---- _update_death_status (:789-793) + alive counts for _get_rewards (:295-297), vanished included ----
+    for (int sl = threadIdx.x; sl < n; sl += WT) {
+        const int c = s.cellof[sl];
+        if (s.health[c] <= 0 || s.age[c] == s.maxage[c]) s.flags[c] |= RL_F_DEAD;
+        else { atomicAdd(&s.misc[M_ALIVE], 1); atomicAdd(&s.misc[M_ALIVE_G + s.gene[c]], 1); }
+    }
+    __syncthreads();
+
+    // ---- _add_food (:763-776): counts + empty mask by ballot, placements by warp 0 ----
+    {
+        int nf = 0, np = 0, ns = 0;
+        for (int ch = warp; ch < Cw; ch += WNW) {
+            const int c = ch * 32 + lane;
+            const uint8_t t = c < C ? s.ntype[c] : (uint8_t)255;
+            const unsigned m = __ballot_sync(0xffffffffu, t == RL_EMPTY);
+            nf += __popc(__ballot_sync(0xffffffffu, t == RL_FOOD));
+            np += __popc(__ballot_sync(0xffffffffu, t == RL_POISON));
+            ns += __popc(__ballot_sync(0xffffffffu, t == RL_SUPER_FOOD));
+            if (lane == 0) s.mask[ch] = m;
+        }
+        if (lane == 0) {
+            if (nf) atomicAdd(&s.misc[M_NFOOD], nf);
+            if (np) atomicAdd(&s.misc[M_NPOISON], np);
+            if (ns) atomicAdd(&s.misc[M_NSUPER], ns);
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const bool want_food = (double)s.misc[M_NFOOD] <= (double)C / 10.0;
+        const bool want_poison = (double)s.misc[M_NPOISON] <= (double)C / 20.0;
+        const bool want_super = s.misc[M_NSUPER] == 0;
+        for (int slot = 0; slot < 7; ++slot) {
+            const bool want = slot < 3 ? want_food : slot < 6 ? want_poison : want_super;
+            if (!want) continue;
+            const int cell = warp_place(s.mask, Cw, rl_draw(key, P.t, RL_SITE_FOOD_PLACE, slot));
+            if (cell < 0) continue;
+            const double p = slot < 6 ? 0.2 : 1.0;
+            if (rl_uniform(rl_draw(key, P.t, RL_SITE_FOOD_ACCEPT, slot)) < p) {
+                if (lane == 0) s.ntype[cell] = slot < 3 ? RL_FOOD : slot < 6 ? RL_POISON : RL_SUPER_FOOD;
+                warp_mask_clear(s.mask, cell);
+            }
+        }
+    }
+    __syncthreads();
+    finish_and_observe<true>(P, s, w, s.ntype, P.b.obs_prime);
+}
+
+// =====================================================================================================
+// Environment.update_env -- environment.py:188-215 (static families)
+// =====================================================================================================
+__global__ void __launch_bounds__(WT) k_world_update(const WParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int w = blockIdx.x;
+    const int C = P.cfg.height * P.cfg.width, Cw = (C + 31) / 32, G = P.cfg.n_genes;
+    WS s; ws_carve(s, smem, C, P.cfg.obs_ld);
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
+
+    const int n_list = load_world<false>(P, s, w);   // :210 (frozen for the whole phase)
+
+    for (int ch = warp; ch < Cw; ch += WNW) {
+        const int c = ch * 32 + lane;
+        const bool in = c < C;
+        const uint8_t t = in ? s.type[c] : (uint8_t)255;
+        const bool ag = t == RL_AGENT;
+        const unsigned fl = ag ? s.flags[c] : 0u;
+        const bool elig = ag && !(fl & (RL_F_DEAD | RL_F_REPRODUCED)) && s.age[c] > 5;   // entities.py:244-248
+        const unsigned me = __ballot_sync(0xffffffffu, t == RL_EMPTY);
+        const unsigned ma = __ballot_sync(0xffffffffu, elig);
+        if (lane == 0) { s.mask[ch] = me; s.amask[ch] = ma; }
+        if (ag) { atomicOr(&s.misc[M_PRESENT], 1 << s.gene[c]); s.src[c] = (uint16_t)c; }
+    }
+    __syncthreads();
+    if (warp == 0 && n_list <= P.cfg.max_agents) {
+        uint32_t trial = 0, birth = 0;
+        // _reproduce (:488-519): parents in row-major order; offspring on a uniformly random empty cell (A.9)
+        for (int wd = 0; wd < Cw; ++wd) {
+            uint32_t bitsw = s.amask[wd];
+            while (bitsw) {
+                const int b = __ffs(bitsw) - 1;
+                bitsw &= bitsw - 1;
+                const int pc = wd * 32 + b;
+                if (rl_uniform(rl_draw(key, P.t, RL_SITE_REPRO_TRIAL, trial++)) > 0.95) {
+                    const int cell = warp_place(s.mask, Cw, rl_draw(key, P.t, RL_SITE_BIRTH_PLACE, birth));
+                    if (cell >= 0) {
+                        ++birth;
+                        spawn_agent(s, cell, s.gene[pc], 200, 0);
+                        if (lane == 0) s.src[cell] = (uint16_t)cell;
+                        warp_mask_clear(s.mask, cell);
+                    }
+                    if (P.cfg.limit_reproduction && lane == 0) s.flags[pc] |= RL_F_REPRODUCED;   // :518-519
+                    __syncwarp();
+                }
+            }
+        }
+        // _produce (:521-547)
+        if (rl_uniform(rl_draw(key, P.t, RL_SITE_PRODUCE_TRIAL, 0)) > 0.95) {
+            const uint32_t all = G >= 32 ? 0xffffffffu : ((1u << G) - 1u);
+            uint32_t cand = all & ~(uint32_t)s.misc[M_PRESENT];
+            if (!cand) cand = all;
+            const int pick = (int)rl_below(rl_draw(key, P.t, RL_SITE_PRODUCE_GENE, 0), (uint32_t)__popc(cand));
+            const int gene = (int)__fns(cand, 0, pick + 1);
+            const int cell = warp_place(s.mask, Cw, rl_draw(key, P.t, RL_SITE_BIRTH_PLACE, birth));
+            if (cell >= 0) {
+                spawn_agent(s, cell, gene, 200, 0);
+                if (lane == 0) s.src[cell] = (uint16_t)cell;
+                warp_mask_clear(s.mask, cell);
+            }
+        }
+    }
+    __syncthreads();
+    // _remove_dead_agents (:795-799)
+    for (int c = threadIdx.x; c < C; c += WT)
+        if (s.type[c] == RL_AGENT && (s.flags[c] & RL_F_DEAD)) s.type[c] = RL_FOOD;
+    __syncthreads();
+    finish_and_observe<false>(P, s, w, s.type, P.b.obs_state);
+}
+
+// =====================================================================================================
+// Environment.reset -- environment.py:133-158
+// =====================================================================================================
+__global__ void __launch_bounds__(WT) k_world_reset(const WParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int w = blockIdx.x;
+    const int C = P.cfg.height * P.cfg.width, Cw = (C + 31) / 32, G = P.cfg.n_genes;
+    WS s; ws_carve(s, smem, C, P.cfg.obs_ld);
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
+    for (int c = threadIdx.x; c < C; c += WT) { s.type[c] = RL_EMPTY; s.src[c] = (uint16_t)c; s.aslot[c] = RL_NONE16; }
+    for (int k = threadIdx.x; k < M_WORDS; k += WT) s.misc[k] = 0;
+    __syncthreads();
+    build_empty_mask(s.type, s.mask, C);
+    __syncthreads();
+    if (warp == 0) {
+        for (int g = 0; g < G; ++g) {                                           // :148
+            const int cell = warp_place(s.mask, Cw, rl_draw(key, 0, RL_SITE_RESET_AGENT_PLACE, g));
+            if (cell >= 0) { spawn_agent(s, cell, g, 200, 0); warp_mask_clear(s.mask, cell); }
+        }
+        for (int pass = 0; pass < 2; ++pass) {                                  // _init_food :759-761
+            const double p = pass == 0 ? 0.1 : 0.05;
+            const uint32_t trial = pass == 0 ? RL_SITE_RESET_FOOD_TRIAL : RL_SITE_RESET_POISON_TRIAL;
+            const uint32_t place = pass == 0 ? RL_SITE_RESET_FOOD_PLACE : RL_SITE_RESET_POISON_PLACE;
+            uint32_t k = 0;
+            for (int base = 0; base < C; base += 32) {
+                const int i = base + lane;
+                const bool ok = i < C && rl_uniform(rl_draw(key, 0, trial, (uint32_t)i)) < p;
+                int succ = __popc(__ballot_sync(0xffffffffu, ok));
+                for (; succ > 0; --succ) {
+                    const int cell = warp_place(s.mask, Cw, rl_draw(key, 0, place, k++));
+                    if (cell >= 0) {
+                        if (lane == 0) s.type[cell] = pass == 0 ? RL_FOOD : RL_POISON;
+                        warp_mask_clear(s.mask, cell);
+                    }
+                }
+            }
+        }
+        const int cell = warp_place(s.mask, Cw, rl_draw(key, 0, RL_SITE_RESET_SUPER_PLACE, 0));   // :757
+        if (cell >= 0) { if (lane == 0) s.type[cell] = RL_SUPER_FOOD; warp_mask_clear(s.mask, cell); }
+    }
+    __syncthreads();
+    finish_and_observe<false>(P, s, w, s.type, P.b.obs_state);
+}
+
+// =====================================================================================================
+// saturated-world generator -- harness, mirrored by oracle rlo_topup / RefWorld.top_up
+// =====================================================================================================
+__global__ void __launch_bounds__(WT) k_world_topup(const WParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int w = blockIdx.x;
+    const int C = P.cfg.height * P.cfg.width, Cw = (C + 31) / 32;
+    WS s; ws_carve(s, smem, C, P.cfg.obs_ld);
+    const int warp = threadIdx.x >> 5;
+    const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
+    const int n = load_world<false>(P, s, w);
+    for (int c = threadIdx.x; c < C; c += WT) s.src[c] = (uint16_t)c;
+    build_empty_mask(s.type, s.mask, C);
+    __syncthreads();
+    if (warp == 0) {
+        int cur = n;
+        for (uint32_t k = 0; cur < P.target; ++k, ++cur) {
+            const int cell = warp_place(s.mask, Cw, rl_draw(key, P.t, RL_SITE_TOPUP_PLACE, k));
+            if (cell < 0) break;
+            const int gene = (int)rl_below(rl_draw(key, P.t, RL_SITE_TOPUP_GENE, k), (uint32_t)P.cfg.n_genes);
+            const int health = 10 * (1 + (int)rl_below(rl_draw(key, P.t, RL_SITE_TOPUP_HEALTH, k), 20));
+            const int age = (int)rl_below(rl_draw(key, P.t, RL_SITE_TOPUP_AGE, k), (uint32_t)P.max_age);
+            spawn_agent(s, cell, gene, health, age);
+            warp_mask_clear(s.mask, cell);
+        }
+    }
+    __syncthreads();
+    finish_and_observe<false>(P, s, w, s.type, P.b.obs_state);
+}
+
+__global__ void __launch_bounds__(WT) k_world_observe(const WParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int w = blockIdx.x;
+    const int C = P.cfg.height * P.cfg.width;
+    WS s; ws_carve(s, smem, C, P.cfg.obs_ld);
+    load_world<false>(P, s, w);
+    for (int c = threadIdx.x; c < C; c += WT) s.src[c] = (uint16_t)c;
+    __syncthreads();
+    finish_and_observe<false>(P, s, w, s.type, P.which ? P.b.obs_prime : P.b.obs_state);
+}
+
+bool g_world_init = false;
+size_t g_world_smem_max = 0;
+
+int world_prepare(const rl_world_cfg* cfg, const rl_world_bufs* b, WParams& P, size_t& smem) {
+    RL_ARG_CHECK(cfg && b);
+    RL_ARG_CHECK(cfg->height >= 3 && cfg->width >= 3);          // World/grid.py:23-24
+    RL_ARG_CHECK((int64_t)cfg->height * cfg->width <= 65535);
+    RL_ARG_CHECK(cfg->n_worlds > 0 && cfg->n_genes > 0 && cfg->n_genes <= RL_MAX_GENES);
+    RL_ARG_CHECK(cfg->slot_cap > 0 && cfg->slot_cap <= cfg->height * cfg->width);
+    RL_ARG_CHECK(cfg->obs_ld >= 160 && cfg->obs_ld % 4 == 0 && cfg->obs_ld <= 192);
+    RL_ARG_CHECK(cfg->max_agents > 0);
+    if (!cfg->static_families) return rl_set_err(RL_ERR_UNSUPPORTED, "static_families=False is not implemented yet");
+    RL_ARG_CHECK(b->type && b->rec && b->n_agents && b->reward && b->obs_state && b->obs_prime);
+    P.cfg = *cfg; P.b = *b; P.t = 0; P.target = 0; P.max_age = 50; P.which = 0;
+    P.magicW = (uint32_t)(0x100000000ull / (uint64_t)cfg->width) + 1u;
+    smem = ws_bytes(cfg->height * cfg->width, cfg->obs_ld);
+    if (smem > 227 * 1024) return rl_set_err(RL_ERR_UNSUPPORTED, "world of %d cells needs %zu B shared memory", cfg->height * cfg->width, smem);
+    if (!g_world_init) {
+        float h[41];
+        for (int k = 0; k < 41; ++k) h[k] = (float)((double)(10 * (k - 20)) / 200.0);
+        RL_CUDA_CHECK(cudaMemcpyToSymbol(c_hratio, h, sizeof(h)));
+        g_world_init = true;
+    }
+    if (smem > g_world_smem_max) {
+        const int v = (int)smem;
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_step, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_update, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_topup, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+        g_world_smem_max = smem;
+    }
+    return RL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rl_world_reset(const rl_world_cfg* cfg, const rl_world_bufs* bufs, void* stream) {
+    WParams P; size_t smem;
+    int rc = world_prepare(cfg, bufs, P, smem);
+    if (rc) return rc;
+    k_world_reset<<<cfg->n_worlds, WT, smem, (cudaStream_t)stream>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_world_step(const rl_world_cfg* cfg, const rl_world_bufs* bufs, uint64_t t, void* stream) {
+    WParams P; size_t smem;
+    int rc = world_prepare(cfg, bufs, P, smem);
+    if (rc) return rc;
+    P.t = t;
+    k_world_step<<<cfg->n_worlds, WT, smem, (cudaStream_t)stream>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_world_update(const rl_world_cfg* cfg, const rl_world_bufs* bufs, uint64_t t, void* stream) {
+    WParams P; size_t smem;
+    int rc = world_prepare(cfg, bufs, P, smem);
+    if (rc) return rc;
+    P.t = t;
+    k_world_update<<<cfg->n_worlds, WT, smem, (cudaStream_t)stream>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_world_top_up(const rl_world_cfg* cfg, const rl_world_bufs* bufs, uint64_t t, int32_t target, int32_t max_age,
+                    void* stream) {
+    WParams P; size_t smem;
+    int rc = world_prepare(cfg, bufs, P, smem);
+    if (rc) return rc;
+    RL_ARG_CHECK(max_age > 0 && target >= 0);
+    P.t = t; P.target = target; P.max_age = max_age;
+    k_world_topup<<<cfg->n_worlds, WT, smem, (cudaStream_t)stream>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_world_observe(const rl_world_cfg* cfg, const rl_world_bufs* bufs, int32_t which, void* stream) {
+    WParams P; size_t smem;
+    int rc = world_prepare(cfg, bufs, P, smem);
+    if (rc) return rc;
+    P.which = which;
+    k_world_observe<<<cfg->n_worlds, WT, smem, (cudaStream_t)stream>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
+}  // extern "C"
