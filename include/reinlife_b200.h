@@ -110,6 +110,71 @@ int rl_world_top_up(const rl_world_cfg* cfg, const rl_world_bufs* bufs, uint64_t
  * Writes obs_state (which=0) or obs_prime (which=1) for the current list; does not change the world. */
 int rl_world_observe(const rl_world_cfg* cfg, const rl_world_bufs* bufs, int32_t which, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Row lists: per-brain compaction of the agent lists of all worlds (deterministic: world-major,
+ * then slot order).  A row id is  world*slot_cap + slot  and addresses rec / reward / obs_* rows.
+ * ---------------------------------------------------------------------------------------------- */
+enum rl_row_kind {
+    RL_ROWS_ALL = 0,    /* every listed agent of the gene: the get_action loop, Helpers/trainer.py:88-89        */
+    RL_ROWS_STORE = 1,  /* age > 1: transitions that reach brain.learn, World/entities.py:194-208             */
+    RL_ROWS_EVENT = 2,  /* age > 1 and (age % train_freq == 0 or dead): train() triggers, Models/PERD3QN.py:120-122 */
+    RL_N_ROW_KINDS = 3
+};
+
+typedef struct rl_rows_bufs {
+    int32_t* count;     /* [n_genes*3, n_worlds]  per-world counts                   */
+    int32_t* offset;    /* [n_genes*3, n_worlds]  exclusive prefix over worlds       */
+    int32_t* total;     /* [n_genes*3]                                               */
+    int32_t* rows;      /* [n_genes*3, row_cap]   row ids                            */
+    int32_t  row_cap;
+    int32_t  _pad;
+} rl_rows_bufs;
+
+/* train_freq[g] > 0; event_on[g] = 1 when brain g trains this step (n_epi > exploration), else no EVENT rows.
+ * kinds_mask: bit k set = build kind k.  Three tiny kernels (count, scan, scatter); no host sync. */
+int rl_rows_build(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_rows_bufs* rows,
+                  const int32_t* train_freq_host, const int32_t* event_on_host, int32_t kinds_mask, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Brains.  Parameters live in one flat float32 buffer per network in KERNEL LAYOUT
+ * (input-major, i.e. transposed nn.Linear weights; first layer zero-padded from 153 to 160 inputs):
+ *
+ *   [ W1t 160 x N1 | b1 N1 | W2t N1 x N2 | b2 N2 | Wh N2 x NH | bh NH | pad to 4 | W2 N2 x N1 (output-major copy) ]
+ *
+ *   RL_MODEL_DUELING (D3QN, PERD3QN; Models/PERD3QN.py:185-202): N1=128, N2=256 = [adv_fc1 | value_fc1], NH=9 =
+ *       [adv_fc2 (rows 0-127 only) | value_fc2 (rows 128-255 only)]; the other NH entries are structural zeros.
+ *   RL_MODEL_DQN (Models/DQN.py:119-130): N1=128, N2=64, NH=8.
+ *   RL_MODEL_PPO (Models/PPO.py:96-112): N1=256, N2=256, NH=9 = [fc_pi | fc_v].
+ * The output-major copy of W2 is maintained by rl_brain_adam / rl_brain_sync_w2 for the backward pass.
+ * ---------------------------------------------------------------------------------------------- */
+enum rl_model_kind { RL_MODEL_DUELING = 0, RL_MODEL_DQN = 1, RL_MODEL_PPO = 2 };
+
+typedef struct rl_model_dims { int32_t n1, n2, nh, off_b1, off_w2t, off_b2, off_wh, off_bh, off_w2, n_train, n_total; } rl_model_dims;
+int rl_model_get_dims(int32_t kind, rl_model_dims* out);
+
+/* act-rule per brain (who explores how) */
+enum rl_act_rule {
+    RL_ACT_DUELING = 0, /* u > eps ? argmax : choice(range(8))      Models/PERD3QN.py:204-210, D3QN.py:167-173 */
+    RL_ACT_DQN = 1,     /* coin < eps ? randint(0,7) : argmax        Models/DQN.py:132-139                      */
+    RL_ACT_PPO = 2      /* inverse-CDF sample of softmax(pi)         Models/PPO.py:164-169                      */
+};
+
+typedef struct rl_brain_act {
+    int32_t kind;           /* rl_model_kind */
+    int32_t rule;           /* rl_act_rule   */
+    const float* params;    /* online network, kernel layout */
+    double  epsilon;
+} rl_brain_act;
+
+/* brain.get_action for every listed agent of every world (Helpers/trainer.py:88-89, Helpers/tester.py:58-68):
+ * forward on obs_state rows, exploration draws keyed (t_act, slot), result written to rec[].action.
+ * q_out (optional) [n_genes, row_cap, 8]: network outputs per list position (Q values, or pi for PPO);
+ * prob_out (optional) [n_worlds*slot_cap]: pi(a) of the sampled action for PPO brains (agent.prob). */
+int rl_brain_act_all(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_rows_bufs* rows,
+                     const rl_brain_act* brains_host, int32_t n_brains, uint64_t t_act,
+                     float* q_out, float* prob_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,166 @@
+"""TEST INFRASTRUCTURE -- CPU restatement of the brains' arithmetic (never imported by reinlife_b200/).
+
+The reference's network math lives in an un-vendored third-party dependency: PyTorch
+(`torch>=1.3.1`, requirements.txt:1; this container: torch 2.11.0 CPU).  This file restates, with
+explicit fp32 tensor algebra and NO autograd / nn.Module / optimizer objects:
+
+* the three forwards            Models/PERD3QN.py:198-202, Models/DQN.py:126-130, Models/PPO.py:101-112
+* one PERD3QN / D3QN train()    Models/PERD3QN.py:94-115, Models/D3QN.py:97-116 (MSE on r + g(1-d)max_a Q_target,
+                                priorities |max_a Q_target - Q(s,a)|, whole-tensor advantage mean)
+* torch.optim.Adam defaults     (betas .9/.999, eps 1e-8, bias-corrected)
+* the action rules              Models/PERD3QN.py:204-210, Models/DQN.py:132-139
+* the event-batched update used for N worlds (mean of per-event gradients, one Adam step)
+* the integer-CDF proportional sampler that stands in for np.random.choice(len, 64, p) (PERD3QN.py:157-165)
+
+Pinned against tests/golden/brain_golden.npz, which oracle/make_brain_golden.py mints by running the
+reference's own modules (DuelingDDQN / Qnet / PPO / PERD3QNAgent.train with the pretrained weights).
+State dicts use the reference's key names.
+"""
+import numpy as np
+import torch
+
+F32 = torch.float32
+
+
+def _t(x):
+    return torch.as_tensor(np.asarray(x), dtype=F32)
+
+
+def lin(x, w, b):
+    return x @ _t(w).T + _t(b)
+
+
+# ------------------------------------------------------------------ forwards
+def dueling_parts(sd, x):
+    x = _t(x)
+    feat = lin(x, sd["fc.weight"], sd["fc.bias"])
+    h1 = torch.relu(feat)
+    a1 = torch.relu(lin(h1, sd["adv_fc1.weight"], sd["adv_fc1.bias"]))
+    v1 = torch.relu(lin(h1, sd["value_fc1.weight"], sd["value_fc1.bias"]))
+    adv = lin(a1, sd["adv_fc2.weight"], sd["adv_fc2.bias"])
+    val = lin(v1, sd["value_fc2.weight"], sd["value_fc2.bias"])
+    return x, h1, a1, v1, adv, val
+
+
+def dueling_forward(sd, x, per_row_mean):
+    """per_row_mean=True: B=1 act semantics (each row its own batch); False: train semantics (PERD3QN.py:202)."""
+    *_, adv, val = dueling_parts(sd, x)
+    mean = adv.mean(1, keepdim=True) if per_row_mean else adv.mean()
+    return (adv + val - mean).numpy()
+
+
+def dqn_forward(sd, x):
+    x = _t(x)
+    h = torch.relu(lin(x, sd["fc1.weight"], sd["fc1.bias"]))
+    h = torch.relu(lin(h, sd["fc2.weight"], sd["fc2.bias"]))
+    return lin(h, sd["fc3.weight"], sd["fc3.bias"]).numpy()
+
+
+def ppo_forward(sd, x):
+    x = _t(x)
+    h = torch.relu(lin(x, sd["fc1.weight"], sd["fc1.bias"]))
+    h = torch.relu(lin(h, sd["fc2.weight"], sd["fc2.bias"]))
+    logits = lin(h, sd["fc_pi.weight"], sd["fc_pi.bias"])
+    z = logits - logits.max(1, keepdim=True)[0]
+    e = torch.exp(z)
+    return (e / e.sum(1, keepdim=True)).numpy(), lin(h, sd["fc_v.weight"], sd["fc_v.bias"]).numpy()
+
+
+# ------------------------------------------------------------------ one dueling train() event, explicit backward
+def dueling_event_grads(sd_eval, sd_target, obs, action, reward, next_obs, done, gamma):
+    """Returns (grads dict in state_dict orientation, loss, priorities) for ONE 64-row event."""
+    B = len(action)
+    x, h1, a1, v1, adv, val = dueling_parts(sd_eval, obs)
+    q = adv + val - adv.mean()
+    qn = torch.as_tensor(dueling_forward(sd_target, next_obs, per_row_mean=False))
+    next_q = qn.max(1)[0]
+    a = torch.as_tensor(np.asarray(action), dtype=torch.long)
+    q_a = q.gather(1, a[:, None])[:, 0]
+    y = _t(reward) + gamma * (1 - _t(done)) * next_q
+    loss = ((q_a - y) ** 2).mean()
+    prio = (next_q - q_a).abs()
+    g = 2 * (q_a - y) / B                                   # dL/dQ[b, a_b]
+    d_adv = torch.zeros(B, 8)
+    d_adv[torch.arange(B), a] = g
+    d_adv -= g.sum() / (8 * B)                              # whole-tensor mean couples every row (Appendix C)
+    d_val = g[:, None]
+    grads = {}
+    grads["adv_fc2.weight"], grads["adv_fc2.bias"] = d_adv.T @ a1, d_adv.sum(0)
+    grads["value_fc2.weight"], grads["value_fc2.bias"] = d_val.T @ v1, d_val.sum(0)
+    d_a1 = (d_adv @ _t(sd_eval["adv_fc2.weight"])) * (a1 > 0)
+    d_v1 = (d_val @ _t(sd_eval["value_fc2.weight"])) * (v1 > 0)
+    grads["adv_fc1.weight"], grads["adv_fc1.bias"] = d_a1.T @ h1, d_a1.sum(0)
+    grads["value_fc1.weight"], grads["value_fc1.bias"] = d_v1.T @ h1, d_v1.sum(0)
+    d_h1 = (d_a1 @ _t(sd_eval["adv_fc1.weight"]) + d_v1 @ _t(sd_eval["value_fc1.weight"])) * (h1 > 0)
+    grads["fc.weight"], grads["fc.bias"] = d_h1.T @ x, d_h1.sum(0)
+    return {k: v.numpy() for k, v in grads.items()}, float(loss), prio.numpy()
+
+
+def adam_step(params, grads, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    """torch.optim.Adam (defaults, no amsgrad / weight decay), in place on dicts of float32 numpy arrays. `step` is 1-based."""
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    step_size = lr / bc1
+    for k in params:
+        g = _t(grads[k])
+        mk = _t(m[k]); vk = _t(v[k]); p = _t(params[k])
+        mk = mk + (g - mk) * (1 - beta1)                    # exp_avg.lerp_(grad, 1-beta1)
+        vk = vk * beta2 + (1 - beta2) * g * g               # exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1-beta2)
+        denom = vk.sqrt() / np.sqrt(bc2) + eps
+        p = p - step_size * (mk / denom)
+        m[k], v[k], params[k] = mk.numpy(), vk.numpy(), p.numpy()
+
+
+def dueling_batched_update(sd_eval, sd_target, events, gamma):
+    """N-world semantics: mean over events of the per-event gradient (DESIGN.md 'learn step')."""
+    acc, losses, prios = None, [], []
+    for ev in events:
+        g, loss, prio = dueling_event_grads(sd_eval, sd_target, *ev, gamma)
+        losses.append(loss); prios.append(prio)
+        acc = g if acc is None else {k: acc[k] + g[k] for k in g}
+    return {k: acc[k] / len(events) for k in acc}, losses, prios
+
+
+# ------------------------------------------------------------------ action rules (given network outputs)
+def first_argmax(q):
+    return int(np.argmax(np.asarray(q)))   # first maximum, like torch.max / Tensor.argmax on CPU
+
+
+def dueling_rule(q, eps, u_explore, r_below8):
+    return first_argmax(q) if u_explore > eps else int(r_below8)      # PERD3QN.py:204-210
+
+
+def dqn_rule(q, eps, coin, r_below8):
+    return int(r_below8) if coin < eps else first_argmax(q)           # DQN.py:135-139
+
+
+# ------------------------------------------------------------------ proportional sampler (integer CDF)
+def per_weight(prio):
+    """float32(float64(p) ** 0.6): the alpha-power of PERD3QN.py:162, rounded once."""
+    return np.power(np.asarray(prio, np.float64), 0.6).astype(np.float32)
+
+
+def per_sample(weights_f32, u53):
+    """weights: float32 [len]; u53: python ints < 2**53 (top 53 bits of each draw).  Exact integer arithmetic:
+    fixed-point weights w*2^24, inclusive prefix sums, index = first i with cum[i] > floor(u53 * total / 2^53)."""
+    fix = [int(np.float64(w) * 16777216.0) for w in weights_f32]
+    cum, run = [], 0
+    for f in fix:
+        run += f
+        cum.append(run)
+    total = run
+    out = []
+    for u in u53:
+        if total == 0:
+            out.append(0)
+            continue
+        target = (int(u) * total) >> 53
+        lo, hi = 0, len(cum) - 1
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if cum[mid] > target:
+                hi = mid
+            else:
+                lo = mid + 1
+        out.append(lo)
+    return out

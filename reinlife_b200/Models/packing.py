@@ -1,0 +1,139 @@
+"""state_dict <-> kernel-layout parameter buffers (layout contract: include/reinlife_b200.h, "Brains").
+
+Key names and shapes are the reference's (Models/PERD3QN.py:185-196, Models/D3QN.py:148-159,
+Models/DQN.py:119-124, Models/PPO.py:96-99) so that `pretrained/**/brain_gene_*.pt` load unchanged
+and checkpoints written here load in the reference.
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+
+from .. import _lib
+
+DUELING, DQN, PPO = 0, 1, 2
+K1 = 160
+
+
+class ModelDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n1", "n2", "nh", "off_b1", "off_w2t", "off_b2", "off_wh", "off_bh",
+                                         "off_w2", "n_train", "n_total")]
+
+
+_dims_cache = {}
+
+
+def dims(kind):
+    if kind not in _dims_cache:
+        d = ModelDims()
+        _lib.check(_lib.load().rl_model_get_dims(C.c_int32(kind), C.byref(d)))
+        _dims_cache[kind] = d
+    return _dims_cache[kind]
+
+
+def _np(t):
+    return t.detach().cpu().numpy().astype(np.float32) if hasattr(t, "detach") else np.asarray(t, np.float32)
+
+
+def _layers(kind, sd):
+    """-> (W1 [N1,153], b1, W2 [N2,N1], b2, Wh_dense [NH,N2], bh) in nn.Linear (output-major) orientation."""
+    if kind == DUELING:
+        w1, b1 = _np(sd["fc.weight"]), _np(sd["fc.bias"])
+        w2 = np.concatenate([_np(sd["adv_fc1.weight"]), _np(sd["value_fc1.weight"])], 0)
+        b2 = np.concatenate([_np(sd["adv_fc1.bias"]), _np(sd["value_fc1.bias"])], 0)
+        wh = np.zeros((9, 256), np.float32)
+        wh[:8, :128] = _np(sd["adv_fc2.weight"])
+        wh[8, 128:] = _np(sd["value_fc2.weight"])[0]
+        bh = np.concatenate([_np(sd["adv_fc2.bias"]), _np(sd["value_fc2.bias"])], 0)
+    elif kind == DQN:
+        w1, b1 = _np(sd["fc1.weight"]), _np(sd["fc1.bias"])
+        w2, b2 = _np(sd["fc2.weight"]), _np(sd["fc2.bias"])
+        wh, bh = _np(sd["fc3.weight"]), _np(sd["fc3.bias"])
+    elif kind == PPO:
+        w1, b1 = _np(sd["fc1.weight"]), _np(sd["fc1.bias"])
+        w2, b2 = _np(sd["fc2.weight"]), _np(sd["fc2.bias"])
+        wh = np.concatenate([_np(sd["fc_pi.weight"]), _np(sd["fc_v.weight"])], 0)
+        bh = np.concatenate([_np(sd["fc_pi.bias"]), _np(sd["fc_v.bias"])], 0)
+    else:
+        raise ValueError(kind)
+    return w1, b1, w2, b2, wh, bh
+
+
+def pack(kind, sd):
+    d = dims(kind)
+    w1, b1, w2, b2, wh, bh = _layers(kind, sd)
+    flat = np.zeros(d.n_total, np.float32)
+    w1t = np.zeros((K1, d.n1), np.float32)
+    w1t[:153] = w1.T
+    flat[0:d.off_b1] = w1t.reshape(-1)
+    flat[d.off_b1:d.off_b1 + d.n1] = b1
+    flat[d.off_w2t:d.off_b2] = w2.T.reshape(-1)
+    flat[d.off_b2:d.off_b2 + d.n2] = b2
+    flat[d.off_wh:d.off_bh] = wh.T.reshape(-1)
+    flat[d.off_bh:d.off_bh + d.nh] = bh
+    flat[d.off_w2:d.off_w2 + d.n1 * d.n2] = w2.reshape(-1)
+    return flat
+
+
+def unpack(kind, flat):
+    import torch
+    d = dims(kind)
+    flat = np.asarray(flat, np.float32)
+    w1 = flat[0:d.off_b1].reshape(K1, d.n1)[:153].T.copy()
+    b1 = flat[d.off_b1:d.off_b1 + d.n1].copy()
+    w2 = flat[d.off_w2t:d.off_b2].reshape(d.n1, d.n2).T.copy()
+    b2 = flat[d.off_b2:d.off_b2 + d.n2].copy()
+    wh = flat[d.off_wh:d.off_bh].reshape(d.n2, d.nh).T.copy()
+    bh = flat[d.off_bh:d.off_bh + d.nh].copy()
+    t = torch.from_numpy
+    if kind == DUELING:
+        return OrderedDict([("fc.weight", t(w1)), ("fc.bias", t(b1)),
+                            ("adv_fc1.weight", t(w2[:128].copy())), ("adv_fc1.bias", t(b2[:128].copy())),
+                            ("adv_fc2.weight", t(wh[:8, :128].copy())), ("adv_fc2.bias", t(bh[:8].copy())),
+                            ("value_fc1.weight", t(w2[128:].copy())), ("value_fc1.bias", t(b2[128:].copy())),
+                            ("value_fc2.weight", t(wh[8:9, 128:].copy())), ("value_fc2.bias", t(bh[8:9].copy()))])
+    if kind == DQN:
+        return OrderedDict([("fc1.weight", t(w1)), ("fc1.bias", t(b1)), ("fc2.weight", t(w2)), ("fc2.bias", t(b2)),
+                            ("fc3.weight", t(wh)), ("fc3.bias", t(bh))])
+    return OrderedDict([("fc1.weight", t(w1)), ("fc1.bias", t(b1)), ("fc2.weight", t(w2)), ("fc2.bias", t(b2)),
+                        ("fc_pi.weight", t(wh[:8].copy())), ("fc_pi.bias", t(bh[:8].copy())),
+                        ("fc_v.weight", t(wh[8:9].copy())), ("fc_v.bias", t(bh[8:9].copy()))])
+
+
+def grad_mask(kind):
+    """1 for trainable entries of the first n_train floats, 0 for padding / structural zeros."""
+    d = dims(kind)
+    m = np.zeros(d.n_train, np.float32)
+    w1t = np.zeros((K1, d.n1), np.float32)
+    w1t[:153] = 1
+    m[0:d.off_b1] = w1t.reshape(-1)
+    m[d.off_b1:d.off_bh + d.nh] = 1
+    if kind == DUELING:
+        wh = np.zeros((d.n2, d.nh), np.float32)
+        wh[:128, :8] = 1
+        wh[128:, 8] = 1
+        m[d.off_wh:d.off_bh] = wh.reshape(-1)
+    return m
+
+
+def default_init(kind, generator=None):
+    """nn.Linear default init (kaiming_uniform(a=sqrt(5)) = U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias),
+    drawn layer by layer in the reference's construction order from torch's global (or the given) generator."""
+    import torch
+
+    def lin(out_f, in_f):
+        bound = 1.0 / np.sqrt(in_f)
+        w = (torch.rand(out_f, in_f, generator=generator) * 2 - 1) * bound
+        b = (torch.rand(out_f, generator=generator) * 2 - 1) * bound
+        return w, b
+    sd = OrderedDict()
+    if kind == DUELING:
+        for name, o, i in (("fc", 128, 153), ("adv_fc1", 128, 128), ("adv_fc2", 8, 128), ("value_fc1", 128, 128), ("value_fc2", 1, 128)):
+            sd[name + ".weight"], sd[name + ".bias"] = lin(o, i)
+    elif kind == DQN:
+        for name, o, i in (("fc1", 128, 153), ("fc2", 64, 128), ("fc3", 8, 64)):
+            sd[name + ".weight"], sd[name + ".bias"] = lin(o, i)
+    else:
+        for name, o, i in (("fc1", 256, 153), ("fc2", 256, 256), ("fc_pi", 8, 256), ("fc_v", 1, 256)):
+            sd[name + ".weight"], sd[name + ".bias"] = lin(o, i)
+    return sd

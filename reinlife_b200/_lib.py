@@ -65,3 +65,17 @@ def exported_symbols():
     hdr = os.path.join(_HERE, "..", "include", "reinlife_b200.h")
     text = open(hdr).read()
     return sorted(set(re.findall(r"^\s*(?:int|const char\*)\s+(rl_[a-z0-9_]+)\s*\(", text, re.M)))
+
+
+ROWS_ALL, ROWS_STORE, ROWS_EVENT, N_ROW_KINDS = 0, 1, 2, 3
+MODEL_DUELING, MODEL_DQN, MODEL_PPO = 0, 1, 2
+ACT_DUELING, ACT_DQN, ACT_PPO = 0, 1, 2
+
+
+class RowsBufs(C.Structure):
+    _fields_ = [("count", C.c_void_p), ("offset", C.c_void_p), ("total", C.c_void_p), ("rows", C.c_void_p),
+                ("row_cap", C.c_int32), ("_pad", C.c_int32)]
+
+
+class BrainAct(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("rule", C.c_int32), ("params", C.c_void_p), ("epsilon", C.c_double)]
