@@ -175,6 +175,72 @@ int rl_brain_act_all(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const r
                      const rl_brain_act* brains_host, int32_t n_brains, uint64_t t_act,
                      float* q_out, float* prob_out, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Replay + learn.  One ring per (world, brain): N worlds = N independent reference runs that share
+ * only the brains' weights (so at N=1 the buffer is exactly Models/PERD3QN.py:133-182).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rl_replay_bufs {             /* per brain; ring index = local world */
+    float*   obs;        /* [n_worlds, capacity, obs_ld]  state        */
+    float*   next_obs;   /* [n_worlds, capacity, obs_ld]  state_prime  */
+    int8_t*  action;     /* [n_worlds, capacity] */
+    float*   reward;     /* [n_worlds, capacity] float32(reward) (PPO: reward/100, PPO.py:73) */
+    uint8_t* done;       /* [n_worlds, capacity] */
+    float*   prio;       /* [n_worlds, capacity] raw priorities, zero-initialised (PERD3QN.py:141) */
+    float*   pw;         /* [n_worlds, capacity] float32(float64(prio)^0.6) */
+    int32_t* len;        /* [n_worlds] */
+    int32_t* pos;        /* [n_worlds] */
+    int32_t  capacity;
+    int32_t  prioritized;/* 1: proportional PER (PERD3QN); 0: uniform (D3QN, DQN) */
+} rl_replay_bufs;
+
+/* brain.memorize for every STORE row of `gene` (PERD3QN.py:91-92,143-155): state = obs_state[prev_slot],
+ * state_prime = obs_prime[slot]; new items get max(priorities) (1.0 while empty).  Needs rows kinds STORE. */
+int rl_replay_store(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_rows_bufs* rows, int32_t gene,
+                    const rl_replay_bufs* replay, void* stream);
+
+/* buffer.sample(batch) for every EVENT row of `gene` (PERD3QN.py:157-175): proportional sampling with
+ * replacement from the world's ring, exact-integer CDF, draws keyed (t, RL_SITE_REPLAY_SAMPLE,
+ * event_rank*batch+i).  sample_idx: [row_cap, batch] int32, one row per event in EVENT-list order. */
+int rl_replay_sample(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                     int32_t batch, uint64_t t, int32_t* sample_idx, void* stream);
+
+/* buffer.update_priorities (PERD3QN.py:177-179) for all events of `gene`, in event order, later writes win. */
+int rl_replay_update_prio(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                          int32_t batch, const int32_t* sample_idx, const float* new_prio, void* stream);
+
+typedef struct rl_learn_bufs {              /* per brain */
+    float*   params;        /* eval / online network, kernel layout [n_total] */
+    float*   target;        /* target network [n_total] */
+    float*   grad_scratch;  /* [n_cta, n_train] per-CTA partial sums (n_cta = rl_learn_grid()) */
+    float*   grad;          /* [n_train + 4]: summed gradient; grad[n_train] = number of events summed */
+    float*   adam_m;        /* [n_train] */
+    float*   adam_v;        /* [n_train] */
+    float*   mask;          /* [n_train] 1 = trainable, 0 = padding / structural zero */
+    int32_t* adam_step;     /* [1] device step counter (advances only when events > 0) */
+    float*   new_prio;      /* [row_cap, batch] |max_a Q_target(s') - Q(s,a)| per sampled row */
+    float*   loss;          /* [row_cap] per-event MSE loss */
+    int32_t  kind;          /* rl_model_kind */
+    int32_t  batch;         /* 64 */
+    float    gamma;
+    float    lr;
+} rl_learn_bufs;
+
+int rl_learn_grid(void);    /* CTAs used by rl_brain_learn = rows of grad_scratch */
+
+/* One train() event per EVENT row of `gene` (PERD3QN.py:94-115 / D3QN.py:97-116): two forwards, MSE TD loss,
+ * explicit backward.  Per-event gradients are SUMMED into `grad` (grad[n_train] = #events); call
+ * rl_brain_adam afterwards (after an optional all-reduce of `grad` across ranks). */
+int rl_brain_learn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                   const int32_t* sample_idx, const rl_learn_bufs* learn, void* stream);
+
+/* torch.optim.Adam defaults on grad/grad[n_train] (mean over events); no-op when no event happened.
+ * Also refreshes the output-major copy of W2. */
+int rl_brain_adam(const rl_learn_bufs* learn, void* stream);
+
+/* target_net.load_state_dict(eval_net.state_dict())  (PERD3QN.py:124-125) */
+int rl_brain_sync_target(const rl_learn_bufs* learn, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

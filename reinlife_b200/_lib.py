@@ -79,3 +79,16 @@ class RowsBufs(C.Structure):
 
 class BrainAct(C.Structure):
     _fields_ = [("kind", C.c_int32), ("rule", C.c_int32), ("params", C.c_void_p), ("epsilon", C.c_double)]
+
+
+class ReplayBufs(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("next_obs", C.c_void_p), ("action", C.c_void_p), ("reward", C.c_void_p),
+                ("done", C.c_void_p), ("prio", C.c_void_p), ("pw", C.c_void_p), ("len", C.c_void_p), ("pos", C.c_void_p),
+                ("capacity", C.c_int32), ("prioritized", C.c_int32)]
+
+
+class LearnBufs(C.Structure):
+    _fields_ = [("params", C.c_void_p), ("target", C.c_void_p), ("grad_scratch", C.c_void_p), ("grad", C.c_void_p),
+                ("adam_m", C.c_void_p), ("adam_v", C.c_void_p), ("mask", C.c_void_p), ("adam_step", C.c_void_p),
+                ("new_prio", C.c_void_p), ("loss", C.c_void_p), ("kind", C.c_int32), ("batch", C.c_int32),
+                ("gamma", C.c_float), ("lr", C.c_float)]

@@ -1,0 +1,104 @@
+"""Device state of one brain (network, optimizer, per-world replay rings) + the learn step driven through the C ABI.
+
+This is the batched stand-in for the object a reference brain holds: eval/target nn.Modules, torch.optim.Adam and
+a replay buffer (Models/PERD3QN.py:50-55, Models/D3QN.py:57-62, Models/DQN.py:48-52, Models/PPO.py:96-99).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .Models import packing
+
+
+class DeviceBrain:
+    def __init__(self, kind, state_dict, device, lr=1e-3, gamma=0.99, batch=64, has_target=True):
+        self.kind, self.device = kind, torch.device(device)
+        self.lib = _lib.load()
+        self.dims = packing.dims(kind)
+        self.lr, self.gamma, self.batch = float(lr), float(gamma), int(batch)
+        flat = torch.from_numpy(packing.pack(kind, state_dict))
+        self.params = flat.to(self.device)
+        self.target = self.params.clone() if has_target else None
+        nt = self.dims.n_train
+        self.adam_m = torch.zeros(nt, device=self.device)
+        self.adam_v = torch.zeros(nt, device=self.device)
+        self.mask = torch.from_numpy(packing.grad_mask(kind)).to(self.device)
+        self.grad = torch.zeros(nt + 4, device=self.device)
+        self.adam_step = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.grad_scratch = None
+        self.new_prio = self.loss = self.sample_idx = None
+        self.learn_bufs = None
+
+    # -- state_dict round trip (reference key names) -----------------------------------------------
+    def state_dict(self, target=False):
+        return packing.unpack(self.kind, (self.target if target else self.params).cpu().numpy())
+
+    def load_state_dict(self, sd, target=False):
+        flat = torch.from_numpy(packing.pack(self.kind, sd)).to(self.device)
+        (self.target if target else self.params).copy_(flat)
+
+    # -- learn buffers -----------------------------------------------------------------------------
+    def alloc_learn(self, row_cap):
+        with torch.cuda.device(self.device):
+            n_cta = self.lib.rl_learn_grid()
+        nt = self.dims.n_train
+        self.grad_scratch = torch.zeros((n_cta, nt), device=self.device)
+        self.new_prio = torch.zeros((row_cap, self.batch), device=self.device)
+        self.loss = torch.zeros(row_cap, device=self.device)
+        self.sample_idx = torch.zeros((row_cap, self.batch), dtype=torch.int32, device=self.device)
+        self.learn_bufs = _lib.LearnBufs(self.params.data_ptr(), self.target.data_ptr() if self.target is not None else None,
+                                         self.grad_scratch.data_ptr(), self.grad.data_ptr(), self.adam_m.data_ptr(),
+                                         self.adam_v.data_ptr(), self.mask.data_ptr(), self.adam_step.data_ptr(),
+                                         self.new_prio.data_ptr(), self.loss.data_ptr(), self.kind, self.batch,
+                                         self.gamma, self.lr)
+
+    def act_desc(self, rule, epsilon):
+        return _lib.BrainAct(self.kind, rule, self.params.data_ptr(), float(epsilon))
+
+
+class ReplayRings:
+    """One ring per local world for one brain (rl_replay_bufs)."""
+
+    def __init__(self, n_worlds, capacity, device, prioritized=True, ld=_lib.OBS_LD):
+        dev = torch.device(device)
+        self.n_worlds, self.capacity, self.prioritized = n_worlds, int(capacity), bool(prioritized)
+        self.obs = torch.empty((n_worlds, capacity, ld), device=dev)
+        self.next_obs = torch.empty((n_worlds, capacity, ld), device=dev)
+        self.action = torch.zeros((n_worlds, capacity), dtype=torch.int8, device=dev)
+        self.reward = torch.zeros((n_worlds, capacity), device=dev)
+        self.done = torch.zeros((n_worlds, capacity), dtype=torch.uint8, device=dev)
+        self.prio = torch.zeros((n_worlds, capacity), device=dev)
+        self.pw = torch.zeros((n_worlds, capacity), device=dev)
+        self.len = torch.zeros(n_worlds, dtype=torch.int32, device=dev)
+        self.pos = torch.zeros(n_worlds, dtype=torch.int32, device=dev)
+        self.bufs = _lib.ReplayBufs(self.obs.data_ptr(), self.next_obs.data_ptr(), self.action.data_ptr(),
+                                    self.reward.data_ptr(), self.done.data_ptr(), self.prio.data_ptr(), self.pw.data_ptr(),
+                                    self.len.data_ptr(), self.pos.data_ptr(), self.capacity, int(self.prioritized))
+
+    @staticmethod
+    def bytes_needed(n_worlds, capacity, ld=_lib.OBS_LD):
+        return n_worlds * capacity * (2 * ld * 4 + 1 + 4 + 1 + 4 + 4)
+
+
+def learn_step(world, rows, gene, brain, replay, t, allreduce=None):
+    """store -> sample -> train events -> (all-reduce) -> Adam -> priorities, for one brain.  No host sync."""
+    lib, st = world.lib, world._stream()
+    with torch.cuda.device(world.device):
+        _lib.check(lib.rl_replay_store(C.byref(world.cfg), C.byref(world.bufs), C.byref(rows.bufs), C.c_int32(gene),
+                                       C.byref(replay.bufs), st))
+        _lib.check(lib.rl_replay_sample(C.byref(world.cfg), C.byref(rows.bufs), C.c_int32(gene), C.byref(replay.bufs),
+                                        C.c_int32(brain.batch), C.c_uint64(t), C.c_void_p(brain.sample_idx.data_ptr()), st))
+        _lib.check(lib.rl_brain_learn(C.byref(world.cfg), C.byref(rows.bufs), C.c_int32(gene), C.byref(replay.bufs),
+                                      C.c_void_p(brain.sample_idx.data_ptr()), C.byref(brain.learn_bufs), st))
+        if allreduce is not None:
+            allreduce(brain.grad)
+        _lib.check(lib.rl_brain_adam(C.byref(brain.learn_bufs), st))
+        _lib.check(lib.rl_replay_update_prio(C.byref(world.cfg), C.byref(rows.bufs), C.c_int32(gene), C.byref(replay.bufs),
+                                             C.c_int32(brain.batch), C.c_void_p(brain.sample_idx.data_ptr()),
+                                             C.c_void_p(brain.new_prio.data_ptr()), st))
+
+
+def sync_target(brain, world):
+    with torch.cuda.device(world.device):
+        _lib.check(world.lib.rl_brain_sync_target(C.byref(brain.learn_bufs), world._stream()))

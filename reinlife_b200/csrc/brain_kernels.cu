@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(NT, 1) k_brain_act(const ActParams P) {
         __syncthreads();
         gather_rows(bufA, LDA, P.obs, P.cfg.obs_ld, ids, nrows);
         __syncthreads();
-        gemm_stage<RL_K1, M::N1, true, true>(bufA, LDA, P.params + L::OFF_W1T, P.params + L::OFF_B1, bufB, LDB, pp);
-        gemm_stage<M::N1, M::N2, true, true>(bufB, LDB, P.params + L::OFF_W2T, P.params + L::OFF_B2, bufA, LDA, pp);
+        gemm_stage<RL_K1, M::N1, 1, true>(bufA, LDA, P.params + L::OFF_W1T, P.params + L::OFF_B1, bufB, LDB, pp);
+        gemm_stage<M::N1, M::N2, 1, true>(bufB, LDB, P.params + L::OFF_W2T, P.params + L::OFF_B2, bufA, LDA, pp);
         head_stage<M::N2, M::NH>(bufA, LDA, Wh_s, bufB, 16);
 
         if (threadIdx.x < nrows) {

@@ -59,13 +59,16 @@ struct Pipe {
 //   A   : shared, row-major, leading dim lda (floats, multiple of 4)
 //   Wg  : global, k-major [K][N] contiguous, 16-byte aligned
 //   OUT : shared, row-major, leading dim ldo; must not alias A
-template <int K, int N, bool RELU, bool HAS_BIAS>
+//   MODE: 0 plain, 1 ReLU, 2 backward mask -- OUT[r][n] = OUT_old[r][n] > 0 ? value : 0 (ReLU derivative, in place)
+// Each thread owns TM rows x TN columns, the columns interleaved in groups of 4 (col = g*(N/NG) + tx*4 + jj) so
+// that every 128-bit shared load of a weight row is a contiguous, conflict-free 16 B x 32 lanes access.
+template <int K, int N, int MODE, bool HAS_BIAS>
 __device__ __forceinline__ void gemm_stage(const float* __restrict__ A, int lda, const float* __restrict__ Wg,
-                                           const float* __restrict__ bias, float* __restrict__ OUT, int ldo, Pipe& pp) {
-    constexpr int TM = Cfg<N>::TM, TN = Cfg<N>::TN;
+                                           const float* __restrict__ bias, float* OUT, int ldo, Pipe& pp) {
+    constexpr int TM = Cfg<N>::TM, TN = Cfg<N>::TN, NG = TN / 4, GS = N / NG;
     constexpr int KC = CHUNK_BYTES / (4 * N);
     static_assert(K % KC == 0 && KC % 4 == 0, "K must be a multiple of the chunk depth");
-    static_assert((R / TM) * (N / TN) == NT, "thread tiling");
+    static_assert((R / TM) * (N / TN) == NT && TN % 4 == 0, "thread tiling");
     constexpr int NCH = K / KC;
     const int tx = threadIdx.x % (N / TN), ty = threadIdx.x / (N / TN);
 
@@ -94,19 +97,11 @@ __device__ __forceinline__ void gemm_stage(const float* __restrict__ A, int lda,
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 float bv[TN];
-                const float* wr = wb + (k4 * 4 + kk) * N + tx * TN;
-                if constexpr (TN % 4 == 0) {
+                const float* wr = wb + (k4 * 4 + kk) * N + tx * 4;
 #pragma unroll
-                    for (int j4 = 0; j4 < TN / 4; ++j4) {
-                        float4 t = *reinterpret_cast<const float4*>(wr + j4 * 4);
-                        bv[j4 * 4 + 0] = t.x; bv[j4 * 4 + 1] = t.y; bv[j4 * 4 + 2] = t.z; bv[j4 * 4 + 3] = t.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int j2 = 0; j2 < TN / 2; ++j2) {
-                        float2 t = *reinterpret_cast<const float2*>(wr + j2 * 2);
-                        bv[j2 * 2 + 0] = t.x; bv[j2 * 2 + 1] = t.y;
-                    }
+                for (int g = 0; g < NG; ++g) {
+                    float4 t = *reinterpret_cast<const float4*>(wr + g * GS);
+                    bv[g * 4 + 0] = t.x; bv[g * 4 + 1] = t.y; bv[g * 4 + 2] = t.z; bv[g * 4 + 3] = t.w;
                 }
 #pragma unroll
                 for (int i = 0; i < TM; ++i) {
@@ -122,13 +117,24 @@ __device__ __forceinline__ void gemm_stage(const float* __restrict__ A, int lda,
     }
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
-        float* o = OUT + (size_t)(ty * TM + i) * ldo + tx * TN;
 #pragma unroll
-        for (int j = 0; j < TN; ++j) {
-            float v = acc[i][j];
-            if (HAS_BIAS) v += bias[tx * TN + j];
-            if (RELU) v = fmaxf(v, 0.f);
-            o[j] = v;
+        for (int g = 0; g < NG; ++g) {
+            float4* o = reinterpret_cast<float4*>(OUT + (size_t)(ty * TM + i) * ldo + g * GS + tx * 4);
+            float v[4] = {acc[i][g * 4 + 0], acc[i][g * 4 + 1], acc[i][g * 4 + 2], acc[i][g * 4 + 3]};
+            if (HAS_BIAS) {
+                const float4 bb = *reinterpret_cast<const float4*>(bias + g * GS + tx * 4);
+                v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
+            }
+            if (MODE == 1) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            if (MODE == 2) {
+                const float4 old = *o;
+                v[0] = old.x > 0.f ? v[0] : 0.f; v[1] = old.y > 0.f ? v[1] : 0.f;
+                v[2] = old.z > 0.f ? v[2] : 0.f; v[3] = old.w > 0.f ? v[3] : 0.f;
+            }
+            *o = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
     __syncthreads();

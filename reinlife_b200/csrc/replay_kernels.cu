@@ -1,0 +1,231 @@
+// replay_kernels.cu -- device replay rings, one per (world, brain).
+//
+// Reference: PrioritizedReplayBuffer (Models/PERD3QN.py:133-182): ring of `capacity` transitions, float32
+// priorities initialised to 0, new items stored with max(priorities) (1.0 while empty), proportional sampling
+// prio^0.6 with replacement (np.random.choice = cumsum + searchsorted), update_priorities by sequential
+// overwrite.  The unused importance weights / beta bookkeeping (:168-172) are not materialised.
+#include "rl_common.cuh"
+
+namespace {
+
+constexpr int RT = 256;
+
+struct ReplayParams {
+    rl_world_cfg cfg;
+    rl_world_bufs wb;
+    rl_rows_bufs rows;
+    rl_replay_bufs rp;
+    int32_t gene, batch;
+    uint64_t t;
+    int32_t* sample_idx;
+    const float* new_prio;
+};
+
+__device__ __forceinline__ float pw_of(float p) { return (float)pow((double)p, 0.6); }   // PERD3QN.py:162 (alpha)
+
+__device__ __forceinline__ float block_max(float v, float* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane_id() == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = red[0];
+    for (int i = 1; i < RT / 32; ++i) r = fmaxf(r, red[i]);
+    __syncthreads();
+    return r;
+}
+
+// ---- memorize: CTA per world ----
+__global__ void __launch_bounds__(RT) k_replay_store(const ReplayParams P) {
+    __shared__ float red[RT / 32];
+    const int w = blockIdx.x, NW = P.cfg.n_worlds, S = P.cfg.slot_cap, ld = P.cfg.obs_ld, cap = P.rp.capacity;
+    const int gk = P.gene * RL_N_ROW_KINDS + RL_ROWS_STORE;
+    const int cnt = P.rows.count[(size_t)gk * NW + w];
+    if (cnt == 0) return;
+    const int off = P.rows.offset[(size_t)gk * NW + w];
+    const int len = P.rp.len[w], pos = P.rp.pos[w];
+    float maxp = 1.0f;
+    if (P.rp.prioritized) {
+        if (len > 0) {                                             // PERD3QN.py:147
+            float m = 0.f;
+            const float* pr = P.rp.prio + (size_t)w * cap;
+            for (int i = threadIdx.x; i < cap; i += RT) m = fmaxf(m, pr[i]);
+            maxp = block_max(m, red);
+        }
+    }
+    const float pwv = P.rp.prioritized ? pw_of(maxp) : 1.0f;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const int skip = max(0, cnt - cap);
+    for (int tr = skip + warp; tr < cnt; tr += RT / 32) {
+        if (off + tr >= P.rows.row_cap) break;
+        const int row = P.rows.rows[(size_t)gk * P.rows.row_cap + off + tr];
+        const int4 rv = reinterpret_cast<const int4*>(P.wb.rec)[row];
+        const int prev = (rv.w >> 16) & 0xFFFF;
+        const int p = (pos + tr) % cap;
+        const float4* s0 = reinterpret_cast<const float4*>(P.wb.obs_state + ((size_t)w * S + prev) * ld);
+        const float4* s1 = reinterpret_cast<const float4*>(P.wb.obs_prime + (size_t)row * ld);
+        float4* d0 = reinterpret_cast<float4*>(P.rp.obs + ((size_t)w * cap + p) * ld);
+        float4* d1 = reinterpret_cast<float4*>(P.rp.next_obs + ((size_t)w * cap + p) * ld);
+        for (int v = lane; v < ld / 4; v += 32) { d0[v] = __ldg(s0 + v); d1[v] = __ldg(s1 + v); }
+        if (lane == 0) {
+            const size_t q = (size_t)w * cap + p;
+            P.rp.action[q] = (int8_t)((rv.w >> 8) & 0xFF);
+            P.rp.reward[q] = P.wb.reward[row];
+            P.rp.done[q] = (rv.w & RL_F_DEAD) ? 1 : 0;
+            if (P.rp.prioritized) { P.rp.prio[q] = maxp; P.rp.pw[q] = pwv; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        P.rp.pos[w] = (pos + cnt) % cap;
+        P.rp.len[w] = min(cap, len + cnt);
+    }
+}
+
+// ---- sample: CTA per world, exact-integer CDF in shared memory ----
+__device__ __forceinline__ unsigned long long fix_of(float w) { return __double2ull_rz((double)w * 16777216.0); }
+
+__global__ void __launch_bounds__(RT) k_replay_sample(const ReplayParams P) {
+    extern __shared__ __align__(16) unsigned long long cum[];
+    __shared__ unsigned long long wsum[RT / 32];
+    const int w = blockIdx.x, NW = P.cfg.n_worlds, cap = P.rp.capacity, batch = P.batch;
+    const int gk = P.gene * RL_N_ROW_KINDS + RL_ROWS_EVENT;
+    const int cnt = P.rows.count[(size_t)gk * NW + w];
+    if (cnt == 0) return;
+    const int off = P.rows.offset[(size_t)gk * NW + w];
+    const int len = P.rp.len[w];
+    const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
+    unsigned long long total = 0;
+    if (P.rp.prioritized) {
+        const float* pw = P.rp.pw + (size_t)w * cap;
+        const int per = (len + RT - 1) / RT;
+        const int i0 = min(len, (int)threadIdx.x * per), i1 = min(len, i0 + per);
+        unsigned long long local = 0;
+        for (int i = i0; i < i1; ++i) local += fix_of(pw[i]);
+        unsigned long long incl = local;
+        const int lane = lane_id(), warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned long long base = 0;
+        for (int i = 0; i < warp; ++i) base += wsum[i];
+        for (int i = 0; i < RT / 32; ++i) total += wsum[i];
+        unsigned long long run = base + incl - local;
+        for (int i = i0; i < i1; ++i) { run += fix_of(pw[i]); cum[i] = run; }
+        __syncthreads();
+    }
+    for (int q = threadIdx.x; q < cnt * batch; q += RT) {
+        const int e = q / batch;
+        if (off + e >= P.rows.row_cap) break;
+        const uint64_t bits = rl_draw(key, P.t, RL_SITE_REPLAY_SAMPLE, (uint32_t)q);
+        int idx = 0;
+        if (P.rp.prioritized) {
+            if (total > 0) {
+                const unsigned long long u53 = bits >> 11;
+                const unsigned long long hi = __umul64hi(u53, total), lo = u53 * total;
+                const unsigned long long target = (hi << 11) | (lo >> 53);     // floor(u53 * total / 2^53)
+                int a = 0, b = len - 1;
+                while (a < b) {
+                    const int mid = (a + b) >> 1;
+                    if (cum[mid] > target) b = mid; else a = mid + 1;
+                }
+                idx = a;
+            }
+        } else {
+            idx = (int)rl_below(bits, (uint32_t)max(len, 1));
+        }
+        P.sample_idx[(size_t)(off + e) * batch + (q - e * batch)] = idx;
+    }
+}
+
+// ---- update_priorities: warp per world, sequential over events, later writes win ----
+__global__ void __launch_bounds__(RT) k_replay_update_prio(const ReplayParams P) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= P.cfg.n_worlds) return;
+    const int NW = P.cfg.n_worlds, cap = P.rp.capacity, batch = P.batch, lane = lane_id();
+    const int gk = P.gene * RL_N_ROW_KINDS + RL_ROWS_EVENT;
+    const int cnt = P.rows.count[(size_t)gk * NW + w];
+    if (cnt == 0) return;
+    const int off = P.rows.offset[(size_t)gk * NW + w];
+    for (int e = 0; e < cnt; ++e) {
+        if (off + e >= P.rows.row_cap) break;
+        for (int h = 0; h < batch; h += 32) {
+            const int i = h + lane;
+            const bool on = i < batch;
+            const size_t q = (size_t)(off + e) * batch + i;
+            const int idx = on ? P.sample_idx[q] : -1 - lane;
+            const float val = on ? P.new_prio[q] : 0.f;
+            const unsigned m = __match_any_sync(0xffffffffu, idx);
+            if (on && (31 - __clz(m)) == lane) {
+                P.rp.prio[(size_t)w * cap + idx] = val;
+                P.rp.pw[(size_t)w * cap + idx] = pw_of(val);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+int fill(ReplayParams& P, const rl_world_cfg* cfg, const rl_world_bufs* wb, const rl_rows_bufs* rows, int32_t gene,
+         const rl_replay_bufs* rp) {
+    RL_ARG_CHECK(cfg && rows && rp);
+    RL_ARG_CHECK(gene >= 0 && gene < cfg->n_genes);
+    RL_ARG_CHECK(rp->capacity > 0 && rp->len && rp->pos);
+    P.cfg = *cfg;
+    if (wb) P.wb = *wb;
+    P.rows = *rows; P.rp = *rp; P.gene = gene; P.batch = 0; P.t = 0; P.sample_idx = nullptr; P.new_prio = nullptr;
+    return RL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rl_replay_store(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_rows_bufs* rows, int32_t gene,
+                    const rl_replay_bufs* replay, void* stream) {
+    ReplayParams P;
+    RL_ARG_CHECK(bufs);
+    int rc = fill(P, cfg, bufs, rows, gene, replay);
+    if (rc) return rc;
+    RL_ARG_CHECK(replay->obs && replay->next_obs && replay->action && replay->reward && replay->done);
+    RL_ARG_CHECK(!replay->prioritized || (replay->prio && replay->pw));
+    k_replay_store<<<cfg->n_worlds, RT, 0, (cudaStream_t)stream>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_replay_sample(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                     int32_t batch, uint64_t t, int32_t* sample_idx, void* stream) {
+    ReplayParams P;
+    int rc = fill(P, cfg, nullptr, rows, gene, replay);
+    if (rc) return rc;
+    RL_ARG_CHECK(batch > 0 && sample_idx);
+    P.batch = batch; P.t = t; P.sample_idx = sample_idx;
+    const size_t smem = replay->prioritized ? (size_t)replay->capacity * 8 : 0;
+    if (smem > 200 * 1024) return rl_set_err(RL_ERR_UNSUPPORTED, "prioritized capacity %d exceeds the in-SM CDF (25600)", replay->capacity);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_replay_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    k_replay_sample<<<cfg->n_worlds, RT, smem, (cudaStream_t)stream>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_replay_update_prio(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                          int32_t batch, const int32_t* sample_idx, const float* new_prio, void* stream) {
+    ReplayParams P;
+    int rc = fill(P, cfg, nullptr, rows, gene, replay);
+    if (rc) return rc;
+    RL_ARG_CHECK(batch > 0 && sample_idx && new_prio);
+    if (!replay->prioritized) return RL_OK;
+    P.batch = batch; P.sample_idx = const_cast<int32_t*>(sample_idx); P.new_prio = new_prio;
+    k_replay_update_prio<<<(cfg->n_worlds * 32 + RT - 1) / RT, RT, 0, (cudaStream_t)stream>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,198 @@
+"""GPU parity of replay + train events + Adam through the C ABI.
+
+* one event == the reference's PERD3QNAgent.train(): weights after 3 consecutive Adam steps vs the reference
+  (atol 1e-5), priorities written back (rtol 1e-4 / atol 1e-4);
+* N events in one step == oracle 'mean of per-event gradients, one Adam step' (DESIGN.md learn-step semantics);
+* the sampler == oracle.per_sample bit-for-bit (integer CDF); store == ring semantics of PERD3QN.py:143-155.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from brain_golden_util import golden, state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(n_worlds=1):
+    from reinlife_b200.World.vecworld import VecWorld
+    from reinlife_b200.rows import RowLists
+    vw = VecWorld(n_worlds, 8, 8, 1, max_agents=100, seed=9)
+    return vw, RowLists(vw)
+
+
+def _fake_events(vw, rows, per_world):
+    """Make the EVENT list by hand: world w has per_world[w] events (row ids w*S + e)."""
+    import reinlife_b200._lib as L
+    cnt = torch.tensor(per_world, dtype=torch.int32)
+    off = (torch.cumsum(cnt, 0) - cnt).int()
+    k = L.ROWS_EVENT
+    rows.count[k] = cnt.cuda(); rows.offset[k] = off.cuda(); rows.total[k] = int(cnt.sum())
+    ids = [w * vw.S + e for w in range(vw.n_worlds) for e in range(per_world[w])]
+    rows.rows[k, :len(ids)] = torch.tensor(ids, dtype=torch.int32).cuda()
+    return len(ids)
+
+
+def _pad(x):
+    return torch.from_numpy(np.pad(np.asarray(x, np.float32), ((0, 0), (0, 7))))
+
+
+def _fill_ring(rp, w, obs, act, rew, nobs, done):
+    n = len(act)
+    rp.obs[w, :n] = _pad(obs).cuda(); rp.next_obs[w, :n] = _pad(nobs).cuda()
+    rp.action[w, :n] = torch.from_numpy(np.asarray(act).astype(np.int8)).cuda()
+    rp.reward[w, :n] = torch.from_numpy(np.asarray(rew).astype(np.float32)).cuda()
+    rp.done[w, :n] = torch.from_numpy(np.asarray(done).astype(np.uint8)).cuda()
+    rp.len[w] = n
+
+
+def test_three_train_events_match_reference_train():
+    from reinlife_b200 import _lib
+    from reinlife_b200.brains import DeviceBrain, ReplayRings
+    from reinlife_b200.Models import packing
+    z = golden()
+    vw, rows = _mk(1)
+    brain = DeviceBrain(0, state_dict("train_perd3qn/w0"), "cuda", lr=1e-3, gamma=0.99)
+    brain.load_state_dict(state_dict("train_perd3qn/target"), target=True)
+    brain.alloc_learn(rows.row_cap)
+    rp = ReplayRings(1, 512, "cuda")
+    _fake_events(vw, rows, [1])
+    for step in range(3):
+        p = f"train_perd3qn/s{step}/"
+        # ring position i holds the i-th sampled transition; the event samples positions 0..63 in order
+        _fill_ring(rp, 0, z[p + "obs"], z[p + "action"], z[p + "reward"], z[p + "next_obs"], z[p + "done"])
+        brain.sample_idx[0] = torch.arange(64, dtype=torch.int32).cuda()
+        _lib.check(vw.lib.rl_brain_learn(C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(rp.bufs),
+                                         C.c_void_p(brain.sample_idx.data_ptr()), C.byref(brain.learn_bufs), vw._stream()))
+        _lib.check(vw.lib.rl_brain_adam(C.byref(brain.learn_bufs), vw._stream()))
+        torch.cuda.synchronize()
+        got, want = brain.state_dict(), state_dict(p + "w")
+        for k in want:
+            np.testing.assert_allclose(got[k].numpy(), want[k], rtol=0, atol=1e-5, err_msg=f"step {step} {k}")
+        ref_after, idx = z[p + "prio_after"], z[p + "indices"]
+        last = {int(i): j for j, i in enumerate(idx)}
+        newp = brain.new_prio[0].cpu().numpy()
+        for i, j in last.items():
+            np.testing.assert_allclose(newp[j], ref_after[i], rtol=1e-4, atol=1e-4)
+    assert int(brain.adam_step) == 3
+    flat = brain.params.cpu().numpy()
+    m = packing.grad_mask(0)
+    assert (flat[:len(m)][m == 0] == 0).all()                      # padding / structural zeros stay zero
+    d = packing.dims(0)
+    w2t = flat[d.off_w2t:d.off_b2].reshape(d.n1, d.n2)
+    assert (flat[d.off_w2:d.off_w2 + d.n1 * d.n2].reshape(d.n2, d.n1) == w2t.T).all()   # output-major W2 copy
+
+
+def test_batched_events_equal_mean_of_event_gradients():
+    from reinlife_b200 import _lib
+    from reinlife_b200.brains import DeviceBrain, ReplayRings
+    from reinlife_b200.Models import packing
+    from oracle import brain_oracle as bo
+    z = golden()
+    rng = np.random.default_rng(1)
+    NW, per_world, cap = 5, [2, 0, 3, 1, 4], 256
+    vw, rows = _mk(NW)
+    w0, tgt = state_dict("train_perd3qn/w0"), state_dict("train_perd3qn/target")
+    brain = DeviceBrain(0, w0, "cuda", lr=1e-3, gamma=0.99)
+    brain.load_state_dict(tgt, target=True)
+    brain.alloc_learn(rows.row_cap)
+    rp = ReplayRings(NW, cap, "cuda")
+    obs_all, rings = z["obs"], []
+    for w in range(NW):
+        n = 200
+        o = obs_all[rng.integers(0, 512, n)]; no = obs_all[rng.integers(0, 512, n)]
+        a = rng.integers(0, 8, n); r = rng.choice([0.0, 0.2, 0.5, -3.0, -20.0], n); d = (r < 0).astype(np.float64)
+        _fill_ring(rp, w, o, a, r, no, d)
+        rings.append((o, a, r, no, d))
+    n_ev = _fake_events(vw, rows, per_world)
+    sidx = rng.integers(0, 200, size=(n_ev, 64)).astype(np.int32)
+    brain.sample_idx[:n_ev] = torch.from_numpy(sidx).cuda()
+    _lib.check(vw.lib.rl_brain_learn(C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(rp.bufs),
+                                     C.c_void_p(brain.sample_idx.data_ptr()), C.byref(brain.learn_bufs), vw._stream()))
+    torch.cuda.synchronize()
+    events, e = [], 0
+    for w in range(NW):
+        o, a, r, no, d = rings[w]
+        for _ in range(per_world[w]):
+            i = sidx[e]; e += 1
+            events.append((o[i], a[i], r[i], no[i], d[i]))
+    g_ref, losses, prios = bo.dueling_batched_update(w0, tgt, events, 0.99)
+    grad = brain.grad.cpu().numpy()
+    nt = brain.dims.n_train
+    assert grad[nt] == n_ev
+    got = packing.unpack(0, np.concatenate([grad[:nt] / n_ev * packing.grad_mask(0), np.zeros(brain.dims.n_total - nt, np.float32)]))
+    for k in g_ref:
+        scale = max(1.0, np.abs(g_ref[k]).max())
+        np.testing.assert_allclose(got[k].numpy(), g_ref[k], rtol=2e-4, atol=2e-5 * scale, err_msg=k)
+    np.testing.assert_allclose(brain.loss[:n_ev].cpu().numpy(), np.array(losses), rtol=2e-4, atol=1e-4)
+    np.testing.assert_allclose(brain.new_prio[:n_ev].cpu().numpy(), np.stack(prios), rtol=2e-4, atol=2e-4)
+
+
+def test_store_sample_update_follow_the_reference_buffer():
+    from reinlife_b200.brains import learn_step, DeviceBrain, ReplayRings
+    from reinlife_b200.World.vecworld import VecWorld
+    from reinlife_b200.rows import RowLists
+    from reinlife_b200.Models import packing
+    from oracle import brain_oracle as bo
+    from oracle import ref_harness as rh
+    NW, cap = 6, 96
+    vw = VecWorld(NW, 12, 12, 2, max_agents=40, seed=21, world_id0=3)
+    rows = RowLists(vw)
+    vw.reset(); vw.top_up(40)
+    torch.manual_seed(0)
+    brains = [DeviceBrain(0, packing.default_init(0), "cuda", lr=1e-3, gamma=0.99) for _ in range(2)]
+    for b in brains:
+        b.alloc_learn(rows.row_cap)
+    rps = [ReplayRings(NW, cap, "cuda") for _ in range(2)]
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    mirror = [[dict(prio=np.zeros(cap, np.float32), items=[None] * cap, len=0, pos=0) for _ in range(NW)] for _ in range(2)]
+    tf = [3, 4]
+    for step in range(8):
+        obs_state = vw.obs_state.cpu().numpy().copy()
+        vw.set_actions(torch.randint(0, 8, (NW, vw.S), device="cuda", dtype=torch.int8, generator=g))
+        vw.step()
+        rows.build(kinds_mask=6, train_freq=tf, event_on=[1, 1])
+        torch.cuda.synchronize()
+        rec = vw.rec_host(); n = vw.n_agents.cpu().numpy()
+        obs_prime = vw.obs_prime.cpu().numpy(); reward = vw.reward.cpu().numpy()
+        for gene in range(2):
+            learn_step(vw, rows, gene, brains[gene], rps[gene], vw.t)
+            torch.cuda.synchronize()
+            sidx = brains[gene].sample_idx.cpu().numpy(); newp = brains[gene].new_prio.cpu().numpy()
+            ev_off = rows.offset[gene * 3 + 2].cpu().numpy()
+            for w in range(NW):
+                mr = mirror[gene][w]
+                for s in range(n[w]):                                  # memorize (PERD3QN.py:143-155)
+                    r = rec[w, s]
+                    if r["gene"] != gene or r["age"] <= 1:
+                        continue
+                    maxp = mr["prio"].max() if mr["len"] > 0 else 1.0
+                    mr["items"][mr["pos"]] = (obs_state[w, r["prev_slot"]], int(r["action"]), reward[w, s],
+                                              obs_prime[w, s], bool(r["flags"] & 32))
+                    mr["prio"][mr["pos"]] = maxp
+                    mr["pos"] = (mr["pos"] + 1) % cap
+                    mr["len"] = min(cap, mr["len"] + 1)
+                assert int(rps[gene].len[w]) == mr["len"] and int(rps[gene].pos[w]) == mr["pos"]
+                ev = [s for s in range(n[w]) if rec[w, s]["gene"] == gene and rec[w, s]["age"] > 1 and
+                      (rec[w, s]["age"] % tf[gene] == 0 or rec[w, s]["flags"] & 32)]
+                wts = bo.per_weight(mr["prio"][:mr["len"]])
+                key = rh.world_key(21, 3 + w)
+                for k_ev in range(len(ev)):                            # sampler: bit-exact integer CDF
+                    u53 = [rh.draw(key, vw.t, rh.SITE["REPLAY_SAMPLE"], k_ev * 64 + i) >> 11 for i in range(64)]
+                    assert sidx[ev_off[w] + k_ev].tolist() == bo.per_sample(wts, u53), (step, gene, w, k_ev)
+                for k_ev in range(len(ev)):                            # update_priorities: sequential overwrite
+                    for i in range(64):
+                        mr["prio"][sidx[ev_off[w] + k_ev, i]] = newp[ev_off[w] + k_ev, i]
+                assert (rps[gene].prio[w].cpu().numpy() == mr["prio"]).all(), (step, gene, w)
+                assert (rps[gene].pw[w, :mr["len"]].cpu().numpy() == bo.per_weight(mr["prio"][:mr["len"]])).all()
+                ro = rps[gene].obs[w].cpu().numpy(); rn = rps[gene].next_obs[w].cpu().numpy()
+                ra = rps[gene].action[w].cpu().numpy(); rr = rps[gene].reward[w].cpu().numpy()
+                rd = rps[gene].done[w].cpu().numpy()
+                for p_ in range(mr["len"]):
+                    it = mr["items"][p_]
+                    assert (ro[p_] == it[0]).all() and ra[p_] == it[1] and rr[p_] == it[2]
+                    assert (rn[p_] == it[3]).all() and rd[p_] == it[4]
+        vw.update(); vw.top_up(40)
+    assert all(int(b.adam_step) > 0 for b in brains)
