@@ -164,8 +164,22 @@ typedef struct rl_brain_act {
     int32_t kind;           /* rl_model_kind */
     int32_t rule;           /* rl_act_rule   */
     const float* params;    /* online network, kernel layout */
-    double  epsilon;
+    const double* epsilon;  /* DEVICE scalar: the brain's current epsilon (see rl_brain_epsilon_update) */
 } rl_brain_act;
+
+/* epsilon schedules, evaluated on the device so that -- exactly like the reference, where the schedule lives inside
+ * get_action -- a brain with no listed agent this step does not advance (no host sync needed to know that):
+ *   RL_ACT_DUELING: if training and n_epi > seen: eps *= decay while eps > eps_min; seen = n_epi   (PERD3QN.py:82-86, D3QN.py:84-89)
+ *   RL_ACT_DQN:     if training and n_epi % 30 == 0: eps = max(0.01, 0.20 - 0.20*(n_epi/max_epi))  (DQN.py:67-69)
+ * eps_dev [n_brains] double, seen_dev [n_brains] int64 are device arrays owned by the caller. */
+typedef struct rl_brain_sched {
+    int32_t rule;           /* rl_act_rule */
+    int32_t training;
+    double  eps_min, decay;
+    int64_t max_epi;
+} rl_brain_sched;
+int rl_brain_epsilon_update(const rl_rows_bufs* rows, const rl_brain_sched* sched_host, int32_t n_brains, int64_t n_epi,
+                            double* eps_dev, int64_t* seen_dev, void* stream);
 
 /* brain.get_action for every listed agent of every world (Helpers/trainer.py:88-89, Helpers/tester.py:58-68):
  * forward on obs_state rows, exploration draws keyed (t_act, slot), result written to rec[].action.
@@ -238,8 +252,24 @@ int rl_brain_learn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t ge
  * Also refreshes the output-major copy of W2. */
 int rl_brain_adam(const rl_learn_bufs* learn, void* stream);
 
-/* target_net.load_state_dict(eval_net.state_dict())  (PERD3QN.py:124-125) */
-int rl_brain_sync_target(const rl_learn_bufs* learn, void* stream);
+/* target_net.load_state_dict(eval_net.state_dict())  (PERD3QN.py:124-125).  cond (device int32, may be NULL): copy only
+ * when *cond > 0 -- the reference syncs inside learn(), i.e. only if some agent of the brain called learn this step. */
+int rl_brain_sync_target(const rl_learn_bufs* learn, const int32_t* cond, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Tracker partials (Helpers/tracker.py:178-266): per gene, summed over all worlds of the shard, for the
+ * current agent list (call after rl_world_step: that is the list tracker.update_results sees,
+ * World/environment.py:206-207).  Deterministic two-level reduction, no host sync.
+ * out (device, float64): [n_genes][RL_N_STATS] then 8 trailing doubles:
+ *   [0] total agents, [1] worlds with >= 1 agent, [2] sum over worlds of #distinct genes present,
+ *   [3] ctrl[0] echoed (step stamp written by the host into `ctrl`), [4..7] reserved.
+ * RL_STAT_COUNT = agents, AGE_SUM, REWARD_SUM (float64 sum of float32 rewards), AGE_MAX, ATTACKS (action >= 4),
+ * KILLS (sum of agent.killed), [6] = worlds in which the gene is present, [7] reserved.
+ * ---------------------------------------------------------------------------------------------- */
+int rl_world_stats(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const int64_t* ctrl_dev, double* scratch_dev,
+                   int32_t* counter_dev, double* out_dev, void* stream);
+int rl_world_stats_scratch_doubles(const rl_world_cfg* cfg);   /* size of scratch_dev in doubles */
 
 #ifdef __cplusplus
 }

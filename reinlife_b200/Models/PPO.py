@@ -1,0 +1,40 @@
+"""PPO brain (ReinLife/Models/PPO.py:10-77): 153-256-256 trunk, softmax policy head + value head."""
+import numpy as np
+import torch
+
+from .. import _lib
+from . import packing
+from ._base import DeviceBrainBase, _NetHandle
+
+
+class PPOAgent(DeviceBrainBase):
+    KIND, RULE, PRIORITIZED, HAS_TARGET = packing.PPO, _lib.ACT_PPO, False, False
+
+    def __init__(self, input_dim=153, output_dim=8, learning_rate=0.0005, gamma=0.98, lmbda=0.95, eps_clip=0.1,
+                 k_epoch=3, train_freq=20, load_model=False):
+        super().__init__(input_dim, output_dim, "PPO")
+        if input_dim != 153 or output_dim != 8:
+            raise ValueError("the device brains are specialised for ReinLife's 153-float observation and 8 actions")
+        self._init_common()
+        self._host_sd = packing.default_init(self.KIND)
+        self._host_sd_target = None
+        self.model = _NetHandle(self)
+        self.learning_rate, self.gamma, self.lmbda, self.eps_clip, self.k_epoch = learning_rate, gamma, lmbda, eps_clip, k_epoch
+        self.load_model = load_model
+        self.train_freq = train_freq
+        self.training = False if load_model else True
+        if self.load_model:
+            self.model.load_state_dict(torch.load(load_model, map_location="cpu"))
+
+    def _lr(self): return self.learning_rate
+    def _gamma(self): return self.gamma
+    def _batch(self): return 64
+    def _capacity(self): return 1
+
+    def get_action(self, s):                       # PPO.py:54-60, 164-169
+        prob = torch.from_numpy(np.asarray(self._q_single(np.asarray(s)), np.float32))
+        a = int(torch.distributions.Categorical(prob).sample().item())
+        return a if self.load_model else (a, prob)
+
+    def learn(self, age, dead, action, state, reward, state_prime, done, prob):
+        raise NotImplementedError("PPO training on the device is not implemented yet (inference / tester path only)")

@@ -1,0 +1,89 @@
+"""Host side of a device brain: hyper-parameters with the reference's names, the epsilon schedule descriptor,
+state_dict round trips under the reference's attribute names (`eval_net`, `target_net`, `agent`, `target`, `model`),
+and the binding to a vectorised Environment (device network + per-world replay rings)."""
+import torch
+
+from .. import _lib
+from . import packing
+from .utils import BasicBrain
+
+
+class _NetHandle:
+    """What `brain.eval_net` / `.agent` / `.model` is here: something with state_dict()/load_state_dict(), so that
+    Agent.save_brain (World/entities.py:224-242) and Saver keep working.  Before the brain is bound to an
+    Environment it holds the host state_dict; afterwards it reads/writes the device buffer."""
+
+    def __init__(self, brain, target=False):
+        self._brain, self._target = brain, target
+
+    def state_dict(self):
+        b = self._brain
+        if b._dev is not None:
+            return b._dev.state_dict(target=self._target)
+        return b._host_sd_target if self._target else b._host_sd
+
+    def load_state_dict(self, sd):
+        b = self._brain
+        sd = {k: torch.as_tensor(v).detach().clone().float() for k, v in sd.items()}
+        if b._dev is not None:
+            b._dev.load_state_dict(sd, target=self._target)
+        elif self._target:
+            b._host_sd_target = sd
+        else:
+            b._host_sd = sd
+
+    def eval(self):
+        return self
+
+    def parameters(self):
+        return list(self.state_dict().values())
+
+
+class DeviceBrainBase(BasicBrain):
+    KIND = None          # packing.DUELING / DQN / PPO
+    RULE = None          # _lib.ACT_*
+    PRIORITIZED = False
+    HAS_TARGET = True
+    DEVICE_LEARN = False  # True once the brain's learn step exists as CUDA kernels
+
+    def _init_common(self):
+        self._dev = None            # brains.DeviceBrain once bound
+        self._replay = None
+        self._env = None
+
+    # ---- binding ---------------------------------------------------------------------------------
+    def _bind(self, env, gene):
+        """Called by Environment: move the network to env.device, allocate the per-world replay rings."""
+        from ..brains import DeviceBrain, ReplayRings
+        if self._env is not None and self._env is not env:
+            raise RuntimeError("a brain object can be bound to one Environment only")
+        if self._dev is None:
+            self._dev = DeviceBrain(self.KIND, self._host_sd, env.device, lr=self._lr(), gamma=self._gamma(),
+                                    batch=self._batch(), has_target=self.HAS_TARGET)
+            if self.HAS_TARGET and self._host_sd_target is not None:
+                self._dev.load_state_dict(self._host_sd_target, target=True)
+        self._env, self._gene = env, gene
+        if env.training and self._trains():
+            if self._replay is None:
+                need = ReplayRings.bytes_needed(env.n_worlds, self._capacity())
+                free, _ = torch.cuda.mem_get_info(env.device)
+                if need > 0.9 * free:
+                    raise MemoryError(f"replay rings for {env.n_worlds} worlds x capacity {self._capacity()} need "
+                                      f"{need / 2**30:.1f} GiB, {free / 2**30:.1f} GiB free; lower `capacity`")
+                self._replay = ReplayRings(env.n_worlds, self._capacity(), env.device, prioritized=self.PRIORITIZED)
+            self._dev.alloc_learn(env.rows.row_cap)
+
+    def _trains(self):
+        return bool(getattr(self, "training", True)) and self.DEVICE_LEARN
+
+    def _sched(self):
+        return _lib.BrainSched(self.RULE, int(bool(getattr(self, "training", False))), 0.0, 1.0, 0)
+
+    def _sync_host_scalars(self, eps, seen):
+        pass
+
+    # ---- plugin surface for single observations (the reference's per-agent calls) ------------------
+    def _q_single(self, state):
+        """Network output for ONE observation through the same act kernel (1 row)."""
+        from ..single import forward_single
+        return forward_single(self, state)

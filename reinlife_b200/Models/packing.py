@@ -116,24 +116,17 @@ def grad_mask(kind):
     return m
 
 
-def default_init(kind, generator=None):
-    """nn.Linear default init (kaiming_uniform(a=sqrt(5)) = U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias),
-    drawn layer by layer in the reference's construction order from torch's global (or the given) generator."""
-    import torch
-
-    def lin(out_f, in_f):
-        bound = 1.0 / np.sqrt(in_f)
-        w = (torch.rand(out_f, in_f, generator=generator) * 2 - 1) * bound
-        b = (torch.rand(out_f, generator=generator) * 2 - 1) * bound
-        return w, b
+def default_init(kind):
+    """Initial weights exactly as the reference draws them: torch.nn.Linear modules constructed in the reference's
+    attribute order (PERD3QN.py:189-196, DQN.py:122-124, PPO.py:96-99) from torch's global RNG -- so the same
+    torch.manual_seed gives the same initial network as the reference class."""
+    import torch.nn as nn
+    spec = {DUELING: (("fc", 153, 128), ("adv_fc1", 128, 128), ("adv_fc2", 128, 8), ("value_fc1", 128, 128), ("value_fc2", 128, 1)),
+            DQN: (("fc1", 153, 128), ("fc2", 128, 64), ("fc3", 64, 8)),
+            PPO: (("fc1", 153, 256), ("fc2", 256, 256), ("fc_pi", 256, 8), ("fc_v", 256, 1))}[kind]
     sd = OrderedDict()
-    if kind == DUELING:
-        for name, o, i in (("fc", 128, 153), ("adv_fc1", 128, 128), ("adv_fc2", 8, 128), ("value_fc1", 128, 128), ("value_fc2", 1, 128)):
-            sd[name + ".weight"], sd[name + ".bias"] = lin(o, i)
-    elif kind == DQN:
-        for name, o, i in (("fc1", 128, 153), ("fc2", 64, 128), ("fc3", 8, 64)):
-            sd[name + ".weight"], sd[name + ".bias"] = lin(o, i)
-    else:
-        for name, o, i in (("fc1", 256, 153), ("fc2", 256, 256), ("fc_pi", 8, 256), ("fc_v", 1, 256)):
-            sd[name + ".weight"], sd[name + ".bias"] = lin(o, i)
+    for name, i, o in spec:
+        layer = nn.Linear(i, o)
+        sd[name + ".weight"] = layer.weight.detach().clone()
+        sd[name + ".bias"] = layer.bias.detach().clone()
     return sd

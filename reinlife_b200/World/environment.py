@@ -1,0 +1,234 @@
+"""Vectorised Environment: `n_worlds` independent instances of the reference's Environment
+(ReinLife/World/environment.py:16-215) stepped together on one GPU, the brains' networks shared by all worlds.
+
+Same constructor keywords and phase methods as the reference (`reset`, `step`, `update_env`, `render`,
+`save_results`) plus the two batched phases that replace the per-agent Python loops of Helpers/trainer.py:88-96:
+`act(n_epi)` and `learn(n_epi)`.  Extra keyword-only arguments: n_worlds, seed, device, world_id0.
+With torch.distributed initialised, `n_worlds` is the GLOBAL world count: each rank owns a contiguous shard and the
+only collective is one all-reduce of the brains' summed gradients per learn step.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..brains import sync_target
+from ..rows import RowLists
+from .vecworld import VecWorld
+from .utils import Actions, EntityTypes
+
+
+class AgentView:
+    """Read-only host snapshot of one agent (the fields of World/entities.py:145-170 that live on the device)."""
+    __slots__ = ("i", "j", "health", "max_health", "age", "max_age", "gene", "action", "killed", "inter_killed",
+                 "intra_killed", "ate_super_food", "reproduced", "dead", "reward", "brain", "coordinates")
+
+    def __init__(self, rec, width, reward, brain):
+        self.i, self.j = divmod(int(rec["cell"]), width)
+        self.coordinates = [self.i, self.j]
+        self.health, self.max_health = int(rec["health"]), 200
+        self.age, self.max_age, self.gene, self.action = int(rec["age"]), int(rec["max_age"]), int(rec["gene"]), int(rec["action"])
+        f = int(rec["flags"])
+        self.killed, self.inter_killed, self.intra_killed = f & 1, (f >> 1) & 1, (f >> 2) & 1
+        self.ate_super_food = 1.0 if f & 8 else -1
+        self.reproduced, self.dead = bool(f & 16), bool(f & 32)
+        self.reward, self.brain = reward, brain
+
+
+class _GridView:
+    def __init__(self, env, world=0):
+        self._env, self._world = env, world
+        self.width, self.height = env.width, env.height
+
+    def get_numpy(self, entity_type=None):
+        g = self._env.world.type[self._world].cpu().numpy().reshape(self.height, self.width).astype(np.int64)
+        return (g == entity_type) if entity_type else g
+
+
+class Environment:
+    def __init__(self, width: int = 30, height: int = 30, brains=None, grid_size: int = 16, max_agents: int = 50,
+                 update_interval: int = 500, print_results: bool = True, static_families: bool = True,
+                 interactive_results: bool = False, google_colab: bool = False, training: bool = True,
+                 save: bool = False, pastel_colors: bool = False, limit_reproduction: bool = False,
+                 incentivize_killing: bool = True, *, n_worlds: int = 1, seed: int = 0, device=None, world_id0=None):
+        self.width, self.height = width, height
+        self.actions, self.entities = Actions, EntityTypes
+        self.best_agents = []
+        self.brains = brains
+        self.max_agents = max_agents
+        self.max_gene = len(brains)                      # TypeError when brains is None, like environment.py:107
+        self.static_families, self.google_colab, self.save = static_families, google_colab, save
+        self.training, self.limit_reproduction, self.incentivize_killing = training, limit_reproduction, incentivize_killing
+        self.action_space, self.observation_space = 8, 153
+        self.update_interval, self.print_results = update_interval, print_results
+        if interactive_results:
+            raise NotImplementedError("interactive matplotlib results are out of scope (SURVEY.md 2, #16)")
+        if not static_families:
+            raise NotImplementedError("static_families=False (per-lineage brain pool) is not implemented yet")
+
+        self.dist = torch.distributed.is_available() and torch.distributed.is_initialized()
+        self.rank = torch.distributed.get_rank() if self.dist else 0
+        self.world_size = torch.distributed.get_world_size() if self.dist else 1
+        if device is None:
+            device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", torch.cuda.current_device() if torch.cuda.is_available() else 0)))
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.RLError("reinlife_b200 runs on CUDA devices only (no CPU fallback)")
+        if n_worlds % self.world_size:
+            raise ValueError(f"n_worlds={n_worlds} must be divisible by the number of ranks ({self.world_size})")
+        self.n_worlds_global = n_worlds
+        self.n_worlds = n_worlds // self.world_size
+        self.seed = seed
+        wid0 = self.rank * self.n_worlds if world_id0 is None else world_id0
+        self.world = VecWorld(self.n_worlds, height, width, len(brains), max_agents=max_agents, seed=seed, world_id0=wid0,
+                              static_families=static_families, limit_reproduction=limit_reproduction,
+                              incentivize_killing=incentivize_killing, device=self.device)
+        self.rows = RowLists(self.world)
+        G = len(brains)
+        for g, b in enumerate(brains):
+            if not hasattr(b, "_bind"):
+                raise TypeError(f"brain {g} ({type(b).__name__}) is not a reinlife_b200.Models brain")
+            b._bind(self, g)
+        self._eps = torch.tensor([float(b.epsilon) if hasattr(b, "epsilon") else 0.0 for b in brains],
+                                 dtype=torch.float64, device=self.device)
+        self._seen = torch.tensor([int(getattr(b, "n_epi", 0)) for b in brains], dtype=torch.int64, device=self.device)
+        self._prob = torch.zeros(self.n_worlds * self.world.S, device=self.device)
+        self._act_descs = (_lib.BrainAct * G)(*[b._dev.act_desc(b.RULE, self._eps.data_ptr() + 8 * g) for g, b in enumerate(brains)])
+        if self.dist:
+            for b in brains:                              # identical weights on every rank
+                torch.distributed.broadcast(b._dev.params, 0)
+                if b._dev.target is not None:
+                    torch.distributed.broadcast(b._dev.target, 0)
+        self._grad_all = None
+        from ..Helpers.tracker import Tracker
+        self.tracker = Tracker(self, update_interval=update_interval, print_results=print_results)
+        self.viz = None
+        self.grid = None
+        self.gpu_launches = 0
+
+    # ------------------------------------------------------------------ reference phases
+    def reset(self):
+        self.world.reset()
+        self.grid = _GridView(self)
+        self.gpu_launches += 1
+
+    def step(self):
+        self.world.step()
+        self.gpu_launches += 1
+
+    def update_env(self, n_epi: int = 0):
+        if self.training:                                  # environment.py:206-207
+            self.tracker.update_results(None, n_epi)
+            self.gpu_launches += 1
+        self.world.update()
+        self.gpu_launches += 1
+
+    def top_up(self, target, max_age=50):
+        """Benchmark-only saturated-world generator."""
+        self.world.top_up(target, max_age)
+        self.gpu_launches += 1
+
+    def render(self, fps: int = 10) -> bool:
+        raise NotImplementedError("the pygame renderer is out of scope (SURVEY.md 2, #18)")
+
+    def save_results(self):
+        from ..Helpers.saver import save_brains
+        return save_brains(self)
+
+    # ------------------------------------------------------------------ batched stand-ins for the per-agent loops
+    def act(self, n_epi: int = 0):
+        """for agent in env.agents: agent.get_action(n_epi)   (Helpers/trainer.py:88-89, Helpers/tester.py:58-68)"""
+        w = self.world
+        G = len(self.brains)
+        self.rows.build(kinds_mask=1)
+        sched = (_lib.BrainSched * G)(*[b._sched() for b in self.brains])
+        with torch.cuda.device(self.device):
+            _lib.check(w.lib.rl_brain_epsilon_update(C.byref(self.rows.bufs), sched, G, C.c_int64(n_epi),
+                                                     C.c_void_p(self._eps.data_ptr()), C.c_void_p(self._seen.data_ptr()),
+                                                     w._stream()))
+            _lib.check(w.lib.rl_brain_act_all(C.byref(w.cfg), C.byref(w.bufs), C.byref(self.rows.bufs), self._act_descs, G,
+                                              C.c_uint64(w.t + 1), None, C.c_void_p(self._prob.data_ptr()), w._stream()))
+        self.gpu_launches += 4 + G
+
+    def learn(self, n_epi: int = 0):
+        """for agent in env.agents: agent.learn(n_epi=n_epi)   (Helpers/trainer.py:95-96), batched:
+        all stores of the step, then every train() trigger as one 64-row event, per-event gradients averaged
+        (all-reduced across ranks), ONE Adam step per brain, then priorities, then the target sync rule."""
+        if not self.training:
+            return
+        w, lib = self.world, self.world.lib
+        G = len(self.brains)
+        trainable = [g for g, b in enumerate(self.brains) if b._trains()]
+        for g, b in enumerate(self.brains):
+            if g not in trainable and getattr(b, "training", True):
+                raise NotImplementedError(f"{b.method}: the learn step is not implemented on the device yet "
+                                          "(inference / tester path only); there is no CPU fallback")
+        if not trainable:
+            return
+        tf = [int(getattr(b, "train_freq", 1)) for b in self.brains]
+        on = [int(b._trains() and n_epi > getattr(b, "exploration", -1)) for b in self.brains]
+        self.rows.build(kinds_mask=6, train_freq=tf, event_on=on)
+        st = w._stream()
+        with torch.cuda.device(self.device):
+            for g in trainable:
+                b = self.brains[g]
+                _lib.check(lib.rl_replay_store(C.byref(w.cfg), C.byref(w.bufs), C.byref(self.rows.bufs), C.c_int32(g),
+                                               C.byref(b._replay.bufs), st))
+                if not on[g]:
+                    continue
+                _lib.check(lib.rl_replay_sample(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                                C.c_int32(b._dev.batch), C.c_uint64(w.t), C.c_void_p(b._dev.sample_idx.data_ptr()), st))
+                _lib.check(lib.rl_brain_learn(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                              C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs), st))
+                self.gpu_launches += 4
+            active = [g for g in trainable if on[g]]
+            if self.dist and active:
+                self._allreduce_grads(active)
+            for g in active:
+                b = self.brains[g]
+                _lib.check(lib.rl_brain_adam(C.byref(b._dev.learn_bufs), st))
+                _lib.check(lib.rl_replay_update_prio(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                                     C.c_int32(b._dev.batch), C.c_void_p(b._dev.sample_idx.data_ptr()),
+                                                     C.c_void_p(b._dev.new_prio.data_ptr()), st))
+                self.gpu_launches += 3
+                if n_epi % int(b.soft_update_freq) == 0:          # PERD3QN.py:124-125, only if learn() was called
+                    cond = self.rows.total.data_ptr() + 4 * (g * _lib.N_ROW_KINDS + _lib.ROWS_STORE)
+                    sync_target(b._dev, w, cond)
+                    self.gpu_launches += 1
+        self.gpu_launches += 3
+
+    def _allreduce_grads(self, active):
+        """One NCCL all-reduce (sum) over the flattened gradient (+event count) of every active brain."""
+        if len(active) == 1:
+            torch.distributed.all_reduce(self.brains[active[0]]._dev.grad)
+            return
+        flat = torch.cat([self.brains[g]._dev.grad for g in active])
+        torch.distributed.all_reduce(flat)
+        o = 0
+        for g in active:
+            n = self.brains[g]._dev.grad.numel()
+            self.brains[g]._dev.grad.copy_(flat[o:o + n])
+            o += n
+
+    # ------------------------------------------------------------------ host views
+    def agents_of(self, world=0):
+        n = int(self.world.n_agents[world])
+        rec = self.world.rec[world, :n].cpu().numpy().view(np.dtype(
+            [("cell", "<u2"), ("health", "<i2"), ("age", "<i2"), ("max_age", "<i2"), ("gene", "<i4"), ("flags", "u1"),
+             ("action", "i1"), ("prev_slot", "<u2")])).reshape(n)
+        rew = self.world.reward[world, :n].cpu().numpy()
+        return [AgentView(rec[s], self.width, float(rew[s]), self.brains[int(rec[s]["gene"])]) for s in range(n)]
+
+    @property
+    def agents(self):
+        """World 0's agents in the reference's (row-major) order."""
+        return self.agents_of(0)
+
+    def count_agents(self):
+        """Total listed agents on this rank (device -> host read)."""
+        return int(self.world.n_agents.sum())
+
+    def epsilons(self):
+        return self._eps.cpu().tolist()

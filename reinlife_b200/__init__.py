@@ -2,5 +2,9 @@
 
 Mirrors the reference's import surface (ReinLife/__init__.py:1-5):
     from reinlife_b200 import trainer, tester, Environment, Models
+The CUDA library is the product: anything that touches the device raises if libreinlife_b200.so is missing.
 """
-from . import _lib  # noqa: F401  (fails loudly if the CUDA library is missing when first used)
+from . import Models                      # noqa: F401
+from .Helpers.trainer import trainer      # noqa: F401
+from .Helpers.tester import tester        # noqa: F401
+from .World.environment import Environment  # noqa: F401

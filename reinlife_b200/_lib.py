@@ -78,7 +78,12 @@ class RowsBufs(C.Structure):
 
 
 class BrainAct(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("rule", C.c_int32), ("params", C.c_void_p), ("epsilon", C.c_double)]
+    _fields_ = [("kind", C.c_int32), ("rule", C.c_int32), ("params", C.c_void_p), ("epsilon", C.c_void_p)]
+
+
+class BrainSched(C.Structure):
+    _fields_ = [("rule", C.c_int32), ("training", C.c_int32), ("eps_min", C.c_double), ("decay", C.c_double),
+                ("max_epi", C.c_int64)]
 
 
 class ReplayBufs(C.Structure):

@@ -53,8 +53,8 @@ class DeviceBrain:
                                          self.new_prio.data_ptr(), self.loss.data_ptr(), self.kind, self.batch,
                                          self.gamma, self.lr)
 
-    def act_desc(self, rule, epsilon):
-        return _lib.BrainAct(self.kind, rule, self.params.data_ptr(), float(epsilon))
+    def act_desc(self, rule, eps_ptr):
+        return _lib.BrainAct(self.kind, rule, self.params.data_ptr(), eps_ptr)
 
 
 class ReplayRings:
@@ -99,6 +99,6 @@ def learn_step(world, rows, gene, brain, replay, t, allreduce=None):
                                              C.c_void_p(brain.new_prio.data_ptr()), st))
 
 
-def sync_target(brain, world):
+def sync_target(brain, world, cond_ptr=None):
     with torch.cuda.device(world.device):
-        _lib.check(world.lib.rl_brain_sync_target(C.byref(brain.learn_bufs), world._stream()))
+        _lib.check(world.lib.rl_brain_sync_target(C.byref(brain.learn_bufs), C.c_void_p(cond_ptr), world._stream()))

@@ -19,7 +19,7 @@ struct ActParams {
     const int32_t* rows;       // row list of this brain, kind ALL
     const int32_t* total;      // device scalar
     const float* params;
-    double epsilon;
+    const double* epsilon;
     uint64_t t_act;
     int32_t rule;
     float* q_out;              // [row_cap][8] or null
@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(NT, 1) k_brain_act(const ActParams P) {
 
     const int total = *P.total;
     const int S = P.cfg.slot_cap;
+    const double epsilon = *P.epsilon;
     for (int tile = blockIdx.x; tile * R < total; tile += gridDim.x) {
         const int nrows = min(R, total - tile * R);
         if (threadIdx.x < R) ids[threadIdx.x] = threadIdx.x < nrows ? P.rows[tile * R + threadIdx.x] : 0;
@@ -123,10 +124,10 @@ __global__ void __launch_bounds__(NT, 1) k_brain_act(const ActParams P) {
             int a = best;
             if (P.rule == RL_ACT_DUELING) {           // PERD3QN.py:204-210
                 const double u = rl_uniform(rl_draw(key, P.t_act, RL_SITE_ACT_EXPLORE, (uint32_t)slot));
-                if (!(u > P.epsilon)) a = (int)rl_below(rl_draw(key, P.t_act, RL_SITE_ACT_RANDOM, (uint32_t)slot), 8);
+                if (!(u > epsilon)) a = (int)rl_below(rl_draw(key, P.t_act, RL_SITE_ACT_RANDOM, (uint32_t)slot), 8);
             } else if (P.rule == RL_ACT_DQN) {        // DQN.py:135-139
                 const double coin = rl_uniform(rl_draw(key, P.t_act, RL_SITE_ACT_EXPLORE, (uint32_t)slot));
-                if (coin < P.epsilon) a = (int)rl_below(rl_draw(key, P.t_act, RL_SITE_ACT_RANDOM, (uint32_t)slot), 8);
+                if (coin < epsilon) a = (int)rl_below(rl_draw(key, P.t_act, RL_SITE_ACT_RANDOM, (uint32_t)slot), 8);
             } else {                                   // PPO.py:164-169: categorical by inverse CDF on one uniform
                 const double u = rl_uniform(rl_draw(key, P.t_act, RL_SITE_ACT_SAMPLE, (uint32_t)slot));
                 float c = 0.f;
@@ -143,6 +144,31 @@ __global__ void __launch_bounds__(NT, 1) k_brain_act(const ActParams P) {
             }
         }
         __syncthreads();
+    }
+}
+
+struct EpsParams {
+    rl_brain_sched sched[RL_MAX_GENES];
+    const int32_t* total;
+    double* eps;
+    int64_t* seen;
+    int64_t n_epi;
+    int32_t n_brains;
+};
+
+__global__ void k_epsilon_update(const EpsParams P) {
+    const int g = threadIdx.x;
+    if (g >= P.n_brains) return;
+    if (P.total[g * RL_N_ROW_KINDS + RL_ROWS_ALL] <= 0) return;      // get_action was not called for this brain
+    const rl_brain_sched s = P.sched[g];
+    if (!s.training) return;
+    if (s.rule == RL_ACT_DUELING) {
+        if (P.n_epi > P.seen[g]) {
+            if (P.eps[g] > s.eps_min) P.eps[g] = P.eps[g] * s.decay;
+            P.seen[g] = P.n_epi;
+        }
+    } else if (s.rule == RL_ACT_DQN) {
+        if (P.n_epi % 30 == 0) P.eps[g] = fmax(0.01, 0.20 - 0.20 * ((double)P.n_epi / (double)s.max_epi));
     }
 }
 
@@ -190,6 +216,17 @@ int rl_model_get_dims(int32_t kind, rl_model_dims* out) {
     return RL_OK;
 }
 
+int rl_brain_epsilon_update(const rl_rows_bufs* rows, const rl_brain_sched* sched, int32_t n_brains, int64_t n_epi,
+                            double* eps_dev, int64_t* seen_dev, void* stream) {
+    RL_ARG_CHECK(rows && sched && eps_dev && seen_dev && n_brains > 0 && n_brains <= RL_MAX_GENES);
+    EpsParams P;
+    for (int g = 0; g < n_brains; ++g) P.sched[g] = sched[g];
+    P.total = rows->total; P.eps = eps_dev; P.seen = seen_dev; P.n_epi = n_epi; P.n_brains = n_brains;
+    k_epsilon_update<<<1, 32, 0, (cudaStream_t)stream>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
 int rl_brain_act_all(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_rows_bufs* rows,
                      const rl_brain_act* brains, int32_t n_brains, uint64_t t_act, float* q_out, float* prob_out,
                      void* stream) {
@@ -200,7 +237,8 @@ int rl_brain_act_all(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const r
         P.cfg = *cfg; P.rec = bufs->rec; P.obs = bufs->obs_state;
         P.rows = rows->rows + (size_t)(g * RL_N_ROW_KINDS + RL_ROWS_ALL) * rows->row_cap;
         P.total = rows->total + g * RL_N_ROW_KINDS + RL_ROWS_ALL;
-        P.params = brains[g].params; P.epsilon = brains[g].epsilon; P.t_act = t_act; P.rule = brains[g].rule;
+        P.params = brains[g].params; P.epsilon = brains[g].epsilon;
+        RL_ARG_CHECK(P.epsilon != nullptr); P.t_act = t_act; P.rule = brains[g].rule;
         P.q_out = q_out ? q_out + (size_t)g * rows->row_cap * 8 : nullptr;
         P.prob_out = prob_out;
         RL_ARG_CHECK(P.params != nullptr);

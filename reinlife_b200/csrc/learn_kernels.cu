@@ -306,6 +306,11 @@ int n_total_of(int kind) {
     return Layout<RL_MODEL_PPO>::N_TOTAL;
 }
 
+__global__ void k_sync_target(const float* __restrict__ src, float* __restrict__ dst, int n, const int32_t* cond) {
+    if (cond && *cond <= 0) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 int g_learn_grid = 0;
 
 }  // namespace
@@ -364,10 +369,10 @@ int rl_brain_adam(const rl_learn_bufs* learn, void* stream) {
     return RL_OK;
 }
 
-int rl_brain_sync_target(const rl_learn_bufs* learn, void* stream) {
+int rl_brain_sync_target(const rl_learn_bufs* learn, const int32_t* cond, void* stream) {
     RL_ARG_CHECK(learn && learn->params && learn->target);
-    RL_CUDA_CHECK(cudaMemcpyAsync(learn->target, learn->params, sizeof(float) * n_total_of(learn->kind),
-                                  cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    k_sync_target<<<64, 256, 0, (cudaStream_t)stream>>>(learn->params, learn->target, n_total_of(learn->kind), cond);
+    RL_CUDA_CHECK(cudaGetLastError());
     return RL_OK;
 }
 

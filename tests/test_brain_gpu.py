@@ -50,7 +50,8 @@ def test_act_matches_reference_forward_and_rule(name, kind, rule, eps):
     rows.build(kinds_mask=1)
     flat = torch.from_numpy(packing.pack(kind, state_dict(name))).cuda()
     G = vw.G
-    acts = (_lib.BrainAct * G)(*[_lib.BrainAct(kind, rule, flat.data_ptr(), eps) for _ in range(G)])
+    eps_dev = torch.full((G,), eps, dtype=torch.float64, device="cuda")
+    acts = (_lib.BrainAct * G)(*[_lib.BrainAct(kind, rule, flat.data_ptr(), eps_dev.data_ptr() + 8 * g) for g in range(G)])
     q_out = torch.zeros((G, rows.row_cap, 8), device="cuda")
     prob_out = torch.zeros(vw.n_worlds * vw.S, device="cuda")
     t_act = 5

@@ -1,0 +1,69 @@
+"""End-to-end through the public API (trainer / tester / Environment) on the GPU."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_trainer_runs_and_learns_perd3qn(tmp_path, monkeypatch):
+    import reinlife_b200 as rl
+    from reinlife_b200.Models import PERD3QN
+    monkeypatch.chdir(tmp_path)
+    torch.manual_seed(0)
+    brains = [PERD3QN(exploration=2, train_freq=5, capacity=400), PERD3QN(exploration=2, train_freq=5, capacity=400)]
+    w_before = [b.eval_net.state_dict()["fc.weight"].clone() for b in brains]
+    env = rl.trainer(brains, n_episodes=30, width=12, height=12, max_agents=30, update_interval=10, print_results=False,
+                     save=True, n_worlds=16, seed=3, saturate_to=30)
+    torch.cuda.synchronize()
+    assert int(env.world.status.max()) == 0
+    for b, w0 in zip(brains, w_before):
+        assert int(b._dev.adam_step) > 0
+        assert not torch.equal(b.eval_net.state_dict()["fc.weight"], w0)
+        assert torch.isfinite(b._dev.params).all()
+    eps = env.epsilons()
+    assert all(abs(e - 0.9 * 0.99 ** 30) < 1e-12 for e in eps)          # n_epi 1..30 decayed once each (PERD3QN.py:82-86)
+    # tracker: 3 aggregation points (n_epi = 10, 20, 30), pooled over the 16 worlds
+    res = env.tracker.results
+    assert len(res["Avg Population Size"][0]) == 3 and len(res["Avg Number of Populations"]) == 3
+    assert 10 < res["Avg Population Size"][0][-1] + res["Avg Population Size"][1][-1] <= 31
+    # checkpoints in the reference layout, loadable as reference-shaped state_dicts
+    import glob
+    files = sorted(glob.glob(str(tmp_path / "experiments" / "*" / "PERD3QN" / "brain_gene_*.pt")))
+    assert len(files) == 2
+    sd = torch.load(files[0])
+    assert sd["fc.weight"].shape == (128, 153) and sd["value_fc2.weight"].shape == (1, 128)
+    # agents view
+    ag = env.agents
+    assert len(ag) == int(env.world.n_agents[0]) and all(0 <= a.gene < 2 for a in ag)
+
+
+def test_tester_inference_dqn_pretrained_weights():
+    import reinlife_b200 as rl
+    from reinlife_b200.Models import DQN
+    from brain_golden_util import state_dict
+    b = DQN(training=False)
+    b.agent.load_state_dict(state_dict("dqn"))
+    env = rl.tester([b], n_worlds=32, n_steps=20, saturate_to=100, seed=1)
+    torch.cuda.synchronize()
+    assert env.epsilons() == [0.0]
+    assert int(env.world.n_agents.min()) == 100
+    # plugin call for a single host observation agrees with the batched kernel
+    from brain_golden_util import golden
+    z = golden()
+    a = b.get_action(z["obs"][0], 0)
+    assert a == int(np.argmax(z["dqn_q_rows"][0]))
+
+
+def test_training_dqn_and_render_fail_loudly():
+    import reinlife_b200 as rl
+    from reinlife_b200.Models import DQN, PERDQN
+    with pytest.raises(ZeroDivisionError):
+        rl.trainer([DQN()], n_episodes=1, save=False, n_worlds=2)           # DQN(max_epi=0) while training (DQN.py:69)
+    with pytest.raises(NotImplementedError):
+        rl.trainer([DQN(max_epi=10)], n_episodes=30, save=False, n_worlds=2, saturate_to=20)
+    with pytest.raises(NotImplementedError):
+        PERDQN()
+    env = rl.Environment(brains=[DQN(training=False)], training=False, n_worlds=1)
+    with pytest.raises(NotImplementedError):
+        env.render()
