@@ -1,0 +1,102 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares; host logic; RNG spec."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+
+def test_library_exports_every_declared_symbol():
+    from reinlife_b200 import _lib
+    lib = _lib.load()
+    syms = _lib.exported_symbols()
+    assert len(syms) >= 20 and "rl_world_step" in syms and "rl_brain_learn" in syms
+    for s in syms:
+        assert getattr(lib, s) is not None
+    assert lib.rl_version() >= 100
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    from reinlife_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.WorldCfg(1, 2, 30, 2, 100, 60, 160, 1, 0, 1, 0, 0)      # height 2 < 3  (World/grid.py:23-24)
+    bufs = _lib.WorldBufs()
+    rc = lib.rl_world_step(C.byref(cfg), C.byref(bufs), C.c_uint64(1), None)
+    assert rc == -1 and b"height" in lib.rl_last_error()
+    with pytest.raises(_lib.RLError):
+        _lib.check(rc)
+    d = __import__("reinlife_b200.Models.packing", fromlist=["x"]).dims(0)
+    assert (d.n1, d.n2, d.nh) == (128, 256, 9) and d.n_train % 4 == 0 and d.n_total == d.off_w2 + 128 * 256
+
+
+def test_struct_layouts_match_the_header():
+    from reinlife_b200 import _lib
+    from reinlife_b200.World.vecworld import REC_DTYPE
+    assert REC_DTYPE.itemsize == 16
+    assert C.sizeof(_lib.WorldCfg) == 56 and C.sizeof(_lib.WorldBufs) == 72
+    assert C.sizeof(_lib.RowsBufs) == 40 and C.sizeof(_lib.ReplayBufs) == 80 and C.sizeof(_lib.LearnBufs) == 96
+    assert C.sizeof(_lib.BrainAct) == 24 and C.sizeof(_lib.BrainSched) == 32
+
+
+def test_pack_unpack_round_trip_and_reference_key_names():
+    from reinlife_b200.Models import packing
+    from brain_golden_util import state_dict
+    for kind, name in ((0, "perd3qn"), (1, "dqn"), (2, "ppo")):
+        sd = state_dict(name)
+        back = packing.unpack(kind, packing.pack(kind, sd))
+        assert list(back.keys()) == list(sd.keys())
+        for k in sd:
+            assert (back[k].numpy() == sd[k]).all(), (name, k)
+        m = packing.grad_mask(kind)
+        assert int(m.sum()) == sum(v.size for v in sd.values())       # trainable entries == reference parameter count
+
+
+def test_rng_spec_c_python_numpy_agree():
+    """include/rl_rng.h (through the C oracle build), its python restatement and the numpy one are the same function."""
+    from oracle import ref_harness as rh
+    from oracle import cpu_port
+    src = r'''
+    #include "../include/rl_rng.h"
+    unsigned long long t_draw(unsigned long long seed, unsigned long long w, unsigned long long step, unsigned site, unsigned idx) {
+        return rl_draw(rl_world_key(seed, w), step, site, idx); }
+    double t_uni(unsigned long long b) { return rl_uniform(b); }
+    unsigned t_below(unsigned long long b, unsigned n) { return rl_below(b, n); }
+    '''
+    import subprocess, tempfile
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle")
+    with tempfile.TemporaryDirectory() as td:
+        cfile = os.path.join(here, "_rng_test.c")
+        open(cfile, "w").write(src)
+        so = os.path.join(td, "rng.so")
+        try:
+            subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", "-o", so, cfile])
+        finally:
+            os.remove(cfile)
+        lib = C.CDLL(so)
+        lib.t_draw.restype = C.c_uint64; lib.t_uni.restype = C.c_double; lib.t_below.restype = C.c_uint32
+        lib.t_draw.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
+        lib.t_uni.argtypes = [C.c_uint64]; lib.t_below.argtypes = [C.c_uint64, C.c_uint32]
+        rng = np.random.default_rng(0)
+        for _ in range(200):
+            seed, w, step = int(rng.integers(1 << 62)), int(rng.integers(1 << 40)), int(rng.integers(1 << 30))
+            site, idx = int(rng.integers(1, 31)), int(rng.integers(1 << 20))
+            c = lib.t_draw(seed, w, step, site, idx)
+            p = rh.draw(rh.world_key(seed, w), step, site, idx)
+            n = int(cpu_port.draws(cpu_port.world_keys(seed, [w]), step, site, [idx])[0])
+            assert c == p == n
+            assert lib.t_uni(c) == rh.uniform(p) == float(cpu_port.uniform(np.array([n], np.uint64))[0])
+            assert lib.t_below(c, 37) == rh.below(p, 37) == int(cpu_port.below(np.array([n], np.uint64), 37)[0])
+
+
+def test_no_product_code_touches_the_oracle():
+    """reinlife_b200/ may mention the oracle in comments but must never import, link or load it."""
+    import re
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "reinlife_b200")
+    bad = re.compile(r"^\s*(from|import)\s+oracle|librl_oracle|#include\s+\"[^\"]*oracle|import_module\(.oracle", re.M)
+    n = 0
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                n += 1
+                assert not bad.search(open(os.path.join(dp, f)).read()), (dp, f)
+    assert n > 15
