@@ -76,12 +76,11 @@ class Environment:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.RLError("reinlife_b200 runs on CUDA devices only (no CPU fallback)")
-        if n_worlds % self.world_size:
-            raise ValueError(f"n_worlds={n_worlds} must be divisible by the number of ranks ({self.world_size})")
+        from ..sharding import shard_worlds
         self.n_worlds_global = n_worlds
-        self.n_worlds = n_worlds // self.world_size
+        self.n_worlds, wid0 = shard_worlds(n_worlds, self.rank, self.world_size)
         self.seed = seed
-        wid0 = self.rank * self.n_worlds if world_id0 is None else world_id0
+        wid0 = wid0 if world_id0 is None else world_id0
         self.world = VecWorld(self.n_worlds, height, width, len(brains), max_agents=max_agents, seed=seed, world_id0=wid0,
                               static_families=static_families, limit_reproduction=limit_reproduction,
                               incentivize_killing=incentivize_killing, device=self.device)
@@ -201,16 +200,8 @@ class Environment:
 
     def _allreduce_grads(self, active):
         """One NCCL all-reduce (sum) over the flattened gradient (+event count) of every active brain."""
-        if len(active) == 1:
-            torch.distributed.all_reduce(self.brains[active[0]]._dev.grad)
-            return
-        flat = torch.cat([self.brains[g]._dev.grad for g in active])
-        torch.distributed.all_reduce(flat)
-        o = 0
-        for g in active:
-            n = self.brains[g]._dev.grad.numel()
-            self.brains[g]._dev.grad.copy_(flat[o:o + n])
-            o += n
+        from ..sharding import allreduce_grads
+        allreduce_grads([self.brains[g]._dev.grad for g in active])
 
     # ------------------------------------------------------------------ host views
     def agents_of(self, world=0):
