@@ -36,6 +36,8 @@ def parse():
     ap.add_argument("--worlds-per-gpu", type=int, default=4096)
     ap.add_argument("--capacity", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
+                    help="train() events: tcgen05 kind::tf32 tensor cores (fp32 accumulate) or fp32 CUDA-core FMA")
     ap.add_argument("--cpu-worlds-per-core", type=int, default=2)
     ap.add_argument("--cpu-steps", type=int, default=8)
     return ap.parse_args()
@@ -131,7 +133,7 @@ def run_b200(args):
     brains = [PERD3QN(exploration=0, capacity=args.capacity), PERD3QN(exploration=0, capacity=args.capacity)]
     n_worlds = args.worlds_per_gpu * world_size
     env = rl.Environment(width=W, height=H, brains=brains, max_agents=TARGET, update_interval=500, print_results=False,
-                         training=True, n_worlds=n_worlds, seed=0, device=torch.device("cuda", local))
+                         training=True, n_worlds=n_worlds, seed=0, device=torch.device("cuda", local), precision=args.precision)
     env.reset()
     env.top_up(TARGET)
     NW, C = env.n_worlds, H * W
@@ -233,7 +235,8 @@ def run_b200(args):
         "k_world_topup": {"bound": "hbm", "ms": phases["top_up"], "achieved": b_obs / phases["top_up"] / 1e6, "peak": hbm_peak, "unit": "GB/s"},
         "learn(k_learn_dueling+replay+adam)": {"bound": "tensor", "ms": phases["learn"],
                                                "achieved": ev_avg * flop_event / phases["learn"] / 1e9, "peak": bf16_peak, "unit": "TFLOP/s",
-                                               "note": "fp32 FMA on CUDA cores (reference precision); peak shown is the bf16 tensor peak"},
+                                               "note": ("tcgen05 kind::tf32, TMEM accumulators; peak shown is the measured bf16 tensor peak (tf32 dense is half of it)"
+                                                        if args.precision == "tf32" else "fp32 FMA on CUDA cores (reference precision); peak shown is the bf16 tensor peak")},
         "act(k_brain_act)": {"bound": "tensor", "ms": phases["act"], "achieved": NW * n_avg * 107008 / phases["act"] / 1e9,
                              "peak": bf16_peak, "unit": "TFLOP/s", "note": "fp32 FMA on CUDA cores"},
     }
@@ -245,7 +248,7 @@ def run_b200(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": ("tf32 (tensor-core learn, fp32 accumulate; act + Adam fp32)" if args.precision == "tf32" else "f32"), "data": "synthetic",
             "config": {"workload": workload_name(args), "grid": [H, W], "worlds_total": n_worlds, "agents_per_world": n_avg,
                        "train_events_per_step": ev_avg, "parallelism": f"worlds sharded x{world_size}, brains replicated, "
                        "1 NCCL all-reduce of summed gradients per step" if world_size > 1 else "single GPU",

@@ -271,6 +271,24 @@ int rl_world_stats(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const int
                    int32_t* counter_dev, double* out_dev, void* stream);
 int rl_world_stats_scratch_doubles(const rl_world_cfg* cfg);   /* size of scratch_dev in doubles */
 
+
+/* Test hook: one-tile tcgen05 kind::tf32 GEMM  D[M,N] = A * B^T  on interleaved no-swizzle operand images
+ * (csrc/tc_tile.cuh).  a_mn / b_mn = 1: the operand image is stored k-rows x mn-columns (MN-major). */
+int rl_tc_gemm_test(const float* a_img, const float* b_img, float* d, int M, int N, int K, int a_mn, int b_mn, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Tensor-core path (tcgen05.mma kind::tf32, fp32 accumulation in TMEM) for the dueling brains.
+ * Same contract and outputs as rl_brain_learn; network products use 10-bit-mantissa operands
+ * (stated tolerance: tests/test_tc_gpu.py).  Weight images (`wimg`, rl_tc_wimg_floats() floats per network)
+ * are derived from the kernel-layout parameters with rl_brain_build_wimg after every parameter change.
+ * ---------------------------------------------------------------------------------------------- */
+int rl_tc_wimg_floats(void);
+int rl_brain_build_wimg(int32_t kind, const float* params, float* wimg, void* stream);
+int rl_brain_learn_tc(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                      const int32_t* sample_idx, const rl_learn_bufs* learn, const float* wimg_eval, const float* wimg_target,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

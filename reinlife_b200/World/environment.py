@@ -52,7 +52,8 @@ class Environment:
                  update_interval: int = 500, print_results: bool = True, static_families: bool = True,
                  interactive_results: bool = False, google_colab: bool = False, training: bool = True,
                  save: bool = False, pastel_colors: bool = False, limit_reproduction: bool = False,
-                 incentivize_killing: bool = True, *, n_worlds: int = 1, seed: int = 0, device=None, world_id0=None):
+                 incentivize_killing: bool = True, *, n_worlds: int = 1, seed: int = 0, device=None, world_id0=None,
+                 precision: str = "tf32"):
         self.width, self.height = width, height
         self.actions, self.entities = Actions, EntityTypes
         self.best_agents = []
@@ -100,6 +101,10 @@ class Environment:
                 torch.distributed.broadcast(b._dev.params, 0)
                 if b._dev.target is not None:
                     torch.distributed.broadcast(b._dev.target, 0)
+        # "tf32": train() events on the tensor cores (tcgen05 kind::tf32, fp32 accumulate); "fp32": CUDA-core FMA path
+        if precision not in ("tf32", "fp32"):
+            raise ValueError("precision must be 'tf32' or 'fp32'")
+        self.precision = precision
         self._grad_all = None
         from ..Helpers.tracker import Tracker
         self.tracker = Tracker(self, update_interval=update_interval, print_results=print_results)
@@ -179,8 +184,17 @@ class Environment:
                     continue
                 _lib.check(lib.rl_replay_sample(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
                                                 C.c_int32(b._dev.batch), C.c_uint64(w.t), C.c_void_p(b._dev.sample_idx.data_ptr()), st))
-                _lib.check(lib.rl_brain_learn(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
-                                              C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs), st))
+                if self.precision == "tf32":
+                    if b._dev.wimg_stale:
+                        b._dev.build_wimg(st)
+                        b._dev.wimg_stale = False
+                        self.gpu_launches += 2
+                    _lib.check(lib.rl_brain_learn_tc(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                                     C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs),
+                                                     C.c_void_p(b._dev.wimg_e.data_ptr()), C.c_void_p(b._dev.wimg_t.data_ptr()), st))
+                else:
+                    _lib.check(lib.rl_brain_learn(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                                  C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs), st))
                 self.gpu_launches += 4
             active = [g for g in trainable if on[g]]
             if self.dist and active:
@@ -192,10 +206,14 @@ class Environment:
                                                      C.c_int32(b._dev.batch), C.c_void_p(b._dev.sample_idx.data_ptr()),
                                                      C.c_void_p(b._dev.new_prio.data_ptr()), st))
                 self.gpu_launches += 3
-                if n_epi % int(b.soft_update_freq) == 0:          # PERD3QN.py:124-125, only if learn() was called
+                synced = n_epi % int(b.soft_update_freq) == 0
+                if synced:                                        # PERD3QN.py:124-125, only if learn() was called
                     cond = self.rows.total.data_ptr() + 4 * (g * _lib.N_ROW_KINDS + _lib.ROWS_STORE)
                     sync_target(b._dev, w, cond)
                     self.gpu_launches += 1
+                if self.precision == "tf32":                      # operand images follow the parameters
+                    b._dev.build_wimg(st, "both" if synced else "eval")
+                    self.gpu_launches += 2 if synced else 1
         self.gpu_launches += 3
 
     def _allreduce_grads(self, active):

@@ -29,6 +29,23 @@ class DeviceBrain:
         self.grad_scratch = None
         self.new_prio = self.loss = self.sample_idx = None
         self.learn_bufs = None
+        self.wimg_e = self.wimg_t = None          # tensor-core weight images (tf32 path)
+        self.wimg_stale = True
+
+    # -- tensor-core weight images -------------------------------------------------------------------
+    def build_wimg(self, stream_ptr, which="both"):
+        """Refresh the tcgen05 operand images from the kernel-layout parameters (after Adam / load / target sync)."""
+        if self.wimg_e is None:
+            n = self.lib.rl_tc_wimg_floats()
+            self.wimg_e = torch.zeros(n, device=self.device)
+            self.wimg_t = torch.zeros(n, device=self.device)
+        with torch.cuda.device(self.device):
+            if which in ("both", "eval"):
+                _lib.check(self.lib.rl_brain_build_wimg(C.c_int32(self.kind), C.c_void_p(self.params.data_ptr()),
+                                                        C.c_void_p(self.wimg_e.data_ptr()), stream_ptr))
+            if which in ("both", "target") and self.target is not None:
+                _lib.check(self.lib.rl_brain_build_wimg(C.c_int32(self.kind), C.c_void_p(self.target.data_ptr()),
+                                                        C.c_void_p(self.wimg_t.data_ptr()), stream_ptr))
 
     # -- state_dict round trip (reference key names) -----------------------------------------------
     def state_dict(self, target=False):
@@ -37,6 +54,7 @@ class DeviceBrain:
     def load_state_dict(self, sd, target=False):
         flat = torch.from_numpy(packing.pack(self.kind, sd)).to(self.device)
         (self.target if target else self.params).copy_(flat)
+        self.wimg_stale = True
 
     # -- learn buffers -----------------------------------------------------------------------------
     def alloc_learn(self, row_cap):

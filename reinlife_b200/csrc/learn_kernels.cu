@@ -315,6 +315,13 @@ int g_learn_grid = 0;
 
 }  // namespace
 
+int rl_learn_reduce(const rl_learn_bufs* learn, const int32_t* ev_total, void* stream) {
+    const int nt = n_train_of(learn->kind);
+    k_grad_reduce<<<(nt + 255) / 256, 256, 0, (cudaStream_t)stream>>>(learn->grad_scratch, rl_learn_grid(), nt, ev_total, learn->grad);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
 extern "C" {
 
 int rl_learn_grid(void) {
@@ -349,10 +356,7 @@ int rl_brain_learn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t ge
     cudaStream_t st = (cudaStream_t)stream;
     k_learn_dueling<<<P.n_cta, NT, LEARN_SMEM, st>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
-    const int nt = n_train_of(learn->kind);
-    k_grad_reduce<<<(nt + 255) / 256, 256, 0, st>>>(learn->grad_scratch, P.n_cta, nt, P.ev_total, learn->grad);
-    RL_CUDA_CHECK(cudaGetLastError());
-    return RL_OK;
+    return rl_learn_reduce(learn, P.ev_total, stream);
 }
 
 int rl_brain_adam(const rl_learn_bufs* learn, void* stream) {

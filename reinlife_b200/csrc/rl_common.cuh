@@ -10,6 +10,9 @@
 extern thread_local char g_rl_err[512];
 int rl_set_err(int code, const char* fmt, ...);
 
+// sums the per-CTA gradient slabs (fixed order) into learn->grad; grad[n_train] = *ev_total (learn_kernels.cu)
+int rl_learn_reduce(const rl_learn_bufs* learn, const int32_t* ev_total, void* stream);
+
 #define RL_CUDA_CHECK(expr)                                                                   \
     do {                                                                                      \
         cudaError_t _e = (expr);                                                              \

@@ -1,0 +1,517 @@
+// tc_kernels.cu -- PERD3QN / D3QN train() events on the 5th-gen tensor cores (tcgen05.mma kind::tf32, TMEM
+// accumulators, bulk-async weight streaming), warp-specialised: warp 8 = weight-stream producer + MMA issuer,
+// warps 0-7 = gather / TMEM epilogues / small SIMT pieces.  Same math and same outputs as k_learn_dueling
+// (learn_kernels.cu, fp32 FMA), which stays as the tight-tolerance reference path.
+//
+// One event (64 rows) per CTA iteration.  All seven big GEMMs of an event run as K-major tf32 MMAs:
+//   target/eval L1  [64x160]x[160x128],  L2 [64x128]x[128x256],  head [64x256]x[256x16],
+//   dH2 = dOut Wh^T [64x16]x[16x256],    dH1 = dH2 W2 [64x256]x[256x128],
+//   dW2 += H1^T dH2 (M=128: A = H1^T image, B = dH2^T image, K = 64 rows), accumulated in TMEM across ALL events
+//   of the CTA and flushed once;  dW1^T = dH1^T X (M=128, N=160), flushed per event.
+// tf32 MN-major operands read back as zeros on this part with the no-swizzle layouts (tests/test_tc_gpu.py pins
+// the K-major conventions), so transposed operand images are written explicitly by the epilogues.
+#include "tc_tile.cuh"
+#include "models.cuh"
+
+namespace {
+
+using namespace tc;
+using mlp::mbar_init; using mlp::mbar_wait; using mlp::fence_mbar_init; using mlp::fence_proxy_async; using mlp::bulk_load;
+
+constexpr int R = 64;
+constexpr int NEPI = 256;                // epilogue threads (warps 0-7)
+constexpr int NTHREADS = NEPI + 32;      // + producer warp
+constexpr int NS = 4;                    // weight-chunk stages
+constexpr int CHUNK_F = 4096;            // floats per chunk (16 KB)
+
+// ---- weight image buffer (per network), in chunks of 16 KB ----
+constexpr int WI_W1 = 0;     // 5 chunks [128 n][32 k]   B of L1:   n = k1, k = kx
+constexpr int WI_W2K = 5;    // 8 chunks [256 n][16 k]   B of L2:   n = n2, k = k1
+constexpr int WI_WH = 13;    // 1 chunk  [16 n][256 k]   B of head: n = j,  k = n2
+constexpr int WI_WHT = 14;   // 1 chunk  [256 n][16 k]   B of dH2:  n = n2, k = j
+constexpr int WI_W2T = 15;   // 8 chunks [128 n][32 k]   B of dH1:  n = k1, k = n2
+constexpr int WI_CHUNKS = 23;
+
+// chunk schedule of one event: (net, chunk).  net 0 = target, 1 = eval
+constexpr int SCHED_N = 37;
+__device__ __forceinline__ void sched_entry(int i, int& net, int& chunk) {
+    if (i < 14) { net = 0; chunk = i; }                 // target: W1[5], W2K[8], WH
+    else if (i < 29) { net = 1; chunk = i - 14; }       // eval:   W1[5], W2K[8], WH, WHT
+    else { net = 1; chunk = WI_W2T + (i - 29); }        // eval:   W2T[8]
+}
+
+struct TcLearnParams {
+    rl_world_cfg cfg;
+    const int32_t* ev_rows;
+    const int32_t* ev_total;
+    rl_replay_bufs rp;
+    const int32_t* sample_idx;
+    rl_learn_bufs lb;
+    const float* wimg_e;
+    const float* wimg_t;
+};
+
+// ---- shared memory carve-up (floats).  Region reuse over one event:
+//   sX  : X' (target) -> X (eval) -> H1^T (eval, written by the L1 epilogue once the L1 MMAs are done) -> dH1^T
+//   sH1 : H1 (target) -> H1 (eval) -> dH2^T half buffer [128][64]
+//   sH2 : H2 (target) -> H2 (eval) -> dH2 -> X^T [160][64] (after the dH1 MMAs)
+constexpr int SM_X = 0;                          // 64x160                                10240
+constexpr int SM_H1 = SM_X + 10240;              // [64][128]                              8192
+constexpr int SM_H2 = SM_H1 + 8192;              // [64][256]                             16384
+constexpr int SM_STAGE = SM_H2 + 16384;          // NS x 4096
+constexpr int SM_DOUT = SM_STAGE + NS * CHUNK_F; // dOut image [64][16] (K-major A)       1024
+constexpr int SM_OUTH = SM_DOUT + 1024;          // head outputs [64][16]                 1024
+constexpr int SM_DPL = SM_OUTH + 1024;           // dOut plain [64][12]                    768
+constexpr int SM_SMALL = SM_DPL + 768;           // rew, dn, nq, gb [4][64] + red[32] + (b1[128] b2[256] bh[16]) x 2 nets
+constexpr int SM_SMALL_N = 4 * 64 + 32 + 2 * (128 + 256 + 16);
+constexpr int SM_INT = SM_SMALL + SM_SMALL_N;    // idx[64], act[64]
+constexpr int SM_FLOATS = SM_INT + 128;
+constexpr size_t TC_SMEM = sizeof(float) * SM_FLOATS + 8 * (2 * NS + 2) + 16;
+static_assert(TC_SMEM <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ float epi_sum(float v, float* red) {     // sum over the 256 epilogue threads
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    epi_bar();
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r += red[i];
+    epi_bar();
+    return r;
+}
+
+// gather 64 rows of 160 floats into an interleaved image (TRANSPOSED = false: [64][160]; true: [160][64])
+template <bool TRANSPOSED>
+__device__ __forceinline__ void gather_img(float* img, const float* __restrict__ src, const int* ids) {
+    // lane -> (row within an 8-row group, 4 consecutive 16-byte chunks): conflict-free stores for the plain image
+    for (int v = threadIdx.x; v < R * 40; v += NEPI) {
+        const int rr = v & 7, cc = (v >> 3) & 3, blk = v >> 5;         // blk: 0..79 -> (row group 0..7, chunk group 0..9)
+        const int rg = blk / 10, cg = blk - rg * 10;
+        const int r = rg * 8 + rr, c4 = cg * 4 + cc;
+        const float4 x = __ldg(reinterpret_cast<const float4*>(src + (size_t)ids[r] * RL_K1) + c4);
+        if (!TRANSPOSED) {
+            *reinterpret_cast<float4*>(img + img_off(r, c4 * 4, RL_K1)) = make_float4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
+        } else {
+            img[img_off(c4 * 4 + 0, r, R)] = to_tf32(x.x); img[img_off(c4 * 4 + 1, r, R)] = to_tf32(x.y);
+            img[img_off(c4 * 4 + 2, r, R)] = to_tf32(x.z); img[img_off(c4 * 4 + 3, r, R)] = to_tf32(x.w);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnParams P) {
+    using L = Layout<RL_MODEL_DUELING>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* sm = reinterpret_cast<float*>(smem_raw);
+    float* sX = sm + SM_X; float* sH1 = sm + SM_H1; float* sH2 = sm + SM_H2;
+    float* sH1T = sX;          // H1^T / dH1^T live in the X region once the eval L1 MMAs are done
+    float* sXT = sH2;          // X^T lives in the dH2 region once the dH1 MMAs are done
+    float* sStage = sm + SM_STAGE; float* sDout = sm + SM_DOUT; float* sOuth = sm + SM_OUTH; float* sDpl = sm + SM_DPL;
+    float* rew = sm + SM_SMALL; float* dn = rew + 64; float* nq = dn + 64; float* gb = nq + 64; float* red = gb + 64;
+    float* bias_t = red + 32;                 // b1[128] b2[256] bh[16] of the target net
+    float* bias_e = bias_t + 400;             // same for the eval net
+    int* idx = reinterpret_cast<int*>(sm + SM_INT); int* act = idx + 64;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_FLOATS);
+    uint64_t* full = bars; uint64_t* empty = bars + NS; uint64_t* done = bars + 2 * NS; uint64_t* ready = done + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* Pe = P.lb.params; const float* Pt = P.lb.target;
+    float* G = P.lb.grad_scratch + (size_t)blockIdx.x * L::N_TRAIN;
+    const int total = *P.ev_total;
+    const int n_my = total > (int)blockIdx.x ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1); mbar_init(ready, 1);
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x < NEPI) {
+        for (int i = threadIdx.x; i < 400; i += NEPI) {
+            const int o = i < 128 ? L::OFF_B1 + i : i < 384 ? L::OFF_B2 + (i - 128) : L::OFF_BH + (i - 384);
+            const bool ok = i < 384 + 9;
+            bias_t[i] = ok ? Pt[o] : 0.f; bias_e[i] = ok ? Pe[o] : 0.f;
+        }
+        for (int i = threadIdx.x; i < L::N_TRAIN / 4; i += NEPI) reinterpret_cast<float4*>(G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t T_WORK = tmem, T_DW2 = tmem + 256;
+    const int S = P.cfg.slot_cap, cap = P.rp.capacity;
+
+    if (warp == 8) {
+        // =================================== producer + MMA issuer (one thread) ===================================
+        if (lane == 0) {
+            uint32_t produced = 0, consumed = 0, stage_no = 0;
+            const uint32_t n_chunks = (uint32_t)n_my * SCHED_N;
+            auto produce = [&]() {
+                while (produced < n_chunks && produced < consumed + (NS - 1)) {
+                    const uint32_t slot = produced % NS;
+                    if (produced >= NS) mbar_wait(&empty[slot], ((produced / NS) - 1) & 1);
+                    int net, ch; sched_entry(produced % SCHED_N, net, ch);
+                    bulk_load(sStage + slot * CHUNK_F, (net ? P.wimg_e : P.wimg_t) + (size_t)ch * CHUNK_F, CHUNK_F * 4, &full[slot]);
+                    ++produced;
+                }
+            };
+            // one GEMM stage whose B operand streams through the chunk ring
+            //   a_base: smem address of the A image, a_k: its width; kc = k columns per chunk; n = N; m = M
+            auto stream_gemm = [&](uint32_t d_tmem, uint32_t a_base, int a_k, int a_col0, int nch, int kc, int m, int n) {
+                const uint32_t idesc = make_idesc(m, n, 0, 0);
+                for (int c = 0; c < nch; ++c) {
+                    const uint32_t slot = consumed % NS;
+                    mbar_wait(&full[slot], (consumed / NS) & 1);
+                    fence_after();
+                    const uint32_t b_base = smem_u32(sStage + slot * CHUNK_F);
+                    for (int ks = 0; ks < kc / 8; ++ks) {
+                        const int kcol = a_col0 + c * kc + ks * 8;
+                        mma_tf32(d_tmem, desc_kmajor(a_base + (kcol >> 2) * 128, a_k), desc_kmajor(b_base + ks * 256, kc), idesc,
+                                 (c | ks) != 0);
+                    }
+                    mma_commit(&empty[slot]);
+                    ++consumed;
+                    produce();
+                }
+            };
+            auto wait_ready = [&]() { mbar_wait(ready, stage_no & 1); fence_after(); };
+            auto signal_done = [&]() { mma_commit(done); ++stage_no; };
+            produce();
+            for (int it = 0; it < n_my; ++it) {
+                const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH1T = smem_u32(sH1T), aH2 = smem_u32(sH2), aD = smem_u32(sDout), aXT = smem_u32(sXT);
+                for (int net = 0; net < 2; ++net) {
+                    wait_ready(); stream_gemm(T_WORK, aX, RL_K1, 0, 5, 32, 64, 128); signal_done();      // L1
+                    wait_ready(); stream_gemm(T_WORK, aH1, 128, 0, 8, 16, 64, 256); signal_done();       // L2
+                    wait_ready(); stream_gemm(T_WORK, aH2, 256, 0, 1, 256, 64, 16); signal_done();       // head
+                }
+                wait_ready(); stream_gemm(T_WORK, aD, 16, 0, 1, 16, 64, 256); signal_done();             // dH2 (pre-mask)
+                for (int half = 0; half < 2; ++half) {                                                      // dW2 halves
+                    wait_ready();
+                    const uint32_t idesc = make_idesc(128, 128, 0, 0);
+                    for (int ks = 0; ks < 8; ++ks)
+                        mma_tf32(T_DW2 + half * 128, desc_kmajor(aH1T + ks * 256, R), desc_kmajor(aH1 + ks * 256, R), idesc, (it | ks) != 0);
+                    if (half == 0) signal_done();
+                }
+                stream_gemm(T_WORK, aH2, 256, 0, 8, 32, 64, 128); signal_done();                         // dH1 (after dW2 half 1)
+                wait_ready();
+                {
+                    const uint32_t idesc = make_idesc(128, 160, 0, 0);                                     // dW1^T
+                    for (int ks = 0; ks < 8; ++ks)
+                        mma_tf32(T_WORK, desc_kmajor(aH1T + ks * 256, R), desc_kmajor(aXT + ks * 256, R), idesc, ks != 0);
+                }
+                signal_done();
+            }
+            wait_ready();      // final hand-shake: epilogue has flushed dW2
+        }
+    } else {
+        // =================================== epilogue warps ===================================
+        uint32_t stage_no = 0;
+        const int q = warp & 3, half = warp >> 2;
+        const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+        const int row = q * 16 + lane;                 // M = 64 accumulators: rows 16q+i in lanes 32q+i (i < 16)
+        const bool rvalid = lane < 16;
+        auto signal_ready = [&]() {
+            fence_proxy_async();
+            fence_before();
+            epi_bar();
+            if (threadIdx.x == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(ready)) : "memory");
+        };
+        auto wait_done = [&]() { mbar_wait(done, stage_no & 1); ++stage_no; fence_after(); };
+
+        for (int it = 0; it < n_my; ++it) {
+            const int e = blockIdx.x + it * gridDim.x;
+            const int w = P.ev_rows[e] / S;
+            const size_t ring = (size_t)w * cap;
+            if (threadIdx.x < R) {
+                const int i = P.sample_idx[(size_t)e * R + threadIdx.x];
+                idx[threadIdx.x] = i;
+                act[threadIdx.x] = P.rp.action[ring + i];
+                rew[threadIdx.x] = P.rp.reward[ring + i];
+                dn[threadIdx.x] = (float)P.rp.done[ring + i];
+            }
+            epi_bar();
+            float mean_e = 0.f;
+            for (int net = 0; net < 2; ++net) {
+                const float* bias = net ? bias_e : bias_t;
+                gather_img<false>(sX, (net ? P.rp.obs : P.rp.next_obs) + ring * RL_K1, idx);
+                signal_ready();
+                // ---- L1 epilogue: H1 = relu(D + b1) -> H1 image (+ H1^T image for the eval net) ----
+                wait_done();
+                for (int cb = 0; cb < 2; ++cb) {
+                    const int c0 = half * 64 + cb * 32;
+                    float v[32];
+                    tmem_ld32(T_WORK + t_lane + c0, v);
+                    tmem_wait_ld();
+                    if (rvalid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = to_tf32(fmaxf(v[j] + bias[c0 + j], 0.f));
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            *reinterpret_cast<float4*>(sH1 + img_off(row, c0 + j4 * 4, 128)) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                        if (net) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) sH1T[img_off(c0 + j, row, R)] = v[j];
+                        }
+                    }
+                }
+                signal_ready();
+                // ---- L2 epilogue: H2 = relu(D + b2) -> H2 image ----
+                wait_done();
+                for (int cb = 0; cb < 4; ++cb) {
+                    const int c0 = half * 128 + cb * 32;
+                    float v[32];
+                    tmem_ld32(T_WORK + t_lane + c0, v);
+                    tmem_wait_ld();
+                    if (rvalid) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            *reinterpret_cast<float4*>(sH2 + img_off(row, c0 + j4 * 4, 256)) =
+                                make_float4(to_tf32(fmaxf(v[j4 * 4] + bias[128 + c0 + j4 * 4], 0.f)), to_tf32(fmaxf(v[j4 * 4 + 1] + bias[128 + c0 + j4 * 4 + 1], 0.f)),
+                                            to_tf32(fmaxf(v[j4 * 4 + 2] + bias[128 + c0 + j4 * 4 + 2], 0.f)), to_tf32(fmaxf(v[j4 * 4 + 3] + bias[128 + c0 + j4 * 4 + 3], 0.f)));
+                    }
+                }
+                signal_ready();
+                // ---- head epilogue: [A(8) | V] + bh ----
+                wait_done();
+                if (half == 0) {
+                    float v[16];
+                    tmem_ld16(T_WORK + t_lane, v);
+                    tmem_wait_ld();
+                    if (rvalid) {
+#pragma unroll
+                        for (int j = 0; j < 9; ++j) sOuth[row * 16 + j] = v[j] + bias[384 + j];
+                    }
+                }
+                fence_before();
+                epi_bar();
+                float s = 0.f;
+                for (int o = threadIdx.x; o < R * 8; o += NEPI) s += sOuth[(o >> 3) * 16 + (o & 7)];
+                const float mean = epi_sum(s, red) * (1.0f / (8 * R));
+                if (net == 0) {
+                    if (threadIdx.x < R) {
+                        const float* o = sOuth + threadIdx.x * 16;
+                        float mx = o[0];
+#pragma unroll
+                        for (int j = 1; j < 8; ++j) mx = fmaxf(mx, o[j]);
+                        nq[threadIdx.x] = mx + o[8] - mean;
+                    }
+                    epi_bar();
+                } else {
+                    mean_e = mean;
+                }
+            }
+            // ---- TD target, loss, priorities, dOut ----
+            {
+                float g = 0.f, sq = 0.f;
+                if (threadIdx.x < R) {
+                    const int b = threadIdx.x;
+                    const float qa = sOuth[b * 16 + act[b]] + sOuth[b * 16 + 8] - mean_e;
+                    const float y = rew[b] + P.lb.gamma * (1.0f - dn[b]) * nq[b];
+                    const float diff = qa - y;
+                    g = 2.0f * diff * (1.0f / R);
+                    sq = diff * diff;
+                    gb[b] = g;
+                    P.lb.new_prio[(size_t)e * R + b] = fabsf(nq[b] - qa);
+                }
+                const float gsum = epi_sum(g, red);
+                const float loss = epi_sum(sq, red) * (1.0f / R);
+                if (threadIdx.x == 0) P.lb.loss[e] = loss;
+                const float shift = gsum * (1.0f / (8 * R));
+                for (int o = threadIdx.x; o < R * 16; o += NEPI) {
+                    const int b = o >> 4, j = o & 15;
+                    const float d = j < 8 ? ((j == act[b] ? gb[b] : 0.f) - shift) : (j == 8 ? gb[b] : 0.f);
+                    sDout[img_off(b, j, 16)] = to_tf32(d);
+                    if (j < 12) sDpl[b * 12 + j] = d;
+                }
+                epi_bar();
+            }
+            // ---- head gradients (SIMT): dWh[k][j] += sum_b H2[b][k] dOut[b][j]; dbh ----
+            {
+                const int k = threadIdx.x;
+                float acc[9];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) acc[j] = 0.f;
+                for (int i = 0; i < R; ++i) {
+                    const int b = (i + (k >> 2)) & 63;                      // rotation: conflict-free image reads
+                    const float h = sH2[img_off(b, k, 256)];
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) acc[j] = fmaf(h, sDpl[b * 12 + j], acc[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 9; ++j) G[L::OFF_WH + k * 9 + j] += acc[j];
+                if (threadIdx.x < 9) {
+                    float s = 0.f;
+                    for (int b = 0; b < R; ++b) s += sDpl[b * 12 + threadIdx.x];
+                    G[L::OFF_BH + threadIdx.x] += s;
+                }
+            }
+            signal_ready();                                    // dOut image ready -> dH2 MMA
+            // ---- dH2 epilogue: mask by H2 > 0, in place; first half transposed into the (dead) H1 region ----
+            wait_done();
+            float* sDT = sH1;                                   // dH2^T half buffer [128][64]
+            for (int cb = 0; cb < 4; ++cb) {
+                const int c0 = half * 128 + cb * 32;
+                float v[32];
+                tmem_ld32(T_WORK + t_lane + c0, v);
+                tmem_wait_ld();
+                if (rvalid) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float4* p = reinterpret_cast<float4*>(sH2 + img_off(row, c0 + j4 * 4, 256));
+                        const float4 h = *p;
+                        v[j4 * 4 + 0] = h.x > 0.f ? to_tf32(v[j4 * 4 + 0]) : 0.f; v[j4 * 4 + 1] = h.y > 0.f ? to_tf32(v[j4 * 4 + 1]) : 0.f;
+                        v[j4 * 4 + 2] = h.z > 0.f ? to_tf32(v[j4 * 4 + 2]) : 0.f; v[j4 * 4 + 3] = h.w > 0.f ? to_tf32(v[j4 * 4 + 3]) : 0.f;
+                        *p = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                    }
+                    if (half == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sDT[img_off(c0 + j, row, R)] = v[j];
+                    }
+                }
+            }
+            fence_before();
+            epi_bar();
+            // db2[n] += sum_b dH2[b][n]
+            {
+                const int n = threadIdx.x;
+                float s = 0.f;
+                for (int i = 0; i < R; ++i) { const int b = (i + (n >> 2)) & 63; s += sH2[img_off(b, n, 256)]; }
+                G[L::OFF_B2 + n] += s;
+            }
+            signal_ready();                                    // dW2 half 0 may run
+            wait_done();                                       // dW2 half 0 finished reading the half buffer
+            for (int o = threadIdx.x; o < R * 128; o += NEPI) {   // second half: transpose from the dH2 image
+                const int b = o & 63, c = o >> 6;
+                sDT[img_off(c, b, R)] = sH2[img_off(b, 128 + c, 256)];
+            }
+            signal_ready();                                    // dW2 half 1 + dH1 may run
+            // ---- dH1 epilogue: mask by H1 > 0 (from H1^T), write dH1^T in place of H1^T ----
+            wait_done();
+            for (int cb = 0; cb < 2; ++cb) {
+                const int c0 = half * 64 + cb * 32;
+                float v[32];
+                tmem_ld32(T_WORK + t_lane + c0, v);
+                tmem_wait_ld();
+                if (rvalid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float* p = sH1T + img_off(c0 + j, row, R);
+                        *p = *p > 0.f ? to_tf32(v[j]) : 0.f;
+                    }
+                }
+            }
+            fence_before();
+            epi_bar();
+            if (threadIdx.x < 128) {                           // db1[k1] += sum_b dH1^T[k1][b]
+                const int k1 = threadIdx.x;
+                float s = 0.f;
+                for (int i = 0; i < R; ++i) { const int b = (i + ((k1 >> 3) & 3)) & 63; s += sH1T[img_off(k1, b, R)]; }
+                G[L::OFF_B1 + k1] += s;
+            }
+            gather_img<true>(sXT, P.rp.obs + ring * RL_K1, idx);  // X^T image for dW1^T (dH2 region is dead: dH1 MMAs are done)
+            signal_ready();
+            // ---- dW1^T epilogue: G[W1t][kx][k1] += D[k1][kx] ----
+            wait_done();
+            {
+                const int k1 = q * 32 + lane;                   // M = 128 accumulator: row = lane
+                for (int cb = 0; cb < 5; ++cb) {
+                    if ((cb & 1) != half && cb < 4) continue;    // split the 5 column blocks over the two warp halves
+                    if (cb == 4 && half != 0) continue;
+                    float v[32];
+                    tmem_ld32(T_WORK + ((uint32_t)(q * 32) << 16) + cb * 32, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) G[L::OFF_W1T + (cb * 32 + j) * 128 + k1] += v[j];
+                }
+            }
+            fence_before();
+            epi_bar();
+        }
+        // ---- flush the TMEM-resident dW2 accumulator once ----
+        if (n_my > 0) {
+            // all MMAs of the last event completed (dW1^T's `done` was the last commit)
+            const int k1 = q * 32 + lane;
+            for (int cb = 0; cb < 4; ++cb) {
+                const int c0 = half * 128 + cb * 32;
+                float v[32];
+                tmem_ld32(T_DW2 + ((uint32_t)(q * 32) << 16) + c0, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)
+                    *reinterpret_cast<float4*>(G + L::OFF_W2T + k1 * 256 + c0 + j4 * 4) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+            }
+        }
+        signal_ready();
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+// ---- weight images (tf32-rounded) from the kernel-layout parameter buffer ----
+__global__ void k_build_wimg_dueling(const float* __restrict__ p, float* __restrict__ wimg) {
+    using L = Layout<RL_MODEL_DUELING>;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // W1: n = k1 (128), k = kx (160)
+    if (i < 128 * 160) {
+        const int n = i / 160, k = i - n * 160;
+        wimg[(WI_W1 + k / 32) * CHUNK_F + img_off(n, k % 32, 32)] = to_tf32(p[L::OFF_W1T + k * 128 + n]);
+    }
+    // W2: W2t[k1][n2]
+    if (i < 128 * 256) {
+        const int k1 = i / 256, n2 = i - k1 * 256;
+        const float v = to_tf32(p[L::OFF_W2T + i]);
+        wimg[(WI_W2K + k1 / 16) * CHUNK_F + img_off(n2, k1 % 16, 16)] = v;      // B of L2: n = n2, k = k1
+        wimg[(WI_W2T + n2 / 32) * CHUNK_F + img_off(k1, n2 % 32, 32)] = v;      // B of dH1: n = k1, k = n2
+    }
+    // head: Wh[n2][j], j < 9 (zero padded to 16)
+    if (i < 256 * 16) {
+        const int n2 = i / 16, j = i - n2 * 16;
+        const float v = j < 9 ? to_tf32(p[L::OFF_WH + n2 * 9 + j]) : 0.f;
+        wimg[WI_WH * CHUNK_F + img_off(j, n2, 256)] = v;                        // B of head: n = j, k = n2
+        wimg[WI_WHT * CHUNK_F + img_off(n2, j, 16)] = v;                        // B of dH2: n = n2, k = j
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int rl_tc_wimg_floats(void) { return WI_CHUNKS * CHUNK_F; }
+
+int rl_brain_build_wimg(int32_t kind, const float* params, float* wimg, void* stream) {
+    RL_ARG_CHECK(params && wimg);
+    if (kind != RL_MODEL_DUELING) return rl_set_err(RL_ERR_UNSUPPORTED, "tensor-core weight images: dueling networks only");
+    k_build_wimg_dueling<<<(128 * 256 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(params, wimg);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_brain_learn_tc(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                      const int32_t* sample_idx, const rl_learn_bufs* learn, const float* wimg_eval, const float* wimg_target,
+                      void* stream) {
+    RL_ARG_CHECK(cfg && rows && replay && sample_idx && learn && wimg_eval && wimg_target);
+    RL_ARG_CHECK(gene >= 0 && gene < cfg->n_genes && cfg->obs_ld == RL_K1 && learn->batch == R);
+    RL_ARG_CHECK(learn->params && learn->target && learn->grad_scratch && learn->grad && learn->new_prio && learn->loss);
+    if (learn->kind != RL_MODEL_DUELING) return rl_set_err(RL_ERR_UNSUPPORTED, "rl_brain_learn_tc: dueling networks only");
+    TcLearnParams P;
+    P.cfg = *cfg;
+    P.ev_rows = rows->rows + (size_t)(gene * RL_N_ROW_KINDS + RL_ROWS_EVENT) * rows->row_cap;
+    P.ev_total = rows->total + gene * RL_N_ROW_KINDS + RL_ROWS_EVENT;
+    P.rp = *replay; P.sample_idx = sample_idx; P.lb = *learn; P.wimg_e = wimg_eval; P.wimg_t = wimg_target;
+    static bool attr = false;
+    if (!attr) {
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dueling_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        attr = true;
+    }
+    const int n_cta = rl_learn_grid();
+    cudaStream_t st = (cudaStream_t)stream;
+    k_learn_dueling_tc<<<n_cta, NTHREADS, TC_SMEM, st>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return rl_learn_reduce(learn, P.ev_total, (void*)st);
+}
+
+}  // extern "C"

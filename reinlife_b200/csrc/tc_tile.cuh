@@ -1,0 +1,96 @@
+// tc_tile.cuh -- tcgen05 (5th-gen tensor core) building blocks for the brain kernels, sm_100a only.
+//
+// Operand format: kind::tf32 (fp32 storage, 10-bit mantissa products, fp32 accumulation in TMEM).
+// Every shared-memory operand -- activations AND weights -- is kept in ONE physical layout, the
+// no-swizzle "interleaved core matrix" image:   8 rows x 16 bytes core matrices,
+//     off(r, c) = (r/8) * (K*8) + (c/4) * 32 + (r%8) * 4 + (c%4)          [floats, K = image width]
+// Because a core matrix is 8 x 4 fp32 in both directions, the SAME image is a K-major operand
+// (descriptor LBO = 128 B between k-chunks, SBO = row-group stride) and an MN-major operand
+// (SBO = 128 B between mn-chunks, LBO = row-group stride).  That lets H1 serve as A of the next layer and as
+// A^T of the weight-gradient GEMM, and W2 as B of the forward and B^T of the backward, with no transposes.
+// Descriptor / instruction-descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (CUTLASS, vendored
+// headers consulted for the encodings only).
+#pragma once
+#include "mlp_tile.cuh"
+
+namespace tc {
+
+using mlp::smem_u32;
+
+// float offset of element (r, c) in an interleaved image of width K
+__host__ __device__ __forceinline__ int img_off(int r, int c, int K) { return (r >> 3) * (K * 8) + (c >> 2) * 32 + (r & 7) * 4 + (c & 3); }
+
+// ---- descriptors -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);   // version = 1 (Blackwell), SWIZZLE_NONE
+}
+// K-major operand inside an image of width K (bytes): LBO = 128 (next 4-column chunk), SBO = K*32 (next 8 rows)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr, int K) { return make_desc(saddr, 128u, (uint32_t)K * 32u); }
+// MN-major operand: SBO = 128 (next 4 mn-elements), LBO = K*32 (next 8 k-rows)
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, int K) { return make_desc(saddr, (uint32_t)K * 32u, 128u); }
+
+// instruction descriptor, kind::tf32, fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- tcgen05 wrappers ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {   // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]; one thread issues
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives once all MMAs issued so far by this thread have completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread = lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float to_tf32(float x) {   // round-to-nearest tf32 (the MMA itself would truncate)
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+}  // namespace tc
