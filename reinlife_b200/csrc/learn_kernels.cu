@@ -256,11 +256,13 @@ __global__ void __launch_bounds__(NT, 1) k_learn_dueling(const LearnParams P) {
 
 // grad[p] = sum over CTA slabs (fixed order); grad[n_train] = number of events
 __global__ void k_grad_reduce(const float* __restrict__ scratch, int n_cta, int n_train, const int32_t* ev_total,
-                              float* __restrict__ grad) {
+                              float* __restrict__ grad, int w1_rowmajor, int n1) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < n_train) {
+        int src = p;
+        if (w1_rowmajor && p < RL_K1 * n1) { const int kx = p / n1, k1 = p - kx * n1; src = k1 * RL_K1 + kx; }
         float s = 0.f;
-        for (int c = 0; c < n_cta; ++c) s += scratch[(size_t)c * n_train + p];
+        for (int c = 0; c < n_cta; ++c) s += scratch[(size_t)c * n_train + src];
         grad[p] = s;
     }
     if (p == 0) grad[n_train] = (float)(*ev_total);
@@ -315,9 +317,11 @@ int g_learn_grid = 0;
 
 }  // namespace
 
-int rl_learn_reduce(const rl_learn_bufs* learn, const int32_t* ev_total, void* stream) {
+int rl_learn_reduce(const rl_learn_bufs* learn, const int32_t* ev_total, int w1_rowmajor, void* stream) {
     const int nt = n_train_of(learn->kind);
-    k_grad_reduce<<<(nt + 255) / 256, 256, 0, (cudaStream_t)stream>>>(learn->grad_scratch, rl_learn_grid(), nt, ev_total, learn->grad);
+    const int n1 = learn->kind == RL_MODEL_PPO ? 256 : 128;
+    k_grad_reduce<<<(nt + 255) / 256, 256, 0, (cudaStream_t)stream>>>(learn->grad_scratch, rl_learn_grid(), nt, ev_total, learn->grad,
+                                                                      w1_rowmajor, n1);
     RL_CUDA_CHECK(cudaGetLastError());
     return RL_OK;
 }
@@ -356,7 +360,7 @@ int rl_brain_learn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t ge
     cudaStream_t st = (cudaStream_t)stream;
     k_learn_dueling<<<P.n_cta, NT, LEARN_SMEM, st>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
-    return rl_learn_reduce(learn, P.ev_total, stream);
+    return rl_learn_reduce(learn, P.ev_total, 0, stream);
 }
 
 int rl_brain_adam(const rl_learn_bufs* learn, void* stream) {

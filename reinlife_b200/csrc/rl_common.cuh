@@ -11,7 +11,8 @@ extern thread_local char g_rl_err[512];
 int rl_set_err(int code, const char* fmt, ...);
 
 // sums the per-CTA gradient slabs (fixed order) into learn->grad; grad[n_train] = *ev_total (learn_kernels.cu)
-int rl_learn_reduce(const rl_learn_bufs* learn, const int32_t* ev_total, void* stream);
+// w1_rowmajor = 1: the slabs hold the first-layer gradient as [N1][160] (tensor-core path) instead of W1t [160][N1]
+int rl_learn_reduce(const rl_learn_bufs* learn, const int32_t* ev_total, int w1_rowmajor, void* stream);
 
 #define RL_CUDA_CHECK(expr)                                                                   \
     do {                                                                                      \

@@ -10,6 +10,7 @@
 //   of the CTA and flushed once;  dW1^T = dH1^T X (M=128, N=160), flushed per event.
 // tf32 MN-major operands read back as zeros on this part with the no-swizzle layouts (tests/test_tc_gpu.py pins
 // the K-major conventions), so transposed operand images are written explicitly by the epilogues.
+#include <stdlib.h>
 #include "tc_tile.cuh"
 #include "models.cuh"
 
@@ -49,6 +50,7 @@ struct TcLearnParams {
     rl_learn_bufs lb;
     const float* wimg_e;
     const float* wimg_t;
+    long long* trace;      // debug: clock64 stamps of CTA 0 (RL_TC_TRACE=1), else nullptr
 };
 
 // ---- shared memory carve-up (floats).  Region reuse over one event:
@@ -56,8 +58,8 @@ struct TcLearnParams {
 //   sH1 : H1 (target) -> H1 (eval) -> dH2^T half buffer [128][64]
 //   sH2 : H2 (target) -> H2 (eval) -> dH2 -> X^T [160][64] (after the dH1 MMAs)
 constexpr int SM_X = 0;                          // 64x160                                10240
-constexpr int SM_H1 = SM_X + 10240;              // [64][128]                              8192
-constexpr int SM_H2 = SM_H1 + 8192;              // [64][256]                             16384
+constexpr int SM_H1 = SM_X + 10240;              // [64][128]                              9216
+constexpr int SM_H2 = SM_H1 + 9216;              // [64][256]                             16384   (H1 region: 36 KB for the padded dH2^T half image)
 constexpr int SM_STAGE = SM_H2 + 16384;          // NS x 4096
 constexpr int SM_DOUT = SM_STAGE + NS * CHUNK_F; // dOut image [64][16] (K-major A)       1024
 constexpr int SM_OUTH = SM_DOUT + 1024;          // head outputs [64][16]                 1024
@@ -68,6 +70,21 @@ constexpr int SM_INT = SM_SMALL + SM_SMALL_N;    // idx[64], act[64]
 constexpr int SM_FLOATS = SM_INT + 128;
 constexpr size_t TC_SMEM = sizeof(float) * SM_FLOATS + 8 * (2 * NS + 2) + 16;
 static_assert(TC_SMEM <= 227 * 1024, "shared memory budget");
+
+// fire-and-forget adds into the CTA-private gradient slab (no return value -> no scoreboard stall, no contention)
+__device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Transposed operand images ([feature rows][64 batch columns]) use a padded chunk stride: LBO = 144 B instead of 128 B.
+// A transposed store writes one feature row for 16 consecutive batch columns; with the pad the four 16-byte chunks land
+// in different banks (conflict-free) -- the descriptor's LBO/SBO make the padding invisible to the tensor core.
+constexpr int TP_CH = 36;                  // floats between consecutive 4-column chunks
+constexpr int TP_RG = 16 * TP_CH;          // floats per 8-row group (64 columns = 16 chunks)
+__device__ __forceinline__ int timg_off(int r, int c) { return (r >> 3) * TP_RG + (c >> 2) * TP_CH + (r & 7) * 4 + (c & 3); }
+__device__ __forceinline__ uint64_t desc_timg(uint32_t saddr) { return make_desc(saddr, TP_CH * 4, TP_RG * 4); }
+constexpr int TP_KSTEP = 2 * TP_CH * 4;    // bytes per MMA k-step (8 batch columns = 2 chunks)
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -83,21 +100,44 @@ __device__ __forceinline__ float epi_sum(float v, float* red) {     // sum over 
     return r;
 }
 
-// gather 64 rows of 160 floats into an interleaved image (TRANSPOSED = false: [64][160]; true: [160][64])
+// gather 64 rows of 160 floats into an interleaved image (TRANSPOSED = false: [64][160]; true: [160][64]).
+// The rows come from the replay ring in HBM: all ten 16-byte loads of a thread are issued before the first store,
+// so a gather costs one DRAM round trip instead of ten.
 template <bool TRANSPOSED>
 __device__ __forceinline__ void gather_img(float* img, const float* __restrict__ src, const int* ids) {
     // lane -> (row within an 8-row group, 4 consecutive 16-byte chunks): conflict-free stores for the plain image
-    for (int v = threadIdx.x; v < R * 40; v += NEPI) {
+    float4 x[10];
+#pragma unroll
+    for (int u = 0; u < 10; ++u) {
+        const int v = threadIdx.x + u * NEPI;
         const int rr = v & 7, cc = (v >> 3) & 3, blk = v >> 5;         // blk: 0..79 -> (row group 0..7, chunk group 0..9)
         const int rg = blk / 10, cg = blk - rg * 10;
+        x[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)ids[rg * 8 + rr] * RL_K1) + cg * 4 + cc);
+    }
+#pragma unroll
+    for (int u = 0; u < 10; ++u) {
+        const int v = threadIdx.x + u * NEPI;
+        const int rr = v & 7, cc = (v >> 3) & 3, blk = v >> 5;
+        const int rg = blk / 10, cg = blk - rg * 10;
         const int r = rg * 8 + rr, c4 = cg * 4 + cc;
-        const float4 x = __ldg(reinterpret_cast<const float4*>(src + (size_t)ids[r] * RL_K1) + c4);
         if (!TRANSPOSED) {
-            *reinterpret_cast<float4*>(img + img_off(r, c4 * 4, RL_K1)) = make_float4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
+            *reinterpret_cast<float4*>(img + img_off(r, c4 * 4, RL_K1)) = make_float4(to_tf32(x[u].x), to_tf32(x[u].y), to_tf32(x[u].z), to_tf32(x[u].w));
         } else {
-            img[img_off(c4 * 4 + 0, r, R)] = to_tf32(x.x); img[img_off(c4 * 4 + 1, r, R)] = to_tf32(x.y);
-            img[img_off(c4 * 4 + 2, r, R)] = to_tf32(x.z); img[img_off(c4 * 4 + 3, r, R)] = to_tf32(x.w);
+            img[timg_off(c4 * 4 + 0, r)] = to_tf32(x[u].x); img[timg_off(c4 * 4 + 1, r)] = to_tf32(x[u].y);
+            img[timg_off(c4 * 4 + 2, r)] = to_tf32(x[u].z); img[timg_off(c4 * 4 + 3, r)] = to_tf32(x[u].w);
         }
+    }
+}
+
+// pull the 2 x 64 replay rows of an upcoming event into L2 (640 B = 5 lines per row)
+__device__ __forceinline__ void prefetch_event(const TcLearnParams& P, int e) {
+    const int S = P.cfg.slot_cap, cap = P.rp.capacity;
+    const size_t ring = (size_t)(P.ev_rows[e] / S) * cap;
+    for (int v = threadIdx.x; v < 2 * R * 5; v += NEPI) {
+        const int which = v / (R * 5), rem = v - which * (R * 5), r = rem / 5, ln = rem - r * 5;
+        const int i = P.sample_idx[(size_t)e * R + r];
+        const float* p = (which ? P.rp.obs : P.rp.next_obs) + (ring + i) * RL_K1 + ln * 32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
     }
 }
 
@@ -144,6 +184,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
     const uint32_t T_WORK = tmem, T_DW2 = tmem + 256;
     const int S = P.cfg.slot_cap, cap = P.rp.capacity;
 
+    if (warp != 8 && n_my > 0) prefetch_event(P, blockIdx.x);
     if (warp == 8) {
         // =================================== producer + MMA issuer (one thread) ===================================
         if (lane == 0) {
@@ -192,7 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
                     wait_ready();
                     const uint32_t idesc = make_idesc(128, 128, 0, 0);
                     for (int ks = 0; ks < 8; ++ks)
-                        mma_tf32(T_DW2 + half * 128, desc_kmajor(aH1T + ks * 256, R), desc_kmajor(aH1 + ks * 256, R), idesc, (it | ks) != 0);
+                        mma_tf32(T_DW2 + half * 128, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aH1 + ks * TP_KSTEP), idesc, (it | ks) != 0);
                     if (half == 0) signal_done();
                 }
                 stream_gemm(T_WORK, aH2, 256, 0, 8, 32, 64, 128); signal_done();                         // dH1 (after dW2 half 1)
@@ -200,7 +241,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
                 {
                     const uint32_t idesc = make_idesc(128, 160, 0, 0);                                     // dW1^T
                     for (int ks = 0; ks < 8; ++ks)
-                        mma_tf32(T_WORK, desc_kmajor(aH1T + ks * 256, R), desc_kmajor(aXT + ks * 256, R), idesc, ks != 0);
+                        mma_tf32(T_WORK, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aXT + ks * TP_KSTEP), idesc, ks != 0);
                 }
                 signal_done();
             }
@@ -219,10 +260,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
             epi_bar();
             if (threadIdx.x == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(ready)) : "memory");
         };
+        int tr_n = 0;
+        auto stamp = [&](int it) { if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 8 && tr_n < 40) P.trace[it * 40 + tr_n++] = clock64(); };
         auto wait_done = [&]() { mbar_wait(done, stage_no & 1); ++stage_no; fence_after(); };
 
         for (int it = 0; it < n_my; ++it) {
+            tr_n = 0; stamp(it);
             const int e = blockIdx.x + it * gridDim.x;
+            if (it + 1 < n_my) prefetch_event(P, e + gridDim.x);
             const int w = P.ev_rows[e] / S;
             const size_t ring = (size_t)w * cap;
             if (threadIdx.x < R) {
@@ -237,45 +282,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
             for (int net = 0; net < 2; ++net) {
                 const float* bias = net ? bias_e : bias_t;
                 gather_img<false>(sX, (net ? P.rp.obs : P.rp.next_obs) + ring * RL_K1, idx);
-                signal_ready();
+                stamp(it); signal_ready();
                 // ---- L1 epilogue: H1 = relu(D + b1) -> H1 image (+ H1^T image for the eval net) ----
-                wait_done();
-                for (int cb = 0; cb < 2; ++cb) {
-                    const int c0 = half * 64 + cb * 32;
-                    float v[32];
-                    tmem_ld32(T_WORK + t_lane + c0, v);
+                wait_done(); stamp(it);
+                {
+                    float va[2][32];
+                    tmem_ld32(T_WORK + t_lane + half * 64, va[0]);
+                    tmem_ld32(T_WORK + t_lane + half * 64 + 32, va[1]);
                     tmem_wait_ld();
                     if (rvalid) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = to_tf32(fmaxf(v[j] + bias[c0 + j], 0.f));
+                        for (int cb = 0; cb < 2; ++cb) {
+                            const int c0 = half * 64 + cb * 32;
+                            float* v = va[cb];
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4)
-                            *reinterpret_cast<float4*>(sH1 + img_off(row, c0 + j4 * 4, 128)) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-                        if (net) {
+                            for (int j = 0; j < 32; ++j) v[j] = to_tf32(fmaxf(v[j] + bias[c0 + j], 0.f));
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) sH1T[img_off(c0 + j, row, R)] = v[j];
+                            for (int j4 = 0; j4 < 8; ++j4)
+                                *reinterpret_cast<float4*>(sH1 + img_off(row, c0 + j4 * 4, 128)) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                            if (net) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) sH1T[timg_off(c0 + j, row)] = v[j];
+                            }
                         }
                     }
                 }
-                signal_ready();
+                stamp(it); signal_ready();
                 // ---- L2 epilogue: H2 = relu(D + b2) -> H2 image ----
-                wait_done();
-                for (int cb = 0; cb < 4; ++cb) {
-                    const int c0 = half * 128 + cb * 32;
-                    float v[32];
-                    tmem_ld32(T_WORK + t_lane + c0, v);
+                wait_done(); stamp(it);
+                for (int cp = 0; cp < 2; ++cp) {
+                    float va[2][32];
+                    tmem_ld32(T_WORK + t_lane + half * 128 + cp * 64, va[0]);
+                    tmem_ld32(T_WORK + t_lane + half * 128 + cp * 64 + 32, va[1]);
                     tmem_wait_ld();
                     if (rvalid) {
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4)
-                            *reinterpret_cast<float4*>(sH2 + img_off(row, c0 + j4 * 4, 256)) =
-                                make_float4(to_tf32(fmaxf(v[j4 * 4] + bias[128 + c0 + j4 * 4], 0.f)), to_tf32(fmaxf(v[j4 * 4 + 1] + bias[128 + c0 + j4 * 4 + 1], 0.f)),
-                                            to_tf32(fmaxf(v[j4 * 4 + 2] + bias[128 + c0 + j4 * 4 + 2], 0.f)), to_tf32(fmaxf(v[j4 * 4 + 3] + bias[128 + c0 + j4 * 4 + 3], 0.f)));
+                        for (int cb = 0; cb < 2; ++cb) {
+                            const int c0 = half * 128 + cp * 64 + cb * 32;
+                            const float* v = va[cb];
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4)
+                                *reinterpret_cast<float4*>(sH2 + img_off(row, c0 + j4 * 4, 256)) =
+                                    make_float4(to_tf32(fmaxf(v[j4 * 4] + bias[128 + c0 + j4 * 4], 0.f)), to_tf32(fmaxf(v[j4 * 4 + 1] + bias[128 + c0 + j4 * 4 + 1], 0.f)),
+                                                to_tf32(fmaxf(v[j4 * 4 + 2] + bias[128 + c0 + j4 * 4 + 2], 0.f)), to_tf32(fmaxf(v[j4 * 4 + 3] + bias[128 + c0 + j4 * 4 + 3], 0.f)));
+                        }
                     }
                 }
-                signal_ready();
+                stamp(it); signal_ready();
                 // ---- head epilogue: [A(8) | V] + bh ----
-                wait_done();
+                wait_done(); stamp(it);
                 if (half == 0) {
                     float v[16];
                     tmem_ld16(T_WORK + t_lane, v);
@@ -303,6 +358,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
                     mean_e = mean;
                 }
             }
+            stamp(it);
             // ---- TD target, loss, priorities, dOut ----
             {
                 float g = 0.f, sq = 0.f;
@@ -328,29 +384,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
                 }
                 epi_bar();
             }
+            stamp(it);
             // ---- head gradients (SIMT): dWh[k][j] += sum_b H2[b][k] dOut[b][j]; dbh ----
             {
                 const int k = threadIdx.x;
                 float acc[9];
 #pragma unroll
                 for (int j = 0; j < 9; ++j) acc[j] = 0.f;
-                for (int i = 0; i < R; ++i) {
-                    const int b = (i + (k >> 2)) & 63;                      // rotation: conflict-free image reads
-                    const float h = sH2[img_off(b, k, 256)];
+                const int r0 = (k >> 2) & 7;                                 // per-lane row rotation: conflict-free image reads
+                const float* hk = sH2 + (k >> 2) * 32 + (k & 3);
+#pragma unroll 1
+                for (int g = 0; g < 8; ++g) {
 #pragma unroll
-                    for (int j = 0; j < 9; ++j) acc[j] = fmaf(h, sDpl[b * 12 + j], acc[j]);
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int rx = rr ^ r0, b = g * 8 + rx;
+                        const float h = hk[g * 2048 + rx * 4];
+                        const float4 d0 = *reinterpret_cast<const float4*>(sDpl + b * 12), d1 = *reinterpret_cast<const float4*>(sDpl + b * 12 + 4);
+                        const float d8 = sDpl[b * 12 + 8];
+                        acc[0] = fmaf(h, d0.x, acc[0]); acc[1] = fmaf(h, d0.y, acc[1]); acc[2] = fmaf(h, d0.z, acc[2]); acc[3] = fmaf(h, d0.w, acc[3]);
+                        acc[4] = fmaf(h, d1.x, acc[4]); acc[5] = fmaf(h, d1.y, acc[5]); acc[6] = fmaf(h, d1.z, acc[6]); acc[7] = fmaf(h, d1.w, acc[7]);
+                        acc[8] = fmaf(h, d8, acc[8]);
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < 9; ++j) G[L::OFF_WH + k * 9 + j] += acc[j];
+                for (int j = 0; j < 9; ++j) red_add(G + L::OFF_WH + k * 9 + j, acc[j]);
                 if (threadIdx.x < 9) {
                     float s = 0.f;
                     for (int b = 0; b < R; ++b) s += sDpl[b * 12 + threadIdx.x];
-                    G[L::OFF_BH + threadIdx.x] += s;
+                    red_add(G + L::OFF_BH + threadIdx.x, s);
                 }
             }
-            signal_ready();                                    // dOut image ready -> dH2 MMA
+            stamp(it); signal_ready();                                    // dOut image ready -> dH2 MMA
             // ---- dH2 epilogue: mask by H2 > 0, in place; first half transposed into the (dead) H1 region ----
-            wait_done();
+            wait_done(); stamp(it);
             float* sDT = sH1;                                   // dH2^T half buffer [128][64]
             for (int cb = 0; cb < 4; ++cb) {
                 const int c0 = half * 128 + cb * 32;
@@ -368,7 +434,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
                     }
                     if (half == 0) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) sDT[img_off(c0 + j, row, R)] = v[j];
+                        for (int j = 0; j < 32; ++j) sDT[timg_off(c0 + j, row)] = v[j];
                     }
                 }
             }
@@ -379,17 +445,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
                 const int n = threadIdx.x;
                 float s = 0.f;
                 for (int i = 0; i < R; ++i) { const int b = (i + (n >> 2)) & 63; s += sH2[img_off(b, n, 256)]; }
-                G[L::OFF_B2 + n] += s;
+                red_add(G + L::OFF_B2 + n, s);
             }
-            signal_ready();                                    // dW2 half 0 may run
-            wait_done();                                       // dW2 half 0 finished reading the half buffer
+            stamp(it); signal_ready();                                    // dW2 half 0 may run
+            wait_done(); stamp(it);                                      // dW2 half 0 finished reading the half buffer
             for (int o = threadIdx.x; o < R * 128; o += NEPI) {   // second half: transpose from the dH2 image
                 const int b = o & 63, c = o >> 6;
-                sDT[img_off(c, b, R)] = sH2[img_off(b, 128 + c, 256)];
+                sDT[timg_off(c, b)] = sH2[img_off(b, 128 + c, 256)];
             }
-            signal_ready();                                    // dW2 half 1 + dH1 may run
+            stamp(it); signal_ready();                                    // dW2 half 1 + dH1 may run
             // ---- dH1 epilogue: mask by H1 > 0 (from H1^T), write dH1^T in place of H1^T ----
-            wait_done();
+            wait_done(); stamp(it);
             for (int cb = 0; cb < 2; ++cb) {
                 const int c0 = half * 64 + cb * 32;
                 float v[32];
@@ -398,7 +464,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
                 if (rvalid) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        float* p = sH1T + img_off(c0 + j, row, R);
+                        float* p = sH1T + timg_off(c0 + j, row);
                         *p = *p > 0.f ? to_tf32(v[j]) : 0.f;
                     }
                 }
@@ -408,27 +474,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
             if (threadIdx.x < 128) {                           // db1[k1] += sum_b dH1^T[k1][b]
                 const int k1 = threadIdx.x;
                 float s = 0.f;
-                for (int i = 0; i < R; ++i) { const int b = (i + ((k1 >> 3) & 3)) & 63; s += sH1T[img_off(k1, b, R)]; }
-                G[L::OFF_B1 + k1] += s;
+                for (int i = 0; i < R; ++i) { const int b = (i + ((k1 >> 3) & 3)) & 63; s += sH1T[timg_off(k1, b)]; }
+                red_add(G + L::OFF_B1 + k1, s);
             }
+            stamp(it);
             gather_img<true>(sXT, P.rp.obs + ring * RL_K1, idx);  // X^T image for dW1^T (dH2 region is dead: dH1 MMAs are done)
-            signal_ready();
-            // ---- dW1^T epilogue: G[W1t][kx][k1] += D[k1][kx] ----
-            wait_done();
+            stamp(it); signal_ready();
+            // ---- dW1^T epilogue: slab region W1 is kept [k1][kx] (160 per row) so each thread adds 16-byte vectors ----
+            wait_done(); stamp(it);
             {
                 const int k1 = q * 32 + lane;                   // M = 128 accumulator: row = lane
-                for (int cb = 0; cb < 5; ++cb) {
-                    if ((cb & 1) != half && cb < 4) continue;    // split the 5 column blocks over the two warp halves
-                    if (cb == 4 && half != 0) continue;
+                float* gr = G + L::OFF_W1T + k1 * RL_K1;
+                for (int cb = half; cb < 5; cb += 2) {           // 5 column blocks of 32 split over the two warp halves
                     float v[32];
                     tmem_ld32(T_WORK + ((uint32_t)(q * 32) << 16) + cb * 32, v);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) G[L::OFF_W1T + (cb * 32 + j) * 128 + k1] += v[j];
+                    for (int j4 = 0; j4 < 8; ++j4) red_add4(gr + cb * 32 + j4 * 4, v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
                 }
             }
             fence_before();
             epi_bar();
+            stamp(it);
         }
         // ---- flush the TMEM-resident dW2 accumulator once ----
         if (n_my > 0) {
@@ -502,6 +569,14 @@ int rl_brain_learn_tc(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t
     P.ev_rows = rows->rows + (size_t)(gene * RL_N_ROW_KINDS + RL_ROWS_EVENT) * rows->row_cap;
     P.ev_total = rows->total + gene * RL_N_ROW_KINDS + RL_ROWS_EVENT;
     P.rp = *replay; P.sample_idx = sample_idx; P.lb = *learn; P.wimg_e = wimg_eval; P.wimg_t = wimg_target;
+    P.trace = nullptr;
+    static long long* trace_dev = nullptr;
+    const bool tracing = getenv("RL_TC_TRACE") != nullptr;
+    if (tracing) {
+        if (!trace_dev) RL_CUDA_CHECK(cudaMalloc(&trace_dev, sizeof(long long) * 8 * 40));
+        RL_CUDA_CHECK(cudaMemsetAsync(trace_dev, 0, sizeof(long long) * 8 * 40, (cudaStream_t)stream));
+        P.trace = trace_dev;
+    }
     static bool attr = false;
     if (!attr) {
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dueling_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
@@ -511,7 +586,17 @@ int rl_brain_learn_tc(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t
     cudaStream_t st = (cudaStream_t)stream;
     k_learn_dueling_tc<<<n_cta, NTHREADS, TC_SMEM, st>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
-    return rl_learn_reduce(learn, P.ev_total, (void*)st);
+    if (tracing) {
+        long long h[8 * 40];
+        RL_CUDA_CHECK(cudaStreamSynchronize(st));
+        RL_CUDA_CHECK(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        for (int it = 1; it < 4; ++it) {
+            fprintf(stderr, "[tc trace] event %d (cycles since event start):", it);
+            for (int k = 1; k < 40 && h[it * 40 + k]; ++k) fprintf(stderr, " %lld", h[it * 40 + k] - h[it * 40]);
+            fprintf(stderr, "\n");
+        }
+    }
+    return rl_learn_reduce(learn, P.ev_total, 1, (void*)st);
 }
 
 }  // extern "C"
