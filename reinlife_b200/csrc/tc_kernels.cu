@@ -186,66 +186,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
 
     if (warp != 8 && n_my > 0) prefetch_event(P, blockIdx.x);
     if (warp == 8) {
-        // =================================== producer + MMA issuer (one thread) ===================================
+        // =================================== weight-stream producer (one thread) ===================================
+        // Streams the fixed 37-chunk schedule of every event through the NS-slot ring; runs ahead of the MMA issuer
+        // (epilogue thread 0) by as many chunks as the ring holds.  A slot is refilled once the MMAs that read it
+        // have completed (tcgen05.commit -> empty[slot]).
         if (lane == 0) {
-            uint32_t produced = 0, consumed = 0, stage_no = 0;
             const uint32_t n_chunks = (uint32_t)n_my * SCHED_N;
-            auto produce = [&]() {
-                while (produced < n_chunks && produced < consumed + (NS - 1)) {
-                    const uint32_t slot = produced % NS;
-                    if (produced >= NS) mbar_wait(&empty[slot], ((produced / NS) - 1) & 1);
-                    int net, ch; sched_entry(produced % SCHED_N, net, ch);
-                    bulk_load(sStage + slot * CHUNK_F, (net ? P.wimg_e : P.wimg_t) + (size_t)ch * CHUNK_F, CHUNK_F * 4, &full[slot]);
-                    ++produced;
-                }
-            };
-            // one GEMM stage whose B operand streams through the chunk ring
-            //   a_base: smem address of the A image, a_k: its width; kc = k columns per chunk; n = N; m = M
-            auto stream_gemm = [&](uint32_t d_tmem, uint32_t a_base, int a_k, int a_col0, int nch, int kc, int m, int n) {
-                const uint32_t idesc = make_idesc(m, n, 0, 0);
-                for (int c = 0; c < nch; ++c) {
-                    const uint32_t slot = consumed % NS;
-                    mbar_wait(&full[slot], (consumed / NS) & 1);
-                    fence_after();
-                    const uint32_t b_base = smem_u32(sStage + slot * CHUNK_F);
-                    for (int ks = 0; ks < kc / 8; ++ks) {
-                        const int kcol = a_col0 + c * kc + ks * 8;
-                        mma_tf32(d_tmem, desc_kmajor(a_base + (kcol >> 2) * 128, a_k), desc_kmajor(b_base + ks * 256, kc), idesc,
-                                 (c | ks) != 0);
-                    }
-                    mma_commit(&empty[slot]);
-                    ++consumed;
-                    produce();
-                }
-            };
-            auto wait_ready = [&]() { mbar_wait(ready, stage_no & 1); fence_after(); };
-            auto signal_done = [&]() { mma_commit(done); ++stage_no; };
-            produce();
-            for (int it = 0; it < n_my; ++it) {
-                const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH1T = smem_u32(sH1T), aH2 = smem_u32(sH2), aD = smem_u32(sDout), aXT = smem_u32(sXT);
-                for (int net = 0; net < 2; ++net) {
-                    wait_ready(); stream_gemm(T_WORK, aX, RL_K1, 0, 5, 32, 64, 128); signal_done();      // L1
-                    wait_ready(); stream_gemm(T_WORK, aH1, 128, 0, 8, 16, 64, 256); signal_done();       // L2
-                    wait_ready(); stream_gemm(T_WORK, aH2, 256, 0, 1, 256, 64, 16); signal_done();       // head
-                }
-                wait_ready(); stream_gemm(T_WORK, aD, 16, 0, 1, 16, 64, 256); signal_done();             // dH2 (pre-mask)
-                for (int half = 0; half < 2; ++half) {                                                      // dW2 halves
-                    wait_ready();
-                    const uint32_t idesc = make_idesc(128, 128, 0, 0);
-                    for (int ks = 0; ks < 8; ++ks)
-                        mma_tf32(T_DW2 + half * 128, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aH1 + ks * TP_KSTEP), idesc, (it | ks) != 0);
-                    if (half == 0) signal_done();
-                }
-                stream_gemm(T_WORK, aH2, 256, 0, 8, 32, 64, 128); signal_done();                         // dH1 (after dW2 half 1)
-                wait_ready();
-                {
-                    const uint32_t idesc = make_idesc(128, 160, 0, 0);                                     // dW1^T
-                    for (int ks = 0; ks < 8; ++ks)
-                        mma_tf32(T_WORK, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aXT + ks * TP_KSTEP), idesc, ks != 0);
-                }
-                signal_done();
+            for (uint32_t produced = 0; produced < n_chunks; ++produced) {
+                const uint32_t slot = produced % NS;
+                if (produced >= NS) mbar_wait(&empty[slot], ((produced / NS) - 1) & 1);
+                int net, ch; sched_entry(produced % SCHED_N, net, ch);
+                bulk_load(sStage + slot * CHUNK_F, (net ? P.wimg_e : P.wimg_t) + (size_t)ch * CHUNK_F, CHUNK_F * 4, &full[slot]);
             }
-            wait_ready();      // final hand-shake: epilogue has flushed dW2
         }
     } else {
         // =================================== epilogue warps ===================================
@@ -254,12 +206,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
         const uint32_t t_lane = (uint32_t)(q * 32) << 16;
         const int row = q * 16 + lane;                 // M = 64 accumulators: rows 16q+i in lanes 32q+i (i < 16)
         const bool rvalid = lane < 16;
-        auto signal_ready = [&]() {
-            fence_proxy_async();
-            fence_before();
-            epi_bar();
-            if (threadIdx.x == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(ready)) : "memory");
+        uint32_t consumed = 0;                          // chunks consumed so far (meaningful in thread 0 only)
+        const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH1T = smem_u32(sH1T), aH2 = smem_u32(sH2), aD = smem_u32(sDout), aXT = smem_u32(sXT);
+        // all epilogue threads: make shared-memory images visible to the tensor core, order TMEM accesses, meet
+        auto stage_sync = [&]() { fence_proxy_async(); fence_before(); epi_bar(); };
+        // thread 0: one GEMM stage whose B operand streams through the chunk ring
+        auto stream_gemm = [&](uint32_t d_tmem, uint32_t a_base, int a_k, int nch, int kc, int m, int n) {
+            const uint32_t idesc = make_idesc(m, n, 0, 0);
+            for (int c = 0; c < nch; ++c) {
+                const uint32_t slot = consumed % NS;
+                mbar_wait(&full[slot], (consumed / NS) & 1);
+                fence_after();
+                const uint32_t b_base = smem_u32(sStage + slot * CHUNK_F);
+                for (int ks = 0; ks < kc / 8; ++ks) {
+                    const int kcol = c * kc + ks * 8;
+                    mma_tf32(d_tmem, desc_kmajor(a_base + (kcol >> 2) * 128, a_k), desc_kmajor(b_base + ks * 256, kc), idesc, (c | ks) != 0);
+                }
+                mma_commit(&empty[slot]);
+                ++consumed;
+            }
         };
+        // issue a stage from thread 0 (after stage_sync), everybody then waits for its completion
+#define RL_STAGE(BODY) do { stage_sync(); if (threadIdx.x == 0) { fence_after(); BODY; mma_commit(done); } } while (0)
         int tr_n = 0;
         auto stamp = [&](int it) { if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 8 && tr_n < 40) P.trace[it * 40 + tr_n++] = clock64(); };
         auto wait_done = [&]() { mbar_wait(done, stage_no & 1); ++stage_no; fence_after(); };
@@ -282,7 +250,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
             for (int net = 0; net < 2; ++net) {
                 const float* bias = net ? bias_e : bias_t;
                 gather_img<false>(sX, (net ? P.rp.obs : P.rp.next_obs) + ring * RL_K1, idx);
-                stamp(it); signal_ready();
+                stamp(it); RL_STAGE(stream_gemm(T_WORK, aX, RL_K1, 5, 32, 64, 128));
                 // ---- L1 epilogue: H1 = relu(D + b1) -> H1 image (+ H1^T image for the eval net) ----
                 wait_done(); stamp(it);
                 {
@@ -307,7 +275,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
                         }
                     }
                 }
-                stamp(it); signal_ready();
+                stamp(it); RL_STAGE(stream_gemm(T_WORK, aH1, 128, 8, 16, 64, 256));
                 // ---- L2 epilogue: H2 = relu(D + b2) -> H2 image ----
                 wait_done(); stamp(it);
                 for (int cp = 0; cp < 2; ++cp) {
@@ -328,7 +296,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
                         }
                     }
                 }
-                stamp(it); signal_ready();
+                stamp(it); RL_STAGE(stream_gemm(T_WORK, aH2, 256, 1, 256, 64, 16));
                 // ---- head epilogue: [A(8) | V] + bh ----
                 wait_done(); stamp(it);
                 if (half == 0) {
@@ -414,7 +382,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
                     red_add(G + L::OFF_BH + threadIdx.x, s);
                 }
             }
-            stamp(it); signal_ready();                                    // dOut image ready -> dH2 MMA
+            stamp(it); RL_STAGE(stream_gemm(T_WORK, aD, 16, 1, 16, 64, 256));   // dH2 (pre-mask) = dOut Wh^T
             // ---- dH2 epilogue: mask by H2 > 0, in place; first half transposed into the (dead) H1 region ----
             wait_done(); stamp(it);
             float* sDT = sH1;                                   // dH2^T half buffer [128][64]
@@ -447,13 +415,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
                 for (int i = 0; i < R; ++i) { const int b = (i + (n >> 2)) & 63; s += sH2[img_off(b, n, 256)]; }
                 red_add(G + L::OFF_B2 + n, s);
             }
-            stamp(it); signal_ready();                                    // dW2 half 0 may run
+            stamp(it);
+            RL_STAGE({ const uint32_t idesc = make_idesc(128, 128, 0, 0);                  // dW2 half 0 (TMEM-resident accumulator)
+                       for (int ks = 0; ks < 8; ++ks)
+                           mma_tf32(T_DW2, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aH1 + ks * TP_KSTEP), idesc, (it | ks) != 0); });
             wait_done(); stamp(it);                                      // dW2 half 0 finished reading the half buffer
             for (int o = threadIdx.x; o < R * 128; o += NEPI) {   // second half: transpose from the dH2 image
                 const int b = o & 63, c = o >> 6;
                 sDT[timg_off(c, b)] = sH2[img_off(b, 128 + c, 256)];
             }
-            stamp(it); signal_ready();                                    // dW2 half 1 + dH1 may run
+            stamp(it);
+            RL_STAGE({ const uint32_t idesc = make_idesc(128, 128, 0, 0);                  // dW2 half 1, then dH1 = dH2 W2
+                       for (int ks = 0; ks < 8; ++ks)
+                           mma_tf32(T_DW2 + 128, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aH1 + ks * TP_KSTEP), idesc, (it | ks) != 0);
+                       stream_gemm(T_WORK, aH2, 256, 8, 32, 64, 128); });
             // ---- dH1 epilogue: mask by H1 > 0 (from H1^T), write dH1^T in place of H1^T ----
             wait_done(); stamp(it);
             for (int cb = 0; cb < 2; ++cb) {
@@ -479,7 +454,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
             }
             stamp(it);
             gather_img<true>(sXT, P.rp.obs + ring * RL_K1, idx);  // X^T image for dW1^T (dH2 region is dead: dH1 MMAs are done)
-            stamp(it); signal_ready();
+            stamp(it);
+            RL_STAGE({ const uint32_t idesc = make_idesc(128, 160, 0, 0);                  // dW1^T = dH1^T X
+                       for (int ks = 0; ks < 8; ++ks)
+                           mma_tf32(T_WORK, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aXT + ks * TP_KSTEP), idesc, ks != 0); });
             // ---- dW1^T epilogue: slab region W1 is kept [k1][kx] (160 per row) so each thread adds 16-byte vectors ----
             wait_done(); stamp(it);
             {
@@ -511,7 +489,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
                     *reinterpret_cast<float4*>(G + L::OFF_W2T + k1 * 256 + c0 + j4 * 4) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
             }
         }
-        signal_ready();
     }
     fence_before();
     __syncthreads();
