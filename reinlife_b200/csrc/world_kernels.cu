@@ -6,6 +6,7 @@
 // Reference semantics: ReinLife/World/environment.py (cited per phase), grid.py:60-117,
 // entities.py:145-248; closed forms: SURVEY.md Appendix A.3-A.6 (validated against the reference
 // through oracle/rl_oracle.c, which keeps the sequential formulation).
+#include <stdlib.h>
 #include "rl_common.cuh"
 
 namespace {
@@ -19,6 +20,7 @@ enum { M_ALIVE = 0, M_NFOOD, M_NPOISON, M_NSUPER, M_NB, M_PRESENT, M_ANY, M_PALL
        M_CNT_G = M_ALIVE_G + RL_MAX_GENES, M_PG = M_CNT_G + RL_MAX_GENES, M_WORDS = M_PG + RL_MAX_GENES };
 
 struct WParams {
+    long long* trace;
     rl_world_cfg cfg;
     rl_world_bufs b;
     uint64_t t;
@@ -27,32 +29,32 @@ struct WParams {
 };
 
 struct WS {
-    float* rows;        // [WNW][ld] observation staging
-    int32_t* gene;      // [C]
-    uint32_t* pk;       // [C] packed observation planes
+    float* planes;      // [3][(H+6)*(W+6)] toroidally padded observation planes: food, health, dead-agent gene (or -2)
+    float* ascal;       // [WNW][32][8] per-warp batch of agent scalars (6 observation scalars + 2 zeros)
     uint32_t* mask;     // [Cw] empty cells
     uint32_t* amask;    // [Cw] agent cells / eligible parents
     uint32_t* wpre;     // [Cw] exclusive popc prefix of amask
     int32_t* misc;      // [M_WORDS]
     int16_t *health, *age, *maxage;
     uint16_t *aslot, *tgt, *src, *cellof;
-    uint8_t *type, *ntype, *flags;
+    uint8_t *type, *ntype, *flags, *gene;
     int8_t* action;
 };
 
-__host__ __device__ inline size_t ws_bytes(int C, int ld) {
-    size_t Cw = (size_t)(C + 31) / 32;
-    size_t Cp = ((size_t)C + 15) & ~(size_t)15;
-    return sizeof(float) * WNW * ld + 4 * Cp * 2 + 4 * ((Cw + 3) & ~(size_t)3) * 3 + 4 * M_WORDS + 2 * Cp * 7 + Cp * 4;
+__host__ __device__ inline size_t ws_bytes(int H, int W) {
+    const size_t C = (size_t)H * W, Cw = (C + 31) / 32, Cp = (C + 15) & ~(size_t)15;
+    const size_t PADN = ((size_t)(H + 6) * (W + 6) + 3) & ~(size_t)3;
+    return 4 * 3 * PADN + 4 * WNW * 32 * 8 + 4 * ((Cw + 3) & ~(size_t)3) * 3 + 4 * M_WORDS + 2 * Cp * 7 + Cp * 5;
 }
 
-__device__ inline void ws_carve(WS& s, unsigned char* base, int C, int ld) {
-    size_t Cw = ((size_t)(C + 31) / 32 + 3) & ~(size_t)3;
-    size_t Cp = ((size_t)C + 15) & ~(size_t)15;
+__device__ inline void ws_carve(WS& s, unsigned char* base, int H, int W) {
+    const size_t C = (size_t)H * W;
+    const size_t Cw = ((C + 31) / 32 + 3) & ~(size_t)3;
+    const size_t Cp = (C + 15) & ~(size_t)15;
+    const size_t PADN = ((size_t)(H + 6) * (W + 6) + 3) & ~(size_t)3;
     unsigned char* p = base;
-    s.rows = (float*)p; p += sizeof(float) * WNW * ld;
-    s.gene = (int32_t*)p; p += 4 * Cp;
-    s.pk = (uint32_t*)p; p += 4 * Cp;
+    s.planes = (float*)p; p += 4 * 3 * PADN;
+    s.ascal = (float*)p; p += 4 * WNW * 32 * 8;
     s.mask = (uint32_t*)p; p += 4 * Cw;
     s.amask = (uint32_t*)p; p += 4 * Cw;
     s.wpre = (uint32_t*)p; p += 4 * Cw;
@@ -67,6 +69,7 @@ __device__ inline void ws_carve(WS& s, unsigned char* base, int C, int ld) {
     s.type = p; p += Cp;
     s.ntype = p; p += Cp;
     s.flags = p; p += Cp;
+    s.gene = p; p += Cp;
     s.action = (int8_t*)p;
 }
 
@@ -121,7 +124,7 @@ __device__ __forceinline__ void spawn_agent(WS& s, int cell, int gene, int healt
     if (lane_id() == 0) {
         s.type[cell] = RL_AGENT;
         s.health[cell] = (int16_t)health; s.age[cell] = (int16_t)age; s.maxage[cell] = 50;
-        s.gene[cell] = gene; s.flags[cell] = 0; s.action[cell] = -1; s.aslot[cell] = RL_NONE16;
+        s.gene[cell] = (uint8_t)gene; s.flags[cell] = 0; s.action[cell] = -1; s.aslot[cell] = RL_NONE16;
     }
     __syncwarp();
 }
@@ -157,7 +160,7 @@ __device__ __forceinline__ int load_world(const WParams& P, WS& s, int w) {
             fl &= ~(RL_F_KILLED | RL_F_INTER_KILLED | RL_F_INTRA_KILLED);
         }
         s.health[c] = (int16_t)h; s.age[c] = (int16_t)age; s.maxage[c] = (int16_t)ma;
-        s.gene[c] = v.z; s.flags[c] = (uint8_t)fl; s.action[c] = (int8_t)act;
+        s.gene[c] = (uint8_t)v.z; s.flags[c] = (uint8_t)fl; s.action[c] = (int8_t)act;
         s.aslot[c] = (uint16_t)sl; s.cellof[sl] = (uint16_t)c;
     }
     __syncthreads();
@@ -173,10 +176,16 @@ __device__ __forceinline__ float hratio(int h) {       // float32(health / max_h
 // Rebuild the agent list from the final grid `ft` (Grid.get_entities, grid.py:60-67), write
 // type/rec/n_agents(/reward), then Environment._get_observations (environment.py:313-375).
 // src[c] = index into the attribute arrays of the agent standing on cell c.
+//
+// Observation: the three planes are materialised ONCE per world as floats on a toroidally padded (H+6)x(W+6)
+// grid (what Grid.fov's np.concatenate builds, grid.py:99-115), so a window element is one shared-memory load at
+// base(i,j) + constant(lane): each lane owns row elements e = lane + 32k (k < 5) of the 160-float row and
+// the warp writes the row as five fully coalesced, 128-byte aligned stores straight to HBM.
 template <bool STEP>
 __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t* ft, float* obs_out) {
     const int H = P.cfg.height, W = P.cfg.width, C = H * W, Cw = (C + 31) / 32;
     const int S = P.cfg.slot_cap, ld = P.cfg.obs_ld, G = P.cfg.n_genes;
+    const int PW = W + 6, PADN = (((H + 6) * PW) + 3) & ~3;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     uint8_t* tg = P.b.type + (size_t)w * C;
 
@@ -210,39 +219,57 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
     const int alive = s.misc[M_ALIVE];
     rl_agent_rec* rg = P.b.rec + (size_t)w * S;
     for (int c = threadIdx.x; c < C; c += WT) {
-        uint8_t t = ft[c];
-        uint32_t pk;
-        if (t == RL_AGENT) {
-            const int slot = s.wpre[c >> 5] + __popc(s.amask[c >> 5] & ((1u << (c & 31)) - 1u));
-            const int sc = s.src[c];
-            const int h = s.health[sc], g = s.gene[sc];
-            const unsigned fl = s.flags[sc] & 0x3Fu;
-            pk = (h < 0 ? 2u : 0u) | 4u | ((fl & RL_F_DEAD) ? 8u : 0u) | (((uint32_t)g & 0xFFu) << 4) |
-                 ((uint32_t)(uint16_t)(int16_t)h << 16);
-            atomicAdd(&s.misc[M_CNT_G + (g & (RL_MAX_GENES - 1))], 1);
-            if (slot < S) {
-                s.cellof[slot] = (uint16_t)c;
-                int4 v;
-                v.x = (c & 0xFFFF) | ((int)(uint16_t)(int16_t)h << 16);
-                v.y = ((int)(uint16_t)s.age[sc]) | ((int)(uint16_t)s.maxage[sc] << 16);
-                v.z = g;
-                const unsigned prev = STEP ? (unsigned)s.aslot[sc] : (unsigned)slot;
-                v.w = (int)(fl | (((unsigned)(uint8_t)s.action[sc]) << 8) | (prev << 16));
-                reinterpret_cast<int4*>(rg)[slot] = v;
-                if (STEP) {                                 // _get_rewards, environment.py:291-311
-                    const int kin = max(0, s.misc[M_ALIVE_G + g] - 1);
-                    double r;
-                    if (fl & RL_F_DEAD) r = (double)(kin - alive);
-                    else if (alive == 1) r = 0.0;
-                    else r = (double)kin / (double)alive;
-                    if ((fl & RL_F_KILLED) && P.cfg.incentivize_killing) r += 0.2;
-                    P.b.reward[(size_t)w * S + slot] = (float)r;
-                }
+        if (ft[c] != RL_AGENT) continue;
+        const int slot = s.wpre[c >> 5] + __popc(s.amask[c >> 5] & ((1u << (c & 31)) - 1u));
+        const int sc = s.src[c];
+        const int h = s.health[sc], g = s.gene[sc];
+        const unsigned fl = s.flags[sc] & 0x3Fu;
+        atomicAdd(&s.misc[M_CNT_G + (g & (RL_MAX_GENES - 1))], 1);
+        if (slot < S) {
+            s.cellof[slot] = (uint16_t)c;
+            int4 v;
+            v.x = (c & 0xFFFF) | ((int)(uint16_t)(int16_t)h << 16);
+            v.y = ((int)(uint16_t)s.age[sc]) | ((int)(uint16_t)s.maxage[sc] << 16);
+            v.z = g;
+            const unsigned prev = STEP ? (unsigned)s.aslot[sc] : (unsigned)slot;
+            v.w = (int)(fl | (((unsigned)(uint8_t)s.action[sc]) << 8) | (prev << 16));
+            reinterpret_cast<int4*>(rg)[slot] = v;
+            if (STEP) {                                 // _get_rewards, environment.py:291-311
+                const int kin = max(0, s.misc[M_ALIVE_G + g] - 1);
+                double r;
+                if (fl & RL_F_DEAD) r = (double)(kin - alive);
+                else if (alive == 1) r = 0.0;
+                else r = (double)kin / (double)alive;
+                if ((fl & RL_F_KILLED) && P.cfg.incentivize_killing) r += 0.2;
+                P.b.reward[(size_t)w * S + slot] = (float)r;
             }
-        } else {
-            pk = t == RL_FOOD ? 1u : t == RL_SUPER_FOOD ? 2u : t == RL_POISON ? 3u : 0u;   // _get_food :432-446
         }
-        s.pk[c] = pk;
+    }
+    // ---- padded planes (_prepare_observations :377-404, _get_food :432-446, _get_genes :448-456) ----
+    {
+        const bool float_path = ft[0] == RL_AGENT;       // np.vectorize dtype quirk of the health plane, SURVEY A.8
+        float* pf = s.planes; float* ph = pf + PADN; float* pg = ph + PADN;
+        const int PH = H + 6;
+        const uint32_t magicPW = (uint32_t)(0x100000000ull / (uint64_t)PW) + 1u;
+        for (int p = threadIdx.x; p < PH * PW; p += WT) {
+            const int pi = (int)__umulhi((uint32_t)p, magicPW), pj = p - pi * PW;
+            int si = pi - 3, sj = pj - 3;                    // H, W >= 3: at most two wraps per side
+            si += si < 0 ? H : 0; si += si < 0 ? H : 0; si -= si >= H ? H : 0; si -= si >= H ? H : 0;
+            sj += sj < 0 ? W : 0; sj += sj < 0 ? W : 0; sj -= sj >= W ? W : 0; sj -= sj >= W ? W : 0;
+            const int c = si * W + sj;
+            const uint8_t t = ft[c];
+            float f = 0.f, hv = -1.f, gv = -2.f;
+            if (t == RL_AGENT) {
+                const int sc = s.src[c];
+                const int h = s.health[sc];
+                f = h < 0 ? 1.f : 0.f;
+                hv = float_path ? hratio(h) : (float)(h / 200);                  // :396-398
+                if (s.flags[sc] & RL_F_DEAD) gv = (float)s.gene[sc];
+            } else {
+                f = t == RL_FOOD ? .5f : t == RL_SUPER_FOOD ? 1.f : t == RL_POISON ? -1.f : 0.f;
+            }
+            pf[p] = f; ph[p] = hv; pg[p] = gv;
+        }
     }
     __syncthreads();
     if (threadIdx.x < G) {
@@ -256,53 +283,69 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
         if (nB > S && P.b.status) atomicOr(&P.b.status[w], 1);
     }
     __syncthreads();
+    if (STEP && P.trace && blockIdx.x == 77 && threadIdx.x == 0) P.trace[6] = clock64();
 
-    // ---- observation rows: one warp per agent, 7x7 toroidal window (Grid.fov, grid.py:90-117) ----
-    const bool float_path = ft[0] == RL_AGENT;   // np.vectorize dtype quirk, SURVEY A.8
-    const float pall = reinterpret_cast<float*>(s.misc)[M_PALL];
-    float* row = s.rows + warp * ld;
-    const int nrow = min(nB, S);
-    for (int sl = warp; sl < nrow; sl += WNW) {
-        const int d = s.cellof[sl];
-        const int i = (int)__umulhi((uint32_t)d, P.magicW), j = d - i * W;
-        const uint32_t me = s.pk[d];
-        const int mygene = (me >> 4) & 0xFF;
+    // ---- observation rows: one warp per agent ----
+    // per-lane constants: element e = lane + 32k of the row -> offset into the padded planes (window elements only)
+    int off[5];
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            const int q = lane + 32 * it;
-            if (q < 49) {
-                const int qi = q / 7, qj = q - qi * 7;
-                int r = i + qi - 3, cc = j + qj - 3;
-                r = r < 0 ? r + H : (r >= H ? r - H : r);
-                cc = cc < 0 ? cc + W : (cc >= W ? cc - W : cc);
-                const uint32_t pk = s.pk[r * W + cc];
-                const unsigned fc = pk & 3u;
-                row[q] = fc == 0 ? 0.f : fc == 1 ? .5f : fc == 2 ? 1.f : -1.f;
-                float hv = -1.f, gv = 0.f;
-                if (pk & 4u) {
-                    const int h = (int16_t)(pk >> 16);
-                    hv = float_path ? hratio(h) : (float)(h / 200);           // :396-398
-                    if (pk & 8u) gv = (int)((pk >> 4) & 0xFF) == mygene ? 1.f : -1.f;   // :424-428, :448-456
-                }
-                row[49 + q] = hv;
-                row[98 + q] = gv;
-            }
+    for (int k = 0; k < 5; ++k) {
+        const int e = lane + 32 * k;
+        const int pl = e / 49, q = e - pl * 49;
+        off[k] = e < 147 ? pl * PADN + (q / 7) * PW + (q - (q / 7) * 7) : 0;
+    }
+    const float pall = reinterpret_cast<float*>(s.misc)[M_PALL];
+    const int nrow = min(nB, S);
+    // Each warp owns a contiguous block of agents and handles it in batches of 32: first every lane prepares ONE
+    // agent of the batch (window base, own gene, the six scalars -> per-warp scratch), then the warp emits the 32
+    // rows, broadcasting the per-agent values by shuffle.  Per row: 5 loads, 2 gene decodes, 5 coalesced stores.
+    const int per_warp = (nrow + WNW - 1) / WNW;
+    const int a0 = warp * per_warp, a1 = min(nrow, a0 + per_warp);
+    float* scr = s.ascal + warp * 256;
+    const float* planes = s.planes;
+    for (int b0 = a0; b0 < a1; b0 += 32) {
+        const int mine = b0 + lane;
+        int base_l = 0; float gene_l = 0.f;
+        if (mine < a1) {
+            const int d = s.cellof[mine];
+            const int i = (int)__umulhi((uint32_t)d, P.magicW), j = d - i * W;
+            base_l = i * PW + j;                           // top-left of the 7x7 window in padded coordinates
+            const int sc = s.src[d];
+            const unsigned fl = s.flags[sc];
+            const int g = s.gene[sc];
+            gene_l = (float)g;
+            float4 lo, hi;
+            lo.x = hratio(s.health[sc]);                                        // :365
+            lo.y = (fl & RL_F_REPRODUCED) ? 1.f : 0.f;                           // :359
+            lo.z = reinterpret_cast<const float*>(s.misc)[M_PG + g];            // :357
+            lo.w = pall;                                                         // :358
+            hi.x = (fl & RL_F_KILLED) ? 1.f : 0.f;                               // :369
+            hi.y = (fl & RL_F_ATE_SUPER) ? 1.f : -1.f;                           // :370
+            hi.z = 0.f; hi.w = 0.f;
+            reinterpret_cast<float4*>(scr + lane * 8)[0] = lo;
+            reinterpret_cast<float4*>(scr + lane * 8)[1] = hi;
         }
-        if (lane < ld - 147) {
-            float v = 0.f;
-            const unsigned fl = s.flags[s.src[d]];
-            if (lane == 0) v = hratio((int16_t)(me >> 16));                   // :365
-            else if (lane == 1) v = (fl & RL_F_REPRODUCED) ? 1.f : 0.f;        // :359
-            else if (lane == 2) v = reinterpret_cast<float*>(s.misc)[M_PG + mygene];
-            else if (lane == 3) v = pall;
-            else if (lane == 4) v = (fl & RL_F_KILLED) ? 1.f : 0.f;            // :369
-            else if (lane == 5) v = (fl & RL_F_ATE_SUPER) ? 1.f : -1.f;        // :370
-            row[147 + lane] = v;
-        }
-        for (int e = 179 + lane; e < ld; e += 32) row[e] = 0.f;
         __syncwarp();
-        float4* og = reinterpret_cast<float4*>(obs_out + ((size_t)w * S + sl) * ld);
-        for (int v4 = lane; v4 < ld / 4; v4 += 32) st_stream_f4(og + v4, reinterpret_cast<const float4*>(row)[v4]);
+        const int cnt = min(32, a1 - b0);
+        float* orow = obs_out + ((size_t)w * S + b0) * ld;
+        const int sidx = lane >= 19 ? min(lane - 19, 7) : 0;   // lanes 19-24: scalars, 25-31: zero pad (slots 6,7 are zero)
+        for (int a = 0; a < cnt; ++a, orow += ld) {
+            const int base = __shfl_sync(0xffffffffu, base_l, a);
+            const float mygene = __shfl_sync(0xffffffffu, gene_l, a);
+            const float v0 = planes[base + off[0]];
+            const float v1 = planes[base + off[1]];
+            const float v2 = planes[base + off[2]];
+            float v3 = planes[base + off[3]];
+            float v4 = planes[base + off[4]];
+            const float sv = scr[a * 8 + sidx];
+            const float g3 = v3 == -2.f ? 0.f : (v3 == mygene ? 1.f : -1.f);             // :424-428
+            const float g4 = v4 == -2.f ? 0.f : (v4 == mygene ? 1.f : -1.f);
+            v3 = lane >= 2 ? g3 : v3;
+            v4 = lane < 19 ? g4 : sv;
+            __stcs(orow + lane, v0); __stcs(orow + 32 + lane, v1); __stcs(orow + 64 + lane, v2);
+            __stcs(orow + 96 + lane, v3); __stcs(orow + 128 + lane, v4);
+            for (int e = 160 + lane; e < ld; e += 32) __stcs(orow + e, 0.f);
+        }
         __syncwarp();
     }
 }
@@ -314,11 +357,14 @@ __global__ void __launch_bounds__(WT) k_world_step(const WParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int w = blockIdx.x;
     const int H = P.cfg.height, W = P.cfg.width, C = H * W, Cw = (C + 31) / 32;
-    WS s; ws_carve(s, smem, C, P.cfg.obs_ld);
+    WS s; ws_carve(s, smem, P.cfg.height, P.cfg.width);
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
 
+#define WSTAMP(k) do { if (P.trace && blockIdx.x == 77 && threadIdx.x == 0) P.trace[k] = clock64(); } while (0)
+    WSTAMP(0);
     const int n = load_world<true>(P, s, w);
+    WSTAMP(1);
 
     // ---- _attack (environment.py:652-699) in closed form + _prepare_movement (:591-625) ----
     for (int sl = threadIdx.x; sl < n; sl += WT) {
@@ -348,6 +394,7 @@ __global__ void __launch_bounds__(WT) k_world_step(const WParams P) {
     }
     __syncthreads();
 
+    WSTAMP(2);
     // ---- _execute_movement conflict fixed point (environment.py:637-644, 717-726) ----
     for (;;) {
         int any = 0;
@@ -373,6 +420,7 @@ __global__ void __launch_bounds__(WT) k_world_step(const WParams P) {
         __syncthreads();
     }
 
+    WSTAMP(3);
     // ---- execute: _eat (:701-715) on the pre-move content, vanish rule, new grid ----
     for (int c = threadIdx.x; c < C; c += WT) {
         const uint8_t t = s.type[c];
@@ -417,6 +465,7 @@ __global__ void __launch_bounds__(WT) k_world_step(const WParams P) {
     }
     __syncthreads();
 
+    WSTAMP(4);
     // ---- _add_food (:763-776): counts + empty mask by ballot, placements by warp 0 ----
     {
         int nf = 0, np = 0, ns = 0;
@@ -440,20 +489,27 @@ __global__ void __launch_bounds__(WT) k_world_step(const WParams P) {
         const bool want_food = (double)s.misc[M_NFOOD] <= (double)C / 10.0;
         const bool want_poison = (double)s.misc[M_NPOISON] <= (double)C / 20.0;
         const bool want_super = s.misc[M_NSUPER] == 0;
-        for (int slot = 0; slot < 7; ++slot) {
-            const bool want = slot < 3 ? want_food : slot < 6 ? want_poison : want_super;
-            if (!want) continue;
+        // set_random draws the index first and the acceptance second (grid.py:75-77): a rejected placement changes
+        // nothing, so lanes 0-6 evaluate the seven acceptance draws in parallel and only accepted slots are scanned.
+        bool acc = false;
+        if (lane < 7) {
+            const bool want = lane < 3 ? want_food : lane < 6 ? want_poison : want_super;
+            acc = want && rl_uniform(rl_draw(key, P.t, RL_SITE_FOOD_ACCEPT, lane)) < (lane < 6 ? 0.2 : 1.0);
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, acc);
+        while (todo) {
+            const int slot = __ffs(todo) - 1;
+            todo &= todo - 1;
             const int cell = warp_place(s.mask, Cw, rl_draw(key, P.t, RL_SITE_FOOD_PLACE, slot));
             if (cell < 0) continue;
-            const double p = slot < 6 ? 0.2 : 1.0;
-            if (rl_uniform(rl_draw(key, P.t, RL_SITE_FOOD_ACCEPT, slot)) < p) {
-                if (lane == 0) s.ntype[cell] = slot < 3 ? RL_FOOD : slot < 6 ? RL_POISON : RL_SUPER_FOOD;
-                warp_mask_clear(s.mask, cell);
-            }
+            if (lane == 0) s.ntype[cell] = slot < 3 ? RL_FOOD : slot < 6 ? RL_POISON : RL_SUPER_FOOD;
+            warp_mask_clear(s.mask, cell);
         }
     }
     __syncthreads();
+    WSTAMP(5);
     finish_and_observe<true>(P, s, w, s.ntype, P.b.obs_prime);
+    WSTAMP(9);
 }
 
 // =====================================================================================================
@@ -463,7 +519,7 @@ __global__ void __launch_bounds__(WT) k_world_update(const WParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int w = blockIdx.x;
     const int C = P.cfg.height * P.cfg.width, Cw = (C + 31) / 32, G = P.cfg.n_genes;
-    WS s; ws_carve(s, smem, C, P.cfg.obs_ld);
+    WS s; ws_carve(s, smem, P.cfg.height, P.cfg.width);
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
 
@@ -486,22 +542,28 @@ __global__ void __launch_bounds__(WT) k_world_update(const WParams P) {
         uint32_t trial = 0, birth = 0;
         // _reproduce (:488-519): parents in row-major order; offspring on a uniformly random empty cell (A.9)
         for (int wd = 0; wd < Cw; ++wd) {
-            uint32_t bitsw = s.amask[wd];
-            while (bitsw) {
-                const int b = __ffs(bitsw) - 1;
-                bitsw &= bitsw - 1;
-                const int pc = wd * 32 + b;
-                if (rl_uniform(rl_draw(key, P.t, RL_SITE_REPRO_TRIAL, trial++)) > 0.95) {
-                    const int cell = warp_place(s.mask, Cw, rl_draw(key, P.t, RL_SITE_BIRTH_PLACE, birth));
-                    if (cell >= 0) {
-                        ++birth;
-                        spawn_agent(s, cell, s.gene[pc], 200, 0);
-                        if (lane == 0) s.src[cell] = (uint16_t)cell;
-                        warp_mask_clear(s.mask, cell);
-                    }
-                    if (P.cfg.limit_reproduction && lane == 0) s.flags[pc] |= RL_F_REPRODUCED;   // :518-519
-                    __syncwarp();
+            const uint32_t m = s.amask[wd];
+            if (!m) continue;
+            // the 0.95 trials of one 32-cell word are drawn in parallel (trial index = rank among eligible parents,
+            // exactly the order of the reference's short-circuited random.random() calls); births stay sequential
+            const bool el = (m >> lane) & 1u;
+            const uint32_t rank = trial + __popc(m & lanemask_lt());
+            const bool succ = el && rl_uniform(rl_draw(key, P.t, RL_SITE_REPRO_TRIAL, rank)) > 0.95;
+            trial += __popc(m);
+            uint32_t sm = __ballot_sync(0xffffffffu, succ);
+            while (sm) {
+                const int bpos = __ffs(sm) - 1;
+                sm &= sm - 1;
+                const int pc = wd * 32 + bpos;
+                const int cell = warp_place(s.mask, Cw, rl_draw(key, P.t, RL_SITE_BIRTH_PLACE, birth));
+                if (cell >= 0) {
+                    ++birth;
+                    spawn_agent(s, cell, s.gene[pc], 200, 0);
+                    if (lane == 0) s.src[cell] = (uint16_t)cell;
+                    warp_mask_clear(s.mask, cell);
                 }
+                if (P.cfg.limit_reproduction && lane == 0) s.flags[pc] |= RL_F_REPRODUCED;   // :518-519
+                __syncwarp();
             }
         }
         // _produce (:521-547)
@@ -534,7 +596,7 @@ __global__ void __launch_bounds__(WT) k_world_reset(const WParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int w = blockIdx.x;
     const int C = P.cfg.height * P.cfg.width, Cw = (C + 31) / 32, G = P.cfg.n_genes;
-    WS s; ws_carve(s, smem, C, P.cfg.obs_ld);
+    WS s; ws_carve(s, smem, P.cfg.height, P.cfg.width);
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
     for (int c = threadIdx.x; c < C; c += WT) { s.type[c] = RL_EMPTY; s.src[c] = (uint16_t)c; s.aslot[c] = RL_NONE16; }
@@ -579,7 +641,7 @@ __global__ void __launch_bounds__(WT) k_world_topup(const WParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int w = blockIdx.x;
     const int C = P.cfg.height * P.cfg.width, Cw = (C + 31) / 32;
-    WS s; ws_carve(s, smem, C, P.cfg.obs_ld);
+    WS s; ws_carve(s, smem, P.cfg.height, P.cfg.width);
     const int warp = threadIdx.x >> 5;
     const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
     const int n = load_world<false>(P, s, w);
@@ -606,7 +668,7 @@ __global__ void __launch_bounds__(WT) k_world_observe(const WParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int w = blockIdx.x;
     const int C = P.cfg.height * P.cfg.width;
-    WS s; ws_carve(s, smem, C, P.cfg.obs_ld);
+    WS s; ws_carve(s, smem, P.cfg.height, P.cfg.width);
     load_world<false>(P, s, w);
     for (int c = threadIdx.x; c < C; c += WT) s.src[c] = (uint16_t)c;
     __syncthreads();
@@ -622,13 +684,13 @@ int world_prepare(const rl_world_cfg* cfg, const rl_world_bufs* b, WParams& P, s
     RL_ARG_CHECK((int64_t)cfg->height * cfg->width <= 65535);
     RL_ARG_CHECK(cfg->n_worlds > 0 && cfg->n_genes > 0 && cfg->n_genes <= RL_MAX_GENES);
     RL_ARG_CHECK(cfg->slot_cap > 0 && cfg->slot_cap <= cfg->height * cfg->width);
-    RL_ARG_CHECK(cfg->obs_ld >= 160 && cfg->obs_ld % 4 == 0 && cfg->obs_ld <= 192);
+    RL_ARG_CHECK(cfg->obs_ld >= 160 && cfg->obs_ld % 32 == 0 && cfg->obs_ld <= 192);
     RL_ARG_CHECK(cfg->max_agents > 0);
     if (!cfg->static_families) return rl_set_err(RL_ERR_UNSUPPORTED, "static_families=False is not implemented yet");
     RL_ARG_CHECK(b->type && b->rec && b->n_agents && b->reward && b->obs_state && b->obs_prime);
-    P.cfg = *cfg; P.b = *b; P.t = 0; P.target = 0; P.max_age = 50; P.which = 0;
+    P.trace = nullptr; P.cfg = *cfg; P.b = *b; P.t = 0; P.target = 0; P.max_age = 50; P.which = 0;
     P.magicW = (uint32_t)(0x100000000ull / (uint64_t)cfg->width) + 1u;
-    smem = ws_bytes(cfg->height * cfg->width, cfg->obs_ld);
+    smem = ws_bytes(cfg->height, cfg->width);
     if (smem > 227 * 1024) return rl_set_err(RL_ERR_UNSUPPORTED, "world of %d cells needs %zu B shared memory", cfg->height * cfg->width, smem);
     if (!g_world_init) {
         float h[41];
@@ -639,6 +701,9 @@ int world_prepare(const rl_world_cfg* cfg, const rl_world_bufs* b, WParams& P, s
     if (smem > g_world_smem_max) {
         const int v = (int)smem;
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_step, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_step, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_update, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_topup, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_update, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_topup, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
@@ -666,8 +731,21 @@ int rl_world_step(const rl_world_cfg* cfg, const rl_world_bufs* bufs, uint64_t t
     int rc = world_prepare(cfg, bufs, P, smem);
     if (rc) return rc;
     P.t = t;
+    static long long* trace_dev = nullptr;
+    const bool tracing = getenv("RL_WORLD_TRACE") != nullptr && cfg->n_worlds > 77;
+    if (tracing) {
+        if (!trace_dev) RL_CUDA_CHECK(cudaMalloc(&trace_dev, 16 * sizeof(long long)));
+        P.trace = trace_dev;
+    }
     k_world_step<<<cfg->n_worlds, WT, smem, (cudaStream_t)stream>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
+    if (tracing) {
+        long long h[16];
+        RL_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+        RL_CUDA_CHECK(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[world trace] load %lld attack %lld conflict %lld execute+death %lld add_food %lld list+planes %lld observe %lld total %lld\n",
+                h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[9] - h[6], h[9] - h[0]);
+    }
     return RL_OK;
 }
 
