@@ -219,6 +219,16 @@ int rl_replay_store(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl
 int rl_replay_sample(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
                      int32_t batch, uint64_t t, int32_t* sample_idx, void* stream);
 
+/* random.sample(buffer, batch) for every EVENT row of `gene` (D3QN.py:138-142, DQN.py:99-100): uniform, WITHOUT
+ * replacement -- CPython's Random.sample restated on the counter RNG (pool method for len <= 277, set method with
+ * redraws above; population index counts from the oldest item of the deque).  `iter`/`n_iter` select the draw stream
+ * of the DQN 5-iteration loop (DQN.py:143); events whose ring holds <= min_len items (DQN.py:79: size() > 1000) or
+ * fewer than `batch` items (where the reference raises ValueError: bit 0 of *status is set, status may be NULL) get
+ * sample_idx[...] = -1 and are skipped by the learn kernels. */
+int rl_replay_sample_uniform(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                             int32_t batch, uint64_t t, int32_t iter, int32_t n_iter, int32_t min_len, int32_t* sample_idx,
+                             int32_t* status, void* stream);
+
 /* buffer.update_priorities (PERD3QN.py:177-179) for all events of `gene`, in event order, later writes win. */
 int rl_replay_update_prio(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
                           int32_t batch, const int32_t* sample_idx, const float* new_prio, void* stream);
@@ -247,6 +257,14 @@ int rl_learn_grid(void);    /* CTAs used by rl_brain_learn = rows of grad_scratc
  * rl_brain_adam afterwards (after an optional all-reduce of `grad` across ranks). */
 int rl_brain_learn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
                    const int32_t* sample_idx, const rl_learn_bufs* learn, void* stream);
+
+/* One of the 5 iterations of train(q, q_target, memory, optimizer) (Models/DQN.py:142-153) for every EVENT row of `gene`:
+ * q_a = q(s)[a], y = r + gamma * max_a q_target(s') * done_mask, smooth-L1 (mean over the 32 sampled rows), explicit
+ * backward.  learn->kind = RL_MODEL_DQN, learn->batch = 32; sample_idx [row_cap, 32] from rl_replay_sample_uniform
+ * (events marked -1 are skipped).  Gradients are summed over events into `grad`, grad[n_train] = number of events that
+ * trained; follow with rl_brain_adam -- five (sample, learn, adam) rounds make one train() call. */
+int rl_brain_learn_dqn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                       const int32_t* sample_idx, const rl_learn_bufs* learn, void* stream);
 
 /* torch.optim.Adam defaults on grad/grad[n_train] (mean over events); no-op when no event happened.
  * Also refreshes the output-major copy of W2. */

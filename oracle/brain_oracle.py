@@ -164,3 +164,128 @@ def per_sample(weights_f32, u53):
                 lo = mid + 1
         out.append(lo)
     return out
+
+
+# ------------------------------------------------------------------ uniform sampler without replacement
+def uniform_sample(n, k, bits_fn):
+    """random.sample(population, k) of CPython (Lib/random.py, Random.sample; used by D3QN.py:140 and DQN.py:100),
+    restated on a counter generator: the c-th _randbelow(m) call returns (bits_fn(c) >> 32) * m >> 32.
+    Returns k distinct population indices (0 = oldest item of the deque).  n >= k is the caller's business
+    (the reference raises ValueError otherwise)."""
+    import math
+    if not 0 <= k <= n:
+        raise ValueError("Sample larger than population or is negative")
+    c = 0
+
+    def randbelow(m):
+        nonlocal c
+        v = ((bits_fn(c) >> 32) * m) >> 32
+        c += 1
+        return v
+    setsize = 21
+    if k > 5:
+        setsize += 4 ** math.ceil(math.log(k * 3, 4))
+    result = [None] * k
+    if n <= setsize:                       # pool method
+        pool = list(range(n))
+        for i in range(k):
+            j = randbelow(n - i)
+            result[i] = pool[j]
+            pool[j] = pool[n - i - 1]
+    else:                                  # set method with redraws
+        selected = set()
+        for i in range(k):
+            j = randbelow(n)
+            while j in selected:
+                j = randbelow(n)
+            selected.add(j)
+            result[i] = j
+    return result
+
+
+# ------------------------------------------------------------------ DQN: one iteration of train() (Models/DQN.py:142-153)
+def _mlp3_parts(sd, x, names):
+    x = _t(x)
+    h1 = torch.relu(lin(x, sd[names[0] + ".weight"], sd[names[0] + ".bias"]))
+    h2 = torch.relu(lin(h1, sd[names[1] + ".weight"], sd[names[1] + ".bias"]))
+    return x, h1, h2
+
+
+def _mlp3_backward(sd, names, x, h1, h2, d_h2):
+    """Given dL/dh2 (post-ReLU activations), the gradients of the two trunk layers."""
+    g = {}
+    d_z2 = d_h2 * (h2 > 0)
+    g[names[1] + ".weight"], g[names[1] + ".bias"] = d_z2.T @ h1, d_z2.sum(0)
+    d_z1 = (d_z2 @ _t(sd[names[1] + ".weight"])) * (h1 > 0)
+    g[names[0] + ".weight"], g[names[0] + ".bias"] = d_z1.T @ x, d_z1.sum(0)
+    return g
+
+
+def dqn_iter_grads(sd, sd_target, obs, action, reward, next_obs, done_mask, gamma=0.98):
+    """(grads, loss) of ONE of the five iterations: smooth_l1_loss(q(s)[a], r + gamma * max q_target(s') * done_mask),
+    mean over the batch, beta = 1."""
+    B = len(action)
+    x, h1, h2 = _mlp3_parts(sd, obs, ("fc1", "fc2"))
+    q = lin(h2, sd["fc3.weight"], sd["fc3.bias"])
+    a = torch.as_tensor(np.asarray(action), dtype=torch.long)
+    q_a = q.gather(1, a[:, None])[:, 0]
+    max_q = torch.as_tensor(dqn_forward(sd_target, next_obs)).max(1)[0]
+    y = _t(reward) + gamma * max_q * _t(done_mask)
+    d = q_a - y
+    loss = torch.where(d.abs() < 1, 0.5 * d * d, d.abs() - 0.5).mean()
+    g_q = d.clamp(-1, 1) / B
+    d_out = torch.zeros(B, 8)
+    d_out[torch.arange(B), a] = g_q
+    grads = {"fc3.weight": d_out.T @ h2, "fc3.bias": d_out.sum(0)}
+    grads.update(_mlp3_backward(sd, ("fc1", "fc2"), x, h1, h2, d_out @ _t(sd["fc3.weight"])))
+    return {k: v.numpy() for k, v in grads.items()}, float(loss)
+
+
+# ------------------------------------------------------------------ PPO: one epoch of learn() (Models/PPO.py:136-162)
+def ppo_gae(delta, gamma, lmbda):
+    """PPO.py:143-150 under numpy >= 2 (NEP 50): `gamma * lmbda` is a python float, `advantage` becomes np.float32
+    after the first addition, so every step is float32(float32(gamma*lmbda) * adv) + delta_t in float32."""
+    gl = np.float32(gamma * lmbda)
+    adv = np.zeros(len(delta), np.float32)
+    run = np.float32(0.0)
+    for t in range(len(delta) - 1, -1, -1):
+        run = np.float32(np.float32(gl * run) + np.float32(delta[t]))
+        adv[t] = run
+    return adv
+
+
+def ppo_epoch_grads(sd, obs, action, reward, next_obs, prob_a, done, gamma=0.98, lmbda=0.95, eps_clip=0.1):
+    """(grads, loss) of ONE epoch on ONE data list of T transitions: loss.mean() with
+    loss = -min(ratio*A, clamp(ratio, 1-eps, 1+eps)*A) + smooth_l1_loss(v(s), td_target)  (the second term a scalar mean)."""
+    T = len(action)
+    names = ("fc1", "fc2")
+    x, h1, h2 = _mlp3_parts(sd, obs, names)
+    logits = lin(h2, sd["fc_pi.weight"], sd["fc_pi.bias"])
+    v = lin(h2, sd["fc_v.weight"], sd["fc_v.bias"])[:, 0]
+    _, _, h2n = _mlp3_parts(sd, next_obs, names)
+    v_next = lin(h2n, sd["fc_v.weight"], sd["fc_v.bias"])[:, 0]
+    done_mask = _t(1.0 - np.asarray(done, np.float32))
+    td = _t(reward) + gamma * v_next * done_mask
+    adv = _t(ppo_gae((td - v).numpy(), gamma, lmbda))
+    z = logits - logits.max(1, keepdim=True)[0]
+    pi = torch.exp(z) / torch.exp(z).sum(1, keepdim=True)
+    a = torch.as_tensor(np.asarray(action), dtype=torch.long)
+    pi_a = pi.gather(1, a[:, None])[:, 0]
+    ratio = torch.exp(torch.log(pi_a) - torch.log(_t(prob_a)))
+    lo, hi = np.float32(1 - eps_clip), np.float32(1 + eps_clip)
+    surr1, surr2 = ratio * adv, ratio.clamp(lo, hi) * adv
+    dv = v - td
+    sl1 = torch.where(dv.abs() < 1, 0.5 * dv * dv, dv.abs() - 0.5).mean()
+    loss = (-torch.min(surr1, surr2)).mean() + sl1
+    inside = (ratio >= lo) & (ratio <= hi)
+    d_ratio = -(adv / T) * (inside | (surr1 < surr2))
+    d_logpa = d_ratio * ratio
+    onehot = torch.zeros(T, 8)
+    onehot[torch.arange(T), a] = 1
+    d_logits = d_logpa[:, None] * (onehot - pi)
+    d_v = dv.clamp(-1, 1) / T
+    grads = {"fc_pi.weight": d_logits.T @ h2, "fc_pi.bias": d_logits.sum(0),
+             "fc_v.weight": d_v[None, :] @ h2, "fc_v.bias": d_v.sum(0, keepdim=True)}
+    d_h2 = d_logits @ _t(sd["fc_pi.weight"]) + d_v[:, None] @ _t(sd["fc_v.weight"])
+    grads.update(_mlp3_backward(sd, names, x, h1, h2, d_h2))
+    return {k: v_.numpy() for k, v_ in grads.items()}, float(loss)

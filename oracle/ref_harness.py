@@ -29,7 +29,7 @@ SITE = dict(RESET_AGENT_PLACE=1, RESET_FOOD_TRIAL=2, RESET_FOOD_PLACE=3, RESET_P
             RESET_POISON_PLACE=5, RESET_SUPER_PLACE=6, FOOD_PLACE=7, FOOD_ACCEPT=8, REPRO_TRIAL=9,
             BIRTH_PLACE=10, PRODUCE_TRIAL=11, PRODUCE_GENE=12, TOPUP_PLACE=13, TOPUP_GENE=14,
             TOPUP_HEALTH=15, TOPUP_AGE=16, ACT_EXPLORE=20, ACT_RANDOM=21, ACT_SAMPLE=22,
-            REPLAY_SAMPLE=30)
+            REPLAY_SAMPLE=30, REPLAY_SAMPLE_UNIFORM=31)
 
 
 def mix64(z):
@@ -185,6 +185,27 @@ class _BrainRandom:
 
     def randint(self, a, b):                        # DQN.py:137 (inclusive bounds)
         return a + below(CTX.bits("ACT_RANDOM", CTX.slot), b - a + 1)
+
+
+class CounterRandom(__import__("random").Random):
+    """CPython's own Random (so .sample / .choice run the stdlib algorithms unchanged) whose _randbelow is served by
+    a counter stream: the c-th call returns below(bits_fn(c), n).  Used to drive random.sample of D3QN.py:140 /
+    DQN.py:100 with the draws of RL_SITE_REPLAY_SAMPLE_UNIFORM."""
+
+    def __init__(self, bits_fn):
+        super().__init__(0)
+        self._bits_fn, self.calls = bits_fn, 0
+
+    def _randbelow(self, n):
+        v = below(self._bits_fn(self.calls), n)
+        self.calls += 1
+        return v
+
+
+def uniform_sample_bits(key, t, event_rank, it=0, n_iter=1):
+    """bits_fn of one (event, iteration) stream of RL_SITE_REPLAY_SAMPLE_UNIFORM (include/rl_rng.h)."""
+    base = ((event_rank * n_iter + it) << 9)
+    return lambda c: draw(key, t, SITE["REPLAY_SAMPLE_UNIFORM"], base + c)
 
 
 _LOADED = {}

@@ -78,6 +78,7 @@ class Tracker:
         if n_epi % self.update_interval == 0 and n_epi != 0:
             self._drain(self.k % self.ring_len)
             self.k = 0
+            self.env.check_status()
             self._average_results()
             if self.print_results:
                 self._print_results()

@@ -5,7 +5,7 @@ from .PERD3QN import PERD3QNAgent
 class D3QNAgent(PERD3QNAgent):
     PRIORITIZED = False
     METHOD = "D3QN"
-    DEVICE_LEARN = False   # uniform random.sample replay (D3QN.py:140) is not on the device yet
+    DEVICE_LEARN = True    # uniform random.sample replay (D3QN.py:138-142) = rl_replay_sample_uniform
 
     def __init__(self, input_dim=153, output_dim=8, exploration=1000, soft_update_freq=200, train_freq=20,
                  learning_rate=1e-3, gamma=0.99, batch_size=64, capacity=10000, load_model=False, training=True):

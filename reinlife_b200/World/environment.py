@@ -95,6 +95,7 @@ class Environment:
                                  dtype=torch.float64, device=self.device)
         self._seen = torch.tensor([int(getattr(b, "n_epi", 0)) for b in brains], dtype=torch.int64, device=self.device)
         self._prob = torch.zeros(self.n_worlds * self.world.S, device=self.device)
+        self._sample_status = torch.zeros(1, dtype=torch.int32, device=self.device)   # bit 0: random.sample on a short buffer
         self._act_descs = (_lib.BrainAct * G)(*[b._dev.act_desc(b.RULE, self._eps.data_ptr() + 8 * g) for g, b in enumerate(brains)])
         if self.dist:
             for b in brains:                              # identical weights on every rank
@@ -182,8 +183,13 @@ class Environment:
                                                C.byref(b._replay.bufs), st))
                 if not on[g]:
                     continue
-                _lib.check(lib.rl_replay_sample(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
-                                                C.c_int32(b._dev.batch), C.c_uint64(w.t), C.c_void_p(b._dev.sample_idx.data_ptr()), st))
+                if b.PRIORITIZED:                                   # PERD3QN.py:157-175
+                    _lib.check(lib.rl_replay_sample(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                                    C.c_int32(b._dev.batch), C.c_uint64(w.t), C.c_void_p(b._dev.sample_idx.data_ptr()), st))
+                else:                                               # random.sample(deque, 64), D3QN.py:138-142
+                    _lib.check(lib.rl_replay_sample_uniform(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                                            C.c_int32(b._dev.batch), C.c_uint64(w.t), C.c_int32(0), C.c_int32(1), C.c_int32(0),
+                                                            C.c_void_p(b._dev.sample_idx.data_ptr()), C.c_void_p(self._sample_status.data_ptr()), st))
                 if self.precision == "tf32":
                     if b._dev.wimg_stale:
                         b._dev.build_wimg(st)
@@ -234,6 +240,13 @@ class Environment:
     def agents(self):
         """World 0's agents in the reference's (row-major) order."""
         return self.agents_of(0)
+
+    def check_status(self):
+        """Raise what the reference would have raised inside the loop (device-side conditions are sticky flags, read at
+        update_interval boundaries and at the end of trainer()): ValueError of random.sample on a buffer shorter than a
+        batch (D3QN.py:140)."""
+        if int(self._sample_status) & 1:
+            raise ValueError("Sample larger than population or is negative")
 
     def count_agents(self):
         """Total listed agents on this rank (device -> host read)."""

@@ -9,8 +9,7 @@
 // One persistent CTA per SM walks the brain's EVENT list.  Activations never leave shared memory; the per-event
 // weight gradients (54k floats) are accumulated into a CTA-private, L2-resident scratch slab and summed across
 // CTAs in a fixed order afterwards (deterministic, no atomics).
-#include "mlp_tile.cuh"
-#include "models.cuh"
+#include "learn_tile.cuh"
 
 namespace {
 
@@ -25,91 +24,6 @@ struct LearnParams {
     rl_learn_bufs lb;
     int32_t n_cta;
 };
-
-__device__ __forceinline__ float block_sum(float v, float* red) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane_id() == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float r = 0.f;
-#pragma unroll
-    for (int i = 0; i < NT / 32; ++i) r += red[i];
-    __syncthreads();
-    return r;
-}
-
-// G[m][n] += sum_b A[b][m] * B[b][n]   (b < 64; A, B in shared memory; G = CTA-private global slab, row-major [M][N])
-template <int M, int N, int TM, int TN>
-__device__ __forceinline__ void outer_accum(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-                                            float* __restrict__ G) {
-    constexpr int NG = TN / 4, GS = N / NG;
-    static_assert((M / TM) * (N / TN) == NT && TM % 4 == 0 && TN % 4 == 0, "thread tiling");
-    const int tx = threadIdx.x % (N / TN), ty = threadIdx.x / (N / TN);
-    float acc[TM][TN];
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-#pragma unroll 2
-    for (int b = 0; b < R; ++b) {
-        float av[TM], bv[TN];
-#pragma unroll
-        for (int i4 = 0; i4 < TM / 4; ++i4) {
-            const float4 t = *reinterpret_cast<const float4*>(A + (size_t)b * lda + ty * TM + i4 * 4);
-            av[i4 * 4 + 0] = t.x; av[i4 * 4 + 1] = t.y; av[i4 * 4 + 2] = t.z; av[i4 * 4 + 3] = t.w;
-        }
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const float4 t = *reinterpret_cast<const float4*>(B + (size_t)b * ldb + g * GS + tx * 4);
-            bv[g * 4 + 0] = t.x; bv[g * 4 + 1] = t.y; bv[g * 4 + 2] = t.z; bv[g * 4 + 3] = t.w;
-        }
-#pragma unroll
-        for (int i = 0; i < TM; ++i)
-#pragma unroll
-            for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    }
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            float4* p = reinterpret_cast<float4*>(G + (size_t)(ty * TM + i) * N + g * GS + tx * 4);
-            float4 o = *p;
-            o.x += acc[i][g * 4 + 0]; o.y += acc[i][g * 4 + 1]; o.z += acc[i][g * 4 + 2]; o.w += acc[i][g * 4 + 3];
-            *p = o;
-        }
-}
-
-// G[n] += sum_b B[b][n]
-template <int N>
-__device__ __forceinline__ void colsum_accum(const float* __restrict__ B, int ldb, float* __restrict__ G) {
-    for (int n = threadIdx.x; n < N; n += NT) {
-        float s = 0.f;
-#pragma unroll 8
-        for (int b = 0; b < R; ++b) s += B[(size_t)b * ldb + n];
-        G[n] += s;
-    }
-}
-
-__device__ __forceinline__ void gather64(float* dst, int ldd, const float* __restrict__ src, const int* ids) {
-    for (int v = threadIdx.x; v < R * (RL_K1 / 4); v += NT) {
-        const int r = v / (RL_K1 / 4), c4 = v - r * (RL_K1 / 4);
-        *reinterpret_cast<float4*>(dst + (size_t)r * ldd + c4 * 4) =
-            __ldg(reinterpret_cast<const float4*>(src + (size_t)ids[r] * RL_K1) + c4);
-    }
-}
-
-template <int N2, int NH>
-__device__ __forceinline__ void head64(const float* H2, int ldh, const float* Wh_s, float* OUT) {
-    for (int o = threadIdx.x; o < R * NH; o += NT) {
-        const int r = o / NH, j = o - r * NH;
-        const float* h = H2 + (size_t)r * ldh;
-        float acc = Wh_s[N2 * NH + j];
-#pragma unroll 8
-        for (int k = 0; k < N2; ++k) acc = fmaf(h[k], Wh_s[k * NH + j], acc);
-        OUT[r * 16 + j] = acc;
-    }
-    __syncthreads();
-}
 
 constexpr int LDX = RL_K1 + 4, LDH1 = 128 + 4, LDH2 = 256 + 4, WHN = 256 * 9 + 16;
 constexpr size_t LEARN_SMEM =
@@ -153,6 +67,7 @@ __global__ void __launch_bounds__(NT, 1) k_learn_dueling(const LearnParams P) {
     for (int e = blockIdx.x; e < total; e += gridDim.x) {
         const int w = P.ev_rows[e] / S;
         const size_t ring = (size_t)w * cap;
+        if (P.sample_idx[(size_t)e * R] < 0) continue;     // event skipped by the uniform sampler (ring shorter than a batch)
         if (threadIdx.x < R) {
             const int i = P.sample_idx[(size_t)e * R + threadIdx.x];
             idx[threadIdx.x] = i;

@@ -19,6 +19,8 @@ struct ReplayParams {
     uint64_t t;
     int32_t* sample_idx;
     const float* new_prio;
+    int32_t* status;
+    int32_t iter, n_iter, min_len;      // uniform sampler: draw stream of (event, iter); rings with len <= min_len are skipped
 };
 
 __device__ __forceinline__ float pw_of(float p) { return (float)pow((double)p, 0.6); }   // PERD3QN.py:162 (alpha)
@@ -141,6 +143,70 @@ __global__ void __launch_bounds__(RT) k_replay_sample(const ReplayParams P) {
     }
 }
 
+// ---- uniform sampling WITHOUT replacement: random.sample(deque, k) (Models/D3QN.py:140, Models/DQN.py:100) ----
+// CPython's algorithm (Lib/random.py, Random.sample) restated on the counter RNG: population index j counts from the
+// OLDEST item of the deque (ring slot (pos - len + j) mod capacity).
+//   n <= 277 (k in 6..85: setsize = 21 + 4^4): pool method -- j = below(n-i); result[i] = pool[j]; pool[j] = pool[n-i-1]
+//   n  > 277: set method -- j = below(n), redrawn while j was already selected.
+// Draw c of (event e, iteration it) is rl_draw(key, t, RL_SITE_REPLAY_SAMPLE_UNIFORM, ((e*n_iter + it) << 9) + c).
+// One warp per event; the set method consumes 32 draws per round and accepts first occurrences in draw order, which
+// is exactly the sequential accept/reject sequence because every draw is a pure function of its counter.
+constexpr int POOL_MAX = 277;
+
+__global__ void __launch_bounds__(RT) k_replay_sample_uniform(const ReplayParams P) {
+    __shared__ uint16_t pool_s[RT / 32][POOL_MAX + 3];
+    __shared__ int sel_s[RT / 32][128];
+    const int w = blockIdx.x, NW = P.cfg.n_worlds, cap = P.rp.capacity, k = P.batch;
+    const int gk = P.gene * RL_N_ROW_KINDS + RL_ROWS_EVENT;
+    const int cnt = P.rows.count[(size_t)gk * NW + w];
+    if (cnt == 0) return;
+    const int off = P.rows.offset[(size_t)gk * NW + w];
+    const int n = P.rp.len[w], pos = P.rp.pos[w];
+    const int first = ((pos - n) % cap + cap) % cap;                // ring slot of the oldest item
+    const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    uint16_t* pool = pool_s[warp];
+    int* sel = sel_s[warp];
+    for (int e = warp; e < cnt; e += RT / 32) {
+        if (off + e >= P.rows.row_cap) break;
+        int32_t* out = P.sample_idx + (size_t)(off + e) * k;
+        const uint32_t base = ((uint32_t)(e * P.n_iter + P.iter)) << 9;
+        if (n <= P.min_len || n < k) {                              // skipped event (DQN.py:79) / reference raises ValueError
+            for (int i = lane; i < k; i += 32) out[i] = -1;
+            if (n > P.min_len && lane == 0 && P.status) atomicOr(P.status, 1);   // random.sample would raise ValueError
+            continue;
+        }
+        if (n <= POOL_MAX) {
+            for (int i = lane; i < n; i += 32) pool[i] = (uint16_t)i;
+            __syncwarp();
+            if (lane == 0) {
+                for (int i = 0; i < k; ++i) {
+                    const int j = (int)rl_below(rl_draw(key, P.t, RL_SITE_REPLAY_SAMPLE_UNIFORM, base + i), (uint32_t)(n - i));
+                    sel[i] = pool[j];
+                    pool[j] = pool[n - i - 1];
+                }
+            }
+            __syncwarp();
+        } else {
+            int nsel = 0;
+            for (uint32_t c = 0; nsel < k; c += 32) {
+                const int j = (int)rl_below(rl_draw(key, P.t, RL_SITE_REPLAY_SAMPLE_UNIFORM, base + c + lane), (uint32_t)n);
+                bool dup = false;
+                for (int i = 0; i < nsel; ++i) dup |= sel[i] == j;
+                const unsigned m = __match_any_sync(0xffffffffu, j);
+                const bool ok = !dup && (__ffs(m) - 1) == lane;
+                const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                const int rank = nsel + __popc(bal & lanemask_lt());
+                if (ok && rank < k) sel[rank] = j;
+                nsel = min(k, nsel + __popc(bal));
+                __syncwarp();
+            }
+        }
+        for (int i = lane; i < k; i += 32) { int p = first + sel[i]; out[i] = p >= cap ? p - cap : p; }
+        __syncwarp();
+    }
+}
+
 // ---- update_priorities: warp per world, sequential over events, later writes win ----
 __global__ void __launch_bounds__(RT) k_replay_update_prio(const ReplayParams P) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -175,7 +241,7 @@ int fill(ReplayParams& P, const rl_world_cfg* cfg, const rl_world_bufs* wb, cons
     RL_ARG_CHECK(rp->capacity > 0 && rp->len && rp->pos);
     P.cfg = *cfg;
     if (wb) P.wb = *wb;
-    P.rows = *rows; P.rp = *rp; P.gene = gene; P.batch = 0; P.t = 0; P.sample_idx = nullptr; P.new_prio = nullptr;
+    P.rows = *rows; P.rp = *rp; P.gene = gene; P.batch = 0; P.t = 0; P.sample_idx = nullptr; P.new_prio = nullptr; P.iter = 0; P.n_iter = 1; P.min_len = 0; P.status = nullptr;
     return RL_OK;
 }
 
@@ -211,6 +277,20 @@ int rl_replay_sample(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t 
         smem_set = smem;
     }
     k_replay_sample<<<cfg->n_worlds, RT, smem, (cudaStream_t)stream>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_replay_sample_uniform(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                             int32_t batch, uint64_t t, int32_t iter, int32_t n_iter, int32_t min_len, int32_t* sample_idx,
+                             int32_t* status, void* stream) {
+    ReplayParams P;
+    int rc = fill(P, cfg, nullptr, rows, gene, replay);
+    if (rc) return rc;
+    RL_ARG_CHECK(batch > 5 && batch <= 85 && sample_idx);          // setsize = 277 holds for 6 <= k <= 85 (Lib/random.py)
+    RL_ARG_CHECK(n_iter > 0 && iter >= 0 && iter < n_iter && min_len >= 0);
+    P.batch = batch; P.t = t; P.sample_idx = sample_idx; P.iter = iter; P.n_iter = n_iter; P.min_len = min_len; P.status = status;
+    k_replay_sample_uniform<<<cfg->n_worlds, RT, 0, (cudaStream_t)stream>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
     return RL_OK;
 }

@@ -135,7 +135,7 @@ __device__ __forceinline__ void prefetch_event(const TcLearnParams& P, int e) {
     const size_t ring = (size_t)(P.ev_rows[e] / S) * cap;
     for (int v = threadIdx.x; v < 2 * R * 5; v += NEPI) {
         const int which = v / (R * 5), rem = v - which * (R * 5), r = rem / 5, ln = rem - r * 5;
-        const int i = P.sample_idx[(size_t)e * R + r];
+        const int i = max(P.sample_idx[(size_t)e * R + r], 0);
         const float* p = (which ? P.rp.obs : P.rp.next_obs) + (ring + i) * RL_K1 + ln * 32;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
     }
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
             const int w = P.ev_rows[e] / S;
             const size_t ring = (size_t)w * cap;
             if (threadIdx.x < R) {
-                const int i = P.sample_idx[(size_t)e * R + threadIdx.x];
+                const int i = max(P.sample_idx[(size_t)e * R + threadIdx.x], 0);   // -1 = skipped by the uniform sampler (error state)
                 idx[threadIdx.x] = i;
                 act[threadIdx.x] = P.rp.action[ring + i];
                 rew[threadIdx.x] = P.rp.reward[ring + i];

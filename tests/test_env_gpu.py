@@ -67,3 +67,23 @@ def test_training_dqn_and_render_fail_loudly():
     env = rl.Environment(brains=[DQN(training=False)], training=False, n_worlds=1)
     with pytest.raises(NotImplementedError):
         env.render()
+
+
+def test_trainer_learns_d3qn_and_reports_short_buffer():
+    """D3QN (uniform random.sample replay, D3QN.py:138-142) trains on the device; a train event on a buffer shorter than a
+    batch surfaces as the reference's ValueError (raised at the next status check instead of inside the loop)."""
+    import reinlife_b200 as rl
+    from reinlife_b200.Models import D3QN
+    torch.manual_seed(1)
+    brains = [D3QN(exploration=12, train_freq=5, capacity=300), D3QN(exploration=12, train_freq=5, capacity=300)]
+    w_before = [b.eval_net.state_dict()["fc.weight"].clone() for b in brains]
+    env = rl.trainer(brains, n_episodes=40, width=12, height=12, max_agents=30, update_interval=10, print_results=False,
+                     save=False, n_worlds=8, seed=5, saturate_to=30, precision="fp32")
+    torch.cuda.synchronize()
+    for b, w0 in zip(brains, w_before):
+        assert int(b._dev.adam_step) > 0 and torch.isfinite(b._dev.params).all()
+        assert not torch.equal(b.eval_net.state_dict()["fc.weight"], w0)
+        assert int(b._replay.len.max()) == 300                                   # the deque is full and wrapping
+    with pytest.raises(ValueError):                                              # ~15 agents/gene x 1 step < 64 items
+        rl.trainer([D3QN(exploration=0, train_freq=2), D3QN(exploration=0, train_freq=2)], n_episodes=6, width=12, height=12,
+                   max_agents=30, print_results=False, save=False, n_worlds=4, seed=5, saturate_to=30, precision="fp32")

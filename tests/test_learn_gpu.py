@@ -196,3 +196,66 @@ def test_store_sample_update_follow_the_reference_buffer():
                     assert (rn[p_] == it[3]).all() and rd[p_] == it[4]
         vw.update(); vw.top_up(40)
     assert all(int(b.adam_step) > 0 for b in brains)
+
+
+def test_uniform_sampler_is_cpython_random_sample_on_the_ring():
+    """rl_replay_sample_uniform == oracle.uniform_sample (== stdlib Random.sample, pinned on CPU) with population index 0 =
+    oldest item of the deque (ring slot (pos - len + j) mod capacity), for both algorithm branches and a wrapped ring."""
+    import reinlife_b200._lib as L
+    from reinlife_b200.brains import ReplayRings
+    from oracle import brain_oracle as bo
+    from oracle import ref_harness as rh
+    NW, cap = 6, 400
+    vw, rows = _mk(NW)
+    rp = ReplayRings(NW, cap, "cuda", prioritized=False)
+    lens = [64, 100, 277, 278, 400, 30]
+    poss = [64, 100, 277, 278, 123, 30]          # world 4: full ring that has wrapped (oldest item at slot 123)
+    rp.len[:] = torch.tensor(lens, dtype=torch.int32).cuda(); rp.pos[:] = torch.tensor(poss, dtype=torch.int32).cuda()
+    per_world = [2, 3, 1, 9, 11, 1]
+    n_ev = _fake_events(vw, rows, per_world)
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for batch, it, n_iter, min_len in ((64, 0, 1, 0), (32, 3, 5, 90)):
+        sidx = torch.full((rows.row_cap, batch), -7, dtype=torch.int32, device="cuda")
+        status.zero_()
+        L.check(vw.lib.rl_replay_sample_uniform(C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(rp.bufs), batch, C.c_uint64(5),
+                                                it, n_iter, min_len, C.c_void_p(sidx.data_ptr()), C.c_void_p(status.data_ptr()),
+                                                vw._stream()))
+        torch.cuda.synchronize()
+        got = sidx.cpu().numpy()
+        e = 0
+        for w in range(NW):
+            key = rh.world_key(9, w)
+            for k_ev in range(per_world[w]):
+                n = lens[w]
+                if n <= min_len or n < batch:
+                    assert (got[e] == -1).all()
+                else:
+                    j = bo.uniform_sample(n, batch, rh.uniform_sample_bits(key, 5, k_ev, it, n_iter))
+                    first = (poss[w] - n) % cap
+                    assert got[e].tolist() == [(first + x) % cap for x in j], (batch, w, k_ev)
+                e += 1
+        assert int(status) == (1 if batch == 64 else 0)      # world 5 holds 30 < 64 items: the reference raises ValueError
+
+
+def test_three_d3qn_train_events_match_reference_train():
+    """D3QNAgent.train() (Models/D3QN.py:97-116) x3 through the same event kernel (uniform replay, no priorities)."""
+    from reinlife_b200 import _lib
+    from reinlife_b200.brains import DeviceBrain, ReplayRings
+    z = golden()
+    vw, rows = _mk(1)
+    brain = DeviceBrain(0, state_dict("train_d3qn/w0"), "cuda", lr=1e-3, gamma=0.99)
+    brain.load_state_dict(state_dict("train_d3qn/target"), target=True)
+    brain.alloc_learn(rows.row_cap)
+    rp = ReplayRings(1, 512, "cuda", prioritized=False)
+    _fake_events(vw, rows, [1])
+    for step in range(3):
+        p = f"train_d3qn/s{step}/"
+        _fill_ring(rp, 0, z[p + "obs"], z[p + "action"], z[p + "reward"], z[p + "next_obs"], z[p + "done"])
+        brain.sample_idx[0] = torch.arange(64, dtype=torch.int32).cuda()
+        _lib.check(vw.lib.rl_brain_learn(C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(rp.bufs),
+                                         C.c_void_p(brain.sample_idx.data_ptr()), C.byref(brain.learn_bufs), vw._stream()))
+        _lib.check(vw.lib.rl_brain_adam(C.byref(brain.learn_bufs), vw._stream()))
+        torch.cuda.synchronize()
+        got, want = brain.state_dict(), state_dict(p + "w")
+        for k in want:
+            np.testing.assert_allclose(got[k].numpy(), want[k], rtol=0, atol=1e-5, err_msg=f"step {step} {k}")
