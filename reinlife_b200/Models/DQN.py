@@ -15,9 +15,10 @@ batch_size = 32
 
 class DQNAgent(DeviceBrainBase):
     KIND, RULE, PRIORITIZED, HAS_TARGET = packing.DQN, _lib.ACT_DQN, False, True
+    DEVICE_LEARN = True
 
     def __init__(self, input_dim=153, output_dim=8, max_epi=0, learning_rate=0.0005, train_freq=20,
-                 load_model=False, training=True):
+                 load_model=False, training=True, *, buffer_limit=buffer_limit):
         super().__init__(input_dim, output_dim, "DQN")
         if input_dim != 153 or output_dim != 8:
             raise ValueError("the device brains are specialised for ReinLife's 153-float observation and 8 actions")
@@ -32,6 +33,10 @@ class DQNAgent(DeviceBrainBase):
         self.epsilon = 0.20
         self.train_freq = train_freq
         self.training = training
+        # module constant in the reference (DQN.py:15: deque(maxlen=50000) per brain); one ring per (world, brain) here,
+        # so many-world runs pass a smaller keyword-only `buffer_limit`.  train() needs size() > 1000 (DQN.py:79).
+        self.buffer_limit = int(buffer_limit)
+        self.min_buffer = 1000
         if not self.training:
             self.epsilon = 0
         if load_model:
@@ -39,8 +44,8 @@ class DQNAgent(DeviceBrainBase):
 
     def _lr(self): return self.learning_rate
     def _gamma(self): return gamma
-    def _batch(self): return 64
-    def _capacity(self): return buffer_limit
+    def _batch(self): return batch_size
+    def _capacity(self): return self.buffer_limit
 
     def _sched(self):
         if self.training and self.max_epi == 0:
@@ -59,4 +64,5 @@ class DQNAgent(DeviceBrainBase):
         return int(np.argmax(q))
 
     def learn(self, age, dead, action, state, reward, state_prime, done):
-        raise NotImplementedError("DQN training on the device is not implemented yet (inference / tester path only)")
+        raise NotImplementedError("per-agent learn() is replaced by Environment.learn(n_epi), which batches every "
+                                  "agent of every world (reinlife_b200.Helpers.trainer drives it)")

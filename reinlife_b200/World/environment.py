@@ -159,12 +159,13 @@ class Environment:
 
     def learn(self, n_epi: int = 0):
         """for agent in env.agents: agent.learn(n_epi=n_epi)   (Helpers/trainer.py:95-96), batched:
-        all stores of the step, then every train() trigger as one 64-row event, per-event gradients averaged
-        (all-reduced across ranks), ONE Adam step per brain, then priorities, then the target sync rule."""
+        all stores of the step, then every train() trigger of every world as one event against the same pre-step
+        weights, per-event gradients averaged (all-reduced across ranks), ONE optimizer step per brain and per
+        reference optimizer step (1 for D3QN/PERD3QN, 5 for DQN's train(), k_epoch for PPO), then priorities / target
+        sync exactly where the reference does them."""
         if not self.training:
             return
         w, lib = self.world, self.world.lib
-        G = len(self.brains)
         trainable = [g for g, b in enumerate(self.brains) if b._trains()]
         for g, b in enumerate(self.brains):
             if g not in trainable and getattr(b, "training", True):
@@ -175,52 +176,82 @@ class Environment:
         tf = [int(getattr(b, "train_freq", 1)) for b in self.brains]
         on = [int(b._trains() and n_epi > getattr(b, "exploration", -1)) for b in self.brains]
         self.rows.build(kinds_mask=6, train_freq=tf, event_on=on)
+        self.gpu_launches += 3
         st = w._stream()
         with torch.cuda.device(self.device):
-            for g in trainable:
+            for g in trainable:                                   # brain.memorize / put_data for every age > 1 agent
                 b = self.brains[g]
                 _lib.check(lib.rl_replay_store(C.byref(w.cfg), C.byref(w.bufs), C.byref(self.rows.bufs), C.c_int32(g),
                                                C.byref(b._replay.bufs), st))
-                if not on[g]:
-                    continue
-                if b.PRIORITIZED:                                   # PERD3QN.py:157-175
-                    _lib.check(lib.rl_replay_sample(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
-                                                    C.c_int32(b._dev.batch), C.c_uint64(w.t), C.c_void_p(b._dev.sample_idx.data_ptr()), st))
-                else:                                               # random.sample(deque, 64), D3QN.py:138-142
-                    _lib.check(lib.rl_replay_sample_uniform(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
-                                                            C.c_int32(b._dev.batch), C.c_uint64(w.t), C.c_int32(0), C.c_int32(1), C.c_int32(0),
-                                                            C.c_void_p(b._dev.sample_idx.data_ptr()), C.c_void_p(self._sample_status.data_ptr()), st))
-                if self.precision == "tf32":
-                    if b._dev.wimg_stale:
-                        b._dev.build_wimg(st)
-                        b._dev.wimg_stale = False
-                        self.gpu_launches += 2
-                    _lib.check(lib.rl_brain_learn_tc(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
-                                                     C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs),
-                                                     C.c_void_p(b._dev.wimg_e.data_ptr()), C.c_void_p(b._dev.wimg_t.data_ptr()), st))
-                else:
-                    _lib.check(lib.rl_brain_learn(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
-                                                  C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs), st))
-                self.gpu_launches += 4
-            active = [g for g in trainable if on[g]]
-            if self.dist and active:
-                self._allreduce_grads(active)
-            for g in active:
-                b = self.brains[g]
-                _lib.check(lib.rl_brain_adam(C.byref(b._dev.learn_bufs), st))
+                self.gpu_launches += 1
+            self._learn_dueling([g for g in trainable if on[g] and self.brains[g].KIND == _lib.MODEL_DUELING], n_epi, st)
+            for g in trainable:
+                if on[g] and self.brains[g].KIND == _lib.MODEL_DQN:
+                    self._learn_dqn(g, st)
+
+    def _learn_dueling(self, active, n_epi, st):
+        """PERD3QN / D3QN: learn() -> train() (PERD3QN.py:94-125, D3QN.py:97-126)."""
+        if not active:
+            return
+        w, lib = self.world, self.world.lib
+        for g in active:
+            b = self.brains[g]
+            if b.PRIORITIZED:                                   # PERD3QN.py:157-175
+                _lib.check(lib.rl_replay_sample(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                                C.c_int32(b._dev.batch), C.c_uint64(w.t), C.c_void_p(b._dev.sample_idx.data_ptr()), st))
+            else:                                               # random.sample(deque, 64), D3QN.py:138-142
+                _lib.check(lib.rl_replay_sample_uniform(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                                        C.c_int32(b._dev.batch), C.c_uint64(w.t), C.c_int32(0), C.c_int32(1), C.c_int32(0),
+                                                        C.c_void_p(b._dev.sample_idx.data_ptr()), C.c_void_p(self._sample_status.data_ptr()), st))
+            if self.precision == "tf32":
+                if b._dev.wimg_stale:
+                    b._dev.build_wimg(st)
+                    b._dev.wimg_stale = False
+                    self.gpu_launches += 2
+                _lib.check(lib.rl_brain_learn_tc(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                                 C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs),
+                                                 C.c_void_p(b._dev.wimg_e.data_ptr()), C.c_void_p(b._dev.wimg_t.data_ptr()), st))
+            else:
+                _lib.check(lib.rl_brain_learn(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                              C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs), st))
+            self.gpu_launches += 3
+        if self.dist:
+            self._allreduce_grads(active)
+        for g in active:
+            b = self.brains[g]
+            _lib.check(lib.rl_brain_adam(C.byref(b._dev.learn_bufs), st))
+            self.gpu_launches += 2
+            if b.PRIORITIZED:
                 _lib.check(lib.rl_replay_update_prio(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
                                                      C.c_int32(b._dev.batch), C.c_void_p(b._dev.sample_idx.data_ptr()),
                                                      C.c_void_p(b._dev.new_prio.data_ptr()), st))
-                self.gpu_launches += 3
-                synced = n_epi % int(b.soft_update_freq) == 0
-                if synced:                                        # PERD3QN.py:124-125, only if learn() was called
-                    cond = self.rows.total.data_ptr() + 4 * (g * _lib.N_ROW_KINDS + _lib.ROWS_STORE)
-                    sync_target(b._dev, w, cond)
-                    self.gpu_launches += 1
-                if self.precision == "tf32":                      # operand images follow the parameters
-                    b._dev.build_wimg(st, "both" if synced else "eval")
-                    self.gpu_launches += 2 if synced else 1
-        self.gpu_launches += 3
+                self.gpu_launches += 1
+            synced = n_epi % int(b.soft_update_freq) == 0
+            if synced:                                        # PERD3QN.py:124-125, only if learn() was called
+                cond = self.rows.total.data_ptr() + 4 * (g * _lib.N_ROW_KINDS + _lib.ROWS_STORE)
+                sync_target(b._dev, w, cond)
+                self.gpu_launches += 1
+            if self.precision == "tf32":                      # operand images follow the parameters
+                b._dev.build_wimg(st, "both" if synced else "eval")
+                self.gpu_launches += 2 if synced else 1
+
+    def _learn_dqn(self, g, st):
+        """DQN: learn() -> train() (DQN.py:78-89, 142-153): if the ring holds > 1000 items, 5 x (random.sample 32,
+        smooth-L1, Adam step); then target <- agent at every trigger, trained or not."""
+        w, lib, b = self.world, self.world.lib, self.brains[g]
+        for it in range(5):
+            _lib.check(lib.rl_replay_sample_uniform(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                                    C.c_int32(32), C.c_uint64(w.t), C.c_int32(it), C.c_int32(5), C.c_int32(b.min_buffer),
+                                                    C.c_void_p(b._dev.sample_idx.data_ptr()), None, st))
+            _lib.check(lib.rl_brain_learn_dqn(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                              C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs), st))
+            if self.dist:
+                self._allreduce_grads([g])
+            _lib.check(lib.rl_brain_adam(C.byref(b._dev.learn_bufs), st))
+            self.gpu_launches += 6
+        cond = self.rows.total.data_ptr() + 4 * (g * _lib.N_ROW_KINDS + _lib.ROWS_EVENT)
+        sync_target(b._dev, w, cond)
+        self.gpu_launches += 1
 
     def _allreduce_grads(self, active):
         """One NCCL all-reduce (sum) over the flattened gradient (+event count) of every active brain."""

@@ -55,13 +55,14 @@ def test_tester_inference_dqn_pretrained_weights():
     assert a == int(np.argmax(z["dqn_q_rows"][0]))
 
 
-def test_training_dqn_and_render_fail_loudly():
+def test_unimplemented_paths_fail_loudly():
     import reinlife_b200 as rl
     from reinlife_b200.Models import DQN, PERDQN
     with pytest.raises(ZeroDivisionError):
         rl.trainer([DQN()], n_episodes=1, save=False, n_worlds=2)           # DQN(max_epi=0) while training (DQN.py:69)
+    from reinlife_b200.Models import PPO
     with pytest.raises(NotImplementedError):
-        rl.trainer([DQN(max_epi=10)], n_episodes=30, save=False, n_worlds=2, saturate_to=20)
+        rl.trainer([PPO()], n_episodes=30, save=False, n_worlds=2, saturate_to=20)
     with pytest.raises(NotImplementedError):
         PERDQN()
     env = rl.Environment(brains=[DQN(training=False)], training=False, n_worlds=1)
@@ -87,3 +88,23 @@ def test_trainer_learns_d3qn_and_reports_short_buffer():
     with pytest.raises(ValueError):                                              # ~15 agents/gene x 1 step < 64 items
         rl.trainer([D3QN(exploration=0, train_freq=2), D3QN(exploration=0, train_freq=2)], n_episodes=6, width=12, height=12,
                    max_agents=30, print_results=False, save=False, n_worlds=4, seed=5, saturate_to=30, precision="fp32")
+
+
+def test_trainer_learns_dqn():
+    """DQN trains on the device: 5 Adam steps per step with a train trigger once a ring holds > 1000 items (DQN.py:79),
+    target <- agent after every trigger (DQN.py:81), linear epsilon (DQN.py:67-69)."""
+    import reinlife_b200 as rl
+    from reinlife_b200.Models import DQN
+    torch.manual_seed(2)
+    b = DQN(max_epi=200, train_freq=5, buffer_limit=1500)
+    w0 = b.agent.state_dict()["fc1.weight"].clone()
+    env = rl.trainer([b], n_episodes=60, width=12, height=12, max_agents=40, update_interval=20, print_results=False,
+                     save=False, n_worlds=6, seed=8, saturate_to=40)
+    torch.cuda.synchronize()
+    assert int(b._replay.len.max()) == 1500
+    steps = int(b._dev.adam_step)
+    assert steps > 0 and steps % 5 == 0
+    assert torch.isfinite(b._dev.params).all() and not torch.equal(b.agent.state_dict()["fc1.weight"], w0)
+    for k, v in b.agent.state_dict().items():                       # target == agent after the last trigger
+        assert torch.equal(v, b.target.state_dict()[k])
+    assert abs(env.epsilons()[0] - max(0.01, 0.20 - 0.20 * (60 / 200))) < 1e-12

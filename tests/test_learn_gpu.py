@@ -259,3 +259,94 @@ def test_three_d3qn_train_events_match_reference_train():
         got, want = brain.state_dict(), state_dict(p + "w")
         for k in want:
             np.testing.assert_allclose(got[k].numpy(), want[k], rtol=0, atol=1e-5, err_msg=f"step {step} {k}")
+
+
+def _golden2():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "brain_golden2.npz"))
+
+
+def _sd2(z, prefix):
+    pre = prefix + "/"
+    return {k[len(pre):]: z[k] for k in z.files if k.startswith(pre) and "/" not in k[len(pre):]}
+
+
+def test_dqn_five_iterations_match_reference_train():
+    """train(q, q_target, memory, optimizer) (Models/DQN.py:142-153): the 5 (sample 32, smooth-L1, Adam) rounds of ONE
+    train() call through rl_brain_learn_dqn + rl_brain_adam vs the weights the reference had after every optimizer step."""
+    from reinlife_b200 import _lib
+    from reinlife_b200.brains import DeviceBrain, ReplayRings
+    z = _golden2()
+    vw, rows = _mk(1)
+    brain = DeviceBrain(1, _sd2(z, "train_dqn/w0"), "cuda", lr=5e-4, gamma=0.98, batch=32)
+    brain.load_state_dict(_sd2(z, "train_dqn/target"), target=True)
+    brain.alloc_learn(rows.row_cap)
+    rp = ReplayRings(1, 64, "cuda", prioritized=False)
+    _fake_events(vw, rows, [1])
+    for it in range(5):
+        p = f"train_dqn/i{it}/"
+        _fill_ring(rp, 0, z[p + "obs"], z[p + "action"], z[p + "reward"], z[p + "next_obs"], 1.0 - z[p + "done_mask"])
+        brain.sample_idx[0] = torch.arange(32, dtype=torch.int32).cuda()
+        _lib.check(vw.lib.rl_brain_learn_dqn(C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(rp.bufs),
+                                             C.c_void_p(brain.sample_idx.data_ptr()), C.byref(brain.learn_bufs), vw._stream()))
+        _lib.check(vw.lib.rl_brain_adam(C.byref(brain.learn_bufs), vw._stream()))
+        torch.cuda.synchronize()
+        got, want = brain.state_dict(), _sd2(z, p + "w")
+        for k in want:
+            np.testing.assert_allclose(got[k].numpy(), want[k], rtol=0, atol=1e-5, err_msg=f"iter {it} {k}")
+    assert int(brain.adam_step) == 5
+
+
+def test_dqn_batched_events_equal_mean_of_event_gradients_and_skip_short_rings():
+    """N events in one iteration == oracle mean of per-event gradients; events flagged -1 by the sampler (ring <= 1000
+    items, DQN.py:79) contribute nothing and are not counted."""
+    from reinlife_b200 import _lib
+    from reinlife_b200.brains import DeviceBrain, ReplayRings
+    from reinlife_b200.Models import packing
+    from oracle import brain_oracle as bo
+    z, z1 = _golden2(), golden()
+    rng = np.random.default_rng(3)
+    NW, per_world, cap = 4, [2, 1, 0, 4], 128
+    vw, rows = _mk(NW)
+    w0, tgt = _sd2(z, "train_dqn/w0"), _sd2(z, "train_dqn/target")
+    brain = DeviceBrain(1, w0, "cuda", lr=5e-4, gamma=0.98, batch=32)
+    brain.load_state_dict(tgt, target=True)
+    brain.alloc_learn(rows.row_cap)
+    rp = ReplayRings(NW, cap, "cuda", prioritized=False)
+    obs_all, rings = z1["obs"], []
+    for w in range(NW):
+        n = 100
+        o = obs_all[rng.integers(0, 512, n)]; no = obs_all[rng.integers(0, 512, n)]
+        a = rng.integers(0, 8, n); r = rng.choice([0.0, 0.2, 0.5, -3.0, -20.0], n); d = (r < 0).astype(np.float64)
+        _fill_ring(rp, w, o, a, r, no, d)
+        rings.append((o, a, r, no, d))
+    n_ev = _fake_events(vw, rows, per_world)
+    sidx = rng.integers(0, 100, size=(n_ev, 32)).astype(np.int32)
+    skipped = {1, 5}
+    for e in skipped:
+        sidx[e] = -1
+    brain.sample_idx[:n_ev] = torch.from_numpy(sidx).cuda()
+    _lib.check(vw.lib.rl_brain_learn_dqn(C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(rp.bufs),
+                                         C.c_void_p(brain.sample_idx.data_ptr()), C.byref(brain.learn_bufs), vw._stream()))
+    torch.cuda.synchronize()
+    acc, losses, e = None, {}, 0
+    for w in range(NW):
+        o, a, r, no, d = rings[w]
+        for _ in range(per_world[w]):
+            if e not in skipped:
+                i = sidx[e]
+                g, loss = bo.dqn_iter_grads(w0, tgt, o[i], a[i], r[i], no[i], 1.0 - d[i])
+                losses[e] = loss
+                acc = g if acc is None else {k: acc[k] + g[k] for k in g}
+            e += 1
+    n_valid = n_ev - len(skipped)
+    grad = brain.grad.cpu().numpy()
+    nt = brain.dims.n_train
+    assert grad[nt] == n_valid
+    got = packing.unpack(1, np.concatenate([grad[:nt] / n_valid * packing.grad_mask(1), np.zeros(brain.dims.n_total - nt, np.float32)]))
+    for k in acc:
+        ref = acc[k] / n_valid
+        np.testing.assert_allclose(got[k].numpy(), ref, rtol=2e-4, atol=2e-5 * max(1.0, np.abs(ref).max()), err_msg=k)
+    loss_dev = brain.loss[:n_ev].cpu().numpy()
+    for e, l in losses.items():
+        np.testing.assert_allclose(loss_dev[e], l, rtol=2e-4, atol=1e-4)
