@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libreinlife_b200.so")
+LIB_PATH = os.environ.get("REINLIFE_B200_LIB") or os.path.join(_HERE, "libreinlife_b200.so")   # override: A/B builds
 
 OBS_DIM = 153
 N_ACTIONS = 8

@@ -7,6 +7,7 @@
 // entities.py:145-248; closed forms: SURVEY.md Appendix A.3-A.6 (validated against the reference
 // through oracle/rl_oracle.c, which keeps the sequential formulation).
 #include <stdlib.h>
+#include <cuda_fp16.h>
 #include "rl_common.cuh"
 
 namespace {
@@ -14,7 +15,6 @@ namespace {
 constexpr int WT = 256;         // threads per world
 constexpr int WNW = WT / 32;    // warps per world
 
-__constant__ float c_hratio[41];  // float32(float64(10*(k-20))/200.0): health/max_health for multiples of 10
 
 enum { M_ALIVE = 0, M_NFOOD, M_NPOISON, M_NSUPER, M_NB, M_PRESENT, M_ANY, M_PALL, M_ALIVE_G = 8,
        M_CNT_G = M_ALIVE_G + RL_MAX_GENES, M_PG = M_CNT_G + RL_MAX_GENES, M_WORDS = M_PG + RL_MAX_GENES };
@@ -25,16 +25,22 @@ struct WParams {
     rl_world_bufs b;
     uint64_t t;
     int32_t target, max_age, which;
+    int32_t dbg;        // RL_WORLD_DEBUG bits (timing experiments only): 1 skip row stores, 2 skip observe, 4 early exit after sim
     uint32_t magicW;
 };
 
 struct WS {
-    float* planes;      // [3][(H+6)*(W+6)] toroidally padded observation planes: food, health, dead-agent gene (or -2)
-    float* ascal;       // [WNW][32][8] per-warp batch of agent scalars (6 observation scalars + 2 zeros)
+    uint32_t* planes;   // [2][(H+6)*(W+6)] toroidally padded observation planes: [0] half2 {food, dead-agent gene or -2}
+                        // (all values exact in fp16), [1] float health ratio
+    float* ascal;       // [WNW][16][8] per-warp batch of agent scalars (6 observation scalars + 2 zeros)
     uint32_t* mask;     // [Cw] empty cells
     uint32_t* amask;    // [Cw] agent cells / eligible parents
     uint32_t* wpre;     // [Cw] exclusive popc prefix of amask
     int32_t* misc;      // [M_WORDS]
+    int32_t* offtab;    // [160] row element e -> offset into the padded planes (window elements), 0 for scalars/pad
+    int32_t* rowmap;    // [H+6] padded row -> source row * W     (Grid.fov's toroidal concatenate, grid.py:99-115)
+    int32_t* colmap;    // [W+6] padded column -> source column
+    float* rtab;        // [RL_MAX_GENES][4] reward by (gene, dead, killed)  (_get_rewards, environment.py:291-311)
     int16_t *health, *age, *maxage;
     uint16_t *aslot, *tgt, *src, *cellof;
     uint8_t *type, *ntype, *flags, *gene;
@@ -44,7 +50,8 @@ struct WS {
 __host__ __device__ inline size_t ws_bytes(int H, int W) {
     const size_t C = (size_t)H * W, Cw = (C + 31) / 32, Cp = (C + 15) & ~(size_t)15;
     const size_t PADN = ((size_t)(H + 6) * (W + 6) + 3) & ~(size_t)3;
-    return 4 * 3 * PADN + 4 * WNW * 32 * 8 + 4 * ((Cw + 3) & ~(size_t)3) * 3 + 4 * M_WORDS + 2 * Cp * 7 + Cp * 5;
+    const size_t TAB = 160 + (((size_t)H + 6 + 3) & ~(size_t)3) + (((size_t)W + 6 + 3) & ~(size_t)3) + RL_MAX_GENES * 4;
+    return 4 * 2 * PADN + 4 * WNW * 16 * 8 + 4 * ((Cw + 3) & ~(size_t)3) * 3 + 4 * M_WORDS + 4 * TAB + 2 * Cp * 7 + Cp * 5;
 }
 
 __device__ inline void ws_carve(WS& s, unsigned char* base, int H, int W) {
@@ -53,12 +60,16 @@ __device__ inline void ws_carve(WS& s, unsigned char* base, int H, int W) {
     const size_t Cp = (C + 15) & ~(size_t)15;
     const size_t PADN = ((size_t)(H + 6) * (W + 6) + 3) & ~(size_t)3;
     unsigned char* p = base;
-    s.planes = (float*)p; p += 4 * 3 * PADN;
-    s.ascal = (float*)p; p += 4 * WNW * 32 * 8;
+    s.planes = (uint32_t*)p; p += 4 * 2 * PADN;
+    s.ascal = (float*)p; p += 4 * WNW * 16 * 8;
     s.mask = (uint32_t*)p; p += 4 * Cw;
     s.amask = (uint32_t*)p; p += 4 * Cw;
     s.wpre = (uint32_t*)p; p += 4 * Cw;
     s.misc = (int32_t*)p; p += 4 * M_WORDS;
+    s.offtab = (int32_t*)p; p += 4 * 160;
+    s.rowmap = (int32_t*)p; p += 4 * (((size_t)H + 6 + 3) & ~(size_t)3);
+    s.colmap = (int32_t*)p; p += 4 * (((size_t)W + 6 + 3) & ~(size_t)3);
+    s.rtab = (float*)p; p += 4 * RL_MAX_GENES * 4;
     s.health = (int16_t*)p; p += 2 * Cp;
     s.age = (int16_t*)p; p += 2 * Cp;
     s.maxage = (int16_t*)p; p += 2 * Cp;
@@ -139,13 +150,35 @@ __device__ __forceinline__ void build_empty_mask(const uint8_t* tarr, uint32_t* 
     }
 }
 
+// per-CTA lookup tables of the observation phase (pure functions of H, W): computed once by the first threads
+__device__ __forceinline__ void init_tables(const WParams& P, WS& s) {
+    const int H = P.cfg.height, W = P.cfg.width, PW = W + 6;
+    const int PADN = (((H + 6) * PW) + 3) & ~3;
+    const int t = threadIdx.x;
+    if (t < 160) {
+        const int pl = t / 49, q = t - pl * 49;
+        s.offtab[t] = t < 147 ? (pl == 1 ? PADN : 0) + (q / 7) * PW + (q - (q / 7) * 7) : 0;   // food / gene share plane 0
+    }
+    for (int k = t; k < H + 6; k += WT) { int si = k - 3; si += si < 0 ? H : 0; si -= si >= H ? H : 0; s.rowmap[k] = si * W; }   // H, W >= 3
+    for (int k = t; k < W + 6; k += WT) { int sj = k - 3; sj += sj < 0 ? W : 0; sj -= sj >= W ? W : 0; s.colmap[k] = sj; }
+}
+
 // load cell types + the agent list into the cell-indexed shared arrays
 template <bool DECAY>
 __device__ __forceinline__ int load_world(const WParams& P, WS& s, int w) {
     const int C = P.cfg.height * P.cfg.width;
     const uint8_t* tg = P.b.type + (size_t)w * C;
-    for (int c = threadIdx.x; c < C; c += WT) { s.type[c] = tg[c]; s.aslot[c] = RL_NONE16; }
+    if ((C & 3) == 0) {                                    // rows of the type array are 4-byte aligned
+        const uint32_t* tg4 = reinterpret_cast<const uint32_t*>(tg);
+        for (int q = threadIdx.x; q < C / 4; q += WT) {
+            reinterpret_cast<uint32_t*>(s.type)[q] = __ldg(tg4 + q);
+            reinterpret_cast<uint2*>(s.aslot)[q] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+        }
+    } else {
+        for (int c = threadIdx.x; c < C; c += WT) { s.type[c] = tg[c]; s.aslot[c] = RL_NONE16; }
+    }
     for (int k = threadIdx.x; k < M_WORDS; k += WT) s.misc[k] = 0;
+    init_tables(P, s);
     const int n = min(P.b.n_agents[w], P.cfg.slot_cap);
     __syncthreads();
     const int4* rg = reinterpret_cast<const int4*>(P.b.rec + (size_t)w * P.cfg.slot_cap);
@@ -167,11 +200,9 @@ __device__ __forceinline__ int load_world(const WParams& P, WS& s, int w) {
     return n;
 }
 
-__device__ __forceinline__ float hratio(int h) {       // float32(health / max_health), environment.py:365,397
-    int k = h / 10;
-    if (k * 10 == h && k >= -20 && k <= 20) return c_hratio[k + 20];
-    return (float)((double)h / 200.0);
-}
+// float32(health / max_health), environment.py:365,397.  The correctly rounded float32 quotient equals
+// float32(float64(h) / 200.0) for every int16 h (no double-rounding case exists; checked exhaustively), so no f64 here.
+__device__ __forceinline__ float hratio(int h) { return __fdiv_rn((float)h, 200.0f); }
 
 // Rebuild the agent list from the final grid `ft` (Grid.get_entities, grid.py:60-67), write
 // type/rec/n_agents(/reward), then Environment._get_observations (environment.py:313-375).
@@ -195,7 +226,16 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
         uint8_t t = in ? ft[c] : (uint8_t)0;
         unsigned m = __ballot_sync(0xffffffffu, in && t == RL_AGENT);
         if (lane == 0) s.amask[ch] = m;
-        if (in) tg[c] = t;
+        if ((C & 3) != 0 && in) tg[c] = t;
+    }
+    if ((C & 3) == 0)
+        for (int q = threadIdx.x; q < C / 4; q += WT) reinterpret_cast<uint32_t*>(tg)[q] = reinterpret_cast<const uint32_t*>(ft)[q];
+    if (STEP && threadIdx.x < P.cfg.n_genes) {           // _get_rewards (environment.py:291-311) by (gene, dead, killed)
+        const int g = threadIdx.x, alive_ = s.misc[M_ALIVE], kin = max(0, s.misc[M_ALIVE_G + g] - 1);
+        const double ra = alive_ == 1 ? 0.0 : (double)kin / (double)max(alive_, 1), rd = (double)(kin - alive_);
+        const double bonus = P.cfg.incentivize_killing ? 0.2 : 0.0;
+        s.rtab[g * 4 + 0] = (float)ra; s.rtab[g * 4 + 1] = (float)(ra + bonus);
+        s.rtab[g * 4 + 2] = (float)rd; s.rtab[g * 4 + 3] = (float)(rd + bonus);
     }
     __syncthreads();
     if (warp == 0) {
@@ -216,7 +256,6 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
     }
     __syncthreads();
     const int nB = s.misc[M_NB];
-    const int alive = s.misc[M_ALIVE];
     rl_agent_rec* rg = P.b.rec + (size_t)w * S;
     for (int c = threadIdx.x; c < C; c += WT) {
         if (ft[c] != RL_AGENT) continue;
@@ -234,29 +273,19 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
             const unsigned prev = STEP ? (unsigned)s.aslot[sc] : (unsigned)slot;
             v.w = (int)(fl | (((unsigned)(uint8_t)s.action[sc]) << 8) | (prev << 16));
             reinterpret_cast<int4*>(rg)[slot] = v;
-            if (STEP) {                                 // _get_rewards, environment.py:291-311
-                const int kin = max(0, s.misc[M_ALIVE_G + g] - 1);
-                double r;
-                if (fl & RL_F_DEAD) r = (double)(kin - alive);
-                else if (alive == 1) r = 0.0;
-                else r = (double)kin / (double)alive;
-                if ((fl & RL_F_KILLED) && P.cfg.incentivize_killing) r += 0.2;
-                P.b.reward[(size_t)w * S + slot] = (float)r;
-            }
+            if (STEP)                                   // _get_rewards, environment.py:291-311 (table built above)
+                P.b.reward[(size_t)w * S + slot] = s.rtab[g * 4 + ((fl & RL_F_DEAD) ? 2 : 0) + ((fl & RL_F_KILLED) ? 1 : 0)];
         }
     }
     // ---- padded planes (_prepare_observations :377-404, _get_food :432-446, _get_genes :448-456) ----
     {
         const bool float_path = ft[0] == RL_AGENT;       // np.vectorize dtype quirk of the health plane, SURVEY A.8
-        float* pf = s.planes; float* ph = pf + PADN; float* pg = ph + PADN;
+        uint32_t* pfg = s.planes; float* ph = reinterpret_cast<float*>(s.planes + PADN);
         const int PH = H + 6;
         const uint32_t magicPW = (uint32_t)(0x100000000ull / (uint64_t)PW) + 1u;
         for (int p = threadIdx.x; p < PH * PW; p += WT) {
             const int pi = (int)__umulhi((uint32_t)p, magicPW), pj = p - pi * PW;
-            int si = pi - 3, sj = pj - 3;                    // H, W >= 3: at most two wraps per side
-            si += si < 0 ? H : 0; si += si < 0 ? H : 0; si -= si >= H ? H : 0; si -= si >= H ? H : 0;
-            sj += sj < 0 ? W : 0; sj += sj < 0 ? W : 0; sj -= sj >= W ? W : 0; sj -= sj >= W ? W : 0;
-            const int c = si * W + sj;
+            const int c = s.rowmap[pi] + s.colmap[pj];
             const uint8_t t = ft[c];
             float f = 0.f, hv = -1.f, gv = -2.f;
             if (t == RL_AGENT) {
@@ -268,17 +297,20 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
             } else {
                 f = t == RL_FOOD ? .5f : t == RL_SUPER_FOOD ? 1.f : t == RL_POISON ? -1.f : 0.f;
             }
-            pf[p] = f; ph[p] = hv; pg[p] = gv;
+            pfg[p] = (uint32_t)__half_as_ushort(__float2half_rn(f)) | ((uint32_t)__half_as_ushort(__float2half_rn(gv)) << 16);
+            ph[p] = hv;
         }
     }
     __syncthreads();
     if (threadIdx.x < G) {
         int cg = s.misc[M_CNT_G + threadIdx.x];
-        reinterpret_cast<float*>(s.misc)[M_PG + threadIdx.x] = (float)((double)cg / (double)nB);   // :357
+        // :357 -- float32(cg / nB); for counts <= 4096 the correctly rounded f32 quotient equals the double-rounded one
+        reinterpret_cast<float*>(s.misc)[M_PG + threadIdx.x] = nB <= 4096 ? __fdiv_rn((float)cg, (float)nB) : (float)((double)cg / (double)nB);
         if (P.b.gene_count) P.b.gene_count[(size_t)w * G + threadIdx.x] = cg;
     }
     if (threadIdx.x == RL_MAX_GENES) {
-        reinterpret_cast<float*>(s.misc)[M_PALL] = (float)((double)nB / (double)P.cfg.max_agents);  // :358
+        reinterpret_cast<float*>(s.misc)[M_PALL] = (nB <= 4096 && P.cfg.max_agents <= 4096)                     // :358
+            ? __fdiv_rn((float)nB, (float)P.cfg.max_agents) : (float)((double)nB / (double)P.cfg.max_agents);
         P.b.n_agents[w] = min(nB, S);
         if (nB > S && P.b.status) atomicOr(&P.b.status[w], 1);
     }
@@ -287,26 +319,25 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
 
     // ---- observation rows: one warp per agent ----
     // per-lane constants: element e = lane + 32k of the row -> offset into the padded planes (window elements only)
+    if (P.dbg & 2) return;
     int off[5];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const int e = lane + 32 * k;
-        const int pl = e / 49, q = e - pl * 49;
-        off[k] = e < 147 ? pl * PADN + (q / 7) * PW + (q - (q / 7) * 7) : 0;
-    }
+    for (int k = 0; k < 5; ++k) off[k] = s.offtab[lane + 32 * k];
     const float pall = reinterpret_cast<float*>(s.misc)[M_PALL];
     const int nrow = min(nB, S);
-    // Each warp owns a contiguous block of agents and handles it in batches of 32: first every lane prepares ONE
-    // agent of the batch (window base, own gene, the six scalars -> per-warp scratch), then the warp emits the 32
+    // Each warp owns a contiguous block of agents and handles it in batches of 16: first lanes 0-15 prepare ONE
+    // agent of the batch each (window base, own gene, the six scalars -> per-warp scratch), then the warp emits the
     // rows, broadcasting the per-agent values by shuffle.  Per row: 5 loads, 2 gene decodes, 5 coalesced stores.
     const int per_warp = (nrow + WNW - 1) / WNW;
     const int a0 = warp * per_warp, a1 = min(nrow, a0 + per_warp);
-    float* scr = s.ascal + warp * 256;
-    const float* planes = s.planes;
-    for (int b0 = a0; b0 < a1; b0 += 32) {
+    float* scr = s.ascal + warp * 128;
+    const uint32_t* planes = s.planes;
+    auto lo_f = [](uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xFFFFu))); };
+    auto hi_f = [](uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); };
+    for (int b0 = a0; b0 < a1; b0 += 16) {
         const int mine = b0 + lane;
         int base_l = 0; float gene_l = 0.f;
-        if (mine < a1) {
+        if (lane < 16 && mine < a1) {
             const int d = s.cellof[mine];
             const int i = (int)__umulhi((uint32_t)d, P.magicW), j = d - i * W;
             base_l = i * PW + j;                           // top-left of the 7x7 window in padded coordinates
@@ -326,25 +357,32 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
             reinterpret_cast<float4*>(scr + lane * 8)[1] = hi;
         }
         __syncwarp();
-        const int cnt = min(32, a1 - b0);
+        const int cnt = min(16, a1 - b0);
         float* orow = obs_out + ((size_t)w * S + b0) * ld;
         const int sidx = lane >= 19 ? min(lane - 19, 7) : 0;   // lanes 19-24: scalars, 25-31: zero pad (slots 6,7 are zero)
+        const bool wide = ld > 160;
+#pragma unroll 2
         for (int a = 0; a < cnt; ++a, orow += ld) {
             const int base = __shfl_sync(0xffffffffu, base_l, a);
             const float mygene = __shfl_sync(0xffffffffu, gene_l, a);
-            const float v0 = planes[base + off[0]];
-            const float v1 = planes[base + off[1]];
-            const float v2 = planes[base + off[2]];
-            float v3 = planes[base + off[3]];
-            float v4 = planes[base + off[4]];
+            const uint32_t w0 = planes[base + off[0]];      // e  0..31 : food
+            const uint32_t w1 = planes[base + off[1]];      // e 32..48 : food, 49..63: health
+            const uint32_t w2 = planes[base + off[2]];      // e 64..95 : health
+            const uint32_t w3 = planes[base + off[3]];      // e 96,97  : health, 98..127: dead-agent gene
+            const uint32_t w4 = planes[base + off[4]];      // e 128..146: dead-agent gene, 147..: scalars / pad
             const float sv = scr[a * 8 + sidx];
-            const float g3 = v3 == -2.f ? 0.f : (v3 == mygene ? 1.f : -1.f);             // :424-428
-            const float g4 = v4 == -2.f ? 0.f : (v4 == mygene ? 1.f : -1.f);
-            v3 = lane >= 2 ? g3 : v3;
-            v4 = lane < 19 ? g4 : sv;
+            const float v0 = lo_f(w0);
+            const float v1 = lane < 17 ? lo_f(w1) : __uint_as_float(w1);
+            const float v2 = __uint_as_float(w2);
+            const float q3 = hi_f(w3), q4 = hi_f(w4);
+            const float g3 = q3 == -2.f ? 0.f : (q3 == mygene ? 1.f : -1.f);             // :424-428
+            const float g4 = q4 == -2.f ? 0.f : (q4 == mygene ? 1.f : -1.f);
+            const float v3 = lane >= 2 ? g3 : __uint_as_float(w3);
+            const float v4 = lane < 19 ? g4 : sv;
+            if (P.dbg & 1) { if (v0 + v1 + v2 + v3 + v4 == 12345.678f) __stcs(orow, v0); continue; }
             __stcs(orow + lane, v0); __stcs(orow + 32 + lane, v1); __stcs(orow + 64 + lane, v2);
             __stcs(orow + 96 + lane, v3); __stcs(orow + 128 + lane, v4);
-            for (int e = 160 + lane; e < ld; e += 32) __stcs(orow + e, 0.f);
+            if (wide) for (int e = 160 + lane; e < ld; e += 32) __stcs(orow + e, 0.f);
         }
         __syncwarp();
     }
@@ -353,7 +391,7 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
 // =====================================================================================================
 // Environment.step -- environment.py:160-186
 // =====================================================================================================
-__global__ void __launch_bounds__(WT) k_world_step(const WParams P) {
+__global__ void __launch_bounds__(WT, 6) k_world_step(const WParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int w = blockIdx.x;
     const int H = P.cfg.height, W = P.cfg.width, C = H * W, Cw = (C + 31) / 32;
@@ -508,6 +546,7 @@ __global__ void __launch_bounds__(WT) k_world_step(const WParams P) {
     }
     __syncthreads();
     WSTAMP(5);
+    if (P.dbg & 4) { if (threadIdx.x < C) P.b.type[(size_t)w * C + threadIdx.x] = s.ntype[threadIdx.x]; return; }
     finish_and_observe<true>(P, s, w, s.ntype, P.b.obs_prime);
     WSTAMP(9);
 }
@@ -515,7 +554,7 @@ __global__ void __launch_bounds__(WT) k_world_step(const WParams P) {
 // =====================================================================================================
 // Environment.update_env -- environment.py:188-215 (static families)
 // =====================================================================================================
-__global__ void __launch_bounds__(WT) k_world_update(const WParams P) {
+__global__ void __launch_bounds__(WT, 6) k_world_update(const WParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int w = blockIdx.x;
     const int C = P.cfg.height * P.cfg.width, Cw = (C + 31) / 32, G = P.cfg.n_genes;
@@ -601,6 +640,7 @@ __global__ void __launch_bounds__(WT) k_world_reset(const WParams P) {
     const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
     for (int c = threadIdx.x; c < C; c += WT) { s.type[c] = RL_EMPTY; s.src[c] = (uint16_t)c; s.aslot[c] = RL_NONE16; }
     for (int k = threadIdx.x; k < M_WORDS; k += WT) s.misc[k] = 0;
+    init_tables(P, s);
     __syncthreads();
     build_empty_mask(s.type, s.mask, C);
     __syncthreads();
@@ -637,7 +677,7 @@ __global__ void __launch_bounds__(WT) k_world_reset(const WParams P) {
 // =====================================================================================================
 // saturated-world generator -- harness, mirrored by oracle rlo_topup / RefWorld.top_up
 // =====================================================================================================
-__global__ void __launch_bounds__(WT) k_world_topup(const WParams P) {
+__global__ void __launch_bounds__(WT, 6) k_world_topup(const WParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int w = blockIdx.x;
     const int C = P.cfg.height * P.cfg.width, Cw = (C + 31) / 32;
@@ -675,7 +715,6 @@ __global__ void __launch_bounds__(WT) k_world_observe(const WParams P) {
     finish_and_observe<false>(P, s, w, s.type, P.which ? P.b.obs_prime : P.b.obs_state);
 }
 
-bool g_world_init = false;
 size_t g_world_smem_max = 0;
 
 int world_prepare(const rl_world_cfg* cfg, const rl_world_bufs* b, WParams& P, size_t& smem) {
@@ -689,15 +728,10 @@ int world_prepare(const rl_world_cfg* cfg, const rl_world_bufs* b, WParams& P, s
     if (!cfg->static_families) return rl_set_err(RL_ERR_UNSUPPORTED, "static_families=False is not implemented yet");
     RL_ARG_CHECK(b->type && b->rec && b->n_agents && b->reward && b->obs_state && b->obs_prime);
     P.trace = nullptr; P.cfg = *cfg; P.b = *b; P.t = 0; P.target = 0; P.max_age = 50; P.which = 0;
+    { const char* d = getenv("RL_WORLD_DEBUG"); P.dbg = d ? atoi(d) : 0; }
     P.magicW = (uint32_t)(0x100000000ull / (uint64_t)cfg->width) + 1u;
     smem = ws_bytes(cfg->height, cfg->width);
     if (smem > 227 * 1024) return rl_set_err(RL_ERR_UNSUPPORTED, "world of %d cells needs %zu B shared memory", cfg->height * cfg->width, smem);
-    if (!g_world_init) {
-        float h[41];
-        for (int k = 0; k < 41; ++k) h[k] = (float)((double)(10 * (k - 20)) / 200.0);
-        RL_CUDA_CHECK(cudaMemcpyToSymbol(c_hratio, h, sizeof(h)));
-        g_world_init = true;
-    }
     if (smem > g_world_smem_max) {
         const int v = (int)smem;
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_step, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
