@@ -66,8 +66,8 @@ constexpr int SM_OUTH = SM_DOUT + 1024;          // head outputs [64][16]       
 constexpr int SM_DPL = SM_OUTH + 1024;           // dOut plain [64][12]                    768
 constexpr int SM_SMALL = SM_DPL + 768;           // rew, dn, nq, gb [4][64] + red[32] + (b1[128] b2[256] bh[16]) x 2 nets
 constexpr int SM_SMALL_N = 4 * 64 + 32 + 2 * (128 + 256 + 16);
-constexpr int SM_INT = SM_SMALL + SM_SMALL_N;    // idx[64], act[64]
-constexpr int SM_FLOATS = SM_INT + 128;
+constexpr int SM_INT = SM_SMALL + SM_SMALL_N;    // per-event metadata, double buffered: [2] x { idx[64], act[64], rew[64], dn[64] }
+constexpr int SM_FLOATS = SM_INT + 2 * 256;
 constexpr size_t TC_SMEM = sizeof(float) * SM_FLOATS + 8 * (2 * NS + 2) + 16;
 static_assert(TC_SMEM <= 227 * 1024, "shared memory budget");
 
@@ -103,10 +103,9 @@ __device__ __forceinline__ float epi_sum(float v, float* red) {     // sum over 
 // gather 64 rows of 160 floats into an interleaved image (TRANSPOSED = false: [64][160]; true: [160][64]).
 // The rows come from the replay ring in HBM: all ten 16-byte loads of a thread are issued before the first store,
 // so a gather costs one DRAM round trip instead of ten.
-template <bool TRANSPOSED>
-__device__ __forceinline__ void gather_img(float* img, const float* __restrict__ src, const int* ids) {
-    // lane -> (row within an 8-row group, 4 consecutive 16-byte chunks): conflict-free stores for the plain image
-    float4 x[10];
+// The gather is split in two so that the DRAM/L2 round trip hides behind a tensor-core stage: gather_load issues the
+// ten 16-byte loads of a thread (rows come from the replay ring in HBM), gather_store writes the image later.
+__device__ __forceinline__ void gather_load(float4 (&x)[10], const float* __restrict__ src, const int* ids) {
 #pragma unroll
     for (int u = 0; u < 10; ++u) {
         const int v = threadIdx.x + u * NEPI;
@@ -114,6 +113,10 @@ __device__ __forceinline__ void gather_img(float* img, const float* __restrict__
         const int rg = blk / 10, cg = blk - rg * 10;
         x[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)ids[rg * 8 + rr] * RL_K1) + cg * 4 + cc);
     }
+}
+template <bool TRANSPOSED>
+__device__ __forceinline__ void gather_store(float* img, const float4 (&x)[10]) {
+    // lane -> (row within an 8-row group, 4 consecutive 16-byte chunks): conflict-free stores for the plain image
 #pragma unroll
     for (int u = 0; u < 10; ++u) {
         const int v = threadIdx.x + u * NEPI;
@@ -129,18 +132,6 @@ __device__ __forceinline__ void gather_img(float* img, const float* __restrict__
     }
 }
 
-// pull the 2 x 64 replay rows of an upcoming event into L2 (640 B = 5 lines per row)
-__device__ __forceinline__ void prefetch_event(const TcLearnParams& P, int e) {
-    const int S = P.cfg.slot_cap, cap = P.rp.capacity;
-    const size_t ring = (size_t)(P.ev_rows[e] / S) * cap;
-    for (int v = threadIdx.x; v < 2 * R * 5; v += NEPI) {
-        const int which = v / (R * 5), rem = v - which * (R * 5), r = rem / 5, ln = rem - r * 5;
-        const int i = max(P.sample_idx[(size_t)e * R + r], 0);
-        const float* p = (which ? P.rp.obs : P.rp.next_obs) + (ring + i) * RL_K1 + ln * 32;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    }
-}
-
 __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnParams P) {
     using L = Layout<RL_MODEL_DUELING>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -149,10 +140,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
     float* sH1T = sX;          // H1^T / dH1^T live in the X region once the eval L1 MMAs are done
     float* sXT = sH2;          // X^T lives in the dH2 region once the dH1 MMAs are done
     float* sStage = sm + SM_STAGE; float* sDout = sm + SM_DOUT; float* sOuth = sm + SM_OUTH; float* sDpl = sm + SM_DPL;
-    float* rew = sm + SM_SMALL; float* dn = rew + 64; float* nq = dn + 64; float* gb = nq + 64; float* red = gb + 64;
+    float* nq = sm + SM_SMALL + 128; float* gb = nq + 64; float* red = gb + 64;
     float* bias_t = red + 32;                 // b1[128] b2[256] bh[16] of the target net
     float* bias_e = bias_t + 400;             // same for the eval net
-    int* idx = reinterpret_cast<int*>(sm + SM_INT); int* act = idx + 64;
+    int* meta = reinterpret_cast<int*>(sm + SM_INT);     // [2][256]: idx, act, rew (float), dn (float) of the current / next event
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_FLOATS);
     uint64_t* full = bars; uint64_t* empty = bars + NS; uint64_t* done = bars + 2 * NS; uint64_t* ready = done + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + 1);
@@ -184,7 +175,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
     const uint32_t T_WORK = tmem, T_DW2 = tmem + 256;
     const int S = P.cfg.slot_cap, cap = P.rp.capacity;
 
-    if (warp != 8 && n_my > 0) prefetch_event(P, blockIdx.x);
     if (warp == 8) {
         // =================================== weight-stream producer (one thread) ===================================
         // Streams the fixed 37-chunk schedule of every event through the NS-slot ring; runs ahead of the MMA issuer
@@ -232,27 +222,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
         auto stamp = [&](int it) { if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 8 && tr_n < 40) P.trace[it * 40 + tr_n++] = clock64(); };
         auto wait_done = [&]() { mbar_wait(done, stage_no & 1); ++stage_no; fence_after(); };
 
+        // per-event metadata of event e -> buffer b, loaded by warps 6-7 (not the MMA-issuing thread) in two phases so that
+        // each dependent global round trip hides behind one tensor-core stage; visible to everybody after the next epi_bar
+        int meta_i = 0; size_t meta_ring = 0;
+        auto load_meta_a = [&](int b, int e) {           // phase A: sampled ring positions
+            if (threadIdx.x >= NEPI - R) {
+                const int r = threadIdx.x - (NEPI - R);
+                meta_ring = (size_t)(P.ev_rows[e] / S) * cap;
+                meta_i = max(P.sample_idx[(size_t)e * R + r], 0);     // -1 = skipped by the uniform sampler (error state)
+                meta[b * 256 + r] = meta_i;
+            }
+        };
+        auto load_meta_b = [&](int b) {                  // phase B: action / reward / done of those positions
+            if (threadIdx.x >= NEPI - R) {
+                const int r = threadIdx.x - (NEPI - R);
+                int* m = meta + b * 256;
+                m[64 + r] = P.rp.action[meta_ring + meta_i];
+                reinterpret_cast<float*>(m)[128 + r] = P.rp.reward[meta_ring + meta_i];
+                reinterpret_cast<float*>(m)[192 + r] = (float)P.rp.done[meta_ring + meta_i];
+            }
+        };
+        // pull the 2 x 64 replay rows of the NEXT event into L2 (640 B = 5 lines per row); ids = its ring positions (smem)
+        auto prefetch_rows = [&](size_t rg_, const int* ids) {
+            for (int v = threadIdx.x; v < 2 * R * 5; v += NEPI) {
+                const int which = v / (R * 5), rem = v - which * (R * 5), r = rem / 5, ln = rem - r * 5;
+                const float* p = (which ? P.rp.obs : P.rp.next_obs) + (rg_ + ids[r]) * RL_K1 + ln * 32;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            }
+        };
+        float4 xr[10];                                   // one gathered 64 x 160 image in flight (registers)
+        if (n_my > 0) {                                  // prologue: metadata + target-net input of the first event
+            load_meta_a(0, blockIdx.x);
+            load_meta_b(0);
+            epi_bar();
+            gather_load(xr, P.rp.next_obs + (size_t)(P.ev_rows[blockIdx.x] / S) * cap * RL_K1, meta);
+            gather_store<false>(sX, xr);
+        }
         for (int it = 0; it < n_my; ++it) {
             tr_n = 0; stamp(it);
             const int e = blockIdx.x + it * gridDim.x;
-            if (it + 1 < n_my) prefetch_event(P, e + gridDim.x);
-            const int w = P.ev_rows[e] / S;
-            const size_t ring = (size_t)w * cap;
-            if (threadIdx.x < R) {
-                const int i = max(P.sample_idx[(size_t)e * R + threadIdx.x], 0);   // -1 = skipped by the uniform sampler (error state)
-                idx[threadIdx.x] = i;
-                act[threadIdx.x] = P.rp.action[ring + i];
-                rew[threadIdx.x] = P.rp.reward[ring + i];
-                dn[threadIdx.x] = (float)P.rp.done[ring + i];
-            }
-            epi_bar();
+            const bool more = it + 1 < n_my;
+            const int* idx = meta + (it & 1) * 256; const int* act = idx + 64;
+            const float* rew = reinterpret_cast<const float*>(idx + 128); const float* dn = rew + 64;
+            const size_t ring = (size_t)(P.ev_rows[e] / S) * cap;
+            const size_t ring_next = more ? (size_t)(P.ev_rows[e + gridDim.x] / S) * cap : 0;
             float mean_e = 0.f;
             for (int net = 0; net < 2; ++net) {
                 const float* bias = net ? bias_e : bias_t;
-                gather_img<false>(sX, (net ? P.rp.obs : P.rp.next_obs) + ring * RL_K1, idx);
                 stamp(it); RL_STAGE(stream_gemm(T_WORK, aX, RL_K1, 5, 32, 64, 128));
+                if (net == 0) {                          // hidden behind the target L1 MMAs: eval-net input rows + next event's metadata
+                    gather_load(xr, P.rp.obs + ring * RL_K1, idx);
+                    if (more) load_meta_a((it + 1) & 1, e + gridDim.x);
+                }
                 // ---- L1 epilogue: H1 = relu(D + b1) -> H1 image (+ H1^T image for the eval net) ----
                 wait_done(); stamp(it);
+                if (net == 0) gather_store<false>(sX, xr);      // sX is free: the target L1 MMAs have completed
                 {
                     float va[2][32];
                     tmem_ld32(T_WORK + t_lane + half * 64, va[0]);
@@ -276,6 +300,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
                     }
                 }
                 stamp(it); RL_STAGE(stream_gemm(T_WORK, aH1, 128, 8, 16, 64, 256));
+                if (net == 0 && more) {                  // hidden behind the target L2 MMAs
+                    load_meta_b((it + 1) & 1);
+                    prefetch_rows(ring_next, meta + ((it + 1) & 1) * 256);
+                }
                 // ---- L2 epilogue: H2 = relu(D + b2) -> H2 image ----
                 wait_done(); stamp(it);
                 for (int cp = 0; cp < 2; ++cp) {
@@ -429,6 +457,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
                        for (int ks = 0; ks < 8; ++ks)
                            mma_tf32(T_DW2 + 128, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aH1 + ks * TP_KSTEP), idesc, (it | ks) != 0);
                        stream_gemm(T_WORK, aH2, 256, 8, 32, 64, 128); });
+            gather_load(xr, P.rp.obs + ring * RL_K1, idx);   // X rows again (for the X^T image), hidden behind the dH1 MMAs
             // ---- dH1 epilogue: mask by H1 > 0 (from H1^T), write dH1^T in place of H1^T ----
             wait_done(); stamp(it);
             for (int cb = 0; cb < 2; ++cb) {
@@ -453,13 +482,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
                 red_add(G + L::OFF_B1 + k1, s);
             }
             stamp(it);
-            gather_img<true>(sXT, P.rp.obs + ring * RL_K1, idx);  // X^T image for dW1^T (dH2 region is dead: dH1 MMAs are done)
+            gather_store<true>(sXT, xr);                      // X^T image for dW1^T (dH2 region is dead: dH1 MMAs are done)
             stamp(it);
             RL_STAGE({ const uint32_t idesc = make_idesc(128, 160, 0, 0);                  // dW1^T = dH1^T X
                        for (int ks = 0; ks < 8; ++ks)
                            mma_tf32(T_WORK, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aXT + ks * TP_KSTEP), idesc, ks != 0); });
+            if (more)                                         // next event's target-net input, hidden behind the dW1 MMAs
+                gather_load(xr, P.rp.next_obs + ring_next * RL_K1, meta + ((it + 1) & 1) * 256);
             // ---- dW1^T epilogue: slab region W1 is kept [k1][kx] (160 per row) so each thread adds 16-byte vectors ----
             wait_done(); stamp(it);
+            if (more) gather_store<false>(sX, xr);            // sX (dH1^T) is free: the dW1 MMAs have completed
             {
                 const int k1 = q * 32 + lane;                   // M = 128 accumulator: row = lane
                 float* gr = G + L::OFF_W1T + k1 * RL_K1;
