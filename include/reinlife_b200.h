@@ -78,6 +78,8 @@ typedef struct rl_world_bufs {
     int32_t*      gene_count;   /* [n_worlds, n_genes] agents per gene in the current list */
     int32_t*      status;       /* [n_worlds] sticky bit 0: slot_cap overflow */
     float*        stats;        /* [n_worlds, n_genes, RL_N_STATS] tracker partials of the last step, may be NULL */
+    float*        reward_div100;/* [n_worlds, slot_cap] float32(reference reward / 100.0) -- what PPOAgent.learn stores
+                                   (Models/PPO.py:73); written by step, may be NULL (needed only with PPO brains) */
 } rl_world_bufs;
 
 /* per world x gene partial sums over the post-step agent list (Helpers/tracker.py:178-266) */
@@ -265,6 +267,45 @@ int rl_brain_learn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t ge
  * trained; follow with rl_brain_adam -- five (sample, learn, adam) rounds make one train() call. */
 int rl_brain_learn_dqn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
                        const int32_t* sample_idx, const rl_learn_bufs* learn, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * PPO (Models/PPO.py:62-77,113-162).  One python-list-like data buffer per (world, brain): `traj` (an rl_replay_bufs
+ * used append-only: len = items held, pos unused, prio[] = pi_old(a), reward[] = reward/100).  A step's train triggers
+ * (age % train_freq == 0 or dead, PPO.py:75) cut the list into segments, one learn() call each; rows after the last
+ * trigger stay for the next step.  Sequence per learn step:
+ *     rl_ppo_store -> k_epoch x ( rl_ppo_epoch -> [all-reduce grad] -> rl_brain_adam ) -> rl_ppo_compact
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rl_ppo_bufs {                /* per brain */
+    rl_replay_bufs traj;     /* capacity = rows per world (<= 8192) */
+    uint8_t* seg_end;        /* [n_worlds, capacity] 1 = this transition's agent triggered learn() */
+    int32_t* n_cons;         /* [n_worlds] rows consumed by this step's learn() calls */
+    int32_t* row_off;        /* [n_worlds + 1] exclusive prefix of n_cons; row_off[n_worlds] = rows of this step */
+    int32_t* flat_src;       /* [row_cap] world*capacity + j of every consumed row, world-major, list order */
+    int32_t* row_T;          /* [row_cap] length of the row's segment (the batch of its learn() call) */
+    uint8_t* row_end;        /* [row_cap] 1 = last row of its segment */
+    float*   td;             /* [row_cap] td_target  (PPO.py:140) */
+    float*   delta;          /* [row_cap] td_target - v(s)  (:141) */
+    float*   adv;            /* [row_cap] GAE advantage (:143-150) */
+    int32_t* status;         /* [1] sticky: bit 0 = data list overflowed `capacity`, bit 1 = row_cap overflow; may be NULL */
+    int32_t  row_cap;
+    float    lmbda;          /* 0.95 */
+    float    eps_clip;       /* 0.1  */
+    int32_t  _pad;
+} rl_ppo_bufs;
+
+/* put_data for every STORE row of `gene` in agent order (state = obs_state[prev_slot], prob = prob[w*slot_cap + prev_slot]
+ * as written by rl_brain_act_all, reward = bufs->reward_div100), then the segment plan of this step (3 kernels). */
+int rl_ppo_store(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_rows_bufs* rows, int32_t gene,
+                 const float* prob, int32_t train_freq, const rl_ppo_bufs* ppo, void* stream);
+
+/* One of the k_epoch optimizer steps of PPO.learn() for every segment: v(s), v(s') -> td_target, delta; GAE per segment
+ * (float32, list order); clipped surrogate + smooth-L1 value loss, explicit backward.  learn->kind = RL_MODEL_PPO,
+ * learn->gamma = 0.98.  Per-segment gradients are summed into `grad`, grad[n_train] = number of segments. */
+int rl_ppo_epoch(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_ppo_bufs* ppo,
+                 const rl_learn_bufs* learn, void* stream);
+
+/* self.data = [] for the consumed rows (PPO.py:133): the rows after the last trigger move to the front. */
+int rl_ppo_compact(const rl_world_cfg* cfg, int32_t gene, const rl_ppo_bufs* ppo, void* stream);
 
 /* torch.optim.Adam defaults on grad/grad[n_train] (mean over events); no-op when no event happened.
  * Also refreshes the output-major copy of W2. */

@@ -9,9 +9,10 @@ from ._base import DeviceBrainBase, _NetHandle
 
 class PPOAgent(DeviceBrainBase):
     KIND, RULE, PRIORITIZED, HAS_TARGET = packing.PPO, _lib.ACT_PPO, False, False
+    DEVICE_LEARN = True
 
     def __init__(self, input_dim=153, output_dim=8, learning_rate=0.0005, gamma=0.98, lmbda=0.95, eps_clip=0.1,
-                 k_epoch=3, train_freq=20, load_model=False):
+                 k_epoch=3, train_freq=20, load_model=False, *, data_capacity=None):
         super().__init__(input_dim, output_dim, "PPO")
         if input_dim != 153 or output_dim != 8:
             raise ValueError("the device brains are specialised for ReinLife's 153-float observation and 8 actions")
@@ -22,6 +23,9 @@ class PPOAgent(DeviceBrainBase):
         self.learning_rate, self.gamma, self.lmbda, self.eps_clip, self.k_epoch = learning_rate, gamma, lmbda, eps_clip, k_epoch
         self.load_model = load_model
         self.train_freq = train_freq
+        # the reference's `data` list is unbounded (PPO.py:113-115); here one fixed-size list per (world, brain):
+        # rows per world, default 32 x max_agents (a list is consumed at every train trigger, PPO.py:75-77,133)
+        self.data_capacity = data_capacity
         self.training = False if load_model else True
         if self.load_model:
             self.model.load_state_dict(torch.load(load_model, map_location="cpu"))
@@ -29,7 +33,23 @@ class PPOAgent(DeviceBrainBase):
     def _lr(self): return self.learning_rate
     def _gamma(self): return self.gamma
     def _batch(self): return 64
-    def _capacity(self): return 1
+    def _capacity(self): return self.data_capacity
+
+    def _bind(self, env, gene):
+        from ..brains import DeviceBrain, PpoData
+        if self._env is not None and self._env is not env:
+            raise RuntimeError("a brain object can be bound to one Environment only")
+        if self._dev is None:
+            self._dev = DeviceBrain(self.KIND, self._host_sd, env.device, lr=self.learning_rate, gamma=self.gamma,
+                                    batch=64, has_target=False)
+        self._env, self._gene = env, gene
+        if env.training and self._trains():
+            cap = int(self.data_capacity or min(8192, 32 * env.max_agents))
+            if self._replay is None:
+                row_cap = env.n_worlds * min(cap, 4 * env.world.S)
+                self._replay = PpoData(env.n_worlds, cap, row_cap, env.device, lmbda=self.lmbda, eps_clip=self.eps_clip)
+            env.world.enable_reward_div100()
+            self._dev.alloc_learn(env.rows.row_cap, need_batch_bufs=False)
 
     def get_action(self, s):                       # PPO.py:54-60, 164-169
         prob = torch.from_numpy(np.asarray(self._q_single(np.asarray(s)), np.float32))
@@ -37,4 +57,5 @@ class PPOAgent(DeviceBrainBase):
         return a if self.load_model else (a, prob)
 
     def learn(self, age, dead, action, state, reward, state_prime, done, prob):
-        raise NotImplementedError("PPO training on the device is not implemented yet (inference / tester path only)")
+        raise NotImplementedError("per-agent learn() is replaced by Environment.learn(n_epi), which batches every "
+                                  "agent of every world (reinlife_b200.Helpers.trainer drives it)")

@@ -181,6 +181,8 @@ class Environment:
         with torch.cuda.device(self.device):
             for g in trainable:                                   # brain.memorize / put_data for every age > 1 agent
                 b = self.brains[g]
+                if b.KIND == _lib.MODEL_PPO:
+                    continue                                      # rl_ppo_store (append-only data list) in _learn_ppo
                 _lib.check(lib.rl_replay_store(C.byref(w.cfg), C.byref(w.bufs), C.byref(self.rows.bufs), C.c_int32(g),
                                                C.byref(b._replay.bufs), st))
                 self.gpu_launches += 1
@@ -188,6 +190,8 @@ class Environment:
             for g in trainable:
                 if on[g] and self.brains[g].KIND == _lib.MODEL_DQN:
                     self._learn_dqn(g, st)
+                elif self.brains[g].KIND == _lib.MODEL_PPO:
+                    self._learn_ppo(g, tf[g], st)
 
     def _learn_dueling(self, active, n_epi, st):
         """PERD3QN / D3QN: learn() -> train() (PERD3QN.py:94-125, D3QN.py:97-126)."""
@@ -253,6 +257,23 @@ class Environment:
         sync_target(b._dev, w, cond)
         self.gpu_launches += 1
 
+    def _learn_ppo(self, g, train_freq, st):
+        """PPO: learn() (PPO.py:71-77): put_data for every age > 1 agent; every trigger consumes the list and runs
+        k_epoch optimizer steps (PPO.py:136-162)."""
+        w, lib, b = self.world, self.world.lib, self.brains[g]
+        _lib.check(lib.rl_ppo_store(C.byref(w.cfg), C.byref(w.bufs), C.byref(self.rows.bufs), C.c_int32(g),
+                                    C.c_void_p(self._prob.data_ptr()), C.c_int32(train_freq), C.byref(b._replay.bufs), st))
+        self.gpu_launches += 3
+        for _ in range(int(b.k_epoch)):
+            _lib.check(lib.rl_ppo_epoch(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                        C.byref(b._dev.learn_bufs), st))
+            if self.dist:
+                self._allreduce_grads([g])
+            _lib.check(lib.rl_brain_adam(C.byref(b._dev.learn_bufs), st))
+            self.gpu_launches += 6
+        _lib.check(lib.rl_ppo_compact(C.byref(w.cfg), C.c_int32(g), C.byref(b._replay.bufs), st))
+        self.gpu_launches += 1
+
     def _allreduce_grads(self, active):
         """One NCCL all-reduce (sum) over the flattened gradient (+event count) of every active brain."""
         from ..sharding import allreduce_grads
@@ -278,6 +299,10 @@ class Environment:
         batch (D3QN.py:140)."""
         if int(self._sample_status) & 1:
             raise ValueError("Sample larger than population or is negative")
+        for b in self.brains:
+            st = getattr(getattr(b, "_replay", None), "status", None)
+            if st is not None and int(st):
+                raise RuntimeError(f"{b.method}: the per-world data list overflowed (status {int(st)}); raise data_capacity")
 
     def count_agents(self):
         """Total listed agents on this rank (device -> host read)."""

@@ -40,11 +40,18 @@ class VecWorld:
         self.gene_count = torch.zeros((n_worlds, n_genes), dtype=torch.int32, device=dev)
         self.status = torch.zeros(n_worlds, dtype=torch.int32, device=dev)
         self.stats = torch.zeros((n_worlds, n_genes, _lib.N_STATS), dtype=torch.float32, device=dev) if with_stats else None
+        self.reward_div100 = None      # allocated by enable_reward_div100() when a PPO brain trains (PPO.py:73)
         self.bufs = _lib.WorldBufs(self.type.data_ptr(), self.rec.data_ptr(), self.n_agents.data_ptr(),
                                    self.reward.data_ptr(), self.obs_state.data_ptr(), self.obs_prime.data_ptr(),
                                    self.gene_count.data_ptr(), self.status.data_ptr(),
-                                   self.stats.data_ptr() if with_stats else None)
+                                   self.stats.data_ptr() if with_stats else None, None)
         self.t = 0
+
+    def enable_reward_div100(self):
+        """Have rl_world_step also write float32(reward / 100.0), the value PPOAgent.learn stores (Models/PPO.py:73)."""
+        if self.reward_div100 is None:
+            self.reward_div100 = torch.zeros((self.n_worlds, self.S), dtype=torch.float32, device=self.device)
+            self.bufs.reward_div100 = self.reward_div100.data_ptr()
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

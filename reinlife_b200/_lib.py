@@ -33,7 +33,7 @@ class WorldCfg(C.Structure):
 class WorldBufs(C.Structure):
     _fields_ = [("type", C.c_void_p), ("rec", C.c_void_p), ("n_agents", C.c_void_p), ("reward", C.c_void_p),
                 ("obs_state", C.c_void_p), ("obs_prime", C.c_void_p), ("gene_count", C.c_void_p),
-                ("status", C.c_void_p), ("stats", C.c_void_p)]
+                ("status", C.c_void_p), ("stats", C.c_void_p), ("reward_div100", C.c_void_p)]
 
 
 _lib = None
@@ -97,3 +97,10 @@ class LearnBufs(C.Structure):
                 ("adam_m", C.c_void_p), ("adam_v", C.c_void_p), ("mask", C.c_void_p), ("adam_step", C.c_void_p),
                 ("new_prio", C.c_void_p), ("loss", C.c_void_p), ("kind", C.c_int32), ("batch", C.c_int32),
                 ("gamma", C.c_float), ("lr", C.c_float)]
+
+
+class PpoBufs(C.Structure):
+    _fields_ = [("traj", ReplayBufs), ("seg_end", C.c_void_p), ("n_cons", C.c_void_p), ("row_off", C.c_void_p),
+                ("flat_src", C.c_void_p), ("row_T", C.c_void_p), ("row_end", C.c_void_p), ("td", C.c_void_p),
+                ("delta", C.c_void_p), ("adv", C.c_void_p), ("status", C.c_void_p), ("row_cap", C.c_int32),
+                ("lmbda", C.c_float), ("eps_clip", C.c_float), ("_pad", C.c_int32)]

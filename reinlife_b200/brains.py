@@ -57,14 +57,15 @@ class DeviceBrain:
         self.wimg_stale = True
 
     # -- learn buffers -----------------------------------------------------------------------------
-    def alloc_learn(self, row_cap):
+    def alloc_learn(self, row_cap, need_batch_bufs=True):
         with torch.cuda.device(self.device):
             n_cta = self.lib.rl_learn_grid()
         nt = self.dims.n_train
         self.grad_scratch = torch.zeros((n_cta, nt), device=self.device)
-        self.new_prio = torch.zeros((row_cap, self.batch), device=self.device)
+        nb = row_cap if need_batch_bufs else 1          # PPO has no sampled batches / priorities
+        self.new_prio = torch.zeros((nb, self.batch), device=self.device)
         self.loss = torch.zeros(row_cap, device=self.device)
-        self.sample_idx = torch.zeros((row_cap, self.batch), dtype=torch.int32, device=self.device)
+        self.sample_idx = torch.zeros((nb, self.batch), dtype=torch.int32, device=self.device)
         self.learn_bufs = _lib.LearnBufs(self.params.data_ptr(), self.target.data_ptr() if self.target is not None else None,
                                          self.grad_scratch.data_ptr(), self.grad.data_ptr(), self.adam_m.data_ptr(),
                                          self.adam_v.data_ptr(), self.mask.data_ptr(), self.adam_step.data_ptr(),
@@ -97,6 +98,34 @@ class ReplayRings:
     @staticmethod
     def bytes_needed(n_worlds, capacity, ld=_lib.OBS_LD):
         return n_worlds * capacity * (2 * ld * 4 + 1 + 4 + 1 + 4 + 4)
+
+
+class PpoData:
+    """PPO's per-(world, brain) data list + the per-step segment plan (rl_ppo_bufs)."""
+
+    def __init__(self, n_worlds, capacity, row_cap, device, lmbda=0.95, eps_clip=0.1):
+        dev = torch.device(device)
+        self.traj = ReplayRings(n_worlds, capacity, dev, prioritized=True)        # prio[] = pi_old(a)
+        self.seg_end = torch.zeros((n_worlds, capacity), dtype=torch.uint8, device=dev)
+        self.n_cons = torch.zeros(n_worlds, dtype=torch.int32, device=dev)
+        self.row_off = torch.zeros(n_worlds + 1, dtype=torch.int32, device=dev)
+        self.row_cap = int(row_cap)
+        self.flat_src = torch.zeros(self.row_cap, dtype=torch.int32, device=dev)
+        self.row_T = torch.ones(self.row_cap, dtype=torch.int32, device=dev)
+        self.row_end = torch.zeros(self.row_cap, dtype=torch.uint8, device=dev)
+        self.td = torch.zeros(self.row_cap, device=dev)
+        self.delta = torch.zeros(self.row_cap, device=dev)
+        self.adv = torch.zeros(self.row_cap, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.bufs = _lib.PpoBufs(self.traj.bufs, self.seg_end.data_ptr(), self.n_cons.data_ptr(), self.row_off.data_ptr(),
+                                 self.flat_src.data_ptr(), self.row_T.data_ptr(), self.row_end.data_ptr(),
+                                 self.td.data_ptr(), self.delta.data_ptr(), self.adv.data_ptr(), self.status.data_ptr(),
+                                 self.row_cap, float(lmbda), float(eps_clip), 0)
+
+    # what the generic code reads from a brain's `_replay`
+    @property
+    def len(self):
+        return self.traj.len
 
 
 def learn_step(world, rows, gene, brain, replay, t, allreduce=None):

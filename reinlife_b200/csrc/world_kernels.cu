@@ -40,7 +40,7 @@ struct WS {
     int32_t* offtab;    // [160] row element e -> offset into the padded planes (window elements), 0 for scalars/pad
     int32_t* rowmap;    // [H+6] padded row -> source row * W     (Grid.fov's toroidal concatenate, grid.py:99-115)
     int32_t* colmap;    // [W+6] padded column -> source column
-    float* rtab;        // [RL_MAX_GENES][4] reward by (gene, dead, killed)  (_get_rewards, environment.py:291-311)
+    float* rtab;        // [RL_MAX_GENES][8] reward by (gene, dead, killed) (_get_rewards, environment.py:291-311); [4..7] = reward / 100.0 (PPO.py:73)
     int16_t *health, *age, *maxage;
     uint16_t *aslot, *tgt, *src, *cellof;
     uint8_t *type, *ntype, *flags, *gene;
@@ -50,7 +50,7 @@ struct WS {
 __host__ __device__ inline size_t ws_bytes(int H, int W) {
     const size_t C = (size_t)H * W, Cw = (C + 31) / 32, Cp = (C + 15) & ~(size_t)15;
     const size_t PADN = ((size_t)(H + 6) * (W + 6) + 3) & ~(size_t)3;
-    const size_t TAB = 160 + (((size_t)H + 6 + 3) & ~(size_t)3) + (((size_t)W + 6 + 3) & ~(size_t)3) + RL_MAX_GENES * 4;
+    const size_t TAB = 160 + (((size_t)H + 6 + 3) & ~(size_t)3) + (((size_t)W + 6 + 3) & ~(size_t)3) + RL_MAX_GENES * 8;
     return 4 * 2 * PADN + 4 * WNW * 16 * 8 + 4 * ((Cw + 3) & ~(size_t)3) * 3 + 4 * M_WORDS + 4 * TAB + 2 * Cp * 7 + Cp * 5;
 }
 
@@ -69,7 +69,7 @@ __device__ inline void ws_carve(WS& s, unsigned char* base, int H, int W) {
     s.offtab = (int32_t*)p; p += 4 * 160;
     s.rowmap = (int32_t*)p; p += 4 * (((size_t)H + 6 + 3) & ~(size_t)3);
     s.colmap = (int32_t*)p; p += 4 * (((size_t)W + 6 + 3) & ~(size_t)3);
-    s.rtab = (float*)p; p += 4 * RL_MAX_GENES * 4;
+    s.rtab = (float*)p; p += 4 * RL_MAX_GENES * 8;
     s.health = (int16_t*)p; p += 2 * Cp;
     s.age = (int16_t*)p; p += 2 * Cp;
     s.maxage = (int16_t*)p; p += 2 * Cp;
@@ -234,8 +234,9 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
         const int g = threadIdx.x, alive_ = s.misc[M_ALIVE], kin = max(0, s.misc[M_ALIVE_G + g] - 1);
         const double ra = alive_ == 1 ? 0.0 : (double)kin / (double)max(alive_, 1), rd = (double)(kin - alive_);
         const double bonus = P.cfg.incentivize_killing ? 0.2 : 0.0;
-        s.rtab[g * 4 + 0] = (float)ra; s.rtab[g * 4 + 1] = (float)(ra + bonus);
-        s.rtab[g * 4 + 2] = (float)rd; s.rtab[g * 4 + 3] = (float)(rd + bonus);
+        const double r4[4] = {ra, ra + bonus, rd, rd + bonus};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s.rtab[g * 8 + k] = (float)r4[k]; s.rtab[g * 8 + 4 + k] = (float)(r4[k] / 100.0); }
     }
     __syncthreads();
     if (warp == 0) {
@@ -274,7 +275,11 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
             v.w = (int)(fl | (((unsigned)(uint8_t)s.action[sc]) << 8) | (prev << 16));
             reinterpret_cast<int4*>(rg)[slot] = v;
             if (STEP)                                   // _get_rewards, environment.py:291-311 (table built above)
-                P.b.reward[(size_t)w * S + slot] = s.rtab[g * 4 + ((fl & RL_F_DEAD) ? 2 : 0) + ((fl & RL_F_KILLED) ? 1 : 0)];
+            {
+                const int ri = g * 8 + ((fl & RL_F_DEAD) ? 2 : 0) + ((fl & RL_F_KILLED) ? 1 : 0);
+                P.b.reward[(size_t)w * S + slot] = s.rtab[ri];
+                if (P.b.reward_div100) P.b.reward_div100[(size_t)w * S + slot] = s.rtab[ri + 4];
+            }
         }
     }
     // ---- padded planes (_prepare_observations :377-404, _get_food :432-446, _get_genes :448-456) ----

@@ -2,6 +2,8 @@
 import ctypes as C
 import os
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 import numpy as np
 import pytest
 
@@ -30,12 +32,30 @@ def test_argument_errors_are_reported_without_a_gpu():
 
 
 def test_struct_layouts_match_the_header():
+    """ctypes mirrors == what a C compiler makes of include/reinlife_b200.h (sizes and the offset of the last member)."""
+    import subprocess, tempfile
     from reinlife_b200 import _lib
     from reinlife_b200.World.vecworld import REC_DTYPE
     assert REC_DTYPE.itemsize == 16
-    assert C.sizeof(_lib.WorldCfg) == 56 and C.sizeof(_lib.WorldBufs) == 72
-    assert C.sizeof(_lib.RowsBufs) == 40 and C.sizeof(_lib.ReplayBufs) == 80 and C.sizeof(_lib.LearnBufs) == 96
-    assert C.sizeof(_lib.BrainAct) == 24 and C.sizeof(_lib.BrainSched) == 32
+    pairs = [("rl_world_cfg", _lib.WorldCfg, "world_id0"), ("rl_world_bufs", _lib.WorldBufs, "reward_div100"),
+             ("rl_rows_bufs", _lib.RowsBufs, "row_cap"), ("rl_replay_bufs", _lib.ReplayBufs, "prioritized"),
+             ("rl_learn_bufs", _lib.LearnBufs, "lr"), ("rl_brain_act", _lib.BrainAct, "epsilon"),
+             ("rl_brain_sched", _lib.BrainSched, "max_epi"), ("rl_ppo_bufs", _lib.PpoBufs, "eps_clip"),
+             ("rl_agent_rec", None, "prev_slot")]
+    body = "".join(f'printf("%s %zu %zu\\n", "{c}", sizeof({c}), offsetof({c}, {m}));' for c, _, m in pairs)
+    src = f'#include <stdio.h>\n#include <stddef.h>\n#include "{os.path.join(ROOT, "include", "reinlife_b200.h")}"\nint main(void){{{body}return 0;}}\n'
+    with tempfile.TemporaryDirectory() as td:
+        cfile, exe = os.path.join(td, "abi.c"), os.path.join(td, "abi")
+        open(cfile, "w").write(src)
+        subprocess.check_call(["gcc", "-o", exe, cfile])
+        out = subprocess.check_output([exe], text=True)
+    got = {ln.split()[0]: (int(ln.split()[1]), int(ln.split()[2])) for ln in out.strip().splitlines()}
+    for cname, ct, member in pairs:
+        if ct is None:
+            assert got[cname] == (16, 14)
+            continue
+        assert C.sizeof(ct) == got[cname][0], cname
+        assert getattr(ct, member).offset == got[cname][1], (cname, member)
 
 
 def test_pack_unpack_round_trip_and_reference_key_names():

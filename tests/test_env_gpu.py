@@ -60,9 +60,6 @@ def test_unimplemented_paths_fail_loudly():
     from reinlife_b200.Models import DQN, PERDQN
     with pytest.raises(ZeroDivisionError):
         rl.trainer([DQN()], n_episodes=1, save=False, n_worlds=2)           # DQN(max_epi=0) while training (DQN.py:69)
-    from reinlife_b200.Models import PPO
-    with pytest.raises(NotImplementedError):
-        rl.trainer([PPO()], n_episodes=30, save=False, n_worlds=2, saturate_to=20)
     with pytest.raises(NotImplementedError):
         PERDQN()
     env = rl.Environment(brains=[DQN(training=False)], training=False, n_worlds=1)
@@ -108,3 +105,21 @@ def test_trainer_learns_dqn():
     for k, v in b.agent.state_dict().items():                       # target == agent after the last trigger
         assert torch.equal(v, b.target.state_dict()[k])
     assert abs(env.epsilons()[0] - max(0.01, 0.20 - 0.20 * (60 / 200))) < 1e-12
+
+
+def test_trainer_learns_ppo_with_perd3qn():
+    """PPO trains on the device next to a PERD3QN brain (BASELINE.json configs[4] brain mix, static families)."""
+    import reinlife_b200 as rl
+    from reinlife_b200.Models import PPO, PERD3QN
+    torch.manual_seed(3)
+    brains = [PPO(train_freq=5), PERD3QN(exploration=2, train_freq=5, capacity=400)]
+    w0 = brains[0].model.state_dict()["fc1.weight"].clone()
+    env = rl.trainer(brains, n_episodes=25, width=12, height=12, max_agents=30, update_interval=10, print_results=False,
+                     save=False, n_worlds=8, seed=6, saturate_to=30)
+    torch.cuda.synchronize()
+    b = brains[0]
+    steps = int(b._dev.adam_step)
+    assert steps > 0 and steps % 3 == 0                                   # k_epoch optimizer steps per learn step
+    assert torch.isfinite(b._dev.params).all() and not torch.equal(b.model.state_dict()["fc1.weight"], w0)
+    assert int(b._replay.status) == 0 and int(b._replay.traj.len.max()) < 200
+    assert int(brains[1]._dev.adam_step) > 0

@@ -350,3 +350,173 @@ def test_dqn_batched_events_equal_mean_of_event_gradients_and_skip_short_rings()
     loss_dev = brain.loss[:n_ev].cpu().numpy()
     for e, l in losses.items():
         np.testing.assert_allclose(loss_dev[e], l, rtol=2e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ PPO
+def _ppo_manual_plan(pd, rows, segs):
+    """Lay segments (lists of transitions per world) into the data lists by hand and write the flat plan the way
+    rl_ppo_store would.  segs[w] = list of segments, each a dict of arrays obs/next_obs/action/reward/prob_a/done."""
+    import reinlife_b200._lib as L
+    NW = len(segs)
+    n_cons, flat, row_T, row_end, n_ev = [], [], [], [], 0
+    cap = pd.traj.capacity
+    for w, ss in enumerate(segs):
+        j = 0
+        for sg in ss:
+            T = len(sg["action"])
+            pd.traj.obs[w, j:j + T] = _pad(sg["obs"]).cuda(); pd.traj.next_obs[w, j:j + T] = _pad(sg["next_obs"]).cuda()
+            pd.traj.action[w, j:j + T] = torch.from_numpy(np.asarray(sg["action"]).astype(np.int8)).cuda()
+            pd.traj.reward[w, j:j + T] = torch.from_numpy(np.asarray(sg["reward"]).astype(np.float32)).cuda()
+            pd.traj.prio[w, j:j + T] = torch.from_numpy(np.asarray(sg["prob_a"]).astype(np.float32)).cuda()
+            pd.traj.done[w, j:j + T] = torch.from_numpy(np.asarray(sg["done"]).astype(np.uint8)).cuda()
+            flat += [w * cap + j + k for k in range(T)]; row_T += [T] * T; row_end += [0] * (T - 1) + [1]
+            j += T; n_ev += 1
+        n_cons.append(j)
+        pd.traj.len[w] = j
+    off = np.concatenate([[0], np.cumsum(n_cons)]).astype(np.int32)
+    pd.n_cons[:] = torch.tensor(n_cons, dtype=torch.int32).cuda(); pd.row_off[:] = torch.from_numpy(off).cuda()
+    n = len(flat)
+    pd.flat_src[:n] = torch.tensor(flat, dtype=torch.int32).cuda(); pd.row_T[:n] = torch.tensor(row_T, dtype=torch.int32).cuda()
+    pd.row_end[:n] = torch.tensor(row_end, dtype=torch.uint8).cuda()
+    rows.total[L.ROWS_EVENT] = n_ev
+    return n_ev
+
+
+@pytest.mark.parametrize("T", [1, 5, 37, 100])
+def test_ppo_three_epochs_match_reference_learn(T):
+    """PPO.learn() (Models/PPO.py:136-162) on one data list of T transitions: weights after each of the 3 optimizer
+    steps vs the reference (golden minted by oracle/make_brain_golden2.py); T = 100 spans two 64-row tiles."""
+    from reinlife_b200 import _lib
+    from reinlife_b200.brains import DeviceBrain, PpoData
+    z = _golden2()
+    vw, rows = _mk(1)
+    brain = DeviceBrain(2, _sd2(z, "train_ppo/w0"), "cuda", lr=5e-4, gamma=0.98, batch=64, has_target=False)
+    brain.alloc_learn(rows.row_cap, need_batch_bufs=False)
+    pd = PpoData(1, 128, 256, "cuda")
+    p = f"train_ppo/T{T}/"
+    seg = dict(obs=z[p + "obs"], next_obs=z[p + "next_obs"], action=z[p + "action"], reward=z[p + "reward"],
+               prob_a=z[p + "prob_a"], done=z[p + "done"])
+    _ppo_manual_plan(pd, rows, [[seg]])
+    for e in range(3):
+        _lib.check(vw.lib.rl_ppo_epoch(C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(pd.bufs), C.byref(brain.learn_bufs), vw._stream()))
+        _lib.check(vw.lib.rl_brain_adam(C.byref(brain.learn_bufs), vw._stream()))
+        torch.cuda.synchronize()
+        got, want = brain.state_dict(), _sd2(z, f"{p}e{e}")
+        for k in want:   # Adam step 1 = lr*g/(|g|+1e-8): near-zero gradients amplify fp32 summation order
+            np.testing.assert_allclose(got[k].numpy(), want[k], rtol=0, atol=3e-5, err_msg=f"T {T} epoch {e} {k}")
+    assert int(brain.adam_step) == 3 and int(pd.status) == 0
+
+
+def test_ppo_batched_segments_equal_mean_of_segment_gradients():
+    """Several learn() calls of several worlds in one epoch == oracle mean over segments of the per-segment gradient
+    (each a mean over its own T rows); td_target / delta / GAE per row vs the oracle."""
+    from reinlife_b200 import _lib
+    from reinlife_b200.brains import DeviceBrain, PpoData
+    from reinlife_b200.Models import packing
+    from oracle import brain_oracle as bo
+    z, z1 = _golden2(), golden()
+    rng = np.random.default_rng(5)
+    w0 = _sd2(z, "train_ppo/w0")
+    obs_all = z1["obs"]
+    lens = [[3, 70], [], [1, 1, 20], [64]]
+    vw, rows = _mk(len(lens))
+    segs = []
+    for ss in lens:
+        cur = []
+        for T in ss:
+            o = obs_all[rng.integers(0, 512, T)]; no = obs_all[rng.integers(0, 512, T)]
+            pi, _ = bo.ppo_forward(w0, o)
+            a = rng.integers(0, 8, T)
+            cur.append(dict(obs=o, next_obs=no, action=a, reward=rng.choice([0.0, 0.002, 0.005, -0.03, -0.42], T),
+                            prob_a=(pi[np.arange(T), a] * rng.uniform(0.6, 1.4, T)).astype(np.float32), done=rng.random(T) < 0.2))
+        segs.append(cur)
+    brain = DeviceBrain(2, w0, "cuda", lr=5e-4, gamma=0.98, batch=64, has_target=False)
+    brain.alloc_learn(rows.row_cap, need_batch_bufs=False)
+    pd = PpoData(len(lens), 128, 512, "cuda")
+    n_ev = _ppo_manual_plan(pd, rows, segs)
+    _lib.check(vw.lib.rl_ppo_epoch(C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(pd.bufs), C.byref(brain.learn_bufs), vw._stream()))
+    torch.cuda.synchronize()
+    acc = None
+    for ss in segs:
+        for sg in ss:
+            g, _ = bo.ppo_epoch_grads(w0, sg["obs"], sg["action"], sg["reward"], sg["next_obs"], sg["prob_a"], sg["done"])
+            acc = g if acc is None else {k: acc[k] + g[k] for k in g}
+    grad = brain.grad.cpu().numpy()
+    nt = brain.dims.n_train
+    assert grad[nt] == n_ev
+    got = packing.unpack(2, np.concatenate([grad[:nt] / n_ev * packing.grad_mask(2), np.zeros(brain.dims.n_total - nt, np.float32)]))
+    for k in acc:
+        ref = acc[k] / n_ev
+        np.testing.assert_allclose(got[k].numpy(), ref, rtol=5e-4, atol=2e-6 + 2e-5 * np.abs(ref).max(), err_msg=k)
+
+
+def test_ppo_store_plan_and_compaction_follow_the_reference_data_list():
+    """rl_ppo_store / rl_ppo_compact vs a python mirror of PPOAgent.learn's bookkeeping (PPO.py:71-77,113-134): the list
+    order is the agent order, every trigger consumes the list so far, the tail stays for the next step."""
+    import reinlife_b200._lib as L
+    from reinlife_b200.brains import PpoData
+    from reinlife_b200.World.vecworld import VecWorld
+    from reinlife_b200.rows import RowLists
+    NW, cap, tf = 5, 400, 4
+    vw = VecWorld(NW, 10, 10, 2, max_agents=30, seed=4, world_id0=1)
+    vw.enable_reward_div100()
+    rows = RowLists(vw)
+    vw.reset(); vw.top_up(30)
+    pds = [PpoData(NW, cap, NW * cap, "cuda") for _ in range(2)]
+    prob = torch.rand(NW * vw.S, device="cuda")
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    mirror = [[[] for _ in range(NW)] for _ in range(2)]
+    for step in range(9):
+        obs_state = vw.obs_state.cpu().numpy().copy()
+        vw.set_actions(torch.randint(0, 8, (NW, vw.S), device="cuda", dtype=torch.int8, generator=g))
+        vw.step()
+        rows.build(kinds_mask=6, train_freq=[tf, tf], event_on=[1, 1])
+        torch.cuda.synchronize()
+        rec = vw.rec_host(); n = vw.n_agents.cpu().numpy()
+        obs_prime = vw.obs_prime.cpu().numpy(); r100 = vw.reward_div100.cpu().numpy(); rew = vw.reward.cpu().numpy()
+        pr = prob.cpu().numpy().reshape(NW, vw.S)
+        for gene in range(2):
+            pd = pds[gene]
+            L.check(vw.lib.rl_ppo_store(C.byref(vw.cfg), C.byref(vw.bufs), C.byref(rows.bufs), gene, C.c_void_p(prob.data_ptr()),
+                                        tf, C.byref(pd.bufs), vw._stream()))
+            torch.cuda.synchronize()
+            exp_flat, exp_T, exp_end, n_ev = [], [], [], 0
+            for w in range(NW):
+                data = mirror[gene][w]
+                cut = 0
+                for s in range(n[w]):
+                    r = rec[w, s]
+                    if r["gene"] != gene or r["age"] <= 1:
+                        continue
+                    data.append((obs_state[w, r["prev_slot"]], int(r["action"]), r100[w, s], obs_prime[w, s],
+                                 pr[w, r["prev_slot"]], bool(r["flags"] & 32)))
+                    if r["age"] % tf == 0 or r["flags"] & 32:                      # learn(): consumes data[cut:len]
+                        T = len(data) - cut
+                        exp_flat += [w * cap + j for j in range(cut, len(data))]; exp_T += [T] * T; exp_end += [0] * (T - 1) + [1]
+                        cut = len(data); n_ev += 1
+                assert int(pd.traj.len[w]) == len(data) and int(pd.n_cons[w]) == cut
+                to = pd.traj.obs[w, :len(data)].cpu().numpy(); tn = pd.traj.next_obs[w, :len(data)].cpu().numpy()
+                ta = pd.traj.action[w].cpu().numpy(); tr = pd.traj.reward[w].cpu().numpy()
+                tp = pd.traj.prio[w].cpu().numpy(); td = pd.traj.done[w].cpu().numpy()
+                for j, it in enumerate(data):
+                    assert (to[j] == it[0]).all() and ta[j] == it[1] and tr[j] == it[2] and (tn[j] == it[3]).all()
+                    assert tp[j] == it[4] and td[j] == it[5]
+                mirror[gene][w] = data[cut:]
+            nr = int(pd.row_off[NW])
+            assert nr == len(exp_flat) and n_ev == int(rows.total[gene * 3 + 2])
+            assert pd.flat_src[:nr].cpu().tolist() == exp_flat and pd.row_T[:nr].cpu().tolist() == exp_T
+            assert pd.row_end[:nr].cpu().tolist() == exp_end
+            L.check(vw.lib.rl_ppo_compact(C.byref(vw.cfg), gene, C.byref(pd.bufs), vw._stream()))
+            torch.cuda.synchronize()
+            for w in range(NW):
+                data = mirror[gene][w]
+                assert int(pd.traj.len[w]) == len(data)
+                to = pd.traj.obs[w, :len(data)].cpu().numpy(); tp = pd.traj.prio[w].cpu().numpy()
+                for j, it in enumerate(data):
+                    assert (to[j] == it[0]).all() and tp[j] == it[4]
+            assert int(pd.status) == 0
+        # reward / 100 is the float32 of the float64 quotient (PPO.py:73), not float32(reward) / 100
+        nz = rew != 0
+        assert (r100[nz] != 0).all()
+        vw.update(); vw.top_up(30)
+    assert sum(len(d) for g_ in mirror for d in g_) >= 0
