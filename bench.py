@@ -211,7 +211,7 @@ def run_b200(args):
         ev[0].record(); env.act(n_epi); ev[1].record(); env.step(); ev[2].record(); env.learn(n_epi); ev[3].record()
         env.update_env(n_epi); ev[4].record(); env.top_up(TARGET); ev[5].record()
         torch.cuda.synchronize()
-        ev_meas += sum(float(b._dev.grad[nt]) for b in brains)
+        ev_meas += sum(float(b._dev.grad[nt]) for b in brains) / world_size    # grad[nt] is all-reduced: events per GPU
         for k, name in enumerate(phases):
             phases[name] += ev[k].elapsed_time(ev[k + 1]) / n_meas
         n_epi += 1
@@ -250,7 +250,7 @@ def run_b200(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": ("tf32 (tensor-core learn, fp32 accumulate; act + Adam fp32)" if args.precision == "tf32" else "f32"), "data": "synthetic",
             "config": {"workload": workload_name(args), "grid": [H, W], "worlds_total": n_worlds, "agents_per_world": n_avg,
-                       "train_events_per_step": ev_avg, "parallelism": f"worlds sharded x{world_size}, brains replicated, "
+                       "train_events_per_step_per_gpu": ev_avg, "parallelism": f"worlds sharded x{world_size}, brains replicated, "
                        "1 NCCL all-reduce of summed gradients per step" if world_size > 1 else "single GPU",
                        "l2": "per-step working set (2 x 262 MB observation tensors + replay rows) exceeds the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

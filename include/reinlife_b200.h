@@ -190,6 +190,7 @@ int rl_brain_epsilon_update(const rl_rows_bufs* rows, const rl_brain_sched* sche
 int rl_brain_act_all(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_rows_bufs* rows,
                      const rl_brain_act* brains_host, int32_t n_brains, uint64_t t_act,
                      float* q_out, float* prob_out, void* stream);
+/* (a brain whose `kind` is negative is skipped by rl_brain_act_all: it acts through rl_brain_act_tc) */
 
 
 /* ------------------------------------------------------------------------------------------------
@@ -343,6 +344,10 @@ int rl_tc_gemm_test(const float* a_img, const float* b_img, float* d, int M, int
  * are derived from the kernel-layout parameters with rl_brain_build_wimg after every parameter change.
  * ---------------------------------------------------------------------------------------------- */
 int rl_tc_wimg_floats(void);
+/* brain.get_action of ONE dueling brain on the tensor cores (same rule, draws and outputs as rl_brain_act_all; the
+ * network products use tf32 operands, so Q values agree with the fp32 path to the tolerance of tests/test_tc_gpu.py). */
+int rl_brain_act_tc(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_rows_bufs* rows, int32_t gene,
+                    const rl_brain_act* brain, const float* wimg_eval, uint64_t t_act, float* q_out, void* stream);
 int rl_brain_build_wimg(int32_t kind, const float* params, float* wimg, void* stream);
 int rl_brain_learn_tc(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
                       const int32_t* sample_idx, const rl_learn_bufs* learn, const float* wimg_eval, const float* wimg_target,

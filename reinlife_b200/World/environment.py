@@ -106,6 +106,7 @@ class Environment:
         if precision not in ("tf32", "fp32"):
             raise ValueError("precision must be 'tf32' or 'fp32'")
         self.precision = precision
+        self._act_tc = os.environ.get("RL_ACT_FP32") is None    # tf32 runs: get_action of dueling brains on the tensor cores too
         self._grad_all = None
         from ..Helpers.tracker import Tracker
         self.tracker = Tracker(self, update_interval=update_interval, print_results=print_results)
@@ -143,7 +144,7 @@ class Environment:
         return save_brains(self)
 
     # ------------------------------------------------------------------ batched stand-ins for the per-agent loops
-    def act(self, n_epi: int = 0):
+    def act(self, n_epi: int = 0, q_out=None):
         """for agent in env.agents: agent.get_action(n_epi)   (Helpers/trainer.py:88-89, Helpers/tester.py:58-68)"""
         w = self.world
         G = len(self.brains)
@@ -153,8 +154,23 @@ class Environment:
             _lib.check(w.lib.rl_brain_epsilon_update(C.byref(self.rows.bufs), sched, G, C.c_int64(n_epi),
                                                      C.c_void_p(self._eps.data_ptr()), C.c_void_p(self._seen.data_ptr()),
                                                      w._stream()))
-            _lib.check(w.lib.rl_brain_act_all(C.byref(w.cfg), C.byref(w.bufs), C.byref(self.rows.bufs), self._act_descs, G,
-                                              C.c_uint64(w.t + 1), None, C.c_void_p(self._prob.data_ptr()), w._stream()))
+            tc = [g for g, b in enumerate(self.brains) if self.precision == "tf32" and b.KIND == _lib.MODEL_DUELING and self._act_tc]
+            descs = self._act_descs
+            if tc:                                   # dueling brains act on the tensor cores; the others on the fp32 path
+                descs = (_lib.BrainAct * G)(*[_lib.BrainAct(-1 if g in tc else d.kind, d.rule, d.params, d.epsilon)
+                                              for g, d in enumerate(self._act_descs)])
+            if len(tc) < G:
+                _lib.check(w.lib.rl_brain_act_all(C.byref(w.cfg), C.byref(w.bufs), C.byref(self.rows.bufs), descs, G,
+                                                  C.c_uint64(w.t + 1), C.c_void_p(q_out), C.c_void_p(self._prob.data_ptr()), w._stream()))
+            for g in tc:
+                b = self.brains[g]
+                if b._dev.wimg_stale:
+                    b._dev.build_wimg(w._stream())
+                    b._dev.wimg_stale = False
+                    self.gpu_launches += 2
+                _lib.check(w.lib.rl_brain_act_tc(C.byref(w.cfg), C.byref(w.bufs), C.byref(self.rows.bufs), C.c_int32(g),
+                                                 C.byref(self._act_descs[g]), C.c_void_p(b._dev.wimg_e.data_ptr()),
+                                                 C.c_uint64(w.t + 1), C.c_void_p(q_out), w._stream()))
         self.gpu_launches += 4 + G
 
     def learn(self, n_epi: int = 0):

@@ -233,6 +233,7 @@ int rl_brain_act_all(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const r
     RL_ARG_CHECK(cfg && bufs && rows && brains && n_brains == cfg->n_genes);
     RL_ARG_CHECK(cfg->obs_ld == RL_K1);
     for (int g = 0; g < n_brains; ++g) {
+        if (brains[g].kind < 0) continue;            // handled elsewhere (rl_brain_act_tc)
         ActParams P;
         P.cfg = *cfg; P.rec = bufs->rec; P.obs = bufs->obs_state;
         P.rows = rows->rows + (size_t)(g * RL_N_ROW_KINDS + RL_ROWS_ALL) * rows->row_cap;

@@ -527,6 +527,193 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
     if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
+// =====================================================================================================
+// brain.get_action for the dueling brains on the tensor cores: the forward half of the event kernel over 64-row
+// tiles of the brain's ALL row list (Helpers/trainer.py:88-89; PERD3QN.py:81-89,198-210; D3QN.py:82-93,161-173).
+// Same pipeline: warp 8 streams the 14 weight chunks of a tile (W1[5], W2K[8], WH), epilogue thread 0 issues the
+// MMAs, the next tile's observation rows are gathered into registers behind the L2 stage.  The epilogue is the one of
+// k_brain_act (per-row dueling combine at B = 1, first-max argmax, exploration draws keyed (t_act, slot)).
+// =====================================================================================================
+struct TcActParams {
+    rl_world_cfg cfg;
+    rl_agent_rec* rec;
+    const float* obs;          // obs_state
+    const int32_t* rows;       // row list of this brain, kind ALL
+    const int32_t* total;      // device scalar
+    const float* params;       // biases are read from the kernel-layout buffer
+    const float* wimg;
+    const double* epsilon;
+    uint64_t t_act;
+    float* q_out;              // [row_cap][8] or null
+};
+constexpr int ACT_SCHED_N = 14;
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_act_dueling_tc(const TcActParams P) {
+    using L = Layout<RL_MODEL_DUELING>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* sm = reinterpret_cast<float*>(smem_raw);
+    float* sX = sm + SM_X; float* sH1 = sm + SM_H1; float* sH2 = sm + SM_H2;
+    float* sStage = sm + SM_STAGE; float* sOuth = sm + SM_OUTH;
+    float* bias = sm + SM_SMALL;                           // b1[128] b2[256] bh[16]
+    int* ids = reinterpret_cast<int*>(sm + SM_INT);        // [2][64] row ids of the current / next tile
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_FLOATS);
+    uint64_t* full = bars; uint64_t* empty = bars + NS; uint64_t* done = bars + 2 * NS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = *P.total;
+    const int n_tiles = (total + R - 1) / R;
+    const int n_my = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 256);
+    if (threadIdx.x < NEPI)
+        for (int i = threadIdx.x; i < 400; i += NEPI) {
+            const int o = i < 128 ? L::OFF_B1 + i : i < 384 ? L::OFF_B2 + (i - 128) : L::OFF_BH + (i - 384);
+            bias[i] = i < 384 + 9 ? P.params[o] : 0.f;
+        }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t T_WORK = *tmem_slot;
+    const int S = P.cfg.slot_cap;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t n_chunks = (uint32_t)n_my * ACT_SCHED_N;
+            for (uint32_t produced = 0; produced < n_chunks; ++produced) {
+                const uint32_t slot = produced % NS;
+                if (produced >= NS) mbar_wait(&empty[slot], ((produced / NS) - 1) & 1);
+                bulk_load(sStage + slot * CHUNK_F, P.wimg + (size_t)(produced % ACT_SCHED_N) * CHUNK_F, CHUNK_F * 4, &full[slot]);
+            }
+        }
+    } else {
+        uint32_t stage_no = 0, consumed = 0;
+        const int q = warp & 3, half = warp >> 2;
+        const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+        const int row = q * 16 + lane;
+        const bool rvalid = lane < 16;
+        const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH2 = smem_u32(sH2);
+        auto stage_sync = [&]() { fence_proxy_async(); fence_before(); epi_bar(); };
+        auto stream_gemm = [&](uint32_t d_tmem, uint32_t a_base, int a_k, int nch, int kc, int m, int n) {
+            const uint32_t idesc = make_idesc(m, n, 0, 0);
+            for (int c = 0; c < nch; ++c) {
+                const uint32_t slot = consumed % NS;
+                mbar_wait(&full[slot], (consumed / NS) & 1);
+                fence_after();
+                const uint32_t b_base = smem_u32(sStage + slot * CHUNK_F);
+                for (int ks = 0; ks < kc / 8; ++ks) {
+                    const int kcol = c * kc + ks * 8;
+                    mma_tf32(d_tmem, desc_kmajor(a_base + (kcol >> 2) * 128, a_k), desc_kmajor(b_base + ks * 256, kc), idesc, (c | ks) != 0);
+                }
+                mma_commit(&empty[slot]);
+                ++consumed;
+            }
+        };
+        auto wait_done = [&]() { mbar_wait(done, stage_no & 1); ++stage_no; fence_after(); };
+        auto load_ids = [&](int b, int tile) {           // rows past `total` read row 0 (results discarded)
+            if (threadIdx.x >= NEPI - R) {
+                const int r = threadIdx.x - (NEPI - R), i = tile * R + r;
+                ids[b * R + r] = i < total ? P.rows[i] : 0;
+            }
+        };
+        float4 xr[10];
+        if (n_my > 0) {
+            load_ids(0, blockIdx.x);
+            epi_bar();
+            gather_load(xr, P.obs, ids);
+            gather_store<false>(sX, xr);
+        }
+        const double epsilon = *P.epsilon;
+        for (int it = 0; it < n_my; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const bool more = it + 1 < n_my;
+            const int* idc = ids + (it & 1) * R;
+            RL_STAGE(stream_gemm(T_WORK, aX, RL_K1, 5, 32, 64, 128));
+            if (more) load_ids((it + 1) & 1, tile + gridDim.x);          // hidden behind the L1 MMAs
+            wait_done();
+            {   // L1 epilogue: H1 = relu(D + b1)
+                float va[2][32];
+                tmem_ld32(T_WORK + t_lane + half * 64, va[0]);
+                tmem_ld32(T_WORK + t_lane + half * 64 + 32, va[1]);
+                tmem_wait_ld();
+                if (rvalid) {
+#pragma unroll
+                    for (int cb = 0; cb < 2; ++cb) {
+                        const int c0 = half * 64 + cb * 32;
+                        const float* v = va[cb];
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            *reinterpret_cast<float4*>(sH1 + img_off(row, c0 + j4 * 4, 128)) =
+                                make_float4(to_tf32(fmaxf(v[j4 * 4] + bias[c0 + j4 * 4], 0.f)), to_tf32(fmaxf(v[j4 * 4 + 1] + bias[c0 + j4 * 4 + 1], 0.f)),
+                                            to_tf32(fmaxf(v[j4 * 4 + 2] + bias[c0 + j4 * 4 + 2], 0.f)), to_tf32(fmaxf(v[j4 * 4 + 3] + bias[c0 + j4 * 4 + 3], 0.f)));
+                    }
+                }
+            }
+            RL_STAGE(stream_gemm(T_WORK, aH1, 128, 8, 16, 64, 256));
+            if (more) gather_load(xr, P.obs, ids + ((it + 1) & 1) * R);  // next tile's rows, hidden behind L2 + head
+            wait_done();
+            for (int cp = 0; cp < 2; ++cp) {   // L2 epilogue: H2 = relu(D + b2)
+                float va[2][32];
+                tmem_ld32(T_WORK + t_lane + half * 128 + cp * 64, va[0]);
+                tmem_ld32(T_WORK + t_lane + half * 128 + cp * 64 + 32, va[1]);
+                tmem_wait_ld();
+                if (rvalid) {
+#pragma unroll
+                    for (int cb = 0; cb < 2; ++cb) {
+                        const int c0 = half * 128 + cp * 64 + cb * 32;
+                        const float* v = va[cb];
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            *reinterpret_cast<float4*>(sH2 + img_off(row, c0 + j4 * 4, 256)) =
+                                make_float4(to_tf32(fmaxf(v[j4 * 4] + bias[128 + c0 + j4 * 4], 0.f)), to_tf32(fmaxf(v[j4 * 4 + 1] + bias[128 + c0 + j4 * 4 + 1], 0.f)),
+                                            to_tf32(fmaxf(v[j4 * 4 + 2] + bias[128 + c0 + j4 * 4 + 2], 0.f)), to_tf32(fmaxf(v[j4 * 4 + 3] + bias[128 + c0 + j4 * 4 + 3], 0.f)));
+                    }
+                }
+            }
+            RL_STAGE(stream_gemm(T_WORK, aH2, 256, 1, 256, 64, 16));
+            wait_done();
+            if (more) gather_store<false>(sX, xr);                       // sX is free since the L1 MMAs completed
+            if (half == 0) {   // head epilogue + action rule, one row per valid lane
+                float v[16];
+                tmem_ld16(T_WORK + t_lane, v);
+                tmem_wait_ld();
+                const int i = tile * R + row;
+                if (rvalid && i < total) {
+                    float qv[8], ssum = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { qv[j] = v[j] + bias[384 + j]; ssum += qv[j]; }
+                    const float val = v[8] + bias[384 + 8], mean = ssum * 0.125f;     // B = 1: per-row mean (PERD3QN.py:202)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) qv[j] = qv[j] + val - mean;
+                    int best = 0;
+#pragma unroll
+                    for (int j = 1; j < 8; ++j) if (qv[j] > qv[best]) best = j;       // first maximum
+                    const int rid = idc[row];
+                    const int w = rid / S, slot = rid - w * S;
+                    const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
+                    int a = best;                                                      // PERD3QN.py:204-210
+                    const double u = rl_uniform(rl_draw(key, P.t_act, RL_SITE_ACT_EXPLORE, (uint32_t)slot));
+                    if (!(u > epsilon)) a = (int)rl_below(rl_draw(key, P.t_act, RL_SITE_ACT_RANDOM, (uint32_t)slot), 8);
+                    reinterpret_cast<int8_t*>(P.rec + rid)[13] = (int8_t)a;
+                    if (P.q_out) {
+                        float4* qo = reinterpret_cast<float4*>(P.q_out + (size_t)i * 8);
+                        qo[0] = make_float4(qv[0], qv[1], qv[2], qv[3]);
+                        qo[1] = make_float4(qv[4], qv[5], qv[6], qv[7]);
+                    }
+                }
+            }
+            fence_before();
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(*tmem_slot, 256);
+}
+
 // ---- weight images (tf32-rounded) from the kernel-layout parameter buffer ----
 __global__ void k_build_wimg_dueling(const float* __restrict__ p, float* __restrict__ wimg) {
     using L = Layout<RL_MODEL_DUELING>;
@@ -562,6 +749,29 @@ int rl_brain_build_wimg(int32_t kind, const float* params, float* wimg, void* st
     RL_ARG_CHECK(params && wimg);
     if (kind != RL_MODEL_DUELING) return rl_set_err(RL_ERR_UNSUPPORTED, "tensor-core weight images: dueling networks only");
     k_build_wimg_dueling<<<(128 * 256 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(params, wimg);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_brain_act_tc(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_rows_bufs* rows, int32_t gene,
+                    const rl_brain_act* brain, const float* wimg_eval, uint64_t t_act, float* q_out, void* stream) {
+    RL_ARG_CHECK(cfg && bufs && rows && brain && wimg_eval);
+    RL_ARG_CHECK(gene >= 0 && gene < cfg->n_genes && cfg->obs_ld == RL_K1);
+    RL_ARG_CHECK(bufs->rec && bufs->obs_state && brain->params && brain->epsilon);
+    if (brain->kind != RL_MODEL_DUELING || brain->rule != RL_ACT_DUELING)
+        return rl_set_err(RL_ERR_UNSUPPORTED, "rl_brain_act_tc: dueling networks only");
+    TcActParams P;
+    P.cfg = *cfg; P.rec = bufs->rec; P.obs = bufs->obs_state;
+    P.rows = rows->rows + (size_t)(gene * RL_N_ROW_KINDS + RL_ROWS_ALL) * rows->row_cap;
+    P.total = rows->total + gene * RL_N_ROW_KINDS + RL_ROWS_ALL;
+    P.params = brain->params; P.wimg = wimg_eval; P.epsilon = brain->epsilon; P.t_act = t_act;
+    P.q_out = q_out ? q_out + (size_t)gene * rows->row_cap * 8 : nullptr;
+    static bool attr = false;
+    if (!attr) {
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_act_dueling_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        attr = true;
+    }
+    k_act_dueling_tc<<<rl_learn_grid(), NTHREADS, TC_SMEM, (cudaStream_t)stream>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
     return RL_OK;
 }
