@@ -8,7 +8,7 @@ SOURCES = ["c_api.cu", "world_kernels.cu", "stats_kernels.cu", "rows_kernels.cu"
 OUT = os.path.join(os.path.dirname(HERE), "libreinlife_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+         "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("RL_NVCC_EXTRA", "").split()   # e.g. -DRL_WT=128 (experiments)
 
 
 def needs_build():

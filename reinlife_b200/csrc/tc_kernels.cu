@@ -528,6 +528,417 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
 }
 
 // =====================================================================================================
+// k_learn_dueling_tc2 -- the same train() event with every activation GEMM in TRANSPOSED-OUTPUT form:
+//   D[feature][batch] = W[feature][k] * Act[batch][k]^T   (A = weight chunk, M = 128 features; B = activation image, N = 64 rows)
+// so that (1) every MMA runs at M = 128 (full tensor rate, M = 64 runs at half), (2) the TMEM epilogues own one FEATURE
+// per lane -- all 32 lanes of all 8 warps carry data (the M = 64 accumulator layout of k_learn_dueling_tc fills 16 of 32),
+// bias is a per-thread scalar, bias gradients are per-thread sums, (3) the feature-major images the weight-gradient GEMMs
+// need (H1^T, dH2^T, dH1^T) are written with 16-byte vector stores, and the batch-major images the next layer needs
+// (H1, H2, dH2 as B operands) by conflict-free scalar scatters into images with a padded chunk stride (LBO = 144 B).
+// Same inputs, outputs, weight images, chunk schedule and per-CTA gradient slabs as k_learn_dueling_tc.
+// =====================================================================================================
+constexpr int NS2 = 4;                                  // weight-chunk stages
+constexpr int V2_X = 0;                                 // X' / X [64][160] plain image -> H1^T / dH1^T timg [128][64]   10240
+constexpr int V2_H1 = V2_X + 10240;                     // H1 bimg [64][128] -> dH2^T half timg [128][64]                  9216
+constexpr int V2_H2 = V2_H1 + 9216;                     // H2 bimg [64][256] -> dH2 bimg -> X^T timg [160][64]            18432
+constexpr int V2_STAGE = V2_H2 + 18432;
+constexpr int V2_DOUT = V2_STAGE + NS2 * CHUNK_F;       // dOut image [64][16]
+constexpr int V2_OUTH = V2_DOUT + 1024;
+constexpr int V2_DPL = V2_OUTH;                         // dOut plain [64][12] aliases the head outputs (dead once q_a / dOut are formed)
+constexpr int V2_SMALL = V2_OUTH + 1024;
+constexpr int V2_INT = V2_SMALL + SM_SMALL_N;
+constexpr int V2_FLOATS = V2_INT + 2 * 256;
+constexpr size_t TC2_SMEM = sizeof(float) * V2_FLOATS + 8 * (2 * NS2 + 2) + 16;
+static_assert(TC2_SMEM <= 227 * 1024, "shared memory budget");
+
+// batch-major image [64 rows][K cols] with the padded chunk stride: consecutive features of one batch row sit in
+// consecutive banks, so a warp whose lanes own consecutive features scatters one batch column conflict-free
+__device__ __forceinline__ int bimg_off(int b, int c, int K) { return (b >> 3) * ((K >> 2) * TP_CH) + (c >> 2) * TP_CH + (b & 7) * 4 + (c & 3); }
+__device__ __forceinline__ uint64_t desc_bimg(uint32_t saddr, int K) { return make_desc(saddr, TP_CH * 4, (uint32_t)(K >> 2) * TP_CH * 4); }
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc2(const TcLearnParams P) {
+    using L = Layout<RL_MODEL_DUELING>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* sm = reinterpret_cast<float*>(smem_raw);
+    float* sX = sm + V2_X; float* sH1 = sm + V2_H1; float* sH2 = sm + V2_H2;
+    float* sH1T = sX;          // H1^T / dH1^T (feature-major) live in the X region once the eval L1 MMAs are done
+    float* sDT = sH1;          // dH2^T half buffer lives in the H1 region once the eval L2 MMAs are done
+    float* sXT = sH2;          // X^T lives in the dH2 region once the dH1 MMAs are done
+    float* sStage = sm + V2_STAGE; float* sDout = sm + V2_DOUT; float* sOuth = sm + V2_OUTH; float* sDpl = sm + V2_DPL;
+    float* nq = sm + V2_SMALL + 128; float* gb = nq + 64; float* red = gb + 64;
+    float* bias_t = red + 32;                 // b1[128] b2[256] bh[16] of the target net
+    float* bias_e = bias_t + 400;             // same for the eval net
+    int* meta = reinterpret_cast<int*>(sm + V2_INT);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + V2_FLOATS);
+    uint64_t* full = bars; uint64_t* empty = bars + NS2; uint64_t* done = bars + 2 * NS2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* Pe = P.lb.params; const float* Pt = P.lb.target;
+    float* G = P.lb.grad_scratch + (size_t)blockIdx.x * L::N_TRAIN;
+    const int total = *P.ev_total;
+    const int n_my = total > (int)blockIdx.x ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x < NEPI) {
+        for (int i = threadIdx.x; i < 400; i += NEPI) {
+            const int o = i < 128 ? L::OFF_B1 + i : i < 384 ? L::OFF_B2 + (i - 128) : L::OFF_BH + (i - 384);
+            const bool ok = i < 384 + 9;
+            bias_t[i] = ok ? Pt[o] : 0.f; bias_e[i] = ok ? Pe[o] : 0.f;
+        }
+        for (int i = threadIdx.x; i < L::N_TRAIN / 4; i += NEPI) reinterpret_cast<float4*>(G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t T_WORK = tmem, T_DW2 = tmem + 256;
+    const int S = P.cfg.slot_cap, cap = P.rp.capacity;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t n_chunks = (uint32_t)n_my * SCHED_N;
+            for (uint32_t produced = 0; produced < n_chunks; ++produced) {
+                const uint32_t slot = produced % NS2;
+                if (produced >= NS2) mbar_wait(&empty[slot], ((produced / NS2) - 1) & 1);
+                int net, ch; sched_entry(produced % SCHED_N, net, ch);
+                bulk_load(sStage + slot * CHUNK_F, (net ? P.wimg_e : P.wimg_t) + (size_t)ch * CHUNK_F, CHUNK_F * 4, &full[slot]);
+            }
+        }
+    } else {
+        uint32_t stage_no = 0, consumed = 0;
+        const int q = warp & 3, half = warp >> 2;
+        const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+        const int f1 = q * 32 + lane;                   // feature owned in 128-feature stages (k1)
+        const int f2 = half * 128 + f1;                 // feature owned in 256-feature stages (n2)
+        const int row64 = q * 16 + lane;                // M = 64 accumulator (head only): rows 16q+i in lanes 32q+i, i < 16
+        const bool rvalid = lane < 16;
+        const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH1T = smem_u32(sH1T), aH2 = smem_u32(sH2), aD = smem_u32(sDout), aXT = smem_u32(sXT);
+        auto stage_sync = [&]() { fence_proxy_async(); fence_before(); epi_bar(); };
+        // thread 0: D[m_halves x 128 features][n] (+)= Wchunk (A, streams through the ring) x Act (B, resident image).
+        // b_lbo / b_sbo / b_kstep describe the activation image; a chunk holds kc k-columns for m_halves*128 feature rows.
+        auto stream_gemm_w = [&](uint32_t d_tmem, int m_halves, uint32_t b_base, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep,
+                                 int nch, int kc, int n) {
+            const uint32_t idesc = make_idesc(128, n, 0, 0);
+            for (int c = 0; c < nch; ++c) {
+                const uint32_t slot = consumed % NS2;
+                mbar_wait(&full[slot], (consumed / NS2) & 1);
+                fence_after();
+                const uint32_t a_base = smem_u32(sStage + slot * CHUNK_F);
+                for (int h = 0; h < m_halves; ++h)
+                    for (int ks = 0; ks < kc / 8; ++ks) {
+                        const uint32_t kstep = (uint32_t)(c * (kc / 8) + ks);
+                        mma_tf32(d_tmem + h * n, desc_kmajor(a_base + h * (128 * kc * 4) + ks * 256, kc),
+                                 make_desc(b_base + kstep * b_kstep, b_lbo, b_sbo), idesc, (c | ks) != 0);
+                    }
+                mma_commit(&empty[slot]);
+                ++consumed;
+            }
+        };
+        int tr_n = 0;
+        auto stamp = [&](int it) { if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 8 && tr_n < 40) P.trace[it * 40 + tr_n++] = clock64(); };
+        auto wait_done = [&]() { mbar_wait(done, stage_no & 1); ++stage_no; fence_after(); };
+        int meta_i = 0; size_t meta_ring = 0;
+        auto load_meta_a = [&](int b, int e) {
+            if (threadIdx.x >= NEPI - R) {
+                const int r = threadIdx.x - (NEPI - R);
+                meta_ring = (size_t)(P.ev_rows[e] / S) * cap;
+                meta_i = max(P.sample_idx[(size_t)e * R + r], 0);
+                meta[b * 256 + r] = meta_i;
+            }
+        };
+        auto load_meta_b = [&](int b) {
+            if (threadIdx.x >= NEPI - R) {
+                const int r = threadIdx.x - (NEPI - R);
+                int* m = meta + b * 256;
+                m[64 + r] = P.rp.action[meta_ring + meta_i];
+                reinterpret_cast<float*>(m)[128 + r] = P.rp.reward[meta_ring + meta_i];
+                reinterpret_cast<float*>(m)[192 + r] = (float)P.rp.done[meta_ring + meta_i];
+            }
+        };
+        auto prefetch_rows = [&](size_t rg_, const int* ids) {
+            for (int v = threadIdx.x; v < 2 * R * 5; v += NEPI) {
+                const int which = v / (R * 5), rem = v - which * (R * 5), r = rem / 5, ln = rem - r * 5;
+                const float* p = (which ? P.rp.obs : P.rp.next_obs) + (rg_ + ids[r]) * RL_K1 + ln * 32;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            }
+        };
+        float4 xr[10];
+        size_t ring_cur = 0;
+        if (n_my > 0) {
+            load_meta_a(0, blockIdx.x);
+            load_meta_b(0);
+            epi_bar();
+            ring_cur = (size_t)(P.ev_rows[blockIdx.x] / S) * cap;
+            gather_load(xr, P.rp.next_obs + ring_cur * RL_K1, meta);
+            gather_store<false>(sX, xr);
+        }
+        for (int it = 0; it < n_my; ++it) {
+            tr_n = 0; stamp(it);
+            const int e = blockIdx.x + it * gridDim.x;
+            const bool more = it + 1 < n_my;
+            const int* idx = meta + (it & 1) * 256; const int* act = idx + 64;
+            const float* rew = reinterpret_cast<const float*>(idx + 128); const float* dn = rew + 64;
+            const size_t ring = ring_cur;
+            size_t ring_next = 0;
+            float mean_e = 0.f;
+            for (int net = 0; net < 2; ++net) {
+                const float* bias = net ? bias_e : bias_t;
+                // ---- L1^T: H1^T[k1][b] = W1[k1][:] . X[b][:]   (A = W1 chunks, B = X image) ----
+                stamp(it); RL_STAGE(stream_gemm_w(T_WORK, 1, aX, 128u, RL_K1 * 32u, 256u, 5, 32, 64));
+                if (net == 0) {
+                    gather_load(xr, P.rp.obs + ring * RL_K1, idx);
+                    if (more) { load_meta_a((it + 1) & 1, e + gridDim.x); ring_next = (size_t)(P.ev_rows[e + gridDim.x] / S) * cap; }
+                }
+                wait_done(); stamp(it);
+                if (net == 0) gather_store<false>(sX, xr);      // sX is free: the target L1 MMAs have completed
+                {   // epilogue: lane = feature k1, this warp's 32 batch columns; H1 = relu(D + b1)
+                    float v[32];
+                    tmem_ld32(T_WORK + t_lane + half * 32, v);
+                    tmem_wait_ld();
+                    const float b1 = bias[f1];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = to_tf32(fmaxf(v[j] + b1, 0.f));
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sH1[bimg_off(half * 32 + j, f1, 128)] = v[j];        // batch-major: B of L2^T
+                    if (net) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4)                                                 // feature-major: A of dW2, relu mask of dH1
+                            *reinterpret_cast<float4*>(sH1T + timg_off(f1, half * 32 + j4 * 4)) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                    }
+                }
+                // ---- L2^T: H2^T[n2][b] = W2[n2][:] . H1[b][:]   (two 128-feature halves per chunk) ----
+                stamp(it); RL_STAGE(stream_gemm_w(T_WORK, 2, aH1, TP_CH * 4u, 32u * TP_CH * 4u, TP_KSTEP, 8, 16, 64));
+                if (net == 0 && more) {
+                    load_meta_b((it + 1) & 1);
+                    prefetch_rows(ring_next, meta + ((it + 1) & 1) * 256);
+                }
+                wait_done(); stamp(it);
+                {   // epilogue: lane = feature n2 (f2), all 64 batch columns; H2 = relu(D + b2) -> batch-major image
+                    const float b2 = bias[128 + f2];
+#pragma unroll
+                    for (int cb = 0; cb < 2; ++cb) {
+                        float v[32];
+                        tmem_ld32(T_WORK + t_lane + half * 64 + cb * 32, v);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sH2[bimg_off(cb * 32 + j, f2, 256)] = to_tf32(fmaxf(v[j] + b2, 0.f));
+                    }
+                }
+                // ---- head (normal form, M = 64): out[b][j] = H2[b][:] . Wh[j][:] ----
+                stamp(it);
+                RL_STAGE({ const uint32_t idesc = make_idesc(64, 16, 0, 0);
+                           const uint32_t slot = consumed % NS2;
+                           mbar_wait(&full[slot], (consumed / NS2) & 1);
+                           fence_after();
+                           const uint32_t b_base = smem_u32(sStage + slot * CHUNK_F);
+                           for (int ks = 0; ks < 32; ++ks)
+                               mma_tf32(T_WORK, desc_bimg(aH2 + ks * TP_KSTEP, 256), desc_kmajor(b_base + ks * 256, 256), idesc, ks != 0);
+                           mma_commit(&empty[slot]);
+                           ++consumed; });
+                wait_done(); stamp(it);
+                if (half == 0) {
+                    float v[16];
+                    tmem_ld16(T_WORK + t_lane, v);
+                    tmem_wait_ld();
+                    if (rvalid) {
+#pragma unroll
+                        for (int j = 0; j < 9; ++j) sOuth[row64 * 16 + j] = v[j] + bias[384 + j];
+                    }
+                }
+                fence_before();
+                epi_bar();
+                float s = 0.f;
+                for (int o = threadIdx.x; o < R * 8; o += NEPI) s += sOuth[(o >> 3) * 16 + (o & 7)];
+                const float mean = epi_sum(s, red) * (1.0f / (8 * R));
+                if (net == 0) {
+                    if (threadIdx.x < R) {
+                        const float* o = sOuth + threadIdx.x * 16;
+                        float mx = o[0];
+#pragma unroll
+                        for (int j = 1; j < 8; ++j) mx = fmaxf(mx, o[j]);
+                        nq[threadIdx.x] = mx + o[8] - mean;
+                    }
+                    epi_bar();
+                } else {
+                    mean_e = mean;
+                }
+            }
+            stamp(it);
+            // ---- TD target, loss, priorities, dOut ----
+            {
+                float g = 0.f, sq = 0.f;
+                if (threadIdx.x < R) {
+                    const int b = threadIdx.x;
+                    const float qa = sOuth[b * 16 + act[b]] + sOuth[b * 16 + 8] - mean_e;
+                    const float y = rew[b] + P.lb.gamma * (1.0f - dn[b]) * nq[b];
+                    const float diff = qa - y;
+                    g = 2.0f * diff * (1.0f / R);
+                    sq = diff * diff;
+                    gb[b] = g;
+                    P.lb.new_prio[(size_t)e * R + b] = fabsf(nq[b] - qa);
+                }
+                const float gsum = epi_sum(g, red);
+                const float loss = epi_sum(sq, red) * (1.0f / R);
+                if (threadIdx.x == 0) P.lb.loss[e] = loss;
+                const float shift = gsum * (1.0f / (8 * R));
+                for (int o = threadIdx.x; o < R * 16; o += NEPI) {
+                    const int b = o >> 4, j = o & 15;
+                    const float d = j < 8 ? ((j == act[b] ? gb[b] : 0.f) - shift) : (j == 8 ? gb[b] : 0.f);
+                    sDout[img_off(b, j, 16)] = to_tf32(d);
+                    if (j < 12) sDpl[b * 12 + j] = d;
+                }
+                epi_bar();
+            }
+            stamp(it);
+            // ---- dH2^T[n2][b] = Wh[n2][:] . dOut[b][:]  (pre-mask), issued first so that it runs under the head-gradient SIMT ----
+            RL_STAGE({ const uint32_t idesc = make_idesc(128, 64, 0, 0);
+                       const uint32_t slot = consumed % NS2;
+                       mbar_wait(&full[slot], (consumed / NS2) & 1);
+                       fence_after();
+                       const uint32_t a_base = smem_u32(sStage + slot * CHUNK_F);
+                       for (int h = 0; h < 2; ++h)
+                           for (int ks = 0; ks < 2; ++ks)
+                               mma_tf32(T_WORK + h * 64, desc_kmajor(a_base + h * (128 * 16 * 4) + ks * 256, 16), desc_kmajor(aD + ks * 256, 16), idesc, ks != 0);
+                       mma_commit(&empty[slot]);
+                       ++consumed; });
+            // ---- head gradients (SIMT): dWh[k][j] += sum_b H2[b][k] dOut[b][j]; dbh ----
+            {
+                const int k = threadIdx.x;
+                float acc[9];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) acc[j] = 0.f;
+                const float* hk = sH2 + (k >> 2) * TP_CH + (k & 3);
+#pragma unroll 1
+                for (int g = 0; g < 8; ++g) {
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int b = g * 8 + rr;
+                        const float h = hk[g * (64 * TP_CH) + rr * 4];
+                        const float4 d0 = *reinterpret_cast<const float4*>(sDpl + b * 12), d1 = *reinterpret_cast<const float4*>(sDpl + b * 12 + 4);
+                        const float d8 = sDpl[b * 12 + 8];
+                        acc[0] = fmaf(h, d0.x, acc[0]); acc[1] = fmaf(h, d0.y, acc[1]); acc[2] = fmaf(h, d0.z, acc[2]); acc[3] = fmaf(h, d0.w, acc[3]);
+                        acc[4] = fmaf(h, d1.x, acc[4]); acc[5] = fmaf(h, d1.y, acc[5]); acc[6] = fmaf(h, d1.z, acc[6]); acc[7] = fmaf(h, d1.w, acc[7]);
+                        acc[8] = fmaf(h, d8, acc[8]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 9; ++j) red_add(G + L::OFF_WH + k * 9 + j, acc[j]);
+                if (threadIdx.x < 9) {
+                    float s = 0.f;
+                    for (int b = 0; b < R; ++b) s += sDpl[b * 12 + threadIdx.x];
+                    red_add(G + L::OFF_BH + threadIdx.x, s);
+                }
+            }
+            // ---- dH2 epilogue: lane = feature n2; mask by H2 > 0; dH2 batch-major in place (B of dH1^T), dH2^T feature-major
+            //      (B of dW2) through the half buffer: features 0-127 now, 128-255 after the first dW2 half has been consumed ----
+            wait_done(); stamp(it);
+            float dv[64];
+            {
+                float sb2 = 0.f;
+#pragma unroll
+                for (int cb = 0; cb < 2; ++cb) {
+                    float v[32];
+                    tmem_ld32(T_WORK + t_lane + half * 64 + cb * 32, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float* ph = sH2 + bimg_off(cb * 32 + j, f2, 256);
+                        const float m = *ph > 0.f ? to_tf32(v[j]) : 0.f;
+                        *ph = m;
+                        dv[cb * 32 + j] = m;
+                        sb2 += m;
+                    }
+                }
+                red_add(G + L::OFF_B2 + f2, sb2);                                  // db2[n2] = sum_b dH2[b][n2]
+                if (half == 0) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 16; ++j4)
+                        *reinterpret_cast<float4*>(sDT + timg_off(f1, j4 * 4)) = make_float4(dv[j4 * 4], dv[j4 * 4 + 1], dv[j4 * 4 + 2], dv[j4 * 4 + 3]);
+                }
+            }
+            stamp(it);
+            RL_STAGE({ const uint32_t idesc = make_idesc(128, 128, 0, 0);                  // dW2 half 0 (TMEM-resident accumulator)
+                       for (int ks = 0; ks < 8; ++ks)
+                           mma_tf32(T_DW2, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aH1 + ks * TP_KSTEP), idesc, (it | ks) != 0); });
+            wait_done(); stamp(it);                                                    // dW2 half 0 finished reading the half buffer
+            if (half == 1) {
+#pragma unroll
+                for (int j4 = 0; j4 < 16; ++j4)
+                    *reinterpret_cast<float4*>(sDT + timg_off(f1, j4 * 4)) = make_float4(dv[j4 * 4], dv[j4 * 4 + 1], dv[j4 * 4 + 2], dv[j4 * 4 + 3]);
+            }
+            stamp(it);
+            // ---- dW2 half 1, then dH1^T[k1][b] = W2^T[k1][:] . dH2[b][:]  (A = W2T chunks, B = dH2 batch-major image) ----
+            RL_STAGE({ const uint32_t idesc = make_idesc(128, 128, 0, 0);
+                       for (int ks = 0; ks < 8; ++ks)
+                           mma_tf32(T_DW2 + 128, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aH1 + ks * TP_KSTEP), idesc, (it | ks) != 0);
+                       stream_gemm_w(T_WORK, 1, aH2, TP_CH * 4u, 64u * TP_CH * 4u, TP_KSTEP, 8, 32, 64); });
+            gather_load(xr, P.rp.obs + ring * RL_K1, idx);   // X rows again (for the X^T image), hidden behind the dH1 MMAs
+            wait_done(); stamp(it);
+            {   // epilogue: lane = feature k1, this warp's 32 batch columns; mask by H1 > 0, dH1^T in place of H1^T, db1
+                float v[32];
+                tmem_ld32(T_WORK + t_lane + half * 32, v);
+                tmem_wait_ld();
+                float sb1 = 0.f;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    float4* ph = reinterpret_cast<float4*>(sH1T + timg_off(f1, half * 32 + j4 * 4));
+                    const float4 h = *ph;
+                    float4 o;
+                    o.x = h.x > 0.f ? to_tf32(v[j4 * 4 + 0]) : 0.f; o.y = h.y > 0.f ? to_tf32(v[j4 * 4 + 1]) : 0.f;
+                    o.z = h.z > 0.f ? to_tf32(v[j4 * 4 + 2]) : 0.f; o.w = h.w > 0.f ? to_tf32(v[j4 * 4 + 3]) : 0.f;
+                    *ph = o;
+                    sb1 += (o.x + o.y) + (o.z + o.w);
+                }
+                red_add(G + L::OFF_B1 + f1, sb1);                                  // db1[k1] (two warps share a feature)
+            }
+            stamp(it);
+            gather_store<true>(sXT, xr);                      // X^T image for dW1^T (dH2 region is dead: dH1 MMAs are done)
+            stamp(it);
+            RL_STAGE({ const uint32_t idesc = make_idesc(128, 160, 0, 0);                  // dW1^T = dH1^T X
+                       for (int ks = 0; ks < 8; ++ks)
+                           mma_tf32(T_WORK, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aXT + ks * TP_KSTEP), idesc, ks != 0); });
+            if (more) gather_load(xr, P.rp.next_obs + ring_next * RL_K1, meta + ((it + 1) & 1) * 256);
+            wait_done(); stamp(it);
+            if (more) gather_store<false>(sX, xr);            // sX (dH1^T) is free: the dW1 MMAs have completed
+            {
+                float* gr = G + L::OFF_W1T + f1 * RL_K1;
+                for (int cb = half; cb < 5; cb += 2) {
+                    float v[32];
+                    tmem_ld32(T_WORK + t_lane + cb * 32, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) red_add4(gr + cb * 32 + j4 * 4, v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                }
+            }
+            fence_before();
+            epi_bar();
+            ring_cur = ring_next;
+            stamp(it);
+        }
+        if (n_my > 0) {     // flush the TMEM-resident dW2 accumulator once
+            for (int cb = 0; cb < 4; ++cb) {
+                const int c0 = half * 128 + cb * 32;
+                float v[32];
+                tmem_ld32(T_DW2 + t_lane + c0, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)
+                    *reinterpret_cast<float4*>(G + L::OFF_W2T + f1 * 256 + c0 + j4 * 4) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+// =====================================================================================================
 // brain.get_action for the dueling brains on the tensor cores: the forward half of the event kernel over 64-row
 // tiles of the brain's ALL row list (Helpers/trainer.py:88-89; PERD3QN.py:81-89,198-210; D3QN.py:82-93,161-173).
 // Same pipeline: warp 8 streams the 14 weight chunks of a tile (W1[5], W2K[8], WH), epilogue thread 0 issues the
@@ -803,7 +1214,17 @@ int rl_brain_learn_tc(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t
     }
     const int n_cta = rl_learn_grid();
     cudaStream_t st = (cudaStream_t)stream;
-    k_learn_dueling_tc<<<n_cta, NTHREADS, TC_SMEM, st>>>(P);
+    static const bool use_v1 = getenv("RL_TC_V1") != nullptr;      // M = 64 batch-major formulation (kept for A/B runs)
+    if (use_v1) {
+        k_learn_dueling_tc<<<n_cta, NTHREADS, TC_SMEM, st>>>(P);
+    } else {
+        static bool attr2 = false;
+        if (!attr2) {
+            RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dueling_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM));
+            attr2 = true;
+        }
+        k_learn_dueling_tc2<<<n_cta, NTHREADS, TC2_SMEM, st>>>(P);
+    }
     RL_CUDA_CHECK(cudaGetLastError());
     if (tracing) {
         long long h[8 * 40];

@@ -12,7 +12,10 @@
 
 namespace {
 
-constexpr int WT = 256;         // threads per world
+#ifndef RL_WT
+#define RL_WT 256
+#endif
+constexpr int WT = RL_WT;       // threads per world
 constexpr int WNW = WT / 32;    // warps per world
 
 
@@ -155,9 +158,9 @@ __device__ __forceinline__ void init_tables(const WParams& P, WS& s) {
     const int H = P.cfg.height, W = P.cfg.width, PW = W + 6;
     const int PADN = (((H + 6) * PW) + 3) & ~3;
     const int t = threadIdx.x;
-    if (t < 160) {
-        const int pl = t / 49, q = t - pl * 49;
-        s.offtab[t] = t < 147 ? (pl == 1 ? PADN : 0) + (q / 7) * PW + (q - (q / 7) * 7) : 0;   // food / gene share plane 0
+    for (int e = t; e < 160; e += WT) {
+        const int pl = e / 49, q = e - pl * 49;
+        s.offtab[e] = e < 147 ? (pl == 1 ? PADN : 0) + (q / 7) * PW + (q - (q / 7) * 7) : 0;   // food / gene share plane 0
     }
     for (int k = t; k < H + 6; k += WT) { int si = k - 3; si += si < 0 ? H : 0; si -= si >= H ? H : 0; s.rowmap[k] = si * W; }   // H, W >= 3
     for (int k = t; k < W + 6; k += WT) { int sj = k - 3; sj += sj < 0 ? W : 0; sj -= sj >= W ? W : 0; s.colmap[k] = sj; }
