@@ -548,7 +548,7 @@ constexpr int V2_DPL = V2_OUTH;                         // dOut plain [64][12] a
 constexpr int V2_SMALL = V2_OUTH + 1024;
 constexpr int V2_INT = V2_SMALL + SM_SMALL_N;
 constexpr int V2_FLOATS = V2_INT + 2 * 256;
-constexpr size_t TC2_SMEM = sizeof(float) * V2_FLOATS + 8 * (2 * NS2 + 2) + 16;
+constexpr size_t TC2_SMEM = sizeof(float) * V2_FLOATS + 8 * (2 * NS2 + 3) + 16;
 static_assert(TC2_SMEM <= 227 * 1024, "shared memory budget");
 
 // batch-major image [64 rows][K cols] with the padded chunk stride: consecutive features of one batch row sit in
@@ -556,7 +556,30 @@ static_assert(TC2_SMEM <= 227 * 1024, "shared memory budget");
 __device__ __forceinline__ int bimg_off(int b, int c, int K) { return (b >> 3) * ((K >> 2) * TP_CH) + (c >> 2) * TP_CH + (b & 7) * 4 + (c & 3); }
 __device__ __forceinline__ uint64_t desc_bimg(uint32_t saddr, int K) { return make_desc(saddr, TP_CH * 4, (uint32_t)(K >> 2) * TP_CH * 4); }
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc2(const TcLearnParams P) {
+constexpr int NTHREADS2 = NEPI + 64;     // warps 0-7 epilogue, warp 8 weight-stream producer, warp 9 MMA issuer
+
+// chunk schedule of one event in the issuer's consumption order (the eval L1^T is issued right after the target L2^T)
+__device__ __forceinline__ void sched_entry2(int i, int& net, int& chunk) {
+    if (i < 5) { net = 0; chunk = WI_W1 + i; }                  // target L1^T
+    else if (i < 13) { net = 0; chunk = WI_W2K + (i - 5); }     // target L2^T
+    else if (i < 18) { net = 1; chunk = WI_W1 + (i - 13); }     // eval L1^T
+    else if (i == 18) { net = 0; chunk = WI_WH; }               // target head
+    else if (i < 27) { net = 1; chunk = WI_W2K + (i - 19); }    // eval L2^T
+    else if (i == 27) { net = 1; chunk = WI_WH; }               // eval head
+    else if (i == 28) { net = 1; chunk = WI_WHT; }              // dH2^T
+    else { net = 1; chunk = WI_W2T + (i - 29); }                // dH1^T
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Roles: the producer (warp 8) streams the fixed 37-chunk schedule of every event through the ring; the issuer (warp 9)
+// runs the fixed stage list of an event, each stage released by a `go` arrival of all 256 epilogue threads (their
+// shared-memory images are written and fenced) and reported back through `done` (main chain) or `doneL1` (the L1^T
+// stages, which run ahead: the eval L1^T under the target L2 epilogue, the NEXT event's target L1^T under the dW1
+// epilogue).  The epilogue warps therefore never wait for weight chunks, only for finished accumulators.
+__global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLearnParams P) {
     using L = Layout<RL_MODEL_DUELING>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* sm = reinterpret_cast<float*>(smem_raw);
@@ -570,8 +593,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc2(const TcLearn
     float* bias_e = bias_t + 400;             // same for the eval net
     int* meta = reinterpret_cast<int*>(sm + V2_INT);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + V2_FLOATS);
-    uint64_t* full = bars; uint64_t* empty = bars + NS2; uint64_t* done = bars + 2 * NS2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 2);
+    uint64_t* full = bars; uint64_t* empty = bars + NS2; uint64_t* done = bars + 2 * NS2; uint64_t* doneL1 = done + 1; uint64_t* go = done + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 3);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* Pe = P.lb.params; const float* Pt = P.lb.target;
@@ -581,7 +604,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc2(const TcLearn
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NS2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(done, 1);
+        mbar_init(done, 1); mbar_init(doneL1, 1); mbar_init(go, NEPI);
         fence_mbar_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -598,61 +621,124 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc2(const TcLearn
     fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t T_WORK = tmem, T_DW2 = tmem + 256;
+    const uint32_t T_L1 = tmem + 192;          // L1^T accumulator [128][64] has its own columns (dW1^T uses 0-159)
     const int S = P.cfg.slot_cap, cap = P.rp.capacity;
+    const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH1T = smem_u32(sH1T), aH2 = smem_u32(sH2), aD = smem_u32(sDout), aXT = smem_u32(sXT);
 
     if (warp == 8) {
+        // =================================== weight-stream producer ===================================
         if (lane == 0) {
             const uint32_t n_chunks = (uint32_t)n_my * SCHED_N;
             for (uint32_t produced = 0; produced < n_chunks; ++produced) {
                 const uint32_t slot = produced % NS2;
                 if (produced >= NS2) mbar_wait(&empty[slot], ((produced / NS2) - 1) & 1);
-                int net, ch; sched_entry(produced % SCHED_N, net, ch);
+                int net, ch; sched_entry2(produced % SCHED_N, net, ch);
                 bulk_load(sStage + slot * CHUNK_F, (net ? P.wimg_e : P.wimg_t) + (size_t)ch * CHUNK_F, CHUNK_F * 4, &full[slot]);
             }
         }
-    } else {
-        uint32_t stage_no = 0, consumed = 0;
-        const int q = warp & 3, half = warp >> 2;
-        const uint32_t t_lane = (uint32_t)(q * 32) << 16;
-        const int f1 = q * 32 + lane;                   // feature owned in 128-feature stages (k1)
-        const int f2 = half * 128 + f1;                 // feature owned in 256-feature stages (n2)
-        const int row64 = q * 16 + lane;                // M = 64 accumulator (head only): rows 16q+i in lanes 32q+i, i < 16
-        const bool rvalid = lane < 16;
-        const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH1T = smem_u32(sH1T), aH2 = smem_u32(sH2), aD = smem_u32(sDout), aXT = smem_u32(sXT);
-        auto stage_sync = [&]() { fence_proxy_async(); fence_before(); epi_bar(); };
-        // thread 0: D[m_halves x 128 features][n] (+)= Wchunk (A, streams through the ring) x Act (B, resident image).
-        // b_lbo / b_sbo / b_kstep describe the activation image; a chunk holds kc k-columns for m_halves*128 feature rows.
-        auto stream_gemm_w = [&](uint32_t d_tmem, int m_halves, uint32_t b_base, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep,
-                                 int nch, int kc, int n) {
-            const uint32_t idesc = make_idesc(128, n, 0, 0);
-            for (int c = 0; c < nch; ++c) {
+    } else if (warp == 9) {
+        // =================================== MMA issuer ===================================
+        if (lane == 0) {
+            uint32_t consumed = 0, go_no = 0;
+            auto wait_go = [&]() { mbar_wait(go, go_no & 1); ++go_no; fence_after(); };
+            auto chunk_wait = [&]() -> uint32_t {
                 const uint32_t slot = consumed % NS2;
                 mbar_wait(&full[slot], (consumed / NS2) & 1);
                 fence_after();
-                const uint32_t a_base = smem_u32(sStage + slot * CHUNK_F);
-                for (int h = 0; h < m_halves; ++h)
-                    for (int ks = 0; ks < kc / 8; ++ks) {
-                        const uint32_t kstep = (uint32_t)(c * (kc / 8) + ks);
-                        mma_tf32(d_tmem + h * n, desc_kmajor(a_base + h * (128 * kc * 4) + ks * 256, kc),
-                                 make_desc(b_base + kstep * b_kstep, b_lbo, b_sbo), idesc, (c | ks) != 0);
-                    }
-                mma_commit(&empty[slot]);
-                ++consumed;
+                return smem_u32(sStage + slot * CHUNK_F);
+            };
+            auto chunk_release = [&]() { mma_commit(&empty[consumed % NS2]); ++consumed; };
+            // D[m_halves x 128 features][n] = Wchunk (A, from the ring) x Act (B, resident image described by lbo/sbo/kstep)
+            auto stream_gemm_w = [&](uint32_t d_tmem, int m_halves, uint32_t b_base, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep,
+                                     int nch, int kc, int n) {
+                const uint32_t idesc = make_idesc(128, n, 0, 0);
+                for (int c = 0; c < nch; ++c) {
+                    const uint32_t a_base = chunk_wait();
+                    for (int h = 0; h < m_halves; ++h)
+                        for (int ks = 0; ks < kc / 8; ++ks) {
+                            const uint32_t kstep = (uint32_t)(c * (kc / 8) + ks);
+                            mma_tf32(d_tmem + h * n, desc_kmajor(a_base + h * (128 * kc * 4) + ks * 256, kc),
+                                     make_desc(b_base + kstep * b_kstep, b_lbo, b_sbo), idesc, (c | ks) != 0);
+                        }
+                    chunk_release();
+                }
+            };
+            auto l1 = [&]() { stream_gemm_w(T_L1, 1, aX, 128u, RL_K1 * 32u, 256u, 5, 32, 64); mma_commit(doneL1); };
+            auto l2 = [&]() { stream_gemm_w(T_WORK, 2, aH1, TP_CH * 4u, 32u * TP_CH * 4u, TP_KSTEP, 8, 16, 64); mma_commit(done); };
+            auto head = [&]() {
+                const uint32_t idesc = make_idesc(64, 16, 0, 0);
+                const uint32_t b_base = chunk_wait();
+                for (int ks = 0; ks < 32; ++ks)
+                    mma_tf32(T_WORK, desc_bimg(aH2 + ks * TP_KSTEP, 256), desc_kmajor(b_base + ks * 256, 256), idesc, ks != 0);
+                chunk_release();
+                mma_commit(done);
+            };
+            for (int it = 0; it < n_my; ++it) {
+                if (it == 0) { wait_go(); l1(); }                 // target L1^T of event 0 (later ones are issued one event ahead)
+                wait_go(); l2(); l1();                            // target L2^T, then the eval L1^T (runs under the target L2 epilogue)
+                wait_go(); head();                                // target head
+                wait_go(); l2();                                  // eval L2^T
+                wait_go(); head();                                // eval head
+                wait_go();                                        // dH2^T[n2][b] = Wh[n2][:] . dOut[b][:]
+                {
+                    const uint32_t idesc = make_idesc(128, 64, 0, 0);
+                    const uint32_t a_base = chunk_wait();
+                    for (int h = 0; h < 2; ++h)
+                        for (int ks = 0; ks < 2; ++ks)
+                            mma_tf32(T_WORK + h * 64, desc_kmajor(a_base + h * (128 * 16 * 4) + ks * 256, 16), desc_kmajor(aD + ks * 256, 16), idesc, ks != 0);
+                    chunk_release();
+                    mma_commit(done);
+                }
+                wait_go();                                        // dW2 half 0 (TMEM-resident accumulator)
+                {
+                    const uint32_t idesc = make_idesc(128, 128, 0, 0);
+                    for (int ks = 0; ks < 8; ++ks)
+                        mma_tf32(T_DW2, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aH1 + ks * TP_KSTEP), idesc, (it | ks) != 0);
+                    mma_commit(done);
+                }
+                wait_go();                                        // dW2 half 1, then dH1^T[k1][b] = W2^T[k1][:] . dH2[b][:]
+                {
+                    const uint32_t idesc = make_idesc(128, 128, 0, 0);
+                    for (int ks = 0; ks < 8; ++ks)
+                        mma_tf32(T_DW2 + 128, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aH1 + ks * TP_KSTEP), idesc, (it | ks) != 0);
+                    stream_gemm_w(T_WORK, 1, aH2, TP_CH * 4u, 64u * TP_CH * 4u, TP_KSTEP, 8, 32, 64);
+                    mma_commit(done);
+                }
+                wait_go();                                        // dW1^T = dH1^T X
+                {
+                    const uint32_t idesc = make_idesc(128, 160, 0, 0);
+                    for (int ks = 0; ks < 8; ++ks)
+                        mma_tf32(T_WORK, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aXT + ks * TP_KSTEP), idesc, ks != 0);
+                    mma_commit(done);
+                }
+                if (it + 1 < n_my) { wait_go(); l1(); }           // next event's target L1^T (runs under the dW1 epilogue)
             }
-        };
+        }
+    } else {
+        // =================================== epilogue warps ===================================
+        uint32_t done_no = 0, l1_no = 0;
+        const int q = warp & 3, half = warp >> 2;
+        const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+        const int f1 = q * 32 + lane;                   // feature owned in 128-feature stages (k1)
+        const int f2 = half * 128 + f1;                 // feature owned in 256-feature stages (n2) == threadIdx.x
+        const int row64 = q * 16 + lane;                // M = 64 accumulator (head only): rows 16q+i in lanes 32q+i, i < 16
+        const bool rvalid = lane < 16;
+        // this thread's shared-memory images are written: make them visible to the tensor core and release the next stage
+        auto go_signal = [&]() { fence_proxy_async(); fence_before(); mbar_arrive(go); };
+        auto wait_done = [&]() { mbar_wait(done, done_no & 1); ++done_no; fence_after(); };
+        auto wait_l1 = [&]() { mbar_wait(doneL1, l1_no & 1); ++l1_no; fence_after(); };
         int tr_n = 0;
         auto stamp = [&](int it) { if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 8 && tr_n < 40) P.trace[it * 40 + tr_n++] = clock64(); };
-        auto wait_done = [&]() { mbar_wait(done, stage_no & 1); ++stage_no; fence_after(); };
         int meta_i = 0; size_t meta_ring = 0;
-        auto load_meta_a = [&](int b, int e) {
+        auto load_meta_a = [&](int b, int e) {           // phase A (warps 6-7): sampled ring positions
             if (threadIdx.x >= NEPI - R) {
                 const int r = threadIdx.x - (NEPI - R);
                 meta_ring = (size_t)(P.ev_rows[e] / S) * cap;
-                meta_i = max(P.sample_idx[(size_t)e * R + r], 0);
+                meta_i = max(P.sample_idx[(size_t)e * R + r], 0);     // -1 = skipped by the uniform sampler (error state)
                 meta[b * 256 + r] = meta_i;
             }
         };
-        auto load_meta_b = [&](int b) {
+        auto load_meta_b = [&](int b) {                  // phase B: action / reward / done of those positions
             if (threadIdx.x >= NEPI - R) {
                 const int r = threadIdx.x - (NEPI - R);
                 int* m = meta + b * 256;
@@ -669,106 +755,105 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc2(const TcLearn
             }
         };
         float4 xr[10];
-        size_t ring_cur = 0;
+        size_t ring_cur = 0, ring_n1 = 0, ring_n2 = 0;
         if (n_my > 0) {
+            // prologue: metadata + target-net input of event 0, its target L1^T released, eval-net rows of event 0 and the
+            // ring positions of event 1 on their way
             load_meta_a(0, blockIdx.x);
             load_meta_b(0);
             epi_bar();
             ring_cur = (size_t)(P.ev_rows[blockIdx.x] / S) * cap;
             gather_load(xr, P.rp.next_obs + ring_cur * RL_K1, meta);
             gather_store<false>(sX, xr);
+            go_signal();                                                                     // -> target L1^T
+            gather_load(xr, P.rp.obs + ring_cur * RL_K1, meta);
+            if (n_my > 1) { load_meta_a(1, blockIdx.x + gridDim.x); ring_n1 = (size_t)(P.ev_rows[blockIdx.x + gridDim.x] / S) * cap; }
         }
+        // L1 epilogue: lane = feature k1, this warp's 32 batch columns; H1 = relu(D + b1)
+        auto l1_epilogue = [&](const float* bias, bool eval) {
+            float v[32];
+            tmem_ld32(T_L1 + t_lane + half * 32, v);
+            tmem_wait_ld();
+            const float b1 = bias[f1];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = to_tf32(fmaxf(v[j] + b1, 0.f));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sH1[bimg_off(half * 32 + j, f1, 128)] = v[j];                // batch-major: B of L2^T
+            if (eval) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)                                                         // feature-major: A of dW2, relu mask of dH1
+                    *reinterpret_cast<float4*>(sH1T + timg_off(f1, half * 32 + j4 * 4)) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+            }
+        };
+        // L2 epilogue: lane = feature n2, all 64 batch columns; H2 = relu(D + b2) -> batch-major image
+        auto l2_epilogue = [&](const float* bias) {
+            const float b2 = bias[128 + f2];
+#pragma unroll
+            for (int cb = 0; cb < 2; ++cb) {
+                float v[32];
+                tmem_ld32(T_WORK + t_lane + half * 64 + cb * 32, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sH2[bimg_off(cb * 32 + j, f2, 256)] = to_tf32(fmaxf(v[j] + b2, 0.f));
+            }
+        };
+        // head epilogue: [A(8) | V] + bh -> sOuth; returns the mean of the whole [64, 8] advantage tensor
+        auto head_epilogue = [&](const float* bias) -> float {
+            if (half == 0) {
+                float v[16];
+                tmem_ld16(T_WORK + t_lane, v);
+                tmem_wait_ld();
+                if (rvalid) {
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) sOuth[row64 * 16 + j] = v[j] + bias[384 + j];
+                }
+            }
+            fence_before();
+            epi_bar();
+            float s = 0.f;
+            for (int o = threadIdx.x; o < R * 8; o += NEPI) s += sOuth[(o >> 3) * 16 + (o & 7)];
+            return epi_sum(s, red) * (1.0f / (8 * R));
+        };
         for (int it = 0; it < n_my; ++it) {
             tr_n = 0; stamp(it);
             const int e = blockIdx.x + it * gridDim.x;
-            const bool more = it + 1 < n_my;
+            const bool more = it + 1 < n_my, more2 = it + 2 < n_my;
             const int* idx = meta + (it & 1) * 256; const int* act = idx + 64;
             const float* rew = reinterpret_cast<const float*>(idx + 128); const float* dn = rew + 64;
             const size_t ring = ring_cur;
-            size_t ring_next = 0;
-            float mean_e = 0.f;
-            for (int net = 0; net < 2; ++net) {
-                const float* bias = net ? bias_e : bias_t;
-                // ---- L1^T: H1^T[k1][b] = W1[k1][:] . X[b][:]   (A = W1 chunks, B = X image) ----
-                stamp(it); RL_STAGE(stream_gemm_w(T_WORK, 1, aX, 128u, RL_K1 * 32u, 256u, 5, 32, 64));
-                if (net == 0) {
-                    gather_load(xr, P.rp.obs + ring * RL_K1, idx);
-                    if (more) { load_meta_a((it + 1) & 1, e + gridDim.x); ring_next = (size_t)(P.ev_rows[e + gridDim.x] / S) * cap; }
-                }
-                wait_done(); stamp(it);
-                if (net == 0) gather_store<false>(sX, xr);      // sX is free: the target L1 MMAs have completed
-                {   // epilogue: lane = feature k1, this warp's 32 batch columns; H1 = relu(D + b1)
-                    float v[32];
-                    tmem_ld32(T_WORK + t_lane + half * 32, v);
-                    tmem_wait_ld();
-                    const float b1 = bias[f1];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = to_tf32(fmaxf(v[j] + b1, 0.f));
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) sH1[bimg_off(half * 32 + j, f1, 128)] = v[j];        // batch-major: B of L2^T
-                    if (net) {
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4)                                                 // feature-major: A of dW2, relu mask of dH1
-                            *reinterpret_cast<float4*>(sH1T + timg_off(f1, half * 32 + j4 * 4)) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-                    }
-                }
-                // ---- L2^T: H2^T[n2][b] = W2[n2][:] . H1[b][:]   (two 128-feature halves per chunk) ----
-                stamp(it); RL_STAGE(stream_gemm_w(T_WORK, 2, aH1, TP_CH * 4u, 32u * TP_CH * 4u, TP_KSTEP, 8, 16, 64));
-                if (net == 0 && more) {
-                    load_meta_b((it + 1) & 1);
-                    prefetch_rows(ring_next, meta + ((it + 1) & 1) * 256);
-                }
-                wait_done(); stamp(it);
-                {   // epilogue: lane = feature n2 (f2), all 64 batch columns; H2 = relu(D + b2) -> batch-major image
-                    const float b2 = bias[128 + f2];
-#pragma unroll
-                    for (int cb = 0; cb < 2; ++cb) {
-                        float v[32];
-                        tmem_ld32(T_WORK + t_lane + half * 64 + cb * 32, v);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) sH2[bimg_off(cb * 32 + j, f2, 256)] = to_tf32(fmaxf(v[j] + b2, 0.f));
-                    }
-                }
-                // ---- head (normal form, M = 64): out[b][j] = H2[b][:] . Wh[j][:] ----
-                stamp(it);
-                RL_STAGE({ const uint32_t idesc = make_idesc(64, 16, 0, 0);
-                           const uint32_t slot = consumed % NS2;
-                           mbar_wait(&full[slot], (consumed / NS2) & 1);
-                           fence_after();
-                           const uint32_t b_base = smem_u32(sStage + slot * CHUNK_F);
-                           for (int ks = 0; ks < 32; ++ks)
-                               mma_tf32(T_WORK, desc_bimg(aH2 + ks * TP_KSTEP, 256), desc_kmajor(b_base + ks * 256, 256), idesc, ks != 0);
-                           mma_commit(&empty[slot]);
-                           ++consumed; });
-                wait_done(); stamp(it);
-                if (half == 0) {
-                    float v[16];
-                    tmem_ld16(T_WORK + t_lane, v);
-                    tmem_wait_ld();
-                    if (rvalid) {
-#pragma unroll
-                        for (int j = 0; j < 9; ++j) sOuth[row64 * 16 + j] = v[j] + bias[384 + j];
-                    }
-                }
-                fence_before();
-                epi_bar();
-                float s = 0.f;
-                for (int o = threadIdx.x; o < R * 8; o += NEPI) s += sOuth[(o >> 3) * 16 + (o & 7)];
-                const float mean = epi_sum(s, red) * (1.0f / (8 * R));
-                if (net == 0) {
-                    if (threadIdx.x < R) {
-                        const float* o = sOuth + threadIdx.x * 16;
-                        float mx = o[0];
-#pragma unroll
-                        for (int j = 1; j < 8; ++j) mx = fmaxf(mx, o[j]);
-                        nq[threadIdx.x] = mx + o[8] - mean;
-                    }
-                    epi_bar();
-                } else {
-                    mean_e = mean;
-                }
+            // ---------------- target net ----------------
+            wait_l1(); stamp(it);                                   // target L1^T (issued one event ahead)
+            gather_store<false>(sX, xr);                            // eval-net input; sX is free: the target L1 MMAs have completed
+            l1_epilogue(bias_t, false);
+            go_signal();                                            // -> target L2^T, eval L1^T
+            if (more) {                                             // hidden behind them
+                load_meta_b((it + 1) & 1);
+                prefetch_rows(ring_n1, meta + ((it + 1) & 1) * 256);
             }
+            wait_done(); stamp(it);
+            l2_epilogue(bias_t);
+            go_signal();                                            // -> target head
+            wait_done(); stamp(it);
+            {
+                const float mean = head_epilogue(bias_t);
+                if (threadIdx.x < R) {
+                    const float* o = sOuth + threadIdx.x * 16;
+                    float mx = o[0];
+#pragma unroll
+                    for (int j = 1; j < 8; ++j) mx = fmaxf(mx, o[j]);
+                    nq[threadIdx.x] = mx + o[8] - mean;
+                }
+                epi_bar();
+            }
+            // ---------------- eval net ----------------
+            wait_l1(); stamp(it);
+            l1_epilogue(bias_e, true);
+            go_signal();                                            // -> eval L2^T
+            wait_done(); stamp(it);
+            l2_epilogue(bias_e);
+            go_signal();                                            // -> eval head
+            wait_done(); stamp(it);
+            const float mean_e = head_epilogue(bias_e);
             stamp(it);
             // ---- TD target, loss, priorities, dOut ----
             {
@@ -793,20 +878,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc2(const TcLearn
                     sDout[img_off(b, j, 16)] = to_tf32(d);
                     if (j < 12) sDpl[b * 12 + j] = d;
                 }
-                epi_bar();
             }
+            go_signal();                                            // -> dH2^T (runs under the head-gradient SIMT below)
+            epi_bar();                                              // sDpl complete for every warp
             stamp(it);
-            // ---- dH2^T[n2][b] = Wh[n2][:] . dOut[b][:]  (pre-mask), issued first so that it runs under the head-gradient SIMT ----
-            RL_STAGE({ const uint32_t idesc = make_idesc(128, 64, 0, 0);
-                       const uint32_t slot = consumed % NS2;
-                       mbar_wait(&full[slot], (consumed / NS2) & 1);
-                       fence_after();
-                       const uint32_t a_base = smem_u32(sStage + slot * CHUNK_F);
-                       for (int h = 0; h < 2; ++h)
-                           for (int ks = 0; ks < 2; ++ks)
-                               mma_tf32(T_WORK + h * 64, desc_kmajor(a_base + h * (128 * 16 * 4) + ks * 256, 16), desc_kmajor(aD + ks * 256, 16), idesc, ks != 0);
-                       mma_commit(&empty[slot]);
-                       ++consumed; });
             // ---- head gradients (SIMT): dWh[k][j] += sum_b H2[b][k] dOut[b][j]; dbh ----
             {
                 const int k = threadIdx.x;
@@ -835,8 +910,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc2(const TcLearn
                     red_add(G + L::OFF_BH + threadIdx.x, s);
                 }
             }
-            // ---- dH2 epilogue: lane = feature n2; mask by H2 > 0; dH2 batch-major in place (B of dH1^T), dH2^T feature-major
-            //      (B of dW2) through the half buffer: features 0-127 now, 128-255 after the first dW2 half has been consumed ----
+            // ---- dH2 epilogue: lane = feature n2 (the column this thread just read in the SIMT loop); mask by H2 > 0;
+            //      dH2 batch-major in place (B of dH1^T), dH2^T feature-major (B of dW2) through the half buffer:
+            //      features 0-127 now, 128-255 after the first dW2 half has been consumed ----
             wait_done(); stamp(it);
             float dv[64];
             {
@@ -862,25 +938,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc2(const TcLearn
                         *reinterpret_cast<float4*>(sDT + timg_off(f1, j4 * 4)) = make_float4(dv[j4 * 4], dv[j4 * 4 + 1], dv[j4 * 4 + 2], dv[j4 * 4 + 3]);
                 }
             }
-            stamp(it);
-            RL_STAGE({ const uint32_t idesc = make_idesc(128, 128, 0, 0);                  // dW2 half 0 (TMEM-resident accumulator)
-                       for (int ks = 0; ks < 8; ++ks)
-                           mma_tf32(T_DW2, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aH1 + ks * TP_KSTEP), idesc, (it | ks) != 0); });
-            wait_done(); stamp(it);                                                    // dW2 half 0 finished reading the half buffer
+            go_signal();                                            // -> dW2 half 0
+            wait_done(); stamp(it);                                 // it finished reading the half buffer
             if (half == 1) {
 #pragma unroll
                 for (int j4 = 0; j4 < 16; ++j4)
                     *reinterpret_cast<float4*>(sDT + timg_off(f1, j4 * 4)) = make_float4(dv[j4 * 4], dv[j4 * 4 + 1], dv[j4 * 4 + 2], dv[j4 * 4 + 3]);
             }
-            stamp(it);
-            // ---- dW2 half 1, then dH1^T[k1][b] = W2^T[k1][:] . dH2[b][:]  (A = W2T chunks, B = dH2 batch-major image) ----
-            RL_STAGE({ const uint32_t idesc = make_idesc(128, 128, 0, 0);
-                       for (int ks = 0; ks < 8; ++ks)
-                           mma_tf32(T_DW2 + 128, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aH1 + ks * TP_KSTEP), idesc, (it | ks) != 0);
-                       stream_gemm_w(T_WORK, 1, aH2, TP_CH * 4u, 64u * TP_CH * 4u, TP_KSTEP, 8, 32, 64); });
-            gather_load(xr, P.rp.obs + ring * RL_K1, idx);   // X rows again (for the X^T image), hidden behind the dH1 MMAs
+            go_signal();                                            // -> dW2 half 1, dH1^T
+            gather_load(xr, P.rp.obs + ring * RL_K1, idx);          // X rows again (for the X^T image), hidden behind the dH1 MMAs
             wait_done(); stamp(it);
-            {   // epilogue: lane = feature k1, this warp's 32 batch columns; mask by H1 > 0, dH1^T in place of H1^T, db1
+            {   // dH1 epilogue: lane = feature k1, this warp's 32 batch columns; mask by H1 > 0, dH1^T in place of H1^T, db1
                 float v[32];
                 tmem_ld32(T_WORK + t_lane + half * 32, v);
                 tmem_wait_ld();
@@ -897,15 +965,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc2(const TcLearn
                 }
                 red_add(G + L::OFF_B1 + f1, sb1);                                  // db1[k1] (two warps share a feature)
             }
-            stamp(it);
-            gather_store<true>(sXT, xr);                      // X^T image for dW1^T (dH2 region is dead: dH1 MMAs are done)
-            stamp(it);
-            RL_STAGE({ const uint32_t idesc = make_idesc(128, 160, 0, 0);                  // dW1^T = dH1^T X
-                       for (int ks = 0; ks < 8; ++ks)
-                           mma_tf32(T_WORK, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aXT + ks * TP_KSTEP), idesc, ks != 0); });
-            if (more) gather_load(xr, P.rp.next_obs + ring_next * RL_K1, meta + ((it + 1) & 1) * 256);
+            gather_store<true>(sXT, xr);                            // X^T image for dW1^T (dH2 region is dead: dH1 MMAs are done)
+            go_signal();                                            // -> dW1^T
+            if (more) gather_load(xr, P.rp.next_obs + ring_n1 * RL_K1, meta + ((it + 1) & 1) * 256);
             wait_done(); stamp(it);
-            if (more) gather_store<false>(sX, xr);            // sX (dH1^T) is free: the dW1 MMAs have completed
+            if (more) {
+                gather_store<false>(sX, xr);                        // sX (dH1^T) is free: the dW1 MMAs have completed
+                go_signal();                                        // -> next event's target L1^T (runs under the dW1 epilogue below)
+                gather_load(xr, P.rp.obs + ring_n1 * RL_K1, meta + ((it + 1) & 1) * 256);   // its eval-net rows
+                if (more2) {                                        // ring positions of the event after it (this event's buffer is dead)
+                    load_meta_a(it & 1, e + 2 * gridDim.x);
+                    ring_n2 = (size_t)(P.ev_rows[e + 2 * gridDim.x] / S) * cap;
+                }
+            }
             {
                 float* gr = G + L::OFF_W1T + f1 * RL_K1;
                 for (int cb = half; cb < 5; cb += 2) {
@@ -918,10 +990,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc2(const TcLearn
             }
             fence_before();
             epi_bar();
-            ring_cur = ring_next;
+            ring_cur = ring_n1; ring_n1 = ring_n2;
             stamp(it);
         }
-        if (n_my > 0) {     // flush the TMEM-resident dW2 accumulator once
+        if (n_my > 0) {     // flush the TMEM-resident dW2 accumulator once (the dW1 `done` covered every earlier MMA)
             for (int cb = 0; cb < 4; ++cb) {
                 const int c0 = half * 128 + cb * 32;
                 float v[32];
@@ -1223,7 +1295,7 @@ int rl_brain_learn_tc(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t
             RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dueling_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM));
             attr2 = true;
         }
-        k_learn_dueling_tc2<<<n_cta, NTHREADS, TC2_SMEM, st>>>(P);
+        k_learn_dueling_tc2<<<n_cta, NTHREADS2, TC2_SMEM, st>>>(P);
     }
     RL_CUDA_CHECK(cudaGetLastError());
     if (tracing) {
