@@ -205,6 +205,7 @@ def run_b200(args):
     n_meas = 5
     n_agents_meas = 0
     ev_meas = 0.0
+    env.kernel_events = []
     for _ in range(n_meas):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         n_agents_meas += int(env.world.n_agents.sum())
@@ -217,6 +218,16 @@ def run_b200(args):
         n_epi += 1
     n_avg = n_agents_meas / n_meas / NW
     ev_avg = ev_meas / n_meas
+    # the event kernel alone (one launch per brain per step): CUDA events recorded around rl_brain_learn(_tc)
+    k_ms = [a.elapsed_time(b) for (_, _, a, b) in env.kernel_events]
+    env.kernel_events = None
+    learn_kernel_ms = sum(k_ms) / max(1, len(k_ms))
+    ev_per_launch = ev_avg / len(brains)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01_final.json"))).get("k_learn_dueling_tc2_bytes_per_launch")
+    except Exception:
+        pass
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -233,22 +244,24 @@ def run_b200(args):
         "k_world_step": {"bound": "hbm", "ms": phases["step"], "achieved": b_step / phases["step"] / 1e6, "peak": hbm_peak, "unit": "GB/s"},
         "k_world_update": {"bound": "hbm", "ms": phases["update"], "achieved": b_obs / phases["update"] / 1e6, "peak": hbm_peak, "unit": "GB/s"},
         "k_world_topup": {"bound": "hbm", "ms": phases["top_up"], "achieved": b_obs / phases["top_up"] / 1e6, "peak": hbm_peak, "unit": "GB/s"},
-        "learn(k_learn_dueling+replay+adam)": {"bound": "tensor", "ms": phases["learn"],
-                                               "achieved": ev_avg * flop_event / phases["learn"] / 1e9, "peak": bf16_peak, "unit": "TFLOP/s",
-                                               "note": ("tcgen05 kind::tf32, TMEM accumulators; peak shown is the measured bf16 tensor peak (tf32 dense is half of it)"
-                                                        if args.precision == "tf32" else "fp32 FMA on CUDA cores (reference precision); peak shown is the bf16 tensor peak")},
-        "act(k_brain_act)": {"bound": "tensor", "ms": phases["act"], "achieved": NW * n_avg * 107008 / phases["act"] / 1e9,
-                             "peak": bf16_peak, "unit": "TFLOP/s", "note": "fp32 FMA on CUDA cores"},
+        "k_learn_dueling_tc2": {"bound": "tensor", "ms": learn_kernel_ms, "launches_per_step": len(brains),
+                                "achieved": ev_per_launch * flop_event / max(learn_kernel_ms, 1e-9) / 1e9, "peak": bf16_peak, "unit": "TFLOP/s",
+                                "note": ("one launch = all train() events of one brain (25.6 MFLOP per 64-row event), timed alone with CUDA events; "
+                                         "tcgen05 kind::tf32, TMEM accumulators; peak shown is the measured sustained bf16 tensor peak (tf32 dense is half of it)"
+                                         if args.precision == "tf32" else "fp32 FMA on CUDA cores (reference precision); peak shown is the bf16 tensor peak")},
+        "act(k_act_dueling_tc x2 + rows)": {"bound": "tensor", "ms": phases["act"], "achieved": NW * n_avg * 107008 / phases["act"] / 1e9,
+                                            "peak": bf16_peak, "unit": "TFLOP/s",
+                                            "note": "tcgen05 kind::tf32 forward" if args.precision == "tf32" else "fp32 FMA on CUDA cores"},
     }
     for v in roof_k.values():
         v["frac"] = v["achieved"] / v["peak"]
-    dominant = max(roof_k, key=lambda k: roof_k[k]["ms"])
-    roofline = dict(roof_k[dominant], kernel=dominant, traffic=None, peak_source=peak_src,
-                    step_share=roof_k[dominant]["ms"] / sum(phases.values()))
+    dominant = max(roof_k, key=lambda k: roof_k[k]["ms"] * roof_k[k].get("launches_per_step", 1))
+    roofline = dict(roof_k[dominant], kernel=dominant, traffic=traffic if dominant == "k_learn_dueling_tc2" else None, peak_source=peak_src,
+                    step_share=roof_k[dominant]["ms"] * roof_k[dominant].get("launches_per_step", 1) / sum(phases.values()))
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": ("tf32 (tensor-core learn, fp32 accumulate; act + Adam fp32)" if args.precision == "tf32" else "f32"), "data": "synthetic",
+            "dtype": ("tf32 (tensor-core forward/backward products, fp32 accumulate; world state exact integers, Adam fp32)" if args.precision == "tf32" else "f32"), "data": "synthetic",
             "config": {"workload": workload_name(args), "grid": [H, W], "worlds_total": n_worlds, "agents_per_world": n_avg,
                        "train_events_per_step_per_gpu": ev_avg, "parallelism": f"worlds sharded x{world_size}, brains replicated, "
                        "1 NCCL all-reduce of summed gradients per step" if world_size > 1 else "single GPU",

@@ -113,6 +113,7 @@ class Environment:
         self.viz = None
         self.grid = None
         self.gpu_launches = 0
+        self.kernel_events = None       # set to a list to collect (name, gene, start, end) CUDA events of the hot kernels
 
     # ------------------------------------------------------------------ reference phases
     def reset(self):
@@ -223,17 +224,27 @@ class Environment:
                 _lib.check(lib.rl_replay_sample_uniform(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
                                                         C.c_int32(b._dev.batch), C.c_uint64(w.t), C.c_int32(0), C.c_int32(1), C.c_int32(0),
                                                         C.c_void_p(b._dev.sample_idx.data_ptr()), C.c_void_p(self._sample_status.data_ptr()), st))
+            ev0 = ev1 = None
+            if self.kernel_events is not None:           # bench.py: CUDA-event time of the event kernel alone (roofline)
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             if self.precision == "tf32":
                 if b._dev.wimg_stale:
                     b._dev.build_wimg(st)
                     b._dev.wimg_stale = False
                     self.gpu_launches += 2
+                if ev0 is not None:
+                    ev0.record()
                 _lib.check(lib.rl_brain_learn_tc(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
                                                  C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs),
                                                  C.c_void_p(b._dev.wimg_e.data_ptr()), C.c_void_p(b._dev.wimg_t.data_ptr()), st))
             else:
+                if ev0 is not None:
+                    ev0.record()
                 _lib.check(lib.rl_brain_learn(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
                                               C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs), st))
+            if ev0 is not None:                          # brackets the event kernel + its 0.03 ms slab reduction
+                ev1.record()
+                self.kernel_events.append(("learn_events", g, ev0, ev1))
             self.gpu_launches += 3
         if self.dist:
             self._allreduce_grads(active)

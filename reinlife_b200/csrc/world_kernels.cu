@@ -16,6 +16,9 @@ namespace {
 #define RL_WT 256
 #endif
 constexpr int WT = RL_WT;       // threads per world
+#ifndef RL_WORLD_MINB
+#define RL_WORLD_MINB 6
+#endif
 constexpr int WNW = WT / 32;    // warps per world
 
 
@@ -399,7 +402,7 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
 // =====================================================================================================
 // Environment.step -- environment.py:160-186
 // =====================================================================================================
-__global__ void __launch_bounds__(WT, 6) k_world_step(const WParams P) {
+__global__ void __launch_bounds__(WT, RL_WORLD_MINB) k_world_step(const WParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int w = blockIdx.x;
     const int H = P.cfg.height, W = P.cfg.width, C = H * W, Cw = (C + 31) / 32;
@@ -562,7 +565,7 @@ __global__ void __launch_bounds__(WT, 6) k_world_step(const WParams P) {
 // =====================================================================================================
 // Environment.update_env -- environment.py:188-215 (static families)
 // =====================================================================================================
-__global__ void __launch_bounds__(WT, 6) k_world_update(const WParams P) {
+__global__ void __launch_bounds__(WT, RL_WORLD_MINB) k_world_update(const WParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int w = blockIdx.x;
     const int C = P.cfg.height * P.cfg.width, Cw = (C + 31) / 32, G = P.cfg.n_genes;
@@ -685,7 +688,7 @@ __global__ void __launch_bounds__(WT) k_world_reset(const WParams P) {
 // =====================================================================================================
 // saturated-world generator -- harness, mirrored by oracle rlo_topup / RefWorld.top_up
 // =====================================================================================================
-__global__ void __launch_bounds__(WT, 6) k_world_topup(const WParams P) {
+__global__ void __launch_bounds__(WT, RL_WORLD_MINB) k_world_topup(const WParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int w = blockIdx.x;
     const int C = P.cfg.height * P.cfg.width, Cw = (C + 31) / 32;
