@@ -889,7 +889,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
 #pragma unroll
                 for (int j = 0; j < 9; ++j) acc[j] = 0.f;
                 const float* hk = sH2 + (k >> 2) * TP_CH + (k & 3);
-#pragma unroll 1
+#pragma unroll 2
                 for (int g = 0; g < 8; ++g) {
 #pragma unroll
                     for (int rr = 0; rr < 8; ++rr) {

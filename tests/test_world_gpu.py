@@ -108,3 +108,64 @@ def test_world_sharding_is_world_id_pure():
     assert torch.equal(full.type[8:], part.type)
     assert torch.equal(full.n_agents[8:], part.n_agents)
     assert torch.equal(full.obs_state[8:], part.obs_state)
+
+
+def test_full_size_world_batch_properties_and_oracle_spot_checks():
+    """BASELINE.json configs[2] size (4096 worlds, 30x30, saturated to 100 agents): size-independent invariants on every
+    world + bit-exact oracle parity on three 16-world slices of the batch (first, middle, last) + run-to-run determinism."""
+    from oracle.world_oracle import OracleWorlds
+    NW, H, W, G, target, steps, seed = 4096, 30, 30, 2, 100, 4, 77
+    slices = [0, 2040, 4080]
+
+    def run():
+        vw = _vw(NW, H, W, G, max_agents=target, seed=seed)
+        ows = [OracleWorlds(16, H, W, G, max_agents=target, seed=seed, world_id0=s0) for s0 in slices]
+        vw.reset(); vw.top_up(target)
+        for ow in ows:
+            ow.reset(); ow.top_up(target)
+        g = torch.Generator(device="cuda"); g.manual_seed(5)
+        sums = []
+        for s in range(steps):
+            acts = torch.randint(0, 8, (NW, vw.S), device="cuda", dtype=torch.int8, generator=g)
+            vw.set_actions(acts)
+            ah = acts.cpu().numpy()
+            vw.step()
+            for ow, s0 in zip(ows, slices):
+                ow.set_actions(ah[s0:s0 + 16]); ow.step()
+            torch.cuda.synchronize()
+            for ow, s0 in zip(ows, slices):
+                for w in range(16):
+                    n = int(ow.n[w])
+                    _cmp_world(("full step", s, s0 + w), vw, s0 + w, ow.type[w], ow.rec[w, :n], reward=ow.reward[w, :n],
+                               obs=ow.obs[w, :n], which="prime")
+            vw.update(); vw.top_up(target)
+            for ow in ows:
+                ow.update(); ow.top_up(target)
+            torch.cuda.synchronize()
+            for ow, s0 in zip(ows, slices):
+                for w in range(16):
+                    n = int(ow.n[w])
+                    _cmp_world(("full update", s, s0 + w), vw, s0 + w, ow.type[w], ow.rec[w, :n], obs=ow.obs[w, :n], which="state")
+            # ---- invariants on ALL worlds
+            n = vw.n_agents.long()
+            is_agent = vw.type == 3
+            assert torch.equal(is_agent.sum(1), n)                                   # one list entry per AGENT cell
+            rec = vw.rec.view(NW, vw.S, 16)
+            cell = rec[:, :, 0].long() | (rec[:, :, 1].long() << 8)
+            slot = torch.arange(vw.S, device="cuda")[None, :]
+            live = slot < n[:, None]
+            nxt = torch.roll(cell, -1, 1)
+            assert bool(((cell < nxt) | ~(slot + 1 < n[:, None])).all())             # row-major (strictly increasing cells)
+            assert bool((torch.gather(vw.type.long(), 1, cell.clamp(max=H * W - 1))[live] == 3).all())
+            assert int(n.min()) == target                                            # saturated by the top-up
+            assert bool((vw.obs_state[:, :, 153:] == 0).all()) and bool(torch.isfinite(vw.reward).all())
+            o = vw.obs_state[live]
+            assert bool(((o[:, :49] == 0) | (o[:, :49] == 0.5) | (o[:, :49] == 1) | (o[:, :49] == -1)).all())   # food plane codes
+            assert bool(((o[:, 98:147] == 0) | (o[:, 98:147] == 1) | (o[:, 98:147] == -1)).all())              # gene plane codes
+            sums.append((int(vw.type.long().sum()), int(cell[live].sum()), float(vw.obs_state.double().sum()), float(vw.reward.double().sum())))
+        assert int(vw.status.max()) == 0
+        return sums
+
+    a = run()
+    b = run()
+    assert a == b                                                                    # bit-reproducible run to run
