@@ -334,6 +334,10 @@ int rl_world_stats_scratch_doubles(const rl_world_cfg* cfg);   /* size of scratc
 
 /* Test hook: one-tile tcgen05 kind::tf32 GEMM  D[M,N] = A * B^T  on interleaved no-swizzle operand images
  * (csrc/tc_tile.cuh).  a_mn / b_mn = 1: the operand image is stored k-rows x mn-columns (MN-major). */
+/* Timing probe (scripts/tc_mma_bench.py): average cycles to issue / to complete `ksteps` back-to-back tcgen05.mma
+ * kind::tf32 (K = 8 each) for operand layout `mode` (0 no-swizzle, 1 no-swizzle with padded chunk stride, 2 SWIZZLE_128B). */
+int rl_tc_mma_bench(int M, int N, int ksteps, int mode, int iters, long long* out_host);
+
 int rl_tc_gemm_test(const float* a_img, const float* b_img, float* d, int M, int N, int K, int a_mn, int b_mn, void* stream);
 
 

@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnP
         // issue a stage from thread 0 (after stage_sync), everybody then waits for its completion
 #define RL_STAGE(BODY) do { stage_sync(); if (threadIdx.x == 0) { fence_after(); BODY; mma_commit(done); } } while (0)
         int tr_n = 0;
-        auto stamp = [&](int it) { if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 8 && tr_n < 40) P.trace[it * 40 + tr_n++] = clock64(); };
+        auto stamp = [&](int it) { if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 8 && tr_n < 30) P.trace[it * 40 + tr_n++] = clock64(); };
         auto wait_done = [&]() { mbar_wait(done, stage_no & 1); ++stage_no; fence_after(); };
 
         // per-event metadata of event e -> buffer b, loaded by warps 6-7 (not the MMA-issuing thread) in two phases so that
@@ -556,6 +556,17 @@ static_assert(TC2_SMEM <= 227 * 1024, "shared memory budget");
 __device__ __forceinline__ int bimg_off(int b, int c, int K) { return (b >> 3) * ((K >> 2) * TP_CH) + (c >> 2) * TP_CH + (b & 7) * 4 + (c & 3); }
 __device__ __forceinline__ uint64_t desc_bimg(uint32_t saddr, int K) { return make_desc(saddr, TP_CH * 4, (uint32_t)(K >> 2) * TP_CH * 4); }
 
+// the MMAs of one weight chunk: MH feature halves x KS k-steps, fully unrolled (straight-line, descriptors by constant adds)
+template <int MH, int KS>
+__device__ __forceinline__ void chunk_mmas(uint32_t d_tmem, int n, uint64_t a_desc, uint32_t a_half_inc, uint64_t b_desc, uint32_t b_inc,
+                                           uint32_t idesc, uint32_t acc) {
+#pragma unroll
+    for (int h = 0; h < MH; ++h)
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+            mma_tf32(d_tmem + h * n, a_desc + h * a_half_inc + ks * 16u, b_desc + ks * b_inc, idesc, acc | (uint32_t)(ks != 0));
+}
+
 constexpr int NTHREADS2 = NEPI + 64;     // warps 0-7 epilogue, warp 8 weight-stream producer, warp 9 MMA issuer
 
 // chunk schedule of one event in the issuer's consumption order (the eval L1^T is issued right after the target L2^T)
@@ -648,28 +659,53 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
                 return smem_u32(sStage + slot * CHUNK_F);
             };
             auto chunk_release = [&]() { mma_commit(&empty[consumed % NS2]); ++consumed; };
-            // D[m_halves x 128 features][n] = Wchunk (A, from the ring) x Act (B, resident image described by lbo/sbo/kstep)
-            auto stream_gemm_w = [&](uint32_t d_tmem, int m_halves, uint32_t b_base, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep,
-                                     int nch, int kc, int n) {
-                const uint32_t idesc = make_idesc(128, n, 0, 0);
-                for (int c = 0; c < nch; ++c) {
-                    const uint32_t a_base = chunk_wait();
-                    for (int h = 0; h < m_halves; ++h)
-                        for (int ks = 0; ks < kc / 8; ++ks) {
-                            const uint32_t kstep = (uint32_t)(c * (kc / 8) + ks);
-                            mma_tf32(d_tmem + h * n, desc_kmajor(a_base + h * (128 * kc * 4) + ks * 256, kc),
-                                     make_desc(b_base + kstep * b_kstep, b_lbo, b_sbo), idesc, (c | ks) != 0);
-                        }
+            // n back-to-back MMAs into one accumulator; operand descriptors advance by a constant number of 16-byte units
+            // (the 14-bit start-address field cannot carry: shared memory is < 256 KB).  Kept as ONE small rolled loop on
+            // purpose: the issuer's code is revisited once per stage, unrolled copies of it miss the instruction cache.
+            auto mma_seq = [&](uint32_t d_tmem, uint64_t a_desc, uint32_t a_inc, uint64_t b_desc, uint32_t b_inc, uint32_t idesc, int n, uint32_t acc) {
+#pragma unroll 1
+                for (int i = 0; i < n; ++i) {
+                    mma_tf32(d_tmem, a_desc, b_desc, idesc, acc);
+                    a_desc += a_inc; b_desc += b_inc; acc = 1u;
+                }
+            };
+            // D[MH x 128 features][n] = Wchunk (A, from the ring) x Act (B, resident image described by lbo/sbo/kstep); the chunk
+            // loop stays rolled (one hot copy of the per-chunk body), the MMAs of a chunk are straight-line code
+            auto stream_l1 = [&](uint32_t d_tmem) {          // 5 chunks [128][32]: 4 k-steps each, B = X image
+                const uint32_t idesc = make_idesc(128, 64, 0, 0);
+                uint64_t b_desc = make_desc(aX, 128u, RL_K1 * 32u);
+#pragma unroll 1
+                for (int c = 0; c < 5; ++c) {
+                    chunk_mmas<1, 4>(d_tmem, 64, desc_kmajor(chunk_wait(), 32), 0u, b_desc, 16u, idesc, c != 0);
+                    b_desc += 64u;
                     chunk_release();
                 }
             };
-            auto l1 = [&]() { stream_gemm_w(T_L1, 1, aX, 128u, RL_K1 * 32u, 256u, 5, 32, 64); mma_commit(doneL1); };
-            auto l2 = [&]() { stream_gemm_w(T_WORK, 2, aH1, TP_CH * 4u, 32u * TP_CH * 4u, TP_KSTEP, 8, 16, 64); mma_commit(done); };
+            auto stream_l2 = [&](uint32_t d_tmem) {          // 8 chunks [256][16]: 2 halves x 2 k-steps, B = H1 bimg
+                const uint32_t idesc = make_idesc(128, 64, 0, 0);
+                uint64_t b_desc = make_desc(aH1, TP_CH * 4u, 32u * TP_CH * 4u);
+#pragma unroll 1
+                for (int c = 0; c < 8; ++c) {
+                    chunk_mmas<2, 2>(d_tmem, 64, desc_kmajor(chunk_wait(), 16), (128u * 16u * 4u) >> 4, b_desc, TP_KSTEP >> 4, idesc, c != 0);
+                    b_desc += 2u * (TP_KSTEP >> 4);
+                    chunk_release();
+                }
+            };
+            auto stream_dh1 = [&](uint32_t d_tmem) {         // 8 chunks [128][32]: 4 k-steps each, B = dH2 bimg
+                const uint32_t idesc = make_idesc(128, 64, 0, 0);
+                uint64_t b_desc = make_desc(aH2, TP_CH * 4u, 64u * TP_CH * 4u);
+#pragma unroll 1
+                for (int c = 0; c < 8; ++c) {
+                    chunk_mmas<1, 4>(d_tmem, 64, desc_kmajor(chunk_wait(), 32), 0u, b_desc, TP_KSTEP >> 4, idesc, c != 0);
+                    b_desc += 4u * (TP_KSTEP >> 4);
+                    chunk_release();
+                }
+            };
+            auto l1 = [&]() { stream_l1(T_L1); mma_commit(doneL1); };
+            auto l2 = [&]() { stream_l2(T_WORK); mma_commit(done); };
             auto head = [&]() {
-                const uint32_t idesc = make_idesc(64, 16, 0, 0);
                 const uint32_t b_base = chunk_wait();
-                for (int ks = 0; ks < 32; ++ks)
-                    mma_tf32(T_WORK, desc_bimg(aH2 + ks * TP_KSTEP, 256), desc_kmajor(b_base + ks * 256, 256), idesc, ks != 0);
+                mma_seq(T_WORK, desc_bimg(aH2, 256), TP_KSTEP >> 4, desc_kmajor(b_base, 256), 16u, make_idesc(64, 16, 0, 0), 32, 0u);
                 chunk_release();
                 mma_commit(done);
             };
@@ -682,35 +718,31 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
                 wait_go();                                        // dH2^T[n2][b] = Wh[n2][:] . dOut[b][:]
                 {
                     const uint32_t idesc = make_idesc(128, 64, 0, 0);
-                    const uint32_t a_base = chunk_wait();
-                    for (int h = 0; h < 2; ++h)
-                        for (int ks = 0; ks < 2; ++ks)
-                            mma_tf32(T_WORK + h * 64, desc_kmajor(a_base + h * (128 * 16 * 4) + ks * 256, 16), desc_kmajor(aD + ks * 256, 16), idesc, ks != 0);
+                    const uint64_t a_desc = desc_kmajor(chunk_wait(), 16), b_desc = desc_kmajor(aD, 16);
+                    mma_seq(T_WORK, a_desc, 16u, b_desc, 16u, idesc, 2, 0u);
+                    mma_seq(T_WORK + 64, a_desc + ((128u * 16u * 4u) >> 4), 16u, b_desc, 16u, idesc, 2, 0u);
                     chunk_release();
                     mma_commit(done);
                 }
                 wait_go();                                        // dW2 half 0 (TMEM-resident accumulator)
                 {
-                    const uint32_t idesc = make_idesc(128, 128, 0, 0);
-                    for (int ks = 0; ks < 8; ++ks)
-                        mma_tf32(T_DW2, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aH1 + ks * TP_KSTEP), idesc, (it | ks) != 0);
+                    mma_seq(T_DW2, desc_timg(aH1T), TP_KSTEP >> 4, desc_timg(aH1), TP_KSTEP >> 4, make_idesc(128, 128, 0, 0), 8, it != 0);
                     mma_commit(done);
                 }
                 wait_go();                                        // dW2 half 1, then dH1^T[k1][b] = W2^T[k1][:] . dH2[b][:]
                 {
-                    const uint32_t idesc = make_idesc(128, 128, 0, 0);
-                    for (int ks = 0; ks < 8; ++ks)
-                        mma_tf32(T_DW2 + 128, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aH1 + ks * TP_KSTEP), idesc, (it | ks) != 0);
-                    stream_gemm_w(T_WORK, 1, aH2, TP_CH * 4u, 64u * TP_CH * 4u, TP_KSTEP, 8, 32, 64);
+                    mma_seq(T_DW2 + 128, desc_timg(aH1T), TP_KSTEP >> 4, desc_timg(aH1), TP_KSTEP >> 4, make_idesc(128, 128, 0, 0), 8, it != 0);
+                    stream_dh1(T_WORK);
                     mma_commit(done);
                 }
+                if (P.trace && blockIdx.x == 0 && it < 8) P.trace[it * 40 + 30] = clock64();
                 wait_go();                                        // dW1^T = dH1^T X
+                if (P.trace && blockIdx.x == 0 && it < 8) P.trace[it * 40 + 31] = clock64();
                 {
-                    const uint32_t idesc = make_idesc(128, 160, 0, 0);
-                    for (int ks = 0; ks < 8; ++ks)
-                        mma_tf32(T_WORK, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aXT + ks * TP_KSTEP), idesc, ks != 0);
+                    mma_seq(T_WORK, desc_timg(aH1T), TP_KSTEP >> 4, desc_timg(aXT), TP_KSTEP >> 4, make_idesc(128, 160, 0, 0), 8, 0u);
                     mma_commit(done);
                 }
+                if (P.trace && blockIdx.x == 0 && it < 8) P.trace[it * 40 + 32] = clock64();
                 if (it + 1 < n_my) { wait_go(); l1(); }           // next event's target L1^T (runs under the dW1 epilogue)
             }
         }
@@ -728,7 +760,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
         auto wait_done = [&]() { mbar_wait(done, done_no & 1); ++done_no; fence_after(); };
         auto wait_l1 = [&]() { mbar_wait(doneL1, l1_no & 1); ++l1_no; fence_after(); };
         int tr_n = 0;
-        auto stamp = [&](int it) { if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 8 && tr_n < 40) P.trace[it * 40 + tr_n++] = clock64(); };
+        auto stamp = [&](int it) { if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 8 && tr_n < 30) P.trace[it * 40 + tr_n++] = clock64(); };
         int meta_i = 0; size_t meta_ring = 0;
         auto load_meta_a = [&](int b, int e) {           // phase A (warps 6-7): sampled ring positions
             if (threadIdx.x >= NEPI - R) {
@@ -965,18 +997,26 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
                 }
                 red_add(G + L::OFF_B1 + f1, sb1);                                  // db1[k1] (two warps share a feature)
             }
+            stamp(it);
             gather_store<true>(sXT, xr);                            // X^T image for dW1^T (dH2 region is dead: dH1 MMAs are done)
+            stamp(it);
             go_signal();                                            // -> dW1^T
+            stamp(it);
             if (more) gather_load(xr, P.rp.next_obs + ring_n1 * RL_K1, meta + ((it + 1) & 1) * 256);
+            stamp(it);
             wait_done(); stamp(it);
             if (more) {
                 gather_store<false>(sX, xr);                        // sX (dH1^T) is free: the dW1 MMAs have completed
+                stamp(it);
                 go_signal();                                        // -> next event's target L1^T (runs under the dW1 epilogue below)
+                stamp(it);
                 gather_load(xr, P.rp.obs + ring_n1 * RL_K1, meta + ((it + 1) & 1) * 256);   // its eval-net rows
+                stamp(it);
                 if (more2) {                                        // ring positions of the event after it (this event's buffer is dead)
                     load_meta_a(it & 1, e + 2 * gridDim.x);
                     ring_n2 = (size_t)(P.ev_rows[e + 2 * gridDim.x] / S) * cap;
                 }
+                stamp(it);
             }
             {
                 float* gr = G + L::OFF_W1T + f1 * RL_K1;
@@ -988,6 +1028,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
                     for (int j4 = 0; j4 < 8; ++j4) red_add4(gr + cb * 32 + j4 * 4, v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
                 }
             }
+            stamp(it);
             fence_before();
             epi_bar();
             ring_cur = ring_n1; ring_n1 = ring_n2;
@@ -1304,7 +1345,9 @@ int rl_brain_learn_tc(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t
         RL_CUDA_CHECK(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
         for (int it = 1; it < 4; ++it) {
             fprintf(stderr, "[tc trace] event %d (cycles since event start):", it);
-            for (int k = 1; k < 40 && h[it * 40 + k]; ++k) fprintf(stderr, " %lld", h[it * 40 + k] - h[it * 40]);
+            for (int k = 1; k < 30 && h[it * 40 + k]; ++k) fprintf(stderr, " %lld", h[it * 40 + k] - h[it * 40]);
+            fprintf(stderr, " | issuer:");
+            for (int k = 30; k < 40 && h[it * 40 + k]; ++k) fprintf(stderr, " %lld", h[it * 40 + k] - h[it * 40]);
             fprintf(stderr, "\n");
         }
     }

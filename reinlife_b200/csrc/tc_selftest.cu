@@ -67,3 +67,141 @@ extern "C" int rl_tc_gemm_test(const float* a_img, const float* b_img, float* d,
                                void* stream) {
     return rl_tc_gemm_test_ex(a_img, b_img, d, M, N, K, a_mn, b_mn, 0, 0, 0, stream);
 }
+
+// ---- timing probe: cycles per tcgen05.mma kind::tf32 for a given operand layout (data is irrelevant: zeros) ----
+namespace {
+using namespace tc;
+struct TcBenchParams { int M, N, ksteps, mode, iters; long long* out; };
+
+__global__ void __launch_bounds__(128) k_tc_mma_bench(const TcBenchParams P) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    float* sm = reinterpret_cast<float*>(smem_raw);
+    for (int i = threadIdx.x; i < 48 * 1024; i += blockDim.x) sm[i] = 0.f;
+    if (threadIdx.x == 0) { mlp::mbar_init(&bar, 1); mlp::fence_mbar_init(); }
+    if (threadIdx.x < 32) tmem_alloc(&tmem_base_s, 256);
+    mlp::fence_proxy_async();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (threadIdx.x < 32) {
+        // the whole warp runs the (warp-uniform) issue loop so that descriptors live in uniform registers; one elected
+        // lane issues the MMAs (P.mode >= 10: elected-lane variant; < 10: `if (threadIdx.x == 0)` variant for comparison)
+        const bool uniform_flow = P.mode >= 10 && P.mode < 20;
+        const int mode = P.mode % 10;
+        uint32_t elected = 0;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+        const bool me = uniform_flow ? (elected != 0) : (threadIdx.x == 0);
+        if (uniform_flow || threadIdx.x == 0) {
+            const uint32_t sa = smem_u32(sm), sb = smem_u32(sm + 24 * 1024);
+            const uint32_t idesc = make_idesc(P.M, P.N, 0, 0);
+            uint32_t ph = 0;
+            long long t_issue = 0, t_total = 0;
+            for (int it = 0; it < P.iters; ++it) {
+                const long long t0 = clock64();
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    if (ks < P.ksteps) {
+                        uint64_t ad, bd;
+                        if (mode == 0) {            // no swizzle, K = 64 floats per row: LBO 128 B, SBO K*32 B
+                            ad = desc_kmajor(sa + ks * 256, 64); bd = desc_kmajor(sb + ks * 256, 64);
+                        } else if (mode == 1) {     // no swizzle, padded chunk stride (LBO 144 B)
+                            ad = make_desc(sa + ks * 288, 144, 16 * 144); bd = make_desc(sb + ks * 288, 144, 16 * 144);
+                        } else {                    // SWIZZLE_128B K-major
+                            const uint32_t ao = (ks >> 2) * (P.M * 128) + (ks & 3) * 32, bo = (ks >> 2) * (P.N * 128) + (ks & 3) * 32;
+                            ad = make_desc(sa + ao, 16, 1024) | (2ull << 61); bd = make_desc(sb + bo, 16, 1024) | (2ull << 61);
+                        }
+                        if (me) {
+                            if (P.mode >= 20) {   // kind::f16 (fp16 operands, K = 16 per instruction = the same 32 bytes), fp32 accumulate
+                                const uint32_t idh = (1u << 4) | ((uint32_t)(P.N >> 3) << 17) | ((uint32_t)(P.M >> 4) << 24);
+                                const uint32_t acc = ks > 0;
+                                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                             "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                             ::"r"(tmem), "l"(ad), "l"(bd), "r"(idh), "r"(acc) : "memory");
+                            } else {
+                                mma_tf32(tmem, ad, bd, idesc, ks > 0);
+                            }
+                        }
+                    }
+                }
+                if (me) mma_commit(&bar);
+                const long long t1 = clock64();
+                mlp::mbar_wait(&bar, ph & 1); ++ph;
+                fence_after();
+                const long long t2 = clock64();
+                if (it > 0) { t_issue += t1 - t0; t_total += t2 - t0; }
+            }
+            if (me) { P.out[0] = t_issue / (P.iters - 1); P.out[1] = t_total / (P.iters - 1); }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem, 256);
+}
+}  // namespace
+
+namespace {
+// n_issuers warps (lane 0 of each) issue `ksteps` MMAs each, concurrently, into disjoint TMEM column ranges
+__global__ void __launch_bounds__(128) k_tc_mma_bench_par(const TcBenchParams P, int n_issuers) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ uint64_t bar[4];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ long long t_end[4];
+    float* sm = reinterpret_cast<float*>(smem_raw);
+    for (int i = threadIdx.x; i < 48 * 1024; i += blockDim.x) sm[i] = 0.f;
+    if (threadIdx.x == 0) { for (int i = 0; i < 4; ++i) mlp::mbar_init(&bar[i], 1); mlp::fence_mbar_init(); }
+    if (threadIdx.x < 32) tmem_alloc(&tmem_base_s, 512);
+    mlp::fence_proxy_async();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const int warp = threadIdx.x >> 5;
+    long long acc = 0;
+    for (int it = 0; it < P.iters; ++it) {
+        __syncthreads();
+        const long long t0 = clock64();
+        if ((threadIdx.x & 31) == 0 && warp < n_issuers) {
+            const uint32_t sa = smem_u32(sm), sb = smem_u32(sm + 24 * 1024);
+            const uint32_t idesc = make_idesc(P.M, P.N, 0, 0);
+            for (int ks = 0; ks < P.ksteps; ++ks)
+                mma_tf32(tmem + warp * 128, desc_kmajor(sa + ks * 256, 64), desc_kmajor(sb + ks * 256, 64), idesc, ks > 0);
+            mma_commit(&bar[warp]);
+            mlp::mbar_wait(&bar[warp], it & 1);
+            fence_after();
+            t_end[warp] = clock64();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && it > 0) {
+            long long m = 0;
+            for (int w = 0; w < n_issuers; ++w) m = t_end[w] > m ? t_end[w] : m;
+            acc += m - t0;
+        }
+    }
+    if (threadIdx.x == 0) { P.out[0] = acc / (P.iters - 1); P.out[1] = acc / (P.iters - 1); }
+    fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+}  // namespace
+
+// out_host[0] = average cycles to issue `ksteps` MMAs + commit, out_host[1] = average cycles until they completed
+extern "C" int rl_tc_mma_bench(int M, int N, int ksteps, int mode, int iters, long long* out_host) {
+    RL_ARG_CHECK(out_host && (M == 64 || M == 128) && N % 16 == 0 && N <= 256 && ksteps > 0 && ksteps <= 8 && iters > 1 && mode >= 0 && mode < 34);
+    long long* dev = nullptr;
+    RL_CUDA_CHECK(cudaMalloc(&dev, 2 * sizeof(long long)));
+    TcBenchParams P{M, N, ksteps, mode, iters, dev};
+    const size_t smem = 192 * 1024;
+    RL_CUDA_CHECK(cudaFuncSetAttribute(k_tc_mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (mode >= 30) {
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_tc_mma_bench_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_tc_mma_bench_par<<<1, 128, smem, 0>>>(P, mode - 30 + 1);
+    } else
+    k_tc_mma_bench<<<1, 128, smem, 0>>>(P);
+    RL_CUDA_CHECK(cudaDeviceSynchronize());
+    RL_CUDA_CHECK(cudaMemcpy(out_host, dev, 2 * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(dev);
+    return RL_OK;
+}
