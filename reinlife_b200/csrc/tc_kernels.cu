@@ -567,7 +567,7 @@ __device__ __forceinline__ void chunk_mmas(uint32_t d_tmem, int n, uint64_t a_de
             mma_tf32(d_tmem + h * n, a_desc + h * a_half_inc + ks * 16u, b_desc + ks * b_inc, idesc, acc | (uint32_t)(ks != 0));
 }
 
-constexpr int NTHREADS2 = NEPI + 64;     // warps 0-7 epilogue, warp 8 weight-stream producer, warp 9 MMA issuer
+constexpr int NTHREADS2 = NEPI + 96;     // warps 0-7 epilogue, warp 8 weight-stream producer, warps 9-10 MMA issuers
 
 // chunk schedule of one event in the issuer's consumption order (the eval L1^T is issued right after the target L2^T)
 __device__ __forceinline__ void sched_entry2(int i, int& net, int& chunk) {
@@ -614,8 +614,8 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
     const int n_my = total > (int)blockIdx.x ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NS2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(done, 1); mbar_init(doneL1, 1); mbar_init(go, NEPI);
+        for (int i = 0; i < NS2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); }     // a slot is released by both issuers
+        mbar_init(done, 2); mbar_init(doneL1, 1); mbar_init(go, NEPI);
         fence_mbar_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -647,9 +647,15 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
                 bulk_load(sStage + slot * CHUNK_F, (net ? P.wimg_e : P.wimg_t) + (size_t)ch * CHUNK_F, CHUNK_F * 4, &full[slot]);
             }
         }
-    } else if (warp == 9) {
-        // =================================== MMA issuer ===================================
+    } else if (warp == 9 || warp == 10) {
+        // =================================== MMA issuers (two warps) ===================================
+        // A tcgen05.mma costs its issuing thread ~100 cycles whatever its N (rl_tc_mma_bench), and two threads issue
+        // concurrently at ~1.5x the rate, so the long stages are split between two issuers: the 128-feature halves of
+        // L2^T / dH2^T, and the K range of the head and of dH1^T (second half into its own accumulator columns, summed by
+        // the epilogue).  Both issuers walk the same go sequence and the same chunk stream; a chunk slot is released by
+        // two arrivals (tcgen05.commit of each issuer that read it, plain arrive of the one that did not), `done` likewise.
         if (lane == 0) {
+            const int role = warp - 9;
             uint32_t consumed = 0, go_no = 0;
             auto wait_go = [&]() { mbar_wait(go, go_no & 1); ++go_no; fence_after(); };
             auto chunk_wait = [&]() -> uint32_t {
@@ -659,9 +665,9 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
                 return smem_u32(sStage + slot * CHUNK_F);
             };
             auto chunk_release = [&]() { mma_commit(&empty[consumed % NS2]); ++consumed; };
-            // n back-to-back MMAs into one accumulator; operand descriptors advance by a constant number of 16-byte units
-            // (the 14-bit start-address field cannot carry: shared memory is < 256 KB).  Kept as ONE small rolled loop on
-            // purpose: the issuer's code is revisited once per stage, unrolled copies of it miss the instruction cache.
+            // a chunk this issuer does not read: wait until it has landed (so that this arrival cannot be counted for the slot's
+            // PREVIOUS round, which the other issuer may still be reading), then release this issuer's share of the slot
+            auto chunk_skip = [&](int n) { for (int i = 0; i < n; ++i) { (void)chunk_wait(); mbar_arrive(&empty[consumed % NS2]); ++consumed; } };
             auto mma_seq = [&](uint32_t d_tmem, uint64_t a_desc, uint32_t a_inc, uint64_t b_desc, uint32_t b_inc, uint32_t idesc, int n, uint32_t acc) {
 #pragma unroll 1
                 for (int i = 0; i < n; ++i) {
@@ -669,43 +675,37 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
                     a_desc += a_inc; b_desc += b_inc; acc = 1u;
                 }
             };
-            // D[MH x 128 features][n] = Wchunk (A, from the ring) x Act (B, resident image described by lbo/sbo/kstep); the chunk
-            // loop stays rolled (one hot copy of the per-chunk body), the MMAs of a chunk are straight-line code
-            auto stream_l1 = [&](uint32_t d_tmem) {          // 5 chunks [128][32]: 4 k-steps each, B = X image
+            // L1^T (issuer 0): 5 chunks [128][32], 4 k-steps each, B = X image
+            auto l1 = [&]() {
+                if (role == 1) { chunk_skip(5); return; }
                 const uint32_t idesc = make_idesc(128, 64, 0, 0);
                 uint64_t b_desc = make_desc(aX, 128u, RL_K1 * 32u);
 #pragma unroll 1
                 for (int c = 0; c < 5; ++c) {
-                    chunk_mmas<1, 4>(d_tmem, 64, desc_kmajor(chunk_wait(), 32), 0u, b_desc, 16u, idesc, c != 0);
+                    chunk_mmas<1, 4>(T_L1, 64, desc_kmajor(chunk_wait(), 32), 0u, b_desc, 16u, idesc, c != 0);
                     b_desc += 64u;
                     chunk_release();
                 }
+                mma_commit(doneL1);
             };
-            auto stream_l2 = [&](uint32_t d_tmem) {          // 8 chunks [256][16]: 2 halves x 2 k-steps, B = H1 bimg
+            // L2^T: 8 chunks [256][16]; issuer r takes feature half r (accumulator columns 64r..), B = H1 bimg
+            auto l2 = [&]() {
                 const uint32_t idesc = make_idesc(128, 64, 0, 0);
                 uint64_t b_desc = make_desc(aH1, TP_CH * 4u, 32u * TP_CH * 4u);
+                const uint32_t a_off = role ? (128u * 16u * 4u) : 0u;
 #pragma unroll 1
                 for (int c = 0; c < 8; ++c) {
-                    chunk_mmas<2, 2>(d_tmem, 64, desc_kmajor(chunk_wait(), 16), (128u * 16u * 4u) >> 4, b_desc, TP_KSTEP >> 4, idesc, c != 0);
+                    chunk_mmas<1, 2>(T_WORK + role * 64, 64, desc_kmajor(chunk_wait() + a_off, 16), 0u, b_desc, TP_KSTEP >> 4, idesc, c != 0);
                     b_desc += 2u * (TP_KSTEP >> 4);
                     chunk_release();
                 }
+                mma_commit(done);
             };
-            auto stream_dh1 = [&](uint32_t d_tmem) {         // 8 chunks [128][32]: 4 k-steps each, B = dH2 bimg
-                const uint32_t idesc = make_idesc(128, 64, 0, 0);
-                uint64_t b_desc = make_desc(aH2, TP_CH * 4u, 64u * TP_CH * 4u);
-#pragma unroll 1
-                for (int c = 0; c < 8; ++c) {
-                    chunk_mmas<1, 4>(d_tmem, 64, desc_kmajor(chunk_wait(), 32), 0u, b_desc, TP_KSTEP >> 4, idesc, c != 0);
-                    b_desc += 4u * (TP_KSTEP >> 4);
-                    chunk_release();
-                }
-            };
-            auto l1 = [&]() { stream_l1(T_L1); mma_commit(doneL1); };
-            auto l2 = [&]() { stream_l2(T_WORK); mma_commit(done); };
+            // head (M = 64): issuer r takes k-steps 16r..16r+15 into accumulator columns 16r.. (the epilogue adds the two)
             auto head = [&]() {
                 const uint32_t b_base = chunk_wait();
-                mma_seq(T_WORK, desc_bimg(aH2, 256), TP_KSTEP >> 4, desc_kmajor(b_base, 256), 16u, make_idesc(64, 16, 0, 0), 32, 0u);
+                mma_seq(T_WORK + role * 16, desc_bimg(aH2 + role * 16 * TP_KSTEP, 256), TP_KSTEP >> 4, desc_kmajor(b_base + role * 16 * 256, 256), 16u,
+                        make_idesc(64, 16, 0, 0), 16, 0u);
                 chunk_release();
                 mma_commit(done);
             };
@@ -715,34 +715,41 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
                 wait_go(); head();                                // target head
                 wait_go(); l2();                                  // eval L2^T
                 wait_go(); head();                                // eval head
-                wait_go();                                        // dH2^T[n2][b] = Wh[n2][:] . dOut[b][:]
+                wait_go();                                        // dH2^T[n2][b] = Wh[n2][:] . dOut[b][:]: issuer r takes feature half r
                 {
-                    const uint32_t idesc = make_idesc(128, 64, 0, 0);
-                    const uint64_t a_desc = desc_kmajor(chunk_wait(), 16), b_desc = desc_kmajor(aD, 16);
-                    mma_seq(T_WORK, a_desc, 16u, b_desc, 16u, idesc, 2, 0u);
-                    mma_seq(T_WORK + 64, a_desc + ((128u * 16u * 4u) >> 4), 16u, b_desc, 16u, idesc, 2, 0u);
+                    const uint64_t a_desc = desc_kmajor(chunk_wait() + (role ? 128u * 16u * 4u : 0u), 16);
+                    mma_seq(T_WORK + role * 64, a_desc, 16u, desc_kmajor(aD, 16), 16u, make_idesc(128, 64, 0, 0), 2, 0u);
                     chunk_release();
                     mma_commit(done);
                 }
-                wait_go();                                        // dW2 half 0 (TMEM-resident accumulator)
-                {
+                wait_go();                                        // dW2 half 0 (TMEM-resident accumulator): issuer 0
+                if (role == 0) {
                     mma_seq(T_DW2, desc_timg(aH1T), TP_KSTEP >> 4, desc_timg(aH1), TP_KSTEP >> 4, make_idesc(128, 128, 0, 0), 8, it != 0);
                     mma_commit(done);
+                } else {
+                    mbar_arrive(done);
                 }
-                wait_go();                                        // dW2 half 1, then dH1^T[k1][b] = W2^T[k1][:] . dH2[b][:]
-                {
-                    mma_seq(T_DW2 + 128, desc_timg(aH1T), TP_KSTEP >> 4, desc_timg(aH1), TP_KSTEP >> 4, make_idesc(128, 128, 0, 0), 8, it != 0);
-                    stream_dh1(T_WORK);
+                wait_go();                                        // dW2 half 1 (issuer 0); dH1^T[k1][b] = W2^T[k1][:] . dH2[b][:] split over K:
+                {                                                 // of every [128][32] chunk issuer r takes k-steps 2r, 2r+1 into columns 64r..
+                    if (role == 0)
+                        mma_seq(T_DW2 + 128, desc_timg(aH1T), TP_KSTEP >> 4, desc_timg(aH1), TP_KSTEP >> 4, make_idesc(128, 128, 0, 0), 8, it != 0);
+                    const uint32_t idesc = make_idesc(128, 64, 0, 0);
+                    uint64_t b_desc = make_desc(aH2 + role * 2 * TP_KSTEP, TP_CH * 4u, 64u * TP_CH * 4u);
+#pragma unroll 1
+                    for (int c = 0; c < 8; ++c) {
+                        chunk_mmas<1, 2>(T_WORK + role * 64, 64, desc_kmajor(chunk_wait() + role * 2 * 256, 32), 0u, b_desc, TP_KSTEP >> 4, idesc, c != 0);
+                        b_desc += 4u * (TP_KSTEP >> 4);
+                        chunk_release();
+                    }
                     mma_commit(done);
                 }
-                if (P.trace && blockIdx.x == 0 && it < 8) P.trace[it * 40 + 30] = clock64();
-                wait_go();                                        // dW1^T = dH1^T X
-                if (P.trace && blockIdx.x == 0 && it < 8) P.trace[it * 40 + 31] = clock64();
-                {
+                wait_go();                                        // dW1^T = dH1^T X: issuer 0
+                if (role == 0) {
                     mma_seq(T_WORK, desc_timg(aH1T), TP_KSTEP >> 4, desc_timg(aXT), TP_KSTEP >> 4, make_idesc(128, 160, 0, 0), 8, 0u);
                     mma_commit(done);
+                } else {
+                    mbar_arrive(done);
                 }
-                if (P.trace && blockIdx.x == 0 && it < 8) P.trace[it * 40 + 32] = clock64();
                 if (it + 1 < n_my) { wait_go(); l1(); }           // next event's target L1^T (runs under the dW1 epilogue)
             }
         }
@@ -787,19 +794,22 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
             }
         };
         float4 xr[10];
-        size_t ring_cur = 0, ring_n1 = 0, ring_n2 = 0;
+        // EVENT-list rows of the current / next / next-next event: loaded early, divided (ring = row / S * cap) only where used,
+        // so that no thread stalls on the load
+        int row_cur = 0, row_n1 = 0, row_n2 = 0;
         if (n_my > 0) {
             // prologue: metadata + target-net input of event 0, its target L1^T released, eval-net rows of event 0 and the
             // ring positions of event 1 on their way
             load_meta_a(0, blockIdx.x);
             load_meta_b(0);
             epi_bar();
-            ring_cur = (size_t)(P.ev_rows[blockIdx.x] / S) * cap;
-            gather_load(xr, P.rp.next_obs + ring_cur * RL_K1, meta);
+            row_cur = P.ev_rows[blockIdx.x];
+            const size_t ring0 = (size_t)(row_cur / S) * cap;
+            gather_load(xr, P.rp.next_obs + ring0 * RL_K1, meta);
             gather_store<false>(sX, xr);
             go_signal();                                                                     // -> target L1^T
-            gather_load(xr, P.rp.obs + ring_cur * RL_K1, meta);
-            if (n_my > 1) { load_meta_a(1, blockIdx.x + gridDim.x); ring_n1 = (size_t)(P.ev_rows[blockIdx.x + gridDim.x] / S) * cap; }
+            gather_load(xr, P.rp.obs + ring0 * RL_K1, meta);
+            if (n_my > 1) { load_meta_a(1, blockIdx.x + gridDim.x); row_n1 = P.ev_rows[blockIdx.x + gridDim.x]; }
         }
         // L1 epilogue: lane = feature k1, this warp's 32 batch columns; H1 = relu(D + b1)
         auto l1_epilogue = [&](const float* bias, bool eval) {
@@ -832,12 +842,13 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
         // head epilogue: [A(8) | V] + bh -> sOuth; returns the mean of the whole [64, 8] advantage tensor
         auto head_epilogue = [&](const float* bias) -> float {
             if (half == 0) {
-                float v[16];
-                tmem_ld16(T_WORK + t_lane, v);
+                float v[16], v2[16];
+                tmem_ld16(T_WORK + t_lane, v);                 // k-steps 0-15 (issuer 0)
+                tmem_ld16(T_WORK + t_lane + 16, v2);           // k-steps 16-31 (issuer 1)
                 tmem_wait_ld();
                 if (rvalid) {
 #pragma unroll
-                    for (int j = 0; j < 9; ++j) sOuth[row64 * 16 + j] = v[j] + bias[384 + j];
+                    for (int j = 0; j < 9; ++j) sOuth[row64 * 16 + j] = (v[j] + v2[j]) + bias[384 + j];
                 }
             }
             fence_before();
@@ -852,12 +863,14 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
             const bool more = it + 1 < n_my, more2 = it + 2 < n_my;
             const int* idx = meta + (it & 1) * 256; const int* act = idx + 64;
             const float* rew = reinterpret_cast<const float*>(idx + 128); const float* dn = rew + 64;
-            const size_t ring = ring_cur;
+            const size_t ring = (size_t)(row_cur / S) * cap;
+            const size_t ring_n1 = (size_t)(row_n1 / S) * cap;
             // ---------------- target net ----------------
             wait_l1(); stamp(it);                                   // target L1^T (issued one event ahead)
             gather_store<false>(sX, xr);                            // eval-net input; sX is free: the target L1 MMAs have completed
             l1_epilogue(bias_t, false);
-            go_signal();                                            // -> target L2^T, eval L1^T
+            go_signal();                                            // -> target L2^T, eval L1^T (two `go` arrivals may never follow each
+                                                                    //    other without a `done` wait in between: parity waits would alias)
             if (more) {                                             // hidden behind them
                 load_meta_b((it + 1) & 1);
                 prefetch_rows(ring_n1, meta + ((it + 1) & 1) * 256);
@@ -981,9 +994,12 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
             gather_load(xr, P.rp.obs + ring * RL_K1, idx);          // X rows again (for the X^T image), hidden behind the dH1 MMAs
             wait_done(); stamp(it);
             {   // dH1 epilogue: lane = feature k1, this warp's 32 batch columns; mask by H1 > 0, dH1^T in place of H1^T, db1
-                float v[32];
-                tmem_ld32(T_WORK + t_lane + half * 32, v);
+                float v[32], v2[32];
+                tmem_ld32(T_WORK + t_lane + half * 32, v);          // k-steps 0,1 of every chunk (issuer 0)
+                tmem_ld32(T_WORK + t_lane + 64 + half * 32, v2);    // k-steps 2,3 (issuer 1)
                 tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += v2[j];
                 float sb1 = 0.f;
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
@@ -1014,7 +1030,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
                 stamp(it);
                 if (more2) {                                        // ring positions of the event after it (this event's buffer is dead)
                     load_meta_a(it & 1, e + 2 * gridDim.x);
-                    ring_n2 = (size_t)(P.ev_rows[e + 2 * gridDim.x] / S) * cap;
+                    row_n2 = P.ev_rows[e + 2 * gridDim.x];
                 }
                 stamp(it);
             }
@@ -1031,7 +1047,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
             stamp(it);
             fence_before();
             epi_bar();
-            ring_cur = ring_n1; ring_n1 = ring_n2;
+            row_cur = row_n1; row_n1 = row_n2;
             stamp(it);
         }
         if (n_my > 0) {     // flush the TMEM-resident dW2 accumulator once (the dW1 `done` covered every earlier MMA)
