@@ -1034,14 +1034,27 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
                 }
                 stamp(it);
             }
-            {
-                float* gr = G + L::OFF_W1T + f1 * RL_K1;
-                for (int cb = half; cb < 5; cb += 2) {
-                    float v[32];
-                    tmem_ld32(T_WORK + t_lane + cb * 32, v);
-                    tmem_wait_ld();
+            {   // dW1^T flush: the accumulator has one k1 row per lane, so a direct flush touches 32 different 128-byte lines per
+                // instruction.  Transpose through the (now dead) X^T / dH2 region instead: rows are staged with an odd leading
+                // dimension (conflict-free column writes), then read back row-wise so that a warp adds 128 contiguous bytes.
+                float* stg = sH2;
+                float* gw = G + L::OFF_W1T;
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int c_lo = pass ? 96 : 0, ncol = pass ? 64 : 96, ldw = ncol + 1;
+                    for (int cb = (pass ? 3 : 0) + half; cb < (pass ? 5 : 3); cb += 2) {
+                        float v[32];
+                        tmem_ld32(T_WORK + t_lane + cb * 32, v);
+                        tmem_wait_ld();
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) red_add4(gr + cb * 32 + j4 * 4, v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                        for (int j = 0; j < 32; ++j) stg[f1 * ldw + (cb * 32 - c_lo) + j] = v[j];
+                    }
+                    epi_bar();
+                    for (int i = threadIdx.x; i < 128 * ncol; i += NEPI) {
+                        const int r = pass ? (i >> 6) : (int)__umulhi((uint32_t)i, 44739243u), c = i - r * ncol;      // i / 96 by multiply-high
+                        red_add(gw + r * RL_K1 + c_lo + c, stg[r * ldw + c]);
+                    }
+                    if (pass == 0) epi_bar();
                 }
             }
             stamp(it);
