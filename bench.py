@@ -36,8 +36,8 @@ def parse():
     ap.add_argument("--worlds-per-gpu", type=int, default=4096)
     ap.add_argument("--capacity", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
-                    help="train() events: tcgen05 kind::tf32 tensor cores (fp32 accumulate) or fp32 CUDA-core FMA")
+    ap.add_argument("--precision", default="fp16", choices=["tf32", "fp16", "fp32"],
+                    help="train() events: tcgen05 with fp16 operands (default) or tf32 operands (both 11 significant bits, fp32 accumulate), or fp32 CUDA-core FMA")
     ap.add_argument("--cpu-worlds-per-core", type=int, default=2)
     ap.add_argument("--cpu-steps", type=int, default=8)
     return ap.parse_args()
@@ -223,9 +223,10 @@ def run_b200(args):
     env.kernel_events = None
     learn_kernel_ms = sum(k_ms) / max(1, len(k_ms))
     ev_per_launch = ev_avg / len(brains)
+    learn_kernel_name = {"fp16": "k_learn_dueling_h", "tf32": "k_learn_dueling_tc2", "fp32": "k_learn_dueling"}[args.precision]
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01_final.json"))).get("k_learn_dueling_tc2_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01_final.json"))).get(learn_kernel_name + "_bytes_per_launch")
     except Exception:
         pass
     peaks = {}
@@ -244,24 +245,26 @@ def run_b200(args):
         "k_world_step": {"bound": "hbm", "ms": phases["step"], "achieved": b_step / phases["step"] / 1e6, "peak": hbm_peak, "unit": "GB/s"},
         "k_world_update": {"bound": "hbm", "ms": phases["update"], "achieved": b_obs / phases["update"] / 1e6, "peak": hbm_peak, "unit": "GB/s"},
         "k_world_topup": {"bound": "hbm", "ms": phases["top_up"], "achieved": b_obs / phases["top_up"] / 1e6, "peak": hbm_peak, "unit": "GB/s"},
-        "k_learn_dueling_tc2": {"bound": "tensor", "ms": learn_kernel_ms, "launches_per_step": len(brains),
+        learn_kernel_name: {"bound": "tensor", "ms": learn_kernel_ms, "launches_per_step": len(brains),
                                 "achieved": ev_per_launch * flop_event / max(learn_kernel_ms, 1e-9) / 1e9, "peak": bf16_peak, "unit": "TFLOP/s",
                                 "note": ("one launch = all train() events of one brain (25.6 MFLOP per 64-row event), timed alone with CUDA events; "
-                                         "tcgen05 kind::tf32, TMEM accumulators; peak shown is the measured sustained bf16 tensor peak (tf32 dense is half of it)"
-                                         if args.precision == "tf32" else "fp32 FMA on CUDA cores (reference precision); peak shown is the bf16 tensor peak")},
+                                         + {"fp16": "tcgen05 kind::f16 (fp16 operands), TMEM accumulators; peak = measured sustained bf16/fp16 tensor peak",
+                                            "tf32": "tcgen05 kind::tf32, TMEM accumulators; peak shown is the measured sustained bf16 tensor peak (tf32 dense is half of it)",
+                                            "fp32": "fp32 FMA on CUDA cores (reference precision); peak shown is the bf16 tensor peak"}[args.precision])},
         "act(k_act_dueling_tc x2 + rows)": {"bound": "tensor", "ms": phases["act"], "achieved": NW * n_avg * 107008 / phases["act"] / 1e9,
                                             "peak": bf16_peak, "unit": "TFLOP/s",
-                                            "note": "tcgen05 kind::tf32 forward" if args.precision == "tf32" else "fp32 FMA on CUDA cores"},
+                                            "note": "tcgen05 kind::tf32 forward" if args.precision in ("tf32", "fp16") else "fp32 FMA on CUDA cores"},
     }
     for v in roof_k.values():
         v["frac"] = v["achieved"] / v["peak"]
     dominant = max(roof_k, key=lambda k: roof_k[k]["ms"] * roof_k[k].get("launches_per_step", 1))
-    roofline = dict(roof_k[dominant], kernel=dominant, traffic=traffic if dominant == "k_learn_dueling_tc2" else None, peak_source=peak_src,
+    roofline = dict(roof_k[dominant], kernel=dominant, traffic=traffic if dominant == learn_kernel_name else None, peak_source=peak_src,
                     step_share=roof_k[dominant]["ms"] * roof_k[dominant].get("launches_per_step", 1) / sum(phases.values()))
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": ("tf32 (tensor-core forward/backward products, fp32 accumulate; world state exact integers, Adam fp32)" if args.precision == "tf32" else "f32"), "data": "synthetic",
+            "dtype": {"fp16": "fp16 operands in the train() events, tf32 in get_action (both 11 significant bits), fp32 accumulate; world state exact integers, Adam fp32",
+                      "tf32": "tf32 (tensor-core forward/backward products, fp32 accumulate; world state exact integers, Adam fp32)", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": workload_name(args), "grid": [H, W], "worlds_total": n_worlds, "agents_per_world": n_avg,
                        "train_events_per_step_per_gpu": ev_avg, "parallelism": f"worlds sharded x{world_size}, brains replicated, "
                        "1 NCCL all-reduce of summed gradients per step" if world_size > 1 else "single GPU",

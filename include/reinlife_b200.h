@@ -357,6 +357,14 @@ int rl_brain_learn_tc(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t
                       const int32_t* sample_idx, const rl_learn_bufs* learn, const float* wimg_eval, const float* wimg_target,
                       void* stream);
 
+/* fp16-operand variant of the tensor-core event kernel (tcgen05.mma kind::f16, fp32 accumulation; fp16 carries the same 11
+ * significant bits as tf32, K = 16 per instruction, half the operand bytes).  `wimg_*_h` are fp16 weight images of
+ * rl_tc_wimg_floats() HALVES each, built by rl_brain_build_wimg_h.  Same contract and outputs as rl_brain_learn_tc. */
+int rl_brain_build_wimg_h(int32_t kind, const float* params, void* wimg_h, void* stream);
+int rl_brain_learn_h(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                     const int32_t* sample_idx, const rl_learn_bufs* learn, const void* wimg_eval_h, const void* wimg_target_h,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,7 +11,7 @@ def trainer(brains: List, n_episodes: int = 10_000, width: int = 30, height: int
             print_results: bool = True, max_agents: int = 100, render: bool = False, static_families: bool = True,
             training: bool = True, save: bool = True, limit_reproduction: bool = False,
             incentivize_killing: bool = True, *, n_worlds: int = 1, seed: int = 0, device=None,
-            saturate_to: int = 0, precision: str = "tf32") -> Environment:
+            saturate_to: int = 0, precision: str = "fp16") -> Environment:
     env = Environment(width=width, height=height, max_agents=max_agents, brains=brains, grid_size=24,
                       static_families=static_families, update_interval=update_interval, print_results=print_results,
                       interactive_results=visualize_results, google_colab=google_colab, training=training,

@@ -53,7 +53,7 @@ class Environment:
                  interactive_results: bool = False, google_colab: bool = False, training: bool = True,
                  save: bool = False, pastel_colors: bool = False, limit_reproduction: bool = False,
                  incentivize_killing: bool = True, *, n_worlds: int = 1, seed: int = 0, device=None, world_id0=None,
-                 precision: str = "tf32"):
+                 precision: str = "fp16"):
         self.width, self.height = width, height
         self.actions, self.entities = Actions, EntityTypes
         self.best_agents = []
@@ -103,9 +103,14 @@ class Environment:
                 if b._dev.target is not None:
                     torch.distributed.broadcast(b._dev.target, 0)
         # "tf32": train() events on the tensor cores (tcgen05 kind::tf32, fp32 accumulate); "fp32": CUDA-core FMA path
-        if precision not in ("tf32", "fp32"):
-            raise ValueError("precision must be 'tf32' or 'fp32'")
-        self.precision = precision
+        if precision not in ("tf32", "fp16", "fp32"):
+            raise ValueError("precision must be 'tf32', 'fp16' or 'fp32'")
+        # "fp16": train() events with fp16 operands (tcgen05 kind::f16, fp32 accumulate); get_action stays on the tf32 forward
+        self._learn_fp16 = precision == "fp16"
+        self.precision = "tf32" if precision == "fp16" else precision
+        for b in brains:
+            if getattr(b, "_dev", None) is not None:
+                b._dev.use_fp16 = self._learn_fp16
         self._act_tc = os.environ.get("RL_ACT_FP32") is None    # tf32 runs: get_action of dueling brains on the tensor cores too
         self._grad_all = None
         from ..Helpers.tracker import Tracker
@@ -234,9 +239,14 @@ class Environment:
                     self.gpu_launches += 2
                 if ev0 is not None:
                     ev0.record()
-                _lib.check(lib.rl_brain_learn_tc(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
-                                                 C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs),
-                                                 C.c_void_p(b._dev.wimg_e.data_ptr()), C.c_void_p(b._dev.wimg_t.data_ptr()), st))
+                if self._learn_fp16:
+                    _lib.check(lib.rl_brain_learn_h(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                                    C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs),
+                                                    C.c_void_p(b._dev.wimg_eh.data_ptr()), C.c_void_p(b._dev.wimg_th.data_ptr()), st))
+                else:
+                    _lib.check(lib.rl_brain_learn_tc(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                                     C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs),
+                                                     C.c_void_p(b._dev.wimg_e.data_ptr()), C.c_void_p(b._dev.wimg_t.data_ptr()), st))
             else:
                 if ev0 is not None:
                     ev0.record()

@@ -29,7 +29,9 @@ class DeviceBrain:
         self.grad_scratch = None
         self.new_prio = self.loss = self.sample_idx = None
         self.learn_bufs = None
-        self.wimg_e = self.wimg_t = None          # tensor-core weight images (tf32 path)
+        self.wimg_e = self.wimg_t = None          # tensor-core weight images (tf32)
+        self.wimg_eh = self.wimg_th = None        # fp16 weight images (precision="fp16" event kernel)
+        self.use_fp16 = False
         self.wimg_stale = True
 
     # -- tensor-core weight images -------------------------------------------------------------------
@@ -39,7 +41,16 @@ class DeviceBrain:
             n = self.lib.rl_tc_wimg_floats()
             self.wimg_e = torch.zeros(n, device=self.device)
             self.wimg_t = torch.zeros(n, device=self.device)
+            self.wimg_eh = torch.zeros(n, dtype=torch.float16, device=self.device)
+            self.wimg_th = torch.zeros(n, dtype=torch.float16, device=self.device)
         with torch.cuda.device(self.device):
+            if self.use_fp16:
+                if which in ("both", "eval"):
+                    _lib.check(self.lib.rl_brain_build_wimg_h(C.c_int32(self.kind), C.c_void_p(self.params.data_ptr()),
+                                                              C.c_void_p(self.wimg_eh.data_ptr()), stream_ptr))
+                if which in ("both", "target") and self.target is not None:
+                    _lib.check(self.lib.rl_brain_build_wimg_h(C.c_int32(self.kind), C.c_void_p(self.target.data_ptr()),
+                                                              C.c_void_p(self.wimg_th.data_ptr()), stream_ptr))
             if which in ("both", "eval"):
                 _lib.check(self.lib.rl_brain_build_wimg(C.c_int32(self.kind), C.c_void_p(self.params.data_ptr()),
                                                         C.c_void_p(self.wimg_e.data_ptr()), stream_ptr))

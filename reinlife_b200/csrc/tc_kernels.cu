@@ -11,6 +11,7 @@
 // tf32 MN-major operands read back as zeros on this part with the no-swizzle layouts (tests/test_tc_gpu.py pins
 // the K-major conventions), so transposed operand images are written explicitly by the epilogues.
 #include <stdlib.h>
+#include <cuda_fp16.h>
 #include "tc_tile.cuh"
 #include "models.cuh"
 
@@ -1081,6 +1082,572 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
 }
 
 // =====================================================================================================
+// k_learn_dueling_h -- the event kernel of k_learn_dueling_tc2 on fp16 operands (tcgen05.mma kind::f16, fp32
+// accumulation in TMEM).  fp16 carries the same 11 significant bits as tf32, but an instruction covers K = 16 instead of
+// 8 and every operand byte count halves: 114 MMA instructions per event instead of 228 (the tensor pipe is
+// instruction-issue bound at N = 64, see rl_tc_mma_bench), 296 KB of weights per event instead of 592 KB, and the
+// weight chunks of a whole stage fit in the ring.  Geometry in BYTES is the one of the tf32 kernel (16-byte chunks = 8
+// halves, 128-byte core matrices, padded chunk stride 144 B), so roles, stages, barriers and TMEM map are unchanged.
+// The backward operands (dOut, dH2, dH1) are scaled by H_SCALE = 256 (exact power of two, removed when the fp32
+// gradients leave TMEM) so that small gradients stay out of the fp16 subnormal range; values are clamped to +-60000.
+// =====================================================================================================
+constexpr int NSH = 8;                                  // weight-chunk stages of 8 KB
+constexpr int HCHUNK = 4096;                            // halves per weight chunk (8 KB): same element shapes as the tf32 chunks
+constexpr int HC = 72;                                  // halves between consecutive 16-byte chunks in padded images (144 B)
+constexpr float H_SCALE = 256.0f;
+// byte offsets of the regions
+constexpr int HB_X = 0;                                 // X' / X plain [64][160] (20480 B) -> H1^T / dH1^T timg [128][64] (18432 B)
+constexpr int HB_H1 = HB_X + 20480;                     // H1 bimg [64][128] (18432 B) -> dH2^T half timg [128][64] (18432 B)
+constexpr int HB_H2 = HB_H1 + 18432;                    // H2 bimg [64][256] (36864 B) -> dH2 bimg -> X^T timg [160][64] (23040 B) -> fp32 dW1 staging (<= 49664 B)
+constexpr int HB_STAGE = HB_H2 + 49920;
+constexpr int HB_DOUT = HB_STAGE + NSH * HCHUNK * 2;    // dOut image [64][16] halves (2048 B)
+constexpr int HB_OUTH = HB_DOUT + 2048;                 // head outputs [64][16] floats (4096 B); dOut plain [64][12] aliases it
+constexpr int HB_SMALL = HB_OUTH + 4096;                // nq, gb, red, biases (floats)
+constexpr int HB_INT = HB_SMALL + 4 * SM_SMALL_N;
+constexpr int HB_BARS = HB_INT + 4 * 512;
+constexpr size_t TCH_SMEM = HB_BARS + 8 * (2 * NSH + 3) + 16;
+static_assert(TCH_SMEM <= 227 * 1024 && HB_BARS % 8 == 0, "shared memory budget");
+
+__device__ __forceinline__ int himg_off(int r, int c, int K) { return (r >> 3) * (K * 8) + (c >> 3) * 64 + (r & 7) * 8 + (c & 7); }
+__device__ __forceinline__ int hbimg_off(int b, int c, int K) { return (b >> 3) * ((K >> 3) * HC) + (c >> 3) * HC + (b & 7) * 8 + (c & 7); }
+__device__ __forceinline__ int htimg_off(int f, int b) { return (f >> 3) * (8 * HC) + (b >> 3) * HC + (f & 7) * 8 + (b & 7); }
+__device__ __forceinline__ uint64_t desc_hplain(uint32_t saddr, int K) { return make_desc(saddr, 128u, (uint32_t)K * 16u); }
+__device__ __forceinline__ uint64_t desc_hbimg(uint32_t saddr, int K) { return make_desc(saddr, 144u, (uint32_t)(K >> 3) * 144u); }
+__device__ __forceinline__ uint64_t desc_htimg(uint32_t saddr) { return make_desc(saddr, 144u, 8u * 144u); }
+__host__ __device__ constexpr uint32_t make_idesc_h(int M, int N) {      // kind::f16: A, B fp16 (format 0), D fp32
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ __half h_sat(float x) { return __float2half_rn(fminf(fmaxf(x, -60000.f), 60000.f)); }
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) { return (uint32_t)__half_as_ushort(__float2half_rn(a)) | ((uint32_t)__half_as_ushort(__float2half_rn(b)) << 16); }
+__device__ __forceinline__ uint32_t pack_h2_sat(float a, float b) { return (uint32_t)__half_as_ushort(h_sat(a)) | ((uint32_t)__half_as_ushort(h_sat(b)) << 16); }
+__device__ __forceinline__ float h_lo(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xFFFFu))); }
+__device__ __forceinline__ float h_hi(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }
+
+// store the gathered 64 x 160 fp32 rows as an fp16 image (plain [64][160] or feature-major X^T [160][64])
+template <bool TRANSPOSED>
+__device__ __forceinline__ void gather_store_h(__half* img, const float4 (&x)[10]) {
+#pragma unroll
+    for (int u = 0; u < 10; ++u) {
+        const int v = threadIdx.x + u * NEPI;
+        const int rr = v & 7, cc = (v >> 3) & 3, blk = v >> 5;
+        const int rg = blk / 10, cg = blk - rg * 10;
+        const int r = rg * 8 + rr, c = (cg * 4 + cc) * 4;
+        if (!TRANSPOSED) {
+            *reinterpret_cast<uint2*>(img + himg_off(r, c, RL_K1)) = make_uint2(pack_h2(x[u].x, x[u].y), pack_h2(x[u].z, x[u].w));
+        } else {
+            img[htimg_off(c + 0, r)] = __float2half_rn(x[u].x); img[htimg_off(c + 1, r)] = __float2half_rn(x[u].y);
+            img[htimg_off(c + 2, r)] = __float2half_rn(x[u].z); img[htimg_off(c + 3, r)] = __float2half_rn(x[u].w);
+        }
+    }
+}
+
+// the MMAs of one fp16 weight chunk: KS k-steps of 16, straight-line
+template <int KS>
+__device__ __forceinline__ void chunk_mmas_h(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t b_inc, uint32_t idesc, uint32_t acc) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) mma_f16(d_tmem, a_desc + ks * 16u, b_desc + ks * b_inc, idesc, acc | (uint32_t)(ks != 0));
+}
+
+struct TcLearnParamsH {
+    TcLearnParams p;
+    const __half* wimg_e;
+    const __half* wimg_t;
+};
+
+__global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnParamsH PH) {
+    using L = Layout<RL_MODEL_DUELING>;
+    const TcLearnParams& P = PH.p;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __half* sX = reinterpret_cast<__half*>(smem_raw + HB_X);
+    __half* sH1 = reinterpret_cast<__half*>(smem_raw + HB_H1);
+    __half* sH2 = reinterpret_cast<__half*>(smem_raw + HB_H2);
+    __half* sH1T = sX;         // H1^T / dH1^T (feature-major) live in the X region once the eval L1 MMAs are done
+    __half* sDT = sH1;         // dH2^T half buffer lives in the H1 region once the eval L2 MMAs are done
+    __half* sXT = sH2;         // X^T lives in the dH2 region once the dH1 MMAs are done
+    __half* sStage = reinterpret_cast<__half*>(smem_raw + HB_STAGE);
+    __half* sDout = reinterpret_cast<__half*>(smem_raw + HB_DOUT);
+    float* sOuth = reinterpret_cast<float*>(smem_raw + HB_OUTH); float* sDpl = sOuth;
+    float* smallf = reinterpret_cast<float*>(smem_raw + HB_SMALL);
+    float* nq = smallf + 128; float* gb = nq + 64; float* red = gb + 64;
+    float* bias_t = red + 32; float* bias_e = bias_t + 400;
+    int* meta = reinterpret_cast<int*>(smem_raw + HB_INT);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + HB_BARS);
+    uint64_t* full = bars; uint64_t* empty = bars + NSH; uint64_t* done = bars + 2 * NSH; uint64_t* doneL1 = done + 1; uint64_t* go = done + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 3);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* Pe = P.lb.params; const float* Pt = P.lb.target;
+    float* G = P.lb.grad_scratch + (size_t)blockIdx.x * L::N_TRAIN;
+    const int total = *P.ev_total;
+    const int n_my = total > (int)blockIdx.x ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSH; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); }
+        mbar_init(done, 2); mbar_init(doneL1, 1); mbar_init(go, NEPI);
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x < NEPI) {
+        for (int i = threadIdx.x; i < 400; i += NEPI) {
+            const int o = i < 128 ? L::OFF_B1 + i : i < 384 ? L::OFF_B2 + (i - 128) : L::OFF_BH + (i - 384);
+            const bool ok = i < 384 + 9;
+            bias_t[i] = ok ? Pt[o] : 0.f; bias_e[i] = ok ? Pe[o] : 0.f;
+        }
+        for (int i = threadIdx.x; i < L::N_TRAIN / 4; i += NEPI) reinterpret_cast<float4*>(G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t T_WORK = tmem, T_DW2 = tmem + 256, T_L1 = tmem + 192;
+    const int S = P.cfg.slot_cap, cap = P.rp.capacity;
+    const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH1T = smem_u32(sH1T), aH2 = smem_u32(sH2), aD = smem_u32(sDout), aXT = smem_u32(sXT);
+
+    if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t n_chunks = (uint32_t)n_my * SCHED_N;
+            for (uint32_t produced = 0; produced < n_chunks; ++produced) {
+                const uint32_t slot = produced % NSH;
+                if (produced >= NSH) mbar_wait(&empty[slot], ((produced / NSH) - 1) & 1);
+                int net, ch; sched_entry2(produced % SCHED_N, net, ch);
+                bulk_load(sStage + slot * HCHUNK, (net ? PH.wimg_e : PH.wimg_t) + (size_t)ch * HCHUNK, HCHUNK * 2, &full[slot]);
+            }
+        }
+    } else if (warp == 9 || warp == 10) {
+        if (lane == 0) {
+            const int role = warp - 9;
+            uint32_t consumed = 0, go_no = 0;
+            auto wait_go = [&]() { mbar_wait(go, go_no & 1); ++go_no; fence_after(); };
+            auto chunk_wait = [&]() -> uint32_t {
+                const uint32_t slot = consumed % NSH;
+                mbar_wait(&full[slot], (consumed / NSH) & 1);
+                fence_after();
+                return smem_u32(sStage + slot * HCHUNK);
+            };
+            auto chunk_release = [&]() { mma_commit(&empty[consumed % NSH]); ++consumed; };
+            auto chunk_skip = [&](int n) { for (int i = 0; i < n; ++i) { (void)chunk_wait(); mbar_arrive(&empty[consumed % NSH]); ++consumed; } };
+            auto mma_seq = [&](uint32_t d_tmem, uint64_t a_desc, uint32_t a_inc, uint64_t b_desc, uint32_t b_inc, uint32_t idesc, int n, uint32_t acc) {
+#pragma unroll 1
+                for (int i = 0; i < n; ++i) {
+                    mma_f16(d_tmem, a_desc, b_desc, idesc, acc);
+                    a_desc += a_inc; b_desc += b_inc; acc = 1u;
+                }
+            };
+            // L1^T (issuer 0): 5 chunks [128][32]: 2 k-steps of 16 each, B = X plain image
+            auto l1 = [&]() {
+                if (role == 1) { chunk_skip(5); return; }
+                const uint32_t idesc = make_idesc_h(128, 64);
+                uint64_t b_desc = desc_hplain(aX, RL_K1);
+#pragma unroll 1
+                for (int c = 0; c < 5; ++c) {
+                    chunk_mmas_h<2>(T_L1, desc_hplain(chunk_wait(), 32), b_desc, 16u, idesc, c != 0);
+                    b_desc += 32u;
+                    chunk_release();
+                }
+                mma_commit(doneL1);
+            };
+            // L2^T: 8 chunks [256][16]: one k-step; issuer r takes feature half r, B = H1 bimg
+            auto l2 = [&]() {
+                const uint32_t idesc = make_idesc_h(128, 64);
+                uint64_t b_desc = desc_hbimg(aH1, 128);
+                const uint32_t a_off = role ? 4096u : 0u;               // rows 128..255 of a [256][16] fp16 chunk
+#pragma unroll 1
+                for (int c = 0; c < 8; ++c) {
+                    chunk_mmas_h<1>(T_WORK + role * 64, desc_hplain(chunk_wait() + a_off, 16), b_desc, 18u, idesc, c != 0);
+                    b_desc += 18u;
+                    chunk_release();
+                }
+                mma_commit(done);
+            };
+            // head (M = 64): 16 k-steps, issuer r takes 8r..8r+7 into accumulator columns 16r..
+            auto head = [&]() {
+                const uint32_t b_base = chunk_wait();
+                mma_seq(T_WORK + role * 16, desc_hbimg(aH2 + role * 8 * 288, 256), 18u, desc_hplain(b_base + role * 8 * 256, 256), 16u,
+                        make_idesc_h(64, 16), 8, 0u);
+                chunk_release();
+                mma_commit(done);
+            };
+            for (int it = 0; it < n_my; ++it) {
+                if (it == 0) { wait_go(); l1(); }
+                wait_go(); l2(); l1();
+                wait_go(); head();
+                wait_go(); l2();
+                wait_go(); head();
+                wait_go();                                        // dH2^T: one k-step, issuer r takes feature half r
+                {
+                    mma_f16(T_WORK + role * 64, desc_hplain(chunk_wait() + (role ? 4096u : 0u), 16), desc_hplain(aD, 16), make_idesc_h(128, 64), 0u);
+                    chunk_release();
+                    mma_commit(done);
+                }
+                wait_go();                                        // dW2 half 0: K = 64 batch rows = 4 k-steps (issuer 0)
+                if (role == 0) {
+                    mma_seq(T_DW2, desc_htimg(aH1T), 18u, desc_htimg(aH1), 18u, make_idesc_h(128, 128), 4, it != 0);
+                    mma_commit(done);
+                } else {
+                    mbar_arrive(done);
+                }
+                wait_go();                                        // dW2 half 1 (issuer 0); dH1^T split over K: of every [128][32] chunk issuer r takes k-step r
+                {
+                    if (role == 0) mma_seq(T_DW2 + 128, desc_htimg(aH1T), 18u, desc_htimg(aH1), 18u, make_idesc_h(128, 128), 4, it != 0);
+                    const uint32_t idesc = make_idesc_h(128, 64);
+                    uint64_t b_desc = desc_hbimg(aH2 + role * 288, 256);
+#pragma unroll 1
+                    for (int c = 0; c < 8; ++c) {
+                        chunk_mmas_h<1>(T_WORK + role * 64, desc_hplain(chunk_wait() + role * 256, 32), b_desc, 18u, idesc, c != 0);
+                        b_desc += 36u;
+                        chunk_release();
+                    }
+                    mma_commit(done);
+                }
+                wait_go();                                        // dW1^T = dH1^T X: 4 k-steps (issuer 0)
+                if (role == 0) {
+                    mma_seq(T_WORK, desc_htimg(aH1T), 18u, desc_htimg(aXT), 18u, make_idesc_h(128, 160), 4, 0u);
+                    mma_commit(done);
+                } else {
+                    mbar_arrive(done);
+                }
+                if (it + 1 < n_my) { wait_go(); l1(); }
+            }
+        }
+    } else {
+        // =================================== epilogue warps ===================================
+        uint32_t done_no = 0, l1_no = 0;
+        const int q = warp & 3, half = warp >> 2;
+        const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+        const int f1 = q * 32 + lane;
+        const int f2 = half * 128 + f1;
+        const int row64 = q * 16 + lane;
+        const bool rvalid = lane < 16;
+        auto go_signal = [&]() { fence_proxy_async(); fence_before(); mbar_arrive(go); };
+        auto wait_done = [&]() { mbar_wait(done, done_no & 1); ++done_no; fence_after(); };
+        auto wait_l1 = [&]() { mbar_wait(doneL1, l1_no & 1); ++l1_no; fence_after(); };
+        int meta_i = 0; size_t meta_ring = 0;
+        auto load_meta_a = [&](int b, int e) {
+            if (threadIdx.x >= NEPI - R) {
+                const int r = threadIdx.x - (NEPI - R);
+                meta_ring = (size_t)(P.ev_rows[e] / S) * cap;
+                meta_i = max(P.sample_idx[(size_t)e * R + r], 0);
+                meta[b * 256 + r] = meta_i;
+            }
+        };
+        auto load_meta_b = [&](int b) {
+            if (threadIdx.x >= NEPI - R) {
+                const int r = threadIdx.x - (NEPI - R);
+                int* m = meta + b * 256;
+                m[64 + r] = P.rp.action[meta_ring + meta_i];
+                reinterpret_cast<float*>(m)[128 + r] = P.rp.reward[meta_ring + meta_i];
+                reinterpret_cast<float*>(m)[192 + r] = (float)P.rp.done[meta_ring + meta_i];
+            }
+        };
+        auto prefetch_rows = [&](size_t rg_, const int* ids) {
+            for (int v = threadIdx.x; v < 2 * R * 5; v += NEPI) {
+                const int which = v / (R * 5), rem = v - which * (R * 5), r = rem / 5, ln = rem - r * 5;
+                const float* p = (which ? P.rp.obs : P.rp.next_obs) + (rg_ + ids[r]) * RL_K1 + ln * 32;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+            }
+        };
+        float4 xr[10];
+        int row_cur = 0, row_n1 = 0, row_n2 = 0;
+        if (n_my > 0) {
+            load_meta_a(0, blockIdx.x);
+            load_meta_b(0);
+            epi_bar();
+            row_cur = P.ev_rows[blockIdx.x];
+            const size_t ring0 = (size_t)(row_cur / S) * cap;
+            gather_load(xr, P.rp.next_obs + ring0 * RL_K1, meta);
+            gather_store_h<false>(sX, xr);
+            go_signal();
+            gather_load(xr, P.rp.obs + ring0 * RL_K1, meta);
+            if (n_my > 1) { load_meta_a(1, blockIdx.x + gridDim.x); row_n1 = P.ev_rows[blockIdx.x + gridDim.x]; }
+        }
+        // L1 epilogue: lane = feature k1, this warp's 32 batch columns; H1 = relu(D + b1)
+        auto l1_epilogue = [&](const float* bias, bool eval) {
+            float v[32];
+            tmem_ld32(T_L1 + t_lane + half * 32, v);
+            tmem_wait_ld();
+            const float b1 = bias[f1];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + b1, 0.f);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sH1[hbimg_off(half * 32 + j, f1, 128)] = __float2half_rn(v[j]);      // batch-major: B of L2^T
+            if (eval) {
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8)                                                                   // feature-major: A of dW2, relu mask of dH1
+                    *reinterpret_cast<uint4*>(sH1T + htimg_off(f1, half * 32 + j8 * 8)) =
+                        make_uint4(pack_h2(v[j8 * 8], v[j8 * 8 + 1]), pack_h2(v[j8 * 8 + 2], v[j8 * 8 + 3]), pack_h2(v[j8 * 8 + 4], v[j8 * 8 + 5]), pack_h2(v[j8 * 8 + 6], v[j8 * 8 + 7]));
+            }
+        };
+        auto l2_epilogue = [&](const float* bias) {
+            const float b2 = bias[128 + f2];
+#pragma unroll
+            for (int cb = 0; cb < 2; ++cb) {
+                float v[32];
+                tmem_ld32(T_WORK + t_lane + half * 64 + cb * 32, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sH2[hbimg_off(cb * 32 + j, f2, 256)] = __float2half_rn(fmaxf(v[j] + b2, 0.f));
+            }
+        };
+        auto head_epilogue = [&](const float* bias) -> float {
+            if (half == 0) {
+                float v[16], v2[16];
+                tmem_ld16(T_WORK + t_lane, v);
+                tmem_ld16(T_WORK + t_lane + 16, v2);
+                tmem_wait_ld();
+                if (rvalid) {
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) sOuth[row64 * 16 + j] = (v[j] + v2[j]) + bias[384 + j];
+                }
+            }
+            fence_before();
+            epi_bar();
+            float s = 0.f;
+            for (int o = threadIdx.x; o < R * 8; o += NEPI) s += sOuth[(o >> 3) * 16 + (o & 7)];
+            return epi_sum(s, red) * (1.0f / (8 * R));
+        };
+        for (int it = 0; it < n_my; ++it) {
+            const int e = blockIdx.x + it * gridDim.x;
+            const bool more = it + 1 < n_my, more2 = it + 2 < n_my;
+            const int* idx = meta + (it & 1) * 256; const int* act = idx + 64;
+            const float* rew = reinterpret_cast<const float*>(idx + 128); const float* dn = rew + 64;
+            const size_t ring = (size_t)(row_cur / S) * cap;
+            const size_t ring_n1 = (size_t)(row_n1 / S) * cap;
+            // ---------------- target net ----------------
+            wait_l1();
+            gather_store_h<false>(sX, xr);
+            l1_epilogue(bias_t, false);
+            go_signal();                                            // -> target L2^T, eval L1^T
+            if (more) {
+                load_meta_b((it + 1) & 1);
+                prefetch_rows(ring_n1, meta + ((it + 1) & 1) * 256);
+            }
+            wait_done();
+            l2_epilogue(bias_t);
+            go_signal();                                            // -> target head
+            wait_done();
+            {
+                const float mean = head_epilogue(bias_t);
+                if (threadIdx.x < R) {
+                    const float* o = sOuth + threadIdx.x * 16;
+                    float mx = o[0];
+#pragma unroll
+                    for (int j = 1; j < 8; ++j) mx = fmaxf(mx, o[j]);
+                    nq[threadIdx.x] = mx + o[8] - mean;
+                }
+                epi_bar();
+            }
+            // ---------------- eval net ----------------
+            wait_l1();
+            l1_epilogue(bias_e, true);
+            go_signal();                                            // -> eval L2^T
+            wait_done();
+            l2_epilogue(bias_e);
+            go_signal();                                            // -> eval head
+            wait_done();
+            const float mean_e = head_epilogue(bias_e);
+            // ---- TD target, loss, priorities, dOut (fp16 image scaled by H_SCALE, fp32 plain copy unscaled) ----
+            {
+                float g = 0.f, sq = 0.f;
+                if (threadIdx.x < R) {
+                    const int b = threadIdx.x;
+                    const float qa = sOuth[b * 16 + act[b]] + sOuth[b * 16 + 8] - mean_e;
+                    const float y = rew[b] + P.lb.gamma * (1.0f - dn[b]) * nq[b];
+                    const float diff = qa - y;
+                    g = 2.0f * diff * (1.0f / R);
+                    sq = diff * diff;
+                    gb[b] = g;
+                    P.lb.new_prio[(size_t)e * R + b] = fabsf(nq[b] - qa);
+                }
+                const float gsum = epi_sum(g, red);
+                const float loss = epi_sum(sq, red) * (1.0f / R);
+                if (threadIdx.x == 0) P.lb.loss[e] = loss;
+                const float shift = gsum * (1.0f / (8 * R));
+                for (int o = threadIdx.x; o < R * 16; o += NEPI) {
+                    const int b = o >> 4, j = o & 15;
+                    const float d = j < 8 ? ((j == act[b] ? gb[b] : 0.f) - shift) : (j == 8 ? gb[b] : 0.f);
+                    sDout[himg_off(b, j, 16)] = h_sat(d * H_SCALE);
+                    if (j < 12) sDpl[b * 12 + j] = d;
+                }
+            }
+            go_signal();                                            // -> dH2^T (runs under the head-gradient SIMT below)
+            epi_bar();
+            // ---- head gradients (SIMT): dWh[k][j] += sum_b H2[b][k] dOut[b][j]; dbh ----
+            {
+                const int k = threadIdx.x;
+                float acc[9];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) acc[j] = 0.f;
+                const __half* hk = sH2 + (k >> 3) * HC + (k & 7);
+#pragma unroll 2
+                for (int g = 0; g < 8; ++g) {
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int b = g * 8 + rr;
+                        const float h = __half2float(hk[g * (32 * HC) + rr * 8]);
+                        const float4 d0 = *reinterpret_cast<const float4*>(sDpl + b * 12), d1 = *reinterpret_cast<const float4*>(sDpl + b * 12 + 4);
+                        const float d8 = sDpl[b * 12 + 8];
+                        acc[0] = fmaf(h, d0.x, acc[0]); acc[1] = fmaf(h, d0.y, acc[1]); acc[2] = fmaf(h, d0.z, acc[2]); acc[3] = fmaf(h, d0.w, acc[3]);
+                        acc[4] = fmaf(h, d1.x, acc[4]); acc[5] = fmaf(h, d1.y, acc[5]); acc[6] = fmaf(h, d1.z, acc[6]); acc[7] = fmaf(h, d1.w, acc[7]);
+                        acc[8] = fmaf(h, d8, acc[8]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 9; ++j) red_add(G + L::OFF_WH + k * 9 + j, acc[j]);
+                if (threadIdx.x < 9) {
+                    float s = 0.f;
+                    for (int b = 0; b < R; ++b) s += sDpl[b * 12 + threadIdx.x];
+                    red_add(G + L::OFF_BH + threadIdx.x, s);
+                }
+            }
+            // ---- dH2 epilogue (values carry the factor H_SCALE): mask by H2 > 0; batch-major in place, feature-major via the half buffer ----
+            wait_done();
+            uint32_t dvp[32];                                       // this thread's 64 masked values as fp16 pairs
+            {
+                float sb2 = 0.f;
+#pragma unroll
+                for (int cb = 0; cb < 2; ++cb) {
+                    float v[32];
+                    tmem_ld32(T_WORK + t_lane + half * 64 + cb * 32, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        __half* ph = sH2 + hbimg_off(cb * 32 + j, f2, 256);
+                        const float m = __half2float(*ph) > 0.f ? v[j] : 0.f;
+                        const __half mh = h_sat(m);
+                        *ph = mh;
+                        v[j] = __half2float(mh);
+                        sb2 += m;
+                    }
+#pragma unroll
+                    for (int j2 = 0; j2 < 16; ++j2) dvp[cb * 16 + j2] = pack_h2(v[j2 * 2], v[j2 * 2 + 1]);
+                }
+                red_add(G + L::OFF_B2 + f2, sb2 * (1.0f / H_SCALE));
+                if (half == 0) {
+#pragma unroll
+                    for (int j8 = 0; j8 < 8; ++j8)
+                        *reinterpret_cast<uint4*>(sDT + htimg_off(f1, j8 * 8)) = make_uint4(dvp[j8 * 4], dvp[j8 * 4 + 1], dvp[j8 * 4 + 2], dvp[j8 * 4 + 3]);
+                }
+            }
+            go_signal();                                            // -> dW2 half 0
+            wait_done();
+            if (half == 1) {
+#pragma unroll
+                for (int j8 = 0; j8 < 8; ++j8)
+                    *reinterpret_cast<uint4*>(sDT + htimg_off(f1, j8 * 8)) = make_uint4(dvp[j8 * 4], dvp[j8 * 4 + 1], dvp[j8 * 4 + 2], dvp[j8 * 4 + 3]);
+            }
+            go_signal();                                            // -> dW2 half 1, dH1^T
+            gather_load(xr, P.rp.obs + ring * RL_K1, idx);
+            wait_done();
+            {   // dH1 epilogue: lane = feature k1, this warp's 32 batch columns; mask by H1 > 0, dH1^T in place of H1^T, db1
+                float v[32], v2[32];
+                tmem_ld32(T_WORK + t_lane + half * 32, v);
+                tmem_ld32(T_WORK + t_lane + 64 + half * 32, v2);
+                tmem_wait_ld();
+                float sb1 = 0.f;
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    uint4* ph = reinterpret_cast<uint4*>(sH1T + htimg_off(f1, half * 32 + j8 * 8));
+                    const uint4 h = *ph;
+                    const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+                    uint32_t ow[4];
+#pragma unroll
+                    for (int p2 = 0; p2 < 4; ++p2) {
+                        const int j = j8 * 8 + p2 * 2;
+                        const float a = h_lo(hw[p2]) > 0.f ? v[j] + v2[j] : 0.f, b = h_hi(hw[p2]) > 0.f ? v[j + 1] + v2[j + 1] : 0.f;
+                        sb1 += a + b;
+                        ow[p2] = pack_h2_sat(a, b);
+                    }
+                    *ph = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                }
+                red_add(G + L::OFF_B1 + f1, sb1 * (1.0f / H_SCALE));
+            }
+            gather_store_h<true>(sXT, xr);
+            go_signal();                                            // -> dW1^T
+            if (more) gather_load(xr, P.rp.next_obs + ring_n1 * RL_K1, meta + ((it + 1) & 1) * 256);
+            wait_done();
+            if (more) {
+                gather_store_h<false>(sX, xr);
+                go_signal();                                        // -> next event's target L1^T
+                gather_load(xr, P.rp.obs + ring_n1 * RL_K1, meta + ((it + 1) & 1) * 256);
+                if (more2) {
+                    load_meta_a(it & 1, e + 2 * gridDim.x);
+                    row_n2 = P.ev_rows[e + 2 * gridDim.x];
+                }
+            }
+            {   // dW1^T flush through a shared-memory transpose (see k_learn_dueling_tc2), unscaled on the way
+                float* stg = reinterpret_cast<float*>(sH2);
+                float* gw = G + L::OFF_W1T;
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int c_lo = pass ? 96 : 0, ncol = pass ? 64 : 96, ldw = ncol + 1;
+                    for (int cb = (pass ? 3 : 0) + half; cb < (pass ? 5 : 3); cb += 2) {
+                        float v[32];
+                        tmem_ld32(T_WORK + t_lane + cb * 32, v);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) stg[f1 * ldw + (cb * 32 - c_lo) + j] = v[j] * (1.0f / H_SCALE);
+                    }
+                    epi_bar();
+                    for (int i = threadIdx.x; i < 128 * ncol; i += NEPI) {
+                        const int r = pass ? (i >> 6) : (int)__umulhi((uint32_t)i, 44739243u), c = i - r * ncol;
+                        red_add(gw + r * RL_K1 + c_lo + c, stg[r * ldw + c]);
+                    }
+                    if (pass == 0) epi_bar();
+                }
+            }
+            fence_before();
+            epi_bar();
+            row_cur = row_n1; row_n1 = row_n2;
+        }
+        if (n_my > 0) {     // flush the TMEM-resident dW2 accumulator once, unscaled
+            for (int cb = 0; cb < 4; ++cb) {
+                const int c0 = half * 128 + cb * 32;
+                float v[32];
+                tmem_ld32(T_DW2 + t_lane + c0, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)
+                    *reinterpret_cast<float4*>(G + L::OFF_W2T + f1 * 256 + c0 + j4 * 4) =
+                        make_float4(v[j4 * 4] * (1.0f / H_SCALE), v[j4 * 4 + 1] * (1.0f / H_SCALE), v[j4 * 4 + 2] * (1.0f / H_SCALE), v[j4 * 4 + 3] * (1.0f / H_SCALE));
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+// fp16 weight images: the chunk shapes and order of the tf32 images, 4096 halves (8 KB) per chunk
+__global__ void k_build_wimg_dueling_h(const float* __restrict__ p, __half* __restrict__ wimg) {
+    using L = Layout<RL_MODEL_DUELING>;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 128 * 160) {
+        const int n = i / 160, k = i - n * 160;
+        wimg[(WI_W1 + k / 32) * HCHUNK + himg_off(n, k % 32, 32)] = __float2half_rn(p[L::OFF_W1T + k * 128 + n]);
+    }
+    if (i < 128 * 256) {
+        const int k1 = i / 256, n2 = i - k1 * 256;
+        const __half v = __float2half_rn(p[L::OFF_W2T + i]);
+        wimg[(WI_W2K + k1 / 16) * HCHUNK + himg_off(n2, k1 % 16, 16)] = v;
+        wimg[(WI_W2T + n2 / 32) * HCHUNK + himg_off(k1, n2 % 32, 32)] = v;
+    }
+    if (i < 256 * 16) {
+        const int n2 = i / 16, j = i - n2 * 16;
+        const __half v = j < 9 ? __float2half_rn(p[L::OFF_WH + n2 * 9 + j]) : __float2half_rn(0.f);
+        wimg[WI_WH * HCHUNK + himg_off(j, n2, 256)] = v;
+        wimg[WI_WHT * HCHUNK + himg_off(n2, j, 16)] = v;
+    }
+}
+
+// =====================================================================================================
 // brain.get_action for the dueling brains on the tensor cores: the forward half of the event kernel over 64-row
 // tiles of the brain's ALL row list (Helpers/trainer.py:88-89; PERD3QN.py:81-89,198-210; D3QN.py:82-93,161-173).
 // Same pipeline: warp 8 streams the 14 weight chunks of a tile (W1[5], W2K[8], WH), epilogue thread 0 issues the
@@ -1304,6 +1871,39 @@ int rl_brain_build_wimg(int32_t kind, const float* params, float* wimg, void* st
     k_build_wimg_dueling<<<(128 * 256 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(params, wimg);
     RL_CUDA_CHECK(cudaGetLastError());
     return RL_OK;
+}
+
+int rl_brain_build_wimg_h(int32_t kind, const float* params, void* wimg_h, void* stream) {
+    RL_ARG_CHECK(params && wimg_h);
+    if (kind != RL_MODEL_DUELING) return rl_set_err(RL_ERR_UNSUPPORTED, "tensor-core weight images: dueling networks only");
+    k_build_wimg_dueling_h<<<(128 * 256 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(params, reinterpret_cast<__half*>(wimg_h));
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_brain_learn_h(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                     const int32_t* sample_idx, const rl_learn_bufs* learn, const void* wimg_eval_h, const void* wimg_target_h,
+                     void* stream) {
+    RL_ARG_CHECK(cfg && rows && replay && sample_idx && learn && wimg_eval_h && wimg_target_h);
+    RL_ARG_CHECK(gene >= 0 && gene < cfg->n_genes && cfg->obs_ld == RL_K1 && learn->batch == R);
+    RL_ARG_CHECK(learn->params && learn->target && learn->grad_scratch && learn->grad && learn->new_prio && learn->loss);
+    if (learn->kind != RL_MODEL_DUELING) return rl_set_err(RL_ERR_UNSUPPORTED, "rl_brain_learn_h: dueling networks only");
+    TcLearnParamsH PH;
+    TcLearnParams& P = PH.p;
+    P.cfg = *cfg;
+    P.ev_rows = rows->rows + (size_t)(gene * RL_N_ROW_KINDS + RL_ROWS_EVENT) * rows->row_cap;
+    P.ev_total = rows->total + gene * RL_N_ROW_KINDS + RL_ROWS_EVENT;
+    P.rp = *replay; P.sample_idx = sample_idx; P.lb = *learn; P.wimg_e = nullptr; P.wimg_t = nullptr; P.trace = nullptr;
+    PH.wimg_e = reinterpret_cast<const __half*>(wimg_eval_h); PH.wimg_t = reinterpret_cast<const __half*>(wimg_target_h);
+    static bool attr = false;
+    if (!attr) {
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dueling_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCH_SMEM));
+        attr = true;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    k_learn_dueling_h<<<rl_learn_grid(), NTHREADS2, TCH_SMEM, st>>>(PH);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return rl_learn_reduce(learn, P.ev_total, 1, (void*)st);
 }
 
 int rl_brain_act_tc(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_rows_bufs* rows, int32_t gene,

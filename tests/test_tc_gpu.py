@@ -43,7 +43,7 @@ def test_tcgen05_tile_gemm(M, N, K, a_mn, b_mn):
 
 
 def test_tensor_core_learn_matches_fp32_learn():
-    """rl_brain_learn_tc (tcgen05 tf32) vs rl_brain_learn (fp32 FMA) on the same events: gradients within 1% of the
+    """rl_brain_learn_tc (tcgen05 tf32) and rl_brain_learn_h (tcgen05 fp16 operands) vs rl_brain_learn (fp32 FMA) on the same events: gradients within 1% of the
     gradient scale, losses / priorities within 2e-2 relative."""
     import sys, os
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -67,81 +67,40 @@ def test_tensor_core_learn_matches_fp32_learn():
     n_ev = _fake_events(vw, rows, per_world)
     sidx = torch.from_numpy(rng.integers(0, 200, size=(n_ev, 64)).astype(np.int32)).cuda()
     out = {}
-    for mode in ("fp32", "tf32"):
+    for mode in ("fp32", "tf32", "fp16"):
         brain = DeviceBrain(0, w0, "cuda", lr=1e-3, gamma=0.99)
+        brain.use_fp16 = mode == "fp16"
         brain.load_state_dict(tgt, target=True)
         brain.alloc_learn(rows.row_cap)
         brain.sample_idx[:n_ev] = sidx
         if mode == "fp32":
             _lib.check(vw.lib.rl_brain_learn(C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(rp.bufs),
                                              C.c_void_p(brain.sample_idx.data_ptr()), C.byref(brain.learn_bufs), vw._stream()))
-        else:
+        elif mode == "tf32":
             brain.build_wimg(vw._stream())
             _lib.check(vw.lib.rl_brain_learn_tc(C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(rp.bufs),
                                                 C.c_void_p(brain.sample_idx.data_ptr()), C.byref(brain.learn_bufs),
                                                 C.c_void_p(brain.wimg_e.data_ptr()), C.c_void_p(brain.wimg_t.data_ptr()), vw._stream()))
+        else:
+            brain.build_wimg(vw._stream())
+            _lib.check(vw.lib.rl_brain_learn_h(C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(rp.bufs),
+                                               C.c_void_p(brain.sample_idx.data_ptr()), C.byref(brain.learn_bufs),
+                                               C.c_void_p(brain.wimg_eh.data_ptr()), C.c_void_p(brain.wimg_th.data_ptr()), vw._stream()))
         torch.cuda.synchronize()
         out[mode] = (brain.grad.cpu().numpy().copy(), brain.loss[:n_ev].cpu().numpy().copy(), brain.new_prio[:n_ev].cpu().numpy().copy())
-    g32, l32, p32 = out["fp32"]; gtc, ltc, ptc = out["tf32"]
-    nt = len(g32) - 4
-    assert gtc[nt] == n_ev
+    g32, l32, p32 = out["fp32"]
     from reinlife_b200.Models import packing
     d = packing.dims(0)
     m = packing.grad_mask(0)
-    for name, lo, hi in (("W1", 0, d.off_b1), ("b1", d.off_b1, d.off_w2t), ("W2", d.off_w2t, d.off_b2), ("b2", d.off_b2, d.off_wh),
-                         ("Wh", d.off_wh, d.off_bh), ("bh", d.off_bh, d.off_bh + 9)):
-        a, b = g32[lo:hi] * m[lo:hi], gtc[lo:hi] * m[lo:hi]
-        scale = np.abs(a).max()
-        err = np.abs(a - b).max() / scale
-        assert err < 1e-2, (name, err, scale)
-    np.testing.assert_allclose(ltc, l32, rtol=2e-2, atol=1e-3)
-    np.testing.assert_allclose(ptc, p32, rtol=2e-2, atol=2e-2)
-
-
-def test_tensor_core_act_matches_fp32_act():
-    """rl_brain_act_tc (tcgen05 tf32 forward) vs rl_brain_act_all (fp32 FMA) on real observations with the pretrained
-    PERD3QN weights: Q values within 2e-2 of the Q scale, >= 99% identical greedy actions, identical exploration draws
-    (epsilon = 0.3: wherever the fp32 path explored, both paths pick the same random action)."""
-    from brain_golden_util import golden, state_dict
-    from reinlife_b200 import _lib
-    from reinlife_b200.brains import DeviceBrain
-    from reinlife_b200.World.vecworld import VecWorld
-    from reinlife_b200.rows import RowLists
-    NW = 24
-    vw = VecWorld(NW, 30, 30, 2, max_agents=100, seed=12)
-    rows = RowLists(vw)
-    vw.reset(); vw.top_up(100)
-    g = torch.Generator(device="cuda"); g.manual_seed(1)
-    for _ in range(3):                       # a few steps so that observations are not the reset ones
-        vw.set_actions(torch.randint(0, 8, (NW, vw.S), device="cuda", dtype=torch.int8, generator=g))
-        vw.step(); vw.update(); vw.top_up(100)
-    rows.build(kinds_mask=1)
-    brains = [DeviceBrain(0, state_dict("perd3qn"), "cuda"), DeviceBrain(0, state_dict("d3qn"), "cuda")]
-    eps = torch.tensor([0.3, 0.0], dtype=torch.float64, device="cuda")
-    descs = (_lib.BrainAct * 2)(*[b.act_desc(_lib.ACT_DUELING, eps.data_ptr() + 8 * i) for i, b in enumerate(brains)])
-    out = {}
-    for mode in ("fp32", "tf32"):
-        q = torch.zeros((2, rows.row_cap, 8), device="cuda")
-        vw.rec[:, :, 13] = 255
-        if mode == "fp32":
-            _lib.check(vw.lib.rl_brain_act_all(C.byref(vw.cfg), C.byref(vw.bufs), C.byref(rows.bufs), descs, 2, C.c_uint64(7),
-                                               C.c_void_p(q.data_ptr()), None, vw._stream()))
-        else:
-            for i, b in enumerate(brains):
-                b.build_wimg(vw._stream())
-                _lib.check(vw.lib.rl_brain_act_tc(C.byref(vw.cfg), C.byref(vw.bufs), C.byref(rows.bufs), i, C.byref(descs[i]),
-                                                  C.c_void_p(b.wimg_e.data_ptr()), C.c_uint64(7), C.c_void_p(q.data_ptr()), vw._stream()))
-        torch.cuda.synchronize()
-        out[mode] = (q.cpu().numpy(), vw.rec[:, :, 13].cpu().numpy().view(np.int8).copy())
-    n_tot = 0
-    for i in range(2):
-        n = int(rows.total[i * 3])
-        n_tot += n
-        q32, qtc = out["fp32"][0][i, :n], out["tf32"][0][i, :n]
-        assert n > 500 and np.abs(q32).max() > 1.0
-        assert np.abs(q32 - qtc).max() < 2e-2 * np.abs(q32).max()
-        assert (q32.argmax(1) == qtc.argmax(1)).mean() >= 0.99
-    a32, atc = out["fp32"][1], out["tf32"][1]
-    listed = a32 != -1
-    assert listed.sum() == n_tot and ((atc != -1) == listed).all()
-    assert (a32[listed] == atc[listed]).mean() >= 0.99
+    nt = len(g32) - 4
+    for mode in ("tf32", "fp16"):       # both carry 11 significant bits per operand, fp32 accumulation
+        gtc, ltc, ptc = out[mode]
+        assert gtc[nt] == n_ev
+        for name, lo, hi in (("W1", 0, d.off_b1), ("b1", d.off_b1, d.off_w2t), ("W2", d.off_w2t, d.off_b2), ("b2", d.off_b2, d.off_wh),
+                             ("Wh", d.off_wh, d.off_bh), ("bh", d.off_bh, d.off_bh + 9)):
+            a, b = g32[lo:hi] * m[lo:hi], gtc[lo:hi] * m[lo:hi]
+            scale = np.abs(a).max()
+            err = np.abs(a - b).max() / scale
+            assert err < 1e-2, (mode, name, err, scale)
+        np.testing.assert_allclose(ltc, l32, rtol=2e-2, atol=1e-3, err_msg=mode)
+        np.testing.assert_allclose(ptc, p32, rtol=2e-2, atol=2e-2, err_msg=mode)
