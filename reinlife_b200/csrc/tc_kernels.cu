@@ -1097,8 +1097,8 @@ constexpr int HC = 72;                                  // halves between consec
 constexpr float H_SCALE = 256.0f;
 // byte offsets of the regions
 constexpr int HB_X = 0;                                 // X' / X plain [64][160] (20480 B) -> H1^T / dH1^T timg [128][64] (18432 B)
-constexpr int HB_H1 = HB_X + 20480;                     // H1 bimg [64][128] (18432 B) -> dH2^T half timg [128][64] (18432 B)
-constexpr int HB_H2 = HB_H1 + 18432;                    // H2 bimg [64][256] (36864 B) -> dH2 bimg -> X^T timg [160][64] (23040 B) -> fp32 dW1 staging (<= 49664 B)
+constexpr int HB_H1 = HB_X + 20480;                     // H1 bimg [64][128] (18432 B) -> full dH2^T timg [256][64] (36864 B)
+constexpr int HB_H2 = HB_H1 + 36864;                    // H2 bimg [64][256] (36864 B) -> dH2 bimg -> X^T timg [160][64] (23040 B) -> fp32 dW1 staging (<= 49664 B)
 constexpr int HB_STAGE = HB_H2 + 49920;
 constexpr int HB_DOUT = HB_STAGE + NSH * HCHUNK * 2;    // dOut image [64][16] halves (2048 B)
 constexpr int HB_OUTH = HB_DOUT + 2048;                 // head outputs [64][16] floats (4096 B); dOut plain [64][12] aliases it
@@ -1170,7 +1170,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
     __half* sH1 = reinterpret_cast<__half*>(smem_raw + HB_H1);
     __half* sH2 = reinterpret_cast<__half*>(smem_raw + HB_H2);
     __half* sH1T = sX;         // H1^T / dH1^T (feature-major) live in the X region once the eval L1 MMAs are done
-    __half* sDT = sH1;         // dH2^T half buffer lives in the H1 region once the eval L2 MMAs are done
+    __half* sDT = sH1;         // the full dH2^T image [256][64] lives in the (double-size) H1 region once the eval L2 MMAs are done
     __half* sXT = sH2;         // X^T lives in the dH2 region once the dH1 MMAs are done
     __half* sStage = reinterpret_cast<__half*>(smem_raw + HB_STAGE);
     __half* sDout = reinterpret_cast<__half*>(smem_raw + HB_DOUT);
@@ -1287,16 +1287,9 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
                     chunk_release();
                     mma_commit(done);
                 }
-                wait_go();                                        // dW2 half 0: K = 64 batch rows = 4 k-steps (issuer 0)
-                if (role == 0) {
-                    mma_seq(T_DW2, desc_htimg(aH1T), 18u, desc_htimg(aH1), 18u, make_idesc_h(128, 128), 4, it != 0);
-                    mma_commit(done);
-                } else {
-                    mbar_arrive(done);
-                }
-                wait_go();                                        // dW2 half 1 (issuer 0); dH1^T split over K: of every [128][32] chunk issuer r takes k-step r
-                {
-                    if (role == 0) mma_seq(T_DW2 + 128, desc_htimg(aH1T), 18u, desc_htimg(aH1), 18u, make_idesc_h(128, 128), 4, it != 0);
+                wait_go();                                        // dW2 = H1^T dH2 (issuer 0: M = 128, N = 256, K = 64 batch rows = 4 k-steps, TMEM-resident
+                {                                                 // accumulator); dH1^T split over K: of every [128][32] chunk issuer r takes k-step r
+                    if (role == 0) mma_seq(T_DW2, desc_htimg(aH1T), 18u, desc_htimg(aH1), 18u, make_idesc_h(128, 256), 4, it != 0);
                     const uint32_t idesc = make_idesc_h(128, 64);
                     uint64_t b_desc = desc_hbimg(aH2 + role * 288, 256);
 #pragma unroll 1
@@ -1509,7 +1502,6 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
             }
             // ---- dH2 epilogue (values carry the factor H_SCALE): mask by H2 > 0; batch-major in place, feature-major via the half buffer ----
             wait_done();
-            uint32_t dvp[32];                                       // this thread's 64 masked values as fp16 pairs
             {
                 float sb2 = 0.f;
 #pragma unroll
@@ -1522,28 +1514,18 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
                         __half* ph = sH2 + hbimg_off(cb * 32 + j, f2, 256);
                         const float m = __half2float(*ph) > 0.f ? v[j] : 0.f;
                         const __half mh = h_sat(m);
-                        *ph = mh;
+                        *ph = mh;                                                   // batch-major, in place: B of dH1^T
                         v[j] = __half2float(mh);
                         sb2 += m;
                     }
 #pragma unroll
-                    for (int j2 = 0; j2 < 16; ++j2) dvp[cb * 16 + j2] = pack_h2(v[j2 * 2], v[j2 * 2 + 1]);
+                    for (int j8 = 0; j8 < 4; ++j8)                                  // feature-major row f2 of the full dH2^T image: B of dW2
+                        *reinterpret_cast<uint4*>(sDT + htimg_off(f2, cb * 32 + j8 * 8)) =
+                            make_uint4(pack_h2(v[j8 * 8], v[j8 * 8 + 1]), pack_h2(v[j8 * 8 + 2], v[j8 * 8 + 3]), pack_h2(v[j8 * 8 + 4], v[j8 * 8 + 5]), pack_h2(v[j8 * 8 + 6], v[j8 * 8 + 7]));
                 }
                 red_add(G + L::OFF_B2 + f2, sb2 * (1.0f / H_SCALE));
-                if (half == 0) {
-#pragma unroll
-                    for (int j8 = 0; j8 < 8; ++j8)
-                        *reinterpret_cast<uint4*>(sDT + htimg_off(f1, j8 * 8)) = make_uint4(dvp[j8 * 4], dvp[j8 * 4 + 1], dvp[j8 * 4 + 2], dvp[j8 * 4 + 3]);
-                }
             }
-            go_signal();                                            // -> dW2 half 0
-            wait_done();
-            if (half == 1) {
-#pragma unroll
-                for (int j8 = 0; j8 < 8; ++j8)
-                    *reinterpret_cast<uint4*>(sDT + htimg_off(f1, j8 * 8)) = make_uint4(dvp[j8 * 4], dvp[j8 * 4 + 1], dvp[j8 * 4 + 2], dvp[j8 * 4 + 3]);
-            }
-            go_signal();                                            // -> dW2 half 1, dH1^T
+            go_signal();                                            // -> dW2, dH1^T
             gather_load(xr, P.rp.obs + ring * RL_K1, idx);
             wait_done();
             {   // dH1 epilogue: lane = feature k1, this warp's 32 batch columns; mask by H1 > 0, dH1^T in place of H1^T, db1
