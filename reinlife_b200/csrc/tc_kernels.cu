@@ -1099,7 +1099,8 @@ constexpr float H_SCALE = 256.0f;
 constexpr int HB_X = 0;                                 // X' / X plain [64][160] (20480 B) -> H1^T / dH1^T timg [128][64] (18432 B)
 constexpr int HB_H1 = HB_X + 20480;                     // H1 bimg [64][128] (18432 B) -> full dH2^T timg [256][64] (36864 B)
 constexpr int HB_H2 = HB_H1 + 36864;                    // H2 bimg [64][256] (36864 B) -> dH2 bimg -> X^T timg [160][64] (23040 B) -> fp32 dW1 staging (<= 49664 B)
-constexpr int HB_STAGE = HB_H2 + 49920;
+constexpr int HB_XT = HB_H2 + 49920;                    // X^T timg [160][64] (23040 B), written once per event from the gathered eval rows
+constexpr int HB_STAGE = HB_XT + 23040;
 constexpr int HB_DOUT = HB_STAGE + NSH * HCHUNK * 2;    // dOut image [64][16] halves (2048 B)
 constexpr int HB_OUTH = HB_DOUT + 2048;                 // head outputs [64][16] floats (4096 B); dOut plain [64][12] aliases it
 constexpr int HB_SMALL = HB_OUTH + 4096;                // nq, gb, red, biases (floats)
@@ -1171,7 +1172,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
     __half* sH2 = reinterpret_cast<__half*>(smem_raw + HB_H2);
     __half* sH1T = sX;         // H1^T / dH1^T (feature-major) live in the X region once the eval L1 MMAs are done
     __half* sDT = sH1;         // the full dH2^T image [256][64] lives in the (double-size) H1 region once the eval L2 MMAs are done
-    __half* sXT = sH2;         // X^T lives in the dH2 region once the dH1 MMAs are done
+    __half* sXT = reinterpret_cast<__half*>(smem_raw + HB_XT);
     __half* sStage = reinterpret_cast<__half*>(smem_raw + HB_STAGE);
     __half* sDout = reinterpret_cast<__half*>(smem_raw + HB_DOUT);
     float* sOuth = reinterpret_cast<float*>(smem_raw + HB_OUTH); float* sDpl = sOuth;
@@ -1411,13 +1412,13 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
             const bool more = it + 1 < n_my, more2 = it + 2 < n_my;
             const int* idx = meta + (it & 1) * 256; const int* act = idx + 64;
             const float* rew = reinterpret_cast<const float*>(idx + 128); const float* dn = rew + 64;
-            const size_t ring = (size_t)(row_cur / S) * cap;
             const size_t ring_n1 = (size_t)(row_n1 / S) * cap;
             // ---------------- target net ----------------
             wait_l1();
             gather_store_h<false>(sX, xr);
             l1_epilogue(bias_t, false);
             go_signal();                                            // -> target L2^T, eval L1^T
+            gather_store_h<true>(sXT, xr);                          // X^T image for this event's dW1^T, from the same registers (hidden behind L2^T)
             if (more) {
                 load_meta_b((it + 1) & 1);
                 prefetch_rows(ring_n1, meta + ((it + 1) & 1) * 256);
@@ -1526,7 +1527,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
                 red_add(G + L::OFF_B2 + f2, sb2 * (1.0f / H_SCALE));
             }
             go_signal();                                            // -> dW2, dH1^T
-            gather_load(xr, P.rp.obs + ring * RL_K1, idx);
+            if (more) gather_load(xr, P.rp.next_obs + ring_n1 * RL_K1, meta + ((it + 1) & 1) * 256);   // next event's target-net rows, two stages ahead
             wait_done();
             {   // dH1 epilogue: lane = feature k1, this warp's 32 batch columns; mask by H1 > 0, dH1^T in place of H1^T, db1
                 float v[32], v2[32];
@@ -1551,9 +1552,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
                 }
                 red_add(G + L::OFF_B1 + f1, sb1 * (1.0f / H_SCALE));
             }
-            gather_store_h<true>(sXT, xr);
             go_signal();                                            // -> dW1^T
-            if (more) gather_load(xr, P.rp.next_obs + ring_n1 * RL_K1, meta + ((it + 1) & 1) * 256);
             wait_done();
             if (more) {
                 gather_store_h<false>(sX, xr);

@@ -74,7 +74,7 @@ using namespace tc;
 struct TcBenchParams { int M, N, ksteps, mode, iters; long long* out; };
 
 __global__ void __launch_bounds__(128) k_tc_mma_bench(const TcBenchParams P) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     float* sm = reinterpret_cast<float*>(smem_raw);
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(128) k_tc_mma_bench(const TcBenchParams P) {
 namespace {
 // n_issuers warps (lane 0 of each) issue `ksteps` MMAs each, concurrently, into disjoint TMEM column ranges
 __global__ void __launch_bounds__(128) k_tc_mma_bench_par(const TcBenchParams P, int n_issuers) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar[4];
     __shared__ uint32_t tmem_base_s;
     __shared__ long long t_end[4];
