@@ -1102,7 +1102,8 @@ constexpr int HB_H2 = HB_H1 + 36864;                    // H2 bimg [64][256] (36
 constexpr int HB_XT = HB_H2 + 49920;                    // X^T timg [160][64] (23040 B), written once per event from the gathered eval rows
 constexpr int HB_STAGE = HB_XT + 23040;
 constexpr int HB_DOUT = HB_STAGE + NSH * HCHUNK * 2;    // dOut image [64][16] halves (2048 B)
-constexpr int HB_OUTH = HB_DOUT + 2048;                 // head outputs [64][16] floats (4096 B); dOut plain [64][12] aliases it
+constexpr int HB_DOUTT = HB_DOUT + 2048;                // dOut^T image [16][64] halves, padded chunk stride (2304 B): B of the dWh GEMM
+constexpr int HB_OUTH = HB_DOUTT + 2304;                // head outputs [64][16] floats (4096 B); dOut plain [64][12] aliases it
 constexpr int HB_SMALL = HB_OUTH + 4096;                // nq, gb, red, biases (floats)
 constexpr int HB_INT = HB_SMALL + 4 * SM_SMALL_N;
 constexpr int HB_BARS = HB_INT + 4 * 512;
@@ -1175,6 +1176,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
     __half* sXT = reinterpret_cast<__half*>(smem_raw + HB_XT);
     __half* sStage = reinterpret_cast<__half*>(smem_raw + HB_STAGE);
     __half* sDout = reinterpret_cast<__half*>(smem_raw + HB_DOUT);
+    __half* sDoutT = reinterpret_cast<__half*>(smem_raw + HB_DOUTT);
     float* sOuth = reinterpret_cast<float*>(smem_raw + HB_OUTH); float* sDpl = sOuth;
     float* smallf = reinterpret_cast<float*>(smem_raw + HB_SMALL);
     float* nq = smallf + 128; float* gb = nq + 64; float* red = gb + 64;
@@ -1210,7 +1212,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
     const uint32_t tmem = *tmem_slot;
     const uint32_t T_WORK = tmem, T_DW2 = tmem + 256, T_L1 = tmem + 192;
     const int S = P.cfg.slot_cap, cap = P.rp.capacity;
-    const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH1T = smem_u32(sH1T), aH2 = smem_u32(sH2), aD = smem_u32(sDout), aXT = smem_u32(sXT);
+    const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH1T = smem_u32(sH1T), aH2 = smem_u32(sH2), aD = smem_u32(sDout), aXT = smem_u32(sXT), aDT2 = smem_u32(sDoutT);
 
     if (warp == 8) {
         if (lane == 0) {
@@ -1286,6 +1288,8 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
                 {
                     mma_f16(T_WORK + role * 64, desc_hplain(chunk_wait() + (role ? 4096u : 0u), 16), desc_hplain(aD, 16), make_idesc_h(128, 64), 0u);
                     chunk_release();
+                    // dWh[n2][j] = sum_b H2[b][n2] dOut[b][j]: A = H2^T rows of feature half r (in the H1 region), B = dOut^T, K = 64 batch rows
+                    mma_seq(T_WORK + 128 + role * 16, desc_htimg(aH1 + role * 16 * 1152), 18u, desc_htimg(aDT2), 18u, make_idesc_h(128, 16), 4, 0u);
                     mma_commit(done);
                 }
                 wait_go();                                        // dW2 = H1^T dH2 (issuer 0: M = 128, N = 256, K = 64 batch rows = 4 k-steps, TMEM-resident
@@ -1379,7 +1383,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
                         make_uint4(pack_h2(v[j8 * 8], v[j8 * 8 + 1]), pack_h2(v[j8 * 8 + 2], v[j8 * 8 + 3]), pack_h2(v[j8 * 8 + 4], v[j8 * 8 + 5]), pack_h2(v[j8 * 8 + 6], v[j8 * 8 + 7]));
             }
         };
-        auto l2_epilogue = [&](const float* bias) {
+        auto l2_epilogue = [&](const float* bias, bool eval) {
             const float b2 = bias[128 + f2];
 #pragma unroll
             for (int cb = 0; cb < 2; ++cb) {
@@ -1387,7 +1391,15 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
                 tmem_ld32(T_WORK + t_lane + half * 64 + cb * 32, v);
                 tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sH2[hbimg_off(cb * 32 + j, f2, 256)] = __float2half_rn(fmaxf(v[j] + b2, 0.f));
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + b2, 0.f);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sH2[hbimg_off(cb * 32 + j, f2, 256)] = __float2half_rn(v[j]);      // batch-major: A of the head GEMM
+                if (eval) {                        // feature-major H2^T [256][64] in the (dead) H1 region: A of the dWh GEMM, relu mask of dH2
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8)
+                        *reinterpret_cast<uint4*>(sH1 + htimg_off(f2, cb * 32 + j8 * 8)) =
+                            make_uint4(pack_h2(v[j8 * 8], v[j8 * 8 + 1]), pack_h2(v[j8 * 8 + 2], v[j8 * 8 + 3]), pack_h2(v[j8 * 8 + 4], v[j8 * 8 + 5]), pack_h2(v[j8 * 8 + 6], v[j8 * 8 + 7]));
+                }
             }
         };
         auto head_epilogue = [&](const float* bias) -> float {
@@ -1424,7 +1436,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
                 prefetch_rows(ring_n1, meta + ((it + 1) & 1) * 256);
             }
             wait_done();
-            l2_epilogue(bias_t);
+            l2_epilogue(bias_t, false);
             go_signal();                                            // -> target head
             wait_done();
             {
@@ -1443,7 +1455,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
             l1_epilogue(bias_e, true);
             go_signal();                                            // -> eval L2^T
             wait_done();
-            l2_epilogue(bias_e);
+            l2_epilogue(bias_e, true);
             go_signal();                                            // -> eval head
             wait_done();
             const float mean_e = head_epilogue(bias_e);
@@ -1467,42 +1479,29 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
                 for (int o = threadIdx.x; o < R * 16; o += NEPI) {
                     const int b = o >> 4, j = o & 15;
                     const float d = j < 8 ? ((j == act[b] ? gb[b] : 0.f) - shift) : (j == 8 ? gb[b] : 0.f);
-                    sDout[himg_off(b, j, 16)] = h_sat(d * H_SCALE);
+                    const __half dh = h_sat(d * H_SCALE);
+                    sDout[himg_off(b, j, 16)] = dh;
+                    sDoutT[htimg_off(j, b)] = dh;
                     if (j < 12) sDpl[b * 12 + j] = d;
                 }
             }
-            go_signal();                                            // -> dH2^T (runs under the head-gradient SIMT below)
+            go_signal();                                            // -> dH2^T and dWh (tensor core)
             epi_bar();
-            // ---- head gradients (SIMT): dWh[k][j] += sum_b H2[b][k] dOut[b][j]; dbh ----
-            {
-                const int k = threadIdx.x;
-                float acc[9];
-#pragma unroll
-                for (int j = 0; j < 9; ++j) acc[j] = 0.f;
-                const __half* hk = sH2 + (k >> 3) * HC + (k & 7);
-#pragma unroll 2
-                for (int g = 0; g < 8; ++g) {
-#pragma unroll
-                    for (int rr = 0; rr < 8; ++rr) {
-                        const int b = g * 8 + rr;
-                        const float h = __half2float(hk[g * (32 * HC) + rr * 8]);
-                        const float4 d0 = *reinterpret_cast<const float4*>(sDpl + b * 12), d1 = *reinterpret_cast<const float4*>(sDpl + b * 12 + 4);
-                        const float d8 = sDpl[b * 12 + 8];
-                        acc[0] = fmaf(h, d0.x, acc[0]); acc[1] = fmaf(h, d0.y, acc[1]); acc[2] = fmaf(h, d0.z, acc[2]); acc[3] = fmaf(h, d0.w, acc[3]);
-                        acc[4] = fmaf(h, d1.x, acc[4]); acc[5] = fmaf(h, d1.y, acc[5]); acc[6] = fmaf(h, d1.z, acc[6]); acc[7] = fmaf(h, d1.w, acc[7]);
-                        acc[8] = fmaf(h, d8, acc[8]);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 9; ++j) red_add(G + L::OFF_WH + k * 9 + j, acc[j]);
-                if (threadIdx.x < 9) {
-                    float s = 0.f;
-                    for (int b = 0; b < R; ++b) s += sDpl[b * 12 + threadIdx.x];
-                    red_add(G + L::OFF_BH + threadIdx.x, s);
-                }
+            if (threadIdx.x < 9) {                                  // dbh[j] = sum_b dOut[b][j]
+                float s = 0.f;
+                for (int b = 0; b < R; ++b) s += sDpl[b * 12 + threadIdx.x];
+                red_add(G + L::OFF_BH + threadIdx.x, s);
             }
-            // ---- dH2 epilogue (values carry the factor H_SCALE): mask by H2 > 0; batch-major in place, feature-major via the half buffer ----
             wait_done();
+            {   // head weight gradients from the tensor core: row n2 = f2 of dWh (scaled by H_SCALE)
+                float wv[16];
+                tmem_ld16(T_WORK + t_lane + 128 + half * 16, wv);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 9; ++j) red_add(G + L::OFF_WH + f2 * 9 + j, wv[j] * (1.0f / H_SCALE));
+            }
+            // ---- dH2 epilogue (values carry the factor H_SCALE): lane = feature n2; mask by H2 > 0 read from H2^T; dH2 batch-major
+            //      over H2 (B of dH1^T), dH2^T feature-major in place of H2^T (B of dW2) ----
             {
                 float sb2 = 0.f;
 #pragma unroll
@@ -1511,18 +1510,23 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
                     tmem_ld32(T_WORK + t_lane + half * 64 + cb * 32, v);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        __half* ph = sH2 + hbimg_off(cb * 32 + j, f2, 256);
-                        const float m = __half2float(*ph) > 0.f ? v[j] : 0.f;
-                        const __half mh = h_sat(m);
-                        *ph = mh;                                                   // batch-major, in place: B of dH1^T
-                        v[j] = __half2float(mh);
-                        sb2 += m;
-                    }
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        uint4* pt = reinterpret_cast<uint4*>(sH1 + htimg_off(f2, cb * 32 + j8 * 8));
+                        const uint4 hq = *pt;
+                        const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
+                        uint32_t ow[4];
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8)                                  // feature-major row f2 of the full dH2^T image: B of dW2
-                        *reinterpret_cast<uint4*>(sDT + htimg_off(f2, cb * 32 + j8 * 8)) =
-                            make_uint4(pack_h2(v[j8 * 8], v[j8 * 8 + 1]), pack_h2(v[j8 * 8 + 2], v[j8 * 8 + 3]), pack_h2(v[j8 * 8 + 4], v[j8 * 8 + 5]), pack_h2(v[j8 * 8 + 6], v[j8 * 8 + 7]));
+                        for (int p2 = 0; p2 < 4; ++p2) {
+                            const int j = j8 * 8 + p2 * 2;
+                            const float m0 = h_lo(hw[p2]) > 0.f ? v[j] : 0.f, m1 = h_hi(hw[p2]) > 0.f ? v[j + 1] : 0.f;
+                            const __half q0 = h_sat(m0), q1 = h_sat(m1);
+                            sH2[hbimg_off(cb * 32 + j, f2, 256)] = q0;
+                            sH2[hbimg_off(cb * 32 + j + 1, f2, 256)] = q1;
+                            ow[p2] = (uint32_t)__half_as_ushort(q0) | ((uint32_t)__half_as_ushort(q1) << 16);
+                            sb2 += m0 + m1;
+                        }
+                        *pt = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    }
                 }
                 red_add(G + L::OFF_B2 + f2, sb2 * (1.0f / H_SCALE));
             }
