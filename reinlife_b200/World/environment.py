@@ -220,6 +220,7 @@ class Environment:
         if not active:
             return
         w, lib = self.world, self.world.lib
+        pending = []
         for g in active:
             b = self.brains[g]
             if b.PRIORITIZED:                                   # PERD3QN.py:157-175
@@ -256,8 +257,10 @@ class Environment:
                 ev1.record()
                 self.kernel_events.append(("learn_events", g, ev0, ev1))
             self.gpu_launches += 3
-        if self.dist:
-            self._allreduce_grads(active)
+            if self.dist:                                # this brain's gradient all-reduce runs under the next brain's event kernel
+                pending.append(torch.distributed.all_reduce(b._dev.grad, async_op=True))
+        for work in pending:
+            work.wait()
         for g in active:
             b = self.brains[g]
             _lib.check(lib.rl_brain_adam(C.byref(b._dev.learn_bufs), st))
