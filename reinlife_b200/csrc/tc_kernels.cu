@@ -1,15 +1,15 @@
-// tc_kernels.cu -- PERD3QN / D3QN train() events on the 5th-gen tensor cores (tcgen05.mma kind::tf32, TMEM
-// accumulators, bulk-async weight streaming), warp-specialised: warp 8 = weight-stream producer + MMA issuer,
-// warps 0-7 = gather / TMEM epilogues / small SIMT pieces.  Same math and same outputs as k_learn_dueling
-// (learn_kernels.cu, fp32 FMA), which stays as the tight-tolerance reference path.
-//
-// One event (64 rows) per CTA iteration.  All seven big GEMMs of an event run as K-major tf32 MMAs:
-//   target/eval L1  [64x160]x[160x128],  L2 [64x128]x[128x256],  head [64x256]x[256x16],
-//   dH2 = dOut Wh^T [64x16]x[16x256],    dH1 = dH2 W2 [64x256]x[256x128],
-//   dW2 += H1^T dH2 (M=128: A = H1^T image, B = dH2^T image, K = 64 rows), accumulated in TMEM across ALL events
-//   of the CTA and flushed once;  dW1^T = dH1^T X (M=128, N=160), flushed per event.
-// tf32 MN-major operands read back as zeros on this part with the no-swizzle layouts (tests/test_tc_gpu.py pins
-// the K-major conventions), so transposed operand images are written explicitly by the epilogues.
+// tc_kernels.cu -- the dueling brains (PERD3QN / D3QN) on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators,
+// cp.async.bulk weight streaming), same math and outputs as the fp32 kernels of learn_kernels.cu / brain_kernels.cu, which
+// stay as the tight-tolerance reference path:
+//   k_learn_dueling_h     train() events, fp16 operands (kind::f16)      -- the default event kernel
+//   k_learn_dueling_tc2   train() events, tf32 operands (kind::tf32)     -- precision="tf32"
+//   k_act_dueling_tc      get_action forward, tf32 operands
+//   k_build_wimg_dueling(_h)  weight operand images (23 chunks per network) from the kernel-layout parameters
+// One event (64 rows) per CTA iteration.  The large GEMMs of an event -- target/eval L1 160->128, L2 128->256, head 256->9,
+// dH2 = dOut Wh^T, dH1 = dH2 W2, dW2 += H1^T dH2 (accumulated in TMEM across ALL events of the CTA), dW1^T = dH1^T X and,
+// in the fp16 kernel, dWh = H2^T dOut -- run as K-major MMAs in transposed-output form (see k_learn_dueling_tc2).
+// tf32 MN-major operands read back as zeros on this part with the no-swizzle layouts (tests/test_tc_gpu.py pins the
+// K-major conventions), so transposed operand images are written explicitly by the epilogues.
 #include <stdlib.h>
 #include <cuda_fp16.h>
 #include "tc_tile.cuh"
@@ -36,11 +36,6 @@ constexpr int WI_CHUNKS = 23;
 
 // chunk schedule of one event: (net, chunk).  net 0 = target, 1 = eval
 constexpr int SCHED_N = 37;
-__device__ __forceinline__ void sched_entry(int i, int& net, int& chunk) {
-    if (i < 14) { net = 0; chunk = i; }                 // target: W1[5], W2K[8], WH
-    else if (i < 29) { net = 1; chunk = i - 14; }       // eval:   W1[5], W2K[8], WH, WHT
-    else { net = 1; chunk = WI_W2T + (i - 29); }        // eval:   W2T[8]
-}
 
 struct TcLearnParams {
     rl_world_cfg cfg;
@@ -74,9 +69,6 @@ static_assert(TC_SMEM <= 227 * 1024, "shared memory budget");
 
 // fire-and-forget adds into the CTA-private gradient slab (no return value -> no scoreboard stall, no contention)
 __device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
-__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 // Transposed operand images ([feature rows][64 batch columns]) use a padded chunk stride: LBO = 144 B instead of 128 B.
 // A transposed store writes one feature row for 16 consecutive batch columns; with the pad the four 16-byte chunks land
@@ -133,410 +125,18 @@ __device__ __forceinline__ void gather_store(float* img, const float4 (&x)[10]) 
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_learn_dueling_tc(const TcLearnParams P) {
-    using L = Layout<RL_MODEL_DUELING>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* sm = reinterpret_cast<float*>(smem_raw);
-    float* sX = sm + SM_X; float* sH1 = sm + SM_H1; float* sH2 = sm + SM_H2;
-    float* sH1T = sX;          // H1^T / dH1^T live in the X region once the eval L1 MMAs are done
-    float* sXT = sH2;          // X^T lives in the dH2 region once the dH1 MMAs are done
-    float* sStage = sm + SM_STAGE; float* sDout = sm + SM_DOUT; float* sOuth = sm + SM_OUTH; float* sDpl = sm + SM_DPL;
-    float* nq = sm + SM_SMALL + 128; float* gb = nq + 64; float* red = gb + 64;
-    float* bias_t = red + 32;                 // b1[128] b2[256] bh[16] of the target net
-    float* bias_e = bias_t + 400;             // same for the eval net
-    int* meta = reinterpret_cast<int*>(sm + SM_INT);     // [2][256]: idx, act, rew (float), dn (float) of the current / next event
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_FLOATS);
-    uint64_t* full = bars; uint64_t* empty = bars + NS; uint64_t* done = bars + 2 * NS; uint64_t* ready = done + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* Pe = P.lb.params; const float* Pt = P.lb.target;
-    float* G = P.lb.grad_scratch + (size_t)blockIdx.x * L::N_TRAIN;
-    const int total = *P.ev_total;
-    const int n_my = total > (int)blockIdx.x ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(done, 1); mbar_init(ready, 1);
-        fence_mbar_init();
-    }
-    if (warp == 8) tmem_alloc(tmem_slot, 512);
-    if (threadIdx.x < NEPI) {
-        for (int i = threadIdx.x; i < 400; i += NEPI) {
-            const int o = i < 128 ? L::OFF_B1 + i : i < 384 ? L::OFF_B2 + (i - 128) : L::OFF_BH + (i - 384);
-            const bool ok = i < 384 + 9;
-            bias_t[i] = ok ? Pt[o] : 0.f; bias_e[i] = ok ? Pe[o] : 0.f;
-        }
-        for (int i = threadIdx.x; i < L::N_TRAIN / 4; i += NEPI) reinterpret_cast<float4*>(G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    fence_before();
-    __syncthreads();
-    fence_after();
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t T_WORK = tmem, T_DW2 = tmem + 256;
-    const int S = P.cfg.slot_cap, cap = P.rp.capacity;
-
-    if (warp == 8) {
-        // =================================== weight-stream producer (one thread) ===================================
-        // Streams the fixed 37-chunk schedule of every event through the NS-slot ring; runs ahead of the MMA issuer
-        // (epilogue thread 0) by as many chunks as the ring holds.  A slot is refilled once the MMAs that read it
-        // have completed (tcgen05.commit -> empty[slot]).
-        if (lane == 0) {
-            const uint32_t n_chunks = (uint32_t)n_my * SCHED_N;
-            for (uint32_t produced = 0; produced < n_chunks; ++produced) {
-                const uint32_t slot = produced % NS;
-                if (produced >= NS) mbar_wait(&empty[slot], ((produced / NS) - 1) & 1);
-                int net, ch; sched_entry(produced % SCHED_N, net, ch);
-                bulk_load(sStage + slot * CHUNK_F, (net ? P.wimg_e : P.wimg_t) + (size_t)ch * CHUNK_F, CHUNK_F * 4, &full[slot]);
-            }
-        }
-    } else {
-        // =================================== epilogue warps ===================================
-        uint32_t stage_no = 0;
-        const int q = warp & 3, half = warp >> 2;
-        const uint32_t t_lane = (uint32_t)(q * 32) << 16;
-        const int row = q * 16 + lane;                 // M = 64 accumulators: rows 16q+i in lanes 32q+i (i < 16)
-        const bool rvalid = lane < 16;
-        uint32_t consumed = 0;                          // chunks consumed so far (meaningful in thread 0 only)
-        const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH1T = smem_u32(sH1T), aH2 = smem_u32(sH2), aD = smem_u32(sDout), aXT = smem_u32(sXT);
-        // all epilogue threads: make shared-memory images visible to the tensor core, order TMEM accesses, meet
-        auto stage_sync = [&]() { fence_proxy_async(); fence_before(); epi_bar(); };
-        // thread 0: one GEMM stage whose B operand streams through the chunk ring
-        auto stream_gemm = [&](uint32_t d_tmem, uint32_t a_base, int a_k, int nch, int kc, int m, int n) {
-            const uint32_t idesc = make_idesc(m, n, 0, 0);
-            for (int c = 0; c < nch; ++c) {
-                const uint32_t slot = consumed % NS;
-                mbar_wait(&full[slot], (consumed / NS) & 1);
-                fence_after();
-                const uint32_t b_base = smem_u32(sStage + slot * CHUNK_F);
-                for (int ks = 0; ks < kc / 8; ++ks) {
-                    const int kcol = c * kc + ks * 8;
-                    mma_tf32(d_tmem, desc_kmajor(a_base + (kcol >> 2) * 128, a_k), desc_kmajor(b_base + ks * 256, kc), idesc, (c | ks) != 0);
-                }
-                mma_commit(&empty[slot]);
-                ++consumed;
-            }
-        };
-        // issue a stage from thread 0 (after stage_sync), everybody then waits for its completion
+// issue a tensor-core stage from epilogue thread 0 (after stage_sync), everybody then waits for its completion (used by the
+// get_action kernel, whose stages are short and strictly sequential)
 #define RL_STAGE(BODY) do { stage_sync(); if (threadIdx.x == 0) { fence_after(); BODY; mma_commit(done); } } while (0)
-        int tr_n = 0;
-        auto stamp = [&](int it) { if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 8 && tr_n < 30) P.trace[it * 40 + tr_n++] = clock64(); };
-        auto wait_done = [&]() { mbar_wait(done, stage_no & 1); ++stage_no; fence_after(); };
-
-        // per-event metadata of event e -> buffer b, loaded by warps 6-7 (not the MMA-issuing thread) in two phases so that
-        // each dependent global round trip hides behind one tensor-core stage; visible to everybody after the next epi_bar
-        int meta_i = 0; size_t meta_ring = 0;
-        auto load_meta_a = [&](int b, int e) {           // phase A: sampled ring positions
-            if (threadIdx.x >= NEPI - R) {
-                const int r = threadIdx.x - (NEPI - R);
-                meta_ring = (size_t)(P.ev_rows[e] / S) * cap;
-                meta_i = max(P.sample_idx[(size_t)e * R + r], 0);     // -1 = skipped by the uniform sampler (error state)
-                meta[b * 256 + r] = meta_i;
-            }
-        };
-        auto load_meta_b = [&](int b) {                  // phase B: action / reward / done of those positions
-            if (threadIdx.x >= NEPI - R) {
-                const int r = threadIdx.x - (NEPI - R);
-                int* m = meta + b * 256;
-                m[64 + r] = P.rp.action[meta_ring + meta_i];
-                reinterpret_cast<float*>(m)[128 + r] = P.rp.reward[meta_ring + meta_i];
-                reinterpret_cast<float*>(m)[192 + r] = (float)P.rp.done[meta_ring + meta_i];
-            }
-        };
-        // pull the 2 x 64 replay rows of the NEXT event into L2 (640 B = 5 lines per row); ids = its ring positions (smem)
-        auto prefetch_rows = [&](size_t rg_, const int* ids) {
-            for (int v = threadIdx.x; v < 2 * R * 5; v += NEPI) {
-                const int which = v / (R * 5), rem = v - which * (R * 5), r = rem / 5, ln = rem - r * 5;
-                const float* p = (which ? P.rp.obs : P.rp.next_obs) + (rg_ + ids[r]) * RL_K1 + ln * 32;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-            }
-        };
-        float4 xr[10];                                   // one gathered 64 x 160 image in flight (registers)
-        if (n_my > 0) {                                  // prologue: metadata + target-net input of the first event
-            load_meta_a(0, blockIdx.x);
-            load_meta_b(0);
-            epi_bar();
-            gather_load(xr, P.rp.next_obs + (size_t)(P.ev_rows[blockIdx.x] / S) * cap * RL_K1, meta);
-            gather_store<false>(sX, xr);
-        }
-        for (int it = 0; it < n_my; ++it) {
-            tr_n = 0; stamp(it);
-            const int e = blockIdx.x + it * gridDim.x;
-            const bool more = it + 1 < n_my;
-            const int* idx = meta + (it & 1) * 256; const int* act = idx + 64;
-            const float* rew = reinterpret_cast<const float*>(idx + 128); const float* dn = rew + 64;
-            const size_t ring = (size_t)(P.ev_rows[e] / S) * cap;
-            const size_t ring_next = more ? (size_t)(P.ev_rows[e + gridDim.x] / S) * cap : 0;
-            float mean_e = 0.f;
-            for (int net = 0; net < 2; ++net) {
-                const float* bias = net ? bias_e : bias_t;
-                stamp(it); RL_STAGE(stream_gemm(T_WORK, aX, RL_K1, 5, 32, 64, 128));
-                if (net == 0) {                          // hidden behind the target L1 MMAs: eval-net input rows + next event's metadata
-                    gather_load(xr, P.rp.obs + ring * RL_K1, idx);
-                    if (more) load_meta_a((it + 1) & 1, e + gridDim.x);
-                }
-                // ---- L1 epilogue: H1 = relu(D + b1) -> H1 image (+ H1^T image for the eval net) ----
-                wait_done(); stamp(it);
-                if (net == 0) gather_store<false>(sX, xr);      // sX is free: the target L1 MMAs have completed
-                {
-                    float va[2][32];
-                    tmem_ld32(T_WORK + t_lane + half * 64, va[0]);
-                    tmem_ld32(T_WORK + t_lane + half * 64 + 32, va[1]);
-                    tmem_wait_ld();
-                    if (rvalid) {
-#pragma unroll
-                        for (int cb = 0; cb < 2; ++cb) {
-                            const int c0 = half * 64 + cb * 32;
-                            float* v = va[cb];
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = to_tf32(fmaxf(v[j] + bias[c0 + j], 0.f));
-#pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4)
-                                *reinterpret_cast<float4*>(sH1 + img_off(row, c0 + j4 * 4, 128)) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-                            if (net) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) sH1T[timg_off(c0 + j, row)] = v[j];
-                            }
-                        }
-                    }
-                }
-                stamp(it); RL_STAGE(stream_gemm(T_WORK, aH1, 128, 8, 16, 64, 256));
-                if (net == 0 && more) {                  // hidden behind the target L2 MMAs
-                    load_meta_b((it + 1) & 1);
-                    prefetch_rows(ring_next, meta + ((it + 1) & 1) * 256);
-                }
-                // ---- L2 epilogue: H2 = relu(D + b2) -> H2 image ----
-                wait_done(); stamp(it);
-                for (int cp = 0; cp < 2; ++cp) {
-                    float va[2][32];
-                    tmem_ld32(T_WORK + t_lane + half * 128 + cp * 64, va[0]);
-                    tmem_ld32(T_WORK + t_lane + half * 128 + cp * 64 + 32, va[1]);
-                    tmem_wait_ld();
-                    if (rvalid) {
-#pragma unroll
-                        for (int cb = 0; cb < 2; ++cb) {
-                            const int c0 = half * 128 + cp * 64 + cb * 32;
-                            const float* v = va[cb];
-#pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4)
-                                *reinterpret_cast<float4*>(sH2 + img_off(row, c0 + j4 * 4, 256)) =
-                                    make_float4(to_tf32(fmaxf(v[j4 * 4] + bias[128 + c0 + j4 * 4], 0.f)), to_tf32(fmaxf(v[j4 * 4 + 1] + bias[128 + c0 + j4 * 4 + 1], 0.f)),
-                                                to_tf32(fmaxf(v[j4 * 4 + 2] + bias[128 + c0 + j4 * 4 + 2], 0.f)), to_tf32(fmaxf(v[j4 * 4 + 3] + bias[128 + c0 + j4 * 4 + 3], 0.f)));
-                        }
-                    }
-                }
-                stamp(it); RL_STAGE(stream_gemm(T_WORK, aH2, 256, 1, 256, 64, 16));
-                // ---- head epilogue: [A(8) | V] + bh ----
-                wait_done(); stamp(it);
-                if (half == 0) {
-                    float v[16];
-                    tmem_ld16(T_WORK + t_lane, v);
-                    tmem_wait_ld();
-                    if (rvalid) {
-#pragma unroll
-                        for (int j = 0; j < 9; ++j) sOuth[row * 16 + j] = v[j] + bias[384 + j];
-                    }
-                }
-                fence_before();
-                epi_bar();
-                float s = 0.f;
-                for (int o = threadIdx.x; o < R * 8; o += NEPI) s += sOuth[(o >> 3) * 16 + (o & 7)];
-                const float mean = epi_sum(s, red) * (1.0f / (8 * R));
-                if (net == 0) {
-                    if (threadIdx.x < R) {
-                        const float* o = sOuth + threadIdx.x * 16;
-                        float mx = o[0];
-#pragma unroll
-                        for (int j = 1; j < 8; ++j) mx = fmaxf(mx, o[j]);
-                        nq[threadIdx.x] = mx + o[8] - mean;
-                    }
-                    epi_bar();
-                } else {
-                    mean_e = mean;
-                }
-            }
-            stamp(it);
-            // ---- TD target, loss, priorities, dOut ----
-            {
-                float g = 0.f, sq = 0.f;
-                if (threadIdx.x < R) {
-                    const int b = threadIdx.x;
-                    const float qa = sOuth[b * 16 + act[b]] + sOuth[b * 16 + 8] - mean_e;
-                    const float y = rew[b] + P.lb.gamma * (1.0f - dn[b]) * nq[b];
-                    const float diff = qa - y;
-                    g = 2.0f * diff * (1.0f / R);
-                    sq = diff * diff;
-                    gb[b] = g;
-                    P.lb.new_prio[(size_t)e * R + b] = fabsf(nq[b] - qa);
-                }
-                const float gsum = epi_sum(g, red);
-                const float loss = epi_sum(sq, red) * (1.0f / R);
-                if (threadIdx.x == 0) P.lb.loss[e] = loss;
-                const float shift = gsum * (1.0f / (8 * R));
-                for (int o = threadIdx.x; o < R * 16; o += NEPI) {
-                    const int b = o >> 4, j = o & 15;
-                    const float d = j < 8 ? ((j == act[b] ? gb[b] : 0.f) - shift) : (j == 8 ? gb[b] : 0.f);
-                    sDout[img_off(b, j, 16)] = to_tf32(d);
-                    if (j < 12) sDpl[b * 12 + j] = d;
-                }
-                epi_bar();
-            }
-            stamp(it);
-            // ---- head gradients (SIMT): dWh[k][j] += sum_b H2[b][k] dOut[b][j]; dbh ----
-            {
-                const int k = threadIdx.x;
-                float acc[9];
-#pragma unroll
-                for (int j = 0; j < 9; ++j) acc[j] = 0.f;
-                const int r0 = (k >> 2) & 7;                                 // per-lane row rotation: conflict-free image reads
-                const float* hk = sH2 + (k >> 2) * 32 + (k & 3);
-#pragma unroll 1
-                for (int g = 0; g < 8; ++g) {
-#pragma unroll
-                    for (int rr = 0; rr < 8; ++rr) {
-                        const int rx = rr ^ r0, b = g * 8 + rx;
-                        const float h = hk[g * 2048 + rx * 4];
-                        const float4 d0 = *reinterpret_cast<const float4*>(sDpl + b * 12), d1 = *reinterpret_cast<const float4*>(sDpl + b * 12 + 4);
-                        const float d8 = sDpl[b * 12 + 8];
-                        acc[0] = fmaf(h, d0.x, acc[0]); acc[1] = fmaf(h, d0.y, acc[1]); acc[2] = fmaf(h, d0.z, acc[2]); acc[3] = fmaf(h, d0.w, acc[3]);
-                        acc[4] = fmaf(h, d1.x, acc[4]); acc[5] = fmaf(h, d1.y, acc[5]); acc[6] = fmaf(h, d1.z, acc[6]); acc[7] = fmaf(h, d1.w, acc[7]);
-                        acc[8] = fmaf(h, d8, acc[8]);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 9; ++j) red_add(G + L::OFF_WH + k * 9 + j, acc[j]);
-                if (threadIdx.x < 9) {
-                    float s = 0.f;
-                    for (int b = 0; b < R; ++b) s += sDpl[b * 12 + threadIdx.x];
-                    red_add(G + L::OFF_BH + threadIdx.x, s);
-                }
-            }
-            stamp(it); RL_STAGE(stream_gemm(T_WORK, aD, 16, 1, 16, 64, 256));   // dH2 (pre-mask) = dOut Wh^T
-            // ---- dH2 epilogue: mask by H2 > 0, in place; first half transposed into the (dead) H1 region ----
-            wait_done(); stamp(it);
-            float* sDT = sH1;                                   // dH2^T half buffer [128][64]
-            for (int cb = 0; cb < 4; ++cb) {
-                const int c0 = half * 128 + cb * 32;
-                float v[32];
-                tmem_ld32(T_WORK + t_lane + c0, v);
-                tmem_wait_ld();
-                if (rvalid) {
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        float4* p = reinterpret_cast<float4*>(sH2 + img_off(row, c0 + j4 * 4, 256));
-                        const float4 h = *p;
-                        v[j4 * 4 + 0] = h.x > 0.f ? to_tf32(v[j4 * 4 + 0]) : 0.f; v[j4 * 4 + 1] = h.y > 0.f ? to_tf32(v[j4 * 4 + 1]) : 0.f;
-                        v[j4 * 4 + 2] = h.z > 0.f ? to_tf32(v[j4 * 4 + 2]) : 0.f; v[j4 * 4 + 3] = h.w > 0.f ? to_tf32(v[j4 * 4 + 3]) : 0.f;
-                        *p = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-                    }
-                    if (half == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) sDT[timg_off(c0 + j, row)] = v[j];
-                    }
-                }
-            }
-            fence_before();
-            epi_bar();
-            // db2[n] += sum_b dH2[b][n]
-            {
-                const int n = threadIdx.x;
-                float s = 0.f;
-                for (int i = 0; i < R; ++i) { const int b = (i + (n >> 2)) & 63; s += sH2[img_off(b, n, 256)]; }
-                red_add(G + L::OFF_B2 + n, s);
-            }
-            stamp(it);
-            RL_STAGE({ const uint32_t idesc = make_idesc(128, 128, 0, 0);                  // dW2 half 0 (TMEM-resident accumulator)
-                       for (int ks = 0; ks < 8; ++ks)
-                           mma_tf32(T_DW2, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aH1 + ks * TP_KSTEP), idesc, (it | ks) != 0); });
-            wait_done(); stamp(it);                                      // dW2 half 0 finished reading the half buffer
-            for (int o = threadIdx.x; o < R * 128; o += NEPI) {   // second half: transpose from the dH2 image
-                const int b = o & 63, c = o >> 6;
-                sDT[timg_off(c, b)] = sH2[img_off(b, 128 + c, 256)];
-            }
-            stamp(it);
-            RL_STAGE({ const uint32_t idesc = make_idesc(128, 128, 0, 0);                  // dW2 half 1, then dH1 = dH2 W2
-                       for (int ks = 0; ks < 8; ++ks)
-                           mma_tf32(T_DW2 + 128, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aH1 + ks * TP_KSTEP), idesc, (it | ks) != 0);
-                       stream_gemm(T_WORK, aH2, 256, 8, 32, 64, 128); });
-            gather_load(xr, P.rp.obs + ring * RL_K1, idx);   // X rows again (for the X^T image), hidden behind the dH1 MMAs
-            // ---- dH1 epilogue: mask by H1 > 0 (from H1^T), write dH1^T in place of H1^T ----
-            wait_done(); stamp(it);
-            for (int cb = 0; cb < 2; ++cb) {
-                const int c0 = half * 64 + cb * 32;
-                float v[32];
-                tmem_ld32(T_WORK + t_lane + c0, v);
-                tmem_wait_ld();
-                if (rvalid) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float* p = sH1T + timg_off(c0 + j, row);
-                        *p = *p > 0.f ? to_tf32(v[j]) : 0.f;
-                    }
-                }
-            }
-            fence_before();
-            epi_bar();
-            if (threadIdx.x < 128) {                           // db1[k1] += sum_b dH1^T[k1][b]
-                const int k1 = threadIdx.x;
-                float s = 0.f;
-                for (int i = 0; i < R; ++i) { const int b = (i + ((k1 >> 3) & 3)) & 63; s += sH1T[timg_off(k1, b)]; }
-                red_add(G + L::OFF_B1 + k1, s);
-            }
-            stamp(it);
-            gather_store<true>(sXT, xr);                      // X^T image for dW1^T (dH2 region is dead: dH1 MMAs are done)
-            stamp(it);
-            RL_STAGE({ const uint32_t idesc = make_idesc(128, 160, 0, 0);                  // dW1^T = dH1^T X
-                       for (int ks = 0; ks < 8; ++ks)
-                           mma_tf32(T_WORK, desc_timg(aH1T + ks * TP_KSTEP), desc_timg(aXT + ks * TP_KSTEP), idesc, ks != 0); });
-            if (more)                                         // next event's target-net input, hidden behind the dW1 MMAs
-                gather_load(xr, P.rp.next_obs + ring_next * RL_K1, meta + ((it + 1) & 1) * 256);
-            // ---- dW1^T epilogue: slab region W1 is kept [k1][kx] (160 per row) so each thread adds 16-byte vectors ----
-            wait_done(); stamp(it);
-            if (more) gather_store<false>(sX, xr);            // sX (dH1^T) is free: the dW1 MMAs have completed
-            {
-                const int k1 = q * 32 + lane;                   // M = 128 accumulator: row = lane
-                float* gr = G + L::OFF_W1T + k1 * RL_K1;
-                for (int cb = half; cb < 5; cb += 2) {           // 5 column blocks of 32 split over the two warp halves
-                    float v[32];
-                    tmem_ld32(T_WORK + ((uint32_t)(q * 32) << 16) + cb * 32, v);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) red_add4(gr + cb * 32 + j4 * 4, v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-                }
-            }
-            fence_before();
-            epi_bar();
-            stamp(it);
-        }
-        // ---- flush the TMEM-resident dW2 accumulator once ----
-        if (n_my > 0) {
-            // all MMAs of the last event completed (dW1^T's `done` was the last commit)
-            const int k1 = q * 32 + lane;
-            for (int cb = 0; cb < 4; ++cb) {
-                const int c0 = half * 128 + cb * 32;
-                float v[32];
-                tmem_ld32(T_DW2 + ((uint32_t)(q * 32) << 16) + c0, v);
-                tmem_wait_ld();
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4)
-                    *reinterpret_cast<float4*>(G + L::OFF_W2T + k1 * 256 + c0 + j4 * 4) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-            }
-        }
-    }
-    fence_before();
-    __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem, 512);
-}
 
 // =====================================================================================================
 // k_learn_dueling_tc2 -- the same train() event with every activation GEMM in TRANSPOSED-OUTPUT form:
 //   D[feature][batch] = W[feature][k] * Act[batch][k]^T   (A = weight chunk, M = 128 features; B = activation image, N = 64 rows)
 // so that (1) every MMA runs at M = 128 (full tensor rate, M = 64 runs at half), (2) the TMEM epilogues own one FEATURE
-// per lane -- all 32 lanes of all 8 warps carry data (the M = 64 accumulator layout of k_learn_dueling_tc fills 16 of 32),
+// per lane -- all 32 lanes of all 8 warps carry data (an M = 64 accumulator layout fills 16 of 32),
 // bias is a per-thread scalar, bias gradients are per-thread sums, (3) the feature-major images the weight-gradient GEMMs
 // need (H1^T, dH2^T, dH1^T) are written with 16-byte vector stores, and the batch-major images the next layer needs
 // (H1, H2, dH2 as B operands) by conflict-free scalar scatters into images with a padded chunk stride (LBO = 144 B).
-// Same inputs, outputs, weight images, chunk schedule and per-CTA gradient slabs as k_learn_dueling_tc.
 // =====================================================================================================
 constexpr int NS2 = 4;                                  // weight-chunk stages
 constexpr int V2_X = 0;                                 // X' / X [64][160] plain image -> H1^T / dH1^T timg [128][64]   10240
@@ -1172,7 +772,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
     __half* sH1 = reinterpret_cast<__half*>(smem_raw + HB_H1);
     __half* sH2 = reinterpret_cast<__half*>(smem_raw + HB_H2);
     __half* sH1T = sX;         // H1^T / dH1^T (feature-major) live in the X region once the eval L1 MMAs are done
-    __half* sDT = sH1;         // the full dH2^T image [256][64] lives in the (double-size) H1 region once the eval L2 MMAs are done
+    // (H2^T, then the full dH2^T image [256][64], live in the double-size H1 region once the eval L2 MMAs are done)
     __half* sXT = reinterpret_cast<__half*>(smem_raw + HB_XT);
     __half* sStage = reinterpret_cast<__half*>(smem_raw + HB_STAGE);
     __half* sDout = reinterpret_cast<__half*>(smem_raw + HB_DOUT);
@@ -1658,7 +1258,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_act_dueling_tc(const TcActParam
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* sm = reinterpret_cast<float*>(smem_raw);
     float* sX = sm + SM_X; float* sH1 = sm + SM_H1; float* sH2 = sm + SM_H2;
-    float* sStage = sm + SM_STAGE; float* sOuth = sm + SM_OUTH;
+    float* sStage = sm + SM_STAGE;
     float* bias = sm + SM_SMALL;                           // b1[128] b2[256] bh[16]
     int* ids = reinterpret_cast<int*>(sm + SM_INT);        // [2][64] row ids of the current / next tile
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_FLOATS);
@@ -1934,24 +1534,14 @@ int rl_brain_learn_tc(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t
         RL_CUDA_CHECK(cudaMemsetAsync(trace_dev, 0, sizeof(long long) * 8 * 40, (cudaStream_t)stream));
         P.trace = trace_dev;
     }
-    static bool attr = false;
-    if (!attr) {
-        RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dueling_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-        attr = true;
+    static bool attr2 = false;
+    if (!attr2) {
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dueling_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM));
+        attr2 = true;
     }
     const int n_cta = rl_learn_grid();
     cudaStream_t st = (cudaStream_t)stream;
-    static const bool use_v1 = getenv("RL_TC_V1") != nullptr;      // M = 64 batch-major formulation (kept for A/B runs)
-    if (use_v1) {
-        k_learn_dueling_tc<<<n_cta, NTHREADS, TC_SMEM, st>>>(P);
-    } else {
-        static bool attr2 = false;
-        if (!attr2) {
-            RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dueling_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM));
-            attr2 = true;
-        }
-        k_learn_dueling_tc2<<<n_cta, NTHREADS2, TC2_SMEM, st>>>(P);
-    }
+    k_learn_dueling_tc2<<<n_cta, NTHREADS2, TC2_SMEM, st>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
     if (tracing) {
         long long h[8 * 40];

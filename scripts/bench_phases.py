@@ -6,7 +6,7 @@ import reinlife_b200 as rl
 from reinlife_b200.Models import PERD3QN
 torch.manual_seed(0)
 brains = [PERD3QN(exploration=0, capacity=2000), PERD3QN(exploration=0, capacity=2000)]
-env = rl.Environment(width=30, height=30, brains=brains, max_agents=100, print_results=False, training=True, n_worlds=4096, seed=0, precision=os.environ.get("RL_PRECISION", "tf32"))
+env = rl.Environment(width=30, height=30, brains=brains, max_agents=100, print_results=False, training=True, n_worlds=4096, seed=0, precision=os.environ.get("RL_PRECISION", "fp16"))
 env.reset(); env.top_up(100)
 names = ["act", "step", "learn", "update", "top_up"]
 tot = {k: 0.0 for k in names}
