@@ -51,7 +51,12 @@ def workload_name(args):
 # ----------------------------------------------------------------------------------------------- reference arm
 def cpu_arm(args, steps, warmup, procs=None):
     from oracle import cpu_port
-    procs = procs or (os.cpu_count() or 1)
+    if not procs:
+        try:
+            procs = len(os.sched_getaffinity(0))          # the cores this process may actually use (cgroup / taskset aware)
+        except AttributeError:
+            procs = os.cpu_count() or 1
+        procs = max(1, min(procs, 128))                   # bounded: one python + torch worker process per core
     a, sec = cpu_port.run_parallel(procs, args.cpu_worlds_per_core, steps, warmup, seed=0, capacity=args.capacity,
                                    exploration=0, train_freq=20, saturate_to=TARGET)
     sample = (f"{procs} single-thread processes x {args.cpu_worlds_per_core} worlds x {steps} steps "
