@@ -361,6 +361,9 @@ int rl_brain_learn_tc(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t
  * significant bits as tf32, K = 16 per instruction, half the operand bytes).  `wimg_*_h` are fp16 weight images of
  * rl_tc_wimg_floats() HALVES each, built by rl_brain_build_wimg_h.  Same contract and outputs as rl_brain_learn_tc. */
 int rl_brain_build_wimg_h(int32_t kind, const float* params, void* wimg_h, void* stream);
+/* get_action of ONE dueling brain with fp16 operands (same contract as rl_brain_act_tc, fp16 weight image) */
+int rl_brain_act_h(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_rows_bufs* rows, int32_t gene,
+                   const rl_brain_act* brain, const void* wimg_eval_h, uint64_t t_act, float* q_out, void* stream);
 int rl_brain_learn_h(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
                      const int32_t* sample_idx, const rl_learn_bufs* learn, const void* wimg_eval_h, const void* wimg_target_h,
                      void* stream);

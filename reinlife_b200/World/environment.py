@@ -174,9 +174,14 @@ class Environment:
                     b._dev.build_wimg(w._stream())
                     b._dev.wimg_stale = False
                     self.gpu_launches += 2
-                _lib.check(w.lib.rl_brain_act_tc(C.byref(w.cfg), C.byref(w.bufs), C.byref(self.rows.bufs), C.c_int32(g),
-                                                 C.byref(self._act_descs[g]), C.c_void_p(b._dev.wimg_e.data_ptr()),
-                                                 C.c_uint64(w.t + 1), C.c_void_p(q_out), w._stream()))
+                if self._learn_fp16:                     # fp16 operands, issuer-warp pipeline (k_act_dueling_h)
+                    _lib.check(w.lib.rl_brain_act_h(C.byref(w.cfg), C.byref(w.bufs), C.byref(self.rows.bufs), C.c_int32(g),
+                                                    C.byref(self._act_descs[g]), C.c_void_p(b._dev.wimg_eh.data_ptr()),
+                                                    C.c_uint64(w.t + 1), C.c_void_p(q_out), w._stream()))
+                else:
+                    _lib.check(w.lib.rl_brain_act_tc(C.byref(w.cfg), C.byref(w.bufs), C.byref(self.rows.bufs), C.c_int32(g),
+                                                     C.byref(self._act_descs[g]), C.c_void_p(b._dev.wimg_e.data_ptr()),
+                                                     C.c_uint64(w.t + 1), C.c_void_p(q_out), w._stream()))
         self.gpu_launches += 4 + G
 
     def learn(self, n_epi: int = 0):

@@ -1210,6 +1210,244 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
     if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
+// =====================================================================================================
+// k_act_dueling_h -- brain.get_action for the dueling brains with the structure of k_learn_dueling_h: fp16 operands,
+// transposed-output GEMMs (M = 128 features, N = 64 rows of a tile of the brain's ALL list), producer warp + two MMA
+// issuers + eight epilogue warps, the NEXT tile's L1^T issued one tile ahead (its rows are gathered behind the L2^T stage).
+// Epilogue = k_brain_act's: per-row dueling combine at B = 1 (PERD3QN.py:202), first-max argmax, exploration draws keyed
+// (t_act, slot) (PERD3QN.py:204-210), rec[].action.
+// =====================================================================================================
+struct TcActParams {
+    rl_world_cfg cfg;
+    rl_agent_rec* rec;
+    const float* obs;          // obs_state
+    const int32_t* rows;       // row list of this brain, kind ALL
+    const int32_t* total;      // device scalar
+    const float* params;       // biases are read from the kernel-layout buffer
+    const float* wimg;
+    const double* epsilon;
+    uint64_t t_act;
+    float* q_out;              // [row_cap][8] or null
+};
+constexpr int ACT_SCHED_N = 14;
+constexpr int AB_X = 0;                                 // X plain [64][160] (20480 B)
+constexpr int AB_H1 = AB_X + 20480;                     // H1 bimg [64][128] (18432 B)
+constexpr int AB_H2 = AB_H1 + 18432;                    // H2 bimg [64][256] (36864 B)
+constexpr int AB_STAGE = AB_H2 + 36864;
+constexpr int AB_BIAS = AB_STAGE + NSH * HCHUNK * 2;    // b1[128] b2[256] bh[16] floats
+constexpr int AB_IDS = AB_BIAS + 4 * 400;               // [2][64] row ids
+constexpr int AB_BARS = AB_IDS + 4 * 128;
+constexpr size_t ACTH_SMEM = AB_BARS + 8 * (2 * NSH + 3) + 16;
+static_assert(ACTH_SMEM <= 227 * 1024 && AB_BARS % 8 == 0, "shared memory budget");
+
+struct TcActParamsH {
+    TcActParams p;
+    const __half* wimg;
+};
+
+__global__ void __launch_bounds__(NTHREADS2, 1) k_act_dueling_h(const TcActParamsH PH) {
+    using L = Layout<RL_MODEL_DUELING>;
+    const TcActParams& P = PH.p;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __half* sX = reinterpret_cast<__half*>(smem_raw + AB_X);
+    __half* sH1 = reinterpret_cast<__half*>(smem_raw + AB_H1);
+    __half* sH2 = reinterpret_cast<__half*>(smem_raw + AB_H2);
+    __half* sStage = reinterpret_cast<__half*>(smem_raw + AB_STAGE);
+    float* bias = reinterpret_cast<float*>(smem_raw + AB_BIAS);
+    int* ids = reinterpret_cast<int*>(smem_raw + AB_IDS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + AB_BARS);
+    uint64_t* full = bars; uint64_t* empty = bars + NSH; uint64_t* done = bars + 2 * NSH; uint64_t* doneL1 = done + 1; uint64_t* go = done + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 3);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = *P.total;
+    const int n_tiles = (total + R - 1) / R;
+    const int n_my = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSH; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); }
+        mbar_init(done, 2); mbar_init(doneL1, 1); mbar_init(go, NEPI);
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 256);
+    if (threadIdx.x < NEPI)
+        for (int i = threadIdx.x; i < 400; i += NEPI) {
+            const int o = i < 128 ? L::OFF_B1 + i : i < 384 ? L::OFF_B2 + (i - 128) : L::OFF_BH + (i - 384);
+            bias[i] = i < 384 + 9 ? P.params[o] : 0.f;
+        }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t T_WORK = tmem, T_L1 = tmem + 192;
+    const int S = P.cfg.slot_cap;
+    const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH2 = smem_u32(sH2);
+
+    if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t n_chunks = (uint32_t)n_my * ACT_SCHED_N;
+            for (uint32_t produced = 0; produced < n_chunks; ++produced) {
+                const uint32_t slot = produced % NSH;
+                if (produced >= NSH) mbar_wait(&empty[slot], ((produced / NSH) - 1) & 1);
+                // consumption order of a tile: L2^T (W2K x 8), head (WH), then the NEXT tile's L1^T (W1 x 5); the very first
+                // tile's L1^T chunks lead the stream
+                const uint32_t i = produced % ACT_SCHED_N;
+                const int ch = i < 5 ? WI_W1 + (int)i : i < 13 ? WI_W2K + (int)(i - 5) : WI_WH;
+                bulk_load(sStage + slot * HCHUNK, PH.wimg + (size_t)ch * HCHUNK, HCHUNK * 2, &full[slot]);
+            }
+        }
+    } else if (warp == 9 || warp == 10) {
+        if (lane == 0) {
+            const int role = warp - 9;
+            uint32_t consumed = 0, go_no = 0;
+            auto wait_go = [&]() { mbar_wait(go, go_no & 1); ++go_no; fence_after(); };
+            auto chunk_wait = [&]() -> uint32_t {
+                const uint32_t slot = consumed % NSH;
+                mbar_wait(&full[slot], (consumed / NSH) & 1);
+                fence_after();
+                return smem_u32(sStage + slot * HCHUNK);
+            };
+            auto chunk_release = [&]() { mma_commit(&empty[consumed % NSH]); ++consumed; };
+            auto chunk_skip = [&](int n) { for (int i = 0; i < n; ++i) { (void)chunk_wait(); mbar_arrive(&empty[consumed % NSH]); ++consumed; } };
+            auto l1 = [&]() {
+                if (role == 1) { chunk_skip(5); return; }
+                const uint32_t idesc = make_idesc_h(128, 64);
+                uint64_t b_desc = desc_hplain(aX, RL_K1);
+#pragma unroll 1
+                for (int c = 0; c < 5; ++c) {
+                    chunk_mmas_h<2>(T_L1, desc_hplain(chunk_wait(), 32), b_desc, 16u, idesc, c != 0);
+                    b_desc += 32u;
+                    chunk_release();
+                }
+                mma_commit(doneL1);
+            };
+            for (int it = 0; it < n_my; ++it) {
+                if (it == 0) { wait_go(); l1(); }
+                wait_go();                                        // L2^T: issuer r takes feature half r
+                {
+                    const uint32_t idesc = make_idesc_h(128, 64);
+                    uint64_t b_desc = desc_hbimg(aH1, 128);
+                    const uint32_t a_off = role ? 4096u : 0u;
+#pragma unroll 1
+                    for (int c = 0; c < 8; ++c) {
+                        chunk_mmas_h<1>(T_WORK + role * 64, desc_hplain(chunk_wait() + a_off, 16), b_desc, 18u, idesc, c != 0);
+                        b_desc += 18u;
+                        chunk_release();
+                    }
+                    mma_commit(done);
+                }
+                wait_go();                                        // head (M = 64): issuer r takes k-steps 8r..8r+7 into columns 16r..
+                {
+                    const uint32_t b_base = chunk_wait();
+                    const uint32_t idesc = make_idesc_h(64, 16);
+                    uint64_t a_desc = desc_hbimg(aH2 + role * 8 * 288, 256), b_desc = desc_hplain(b_base + role * 8 * 256, 256);
+#pragma unroll 1
+                    for (int ks = 0; ks < 8; ++ks) { mma_f16(T_WORK + role * 16, a_desc, b_desc, idesc, ks != 0); a_desc += 18u; b_desc += 16u; }
+                    chunk_release();
+                    mma_commit(done);
+                }
+                if (it + 1 < n_my) { wait_go(); l1(); }           // next tile's L1^T (runs under this tile's head epilogue)
+            }
+        }
+    } else {
+        uint32_t done_no = 0, l1_no = 0;
+        const int q = warp & 3, half = warp >> 2;
+        const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+        const int f1 = q * 32 + lane, f2 = half * 128 + f1;
+        const int row64 = q * 16 + lane;
+        const bool rvalid = lane < 16;
+        auto go_signal = [&]() { fence_proxy_async(); fence_before(); mbar_arrive(go); };
+        auto wait_done = [&]() { mbar_wait(done, done_no & 1); ++done_no; fence_after(); };
+        auto wait_l1 = [&]() { mbar_wait(doneL1, l1_no & 1); ++l1_no; fence_after(); };
+        auto load_ids = [&](int b, int tile) {           // rows past `total` read row 0 (results discarded)
+            if (threadIdx.x >= NEPI - R) {
+                const int r = threadIdx.x - (NEPI - R), i = tile * R + r;
+                ids[b * R + r] = i < total ? P.rows[i] : 0;
+            }
+        };
+        float4 xr[10];
+        if (n_my > 0) {
+            load_ids(0, blockIdx.x);
+            if (n_my > 1) load_ids(1, blockIdx.x + gridDim.x);
+            epi_bar();
+            gather_load(xr, P.obs, ids);
+            gather_store_h<false>(sX, xr);
+            go_signal();                                          // -> L1^T of the first tile
+        }
+        const double epsilon = *P.epsilon;
+        for (int it = 0; it < n_my; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const bool more = it + 1 < n_my;
+            // this tile's row id is read before the first `go` arrival: the id buffer is recycled (for tile it+2) only by threads
+            // that have seen the L2^T `done`, i.e. after all 256 arrivals
+            const int rid = ids[(it & 1) * R + (row64 & 63)];
+            wait_l1();
+            {   // L1 epilogue: lane = feature k1, this warp's 32 rows; H1 = relu(D + b1) -> batch-major image
+                float v[32];
+                tmem_ld32(T_L1 + t_lane + half * 32, v);
+                tmem_wait_ld();
+                const float b1 = bias[f1];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sH1[hbimg_off(half * 32 + j, f1, 128)] = __float2half_rn(fmaxf(v[j] + b1, 0.f));
+            }
+            go_signal();                                          // -> L2^T
+            if (more) gather_load(xr, P.obs, ids + ((it + 1) & 1) * R);   // next tile's rows, hidden behind L2^T and the head
+            wait_done();
+            {   // L2 epilogue: lane = feature n2, all 64 rows; H2 = relu(D + b2) -> batch-major image
+                const float b2 = bias[128 + f2];
+#pragma unroll
+                for (int cb = 0; cb < 2; ++cb) {
+                    float v[32];
+                    tmem_ld32(T_WORK + t_lane + half * 64 + cb * 32, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sH2[hbimg_off(cb * 32 + j, f2, 256)] = __float2half_rn(fmaxf(v[j] + b2, 0.f));
+                }
+            }
+            go_signal();                                          // -> head
+            if (more) {                                           // sX is free since this tile's L1^T completed
+                gather_store_h<false>(sX, xr);
+                if (it + 2 < n_my) load_ids(it & 1, tile + 2 * gridDim.x);
+            }
+            wait_done();
+            if (more) go_signal();                                // -> next tile's L1^T (runs under the head epilogue below)
+            if (half == 0) {
+                float v[16], v2[16];
+                tmem_ld16(T_WORK + t_lane, v);
+                tmem_ld16(T_WORK + t_lane + 16, v2);
+                tmem_wait_ld();
+                const int i = tile * R + row64;
+                if (rvalid && i < total) {
+                    float qv[8], ssum = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { qv[j] = (v[j] + v2[j]) + bias[384 + j]; ssum += qv[j]; }
+                    const float val = (v[8] + v2[8]) + bias[384 + 8], mean = ssum * 0.125f;     // B = 1: per-row mean (PERD3QN.py:202)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) qv[j] = qv[j] + val - mean;
+                    int best = 0;
+#pragma unroll
+                    for (int j = 1; j < 8; ++j) if (qv[j] > qv[best]) best = j;                   // first maximum
+                    const int w = rid / S, slot = rid - w * S;
+                    const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
+                    int a = best;                                                                  // PERD3QN.py:204-210
+                    const double u = rl_uniform(rl_draw(key, P.t_act, RL_SITE_ACT_EXPLORE, (uint32_t)slot));
+                    if (!(u > epsilon)) a = (int)rl_below(rl_draw(key, P.t_act, RL_SITE_ACT_RANDOM, (uint32_t)slot), 8);
+                    reinterpret_cast<int8_t*>(P.rec + rid)[13] = (int8_t)a;
+                    if (P.q_out) {
+                        float4* qo = reinterpret_cast<float4*>(P.q_out + (size_t)i * 8);
+                        qo[0] = make_float4(qv[0], qv[1], qv[2], qv[3]);
+                        qo[1] = make_float4(qv[4], qv[5], qv[6], qv[7]);
+                    }
+                }
+            }
+            fence_before();
+            epi_bar();
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 256);
+}
+
 // fp16 weight images: the chunk shapes and order of the tf32 images, 4096 halves (8 KB) per chunk
 __global__ void k_build_wimg_dueling_h(const float* __restrict__ p, __half* __restrict__ wimg) {
     using L = Layout<RL_MODEL_DUELING>;
@@ -1239,19 +1477,6 @@ __global__ void k_build_wimg_dueling_h(const float* __restrict__ p, __half* __re
 // MMAs, the next tile's observation rows are gathered into registers behind the L2 stage.  The epilogue is the one of
 // k_brain_act (per-row dueling combine at B = 1, first-max argmax, exploration draws keyed (t_act, slot)).
 // =====================================================================================================
-struct TcActParams {
-    rl_world_cfg cfg;
-    rl_agent_rec* rec;
-    const float* obs;          // obs_state
-    const int32_t* rows;       // row list of this brain, kind ALL
-    const int32_t* total;      // device scalar
-    const float* params;       // biases are read from the kernel-layout buffer
-    const float* wimg;
-    const double* epsilon;
-    uint64_t t_act;
-    float* q_out;              // [row_cap][8] or null
-};
-constexpr int ACT_SCHED_N = 14;
 
 __global__ void __launch_bounds__(NTHREADS, 1) k_act_dueling_tc(const TcActParams P) {
     using L = Layout<RL_MODEL_DUELING>;
@@ -1510,6 +1735,31 @@ int rl_brain_act_tc(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl
         attr = true;
     }
     k_act_dueling_tc<<<rl_learn_grid(), NTHREADS, TC_SMEM, (cudaStream_t)stream>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_brain_act_h(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_rows_bufs* rows, int32_t gene,
+                   const rl_brain_act* brain, const void* wimg_eval_h, uint64_t t_act, float* q_out, void* stream) {
+    RL_ARG_CHECK(cfg && bufs && rows && brain && wimg_eval_h);
+    RL_ARG_CHECK(gene >= 0 && gene < cfg->n_genes && cfg->obs_ld == RL_K1);
+    RL_ARG_CHECK(bufs->rec && bufs->obs_state && brain->params && brain->epsilon);
+    if (brain->kind != RL_MODEL_DUELING || brain->rule != RL_ACT_DUELING)
+        return rl_set_err(RL_ERR_UNSUPPORTED, "rl_brain_act_h: dueling networks only");
+    TcActParamsH PH;
+    TcActParams& P = PH.p;
+    P.cfg = *cfg; P.rec = bufs->rec; P.obs = bufs->obs_state;
+    P.rows = rows->rows + (size_t)(gene * RL_N_ROW_KINDS + RL_ROWS_ALL) * rows->row_cap;
+    P.total = rows->total + gene * RL_N_ROW_KINDS + RL_ROWS_ALL;
+    P.params = brain->params; P.wimg = nullptr; P.epsilon = brain->epsilon; P.t_act = t_act;
+    P.q_out = q_out ? q_out + (size_t)gene * rows->row_cap * 8 : nullptr;
+    PH.wimg = reinterpret_cast<const __half*>(wimg_eval_h);
+    static bool attr = false;
+    if (!attr) {
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_act_dueling_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACTH_SMEM));
+        attr = true;
+    }
+    k_act_dueling_h<<<rl_learn_grid(), NTHREADS2, ACTH_SMEM, (cudaStream_t)stream>>>(PH);
     RL_CUDA_CHECK(cudaGetLastError());
     return RL_OK;
 }

@@ -107,7 +107,7 @@ def test_tensor_core_learn_matches_fp32_learn():
 
 
 def test_tensor_core_act_matches_fp32_act():
-    """rl_brain_act_tc (tcgen05 tf32 forward) vs rl_brain_act_all (fp32 FMA) on real observations with the pretrained
+    """rl_brain_act_tc (tcgen05 tf32 forward) and rl_brain_act_h (fp16 operands) vs rl_brain_act_all (fp32 FMA) on real observations with the pretrained
     PERD3QN weights: Q values within 2e-2 of the Q scale, >= 99% identical greedy actions, identical exploration draws
     (epsilon = 0.3: wherever the fp32 path explored, both paths pick the same random action)."""
     from brain_golden_util import golden, state_dict
@@ -128,7 +128,7 @@ def test_tensor_core_act_matches_fp32_act():
     eps = torch.tensor([0.3, 0.0], dtype=torch.float64, device="cuda")
     descs = (_lib.BrainAct * 2)(*[b.act_desc(_lib.ACT_DUELING, eps.data_ptr() + 8 * i) for i, b in enumerate(brains)])
     out = {}
-    for mode in ("fp32", "tf32"):
+    for mode in ("fp32", "tf32", "fp16"):
         q = torch.zeros((2, rows.row_cap, 8), device="cuda")
         vw.rec[:, :, 13] = 255
         if mode == "fp32":
@@ -136,20 +136,27 @@ def test_tensor_core_act_matches_fp32_act():
                                                C.c_void_p(q.data_ptr()), None, vw._stream()))
         else:
             for i, b in enumerate(brains):
+                b.use_fp16 = mode == "fp16"
                 b.build_wimg(vw._stream())
-                _lib.check(vw.lib.rl_brain_act_tc(C.byref(vw.cfg), C.byref(vw.bufs), C.byref(rows.bufs), i, C.byref(descs[i]),
-                                                  C.c_void_p(b.wimg_e.data_ptr()), C.c_uint64(7), C.c_void_p(q.data_ptr()), vw._stream()))
+                if mode == "tf32":
+                    _lib.check(vw.lib.rl_brain_act_tc(C.byref(vw.cfg), C.byref(vw.bufs), C.byref(rows.bufs), i, C.byref(descs[i]),
+                                                      C.c_void_p(b.wimg_e.data_ptr()), C.c_uint64(7), C.c_void_p(q.data_ptr()), vw._stream()))
+                else:
+                    _lib.check(vw.lib.rl_brain_act_h(C.byref(vw.cfg), C.byref(vw.bufs), C.byref(rows.bufs), i, C.byref(descs[i]),
+                                                     C.c_void_p(b.wimg_eh.data_ptr()), C.c_uint64(7), C.c_void_p(q.data_ptr()), vw._stream()))
         torch.cuda.synchronize()
         out[mode] = (q.cpu().numpy(), vw.rec[:, :, 13].cpu().numpy().view(np.int8).copy())
-    n_tot = 0
-    for i in range(2):
-        n = int(rows.total[i * 3])
-        n_tot += n
-        q32, qtc = out["fp32"][0][i, :n], out["tf32"][0][i, :n]
-        assert n > 500 and np.abs(q32).max() > 1.0
-        assert np.abs(q32 - qtc).max() < 2e-2 * np.abs(q32).max()
-        assert (q32.argmax(1) == qtc.argmax(1)).mean() >= 0.99
-    a32, atc = out["fp32"][1], out["tf32"][1]
+    a32 = out["fp32"][1]
     listed = a32 != -1
-    assert listed.sum() == n_tot and ((atc != -1) == listed).all()
-    assert (a32[listed] == atc[listed]).mean() >= 0.99
+    for mode in ("tf32", "fp16"):
+        n_tot = 0
+        for i in range(2):
+            n = int(rows.total[i * 3])
+            n_tot += n
+            q32, qtc = out["fp32"][0][i, :n], out[mode][0][i, :n]
+            assert n > 500 and np.abs(q32).max() > 1.0
+            assert np.abs(q32 - qtc).max() < 2e-2 * np.abs(q32).max(), mode
+            assert (q32.argmax(1) == qtc.argmax(1)).mean() >= 0.99, mode
+        atc = out[mode][1]
+        assert listed.sum() == n_tot and ((atc != -1) == listed).all(), mode
+        assert (a32[listed] == atc[listed]).mean() >= 0.99, mode
