@@ -256,9 +256,10 @@ def run_b200(args):
                                          + {"fp16": "tcgen05 kind::f16 (fp16 operands), TMEM accumulators; peak = measured sustained bf16/fp16 tensor peak",
                                             "tf32": "tcgen05 kind::tf32, TMEM accumulators; peak shown is the measured sustained bf16 tensor peak (tf32 dense is half of it)",
                                             "fp32": "fp32 FMA on CUDA cores (reference precision); peak shown is the bf16 tensor peak"}[args.precision])},
-        "act(k_act_dueling_tc x2 + rows)": {"bound": "tensor", "ms": phases["act"], "achieved": NW * n_avg * 107008 / phases["act"] / 1e9,
-                                            "peak": bf16_peak, "unit": "TFLOP/s",
-                                            "note": "tcgen05 kind::tf32 forward" if args.precision in ("tf32", "fp16") else "fp32 FMA on CUDA cores"},
+        "act(get_action kernels x2 + row lists)": {"bound": "tensor", "ms": phases["act"], "achieved": NW * n_avg * 107008 / phases["act"] / 1e9,
+                                                   "peak": bf16_peak, "unit": "TFLOP/s",
+                                                   "note": {"fp16": "k_act_dueling_h, tcgen05 kind::f16", "tf32": "k_act_dueling_tc, tcgen05 kind::tf32",
+                                                            "fp32": "k_brain_act, fp32 FMA on CUDA cores"}[args.precision]},
     }
     for v in roof_k.values():
         v["frac"] = v["achieved"] / v["peak"]
@@ -268,7 +269,7 @@ def run_b200(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp16": "fp16 operands in the train() events, tf32 in get_action (both 11 significant bits), fp32 accumulate; world state exact integers, Adam fp32",
+            "dtype": {"fp16": "fp16 operands (11 significant bits, like tf32) in get_action and the train() events, fp32 accumulate; world state exact integers, Adam fp32",
                       "tf32": "tf32 (tensor-core forward/backward products, fp32 accumulate; world state exact integers, Adam fp32)", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": workload_name(args), "grid": [H, W], "worlds_total": n_worlds, "agents_per_world": n_avg,
                        "train_events_per_step_per_gpu": ev_avg, "parallelism": f"worlds sharded x{world_size}, brains replicated, "
