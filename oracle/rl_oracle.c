@@ -102,7 +102,6 @@ static int set_random_cell(World* w, uint64_t place_bits, int use_accept, uint64
     return cell;
 }
 
-static int wrap(int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); }
 
 static void neighbour(const World* w, int i, int j, int dir, int* oi, int* oj) {
     /* up = i-1, right = j+1, down = i+1, left = j-1, toroidal -- environment.py:601-623,664-689 */
