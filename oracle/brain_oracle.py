@@ -289,3 +289,132 @@ def ppo_epoch_grads(sd, obs, action, reward, next_obs, prob_a, done, gamma=0.98,
     d_h2 = d_logits @ _t(sd["fc_pi.weight"]) + d_v[:, None] @ _t(sd["fc_v.weight"])
     grads.update(_mlp3_backward(sd, names, x, h1, h2, d_h2))
     return {k: v_.numpy() for k, v_ in grads.items()}, float(loss)
+
+
+# ------------------------------------------------------------------ PERDQN (Models/PERDQN.py)
+PERDQN_NAMES = ("fc.0", "fc.2", "fc.4")          # nn.Sequential indices of the three Linear layers (PERDQN.py:314-320)
+
+
+def perdqn_forward(sd, x):
+    """DQN.forward, PERDQN.py:311-323: 153 -> 64 -> 64 -> 8, ReLU between."""
+    _, _, h2 = _mlp3_parts(sd, x, PERDQN_NAMES[:2])
+    return lin(h2, sd["fc.4.weight"], sd["fc.4.bias"]).numpy()
+
+
+def perdqn_rule(q, eps, u, r_below8):
+    """get_action, PERDQN.py:101-111: np.random.rand() <= eps -> random.randrange(8), else torch.max(q, 1) index."""
+    return int(r_below8) if u <= eps else first_argmax(q)
+
+
+def perdqn_store_error(sd, sd_target, state, action, reward, next_state, done, gamma=0.99):
+    """append_sample, PERDQN.py:113-128.  `old_val = target[0][action]` is a VIEW of the tensor that the next lines
+    overwrite in place (`target[0][action] = reward [+ gamma * max Q_target(s')]`), so
+    `error = abs(old_val - target[0][action])` compares the new value with itself: the stored error is exactly 0 for every
+    transition, whatever the two B=1 forwards computed (pinned by the golden run: all 400 recorded errors are 0.0).
+    New items therefore always enter the tree with priority float32(0.01) ** 0.6."""
+    return np.zeros(len(np.asarray(action)), np.float32)
+
+
+def perdqn_priority(error_f32, e=0.01, a=0.6):
+    """Memory._get_priority, PERDQN.py:272-273.  The error reaches it as a float32 torch scalar (add, :126-128) or a
+    numpy float32 scalar (update, :168-174); with numpy >= 2 (NEP 50) `(abs(error) + 0.01) ** 0.6` stays float32 in both
+    cases (numpy 1.x promoted the numpy-scalar case to float64).  The tree then holds float64(float32 value)."""
+    # scalar by scalar, as the reference does: numpy's float32 SCALAR power is libm powf, its array power a SIMD routine
+    # that differs in the last bit for ~15% of the inputs
+    flat = np.asarray(error_f32, np.float32).reshape(-1)
+    out = np.array([(np.abs(x) + e) ** a for x in flat], np.float32)
+    return out.reshape(np.shape(error_f32))
+
+
+class SumTreeOracle:
+    """SumTree + Memory of PERDQN.py:198-308 without the python objects: `tree` float64 [2*capacity-1] with the
+    reference's incremental `+= change` propagation (so rounding matches), ring write pointer, n_entries, beta."""
+
+    def __init__(self, capacity, beta=0.4, beta_increment=0.001):
+        self.capacity = int(capacity)
+        self.tree = np.zeros(2 * self.capacity - 1)
+        self.write, self.n_entries = 0, 0
+        self.beta, self.beta_increment = beta, beta_increment
+
+    def update(self, idx, p):                      # SumTree.update + _propagate, :243-247, :211-218 (Memory.update path)
+        """`p` arrives as a numpy float32 scalar (train_model, :168-174): numpy-scalar arithmetic, float64 throughout."""
+        change = np.float64(p) - self.tree[idx]
+        self.tree[idx] = p
+        while idx != 0:
+            idx = (idx - 1) // 2
+            self.tree[idx] += change
+
+    def _update_f32(self, idx, p):
+        """The same two functions when `p` is a 0-d float32 torch tensor (Memory.add <- append_sample, :126-128):
+        `p - self.tree[idx]` and `self.tree[parent] += change` are then TENSOR operations (numpy defers to
+        Tensor.__rsub__/__radd__), i.e. float32 arithmetic on the float32-rounded node, stored back as float64."""
+        f = np.float32
+        change = f(f(p) - f(self.tree[idx]))
+        self.tree[idx] = np.float64(f(p))
+        while idx != 0:
+            idx = (idx - 1) // 2
+            self.tree[idx] = np.float64(f(f(self.tree[idx]) + change))
+
+    def add(self, p):                              # SumTree.add, :229-240; returns the data slot written
+        slot = self.write
+        self._update_f32(slot + self.capacity - 1, p)
+        self.write = (self.write + 1) % self.capacity
+        self.n_entries = min(self.capacity, self.n_entries + 1)
+        return slot
+
+    def retrieve(self, s):                         # SumTree._retrieve, :220-230, iterative
+        idx = 0
+        while True:
+            left = 2 * idx + 1
+            if left >= len(self.tree):
+                return idx
+            if s <= self.tree[left]:
+                idx = left
+            else:
+                s = s - self.tree[left]
+                idx = left + 1
+
+    def sample(self, n, next_u, max_tries=1 << 20):
+        """Memory.sample, :278-303.  `next_u()` returns the float of the next random.random() call
+        (random.uniform(a, b) = a + (b - a) * random()).  Returns (data slots, tree indices, is_weights float64)."""
+        total = self.tree[0]
+        segment = total / n
+        self.beta = float(np.min([1., self.beta + self.beta_increment]))
+        slots, idxs, prios = [], [], []
+        for i in range(n):
+            a, b = segment * i, segment * (i + 1)
+            for _ in range(max_tries):
+                s = a + (b - a) * next_u()
+                idx = self.retrieve(s)
+                slot = idx - self.capacity + 1
+                if slot < self.n_entries:          # `not isinstance(data, int)`: the slot has been written
+                    break
+            else:
+                raise RuntimeError("stratum without a filled leaf")
+            slots.append(slot); idxs.append(idx); prios.append(self.tree[idx])
+        probs = np.asarray(prios) / total
+        w = np.power(self.n_entries * probs, -self.beta)
+        w /= w.max()
+        return slots, idxs, w
+
+
+def perdqn_event_grads(sd, sd_target, obs, action, reward, next_obs, done, is_weights, gamma=0.99):
+    """train_model, PERDQN.py:130-186, given the sampled batch: (grads, loss, errors).  `F.mse_loss(pred, target)` is a
+    scalar mean there, so loss = mean_i(float32(is_w_i) * mse) and every row's gradient carries mean(float32(is_w))."""
+    B = len(action)
+    x, h1, h2 = _mlp3_parts(sd, obs, PERDQN_NAMES[:2])
+    q = lin(h2, sd["fc.4.weight"], sd["fc.4.bias"])
+    a = torch.as_tensor(np.asarray(action), dtype=torch.long)
+    pred = q.gather(1, a[:, None])[:, 0]
+    nmax = torch.as_tensor(perdqn_forward(sd_target, next_obs)).max(1)[0]
+    tgt = _t(reward) + (1 - _t(np.asarray(done, np.float32))) * gamma * nmax
+    errors = (pred - tgt).abs()
+    w = _t(np.asarray(is_weights, np.float32))
+    mse = ((pred - tgt) ** 2).mean()
+    loss = (w * mse).mean()
+    g_q = (w.sum() / B) * 2 * (pred - tgt) / B
+    d_out = torch.zeros(B, 8)
+    d_out[torch.arange(B), a] = g_q
+    grads = {"fc.4.weight": d_out.T @ h2, "fc.4.bias": d_out.sum(0)}
+    grads.update(_mlp3_backward(sd, PERDQN_NAMES[:2], x, h1, h2, d_out @ _t(sd["fc.4.weight"])))
+    return {k: v.numpy() for k, v in grads.items()}, float(loss), errors.numpy()
