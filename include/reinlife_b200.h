@@ -159,7 +159,8 @@ int rl_model_get_dims(int32_t kind, rl_model_dims* out);
 enum rl_act_rule {
     RL_ACT_DUELING = 0, /* u > eps ? argmax : choice(range(8))      Models/PERD3QN.py:204-210, D3QN.py:167-173 */
     RL_ACT_DQN = 1,     /* coin < eps ? randint(0,7) : argmax        Models/DQN.py:132-139                      */
-    RL_ACT_PPO = 2      /* inverse-CDF sample of softmax(pi)         Models/PPO.py:164-169                      */
+    RL_ACT_PPO = 2,     /* inverse-CDF sample of softmax(pi)         Models/PPO.py:164-169                      */
+    RL_ACT_PERDQN = 3   /* u <= eps ? randrange(8) : argmax          Models/PERDQN.py:101-111 (epsilon moves in train_model) */
 };
 
 typedef struct rl_brain_act {
@@ -268,6 +269,54 @@ int rl_brain_learn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t ge
  * trained; follow with rl_brain_adam -- five (sample, learn, adam) rounds make one train() call. */
 int rl_brain_learn_dqn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
                        const int32_t* sample_idx, const rl_learn_bufs* learn, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * PERDQN (Models/PERDQN.py).  Network 153-64-64-8 (:311-323) = RL_MODEL_DQN layout with the first hidden layer
+ * zero-padded from 64 to 128 units (padded weights have mask 0 and stay exactly 0).  Memory (:262-308) = the brain's
+ * rl_replay_bufs ring (prioritized = 0; pos = SumTree.write, len = n_entries) plus one SumTree per world:
+ * Sequence per learn step:
+ *     rl_sumtree_add -> rl_replay_store -> rl_sumtree_sample -> rl_brain_learn_perdqn -> [all-reduce grad] ->
+ *     rl_brain_adam -> rl_sumtree_update -> rl_perdqn_epsilon_step -> rl_brain_sync_target(cond = #EVENT rows)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rl_sumtree_bufs {            /* per brain */
+    double*  tree;          /* [n_worlds, 2*capacity-1] float64 nodes, zero-initialised; leaf of slot d = d+capacity-1 (:198-259) */
+    double*  beta;          /* [n_worlds] Memory.beta, initialised to 0.4, +0.001 per sample() up to 1 (:266-267,284) */
+    int32_t* status;        /* [1] sticky bit 0: a stratum needed more than 64 redraws (:290-295); may be NULL */
+    int32_t  capacity;      /* = replay->capacity */
+    int32_t  train_start;   /* train_model only once n_entries >= train_start (1000, :69,192) */
+    float    p_new;         /* priority of a new item = float32(0.01)**0.6: append_sample's error is always 0 (see
+                               csrc/sumtree_kernels.cu) */
+    int32_t  _pad;
+} rl_sumtree_bufs;
+
+/* Memory.add (:275-277, SumTree.add :229-240) for every STORE row of `gene`, agent order, float32 propagation of the
+ * reference's tensor path.  Call BEFORE rl_replay_store of the same step (it reads the ring's write position). */
+int rl_sumtree_add(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                   const rl_sumtree_bufs* tree, void* stream);
+
+/* Memory.sample(64) (:278-303) for every EVENT row of `gene`: stratified draws keyed (t, RL_SITE_SUMTREE_SAMPLE, ...),
+ * redraw while the leaf holds no data.  sample_idx [row_cap, 64] = data slots (-1 for events of a world whose memory
+ * holds < train_start items: no train_model call, :192); ev_weight [row_cap] = mean of float32(is_weight) of the event,
+ * the factor of loss = (is_weights * mse_loss(pred, target)).mean() (:182). */
+int rl_sumtree_sample(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                      const rl_sumtree_bufs* tree, int32_t batch, uint64_t t, int32_t* sample_idx, float* ev_weight,
+                      void* stream);
+
+/* train_model's forward/backward (:144-186) for every EVENT row: pred = model(s)[a], target = r + (1-done) * gamma *
+ * max target_model(s'), loss as above; errors |pred - target| -> learn->new_prio [row_cap, 64]; gradients summed over
+ * events into learn->grad, grad[n_train] = events that trained.  learn->kind = RL_MODEL_DQN, learn->batch = 64. */
+int rl_brain_learn_perdqn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                          const int32_t* sample_idx, const float* ev_weight, const rl_learn_bufs* learn, void* stream);
+
+/* Memory.update (:305-308) for the 64 sampled leaves of every trained event: event order, batch order, duplicates
+ * included, priority = powf(|error| + 0.01, 0.6), float64 propagation. */
+int rl_sumtree_update(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                      const rl_sumtree_bufs* tree, int32_t batch, const int32_t* sample_idx, const float* errors,
+                      void* stream);
+
+/* train_model's `if epsilon > epsilon_min: epsilon -= epsilon_decay` (:132-133), applied once per optimizer step that
+ * happened (learn->grad[n_train] > 0); eps_dev = the brain's device epsilon (rl_brain_act.epsilon). */
+int rl_perdqn_epsilon_step(const rl_learn_bufs* learn, double* eps_dev, double eps_min, double eps_decay, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * PPO (Models/PPO.py:62-77,113-162).  One python-list-like data buffer per (world, brain): `traj` (an rl_replay_bufs

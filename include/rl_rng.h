@@ -44,8 +44,9 @@ enum rl_rng_site {
     RL_SITE_ACT_RANDOM         = 21, /* [slot]  PERD3QN.py:209 / D3QN.py:172 / DQN.py:137     */
     RL_SITE_ACT_SAMPLE         = 22, /* [slot]  PPO.py:166-167 (inverse CDF on one uniform)   */
     RL_SITE_REPLAY_SAMPLE      = 30, /* [event_rank*batch + i]  PERD3QN.py:165 (np.random.choice, with replacement) */
-    RL_SITE_REPLAY_SAMPLE_UNIFORM = 31 /* [((event_rank*n_iter + iter) << 9) + c]  c-th _randbelow call of random.sample:
+    RL_SITE_REPLAY_SAMPLE_UNIFORM = 31,/* [((event_rank*n_iter + iter) << 9) + c]  c-th _randbelow call of random.sample:
                                           D3QN.py:140 (n_iter 1), DQN.py:100 inside the 5-iteration loop of DQN.py:143 */
+    RL_SITE_SUMTREE_SAMPLE     = 32  /* [((event_rank*64 + stratum) << 6) + redraw]  random.uniform of PERDQN.py:292 */
 };
 
 RL_HD uint64_t rl_mix64(uint64_t z) {

@@ -374,17 +374,18 @@ class SumTreeOracle:
                 s = s - self.tree[left]
                 idx = left + 1
 
-    def sample(self, n, next_u, max_tries=1 << 20):
+    def sample(self, n, next_u=None, max_tries=1 << 20, indexed_u=None):
         """Memory.sample, :278-303.  `next_u()` returns the float of the next random.random() call
-        (random.uniform(a, b) = a + (b - a) * random()).  Returns (data slots, tree indices, is_weights float64)."""
+        (random.uniform(a, b) = a + (b - a) * random()); alternatively `indexed_u(stratum, redraw)` serves the draws of
+        a counter generator.  Returns (data slots, tree indices, is_weights float64)."""
         total = self.tree[0]
         segment = total / n
         self.beta = float(np.min([1., self.beta + self.beta_increment]))
         slots, idxs, prios = [], [], []
         for i in range(n):
             a, b = segment * i, segment * (i + 1)
-            for _ in range(max_tries):
-                s = a + (b - a) * next_u()
+            for tries in range(max_tries):
+                s = a + (b - a) * (indexed_u(i, tries) if indexed_u is not None else next_u())
                 idx = self.retrieve(s)
                 slot = idx - self.capacity + 1
                 if slot < self.n_entries:          # `not isinstance(data, int)`: the slot has been written

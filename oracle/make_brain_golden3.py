@@ -88,6 +88,12 @@ def main():
     with torch.no_grad():
         out["fwd/q"] = net(torch.tensor(obs[:64], dtype=torch.float)).numpy()
 
+    # ---------------- construction: weights drawn from torch's global RNG (xavier on the online model, PERDQN.py:73-83)
+    torch.manual_seed(123)
+    fresh = PERDQNAgent()
+    out.update(sd_np(fresh.model.state_dict(), "init/w"))
+    out["init/next_rand"] = torch.rand(4).numpy()              # where the global stream stands after construction
+
     # ---------------- a training run
     torch.manual_seed(77)
     agent = PERDQNAgent(capacity=CAP, explore_step=50)

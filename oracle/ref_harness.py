@@ -29,7 +29,7 @@ SITE = dict(RESET_AGENT_PLACE=1, RESET_FOOD_TRIAL=2, RESET_FOOD_PLACE=3, RESET_P
             RESET_POISON_PLACE=5, RESET_SUPER_PLACE=6, FOOD_PLACE=7, FOOD_ACCEPT=8, REPRO_TRIAL=9,
             BIRTH_PLACE=10, PRODUCE_TRIAL=11, PRODUCE_GENE=12, TOPUP_PLACE=13, TOPUP_GENE=14,
             TOPUP_HEALTH=15, TOPUP_AGE=16, ACT_EXPLORE=20, ACT_RANDOM=21, ACT_SAMPLE=22,
-            REPLAY_SAMPLE=30, REPLAY_SAMPLE_UNIFORM=31)
+            REPLAY_SAMPLE=30, REPLAY_SAMPLE_UNIFORM=31, SUMTREE_SAMPLE=32)
 
 
 def mix64(z):

@@ -11,8 +11,15 @@ import numpy as np
 
 from .. import _lib
 
-DUELING, DQN, PPO = 0, 1, 2
+DUELING, DQN, PPO = 0, 1, 2       # = rl_model_kind
+PERDQN = 3                        # host-side kind: Models/PERDQN.py:311-323 (153-64-64-8) carried in the DQN kernel layout,
+                                  # first hidden layer zero-padded from 64 to 128 units (include/reinlife_b200.h, "PERDQN")
 K1 = 160
+
+
+def device_kind(kind):
+    """rl_model_kind the kernels see for a host-side kind."""
+    return DQN if kind == PERDQN else kind
 
 
 class ModelDims(C.Structure):
@@ -24,6 +31,7 @@ _dims_cache = {}
 
 
 def dims(kind):
+    kind = device_kind(kind)
     if kind not in _dims_cache:
         d = ModelDims()
         _lib.check(_lib.load().rl_model_get_dims(C.c_int32(kind), C.byref(d)))
@@ -49,6 +57,12 @@ def _layers(kind, sd):
         w1, b1 = _np(sd["fc1.weight"]), _np(sd["fc1.bias"])
         w2, b2 = _np(sd["fc2.weight"]), _np(sd["fc2.bias"])
         wh, bh = _np(sd["fc3.weight"]), _np(sd["fc3.bias"])
+    elif kind == PERDQN:
+        w1, b1 = np.zeros((128, 153), np.float32), np.zeros(128, np.float32)
+        w1[:64], b1[:64] = _np(sd["fc.0.weight"]), _np(sd["fc.0.bias"])
+        w2 = np.zeros((64, 128), np.float32)
+        w2[:, :64], b2 = _np(sd["fc.2.weight"]), _np(sd["fc.2.bias"])
+        wh, bh = _np(sd["fc.4.weight"]), _np(sd["fc.4.bias"])
     elif kind == PPO:
         w1, b1 = _np(sd["fc1.weight"]), _np(sd["fc1.bias"])
         w2, b2 = _np(sd["fc2.weight"]), _np(sd["fc2.bias"])
@@ -95,6 +109,10 @@ def unpack(kind, flat):
     if kind == DQN:
         return OrderedDict([("fc1.weight", t(w1)), ("fc1.bias", t(b1)), ("fc2.weight", t(w2)), ("fc2.bias", t(b2)),
                             ("fc3.weight", t(wh)), ("fc3.bias", t(bh))])
+    if kind == PERDQN:
+        return OrderedDict([("fc.0.weight", t(w1[:64].copy())), ("fc.0.bias", t(b1[:64].copy())),
+                            ("fc.2.weight", t(w2[:, :64].copy())), ("fc.2.bias", t(b2)),
+                            ("fc.4.weight", t(wh)), ("fc.4.bias", t(bh))])
     return OrderedDict([("fc1.weight", t(w1)), ("fc1.bias", t(b1)), ("fc2.weight", t(w2)), ("fc2.bias", t(b2)),
                         ("fc_pi.weight", t(wh[:8].copy())), ("fc_pi.bias", t(bh[:8].copy())),
                         ("fc_v.weight", t(wh[8:9].copy())), ("fc_v.bias", t(bh[8:9].copy()))])
@@ -113,6 +131,13 @@ def grad_mask(kind):
         wh[:128, :8] = 1
         wh[128:, 8] = 1
         m[d.off_wh:d.off_bh] = wh.reshape(-1)
+    if kind == PERDQN:                          # the padded hidden units 64..127 are not parameters
+        w1t[:, 64:] = 0
+        m[0:d.off_b1] = w1t.reshape(-1)
+        m[d.off_b1 + 64:d.off_b1 + 128] = 0
+        w2t = np.zeros((d.n1, d.n2), np.float32)
+        w2t[:64] = 1
+        m[d.off_w2t:d.off_b2] = w2t.reshape(-1)
     return m
 
 
@@ -121,6 +146,17 @@ def default_init(kind):
     attribute order (PERD3QN.py:189-196, DQN.py:122-124, PPO.py:96-99) from torch's global RNG -- so the same
     torch.manual_seed gives the same initial network as the reference class."""
     import torch.nn as nn
+    if kind == PERDQN:
+        # PERDQN.py:73-74,92-95: DQN(...) = Sequential(Linear, ReLU, Linear, ReLU, Linear) with default init, then
+        # model.apply(weights_init): xavier_uniform on every Linear weight in module order (biases keep the default draw)
+        layers = [nn.Linear(153, 64), nn.Linear(64, 64), nn.Linear(64, 8)]
+        for layer in layers:
+            nn.init.xavier_uniform_(layer.weight)
+        sd = OrderedDict()
+        for i, layer in zip((0, 2, 4), layers):
+            sd[f"fc.{i}.weight"] = layer.weight.detach().clone()
+            sd[f"fc.{i}.bias"] = layer.bias.detach().clone()
+        return sd
     spec = {DUELING: (("fc", 153, 128), ("adv_fc1", 128, 128), ("adv_fc2", 128, 8), ("value_fc1", 128, 128), ("value_fc2", 128, 1)),
             DQN: (("fc1", 153, 128), ("fc2", 128, 64), ("fc3", 64, 8)),
             PPO: (("fc1", 153, 256), ("fc2", 256, 256), ("fc_pi", 256, 8), ("fc_v", 256, 1))}[kind]

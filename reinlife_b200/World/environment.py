@@ -210,12 +210,18 @@ class Environment:
                 b = self.brains[g]
                 if b.KIND == _lib.MODEL_PPO:
                     continue                                      # rl_ppo_store (append-only data list) in _learn_ppo
+                if b.method == "PERDQN":                          # Memory.add (PERDQN.py:275-277) walks the ring's write pointer
+                    _lib.check(lib.rl_sumtree_add(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                                  C.byref(b.memory.bufs), st))
+                    self.gpu_launches += 1
                 _lib.check(lib.rl_replay_store(C.byref(w.cfg), C.byref(w.bufs), C.byref(self.rows.bufs), C.c_int32(g),
                                                C.byref(b._replay.bufs), st))
                 self.gpu_launches += 1
             self._learn_dueling([g for g in trainable if on[g] and self.brains[g].KIND == _lib.MODEL_DUELING], n_epi, st)
             for g in trainable:
-                if on[g] and self.brains[g].KIND == _lib.MODEL_DQN:
+                if self.brains[g].method == "PERDQN":
+                    self._learn_perdqn(g, st)
+                elif on[g] and self.brains[g].KIND == _lib.MODEL_DQN:
                     self._learn_dqn(g, st)
                 elif self.brains[g].KIND == _lib.MODEL_PPO:
                     self._learn_ppo(g, tf[g], st)
@@ -302,6 +308,30 @@ class Environment:
         sync_target(b._dev, w, cond)
         self.gpu_launches += 1
 
+    def _learn_perdqn(self, g, st):
+        """PERDQN: learn() (PERDQN.py:188-195): every trigger of a world whose memory holds >= train_start items is one
+        train_model() event (stratified SumTree sample, importance-weighted MSE, priorities of the sampled leaves
+        refreshed); epsilon steps once per optimizer step; target_model <- model at every trigger, trained or not."""
+        w, lib, b = self.world, self.world.lib, self.brains[g]
+        tr, dev = b.memory, b._dev
+        _lib.check(lib.rl_sumtree_sample(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                         C.byref(tr.bufs), C.c_int32(64), C.c_uint64(w.t), C.c_void_p(dev.sample_idx.data_ptr()),
+                                         C.c_void_p(tr.ev_weight.data_ptr()), st))
+        _lib.check(lib.rl_brain_learn_perdqn(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                             C.c_void_p(dev.sample_idx.data_ptr()), C.c_void_p(tr.ev_weight.data_ptr()),
+                                             C.byref(dev.learn_bufs), st))
+        if self.dist:
+            self._allreduce_grads([g])
+        _lib.check(lib.rl_brain_adam(C.byref(dev.learn_bufs), st))
+        _lib.check(lib.rl_sumtree_update(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                         C.byref(tr.bufs), C.c_int32(64), C.c_void_p(dev.sample_idx.data_ptr()),
+                                         C.c_void_p(dev.new_prio.data_ptr()), st))
+        _lib.check(lib.rl_perdqn_epsilon_step(C.byref(dev.learn_bufs), C.c_void_p(self._eps.data_ptr() + 8 * g),
+                                              C.c_double(b.epsilon_min), C.c_double(b.epsilon_decay), st))
+        cond = self.rows.total.data_ptr() + 4 * (g * _lib.N_ROW_KINDS + _lib.ROWS_EVENT)
+        sync_target(dev, w, cond)
+        self.gpu_launches += 10
+
     def _learn_ppo(self, g, train_freq, st):
         """PPO: learn() (PPO.py:71-77): put_data for every age > 1 agent; every trigger consumes the list and runs
         k_epoch optimizer steps (PPO.py:136-162)."""
@@ -348,6 +378,10 @@ class Environment:
             st = getattr(getattr(b, "_replay", None), "status", None)
             if st is not None and int(st):
                 raise RuntimeError(f"{b.method}: the per-world data list overflowed (status {int(st)}); raise data_capacity")
+            mem = getattr(b, "memory", None)
+            if mem is not None and int(mem.status):
+                raise RuntimeError("PERDQN: a SumTree stratum found no filled leaf in 64 redraws (PERDQN.py:290-295 would "
+                                   "keep drawing)")
 
     def count_agents(self):
         """Total listed agents on this rank (device -> host read)."""

@@ -69,7 +69,7 @@ def exported_symbols():
 
 ROWS_ALL, ROWS_STORE, ROWS_EVENT, N_ROW_KINDS = 0, 1, 2, 3
 MODEL_DUELING, MODEL_DQN, MODEL_PPO = 0, 1, 2
-ACT_DUELING, ACT_DQN, ACT_PPO = 0, 1, 2
+ACT_DUELING, ACT_DQN, ACT_PPO, ACT_PERDQN = 0, 1, 2, 3
 
 
 class RowsBufs(C.Structure):
@@ -104,3 +104,8 @@ class PpoBufs(C.Structure):
                 ("flat_src", C.c_void_p), ("row_T", C.c_void_p), ("row_end", C.c_void_p), ("td", C.c_void_p),
                 ("delta", C.c_void_p), ("adv", C.c_void_p), ("status", C.c_void_p), ("row_cap", C.c_int32),
                 ("lmbda", C.c_float), ("eps_clip", C.c_float), ("_pad", C.c_int32)]
+
+
+class SumTreeBufs(C.Structure):
+    _fields_ = [("tree", C.c_void_p), ("beta", C.c_void_p), ("status", C.c_void_p), ("capacity", C.c_int32),
+                ("train_start", C.c_int32), ("p_new", C.c_float), ("_pad", C.c_int32)]

@@ -13,11 +13,11 @@ from .Models import packing
 
 class DeviceBrain:
     def __init__(self, kind, state_dict, device, lr=1e-3, gamma=0.99, batch=64, has_target=True):
-        self.kind, self.device = kind, torch.device(device)
+        self.host_kind, self.kind, self.device = kind, packing.device_kind(kind), torch.device(device)   # kind = rl_model_kind
         self.lib = _lib.load()
         self.dims = packing.dims(kind)
         self.lr, self.gamma, self.batch = float(lr), float(gamma), int(batch)
-        flat = torch.from_numpy(packing.pack(kind, state_dict))
+        flat = torch.from_numpy(packing.pack(kind, state_dict))      # host kind: PERDQN packs into the padded DQN layout
         self.params = flat.to(self.device)
         self.target = self.params.clone() if has_target else None
         nt = self.dims.n_train
@@ -60,10 +60,10 @@ class DeviceBrain:
 
     # -- state_dict round trip (reference key names) -----------------------------------------------
     def state_dict(self, target=False):
-        return packing.unpack(self.kind, (self.target if target else self.params).cpu().numpy())
+        return packing.unpack(self.host_kind, (self.target if target else self.params).cpu().numpy())
 
     def load_state_dict(self, sd, target=False):
-        flat = torch.from_numpy(packing.pack(self.kind, sd)).to(self.device)
+        flat = torch.from_numpy(packing.pack(self.host_kind, sd)).to(self.device)
         (self.target if target else self.params).copy_(flat)
         self.wimg_stale = True
 
@@ -109,6 +109,27 @@ class ReplayRings:
     @staticmethod
     def bytes_needed(n_worlds, capacity, ld=_lib.OBS_LD):
         return n_worlds * capacity * (2 * ld * 4 + 1 + 4 + 1 + 4 + 4)
+
+
+class SumTrees:
+    """PERDQN's Memory per local world (rl_sumtree_bufs): float64 sum trees + beta; the transitions themselves live in
+    the brain's ReplayRings (pos = SumTree.write, len = n_entries)."""
+
+    def __init__(self, n_worlds, capacity, device, train_start=1000, ev_cap=1):
+        dev = torch.device(device)
+        self.capacity = int(capacity)
+        self.tree = torch.zeros((n_worlds, 2 * self.capacity - 1), dtype=torch.float64, device=dev)
+        self.beta = torch.full((n_worlds,), 0.4, dtype=torch.float64, device=dev)          # Memory.beta, PERDQN.py:266
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ev_weight = torch.zeros(int(ev_cap), device=dev)
+        # Memory._get_priority(0) as append_sample computes it -- float32 torch scalars (PERDQN.py:126-128,272-273)
+        self.p_new = float((torch.zeros((), dtype=torch.float32).abs() + 0.01) ** 0.6)
+        self.bufs = _lib.SumTreeBufs(self.tree.data_ptr(), self.beta.data_ptr(), self.status.data_ptr(), self.capacity,
+                                     int(train_start), self.p_new, 0)
+
+    @staticmethod
+    def bytes_needed(n_worlds, capacity):
+        return n_worlds * (2 * capacity - 1) * 8
 
 
 class PpoData:

@@ -2,7 +2,7 @@
 //
 // Reference: the per-agent B=1 forwards of Helpers/trainer.py:88-89 / Helpers/tester.py:58-68 through
 // Models/PERD3QN.py:81-89,198-210, Models/D3QN.py:82-93,161-173, Models/DQN.py:65-78,126-139,
-// Models/PPO.py:54-60,101-106,164-169.  Here: persistent CTAs walk 64-row tiles of the per-brain row
+// Models/PPO.py:54-60,101-106,164-169, Models/PERDQN.py:101-111,311-323 (DQN layout, first hidden layer zero-padded).  Here: persistent CTAs walk 64-row tiles of the per-brain row
 // list; the whole 3-stage network runs out of shared memory (mlp_tile.cuh), and the exploration rule +
 // argmax are fused into the epilogue that writes rec[].action.
 #include "mlp_tile.cuh"
@@ -128,6 +128,9 @@ __global__ void __launch_bounds__(NT, 1) k_brain_act(const ActParams P) {
             } else if (P.rule == RL_ACT_DQN) {        // DQN.py:135-139
                 const double coin = rl_uniform(rl_draw(key, P.t_act, RL_SITE_ACT_EXPLORE, (uint32_t)slot));
                 if (coin < epsilon) a = (int)rl_below(rl_draw(key, P.t_act, RL_SITE_ACT_RANDOM, (uint32_t)slot), 8);
+            } else if (P.rule == RL_ACT_PERDQN) {     // PERDQN.py:101-111: np.random.rand() <= eps -> random.randrange(8)
+                const double u = rl_uniform(rl_draw(key, P.t_act, RL_SITE_ACT_EXPLORE, (uint32_t)slot));
+                if (u <= epsilon) a = (int)rl_below(rl_draw(key, P.t_act, RL_SITE_ACT_RANDOM, (uint32_t)slot), 8);
             } else {                                   // PPO.py:164-169: categorical by inverse CDF on one uniform
                 const double u = rl_uniform(rl_draw(key, P.t_act, RL_SITE_ACT_SAMPLE, (uint32_t)slot));
                 float c = 0.f;

@@ -1,4 +1,6 @@
-// learn_rows_kernels.cu -- train steps whose loss is a sum over independent rows: DQN (Models/DQN.py:142-153).
+// learn_rows_kernels.cu -- train steps whose loss is a sum over independent rows: DQN (Models/DQN.py:142-153) and
+// PERDQN (Models/PERDQN.py:130-186; its 153-64-64-8 network runs in the DQN layout with the first hidden layer
+// zero-padded from 64 to 128 units -- padded units stay exactly zero through forward, backward and Adam).
 //
 // Reference: train(q, q_target, memory, optimizer) runs 5 iterations of
 //     s, a, r, s', done_mask = memory.sample(32);  q_a = q(s).gather(1, a);  y = r + gamma * max_a q_target(s') * done_mask
@@ -19,16 +21,25 @@ struct RowsLearnParams {
     const int32_t* ev_total;    // device scalar
     rl_replay_bufs rp;
     const int32_t* sample_idx;  // [row_cap, batch]
+    const float* ev_weight;     // PERDQN: [row_cap] mean of the event's float32 importance weights (PERDQN.py:182)
     rl_learn_bufs lb;
 };
 
-constexpr int DQ_B = 32;                                  // batch_size, DQN.py:16
+// MODE 0: DQN  -- 32-row events, smooth-L1 (DQN.py:149).
+// MODE 1: PERDQN -- 64-row events, loss = mean_i(is_w_i * mse_loss(pred, target)) with mse_loss a scalar mean
+//         (PERDQN.py:182), errors |pred - target| written to lb.new_prio for Memory.update (PERDQN.py:168-174).
+template <int MODE> struct RowsMode;
+template <> struct RowsMode<0> { static constexpr int B = 32; };
+template <> struct RowsMode<1> { static constexpr int B = 64; };
+
 constexpr int DQ_LDX = RL_K1 + 4, DQ_LDH1 = 128 + 4, DQ_LDH2 = 64 + 4, DQ_WHN = 64 * 8 + 16;
 constexpr size_t DQN_SMEM =
     sizeof(float) * ((size_t)R * DQ_LDX + (size_t)R * DQ_LDH1 + (size_t)R * DQ_LDH2 + 2 * (CHUNK_BYTES / 4) + 2 * DQ_WHN + R * 8 + R * 8 + 5 * R) +
     sizeof(int) * 2 * R + 64;
 
+template <int MODE>
 __global__ void __launch_bounds__(NT, 1) k_learn_dqn(const RowsLearnParams P) {
+    constexpr int DQ_B = RowsMode<MODE>::B;
     using M = Model<RL_MODEL_DQN>;
     using L = Layout<RL_MODEL_DQN>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -112,22 +123,34 @@ __global__ void __launch_bounds__(NT, 1) k_learn_dqn(const RowsLearnParams P) {
             outh[o] = acc;
         }
         __syncthreads();
-        // ---- smooth-L1 (beta = 1, mean over the 32 rows of an event) and its gradient ----
+        // ---- loss and its gradient w.r.t. q(s)[a] ----
         if (threadIdx.x < R) {
             const int b = threadIdx.x;
             const float qa = outh[b * 8 + act[b]];
-            const float y = rew[b] + gamma * nq[b] * dmask[b];                       // DQN.py:148
+            const float y = rew[b] + gamma * nq[b] * dmask[b];                       // DQN.py:148, PERDQN.py:163
             const float d = qa - y, ad = fabsf(d);
-            float l = (ad < 1.f ? 0.5f * d * d : ad - 0.5f) * wt[b];
-            const float g = fminf(fmaxf(d, -1.f), 1.f) * (1.0f / DQ_B) * wt[b];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);   // one warp = one event
             const int e = (tile * R + b) / DQ_B;
-            if ((b & 31) == 0 && e < total) P.lb.loss[e] = l * (1.0f / DQ_B);
+            float l, g;
+            if (MODE == 0) {                                                         // smooth-L1, beta = 1, mean over 32 rows
+                l = (ad < 1.f ? 0.5f * d * d : ad - 0.5f) * wt[b];
+                g = fminf(fmaxf(d, -1.f), 1.f) * (1.0f / DQ_B) * wt[b];
+            } else {                                                                 // mean(is_w) * mse
+                const float ew = e < total ? P.ev_weight[e] : 0.f;
+                l = d * d * wt[b] * ew;
+                g = ew * 2.f * d * (1.0f / DQ_B) * wt[b];
+                if (e < total) P.lb.new_prio[(size_t)tile * R + b] = ad;             // errors, PERDQN.py:166
+            }
+            lrow[b] = l;
 #pragma unroll
             for (int j = 0; j < 8; ++j) dout[b * 8 + j] = j == act[b] ? g : 0.f;
         }
         __syncthreads();
+        if (threadIdx.x < R / DQ_B) {                                                // per-event loss, fixed summation order
+            const int e = tile * (R / DQ_B) + threadIdx.x;
+            float l = 0.f;
+            for (int b = 0; b < DQ_B; ++b) l += lrow[threadIdx.x * DQ_B + b];
+            if (e < total) P.lb.loss[e] = l * (1.0f / DQ_B);
+        }
         // ---- fc3 gradients: dWh[k][j] += sum_b H2[b][k] dOut[b][j]; dbh ----
         {
             const int k = threadIdx.x >> 2, j0 = (threadIdx.x & 3) * 2;
@@ -189,25 +212,52 @@ int rl_brain_learn_dqn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_
                        const int32_t* sample_idx, const rl_learn_bufs* learn, void* stream) {
     RL_ARG_CHECK(cfg && rows && replay && sample_idx && learn);
     RL_ARG_CHECK(gene >= 0 && gene < cfg->n_genes && cfg->obs_ld == RL_K1);
-    RL_ARG_CHECK(learn->kind == RL_MODEL_DQN && learn->batch == DQ_B);
+    RL_ARG_CHECK(learn->kind == RL_MODEL_DQN && learn->batch == 32);
     RL_ARG_CHECK(learn->params && learn->target && learn->grad_scratch && learn->grad && learn->loss);
     RL_ARG_CHECK((int64_t)cfg->n_worlds * replay->capacity < (1ll << 31));
     RowsLearnParams P;
     P.cfg = *cfg;
     P.ev_rows = rows->rows + (size_t)(gene * RL_N_ROW_KINDS + RL_ROWS_EVENT) * rows->row_cap;
     P.ev_total = rows->total + gene * RL_N_ROW_KINDS + RL_ROWS_EVENT;
-    P.rp = *replay; P.sample_idx = sample_idx; P.lb = *learn;
+    P.rp = *replay; P.sample_idx = sample_idx; P.ev_weight = nullptr; P.lb = *learn;
     static bool attr = false;
     if (!attr) {
-        RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dqn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DQN_SMEM));
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dqn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DQN_SMEM));
         attr = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    k_learn_dqn<<<rl_learn_grid(), NT, DQN_SMEM, st>>>(P);
+    k_learn_dqn<0><<<rl_learn_grid(), NT, DQN_SMEM, st>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
     int rc = rl_learn_reduce(learn, P.ev_total, 0, stream);
     if (rc) return rc;
-    k_count_valid<<<1, 256, 0, st>>>(sample_idx, DQ_B, P.ev_total, learn->grad + Layout<RL_MODEL_DQN>::N_TRAIN);
+    k_count_valid<<<1, 256, 0, st>>>(sample_idx, 32, P.ev_total, learn->grad + Layout<RL_MODEL_DQN>::N_TRAIN);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_brain_learn_perdqn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                          const int32_t* sample_idx, const float* ev_weight, const rl_learn_bufs* learn, void* stream) {
+    RL_ARG_CHECK(cfg && rows && replay && sample_idx && ev_weight && learn);
+    RL_ARG_CHECK(gene >= 0 && gene < cfg->n_genes && cfg->obs_ld == RL_K1);
+    RL_ARG_CHECK(learn->kind == RL_MODEL_DQN && learn->batch == 64);
+    RL_ARG_CHECK(learn->params && learn->target && learn->grad_scratch && learn->grad && learn->loss && learn->new_prio);
+    RL_ARG_CHECK((int64_t)cfg->n_worlds * replay->capacity < (1ll << 31));
+    RowsLearnParams P;
+    P.cfg = *cfg;
+    P.ev_rows = rows->rows + (size_t)(gene * RL_N_ROW_KINDS + RL_ROWS_EVENT) * rows->row_cap;
+    P.ev_total = rows->total + gene * RL_N_ROW_KINDS + RL_ROWS_EVENT;
+    P.rp = *replay; P.sample_idx = sample_idx; P.ev_weight = ev_weight; P.lb = *learn;
+    static bool attr = false;
+    if (!attr) {
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dqn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DQN_SMEM));
+        attr = true;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    k_learn_dqn<1><<<rl_learn_grid(), NT, DQN_SMEM, st>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    int rc = rl_learn_reduce(learn, P.ev_total, 0, stream);
+    if (rc) return rc;
+    k_count_valid<<<1, 256, 0, st>>>(sample_idx, 64, P.ev_total, learn->grad + Layout<RL_MODEL_DQN>::N_TRAIN);
     RL_CUDA_CHECK(cudaGetLastError());
     return RL_OK;
 }

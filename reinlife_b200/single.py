@@ -34,7 +34,7 @@ def forward_single(brain, state):
     row = torch.zeros(vw.ld, dtype=torch.float32)
     row[:_lib.OBS_DIM] = torch.from_numpy(state.astype(np.float32))
     vw.obs_state[0, 0].copy_(row.to(dev))
-    acts = (_lib.BrainAct * 1)(_lib.BrainAct(brain.KIND, _lib.ACT_DQN, brain._dev.params.data_ptr(), eps.data_ptr()))
+    acts = (_lib.BrainAct * 1)(_lib.BrainAct(brain._dev.kind, _lib.ACT_DQN, brain._dev.params.data_ptr(), eps.data_ptr()))
     with torch.cuda.device(dev):
         _lib.check(vw.lib.rl_brain_act_all(C.byref(vw.cfg), C.byref(vw.bufs), C.byref(rows.bufs), acts, 1, C.c_uint64(0),
                                            C.c_void_p(q_out.data_ptr()), None, vw._stream()))

@@ -41,6 +41,7 @@ def test_struct_layouts_match_the_header():
              ("rl_rows_bufs", _lib.RowsBufs, "row_cap"), ("rl_replay_bufs", _lib.ReplayBufs, "prioritized"),
              ("rl_learn_bufs", _lib.LearnBufs, "lr"), ("rl_brain_act", _lib.BrainAct, "epsilon"),
              ("rl_brain_sched", _lib.BrainSched, "max_epi"), ("rl_ppo_bufs", _lib.PpoBufs, "eps_clip"),
+             ("rl_sumtree_bufs", _lib.SumTreeBufs, "p_new"),
              ("rl_agent_rec", None, "prev_slot")]
     body = "".join(f'printf("%s %zu %zu\\n", "{c}", sizeof({c}), offsetof({c}, {m}));' for c, _, m in pairs)
     src = f'#include <stdio.h>\n#include <stddef.h>\n#include "{os.path.join(ROOT, "include", "reinlife_b200.h")}"\nint main(void){{{body}return 0;}}\n'

@@ -85,3 +85,24 @@ def test_sumtree_redraws_unfilled_leaves():
 def test_perdqn_rule():
     q = [0.1, 0.9, 0.9, 0.2]
     assert bo.perdqn_rule(q, 0.5, 0.5, 7) == 7 and bo.perdqn_rule(q, 0.5, 0.5000001, 7) == 1
+
+
+def test_host_brain_draws_the_reference_initial_weights():
+    """reinlife_b200.Models.PERDQN() consumes torch's global RNG exactly like the reference constructor (model with
+    xavier weights, then the throw-away target_model draw) and round-trips through the padded kernel layout."""
+    import torch
+    from reinlife_b200.Models import PERDQN, packing
+    z = golden3()
+    torch.manual_seed(123)
+    b = PERDQN()
+    want = sd3("init/w")
+    assert b.method == "PERDQN" and abs(b.epsilon_decay - 0.99 / 5000) < 1e-18 and b.train_start == 1000
+    for k, v in b.model.state_dict().items():
+        assert np.array_equal(v.numpy(), want[k]), k
+    assert np.array_equal(torch.rand(4).numpy(), z["init/next_rand"])
+    flat = packing.pack(packing.PERDQN, want)
+    back = packing.unpack(packing.PERDQN, flat)
+    assert list(back) == list(want) and all(np.array_equal(back[k].numpy(), want[k]) for k in want)
+    m, d = packing.grad_mask(packing.PERDQN), packing.dims(packing.PERDQN)
+    assert int(m.sum()) == 153 * 64 + 64 + 64 * 64 + 64 + 64 * 8 + 8 == 14536          # SURVEY 2.2: 14 536 parameters
+    assert not flat[:d.n_train][m == 0].any()
