@@ -2,7 +2,7 @@
 
     python scripts/bench_configs.py tester_dqn      # configs[1]: 256 worlds, 30x30, DQN x1, inference only (tester loop body)
     python scripts/bench_configs.py ppo_perd3qn     # configs[4] brain mix on 60x60 / 400 agents, 1024 worlds, STATIC families
-    python scripts/bench_configs.py d3qn | dqn | ppo  # configs[2] shape with the other trainable families (fp32 learn kernels)
+    python scripts/bench_configs.py d3qn | dqn | ppo | perdqn  # configs[2] shape with the other trainable families (fp32 learn kernels)
 """
 import os
 import sys
@@ -10,7 +10,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import reinlife_b200 as rl
-from reinlife_b200.Models import D3QN, DQN, PERD3QN, PPO
+from reinlife_b200.Models import D3QN, DQN, PERD3QN, PERDQN, PPO
 
 which = sys.argv[1] if len(sys.argv) > 1 else "tester_dqn"
 steps, warm = 30, 8
@@ -28,6 +28,10 @@ elif which == "dqn":
     brains = [DQN(max_epi=1000, buffer_limit=2000), DQN(max_epi=1000, buffer_limit=2000)]
     kw, training = dict(width=30, height=30, max_agents=100, n_worlds=4096), True
     warm = 40                                  # rings must hold > 1000 items before train() does anything (DQN.py:79)
+elif which == "perdqn":
+    brains = [PERDQN(capacity=2000), PERDQN(capacity=2000)]
+    kw, training = dict(width=30, height=30, max_agents=100, n_worlds=4096), True
+    warm = 30                                  # memories must hold >= train_start = 1000 items (PERDQN.py:192): ~45 stores/step
 elif which == "ppo":
     brains, kw, training = [PPO(), PPO()], dict(width=30, height=30, max_agents=100, n_worlds=4096), True
 else:
