@@ -195,6 +195,12 @@ def test_get_action_matches_oracle_forward_and_rule():
             assert rec[w, s]["action"] == bo.perdqn_rule(q[i], eps, u, rb), (g, i)
             checked += 1; explored += u <= eps
     assert checked == int(vw.n_agents.sum()) and 0 < explored < checked
+    # the reference's per-agent plugin call on a host observation (Helpers/tester.py:66-68): same network, epsilon 0
+    from reinlife_b200.Models import PERDQN
+    b = PERDQN(training=False)
+    b.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    for i in (0, 5, 17):
+        assert b.get_action(obs[i]) == int(np.argmax(q_ref[i]))
 
 
 def test_trainer_learns_perdqn():
