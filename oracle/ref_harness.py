@@ -73,6 +73,7 @@ class Ctx:
         self.slot = 0          # agent slot during the act phase
         self.event_rank = 0    # replay-sample event rank within (world, brain)
         self.sample_i = 0
+        self.last_choice = -1  # index random.choice picked in _produce
 
     def set_world(self, seed, world):
         self.seed, self.world = seed, world
@@ -110,9 +111,10 @@ class _EnvRandom:
             return uniform(CTX.bits("PRODUCE_TRIAL", 0))
         raise RuntimeError(f"unexpected random.random() caller {name}")
 
-    def choice(self, seq):                          # environment.py:536/538 (static), :544 (non-static)
+    def choice(self, seq):                          # environment.py:536/538 (static), :543 (non-static: best_agents)
         seq = list(seq)
-        return seq[below(CTX.bits("PRODUCE_GENE", 0), len(seq))]
+        CTX.last_choice = below(CTX.bits("PRODUCE_GENE", 0), len(seq))
+        return seq[CTX.last_choice]
 
     def randint(self, a, b):                        # environment.py:512 -- dead code
         raise RuntimeError("random.randint reached: _get_empty_within_fov returned coordinates")
@@ -300,10 +302,34 @@ class RefWorld:
     def _mark_slots(self):
         for s, a in enumerate(self.env.agents):
             a._slot_a = s
+        self._number_new_agents()
+
+    def _number_new_agents(self):
+        """Object identity for `agent not in self.best_agents` (environment.py:738): agents that are new at the end of
+        reset / update_env / top-up get consecutive serial numbers in row-major order."""
+        for a in self.env.grid.get_entities(self.env.entities.agent):
+            if not hasattr(a, "_serial"):
+                a._serial = self._next_serial
+                self._next_serial += 1
+
+    def ns_state(self):
+        """(fitness f64[n], serial i64[n]) of the listed agents + (best serial, best fitness, best brain id)[10] + max_gene
+        (non-static families).  Brain ids: the gene of the lineage, or -1-k for the private copy of initial best agent k."""
+        env = self.env
+        agents = env.grid.get_entities(env.entities.agent)
+        fit = _np.array([float(a.fitness) for a in agents], _np.float64)
+        ser = _np.array([a._serial for a in agents], _np.int64)
+        best = [(b._serial, float(b.fitness), b.gene if b._serial >= 0 else b._serial) for b in env.best_agents]
+        return dict(fitness=fit, serial=ser, best_serial=_np.array([b[0] for b in best], _np.int64),
+                    best_fitness=_np.array([b[1] for b in best], _np.float64),
+                    best_brain=_np.array([b[2] for b in best], _np.int32), max_gene=int(env.max_gene))
 
     def reset(self):
         self._enter(0)
+        self._next_serial = 0
         self.env.reset()
+        for k, b in enumerate(self.env.best_agents):        # the ten deep copies of agent 0 (environment.py:149)
+            b._serial = -1 - k
         self._mark_slots()
         self.t = 0
 
@@ -332,6 +358,8 @@ class RefWorld:
             a.dead = bool(f & 32)
             a.action = int(r["action"])
         env.agents = env.grid.get_entities(env.entities.agent)
+        if not hasattr(self, "_next_serial"):
+            self._next_serial = 0
         self._mark_slots()
 
     def observe(self):
@@ -385,3 +413,6 @@ class NullBrain:
     """Minimal BasicBrain stand-in for world-only goldens (never asked to act or learn)."""
     method = "PERD3QN"
     input_dim, output_dim = 153, 8
+
+    def apply_gaussian_noise(self):                 # Agent.mutate_brain (entities.py:210-213) after a non-static _produce
+        pass

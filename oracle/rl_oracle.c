@@ -30,7 +30,25 @@ typedef struct {
     int killed, inter_killed, intra_killed, ate_super, reproduced, dead;
     int prev_slot;
     double reward;
+    double fitness;    /* Agent.fitness, entities.py:170,189 (python int 0, then float64 sums) */
+    int64_t serial;    /* object identity (`agent not in self.best_agents`, environment.py:738); -1 = not numbered yet */
 } Agent;
+
+/* ---- non-static families (static_families=False): environment.py:149,506-507,541-547,728-739 ----
+ * What the World needs beyond the static state: Agent.fitness, object identity (a serial number, handed out in
+ * row-major order to the agents that are new at the end of reset / update_env / top-up), max_gene, and the ten
+ * best_agents entries.  A brain is identified by the gene of its lineage (offspring share the parent's brain object,
+ * :506-507; every _produce creates gene max_gene+1 with a deepcopy of a best agent's brain, :542-545); the ten initial
+ * best agents are deep copies of agent 0 made at reset (:149) and own private copies of brain 0: brain ids -1..-10. */
+typedef struct { int64_t serial; double fitness; int32_t brain; int32_t _pad; } rlo_best;
+typedef struct {
+    int32_t max_gene;            /* Environment.max_gene */
+    int32_t produced_gene;       /* gene created by the last update_env, -1 if none (set even when the grid was full) */
+    int32_t produced_src_best;   /* index into best[] that random.choice picked (:543) */
+    int32_t produced_src_brain;  /* brain id that was deep-copied */
+    int64_t next_serial;
+    rlo_best best[10];
+} rlo_ns;
 
 typedef struct {
     const rlo_cfg* cfg;
@@ -64,6 +82,7 @@ static int new_agent(World* w, int cell, int gene) {   /* entities.py:145-160 */
     a->i = cell / w->W; a->j = cell % w->W; a->it = a->i; a->jt = a->j;
     a->health = 200; a->age = 0; a->max_age = 50; a->gene = gene; a->action = -1;
     a->prev_slot = 0xFFFF;
+    a->fitness = 0.0; a->serial = -1;
     w->type[cell] = RL_AGENT; w->who[cell] = w->n_pool;
     return w->n_pool++;
 }
@@ -80,6 +99,11 @@ static void load_state(World* w, const uint8_t* type, const rl_agent_rec* rec, i
         a->reproduced = !!(rec[s].flags & RL_F_REPRODUCED); a->dead = !!(rec[s].flags & RL_F_DEAD);
         a->prev_slot = s;
     }
+}
+
+static void load_extra(World* w, const double* fit, const int64_t* ser, int n) {
+    if (!fit) return;
+    for (int s = 0; s < n; ++s) { w->pool[s].fitness = fit[s]; w->pool[s].serial = ser[s]; }   /* ids = slots after load_state */
 }
 
 /* Grid.get_entities(agent): row-major scan -- grid.py:60-67 */
@@ -158,6 +182,17 @@ static void observe(World* w, double* obs /* [n_list,153] */) {
     free(food); free(healthf); free(genes);
 }
 
+/* new agents get their serial in row-major order of the final list (mirrors the harness, which numbers objects at dump time) */
+static void store_extra(World* w, double* fit, int64_t* ser, rlo_ns* ns) {
+    if (!fit) return;
+    rebuild_list(w);
+    for (int s = 0; s < w->n_list; ++s) {
+        Agent* a = &w->pool[w->list[s]];
+        if (a->serial < 0) a->serial = ns->next_serial++;
+        fit[s] = a->fitness; ser[s] = a->serial;
+    }
+}
+
 static void store_state(World* w, uint8_t* type, rl_agent_rec* rec, int32_t* n, double* reward) {
     rebuild_list(w);
     memcpy(type, w->type, w->C);
@@ -206,10 +241,11 @@ int rlo_reset(const rlo_cfg* cfg, int64_t world_id, uint8_t* type, rl_agent_rec*
 }
 
 /* ---- Environment.step -- environment.py:160-186 ---- */
-int rlo_step(const rlo_cfg* cfg, int64_t world_id, uint64_t t, uint8_t* type, rl_agent_rec* rec, int32_t* n,
-             double* reward, double* obs) {
+static int step_impl(const rlo_cfg* cfg, int64_t world_id, uint64_t t, uint8_t* type, rl_agent_rec* rec, int32_t* n,
+                     double* reward, double* obs, double* fit, int64_t* ser, rlo_ns* ns) {
     World w; world_init(&w, cfg, world_id, t);
     load_state(&w, type, rec, *n);
+    load_extra(&w, fit, ser, *n);
     const int H = w.H, W = w.W;
     (void)H;
 
@@ -293,6 +329,9 @@ int rlo_step(const rlo_cfg* cfg, int64_t world_id, uint64_t t, uint8_t* type, rl
         else r = (double)kin / (double)alive;
         if (a->killed && cfg->incentivize_killing) r += 0.2;
         a->reward = r;
+        a->fitness += r;                                                   /* update_rl_stats, entities.py:187-192 */
+        if (ns)                                                            /* best_agents holds the live object */
+            for (int k = 0; k < 10; ++k) if (ns->best[k].serial == a->serial) ns->best[k].fitness = a->fitness;
     }
     /* _add_food :763-776 */
     {
@@ -319,16 +358,43 @@ int rlo_step(const rlo_cfg* cfg, int64_t world_id, uint64_t t, uint8_t* type, rl
     }
     observe(&w, obs);                                                      /* :186 */
     store_state(&w, type, rec, n, reward);
+    store_extra(&w, fit, ser, ns);
     world_free(&w);
     return 0;
 }
 
+int rlo_step(const rlo_cfg* cfg, int64_t world_id, uint64_t t, uint8_t* type, rl_agent_rec* rec, int32_t* n,
+             double* reward, double* obs) {
+    return step_impl(cfg, world_id, t, type, rec, n, reward, obs, NULL, NULL, NULL);
+}
+int rlo_step_ns(const rlo_cfg* cfg, int64_t world_id, uint64_t t, uint8_t* type, rl_agent_rec* rec, int32_t* n,
+                double* reward, double* obs, double* fitness, int64_t* serial, rlo_ns* ns) {
+    return step_impl(cfg, world_id, t, type, rec, n, reward, obs, fitness, serial, ns);
+}
+
 /* ---- Environment.update_env -- environment.py:188-215 (tracker / best-agents excluded) ---- */
-int rlo_update(const rlo_cfg* cfg, int64_t world_id, uint64_t t, uint8_t* type, rl_agent_rec* rec, int32_t* n, double* obs) {
+static int update_impl(const rlo_cfg* cfg, int64_t world_id, uint64_t t, uint8_t* type, rl_agent_rec* rec, int32_t* n, double* obs,
+                       double* fit, int64_t* ser, rlo_ns* ns) {
     World w; world_init(&w, cfg, world_id, t);
     load_state(&w, type, rec, *n);
-    rebuild_list(&w);                                                      /* :210 */
+    load_extra(&w, fit, ser, *n);
+    rebuild_list(&w);                                                      /* :210 (== the list of :349, self.agents) */
     const int n_list = w.n_list;                                           /* frozen for the loop */
+    if (ns) {                                                              /* _update_best_agents :728-739 */
+        int mi = 0;
+        for (int k = 1; k < 10; ++k) if (ns->best[k].fitness < ns->best[mi].fitness) mi = k;      /* np.argmin: first minimum */
+        if (n_list > 0) {
+            int xi = 0;
+            for (int s = 1; s < n_list; ++s) if (w.pool[w.list[s]].fitness > w.pool[w.list[xi]].fitness) xi = s;   /* np.argmax: first maximum */
+            const Agent* a = &w.pool[w.list[xi]];
+            int present = 0;
+            for (int k = 0; k < 10; ++k) present |= (ns->best[k].serial == a->serial);
+            if (!present && a->fitness > ns->best[mi].fitness) {
+                ns->best[mi].serial = a->serial; ns->best[mi].fitness = a->fitness; ns->best[mi].brain = a->gene;
+            }
+        }
+        ns->produced_gene = -1; ns->produced_src_best = -1; ns->produced_src_brain = 0;
+    }
     uint32_t trial = 0, birth = 0;
     /* _reproduce :488-519 */
     for (int s = 0; s < n_list; ++s) {
@@ -341,8 +407,16 @@ int rlo_update(const rlo_cfg* cfg, int64_t world_id, uint64_t t, uint8_t* type, 
             if (cfg->limit_reproduction) a->reproduced = 1;                /* :518-519 */
         }
     }
-    /* _produce :521-547 (static families) */
-    if (n_list <= cfg->max_agents && rl_uniform(rl_draw(w.key, t, RL_SITE_PRODUCE_TRIAL, 0)) > 0.95) {
+    /* _produce :521-547 */
+    if (ns) {                                                              /* non-static: :541-547 */
+        if (n_list <= cfg->max_agents && rl_uniform(rl_draw(w.key, t, RL_SITE_PRODUCE_TRIAL, 0)) > 0.95) {
+            ns->max_gene += 1;                                             /* :542, before the placement can fail */
+            const int k = (int)rl_below(rl_draw(w.key, t, RL_SITE_PRODUCE_GENE, 0), 10);   /* random.choice(self.best_agents) :543 */
+            ns->produced_gene = ns->max_gene; ns->produced_src_best = k; ns->produced_src_brain = ns->best[k].brain;
+            int cell = set_random_cell(&w, rl_draw(w.key, t, RL_SITE_BIRTH_PLACE, birth), 0, 0, 1.0);
+            if (cell >= 0) { birth++; new_agent(&w, cell, ns->max_gene); }
+        }
+    } else if (n_list <= cfg->max_agents && rl_uniform(rl_draw(w.key, t, RL_SITE_PRODUCE_TRIAL, 0)) > 0.95) {
         int present[RL_MAX_GENES]; memset(present, 0, sizeof(present));
         for (int s = 0; s < n_list; ++s) present[w.pool[w.list[s]].gene] = 1;
         int cand[RL_MAX_GENES], nc = 0;
@@ -360,7 +434,30 @@ int rlo_update(const rlo_cfg* cfg, int64_t world_id, uint64_t t, uint8_t* type, 
     observe(&w, obs);                                                      /* :214 */
     for (int s = 0; s < w.n_list; ++s) w.pool[w.list[s]].prev_slot = s;   /* state <- state_prime :215 */
     store_state(&w, type, rec, n, NULL);
+    store_extra(&w, fit, ser, ns);
     world_free(&w);
+    return 0;
+}
+
+int rlo_update(const rlo_cfg* cfg, int64_t world_id, uint64_t t, uint8_t* type, rl_agent_rec* rec, int32_t* n, double* obs) {
+    return update_impl(cfg, world_id, t, type, rec, n, obs, NULL, NULL, NULL);
+}
+int rlo_update_ns(const rlo_cfg* cfg, int64_t world_id, uint64_t t, uint8_t* type, rl_agent_rec* rec, int32_t* n, double* obs,
+                  double* fitness, int64_t* serial, rlo_ns* ns) {
+    return update_impl(cfg, world_id, t, type, rec, n, obs, fitness, serial, ns);
+}
+
+/* reset with static_families=False: same world as the static reset (:147-148 does not branch); plus the ten deep copies
+ * of agent 0 (:149) and the numbering of the first agents */
+int rlo_reset_ns(const rlo_cfg* cfg, int64_t world_id, uint8_t* type, rl_agent_rec* rec, int32_t* n, double* obs,
+                 double* fitness, int64_t* serial, rlo_ns* ns) {
+    int rc = rlo_reset(cfg, world_id, type, rec, n, obs);
+    if (rc) return rc;
+    memset(ns, 0, sizeof(*ns));
+    ns->max_gene = cfg->n_genes;                                           /* :108 */
+    ns->produced_gene = -1; ns->produced_src_best = -1;
+    for (int s = 0; s < *n; ++s) { fitness[s] = 0.0; serial[s] = ns->next_serial++; }
+    for (int k = 0; k < 10; ++k) { ns->best[k].serial = -1 - k; ns->best[k].fitness = 0.0; ns->best[k].brain = -1 - k; }
     return 0;
 }
 
