@@ -40,79 +40,66 @@ def _network_of(brain):
 
 
 class Saver:
+    """Saver(main_folder, google_colab=False).save(agents, family, results, settings, fig) -- saver.py:51-97."""
+
     def __init__(self, main_folder: str, google_colab: bool = False):
         self.google_colab = google_colab
         self.separator = os.sep
         self.main_folder = os.path.join(os.getcwd(), main_folder)
 
-    # -- saver.py:58-97
     def save(self, agents, family: bool, results: dict, settings: dict, fig=None):
-        directory_paths, agent_paths, experiment_path = self._get_paths(agents, family)
-        self._create_directories(directory_paths)
+        exp = self._experiment_dir()
+        stems = self._brain_stems(agents, family, exp)
+        for d in sorted({os.path.dirname(stem) for stem in stems.values()}):
+            os.makedirs(d, exist_ok=True)
         written = []
-        for agent in agents:
-            torch.save(_network_of(agent.brain).state_dict(), agent_paths[agent] + ".pt")
-            written.append(agent_paths[agent] + ".pt")
-        with open(os.path.join(experiment_path, "results.json"), "w") as f:
-            json.dump(results, f, indent=4)
-        with open(os.path.join(experiment_path, "settings.json"), "w") as f:
-            json.dump(settings, f, indent=4)
+        for agent, stem in stems.items():
+            torch.save(_network_of(agent.brain).state_dict(), stem + ".pt")
+            written.append(stem + ".pt")
+            folder, base = os.path.split(stem)
+            with open(os.path.join(folder, base.replace("brain", "parameters") + ".json"), "w") as f:
+                json.dump(self._scalar_attributes(agent.brain), f, indent=4)
+        for name, payload in (("results.json", results), ("settings.json", settings)):
+            with open(os.path.join(exp, name), "w") as f:
+                json.dump(payload, f, indent=4)
         if fig is not None and hasattr(fig, "savefig"):
-            fig.savefig(os.path.join(experiment_path, "results.png"), dpi=150)
-        self._save_params(agents, agent_paths)
+            fig.savefig(os.path.join(exp, "results.png"), dpi=150)
         return written
 
-    # -- saver.py:99-147
-    def _get_paths(self, agents, family: bool):
-        today = str(date.today())
-        experiment_path = os.path.join(self.main_folder, today + "_V1")
-        if os.path.exists(experiment_path):
-            paths = [path for path in os.listdir(self.main_folder) if today in path]
-            index = str(max(self.get_int(path.split("V")[-1]) for path in paths) + 1)
-            experiment_path = experiment_path[:-1] + index
-        model_paths = sorted({os.path.join(experiment_path, agent.brain.method) for agent in agents})
-        if family:
-            agents_paths = {agent: os.path.join(experiment_path, agent.brain.method, "brain_gene_" + str(agent.gene))
-                            for agent in agents}
-        else:                       # brain_1, brain_2, ... per method, in the order the agents are listed
-            agents_paths, seen = {}, {}
-            for agent in agents:
-                seen[agent.brain.method] = seen.get(agent.brain.method, 0) + 1
-                agents_paths[agent] = os.path.join(experiment_path, agent.brain.method, "brain_" + str(seen[agent.brain.method]))
-        return [self.main_folder, experiment_path] + model_paths, agents_paths, experiment_path
+    def _experiment_dir(self):
+        """<main_folder>/<today>_V<n>, n = 1 + the highest version already present for today (saver.py:119-127)."""
+        os.makedirs(self.main_folder, exist_ok=True)
+        tag = f"{date.today()}_V"
+        taken = [int(name[len(tag):]) for name in os.listdir(self.main_folder)
+                 if name.startswith(tag) and name[len(tag):].isdigit()]
+        exp = os.path.join(self.main_folder, tag + str(max(taken, default=0) + 1))
+        os.makedirs(exp)
+        return exp
 
-    def _create_directories(self, all_paths):
-        for path in all_paths:
-            if not os.path.exists(path) and not self._create_directory(path):
-                raise Exception(f"{path} could not be created")
-
-    # -- saver.py:170-194: every non-routine member whose type is exactly float / int / bool / str
     @staticmethod
-    def _save_params(agents, agent_paths):
+    def _brain_stems(agents, family, exp):
+        """agent -> path without extension: brain_gene_<gene> for static families (saver.py:130-134), otherwise
+        brain_1, brain_2, ... per method in list order (saver.py:136-145)."""
+        stems, per_method = {}, {}
         for agent in agents:
-            params = {}
-            for name, val in inspect.getmembers(agent.brain, lambda a: not inspect.isroutine(a)):
-                if type(val) in (float, int, bool, str) and not name.isupper() and (not name.startswith("_") or name == "_method"):
-                    params[name] = val          # class constants of the device brains (KIND, RULE, ...) and private state are skipped
-            folder, base = os.path.split(agent_paths[agent])
-            with open(os.path.join(folder, base.replace("brain", "parameters") + ".json"), "w") as f:
-                json.dump(params, f, indent=4)
+            method = agent.brain.method
+            if family:
+                name = f"brain_gene_{agent.gene}"
+            else:
+                per_method[method] = per_method.get(method, 0) + 1
+                name = f"brain_{per_method[method]}"
+            stems[agent] = os.path.join(exp, method, name)
+        return stems
 
     @staticmethod
-    def _create_directory(path: str) -> bool:
-        try:
-            os.mkdir(path)
-        except OSError:
-            return False
-        return True
-
-    @staticmethod
-    def get_key(val, dictionary):
-        return next(key for key, value in dictionary.items() if value == val)
-
-    @staticmethod
-    def get_int(a_string: str) -> int:
-        return int("".join(s for s in a_string if s.isdigit()))
+    def _scalar_attributes(brain):
+        """saver.py:170-194: every non-routine member whose type is exactly float / int / bool / str.  Class constants
+        of the device brains (KIND, RULE, ...) and private state other than `_method` are left out."""
+        out = {}
+        for name, val in inspect.getmembers(brain, lambda a: not inspect.isroutine(a)):
+            if type(val) in (float, int, bool, str) and not name.isupper() and (not name.startswith("_") or name == "_method"):
+                out[name] = val
+        return out
 
 
 def save_brains(env, root="experiments"):
