@@ -119,6 +119,60 @@ class Clocks:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ----------------------------------------------------------------------------------------------- post-timing self-check
+def parity_check(env, brains, precision):
+    """Re-run the LAST step's train() events of every brain (same EVENT list, same sampled ring positions, current
+    weights) through the benchmarked event kernel and through the fp32 CUDA-core kernel (the path held to the
+    reference at atol 1e-5 in tests/test_learn_gpu.py) and report the largest disagreement: summed gradients per
+    tensor relative to that tensor's gradient scale, per-event loss and priorities relative.  Outside the timed
+    regions; the tolerance is the one of tests/test_scale_gpu.py."""
+    import ctypes as C
+    import torch
+    from reinlife_b200 import _lib
+    w, lib = env.world, env.world.lib
+    st = w._stream()
+    out = {"kernel_vs": "k_learn_dueling (fp32 FMA)", "tol_grad": 1e-2, "tol_loss": 2e-2, "events": 0,
+           "max_rel_grad_err": 0.0, "max_rel_loss_err": 0.0, "max_rel_prio_err": 0.0}
+    if precision == "fp32":
+        out.update(ok=True, note="benchmarked kernel is the fp32 kernel itself")
+        return out
+    with torch.cuda.device(env.device):
+        for g, b in enumerate(brains):
+            dev = b._dev
+            d = dev.dims
+            n_ev = int(env.rows.total[g * _lib.N_ROW_KINDS + _lib.ROWS_EVENT])
+            if n_ev == 0:
+                continue
+            res = {}
+            for mode in (precision, "fp32"):
+                if mode == "fp32":
+                    _lib.check(lib.rl_brain_learn(C.byref(w.cfg), C.byref(env.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                                  C.c_void_p(dev.sample_idx.data_ptr()), C.byref(dev.learn_bufs), st))
+                elif mode == "fp16":
+                    _lib.check(lib.rl_brain_learn_h(C.byref(w.cfg), C.byref(env.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                                    C.c_void_p(dev.sample_idx.data_ptr()), C.byref(dev.learn_bufs),
+                                                    C.c_void_p(dev.wimg_eh.data_ptr()), C.c_void_p(dev.wimg_th.data_ptr()), st))
+                else:
+                    _lib.check(lib.rl_brain_learn_tc(C.byref(w.cfg), C.byref(env.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                                                     C.c_void_p(dev.sample_idx.data_ptr()), C.byref(dev.learn_bufs),
+                                                     C.c_void_p(dev.wimg_e.data_ptr()), C.c_void_p(dev.wimg_t.data_ptr()), st))
+                torch.cuda.synchronize()
+                res[mode] = (dev.grad[:d.n_train].double() * dev.mask.double(), dev.loss[:n_ev].double().clone(),
+                             dev.new_prio[:n_ev].double().clone(), float(dev.grad[d.n_train]))
+            a, ref = res[precision], res["fp32"]
+            assert a[3] == ref[3] == n_ev, (a[3], ref[3], n_ev)
+            for lo, hi in ((0, d.off_b1), (d.off_b1, d.off_w2t), (d.off_w2t, d.off_b2), (d.off_b2, d.off_wh),
+                           (d.off_wh, d.off_bh), (d.off_bh, d.off_bh + 9)):
+                scale = float(ref[0][lo:hi].abs().max())
+                out["max_rel_grad_err"] = max(out["max_rel_grad_err"], float((a[0][lo:hi] - ref[0][lo:hi]).abs().max()) / max(scale, 1e-30))
+            out["max_rel_loss_err"] = max(out["max_rel_loss_err"], float(((a[1] - ref[1]).abs() / (ref[1].abs() + 1e-3 / 2e-2)).max()))
+            out["max_rel_prio_err"] = max(out["max_rel_prio_err"], float(((a[2] - ref[2]).abs() / (ref[2].abs() + 1.0)).max()))
+            out["events"] += n_ev
+    out["ok"] = bool(out["events"] > 0 and out["max_rel_grad_err"] < out["tol_grad"] and out["max_rel_loss_err"] < out["tol_loss"]
+                     and out["max_rel_prio_err"] < 2e-2)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     import torch
@@ -187,7 +241,7 @@ def run_b200(args):
     #      pinned control block -> device (step stamp read by the stats kernel), tracker record + event counts -> host
     count.zero_()
     nt = brains[0]._dev.dims.n_train
-    h2d = env.tracker.ctrl_host.numel() * 8
+    h2d = env.tracker.ctrl_host[0].numel() * 8
     d2h = env.tracker.nv * 8 + 4 * len(brains)
     barrier()
     t0 = time.perf_counter()
@@ -223,6 +277,7 @@ def run_b200(args):
         n_epi += 1
     n_avg = n_agents_meas / n_meas / NW
     ev_avg = ev_meas / n_meas
+    parity = parity_check(env, brains, args.precision) if rank == 0 else None
     # the event kernel alone (one launch per brain per step): CUDA events recorded around rl_brain_learn(_tc)
     k_ms = [a.elapsed_time(b) for (_, _, a, b) in env.kernel_events]
     env.kernel_events = None
@@ -278,7 +333,7 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "public Environment API; per step: pinned control block H2D, tracker record + event counts D2H (host sync)"},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "roofline_kernels": roof_k,
-            "phase_ms": phases}
+            "phase_ms": phases, "parity_check": parity}
     if rank == 0:
         if world_size == 1 and not args.no_cpu_baseline:
             try:

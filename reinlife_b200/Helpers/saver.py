@@ -104,6 +104,8 @@ class Saver:
 
 def save_brains(env, root="experiments"):
     """Environment.save_results (environment.py:233-256): one stand-in agent per brain for static families."""
+    if hasattr(env, "sync_host_scalars"):
+        env.sync_host_scalars()            # epsilon / n_epi live on the device while training
     settings = {"Update interval": env.update_interval, "Width": env.width, "Height": env.height,
                 "Max agents": env.max_agents, "Families": env.static_families}
     results = getattr(getattr(env, "tracker", None), "results", None)

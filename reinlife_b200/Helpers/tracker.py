@@ -30,20 +30,24 @@ class Tracker:
         n_scr = w.lib.rl_world_stats_scratch_doubles(C.byref(w.cfg))
         self.scratch = torch.zeros(n_scr, dtype=torch.float64, device=dev)
         self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.ctrl = torch.zeros(2, dtype=torch.int64, device=dev)
-        self.ctrl_host = torch.zeros(2, dtype=torch.int64).pin_memory()
+        # step stamp echoed by the stats kernel: one pinned control block PER ring slot, so that a host that runs ahead of
+        # the device never rewrites a block whose H2D copy is still pending (the drain below syncs every ring_len steps)
+        self.ctrl = torch.zeros((self.ring_len, 2), dtype=torch.int64, device=dev)
+        self.ctrl_host = torch.zeros((self.ring_len, 2), dtype=torch.int64).pin_memory()
         self.k = 0
         self.rows_host = []          # per-step series values since the last aggregation
+        self.history = None          # set to [] to keep every per-step series (parity tests: tracker.track_results)
         self.fig = None
 
     def record(self, n_epi):
         """Launch the reduction for the current agent list into the next ring slot (no sync)."""
         w = self.env.world
-        self.ctrl_host[0] = n_epi
-        self.ctrl.copy_(self.ctrl_host, non_blocking=True)
-        out = self.ring[self.k % self.ring_len]
+        slot = self.k % self.ring_len
+        self.ctrl_host[slot, 0] = n_epi
+        self.ctrl[slot].copy_(self.ctrl_host[slot], non_blocking=True)
+        out = self.ring[slot]
         with torch.cuda.device(self.env.device):
-            _lib.check(w.lib.rl_world_stats(C.byref(w.cfg), C.byref(w.bufs), C.c_void_p(self.ctrl.data_ptr()),
+            _lib.check(w.lib.rl_world_stats(C.byref(w.cfg), C.byref(w.bufs), C.c_void_p(self.ctrl[slot].data_ptr()),
                                             C.c_void_p(self.scratch.data_ptr()), C.c_void_p(self.counter.data_ptr()),
                                             C.c_void_p(out.data_ptr()), w._stream()))
         self.k += 1
@@ -56,19 +60,27 @@ class Tracker:
             return
         host = self.ring[:n].cpu().numpy()
         for rec in host:
-            self.rows_host.append(self.series_from_record(rec))
+            row = self.series_from_record(rec)
+            self.rows_host.append(row)
+            if self.history is not None:
+                self.history.append(row)
 
     def series_from_record(self, rec):
         G, NS = self.nr_genes, _lib.N_STATS
         out = {}
+        tail = rec[G * NS:]
+        if tail[0] == 0:              # no agent anywhere: the reference appends -1 to EVERY series (tracker.py:189-199)
+            for g in range(G):
+                out[g] = [-1] * 7
+            out["populations"] = -1
+            return out
         for g in range(G):
             cnt, age, rew, amax, att, kil, worlds = rec[g * NS:g * NS + 7]
-            if cnt == 0:
+            if cnt == 0:              # other genes alive: sum([]) = 0 kills, 0 intra kills (tracker.py:252-261)
                 vals = [-1, -1, -1, -1, -1, 0.0, 0]
             else:
                 vals = [cnt / worlds, age / cnt, rew / cnt, amax, att / cnt, kil / max(worlds, 1.0), 1.0 if kil != 0 else 0]
             out[g] = vals
-        tail = rec[G * NS:]
         out["populations"] = tail[2] / tail[1] if tail[1] > 0 else -1
         return out
 
@@ -79,6 +91,7 @@ class Tracker:
             self._drain(self.k % self.ring_len)
             self.k = 0
             self.env.check_status()
+            self.env.sync_host_scalars()
             self._average_results()
             if self.print_results:
                 self._print_results()

@@ -80,7 +80,13 @@ class DeviceBrainBase(BasicBrain):
         return _lib.BrainSched(self.RULE, int(bool(getattr(self, "training", False))), 0.0, 1.0, 0)
 
     def _sync_host_scalars(self, eps, seen):
-        pass
+        """Device -> host copy of the schedule state the kernels own once the brain is bound (rl_brain_epsilon_update,
+        rl_perdqn_epsilon_step), so that `brain.epsilon` / `brain.n_epi`, the per-agent plugin calls and the
+        parameters_*.json written by the Saver (Helpers/saver.py:170-194) show the decayed values like the reference's."""
+        if hasattr(self, "epsilon") and getattr(self, "training", True):
+            self.epsilon = float(eps)
+        if hasattr(self, "n_epi"):
+            self.n_epi = int(seen)
 
     # ---- plugin surface for single observations (the reference's per-agent calls) ------------------
     def _q_single(self, state):

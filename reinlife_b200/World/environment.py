@@ -113,6 +113,15 @@ class Environment:
                 b._dev.use_fp16 = self._learn_fp16
         self._act_tc = os.environ.get("RL_ACT_FP32") is None    # tf32 runs: get_action of dueling brains on the tensor cores too
         self._grad_all = None
+        # Multi-GPU: the "did this brain act / store / trigger this step" conditions of the epsilon schedules and target
+        # syncs must be the same on every rank (the reference has ONE brain object), so they are taken from the row totals
+        # summed over all ranks (one 4*3G-byte all-reduce after each row-list build), not from this rank's lists.
+        self._gate = self.rows.total
+        self._rows_gate = self.rows.bufs
+        if self.dist:
+            self._gate = torch.zeros_like(self.rows.total)
+            rb = self.rows.bufs
+            self._rows_gate = _lib.RowsBufs(rb.count, rb.offset, self._gate.data_ptr(), rb.rows, rb.row_cap, 0)
         from ..Helpers.tracker import Tracker
         self.tracker = Tracker(self, update_interval=update_interval, print_results=print_results)
         self.viz = None
@@ -155,9 +164,10 @@ class Environment:
         w = self.world
         G = len(self.brains)
         self.rows.build(kinds_mask=1)
+        self._reduce_gate()
         sched = (_lib.BrainSched * G)(*[b._sched() for b in self.brains])
         with torch.cuda.device(self.device):
-            _lib.check(w.lib.rl_brain_epsilon_update(C.byref(self.rows.bufs), sched, G, C.c_int64(n_epi),
+            _lib.check(w.lib.rl_brain_epsilon_update(C.byref(self._rows_gate), sched, G, C.c_int64(n_epi),
                                                      C.c_void_p(self._eps.data_ptr()), C.c_void_p(self._seen.data_ptr()),
                                                      w._stream()))
             tc = [g for g, b in enumerate(self.brains) if self.precision == "tf32" and b.KIND == _lib.MODEL_DUELING and self._act_tc]
@@ -203,6 +213,7 @@ class Environment:
         tf = [int(getattr(b, "train_freq", 1)) for b in self.brains]
         on = [int(b._trains() and n_epi > getattr(b, "exploration", -1)) for b in self.brains]
         self.rows.build(kinds_mask=6, train_freq=tf, event_on=on)
+        self._reduce_gate()
         self.gpu_launches += 3
         st = w._stream()
         with torch.cuda.device(self.device):
@@ -283,7 +294,7 @@ class Environment:
                 self.gpu_launches += 1
             synced = n_epi % int(b.soft_update_freq) == 0
             if synced:                                        # PERD3QN.py:124-125, only if learn() was called
-                cond = self.rows.total.data_ptr() + 4 * (g * _lib.N_ROW_KINDS + _lib.ROWS_STORE)
+                cond = self._gate.data_ptr() + 4 * (g * _lib.N_ROW_KINDS + _lib.ROWS_STORE)
                 sync_target(b._dev, w, cond)
                 self.gpu_launches += 1
             if self.precision == "tf32":                      # operand images follow the parameters
@@ -304,7 +315,7 @@ class Environment:
                 self._allreduce_grads([g])
             _lib.check(lib.rl_brain_adam(C.byref(b._dev.learn_bufs), st))
             self.gpu_launches += 6
-        cond = self.rows.total.data_ptr() + 4 * (g * _lib.N_ROW_KINDS + _lib.ROWS_EVENT)
+        cond = self._gate.data_ptr() + 4 * (g * _lib.N_ROW_KINDS + _lib.ROWS_EVENT)
         sync_target(b._dev, w, cond)
         self.gpu_launches += 1
 
@@ -328,7 +339,7 @@ class Environment:
                                          C.c_void_p(dev.new_prio.data_ptr()), st))
         _lib.check(lib.rl_perdqn_epsilon_step(C.byref(dev.learn_bufs), C.c_void_p(self._eps.data_ptr() + 8 * g),
                                               C.c_double(b.epsilon_min), C.c_double(b.epsilon_decay), st))
-        cond = self.rows.total.data_ptr() + 4 * (g * _lib.N_ROW_KINDS + _lib.ROWS_EVENT)
+        cond = self._gate.data_ptr() + 4 * (g * _lib.N_ROW_KINDS + _lib.ROWS_EVENT)
         sync_target(dev, w, cond)
         self.gpu_launches += 10
 
@@ -348,6 +359,11 @@ class Environment:
             self.gpu_launches += 6
         _lib.check(lib.rl_ppo_compact(C.byref(w.cfg), C.c_int32(g), C.byref(b._replay.bufs), st))
         self.gpu_launches += 1
+
+    def _reduce_gate(self):
+        if self.dist:
+            self._gate.copy_(self.rows.total)
+            torch.distributed.all_reduce(self._gate)
 
     def _allreduce_grads(self, active):
         """One NCCL all-reduce (sum) over the flattened gradient (+event count) of every active brain."""
@@ -372,6 +388,7 @@ class Environment:
         """Raise what the reference would have raised inside the loop (device-side conditions are sticky flags, read at
         update_interval boundaries and at the end of trainer()): ValueError of random.sample on a buffer shorter than a
         batch (D3QN.py:140)."""
+        self.sync_host_scalars()
         if int(self._sample_status) & 1:
             raise ValueError("Sample larger than population or is negative")
         for b in self.brains:
@@ -382,6 +399,12 @@ class Environment:
             if mem is not None and int(mem.status):
                 raise RuntimeError("PERDQN: a SumTree stratum found no filled leaf in 64 redraws (PERDQN.py:290-295 would "
                                    "keep drawing)")
+
+    def sync_host_scalars(self):
+        """Copy the device-side schedule state (epsilon, last n_epi seen) back into the brain objects (one small D2H)."""
+        eps, seen = self._eps.cpu().tolist(), self._seen.cpu().tolist()
+        for g, b in enumerate(self.brains):
+            b._sync_host_scalars(eps[g], seen[g])
 
     def count_agents(self):
         """Total listed agents on this rank (device -> host read)."""

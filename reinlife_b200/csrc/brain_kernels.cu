@@ -175,16 +175,7 @@ __global__ void k_epsilon_update(const EpsParams P) {
     }
 }
 
-int g_sm_count = 0;
-int sm_count() {
-    if (!g_sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
-    }
-    return g_sm_count;
-}
+int sm_count() { return rl_device_sm_count(); }
 
 template <int KIND>
 int launch_act(const ActParams& P, cudaStream_t st) {
@@ -192,7 +183,6 @@ int launch_act(const ActParams& P, cudaStream_t st) {
     constexpr size_t smem = act_smem<KIND>();
     if (!attr_set) {
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_brain_act<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
     }
     k_brain_act<KIND><<<sm_count(), NT, smem, st>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());

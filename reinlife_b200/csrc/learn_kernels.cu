@@ -228,8 +228,6 @@ __global__ void k_sync_target(const float* __restrict__ src, float* __restrict__
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
-int g_learn_grid = 0;
-
 }  // namespace
 
 int rl_learn_reduce(const rl_learn_bufs* learn, const int32_t* ev_total, int w1_rowmajor, void* stream) {
@@ -243,15 +241,7 @@ int rl_learn_reduce(const rl_learn_bufs* learn, const int32_t* ev_total, int w1_
 
 extern "C" {
 
-int rl_learn_grid(void) {
-    if (!g_learn_grid) {
-        int dev = 0, sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
-        g_learn_grid = sm > 0 ? sm : 148;
-    }
-    return g_learn_grid;
-}
+int rl_learn_grid(void) { return rl_device_sm_count(); }
 
 int rl_brain_learn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
                    const int32_t* sample_idx, const rl_learn_bufs* learn, void* stream) {
@@ -267,10 +257,9 @@ int rl_brain_learn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t ge
     P.ev_rows = rows->rows + (size_t)(gene * RL_N_ROW_KINDS + RL_ROWS_EVENT) * rows->row_cap;
     P.ev_total = rows->total + gene * RL_N_ROW_KINDS + RL_ROWS_EVENT;
     P.rp = *replay; P.sample_idx = sample_idx; P.lb = *learn; P.n_cta = rl_learn_grid();
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need()) {
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dueling, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEARN_SMEM));
-        attr = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
     k_learn_dueling<<<P.n_cta, NT, LEARN_SMEM, st>>>(P);

@@ -220,10 +220,9 @@ int rl_brain_learn_dqn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_
     P.ev_rows = rows->rows + (size_t)(gene * RL_N_ROW_KINDS + RL_ROWS_EVENT) * rows->row_cap;
     P.ev_total = rows->total + gene * RL_N_ROW_KINDS + RL_ROWS_EVENT;
     P.rp = *replay; P.sample_idx = sample_idx; P.ev_weight = nullptr; P.lb = *learn;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need()) {
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dqn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DQN_SMEM));
-        attr = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
     k_learn_dqn<0><<<rl_learn_grid(), NT, DQN_SMEM, st>>>(P);
@@ -247,10 +246,9 @@ int rl_brain_learn_perdqn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int
     P.ev_rows = rows->rows + (size_t)(gene * RL_N_ROW_KINDS + RL_ROWS_EVENT) * rows->row_cap;
     P.ev_total = rows->total + gene * RL_N_ROW_KINDS + RL_ROWS_EVENT;
     P.rp = *replay; P.sample_idx = sample_idx; P.ev_weight = ev_weight; P.lb = *learn;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need()) {
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dqn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DQN_SMEM));
-        attr = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
     k_learn_dqn<1><<<rl_learn_grid(), NT, DQN_SMEM, st>>>(P);

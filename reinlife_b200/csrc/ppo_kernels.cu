@@ -367,11 +367,10 @@ int rl_ppo_epoch(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene
     if (rc) return rc;
     RL_ARG_CHECK(learn->kind == RL_MODEL_PPO && learn->params && learn->grad_scratch && learn->grad);
     P.lb = *learn;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need()) {
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_ppo_tiles<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PPO_SMEM));
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_ppo_tiles<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PPO_SMEM));
-        attr = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
     const float clip_lo = (float)(1.0 - (double)ppo->eps_clip), clip_hi = (float)(1.0 + (double)ppo->eps_clip);

@@ -22,6 +22,31 @@ int rl_learn_reduce(const rl_learn_bufs* learn, const int32_t* ev_total, int w1_
                               __FILE__, __LINE__);                                            \
     } while (0)
 
+// One-time setup per DEVICE (cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are per-device settings;
+// a process may drive several GPUs through Environment(device=...)).
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool need() {
+        int d = 0;
+        cudaGetDevice(&d);
+        d &= 63;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+inline int rl_device_sm_count() {
+    static int sm[64] = {};
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (!sm[d]) {
+        cudaDeviceGetAttribute(&sm[d], cudaDevAttrMultiProcessorCount, d);
+        if (sm[d] <= 0) sm[d] = 148;
+    }
+    return sm[d];
+}
+
 #define RL_ARG_CHECK(cond)                                                                    \
     do {                                                                                      \
         if (!(cond)) return rl_set_err(RL_ERR_ARG, "argument check failed: %s (%s:%d)", #cond, __FILE__, __LINE__); \

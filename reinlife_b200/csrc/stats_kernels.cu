@@ -21,14 +21,16 @@ struct StatsParams {
 __global__ void __launch_bounds__(ST) k_world_stats(const StatsParams P) {
     const int G = P.cfg.n_genes, S = P.cfg.slot_cap, NV = G * RL_N_STATS + 8;
     __shared__ double acc[RL_MAX_GENES * RL_N_STATS + 8];
+    __shared__ double wrew[ST / 32][RL_MAX_GENES];      // per-warp reward partials (merged in warp order: deterministic)
     __shared__ int is_last;
     for (int i = threadIdx.x; i < NV; i += ST) acc[i] = 0.0;
+    for (int i = threadIdx.x; i < (ST / 32) * RL_MAX_GENES; i += ST) (&wrew[0][0])[i] = 0.0;
     __syncthreads();
     const int w0 = blockIdx.x * P.per_block, w1 = min(P.cfg.n_worlds, w0 + P.per_block);
     const int lane = lane_id(), warp = threadIdx.x >> 5;
-    // one warp per world, fixed world->warp assignment, per-warp partials merged through shared-memory atomics on
-    // doubles whose addends are integers or exactly representable sums => order-independent except REWARD_SUM,
-    // which is accumulated per warp in registers in slot order and merged in warp order below.
+    // one warp per world, fixed world->warp assignment.  Counts / age sums / attacks / kills are integers (exact in
+    // double, so the shared-memory atomics are order-independent); REWARD_SUM is not: every warp adds its worlds'
+    // sums into its own shared slot in world order, and the slots are merged in warp order below.
     for (int w = w0 + warp; w < w1; w += ST / 32) {
         const int n = min(P.n_agents[w], S);
         unsigned present = 0;
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(ST) k_world_stats(const StatsParams P) {
             if (lane == 0 && cnt > 0) {
                 double* a = acc + g * RL_N_STATS;
                 atomicAdd(&a[RL_STAT_COUNT], cnt); atomicAdd(&a[RL_STAT_AGE_SUM], age);
-                atomicAdd(&a[RL_STAT_REWARD_SUM], rew);
+                wrew[warp][g] += rew;
                 atomicAdd(&a[RL_STAT_ATTACKS], att); atomicAdd(&a[RL_STAT_KILLS], kil); atomicAdd(&a[6], 1.0);
                 // max via CAS on the bit pattern (non-negative doubles order like integers)
                 atomicMax(reinterpret_cast<unsigned long long*>(&a[RL_STAT_AGE_MAX]), (unsigned long long)__double_as_longlong(amax));
@@ -69,6 +71,12 @@ __global__ void __launch_bounds__(ST) k_world_stats(const StatsParams P) {
             if (n > 0) atomicAdd(&t[1], 1.0);
             atomicAdd(&t[2], (double)__popc(present));
         }
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        double r = 0.0;
+        for (int k = 0; k < ST / 32; ++k) r += wrew[k][threadIdx.x];
+        acc[threadIdx.x * RL_N_STATS + RL_STAT_REWARD_SUM] = r;
     }
     __syncthreads();
     double* mine = P.scratch + (size_t)blockIdx.x * NV;

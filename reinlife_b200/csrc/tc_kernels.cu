@@ -1705,10 +1705,9 @@ int rl_brain_learn_h(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t 
     P.ev_total = rows->total + gene * RL_N_ROW_KINDS + RL_ROWS_EVENT;
     P.rp = *replay; P.sample_idx = sample_idx; P.lb = *learn; P.wimg_e = nullptr; P.wimg_t = nullptr; P.trace = nullptr;
     PH.wimg_e = reinterpret_cast<const __half*>(wimg_eval_h); PH.wimg_t = reinterpret_cast<const __half*>(wimg_target_h);
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need()) {
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dueling_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCH_SMEM));
-        attr = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
     k_learn_dueling_h<<<rl_learn_grid(), NTHREADS2, TCH_SMEM, st>>>(PH);
@@ -1729,10 +1728,9 @@ int rl_brain_act_tc(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl
     P.total = rows->total + gene * RL_N_ROW_KINDS + RL_ROWS_ALL;
     P.params = brain->params; P.wimg = wimg_eval; P.epsilon = brain->epsilon; P.t_act = t_act;
     P.q_out = q_out ? q_out + (size_t)gene * rows->row_cap * 8 : nullptr;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need()) {
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_act_dueling_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-        attr = true;
     }
     k_act_dueling_tc<<<rl_learn_grid(), NTHREADS, TC_SMEM, (cudaStream_t)stream>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
@@ -1754,10 +1752,9 @@ int rl_brain_act_h(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_
     P.params = brain->params; P.wimg = nullptr; P.epsilon = brain->epsilon; P.t_act = t_act;
     P.q_out = q_out ? q_out + (size_t)gene * rows->row_cap * 8 : nullptr;
     PH.wimg = reinterpret_cast<const __half*>(wimg_eval_h);
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need()) {
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_act_dueling_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACTH_SMEM));
-        attr = true;
     }
     k_act_dueling_h<<<rl_learn_grid(), NTHREADS2, ACTH_SMEM, (cudaStream_t)stream>>>(PH);
     RL_CUDA_CHECK(cudaGetLastError());
@@ -1784,10 +1781,9 @@ int rl_brain_learn_tc(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t
         RL_CUDA_CHECK(cudaMemsetAsync(trace_dev, 0, sizeof(long long) * 8 * 40, (cudaStream_t)stream));
         P.trace = trace_dev;
     }
-    static bool attr2 = false;
-    if (!attr2) {
+    static PerDeviceOnce attr2;
+    if (attr2.need()) {
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dueling_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM));
-        attr2 = true;
     }
     const int n_cta = rl_learn_grid();
     cudaStream_t st = (cudaStream_t)stream;
