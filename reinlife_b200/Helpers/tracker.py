@@ -15,6 +15,41 @@ VARIABLES = ["Avg Population Size", "Avg Population Age", "Avg Population Fitnes
              "Avg Number of Attacks", "Avg Number of Kills", "Avg Number of Intra Kills", "Avg Number of Populations"]
 
 
+def series_from_record(rec, n_genes):
+    """One stats record of rl_world_stats -> the per-step value of every series, as Tracker._track_results appends them
+    (tracker.py:178-266).  Index order per gene: size, age, fitness, best age, attacks, kills, intra kills."""
+    G, NS = n_genes, _lib.N_STATS
+    out = {}
+    tail = rec[G * NS:]
+    if tail[0] == 0:              # no agent anywhere: the reference appends -1 to EVERY series (tracker.py:189-199)
+        for g in range(G):
+            out[g] = [-1] * 7
+        out["populations"] = -1
+        return out
+    for g in range(G):
+        cnt, age, rew, amax, att, kil, worlds = rec[g * NS:g * NS + 7]
+        if cnt == 0:              # other genes alive: sum([]) = 0 kills, 0 intra kills (tracker.py:252-261)
+            vals = [-1, -1, -1, -1, -1, 0.0, 0]
+        else:
+            vals = [cnt / worlds, age / cnt, rew / cnt, amax, att / cnt, kil / max(worlds, 1.0), 1.0 if kil != 0 else 0]
+        out[g] = vals
+    out["populations"] = tail[2] / tail[1] if tail[1] > 0 else -1
+    return out
+
+
+def average_rows(rows, n_genes):
+    """Tracker._aggregate (tracker.py:279-282) over the rows of one update interval: mean of the values > -1."""
+    res = {}
+    for vi, var in enumerate(VARIABLES[:-1]):
+        res[var] = []
+        for g in range(n_genes):
+            vals = [r[g][vi] for r in rows if r[g][vi] > -1]
+            res[var].append(float(np.mean(vals)) if vals else float("nan"))
+    vals = [r["populations"] for r in rows if r["populations"] > -1]
+    res[VARIABLES[-1]] = float(np.mean(vals)) if vals else float("nan")
+    return res
+
+
 class Tracker:
     def __init__(self, env, update_interval, print_results=True):
         self.env, self.update_interval, self.print_results = env, int(update_interval), print_results
@@ -66,23 +101,7 @@ class Tracker:
                 self.history.append(row)
 
     def series_from_record(self, rec):
-        G, NS = self.nr_genes, _lib.N_STATS
-        out = {}
-        tail = rec[G * NS:]
-        if tail[0] == 0:              # no agent anywhere: the reference appends -1 to EVERY series (tracker.py:189-199)
-            for g in range(G):
-                out[g] = [-1] * 7
-            out["populations"] = -1
-            return out
-        for g in range(G):
-            cnt, age, rew, amax, att, kil, worlds = rec[g * NS:g * NS + 7]
-            if cnt == 0:              # other genes alive: sum([]) = 0 kills, 0 intra kills (tracker.py:252-261)
-                vals = [-1, -1, -1, -1, -1, 0.0, 0]
-            else:
-                vals = [cnt / worlds, age / cnt, rew / cnt, amax, att / cnt, kil / max(worlds, 1.0), 1.0 if kil != 0 else 0]
-            out[g] = vals
-        out["populations"] = tail[2] / tail[1] if tail[1] > 0 else -1
-        return out
+        return series_from_record(rec, self.nr_genes)
 
     def update_results(self, agents=None, n_epi=0):
         """Same cadence as the reference (tracker.py:107-132): called every step from update_env."""
@@ -97,13 +116,11 @@ class Tracker:
                 self._print_results()
 
     def _average_results(self):
-        rows = self.rows_host[-self.update_interval:]
-        for vi, var in enumerate(VARIABLES[:-1]):
+        res = average_rows(self.rows_host[-self.update_interval:], self.nr_genes)
+        for var in VARIABLES[:-1]:
             for g in range(self.nr_genes):
-                vals = [r[g][vi] for r in rows if r[g][vi] > -1]
-                self.results[var][g].append(float(np.mean(vals)) if vals else float("nan"))
-        vals = [r["populations"] for r in rows if r["populations"] > -1]
-        self.results[VARIABLES[-1]].append(float(np.mean(vals)) if vals else float("nan"))
+                self.results[var][g].append(res[var][g])
+        self.results[VARIABLES[-1]].append(res[VARIABLES[-1]])
         self.rows_host = []
 
     def _print_results(self):

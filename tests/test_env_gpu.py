@@ -123,3 +123,63 @@ def test_trainer_learns_ppo_with_perd3qn():
     assert torch.isfinite(b._dev.params).all() and not torch.equal(b.model.state_dict()["fc1.weight"], w0)
     assert int(b._replay.status) == 0 and int(b._replay.traj.len.max()) < 200
     assert int(brains[1]._dev.adam_step) > 0
+
+
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_tracker_matches_reference_tracker(k):
+    """(f)1: Environment(training=True).update_env -> rl_world_stats -> Tracker vs the per-step `track_results` series and
+    the per-interval averaged `results` recorded from the UNMODIFIED reference's Tracker (Helpers/tracker.py:178-282) on
+    teacher-forced trajectories (tests/golden/tracker_golden.npz); trajectory 2 goes extinct for 18 steps (all -1)."""
+    import reinlife_b200 as rl
+    from reinlife_b200.Models import PERD3QN
+    from reinlife_b200.Helpers.tracker import VARIABLES
+    from test_tracker_cpu import load_tracker_golden, check_series
+    z, meta = load_tracker_golden()
+    m = meta[k]
+    G = m["n_genes"]
+    brains = [PERD3QN(capacity=64) for _ in range(G)]
+    env = rl.Environment(width=m["width"], height=m["height"], brains=brains, max_agents=m["max_agents"],
+                         update_interval=m["interval"], print_results=False, training=True, n_worlds=1, seed=m["seed"],
+                         world_id0=m["world"])
+    env.tracker.history = []
+    env.reset()
+    actions, counts = z[f"t{k}_actions"], z[f"t{k}_counts"]
+    pos = 0
+    for n_epi in range(m["steps"] + 1):
+        n = int(env.world.n_agents[0])
+        assert n == counts[n_epi], (k, n_epi)
+        a = np.zeros((1, env.world.S), np.int8)
+        a[0, :n] = actions[pos:pos + n]; pos += n
+        env.world.set_actions(a)
+        env.step()
+        env.update_env(n_epi)
+    env.tracker._drain(env.tracker.k % env.tracker.ring_len)
+    hist = env.tracker.history
+    assert len(hist) == m["steps"] + 1
+    for step, row in enumerate(hist):
+        check_series(row, z, k, step, G)
+    want = z[f"t{k}_results"]
+    for vi, var in enumerate(VARIABLES[:-1]):
+        for g in range(G):
+            np.testing.assert_allclose(env.tracker.results[var][g], want[vi, g], rtol=1e-6, atol=1e-9, equal_nan=True)
+    np.testing.assert_allclose(env.tracker.results[VARIABLES[-1]], z[f"t{k}_results_pop"], rtol=1e-12, equal_nan=True)
+
+
+def test_saved_parameters_carry_the_decayed_epsilon(tmp_path, monkeypatch):
+    """parameters_gene_*.json and brain.epsilon / brain.n_epi follow the device schedule (the reference writes the decayed
+    values, e.g. pretrained/PERD3QN/.../parameters_gene_0.json)."""
+    import glob
+    import json
+    import reinlife_b200 as rl
+    from reinlife_b200.Models import PERD3QN
+    monkeypatch.chdir(tmp_path)
+    torch.manual_seed(0)
+    brains = [PERD3QN(exploration=1000, capacity=64), PERD3QN(exploration=1000, capacity=64)]
+    env = rl.trainer(brains, n_episodes=25, width=10, height=10, max_agents=20, update_interval=10, print_results=False,
+                     save=True, n_worlds=4, seed=2, saturate_to=20)
+    eps = env.epsilons()
+    for g, b in enumerate(brains):
+        assert b.epsilon == eps[g] and abs(b.epsilon - 0.9 * 0.99 ** 25) < 1e-12 and b.n_epi == 25
+    for f in sorted(glob.glob(str(tmp_path / "experiments" / "*" / "PERD3QN" / "parameters_gene_*.json"))):
+        p = json.load(open(f))
+        assert abs(p["epsilon"] - 0.9 * 0.99 ** 25) < 1e-12 and p["n_epi"] == 25
