@@ -64,5 +64,5 @@ class DQNAgent(DeviceBrainBase):
         return int(np.argmax(q))
 
     def learn(self, age, dead, action, state, reward, state_prime, done):
-        raise NotImplementedError("per-agent learn() is replaced by Environment.learn(n_epi), which batches every "
-                                  "agent of every world (reinlife_b200.Helpers.trainer drives it)")
+        """DQN.py:85-89: memorize; on a trigger train() (5 x sample 32 once the buffer holds > 1000) and target <- agent."""
+        self._plugin_learn(age=age, dead=dead, action=action, state=state, reward=reward, state_prime=state_prime, done=done)

@@ -70,8 +70,10 @@ class PERD3QNAgent(DeviceBrainBase):
         return random.choice(list(range(self.output_dim)))
 
     def learn(self, age, dead, action, state, reward, state_prime, done, n_epi):
-        raise NotImplementedError("per-agent learn() is replaced by Environment.learn(n_epi), which batches every "
-                                  "agent of every world (reinlife_b200.Helpers.trainer drives it)")
+        """PERD3QN.py:117-125 / D3QN.py:118-126: memorize; if n_epi > exploration: train() on a trigger, target sync every
+        soft_update_freq episodes -- on this brain's private device ring (reinlife_b200/plugin.py)."""
+        self._plugin_learn(age=age, dead=dead, action=action, state=state, reward=reward, state_prime=state_prime,
+                           done=done, n_epi=n_epi)
 
     def apply_gaussian_noise(self):                # PERD3QN.py:127-130: net effect = target <- eval
         self.target_net.load_state_dict(self.eval_net.state_dict())

@@ -85,5 +85,6 @@ class PERDQNAgent(DeviceBrainBase):
         return int(np.argmax(q))
 
     def learn(self, age, dead, action, state, reward, state_prime, done):
-        raise NotImplementedError("per-agent learn() is replaced by Environment.learn(n_epi), which batches every "
-                                  "agent of every world (reinlife_b200.Helpers.trainer drives it)")
+        """PERDQN.py:188-195: append_sample; on a trigger train_model() once the memory holds train_start items, then
+        target_model <- model."""
+        self._plugin_learn(age=age, dead=dead, action=action, state=state, reward=reward, state_prime=state_prime, done=done)

@@ -57,5 +57,7 @@ class PPOAgent(DeviceBrainBase):
         return a if self.load_model else (a, prob)
 
     def learn(self, age, dead, action, state, reward, state_prime, done, prob):
-        raise NotImplementedError("per-agent learn() is replaced by Environment.learn(n_epi), which batches every "
-                                  "agent of every world (reinlife_b200.Helpers.trainer drives it)")
+        """PPO.py:71-77: put_data((state, action, reward / 100.0, state_prime, prob[action].item(), done)); on a trigger
+        learn() consumes the data list (k_epoch optimizer steps)."""
+        self._plugin_learn(age=age, dead=dead, action=action, state=state, reward=reward, state_prime=state_prime, done=done,
+                           prob_a=float(prob[int(action)]))

@@ -50,6 +50,7 @@ class DeviceBrainBase(BasicBrain):
         self._dev = None            # brains.DeviceBrain once bound
         self._replay = None
         self._env = None
+        self._plugin_host = None    # plugin.PluginHost: private one-world context of the per-agent learn() calls
 
     # ---- binding ---------------------------------------------------------------------------------
     def _bind(self, env, gene):
@@ -89,6 +90,18 @@ class DeviceBrainBase(BasicBrain):
             self.n_epi = int(seen)
 
     # ---- plugin surface for single observations (the reference's per-agent calls) ------------------
+    def _plugin_learn(self, **kw):
+        """brain.learn(...) with host buffers (World/entities.py:194-208): see reinlife_b200/plugin.py."""
+        if self._plugin_host is None:
+            if self._env is not None:
+                raise RuntimeError("this brain is bound to a vectorised Environment: its agents learn through "
+                                   "Environment.learn(n_epi); per-agent learn() is for a brain used on its own")
+            if not self._trains():
+                return                      # a non-training brain: the reference would still fill its buffer; nothing reads it
+            from ..plugin import PluginHost
+            self._plugin_host = PluginHost(self)
+        self._plugin_host.learn(**kw)
+
     def _q_single(self, state):
         """Network output for ONE observation through the same act kernel (1 row)."""
         from ..single import forward_single

@@ -53,7 +53,7 @@ class Environment:
                  interactive_results: bool = False, google_colab: bool = False, training: bool = True,
                  save: bool = False, pastel_colors: bool = False, limit_reproduction: bool = False,
                  incentivize_killing: bool = True, *, n_worlds: int = 1, seed: int = 0, device=None, world_id0=None,
-                 precision: str = "fp16"):
+                 precision: str = "fp16", sequential_events: bool = False):
         self.width, self.height = width, height
         self.actions, self.entities = Actions, EntityTypes
         self.best_agents = []
@@ -111,6 +111,13 @@ class Environment:
         for b in brains:
             if getattr(b, "_dev", None) is not None:
                 b._dev.use_fp16 = self._learn_fp16
+        # sequential_events=True (one world, one rank): learn() walks the agents in the reference's order and runs
+        # store -> train -> priorities -> Adam -> target sync PER AGENT, so that every train() sees the weights and the ring
+        # the previous agent's train() left (Helpers/trainer.py:95-96, PERD3QN.py:117-125) -- the reference's exact N = 1
+        # semantics; the default batches all events of a step against the pre-step weights (learn-step semantics)
+        self.sequential_events = bool(sequential_events)
+        if self.sequential_events and (self.n_worlds != 1 or self.world_size != 1):
+            raise ValueError("sequential_events=True is the exact single-world mode: n_worlds must be 1 (one rank)")
         self._act_tc = os.environ.get("RL_ACT_FP32") is None    # tf32 runs: get_action of dueling brains on the tensor cores too
         self._grad_all = None
         # Multi-GPU: the "did this brain act / store / trigger this step" conditions of the epsilon schedules and target
@@ -118,6 +125,14 @@ class Environment:
         # summed over all ranks (one 4*3G-byte all-reduce after each row-list build), not from this rank's lists.
         self._gate = self.rows.total
         self._rows_gate = self.rows.bufs
+        # row lists / gate / sampler key the learn pipeline currently works on (the per-agent pipeline of
+        # sequential_events swaps in one-row views of the lists)
+        self._rb_store = self._rb_event = self.rows.bufs
+        self._gate_base = None
+        self._t_key = None
+        self.sample_override = None     # tests: callable(gene, k_event) -> 64 ring positions used instead of the sampler
+        self.event_hook = None          # tests: callable(gene, k_event) after every sequential train() event
+        self._seq_event = None
         if self.dist:
             self._gate = torch.zeros_like(self.rows.total)
             rb = self.rows.bufs
@@ -213,8 +228,17 @@ class Environment:
         tf = [int(getattr(b, "train_freq", 1)) for b in self.brains]
         on = [int(b._trains() and n_epi > getattr(b, "exploration", -1)) for b in self.brains]
         self.rows.build(kinds_mask=6, train_freq=tf, event_on=on)
-        self._reduce_gate()
         self.gpu_launches += 3
+        if self.sequential_events:
+            return self._learn_sequential(n_epi, trainable, tf, on)
+        self._reduce_gate()
+        self._rb_store = self._rb_event = self.rows.bufs
+        self._gate_base, self._t_key = self._gate.data_ptr(), w.t
+        self._learn_lists(trainable, tf, on, n_epi)
+
+    def _learn_lists(self, trainable, tf, on, n_epi):
+        """The learn pipeline of every brain in `trainable` over the row lists self._rb_store / self._rb_event."""
+        w, lib = self.world, self.world.lib
         st = w._stream()
         with torch.cuda.device(self.device):
             for g in trainable:                                   # brain.memorize / put_data for every age > 1 agent
@@ -222,10 +246,10 @@ class Environment:
                 if b.KIND == _lib.MODEL_PPO:
                     continue                                      # rl_ppo_store (append-only data list) in _learn_ppo
                 if b.method == "PERDQN":                          # Memory.add (PERDQN.py:275-277) walks the ring's write pointer
-                    _lib.check(lib.rl_sumtree_add(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                    _lib.check(lib.rl_sumtree_add(C.byref(w.cfg), C.byref(self._rb_store), C.c_int32(g), C.byref(b._replay.bufs),
                                                   C.byref(b.memory.bufs), st))
                     self.gpu_launches += 1
-                _lib.check(lib.rl_replay_store(C.byref(w.cfg), C.byref(w.bufs), C.byref(self.rows.bufs), C.c_int32(g),
+                _lib.check(lib.rl_replay_store(C.byref(w.cfg), C.byref(w.bufs), C.byref(self._rb_store), C.c_int32(g),
                                                C.byref(b._replay.bufs), st))
                 self.gpu_launches += 1
             self._learn_dueling([g for g in trainable if on[g] and self.brains[g].KIND == _lib.MODEL_DUELING], n_epi, st)
@@ -237,6 +261,50 @@ class Environment:
                 elif self.brains[g].KIND == _lib.MODEL_PPO:
                     self._learn_ppo(g, tf[g], st)
 
+    # ------------------------------------------------------------------ exact single-world semantics
+    def _one_row_views(self, k_store, k_event, trigger):
+        """Row-list structs whose STORE list is [k_store-th STORE row] and whose EVENT list is [k_event-th EVENT row]
+        (empty when the agent does not trigger): pointer arithmetic on the lists rl_rows_build wrote, no copies."""
+        rb = self.rows.bufs
+        c1, c0 = self._seq_c1.data_ptr(), self._seq_c0.data_ptr()
+        self._rb_store = _lib.RowsBufs(c1, c0, c1, rb.rows + 4 * k_store, rb.row_cap, 0)
+        ce = c1 if trigger else c0
+        self._rb_event = _lib.RowsBufs(ce, c0, ce, rb.rows + 4 * k_event, rb.row_cap, 0)
+        self._seq_gate[_lib.ROWS_STORE::_lib.N_ROW_KINDS] = 1
+        self._seq_gate[_lib.ROWS_EVENT::_lib.N_ROW_KINDS] = 1 if trigger else 0
+        self._gate_base = self._seq_gate.data_ptr()
+
+    def _learn_sequential(self, n_epi, trainable, tf, on):
+        """for agent in env.agents: agent.learn(n_epi=n_epi) with the reference's per-agent order of effects
+        (Helpers/trainer.py:95-96 -> World/entities.py:194-208 -> brain.learn)."""
+        G = len(self.brains)
+        if not hasattr(self, "_seq_c1"):
+            K = G * _lib.N_ROW_KINDS
+            self._seq_c1 = torch.ones(K, dtype=torch.int32, device=self.device)
+            self._seq_c0 = torch.zeros(K, dtype=torch.int32, device=self.device)
+            self._seq_gate = torch.zeros(K, dtype=torch.int32, device=self.device)
+        n = int(self.world.n_agents[0])
+        rec = self.world.rec_host()[0, :n]
+        k_store, k_event = [0] * G, [0] * G
+        for s in range(n):                                        # row-major = the reference's agent order
+            g, age, dead = int(rec["gene"][s]), int(rec["age"][s]), bool(rec["flags"][s] & _lib.F_DEAD)
+            if age <= 1 or g not in trainable:                    # World/entities.py:196: learn only if age > 1
+                continue
+            trigger = bool(on[g]) and (age % tf[g] == 0 or dead)
+            self._learn_agent(g, k_store[g], k_event[g], trigger, tf, on, n_epi)
+            k_store[g] += 1
+            k_event[g] += int(trigger)
+        self._rb_store = self._rb_event = self.rows.bufs
+
+    def _learn_agent(self, g, k_store, k_event, trigger, tf, on, n_epi):
+        self._one_row_views(k_store, k_event, trigger)
+        self._t_key = (self.world.t << 20) | k_event              # sampler draws: a stream per (step, event) -- rl_rng.h
+        self._seq_event = (g, k_event) if trigger else None
+        self._learn_lists([g], tf, on, n_epi)
+        self._seq_event = None
+        if trigger and self.event_hook is not None:
+            self.event_hook(g, k_event)
+
     def _learn_dueling(self, active, n_epi, st):
         """PERD3QN / D3QN: learn() -> train() (PERD3QN.py:94-125, D3QN.py:97-126)."""
         if not active:
@@ -246,12 +314,19 @@ class Environment:
         for g in active:
             b = self.brains[g]
             if b.PRIORITIZED:                                   # PERD3QN.py:157-175
-                _lib.check(lib.rl_replay_sample(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
-                                                C.c_int32(b._dev.batch), C.c_uint64(w.t), C.c_void_p(b._dev.sample_idx.data_ptr()), st))
+                _lib.check(lib.rl_replay_sample(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
+                                                C.c_int32(b._dev.batch), C.c_uint64(self._t_key), C.c_void_p(b._dev.sample_idx.data_ptr()), st))
             else:                                               # random.sample(deque, 64), D3QN.py:138-142
-                _lib.check(lib.rl_replay_sample_uniform(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
-                                                        C.c_int32(b._dev.batch), C.c_uint64(w.t), C.c_int32(0), C.c_int32(1), C.c_int32(0),
+                _lib.check(lib.rl_replay_sample_uniform(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
+                                                        C.c_int32(b._dev.batch), C.c_uint64(self._t_key), C.c_int32(0), C.c_int32(1), C.c_int32(0),
                                                         C.c_void_p(b._dev.sample_idx.data_ptr()), C.c_void_p(self._sample_status.data_ptr()), st))
+            if self.sequential_events and not b.PRIORITIZED and getattr(self, "_seq_event", None) is not None:
+                if int(self._sample_status) & 1:                      # the reference raises inside train(), before any update
+                    self._sample_status.zero_()
+                    raise ValueError("Sample larger than population or is negative")     # random.sample, D3QN.py:140
+            if self.sample_override is not None and getattr(self, "_seq_event", None) is not None:
+                idx = self.sample_override(*self._seq_event)          # tests: the reference's recorded np.random.choice result
+                b._dev.sample_idx[0].copy_(torch.as_tensor(idx, dtype=torch.int32))
             ev0 = ev1 = None
             if self.kernel_events is not None:           # bench.py: CUDA-event time of the event kernel alone (roofline)
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -263,17 +338,17 @@ class Environment:
                 if ev0 is not None:
                     ev0.record()
                 if self._learn_fp16:
-                    _lib.check(lib.rl_brain_learn_h(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                    _lib.check(lib.rl_brain_learn_h(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
                                                     C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs),
                                                     C.c_void_p(b._dev.wimg_eh.data_ptr()), C.c_void_p(b._dev.wimg_th.data_ptr()), st))
                 else:
-                    _lib.check(lib.rl_brain_learn_tc(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                    _lib.check(lib.rl_brain_learn_tc(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
                                                      C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs),
                                                      C.c_void_p(b._dev.wimg_e.data_ptr()), C.c_void_p(b._dev.wimg_t.data_ptr()), st))
             else:
                 if ev0 is not None:
                     ev0.record()
-                _lib.check(lib.rl_brain_learn(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                _lib.check(lib.rl_brain_learn(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
                                               C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs), st))
             if ev0 is not None:                          # brackets the event kernel + its 0.03 ms slab reduction
                 ev1.record()
@@ -288,13 +363,13 @@ class Environment:
             _lib.check(lib.rl_brain_adam(C.byref(b._dev.learn_bufs), st))
             self.gpu_launches += 2
             if b.PRIORITIZED:
-                _lib.check(lib.rl_replay_update_prio(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                _lib.check(lib.rl_replay_update_prio(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
                                                      C.c_int32(b._dev.batch), C.c_void_p(b._dev.sample_idx.data_ptr()),
                                                      C.c_void_p(b._dev.new_prio.data_ptr()), st))
                 self.gpu_launches += 1
             synced = n_epi % int(b.soft_update_freq) == 0
             if synced:                                        # PERD3QN.py:124-125, only if learn() was called
-                cond = self._gate.data_ptr() + 4 * (g * _lib.N_ROW_KINDS + _lib.ROWS_STORE)
+                cond = self._gate_base + 4 * (g * _lib.N_ROW_KINDS + _lib.ROWS_STORE)
                 sync_target(b._dev, w, cond)
                 self.gpu_launches += 1
             if self.precision == "tf32":                      # operand images follow the parameters
@@ -306,16 +381,16 @@ class Environment:
         smooth-L1, Adam step); then target <- agent at every trigger, trained or not."""
         w, lib, b = self.world, self.world.lib, self.brains[g]
         for it in range(5):
-            _lib.check(lib.rl_replay_sample_uniform(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
-                                                    C.c_int32(32), C.c_uint64(w.t), C.c_int32(it), C.c_int32(5), C.c_int32(b.min_buffer),
+            _lib.check(lib.rl_replay_sample_uniform(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
+                                                    C.c_int32(32), C.c_uint64(self._t_key), C.c_int32(it), C.c_int32(5), C.c_int32(b.min_buffer),
                                                     C.c_void_p(b._dev.sample_idx.data_ptr()), None, st))
-            _lib.check(lib.rl_brain_learn_dqn(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+            _lib.check(lib.rl_brain_learn_dqn(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
                                               C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs), st))
             if self.dist:
                 self._allreduce_grads([g])
             _lib.check(lib.rl_brain_adam(C.byref(b._dev.learn_bufs), st))
             self.gpu_launches += 6
-        cond = self._gate.data_ptr() + 4 * (g * _lib.N_ROW_KINDS + _lib.ROWS_EVENT)
+        cond = self._gate_base + 4 * (g * _lib.N_ROW_KINDS + _lib.ROWS_EVENT)
         sync_target(b._dev, w, cond)
         self.gpu_launches += 1
 
@@ -325,21 +400,21 @@ class Environment:
         refreshed); epsilon steps once per optimizer step; target_model <- model at every trigger, trained or not."""
         w, lib, b = self.world, self.world.lib, self.brains[g]
         tr, dev = b.memory, b._dev
-        _lib.check(lib.rl_sumtree_sample(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
-                                         C.byref(tr.bufs), C.c_int32(64), C.c_uint64(w.t), C.c_void_p(dev.sample_idx.data_ptr()),
+        _lib.check(lib.rl_sumtree_sample(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
+                                         C.byref(tr.bufs), C.c_int32(64), C.c_uint64(self._t_key), C.c_void_p(dev.sample_idx.data_ptr()),
                                          C.c_void_p(tr.ev_weight.data_ptr()), st))
-        _lib.check(lib.rl_brain_learn_perdqn(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+        _lib.check(lib.rl_brain_learn_perdqn(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
                                              C.c_void_p(dev.sample_idx.data_ptr()), C.c_void_p(tr.ev_weight.data_ptr()),
                                              C.byref(dev.learn_bufs), st))
         if self.dist:
             self._allreduce_grads([g])
         _lib.check(lib.rl_brain_adam(C.byref(dev.learn_bufs), st))
-        _lib.check(lib.rl_sumtree_update(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+        _lib.check(lib.rl_sumtree_update(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
                                          C.byref(tr.bufs), C.c_int32(64), C.c_void_p(dev.sample_idx.data_ptr()),
                                          C.c_void_p(dev.new_prio.data_ptr()), st))
         _lib.check(lib.rl_perdqn_epsilon_step(C.byref(dev.learn_bufs), C.c_void_p(self._eps.data_ptr() + 8 * g),
                                               C.c_double(b.epsilon_min), C.c_double(b.epsilon_decay), st))
-        cond = self._gate.data_ptr() + 4 * (g * _lib.N_ROW_KINDS + _lib.ROWS_EVENT)
+        cond = self._gate_base + 4 * (g * _lib.N_ROW_KINDS + _lib.ROWS_EVENT)
         sync_target(dev, w, cond)
         self.gpu_launches += 10
 
@@ -347,11 +422,11 @@ class Environment:
         """PPO: learn() (PPO.py:71-77): put_data for every age > 1 agent; every trigger consumes the list and runs
         k_epoch optimizer steps (PPO.py:136-162)."""
         w, lib, b = self.world, self.world.lib, self.brains[g]
-        _lib.check(lib.rl_ppo_store(C.byref(w.cfg), C.byref(w.bufs), C.byref(self.rows.bufs), C.c_int32(g),
+        _lib.check(lib.rl_ppo_store(C.byref(w.cfg), C.byref(w.bufs), C.byref(self._rb_store), C.c_int32(g),
                                     C.c_void_p(self._prob.data_ptr()), C.c_int32(train_freq), C.byref(b._replay.bufs), st))
         self.gpu_launches += 3
         for _ in range(int(b.k_epoch)):
-            _lib.check(lib.rl_ppo_epoch(C.byref(w.cfg), C.byref(self.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+            _lib.check(lib.rl_ppo_epoch(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
                                         C.byref(b._dev.learn_bufs), st))
             if self.dist:
                 self._allreduce_grads([g])
