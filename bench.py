@@ -5,7 +5,7 @@ PERD3QN x2 training (BASELINE.json configs[2] per GPU; worlds are sharded across
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 \
         bench.py --gpus 8 --steps 20 --warmup 5
-    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1     # CPU port of the same loop, all host cores
+    python bench.py --impl reference --gpus 1 --steps 20 --warmup 5    # the unmodified Python reference (baseline/_ref), all host cores
 
 One step = one pass of the reference's trainer loop body (Helpers/trainer.py:85-99) over every world:
 act (batched get_action) -> env.step -> learn (store, PER sample, one 64-row train() event per trigger, Adam)
@@ -40,6 +40,7 @@ def parse():
                     help="train() events: tcgen05 with fp16 operands (default) or tf32 operands (both 11 significant bits, fp32 accumulate), or fp32 CUDA-core FMA")
     ap.add_argument("--cpu-worlds-per-core", type=int, default=2)
     ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--ref-steps", type=int, default=30, help="timed steps per process of the unmodified reference (cpu_baseline)")
     return ap.parse_args()
 
 
@@ -64,16 +65,38 @@ def cpu_arm(args, steps, warmup, procs=None):
     return a / sec, procs, sample, sec
 
 
+def ref_python_arm(steps, warmup, procs=0):
+    """The UNMODIFIED Python reference (baseline/_ref, baseline/run_ref.py; nothing of reinlife_b200 / oracle on that
+    path): one process per usable host core, each one saturated 30x30x100-agent world with PERD3QNx2 training, the
+    reference's own loop body.  The reference is sequential per world, so its per-core rate does not depend on how many
+    worlds a core is given; the aggregate over all cores is the whole box's CPU throughput for this workload."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import run_ref
+    if not run_ref.available():
+        return None
+    t0 = time.perf_counter()
+    value, procs, res = run_ref.run_parallel(procs, steps, warmup)
+    sample = (f"{procs} single-thread processes x 1 world x {steps} steps (+{warmup} warm-up) of the unmodified reference "
+              f"(baseline/_ref): get_action -> env.step -> learn -> update_env per agent, PERD3QNx2 exploration=0, top-up excluded")
+    return value, procs, sample, max(r["sec"] for r in res), time.perf_counter() - t0
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, procs, sample, sec = cpu_arm(args, max(1, args.steps), max(0, args.warmup))
+    kind = "reference"
+    ref = ref_python_arm(max(1, args.steps), max(0, args.warmup))
+    if ref is not None:
+        val, procs, sample, sec, _ = ref
+    else:                                   # baseline/_ref did not travel: the oracle port of the same loop
+        kind = "port"
+        val, procs, sample, sec = cpu_arm(args, max(1, args.steps), max(0, args.warmup))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(1, args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "grid": [H, W], "agents_per_world": TARGET},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -338,9 +361,19 @@ def run_b200(args):
         if world_size == 1 and not args.no_cpu_baseline:
             try:
                 val, procs, sample, _ = cpu_arm(args, args.cpu_steps, 2)
-                line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample}
+                port = {"value": val, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample}
             except Exception as e:   # the baseline is a report, never a reason to lose the GPU number
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+                port = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+            try:
+                ref = ref_python_arm(args.ref_steps, 5)
+            except Exception as e:
+                ref = None
+                port["reference_error"] = str(e)[-300:]
+            if ref is not None:              # the unmodified Python reference is the baseline; the (7x faster) oracle port beside it
+                line["cpu_baseline"] = {"value": ref[0], "unit": UNIT, "cores": ref[1], "kind": "reference", "sample": ref[2]}
+                line["cpu_baseline_port"] = port
+            else:
+                line["cpu_baseline"] = port
         print(json.dumps(line))
     if world_size > 1:
         dist.destroy_process_group()

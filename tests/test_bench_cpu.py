@@ -1,4 +1,5 @@
-"""bench.py contract checks that need no GPU: the reference arm (CPU port of the same loop on the host cores) prints ONE
+"""bench.py contract checks that need no GPU: the reference arm (the unmodified Python reference from baseline/_ref when
+it is installed, else the oracle port of the same loop, on the host cores) prints ONE
 JSON line with the keys the driver reads, and the B200 arm refuses to run without a CUDA device (no CPU fallback)."""
 import json
 import os
@@ -18,7 +19,8 @@ def test_reference_arm_prints_the_contract_line():
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1 and "workload" in d["config"]
     cb, e2e = d["cpu_baseline"], d["e2e"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    have_ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "ReinLife"))
+    assert cb["kind"] == ("reference" if have_ref else "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert e2e["value"] == d["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
 
 
