@@ -388,6 +388,11 @@ int rl_world_stats_scratch_doubles(const rl_world_cfg* cfg);   /* size of scratc
 int rl_tc_mma_bench(int M, int N, int ksteps, int mode, int iters, long long* out_host);
 
 int rl_tc_gemm_test(const float* a_img, const float* b_img, float* d, int M, int N, int K, int a_mn, int b_mn, void* stream);
+/* Test hook: one-tile tcgen05 kind::f16 GEMM  D[M,N] = A * B^T  on fp16 operand images with caller-supplied descriptor
+ * geometry (leading / stride byte offsets, byte advance per K = 16 step) and major-ness (a_mn / b_mn = 1: MN-major). */
+int rl_tc_gemm_test_h(const void* a_img, const void* b_img, float* d, int M, int N, int K, int a_halves, int b_halves,
+                      uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kstep, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep,
+                      int a_mn, int b_mn, void* stream);
 
 
 /* ------------------------------------------------------------------------------------------------
@@ -414,6 +419,13 @@ int rl_brain_build_wimg_h(int32_t kind, const float* params, void* wimg_h, void*
 int rl_brain_act_h(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_rows_bufs* rows, int32_t gene,
                    const rl_brain_act* brain, const void* wimg_eval_h, uint64_t t_act, float* q_out, void* stream);
 int rl_brain_learn_h(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                     const int32_t* sample_idx, const rl_learn_bufs* learn, const void* wimg_eval_h, const void* wimg_target_h,
+                     void* stream);
+
+/* The same events, TWO per CTA iteration in batch-major form (csrc/tc_pair_kernels.cu: M = 128 tiles, N = 128 / 256 per MMA,
+ * MN-major fp16 operands for the weight-gradient GEMMs, no transposed images).  Same contract, weight images, outputs and
+ * tolerance as rl_brain_learn_h; the default event kernel of precision="fp16". */
+int rl_brain_learn_p(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
                      const int32_t* sample_idx, const rl_learn_bufs* learn, const void* wimg_eval_h, const void* wimg_target_h,
                      void* stream);
 

@@ -411,6 +411,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_tc2(const TcLear
             go_signal();                                                                     // -> target L1^T
             gather_load(xr, P.rp.obs + ring0 * RL_K1, meta);
             if (n_my > 1) { load_meta_a(1, blockIdx.x + gridDim.x); row_n1 = P.ev_rows[blockIdx.x + gridDim.x]; }
+            epi_bar();          // event 1's ring positions (written by warps 6-7) are read by every warp's prefetch_rows below
         }
         // L1 epilogue: lane = feature k1, this warp's 32 batch columns; H1 = relu(D + b1)
         auto l1_epilogue = [&](const float* bias, bool eval) {
@@ -965,6 +966,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_learn_dueling_h(const TcLearnP
             go_signal();
             gather_load(xr, P.rp.obs + ring0 * RL_K1, meta);
             if (n_my > 1) { load_meta_a(1, blockIdx.x + gridDim.x); row_n1 = P.ev_rows[blockIdx.x + gridDim.x]; }
+            epi_bar();          // event 1's ring positions (written by warps 6-7) are read by every warp's prefetch_rows below
         }
         // L1 epilogue: lane = feature k1, this warp's 32 batch columns; H1 = relu(D + b1)
         auto l1_epilogue = [&](const float* bias, bool eval) {

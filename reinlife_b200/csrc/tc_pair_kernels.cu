@@ -1,0 +1,604 @@
+// tc_pair_kernels.cu -- k_learn_dueling_p: the train() events of the dueling brains (PERD3QN.py:94-115, D3QN.py:97-116)
+// on the 5th-gen tensor cores, TWO events (2 x 64 rows) per CTA iteration in BATCH-MAJOR form.
+//
+// Why a second design next to tc_kernels.cu::k_learn_dueling_h.  tcgen05.mma costs its issuing thread ~100-230 cycles
+// whatever its N (scripts/tc_mma_bench.py), so an event processed alone (batch 64) is issue-bound: the transposed-output
+// form of k_learn_dueling_h reaches M = 128 but every MMA is N = 64, every operand needs a batch-major AND a
+// feature-major image (scalar scatter stores), and every stage is handed over once per 64 rows.  Here
+//   * a pair of events is one M = 128 tile: D[batch 128][features] = Act[128][K] * W[features][K]^T, N = 128 / 256 per MMA
+//     -- the same ~117 MMA instructions now cover two events;
+//   * fp16 operands may be MN-major (scripts/tc_probe_h.py pins it): the weight-gradient GEMMs dW2 = H1^T dH2,
+//     dW1 = dH1^T X, dWh = H2^T dOut read the SAME batch-major images the forward wrote (core matrix = 8 rows x 16 B in
+//     both readings), so no transposed image exists any more: X, H1, H2, dOut only, dH2 / dH1 written in place;
+//   * an epilogue thread owns one batch ROW: activations leave as 16-byte vector stores, the dueling combine / TD
+//     error / dOut of a row are thread-local, bias gradients are warp reduce-scatters (db2, dbh) or ride a GEMM for free
+//     (db1 = column 159 of dW1, whose X column is set to 1 -- the matching W1 rows are structural zeros);
+//   * dW2 stays resident in TMEM across all pairs of the CTA, dW1 is flushed once per pair with 16-byte vector reds.
+// Same contract, outputs and tolerance as rl_brain_learn_h (tests/test_scale_gpu.py, tests/test_tc_gpu.py).
+#include <cuda_fp16.h>
+#include "tc_tile.cuh"
+#include "models.cuh"
+
+namespace {
+
+using namespace tc;
+using mlp::mbar_init; using mlp::mbar_wait; using mlp::fence_mbar_init; using mlp::fence_proxy_async; using mlp::bulk_load;
+
+constexpr int R = 64;                    // rows per event
+constexpr int PB = 128;                  // rows per pair
+constexpr int NEPI = 256;                // epilogue threads (warps 0-7)
+constexpr int NTH = NEPI + 64;           // + producer warp (8) + MMA issuer warp (9)
+constexpr int NSP = 8;                   // weight-chunk ring slots of 8 KB
+constexpr int HCH = 4096;                // halves per weight chunk
+constexpr float H_SCALE = 256.0f;        // backward operands are scaled by 2^8 (exact), removed when gradients leave TMEM
+
+// weight image chunk ids (tc_kernels.cu::k_build_wimg_dueling_h)
+constexpr int WI_W1 = 0, WI_W2K = 5, WI_WH = 13, WI_WHT = 14, WI_W2T = 15;
+constexpr int SCHED_P = 37;              // chunks per pair: t W1[5] W2K[8] WH | e W1[5] W2K[8] WH WHT W2T[8]
+
+// ---- shared memory (bytes) ----
+constexpr int PO_X = 0;                                   // X' / X [128][160] halves
+constexpr int PO_H1 = PO_X + PB * 160 * 2;                // H1 -> dH1 [128][128]
+constexpr int PO_H2 = PO_H1 + PB * 128 * 2;               // H2 -> dH2 [128][256]
+constexpr int PO_STG = PO_H2 + PB * 256 * 2;              // weight ring
+constexpr int PO_DOUT = PO_STG + NSP * HCH * 2;           // dOut [128][16] halves
+constexpr int PO_BIAS = PO_DOUT + PB * 16 * 2;            // b1[128] b2[256] bh[16] x {target, eval} floats
+constexpr int PO_RED = PO_BIAS + 4 * 800;                 // reduction scratch floats [64]
+constexpr int PO_META = PO_RED + 4 * 64;                  // [2] x { idx[128] act[128] rew[128] dn[128] } int / float
+constexpr int PO_RING = PO_META + 2 * 4 * 4 * PB;         // [2][2] ring base (elements) per buffer / event, 64-bit
+constexpr int PO_BARS = PO_RING + 2 * 2 * 8;
+constexpr size_t PAIR_SMEM = PO_BARS + 8 * (2 * NSP + 2) + 16;
+static_assert(PAIR_SMEM <= 227 * 1024 && PO_BARS % 8 == 0 && PO_RING % 8 == 0, "shared memory budget");
+
+// interleaved no-swizzle fp16 image of width K: 8 rows x 16 bytes core matrices
+__device__ __forceinline__ int himg(int r, int c, int K) { return (r >> 3) * (K * 8) + (c >> 3) * 64 + (r & 7) * 8 + (c & 7); }
+// K-major reading (rows = M / N index): LBO = next 8 k (128 B), SBO = next 8 rows (K * 16 B); one K = 16 step = +256 B
+__device__ __forceinline__ uint64_t dk(uint32_t addr, int K) { return make_desc(addr, 128u, (uint32_t)K * 16u); }
+// MN-major reading (rows = k index, columns = M / N index): SBO = next 8 columns (128 B), LBO = next 8 rows (W * 16 B);
+// one K = 16 step = +2 * W * 16 B
+__device__ __forceinline__ uint64_t dm(uint32_t addr, int W) { return make_desc(addr, (uint32_t)W * 16u, 128u); }
+__host__ __device__ constexpr uint32_t idesc_h(int M, int N, int a_mn, int b_mn) {      // kind::f16: fp16 A/B, fp32 D
+    return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_h(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ uint32_t pk(float a, float b) {
+    return (uint32_t)__half_as_ushort(__float2half_rn(a)) | ((uint32_t)__half_as_ushort(__float2half_rn(b)) << 16);
+}
+__device__ __forceinline__ float sat(float x) { return fminf(fmaxf(x, -60000.f), 60000.f); }
+__device__ __forceinline__ float hlo(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xFFFFu))); }
+__device__ __forceinline__ float hhi(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }
+__device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void head_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+
+// Sum v[0..31] over the 32 lanes of the warp; lane L returns the total of element L (reduce-scatter, 31 shuffles).
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const bool up = (lane & w) != 0;
+#pragma unroll
+        for (int k = 0; k < w; ++k) {
+            const float send = up ? v[k] : v[k + w];
+            const float keep = up ? v[k + w] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+        }
+    }
+    return v[0];
+}
+
+struct PairParams {
+    rl_world_cfg cfg;
+    const int32_t* ev_rows;
+    const int32_t* ev_total;
+    rl_replay_bufs rp;
+    const int32_t* sample_idx;
+    rl_learn_bufs lb;
+    const __half* wimg_e;
+    const __half* wimg_t;
+};
+
+__device__ __forceinline__ void sched_pair(int i, int& net, int& chunk) {
+    if (i < 5) { net = 0; chunk = WI_W1 + i; }
+    else if (i < 13) { net = 0; chunk = WI_W2K + (i - 5); }
+    else if (i == 13) { net = 0; chunk = WI_WH; }
+    else if (i < 19) { net = 1; chunk = WI_W1 + (i - 14); }
+    else if (i < 27) { net = 1; chunk = WI_W2K + (i - 19); }
+    else if (i == 27) { net = 1; chunk = WI_WH; }
+    else if (i == 28) { net = 1; chunk = WI_WHT; }
+    else { net = 1; chunk = WI_W2T + (i - 29); }
+}
+
+__global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) {
+    using L = Layout<RL_MODEL_DUELING>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __half* sX = reinterpret_cast<__half*>(smem + PO_X);
+    __half* sH1 = reinterpret_cast<__half*>(smem + PO_H1);
+    __half* sH2 = reinterpret_cast<__half*>(smem + PO_H2);
+    __half* sStg = reinterpret_cast<__half*>(smem + PO_STG);
+    __half* sDout = reinterpret_cast<__half*>(smem + PO_DOUT);
+    float* bias_t = reinterpret_cast<float*>(smem + PO_BIAS);
+    float* bias_e = bias_t + 400;
+    float* red = reinterpret_cast<float*>(smem + PO_RED);
+    int* meta = reinterpret_cast<int*>(smem + PO_META);
+    unsigned long long* ringb = reinterpret_cast<unsigned long long*>(smem + PO_RING);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PO_BARS);
+    uint64_t* full = bars; uint64_t* empty = bars + NSP; uint64_t* done = bars + 2 * NSP; uint64_t* go = done + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(go + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* G = P.lb.grad_scratch + (size_t)blockIdx.x * L::N_TRAIN;
+    const int total = *P.ev_total;
+    const int n_my = total > (int)blockIdx.x ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int n_pairs = (n_my + 1) >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSP; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1); mbar_init(go, NEPI);
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x < NEPI) {
+        const float* Pe = P.lb.params; const float* Pt = P.lb.target;
+        for (int i = threadIdx.x; i < 400; i += NEPI) {
+            const int o = i < 128 ? L::OFF_B1 + i : i < 384 ? L::OFF_B2 + (i - 128) : L::OFF_BH + (i - 384);
+            const bool ok = i < 384 + 9;
+            bias_t[i] = ok ? Pt[o] : 0.f; bias_e[i] = ok ? Pe[o] : 0.f;
+        }
+        for (int i = threadIdx.x; i < L::N_TRAIN / 4; i += NEPI) reinterpret_cast<float4*>(G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t T0 = tmem, T_DW2 = tmem + 256;
+    const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH2 = smem_u32(sH2), aD = smem_u32(sDout);
+
+    if (warp == 8) {
+        // =================================== weight-stream producer ===================================
+        if (lane == 0) {
+            const uint32_t n_chunks = (uint32_t)n_pairs * SCHED_P;
+            for (uint32_t produced = 0; produced < n_chunks; ++produced) {
+                const uint32_t slot = produced % NSP;
+                if (produced >= NSP) mbar_wait(&empty[slot], ((produced / NSP) - 1) & 1);
+                int net, ch; sched_pair(produced % SCHED_P, net, ch);
+                bulk_load(sStg + slot * HCH, (net ? P.wimg_e : P.wimg_t) + (size_t)ch * HCH, HCH * 2, &full[slot]);
+            }
+        }
+    } else if (warp == 9) {
+        // =================================== MMA issuer ===================================
+        if (lane == 0) {
+            uint32_t consumed = 0, go_no = 0;
+            auto wait_go = [&]() { mbar_wait(go, go_no & 1); ++go_no; fence_after(); };
+            auto chunk_wait = [&]() -> uint32_t {
+                const uint32_t slot = consumed % NSP;
+                mbar_wait(&full[slot], (consumed / NSP) & 1);
+                fence_after();
+                return smem_u32(sStg + slot * HCH);
+            };
+            auto chunk_release = [&]() { mma_commit(&empty[consumed % NSP]); ++consumed; };
+            // L1: D[128 b][128 k1] = X[128][160] W1[128][160]^T -- 5 chunks [128 n][32 k], 2 k-steps each
+            auto l1 = [&]() {
+                const uint32_t id = idesc_h(128, 128, 0, 0);
+                uint64_t a = dk(aX, 160);
+#pragma unroll 1
+                for (int c = 0; c < 5; ++c) {
+                    const uint64_t b = dk(chunk_wait(), 32);
+                    mma_h(T0, a, b, id, c != 0);
+                    mma_h(T0, a + 16u, b + 16u, id, 1u);
+                    a += 32u;
+                    chunk_release();
+                }
+                mma_commit(done);
+            };
+            // L2: D[128 b][256 n2] = H1[128][128] W2[256][128]^T -- 8 chunks [256 n][16 k], one k-step each
+            auto l2 = [&]() {
+                const uint32_t id = idesc_h(128, 256, 0, 0);
+                uint64_t a = dk(aH1, 128);
+#pragma unroll 1
+                for (int c = 0; c < 8; ++c) {
+                    mma_h(T0, a, dk(chunk_wait(), 16), id, c != 0);
+                    a += 16u;
+                    chunk_release();
+                }
+                mma_commit(done);
+            };
+            // head: D[128 b][16] = H2[128][256] Wh[16][256]^T -- one chunk, 16 k-steps
+            auto head = [&]() {
+                const uint32_t id = idesc_h(128, 16, 0, 0);
+                uint64_t a = dk(aH2, 256), b = dk(chunk_wait(), 256);
+#pragma unroll 1
+                for (int ks = 0; ks < 16; ++ks) { mma_h(T0, a, b, id, ks != 0); a += 16u; b += 16u; }
+                chunk_release();
+                mma_commit(done);
+            };
+            for (int p = 0; p < n_pairs; ++p) {
+                wait_go(); l1();                                   // target net
+                wait_go(); l2();
+                wait_go(); head();
+                wait_go(); l1();                                   // eval net
+                wait_go(); l2();
+                wait_go(); head();
+                wait_go();
+                {   // dH2 half 0 (n2 < 128) -> columns 128..255: A = dOut [128][16], B = Wh^T chunk rows 0..127 [256 n2][16 j]
+                    const uint32_t wht = chunk_wait();
+                    mma_h(T0 + 128, dk(aD, 16), dk(wht, 16), idesc_h(128, 128, 0, 0), 0u);
+                    // dWh[n2][j] = sum_b H2[b][n2] dOut[b][j]: A = H2 read MN-major (M = n2 half), B = dOut read MN-major, K = 128 rows
+                    const uint32_t id = idesc_h(128, 16, 1, 1);
+#pragma unroll 1
+                    for (int mh = 0; mh < 2; ++mh) {
+                        uint64_t a = dm(aH2 + mh * 2048u, 256), b = dm(aD, 16);
+#pragma unroll 1
+                        for (int ks = 0; ks < 8; ++ks) { mma_h(T0 + 16 * mh, a, b, id, ks != 0); a += 512u; b += 32u; }
+                    }
+                    mma_commit(done);
+                    wait_go();                                     // dWh drained: dH2 half 1 (n2 >= 128) -> columns 0..127
+                    mma_h(T0, dk(aD, 16), dk(wht + 4096u, 16), idesc_h(128, 128, 0, 0), 0u);
+                    chunk_release();
+                    mma_commit(done);
+                }
+                wait_go();
+                {   // dH1[128 b][128 k1] = dH2[128][256] W2^T[128 k1][256 n2]^T: 8 chunks [128][32], 2 k-steps each
+                    const uint32_t id = idesc_h(128, 128, 0, 0);
+                    uint64_t a = dk(aH2, 256);
+#pragma unroll 1
+                    for (int c = 0; c < 8; ++c) {
+                        const uint64_t b = dk(chunk_wait(), 32);
+                        mma_h(T0, a, b, id, c != 0);
+                        mma_h(T0, a + 16u, b + 16u, id, 1u);
+                        a += 32u;
+                        chunk_release();
+                    }
+                    // dW2[k1][n2] += sum_b H1[b][k1] dH2[b][n2]: both images read MN-major, accumulator resident in TMEM
+                    const uint32_t id2 = idesc_h(128, 256, 1, 1);
+                    uint64_t a2 = dm(aH1, 128), b2 = dm(aH2, 256);
+#pragma unroll 1
+                    for (int ks = 0; ks < 8; ++ks) { mma_h(T_DW2, a2, b2, id2, (p != 0 || ks != 0) ? 1u : 0u); a2 += 256u; b2 += 512u; }
+                    mma_commit(done);
+                }
+                wait_go();
+                {   // dW1[k1][x] = sum_b dH1[b][k1] X[b][x]: dH1 (in the H1 region) and X read MN-major, N = 160
+                    const uint32_t id = idesc_h(128, 160, 1, 1);
+                    uint64_t a = dm(aH1, 128), b = dm(aX, 160);
+#pragma unroll 1
+                    for (int ks = 0; ks < 8; ++ks) { mma_h(T0, a, b, id, ks != 0); a += 256u; b += 320u; }
+                    mma_commit(done);
+                }
+            }
+        }
+    } else {
+        // =================================== epilogue warps ===================================
+        uint32_t done_no = 0;
+        const int q = warp & 3, hh = warp >> 2;
+        const int row = q * 32 + lane;                    // batch row of the pair == TMEM lane
+        const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+        const int S = P.cfg.slot_cap, cap = P.rp.capacity;
+        auto go_signal = [&]() { fence_proxy_async(); fence_before(); mbar_arrive(go); };
+        auto wait_done = [&]() { mbar_wait(done, done_no & 1); ++done_no; fence_after(); };
+        // ---- metadata of a pair: ring positions, actions, rewards, dones of its 128 sampled rows ----
+        auto load_meta = [&](int buf, int p) {
+            if (threadIdx.x < PB) {
+                const int r = threadIdx.x, ev = r >> 6;
+                const int it = 2 * p + ev;
+                const bool valid = it < n_my;
+                const int e = (int)blockIdx.x + (valid ? it : 2 * p) * (int)gridDim.x;     // a missing second event mirrors the first
+                const size_t ring = (size_t)(P.ev_rows[e] / S) * cap;
+                const int i = max(P.sample_idx[(size_t)e * R + (r & 63)], 0);
+                int* m = meta + buf * 4 * PB;
+                m[r] = i;
+                m[PB + r] = P.rp.action[ring + i];
+                reinterpret_cast<float*>(m)[2 * PB + r] = P.rp.reward[ring + i];
+                reinterpret_cast<float*>(m)[3 * PB + r] = (float)P.rp.done[ring + i];
+                if ((r & 63) == 0) ringb[buf * 2 + ev] = (unsigned long long)ring;
+            }
+        };
+        // ---- 128 rows x 160 floats from the replay ring -> packed fp16 in registers (unit = 8 consecutive columns) ----
+        uint4 xh[10];
+        auto gather_load = [&](const float* __restrict__ src, int buf) {
+            const int* ids = meta + buf * 4 * PB;
+#pragma unroll
+            for (int u = 0; u < 10; ++u) {
+                const int v = threadIdx.x + u * NEPI;
+                const int rr = v & 7, o4 = (v >> 3) & 3, blk = v >> 5;
+                const int rg = blk / 5, og = blk - rg * 5;
+                const int r = rg * 8 + rr, oct = og * 4 + o4;
+                const float4* g = reinterpret_cast<const float4*>(src + ((size_t)ringb[buf * 2 + (r >> 6)] + ids[r]) * RL_K1) + oct * 2;
+                const float4 a = __ldg(g), b = __ldg(g + 1);
+                xh[u] = make_uint4(pk(a.x, a.y), pk(a.z, a.w), pk(b.x, b.y), oct == 19 ? pk(b.z, 1.0f) : pk(b.z, b.w));   // column 159 := 1 (db1)
+            }
+        };
+        auto gather_store = [&]() {
+#pragma unroll
+            for (int u = 0; u < 10; ++u) {
+                const int v = threadIdx.x + u * NEPI;
+                const int rr = v & 7, o4 = (v >> 3) & 3, blk = v >> 5;
+                const int rg = blk / 5, og = blk - rg * 5;
+                *reinterpret_cast<uint4*>(sX + himg(rg * 8 + rr, (og * 4 + o4) * 8, 160)) = xh[u];
+            }
+        };
+        // ---- L1 epilogue: this thread's row, columns [64 hh, 64 hh + 64): H1 = relu(D + b1) ----
+        auto l1_epilogue = [&](const float* bias) {
+#pragma unroll
+            for (int cb = 0; cb < 2; ++cb) {
+                const int c0 = hh * 64 + cb * 32;
+                float v[32];
+                tmem_ld32(T0 + t_lane + c0, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 b = *reinterpret_cast<const float4*>(bias + c0 + j4 * 4);
+                    v[j4 * 4] = fmaxf(v[j4 * 4] + b.x, 0.f); v[j4 * 4 + 1] = fmaxf(v[j4 * 4 + 1] + b.y, 0.f);
+                    v[j4 * 4 + 2] = fmaxf(v[j4 * 4 + 2] + b.z, 0.f); v[j4 * 4 + 3] = fmaxf(v[j4 * 4 + 3] + b.w, 0.f);
+                }
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8)
+                    *reinterpret_cast<uint4*>(sH1 + himg(row, c0 + j8 * 8, 128)) =
+                        make_uint4(pk(v[j8 * 8], v[j8 * 8 + 1]), pk(v[j8 * 8 + 2], v[j8 * 8 + 3]), pk(v[j8 * 8 + 4], v[j8 * 8 + 5]), pk(v[j8 * 8 + 6], v[j8 * 8 + 7]));
+            }
+        };
+        // ---- L2 epilogue: this thread's row, columns [128 hh, 128 hh + 128): H2 = relu(D + b2) ----
+        auto l2_epilogue = [&](const float* bias) {
+#pragma unroll 1
+            for (int cb = 0; cb < 4; ++cb) {
+                const int c0 = hh * 128 + cb * 32;
+                float v[32];
+                tmem_ld32(T0 + t_lane + c0, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 b = *reinterpret_cast<const float4*>(bias + 128 + c0 + j4 * 4);
+                    v[j4 * 4] = fmaxf(v[j4 * 4] + b.x, 0.f); v[j4 * 4 + 1] = fmaxf(v[j4 * 4 + 1] + b.y, 0.f);
+                    v[j4 * 4 + 2] = fmaxf(v[j4 * 4 + 2] + b.z, 0.f); v[j4 * 4 + 3] = fmaxf(v[j4 * 4 + 3] + b.w, 0.f);
+                }
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8)
+                    *reinterpret_cast<uint4*>(sH2 + himg(row, c0 + j8 * 8, 256)) =
+                        make_uint4(pk(v[j8 * 8], v[j8 * 8 + 1]), pk(v[j8 * 8 + 2], v[j8 * 8 + 3]), pk(v[j8 * 8 + 4], v[j8 * 8 + 5]), pk(v[j8 * 8 + 6], v[j8 * 8 + 7]));
+            }
+        };
+        // ---- head epilogue (warps 0-3: one row each): out[0..8] of the row, mean of the advantages over the row's EVENT
+        //      (PERD3QN.py:202: advantage.mean() over the whole [64, 8] tensor) ----
+        auto head_epilogue = [&](const float* bias, float (&out)[9]) -> float {
+            float v[16];
+            tmem_ld16(T0 + t_lane, v);
+            tmem_wait_ld();
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) { out[j] = v[j] + bias[384 + j]; if (j < 8) s += out[j]; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) red[q] = s;
+            head_bar();
+            const float m = (q < 2 ? red[0] + red[1] : red[2] + red[3]) * (1.0f / (8 * R));
+            head_bar();
+            return m;
+        };
+
+        if (n_pairs > 0) {
+            load_meta(0, 0);
+            epi_bar();
+            gather_load(P.rp.next_obs, 0);
+            gather_store();
+            go_signal();                                            // -> target L1 of pair 0
+        }
+        for (int p = 0; p < n_pairs; ++p) {
+            const int buf = p & 1;
+            const int* idx = meta + buf * 4 * PB; const int* act = idx + PB;
+            const float* rew = reinterpret_cast<const float*>(idx + 2 * PB); const float* dn = rew + PB;
+            const bool more = p + 1 < n_pairs;
+            const int ev = row >> 6;
+            const bool valid = 2 * p + ev < n_my;
+            const int e = (int)blockIdx.x + (2 * p + ev) * (int)gridDim.x;
+            // ---------------- target net ----------------
+            gather_load(P.rp.obs, buf);                             // eval rows of this pair: in flight behind the target L1
+            wait_done();
+            l1_epilogue(bias_t);
+            go_signal();                                            // -> target L2
+            if (more) load_meta(buf ^ 1, p + 1);
+            wait_done();
+            l2_epilogue(bias_t);
+            gather_store();                                         // X image <- eval rows (the target L1 is done with X')
+            go_signal();                                            // -> target head
+            wait_done();
+            float nq = 0.f;
+            if (hh == 0) {
+                float o[9];
+                const float mean = head_epilogue(bias_t, o);
+                float mx = o[0];
+#pragma unroll
+                for (int j = 1; j < 8; ++j) mx = fmaxf(mx, o[j]);
+                nq = mx + o[8] - mean;
+            }
+            fence_before();
+            go_signal();                                            // -> eval L1
+            // ---------------- eval net ----------------
+            wait_done();
+            l1_epilogue(bias_e);
+            go_signal();                                            // -> eval L2
+            wait_done();
+            l2_epilogue(bias_e);
+            go_signal();                                            // -> eval head
+            wait_done();
+            if (hh == 0) {
+                // ---- TD target, loss, priorities, dOut of this row (PERD3QN.py:103-110), all thread-local ----
+                float o[9];
+                const float mean = head_epilogue(bias_e, o);
+                const int a = act[row];
+                float qsel = o[0];
+#pragma unroll
+                for (int j = 1; j < 8; ++j) qsel = (a == j) ? o[j] : qsel;
+                const float qa = qsel + o[8] - mean;
+                const float y = rew[row] + P.lb.gamma * (1.0f - dn[row]) * nq;
+                const float diff = qa - y;
+                float g = valid ? 2.0f * diff * (1.0f / R) : 0.f;
+                float sq = diff * diff, gs = g;
+#pragma unroll
+                for (int o2 = 16; o2 > 0; o2 >>= 1) { sq += __shfl_xor_sync(0xffffffffu, sq, o2); gs += __shfl_xor_sync(0xffffffffu, gs, o2); }
+                if (lane == 0) { red[8 + q] = sq; red[16 + q] = gs; }
+                head_bar();
+                const float loss = (q < 2 ? red[8] + red[9] : red[10] + red[11]) * (1.0f / R);
+                const float shift = (q < 2 ? red[16] + red[17] : red[18] + red[19]) * (1.0f / (8 * R));
+                if (valid) {
+                    P.lb.new_prio[(size_t)e * R + (row & 63)] = fabsf(nq - qa);
+                    if ((row & 63) == 0) P.lb.loss[e] = loss;
+                }
+                float d[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) d[j] = j < 8 ? ((j == a ? g : 0.f) - (valid ? shift : 0.f)) : (j == 8 ? g : 0.f);
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[j] = pk(sat(d[2 * j] * H_SCALE), sat(d[2 * j + 1] * H_SCALE));
+                *reinterpret_cast<uint4*>(sDout + himg(row, 0, 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(sDout + himg(row, 8, 16)) = make_uint4(w[4], w[5], w[6], w[7]);
+                // dbh[j] = sum over the rows of dOut[b][j]
+#pragma unroll
+                for (int j = 0; j < 9; ++j) {
+                    float s = d[j];
+#pragma unroll
+                    for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+                    if (lane == 0) red_add(G + L::OFF_BH + j, s);
+                }
+                head_bar();
+            }
+            go_signal();                                            // -> dH2 half 0 + dWh
+            wait_done();
+            {   // head weight gradients: row n2 = 128 hh + this thread's TMEM lane, 9 columns
+                float wv[16];
+                tmem_ld16(T0 + t_lane + 16 * hh, wv);
+                tmem_wait_ld();
+                const int n2 = hh * 128 + row;
+#pragma unroll
+                for (int j = 0; j < 9; ++j) red_add(G + L::OFF_WH + n2 * 9 + j, wv[j] * (1.0f / H_SCALE));
+            }
+            fence_before();
+            go_signal();                                            // -> dH2 half 1 (its accumulator overwrites the dWh columns)
+            // ---- dH2 epilogue, two halves of 128 features: mask by H2 > 0, dH2 in place of H2, db2 by warp reduce-scatter ----
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                if (half == 1) wait_done();
+                const uint32_t tcol = half == 0 ? 128u : 0u;
+#pragma unroll 1
+                for (int cb = 0; cb < 2; ++cb) {
+                    const int c0 = hh * 64 + cb * 32;                 // column within the half
+                    const int n0 = half * 128 + c0;                   // feature n2 of v[0]
+                    float v[32];
+                    tmem_ld32(T0 + t_lane + tcol + c0, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        uint4* ph = reinterpret_cast<uint4*>(sH2 + himg(row, n0 + j8 * 8, 256));
+                        const uint4 h4 = *ph;
+                        const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w};
+                        uint32_t ow[4];
+#pragma unroll
+                        for (int p2 = 0; p2 < 4; ++p2) {
+                            const int j = j8 * 8 + p2 * 2;
+                            v[j] = hlo(hw[p2]) > 0.f ? sat(v[j]) : 0.f;
+                            v[j + 1] = hhi(hw[p2]) > 0.f ? sat(v[j + 1]) : 0.f;
+                            ow[p2] = pk(v[j], v[j + 1]);
+                        }
+                        *ph = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    }
+                    const float cs = warp_colsum32(v, lane);
+                    red_add(G + L::OFF_B2 + n0 + lane, cs * (1.0f / H_SCALE));
+                }
+            }
+            go_signal();                                            // -> dH1, dW2
+            if (more) {
+                epi_bar();                                          // the next pair's ring positions (threads 0-127) are visible to every warp
+                gather_load(P.rp.next_obs, buf ^ 1);                // next pair's target rows, in flight behind dH1 / dW1
+            }
+            wait_done();
+            {   // dH1 epilogue: this thread's row, columns [64 hh, +64): mask by H1 > 0, dH1 in place of H1
+#pragma unroll 1
+                for (int cb = 0; cb < 2; ++cb) {
+                    const int c0 = hh * 64 + cb * 32;
+                    float v[32];
+                    tmem_ld32(T0 + t_lane + c0, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        uint4* ph = reinterpret_cast<uint4*>(sH1 + himg(row, c0 + j8 * 8, 128));
+                        const uint4 h4 = *ph;
+                        const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w};
+                        uint32_t ow[4];
+#pragma unroll
+                        for (int p2 = 0; p2 < 4; ++p2) {
+                            const int j = j8 * 8 + p2 * 2;
+                            ow[p2] = pk(hlo(hw[p2]) > 0.f ? sat(v[j]) : 0.f, hhi(hw[p2]) > 0.f ? sat(v[j + 1]) : 0.f);
+                        }
+                        *ph = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    }
+                }
+            }
+            go_signal();                                            // -> dW1
+            wait_done();
+            {   // dW1 flush: TMEM lane = k1 = row, columns [80 hh, +80) of the 160 inputs; column 159 carries db1
+                float* gw = G + L::OFF_W1T + row * RL_K1 + hh * 80;
+#pragma unroll 1
+                for (int cb = 0; cb < 5; ++cb) {
+                    float v[16];
+                    tmem_ld16(T0 + t_lane + hh * 80 + cb * 16, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] *= (1.0f / H_SCALE);
+                    if (hh == 1 && cb == 4) { red_add(G + L::OFF_B1 + row, v[15]); v[15] = 0.f; }
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) red_add4(gw + cb * 16 + j4 * 4, v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                }
+            }
+            if (more) {
+                gather_store();                                     // X image <- next pair's target rows (dW1 is done with X)
+                fence_before();
+                go_signal();                                        // -> next pair's target L1
+            }
+        }
+        if (n_pairs > 0) {     // flush the TMEM-resident dW2 accumulator once: lane = k1, columns [128 hh, +128) of n2
+#pragma unroll 1
+            for (int cb = 0; cb < 4; ++cb) {
+                const int c0 = hh * 128 + cb * 32;
+                float v[32];
+                tmem_ld32(T_DW2 + t_lane + c0, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)
+                    *reinterpret_cast<float4*>(G + L::OFF_W2T + row * 256 + c0 + j4 * 4) =
+                        make_float4(v[j4 * 4] * (1.0f / H_SCALE), v[j4 * 4 + 1] * (1.0f / H_SCALE), v[j4 * 4 + 2] * (1.0f / H_SCALE), v[j4 * 4 + 3] * (1.0f / H_SCALE));
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+extern "C" int rl_brain_learn_p(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                                const int32_t* sample_idx, const rl_learn_bufs* learn, const void* wimg_eval_h,
+                                const void* wimg_target_h, void* stream) {
+    RL_ARG_CHECK(cfg && rows && replay && sample_idx && learn && wimg_eval_h && wimg_target_h);
+    RL_ARG_CHECK(gene >= 0 && gene < cfg->n_genes && cfg->obs_ld == RL_K1 && learn->batch == R);
+    RL_ARG_CHECK(learn->params && learn->target && learn->grad_scratch && learn->grad && learn->new_prio && learn->loss);
+    if (learn->kind != RL_MODEL_DUELING) return rl_set_err(RL_ERR_UNSUPPORTED, "rl_brain_learn_p: dueling networks only");
+    PairParams P;
+    P.cfg = *cfg;
+    P.ev_rows = rows->rows + (size_t)(gene * RL_N_ROW_KINDS + RL_ROWS_EVENT) * rows->row_cap;
+    P.ev_total = rows->total + gene * RL_N_ROW_KINDS + RL_ROWS_EVENT;
+    P.rp = *replay; P.sample_idx = sample_idx; P.lb = *learn;
+    P.wimg_e = reinterpret_cast<const __half*>(wimg_eval_h); P.wimg_t = reinterpret_cast<const __half*>(wimg_target_h);
+    static PerDeviceOnce attr;
+    if (attr.need()) RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dueling_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM));
+    cudaStream_t st = (cudaStream_t)stream;
+    k_learn_dueling_p<<<rl_learn_grid(), NTH, PAIR_SMEM, st>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return rl_learn_reduce(learn, P.ev_total, 1, (void*)st);
+}

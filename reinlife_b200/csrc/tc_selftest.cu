@@ -68,6 +68,72 @@ extern "C" int rl_tc_gemm_test(const float* a_img, const float* b_img, float* d,
     return rl_tc_gemm_test_ex(a_img, b_img, d, M, N, K, a_mn, b_mn, 0, 0, 0, stream);
 }
 
+// ---- fp16 one-tile GEMM with caller-supplied descriptor geometry (pins the K-major / MN-major conventions of kind::f16) ----
+namespace {
+using namespace tc;
+struct TcTestParamsH { const uint16_t* a; const uint16_t* b; float* d; int M, N, K, a_halves, b_halves;
+                       uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep; int a_mn, b_mn; };
+
+__global__ void __launch_bounds__(128) k_tc_gemm_test_h(const TcTestParamsH P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint16_t* sa = reinterpret_cast<uint16_t*>(smem_raw);
+    uint16_t* sb = sa + ((P.a_halves + 63) & ~63);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    for (int i = threadIdx.x; i < P.a_halves; i += blockDim.x) sa[i] = P.a[i];
+    for (int i = threadIdx.x; i < P.b_halves; i += blockDim.x) sb[i] = P.b[i];
+    if (threadIdx.x == 0) { mlp::mbar_init(&bar, 1); mlp::fence_mbar_init(); }
+    if (threadIdx.x < 32) tmem_alloc(&tmem_base_s, 256);
+    mlp::fence_proxy_async();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = (1u << 4) | ((uint32_t)P.a_mn << 15) | ((uint32_t)P.b_mn << 16) | ((uint32_t)(P.N >> 3) << 17) | ((uint32_t)(P.M >> 4) << 24);
+        for (int ks = 0; ks < P.K / 16; ++ks) {
+            const uint64_t ad = make_desc(smem_u32(sa) + ks * P.a_kstep, P.a_lbo, P.a_sbo);
+            const uint64_t bd = make_desc(smem_u32(sb) + ks * P.b_kstep, P.b_lbo, P.b_sbo);
+            const uint32_t acc = ks > 0;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                         ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+        }
+        mma_commit(&bar);
+    }
+    mlp::mbar_wait(&bar, 0);
+    fence_after();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c0 = 0; c0 < P.N; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_wait_ld();
+        int row = -1;
+        if (P.M == 128) row = warp * 32 + lane;
+        else if (lane < 16) row = warp * 16 + lane;
+        if (row >= 0)
+            for (int j = 0; j < 16; ++j) P.d[(size_t)row * P.N + c0 + j] = v[j];
+    }
+    fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem, 256);
+}
+}  // namespace
+
+extern "C" int rl_tc_gemm_test_h(const void* a_img, const void* b_img, float* d, int M, int N, int K, int a_halves, int b_halves,
+                                 uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kstep, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep,
+                                 int a_mn, int b_mn, void* stream) {
+    RL_ARG_CHECK(a_img && b_img && d && (M == 64 || M == 128) && N % 16 == 0 && N <= 256 && K % 16 == 0);
+    TcTestParamsH P{reinterpret_cast<const uint16_t*>(a_img), reinterpret_cast<const uint16_t*>(b_img), d, M, N, K, a_halves, b_halves,
+                    a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep, a_mn, b_mn};
+    const size_t smem = 2 * (size_t)(((a_halves + 63) & ~63) + b_halves) + 256;
+    RL_ARG_CHECK(smem <= 200 * 1024);
+    RL_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm_test_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tc_gemm_test_h<<<1, 128, smem, (cudaStream_t)stream>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
 // ---- timing probe: cycles per tcgen05.mma kind::tf32 for a given operand layout (data is irrelevant: zeros) ----
 namespace {
 using namespace tc;

@@ -53,7 +53,7 @@ def _run_event_kernel(mode, vw, rows, rp, w0, tgt, sidx, n_ev):
     from reinlife_b200 import _lib
     from reinlife_b200.brains import DeviceBrain
     brain = DeviceBrain(0, w0, "cuda", lr=1e-3, gamma=0.99)
-    brain.use_fp16 = mode == "fp16"
+    brain.use_fp16 = mode in ("fp16", "fp16p")
     brain.load_state_dict(tgt, target=True)
     brain.alloc_learn(rows.row_cap)
     brain.sample_idx[:n_ev] = sidx
@@ -68,7 +68,8 @@ def _run_event_kernel(mode, vw, rows, rp, w0, tgt, sidx, n_ev):
                                             C.c_void_p(brain.wimg_e.data_ptr()), C.c_void_p(brain.wimg_t.data_ptr()), st))
     else:
         brain.build_wimg(st)
-        _lib.check(vw.lib.rl_brain_learn_h(C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(rp.bufs),
+        fn = vw.lib.rl_brain_learn_p if mode == "fp16p" else vw.lib.rl_brain_learn_h     # fp16p: two events per CTA iteration
+        _lib.check(fn(C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(rp.bufs),
                                            C.c_void_p(brain.sample_idx.data_ptr()), C.byref(brain.learn_bufs),
                                            C.c_void_p(brain.wimg_eh.data_ptr()), C.c_void_p(brain.wimg_th.data_ptr()), st))
     torch.cuda.synchronize()
@@ -131,7 +132,7 @@ def test_event_kernels_600_events_vs_oracle_and_fp32():
     assert n_ev >= 600 and n_ev >= 4 * vw.lib.rl_learn_grid()
     w0, tgt = state_dict("train_perd3qn/w0"), state_dict("train_perd3qn/target")
     sidx_d = torch.from_numpy(sidx).cuda()
-    out = {m: _run_event_kernel(m, vw, rows, rp, w0, tgt, sidx_d, n_ev) for m in ("fp32", "tf32", "fp16")}
+    out = {m: _run_event_kernel(m, vw, rows, rp, w0, tgt, sidx_d, n_ev) for m in ("fp32", "tf32", "fp16", "fp16p")}
     events, e = [], 0
     for w in range(NW):
         for _ in range(per_world[w]):
@@ -151,7 +152,7 @@ def test_event_kernels_600_events_vs_oracle_and_fp32():
     # (b) tensor-core kernels vs the ORACLE directly: gradients (packed into the kernel layout), per-event loss, priorities
     flat_ref = packing.pack(0, {k: torch.from_numpy(np.asarray(v, np.float32)) for k, v in g_ref.items()})[:nt] * n_ev
     ref = (np.concatenate([flat_ref, np.zeros(4, np.float32)]), np.array(losses, np.float32), np.stack(prios).astype(np.float32))
-    for mode in ("tf32", "fp16"):
+    for mode in ("tf32", "fp16", "fp16p"):
         _check_tc_vs(ref, out[mode], m, d, n_ev, f"{mode} vs oracle")
         _check_tc_vs(out["fp32"], out[mode], m, d, n_ev, f"{mode} vs fp32 kernel")
 
@@ -169,9 +170,9 @@ def test_event_kernels_bench_scale_20k_events():
     assert n_ev >= 20000
     w0, tgt = state_dict("train_perd3qn/w0"), state_dict("train_perd3qn/target")
     sidx_d = torch.from_numpy(sidx).cuda()
-    out = {m: _run_event_kernel(m, vw, rows, rp, w0, tgt, sidx_d, n_ev) for m in ("fp32", "tf32", "fp16")}
+    out = {m: _run_event_kernel(m, vw, rows, rp, w0, tgt, sidx_d, n_ev) for m in ("fp32", "tf32", "fp16", "fp16p")}
     d, m = packing.dims(0), packing.grad_mask(0)
-    for mode in ("tf32", "fp16"):
+    for mode in ("tf32", "fp16", "fp16p"):
         _check_tc_vs(out["fp32"], out[mode], m, d, n_ev, f"{mode} vs fp32 kernel, {n_ev} events")
     ev_world = np.repeat(np.arange(NW), per_world)
     rng = np.random.default_rng(2)
@@ -180,7 +181,7 @@ def test_event_kernels_bench_scale_20k_events():
         _, loss, prio = bo.dueling_event_grads(w0, tgt, *_oracle_event(z, ring, int(ev_world[e]), sidx[e]), 0.99)
         np.testing.assert_allclose(out["fp32"][1][e], loss, rtol=2e-4, atol=1e-4, err_msg=f"fp32 event {e}")
         np.testing.assert_allclose(out["fp32"][2][e], prio, rtol=2e-4, atol=2e-4, err_msg=f"fp32 event {e}")
-        for mode in ("tf32", "fp16"):
+        for mode in ("tf32", "fp16", "fp16p"):
             np.testing.assert_allclose(out[mode][1][e], loss, rtol=2e-2, atol=1e-3, err_msg=f"{mode} event {e}")
             np.testing.assert_allclose(out[mode][2][e], prio, rtol=2e-2, atol=2e-2, err_msg=f"{mode} event {e}")
 
@@ -193,7 +194,7 @@ def test_event_kernels_are_deterministic_run_to_run():
     z, vw, rows, rp, ring, n_ev, sidx = _events_setup(NW, per_world, seed=21)
     w0, tgt = state_dict("train_perd3qn/w0"), state_dict("train_perd3qn/target")
     sidx_d = torch.from_numpy(sidx).cuda()
-    for mode in ("fp32", "fp16", "tf32"):
+    for mode in ("fp32", "fp16", "fp16p", "tf32"):
         a = _run_event_kernel(mode, vw, rows, rp, w0, tgt, sidx_d, n_ev)
         b = _run_event_kernel(mode, vw, rows, rp, w0, tgt, sidx_d, n_ev)
         assert (a[1] == b[1]).all() and (a[2] == b[2]).all(), mode
@@ -255,12 +256,12 @@ def test_act_kernels_600_tiles_per_brain():
         q32 = out["fp32"][0][i, :n]
         np.testing.assert_allclose(q32[pick], q_or, rtol=1e-4, atol=1e-4)
         scale = np.abs(q32).max()
-        for mode in ("tf32", "fp16"):
+        for mode in ("tf32", "fp16", "fp16p"):
             qtc = out[mode][0][i, :n]
             assert np.abs(qtc[pick] - q_or).max() < 2e-2 * scale, (mode, "vs oracle")
             assert np.abs(q32 - qtc).max() < 2e-2 * scale, mode
             assert (q32.argmax(1) == qtc.argmax(1)).mean() >= 0.99, mode
-    for mode in ("tf32", "fp16"):
+    for mode in ("tf32", "fp16", "fp16p"):
         atc = out[mode][1]
         assert ((atc != -1) == listed).all(), mode
         assert (a32[listed] == atc[listed]).mean() >= 0.99, mode
