@@ -15,6 +15,7 @@
 //     (db1 = column 159 of dW1, whose X column is set to 1 -- the matching W1 rows are structural zeros);
 //   * dW2 stays resident in TMEM across all pairs of the CTA, dW1 is flushed once per pair with 16-byte vector reds.
 // Same contract, outputs and tolerance as rl_brain_learn_h (tests/test_scale_gpu.py, tests/test_tc_gpu.py).
+#include <stdlib.h>
 #include <cuda_fp16.h>
 #include "tc_tile.cuh"
 #include "models.cuh"
@@ -47,7 +48,8 @@ constexpr int PO_RED = PO_BIAS + 4 * 800;                 // reduction scratch f
 constexpr int PO_META = PO_RED + 4 * 64;                  // [2] x { idx[128] act[128] rew[128] dn[128] } int / float
 constexpr int PO_RING = PO_META + 2 * 4 * 4 * PB;         // [2][2] ring base (elements) per buffer / event, 64-bit
 constexpr int PO_BARS = PO_RING + 2 * 2 * 8;
-constexpr size_t PAIR_SMEM = PO_BARS + 8 * (2 * NSP + 2) + 16;
+constexpr int NSTG = 8;                  // chunk-consuming stages per pair: tL1 tL2 thead eL1 eL2 ehead dH2 dH1
+constexpr size_t PAIR_SMEM = PO_BARS + 8 * (NSP + NSTG + 3) + 16;
 static_assert(PAIR_SMEM <= 227 * 1024 && PO_BARS % 8 == 0 && PO_RING % 8 == 0, "shared memory budget");
 
 // interleaved no-swizzle fp16 image of width K: 8 rows x 16 bytes core matrices
@@ -104,6 +106,7 @@ struct PairParams {
     rl_learn_bufs lb;
     const __half* wimg_e;
     const __half* wimg_t;
+    long long* trace;      // debug: clock64 stamps of CTA 0, pair 3 (RL_TC_TRACE=1), else nullptr
 };
 
 __device__ __forceinline__ void sched_pair(int i, int& net, int& chunk) {
@@ -131,7 +134,9 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
     int* meta = reinterpret_cast<int*>(smem + PO_META);
     unsigned long long* ringb = reinterpret_cast<unsigned long long*>(smem + PO_RING);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PO_BARS);
-    uint64_t* full = bars; uint64_t* empty = bars + NSP; uint64_t* done = bars + 2 * NSP; uint64_t* go = done + 1;
+    // full[slot]: chunk landed; sfree[stage]: every MMA of that chunk-consuming stage has completed (its ring slots are free
+    // again -- one tcgen05.commit per STAGE instead of one per chunk: a commit between MMAs costs the issuer ~200 cycles)
+    uint64_t* full = bars; uint64_t* sfree = bars + NSP; uint64_t* done = sfree + NSTG; uint64_t* doneL1 = done + 1; uint64_t* go = done + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(go + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -141,8 +146,9 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
     const int n_pairs = (n_my + 1) >> 1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NSP; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(done, 1); mbar_init(go, NEPI);
+        for (int i = 0; i < NSP; ++i) mbar_init(&full[i], 1);
+        for (int i = 0; i < NSTG; ++i) mbar_init(&sfree[i], 1);
+        mbar_init(done, 1); mbar_init(doneL1, 1); mbar_init(go, NEPI);
         fence_mbar_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -166,25 +172,35 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
         // =================================== weight-stream producer ===================================
         if (lane == 0) {
             const uint32_t n_chunks = (uint32_t)n_pairs * SCHED_P;
+            uint32_t freed = 0, stage = 0;                          // chunks of completed stages / next stage to wait for
             for (uint32_t produced = 0; produced < n_chunks; ++produced) {
-                const uint32_t slot = produced % NSP;
-                if (produced >= NSP) mbar_wait(&empty[slot], ((produced / NSP) - 1) & 1);
+                while (produced - freed >= (uint32_t)NSP) {
+                    const uint32_t k = stage % NSTG;
+                    mbar_wait(&sfree[k], (stage / NSTG) & 1);
+                    freed += (k == 0 || k == 3) ? 5u : (k == 1 || k == 4 || k == 7) ? 8u : 1u;
+                    ++stage;
+                }
                 int net, ch; sched_pair(produced % SCHED_P, net, ch);
+                const uint32_t slot = produced % NSP;
                 bulk_load(sStg + slot * HCH, (net ? P.wimg_e : P.wimg_t) + (size_t)ch * HCH, HCH * 2, &full[slot]);
             }
         }
     } else if (warp == 9) {
         // =================================== MMA issuer ===================================
+        // TMEM columns of the work area: L1 accumulators 128..255, L2 / dH2 0..255, heads 0..15, dWh 0..31, dH1 0..127,
+        // dW1 0..159 -- the L1 of the eval net runs under the target head epilogue, the next pair's target L1 under nothing
+        // that touches 128..255.
         if (lane == 0) {
-            uint32_t consumed = 0, go_no = 0;
+            uint32_t consumed = 0, go_no = 0, stage = 0;
             auto wait_go = [&]() { mbar_wait(go, go_no & 1); ++go_no; fence_after(); };
             auto chunk_wait = [&]() -> uint32_t {
                 const uint32_t slot = consumed % NSP;
                 mbar_wait(&full[slot], (consumed / NSP) & 1);
                 fence_after();
+                ++consumed;
                 return smem_u32(sStg + slot * HCH);
             };
-            auto chunk_release = [&]() { mma_commit(&empty[consumed % NSP]); ++consumed; };
+            auto stage_free = [&]() { mma_commit(&sfree[stage % NSTG]); ++stage; };
             // L1: D[128 b][128 k1] = X[128][160] W1[128][160]^T -- 5 chunks [128 n][32 k], 2 k-steps each
             auto l1 = [&]() {
                 const uint32_t id = idesc_h(128, 128, 0, 0);
@@ -192,12 +208,12 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
 #pragma unroll 1
                 for (int c = 0; c < 5; ++c) {
                     const uint64_t b = dk(chunk_wait(), 32);
-                    mma_h(T0, a, b, id, c != 0);
-                    mma_h(T0, a + 16u, b + 16u, id, 1u);
+                    mma_h(T0 + 128, a, b, id, c != 0);
+                    mma_h(T0 + 128, a + 16u, b + 16u, id, 1u);
                     a += 32u;
-                    chunk_release();
                 }
-                mma_commit(done);
+                stage_free();
+                mma_commit(doneL1);
             };
             // L2: D[128 b][256 n2] = H1[128][128] W2[256][128]^T -- 8 chunks [256 n][16 k], one k-step each
             auto l2 = [&]() {
@@ -207,8 +223,8 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 for (int c = 0; c < 8; ++c) {
                     mma_h(T0, a, dk(chunk_wait(), 16), id, c != 0);
                     a += 16u;
-                    chunk_release();
                 }
+                stage_free();
                 mma_commit(done);
             };
             // head: D[128 b][16] = H2[128][256] Wh[16][256]^T -- one chunk, 16 k-steps
@@ -217,14 +233,13 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 uint64_t a = dk(aH2, 256), b = dk(chunk_wait(), 256);
 #pragma unroll 1
                 for (int ks = 0; ks < 16; ++ks) { mma_h(T0, a, b, id, ks != 0); a += 16u; b += 16u; }
-                chunk_release();
+                stage_free();
                 mma_commit(done);
             };
             for (int p = 0; p < n_pairs; ++p) {
                 wait_go(); l1();                                   // target net
                 wait_go(); l2();
-                wait_go(); head();
-                wait_go(); l1();                                   // eval net
+                wait_go(); head(); l1();                           // target head, then the eval L1 (runs under the target head epilogue)
                 wait_go(); l2();
                 wait_go(); head();
                 wait_go();
@@ -242,7 +257,7 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                     mma_commit(done);
                     wait_go();                                     // dWh drained: dH2 half 1 (n2 >= 128) -> columns 0..127
                     mma_h(T0, dk(aD, 16), dk(wht + 4096u, 16), idesc_h(128, 128, 0, 0), 0u);
-                    chunk_release();
+                    stage_free();
                     mma_commit(done);
                 }
                 wait_go();
@@ -255,8 +270,8 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                         mma_h(T0, a, b, id, c != 0);
                         mma_h(T0, a + 16u, b + 16u, id, 1u);
                         a += 32u;
-                        chunk_release();
                     }
+                    stage_free();
                     // dW2[k1][n2] += sum_b H1[b][k1] dH2[b][n2]: both images read MN-major, accumulator resident in TMEM
                     const uint32_t id2 = idesc_h(128, 256, 1, 1);
                     uint64_t a2 = dm(aH1, 128), b2 = dm(aH2, 256);
@@ -276,28 +291,49 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
         }
     } else {
         // =================================== epilogue warps ===================================
-        uint32_t done_no = 0;
+        uint32_t done_no = 0, l1_no = 0;
         const int q = warp & 3, hh = warp >> 2;
         const int row = q * 32 + lane;                    // batch row of the pair == TMEM lane
         const uint32_t t_lane = (uint32_t)(q * 32) << 16;
         const int S = P.cfg.slot_cap, cap = P.rp.capacity;
-        auto go_signal = [&]() { fence_proxy_async(); fence_before(); mbar_arrive(go); };
-        auto wait_done = [&]() { mbar_wait(done, done_no & 1); ++done_no; fence_after(); };
-        // ---- metadata of a pair: ring positions, actions, rewards, dones of its 128 sampled rows ----
-        auto load_meta = [&](int buf, int p) {
+        int tr_n = 0, tr_p = -1;
+        auto stamp = [&]() { if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && tr_p == 3 && tr_n < 40) P.trace[tr_n++] = clock64(); };
+        auto go_signal = [&]() { fence_proxy_async(); fence_before(); mbar_arrive(go); stamp(); };
+        auto wait_done = [&]() { mbar_wait(done, done_no & 1); ++done_no; fence_after(); stamp(); };
+        auto wait_l1 = [&]() { mbar_wait(doneL1, l1_no & 1); ++l1_no; fence_after(); stamp(); };
+        // ---- metadata of a pair (threads 0-127, one sampled row each) in three phases so that no global-load latency
+        //      sits on the critical path: A event row + ring position, B action / reward / done (+ L2 prefetch of the
+        //      sample's two rows), C to shared memory ----
+        size_t m_ring = 0; int m_row = 0, m_i = 0, m_act = 0; float m_rew = 0.f, m_dn = 0.f;
+        auto meta_a = [&](int p) {
             if (threadIdx.x < PB) {
                 const int r = threadIdx.x, ev = r >> 6;
                 const int it = 2 * p + ev;
-                const bool valid = it < n_my;
-                const int e = (int)blockIdx.x + (valid ? it : 2 * p) * (int)gridDim.x;     // a missing second event mirrors the first
-                const size_t ring = (size_t)(P.ev_rows[e] / S) * cap;
-                const int i = max(P.sample_idx[(size_t)e * R + (r & 63)], 0);
+                const int e = (int)blockIdx.x + (it < n_my ? it : 2 * p) * (int)gridDim.x;     // a missing second event mirrors the first
+                m_row = P.ev_rows[e];
+                m_i = P.sample_idx[(size_t)e * R + (r & 63)];       // (no dependent instruction here: the loads stay in flight)
+            }
+        };
+        auto meta_b = [&]() {
+            if (threadIdx.x < PB) {
+                m_ring = (size_t)(m_row / S) * cap; m_i = max(m_i, 0);
+                m_act = P.rp.action[m_ring + m_i]; m_rew = P.rp.reward[m_ring + m_i]; m_dn = (float)P.rp.done[m_ring + m_i];
+                // pull the two 640-byte rows of this sample towards L2 now: the gathers of the next pair then hit L2, not HBM
+                const float* r0 = P.rp.next_obs + (m_ring + m_i) * RL_K1; const float* r1 = P.rp.obs + (m_ring + m_i) * RL_K1;
+#pragma unroll
+                for (int ln = 0; ln < 5; ++ln) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + ln * 32));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + ln * 32));
+                }
+            }
+        };
+        auto meta_c = [&](int buf) {
+            if (threadIdx.x < PB) {
+                const int r = threadIdx.x;
                 int* m = meta + buf * 4 * PB;
-                m[r] = i;
-                m[PB + r] = P.rp.action[ring + i];
-                reinterpret_cast<float*>(m)[2 * PB + r] = P.rp.reward[ring + i];
-                reinterpret_cast<float*>(m)[3 * PB + r] = (float)P.rp.done[ring + i];
-                if ((r & 63) == 0) ringb[buf * 2 + ev] = (unsigned long long)ring;
+                m[r] = m_i; m[PB + r] = m_act;
+                reinterpret_cast<float*>(m)[2 * PB + r] = m_rew; reinterpret_cast<float*>(m)[3 * PB + r] = m_dn;
+                if ((r & 63) == 0) ringb[buf * 2 + (r >> 6)] = (unsigned long long)m_ring;
             }
         };
         // ---- 128 rows x 160 floats from the replay ring -> packed fp16 in registers (unit = 8 consecutive columns) ----
@@ -324,44 +360,40 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 *reinterpret_cast<uint4*>(sX + himg(rg * 8 + rr, (og * 4 + o4) * 8, 160)) = xh[u];
             }
         };
-        // ---- L1 epilogue: this thread's row, columns [64 hh, 64 hh + 64): H1 = relu(D + b1) ----
-        auto l1_epilogue = [&](const float* bias) {
+        // relu(D + bias) of 32 accumulator columns -> 4 x 16-byte stores into a batch-major image of width K
+        auto relu_store32 = [&](float (&v)[32], const float* bias, __half* img, int c0, int K) {
 #pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {
-                const int c0 = hh * 64 + cb * 32;
-                float v[32];
-                tmem_ld32(T0 + t_lane + c0, v);
-                tmem_wait_ld();
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 b = *reinterpret_cast<const float4*>(bias + c0 + j4 * 4);
-                    v[j4 * 4] = fmaxf(v[j4 * 4] + b.x, 0.f); v[j4 * 4 + 1] = fmaxf(v[j4 * 4 + 1] + b.y, 0.f);
-                    v[j4 * 4 + 2] = fmaxf(v[j4 * 4 + 2] + b.z, 0.f); v[j4 * 4 + 3] = fmaxf(v[j4 * 4 + 3] + b.w, 0.f);
-                }
-#pragma unroll
-                for (int j8 = 0; j8 < 4; ++j8)
-                    *reinterpret_cast<uint4*>(sH1 + himg(row, c0 + j8 * 8, 128)) =
-                        make_uint4(pk(v[j8 * 8], v[j8 * 8 + 1]), pk(v[j8 * 8 + 2], v[j8 * 8 + 3]), pk(v[j8 * 8 + 4], v[j8 * 8 + 5]), pk(v[j8 * 8 + 6], v[j8 * 8 + 7]));
+            for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 b = *reinterpret_cast<const float4*>(bias + j4 * 4);
+                v[j4 * 4] = fmaxf(v[j4 * 4] + b.x, 0.f); v[j4 * 4 + 1] = fmaxf(v[j4 * 4 + 1] + b.y, 0.f);
+                v[j4 * 4 + 2] = fmaxf(v[j4 * 4 + 2] + b.z, 0.f); v[j4 * 4 + 3] = fmaxf(v[j4 * 4 + 3] + b.w, 0.f);
             }
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8)
+                *reinterpret_cast<uint4*>(img + himg(row, c0 + j8 * 8, K)) =
+                    make_uint4(pk(v[j8 * 8], v[j8 * 8 + 1]), pk(v[j8 * 8 + 2], v[j8 * 8 + 3]), pk(v[j8 * 8 + 4], v[j8 * 8 + 5]), pk(v[j8 * 8 + 6], v[j8 * 8 + 7]));
+        };
+        // ---- L1 epilogue: this thread's row, columns [64 hh, 64 hh + 64) of the accumulator at TMEM columns 128..255 ----
+        auto l1_epilogue = [&](const float* bias) {
+            const int c0 = hh * 64;
+            float v0[32], v1[32];
+            tmem_ld32(T0 + t_lane + 128 + c0, v0);
+            tmem_ld32(T0 + t_lane + 128 + c0 + 32, v1);
+            tmem_wait_ld();
+            relu_store32(v0, bias + c0, sH1, c0, 128);
+            relu_store32(v1, bias + c0 + 32, sH1, c0 + 32, 128);
         };
         // ---- L2 epilogue: this thread's row, columns [128 hh, 128 hh + 128): H2 = relu(D + b2) ----
         auto l2_epilogue = [&](const float* bias) {
 #pragma unroll 1
-            for (int cb = 0; cb < 4; ++cb) {
-                const int c0 = hh * 128 + cb * 32;
-                float v[32];
-                tmem_ld32(T0 + t_lane + c0, v);
+            for (int cb = 0; cb < 2; ++cb) {
+                const int c0 = hh * 128 + cb * 64;
+                float v0[32], v1[32];
+                tmem_ld32(T0 + t_lane + c0, v0);
+                tmem_ld32(T0 + t_lane + c0 + 32, v1);
                 tmem_wait_ld();
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 b = *reinterpret_cast<const float4*>(bias + 128 + c0 + j4 * 4);
-                    v[j4 * 4] = fmaxf(v[j4 * 4] + b.x, 0.f); v[j4 * 4 + 1] = fmaxf(v[j4 * 4 + 1] + b.y, 0.f);
-                    v[j4 * 4 + 2] = fmaxf(v[j4 * 4 + 2] + b.z, 0.f); v[j4 * 4 + 3] = fmaxf(v[j4 * 4 + 3] + b.w, 0.f);
-                }
-#pragma unroll
-                for (int j8 = 0; j8 < 4; ++j8)
-                    *reinterpret_cast<uint4*>(sH2 + himg(row, c0 + j8 * 8, 256)) =
-                        make_uint4(pk(v[j8 * 8], v[j8 * 8 + 1]), pk(v[j8 * 8 + 2], v[j8 * 8 + 3]), pk(v[j8 * 8 + 4], v[j8 * 8 + 5]), pk(v[j8 * 8 + 6], v[j8 * 8 + 7]));
+                relu_store32(v0, bias + 128 + c0, sH2, c0, 256);
+                relu_store32(v1, bias + 128 + c0 + 32, sH2, c0 + 32, 256);
             }
         };
         // ---- head epilogue (warps 0-3: one row each): out[0..8] of the row, mean of the advantages over the row's EVENT
@@ -383,7 +415,7 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
         };
 
         if (n_pairs > 0) {
-            load_meta(0, 0);
+            meta_a(0); meta_b(); meta_c(0);
             epi_bar();
             gather_load(P.rp.next_obs, 0);
             gather_store();
@@ -391,6 +423,7 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
         }
         for (int p = 0; p < n_pairs; ++p) {
             const int buf = p & 1;
+            tr_p = p; stamp();
             const int* idx = meta + buf * 4 * PB; const int* act = idx + PB;
             const float* rew = reinterpret_cast<const float*>(idx + 2 * PB); const float* dn = rew + PB;
             const bool more = p + 1 < n_pairs;
@@ -398,15 +431,17 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
             const bool valid = 2 * p + ev < n_my;
             const int e = (int)blockIdx.x + (2 * p + ev) * (int)gridDim.x;
             // ---------------- target net ----------------
-            gather_load(P.rp.obs, buf);                             // eval rows of this pair: in flight behind the target L1
-            wait_done();
+            if (more) meta_a(p + 1);
+            wait_l1();
             l1_epilogue(bias_t);
             go_signal();                                            // -> target L2
-            if (more) load_meta(buf ^ 1, p + 1);
+            gather_load(P.rp.obs, buf);                             // eval rows of this pair: their latency sits behind the target L2
+            if (more) meta_b();
             wait_done();
             l2_epilogue(bias_t);
             gather_store();                                         // X image <- eval rows (the target L1 is done with X')
-            go_signal();                                            // -> target head
+            go_signal();                                            // -> target head, eval L1
+            if (more) meta_c(buf ^ 1);
             wait_done();
             float nq = 0.f;
             if (hh == 0) {
@@ -417,16 +452,15 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 for (int j = 1; j < 8; ++j) mx = fmaxf(mx, o[j]);
                 nq = mx + o[8] - mean;
             }
-            fence_before();
-            go_signal();                                            // -> eval L1
             // ---------------- eval net ----------------
-            wait_done();
+            wait_l1();
             l1_epilogue(bias_e);
-            go_signal();                                            // -> eval L2
+            go_signal();                                            // -> eval L2 (overwrites the target head columns: consumed above)
             wait_done();
             l2_epilogue(bias_e);
             go_signal();                                            // -> eval head
             wait_done();
+            float dbh = 0.f;                                        // lane j < 9 of warps 0-3: sum over the warp's rows of dOut[.][j]
             if (hh == 0) {
                 // ---- TD target, loss, priorities, dOut of this row (PERD3QN.py:103-110), all thread-local ----
                 float o[9];
@@ -438,54 +472,55 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 const float qa = qsel + o[8] - mean;
                 const float y = rew[row] + P.lb.gamma * (1.0f - dn[row]) * nq;
                 const float diff = qa - y;
-                float g = valid ? 2.0f * diff * (1.0f / R) : 0.f;
+                const float g = valid ? 2.0f * diff * (1.0f / R) : 0.f;
                 float sq = diff * diff, gs = g;
 #pragma unroll
                 for (int o2 = 16; o2 > 0; o2 >>= 1) { sq += __shfl_xor_sync(0xffffffffu, sq, o2); gs += __shfl_xor_sync(0xffffffffu, gs, o2); }
                 if (lane == 0) { red[8 + q] = sq; red[16 + q] = gs; }
                 head_bar();
                 const float loss = (q < 2 ? red[8] + red[9] : red[10] + red[11]) * (1.0f / R);
-                const float shift = (q < 2 ? red[16] + red[17] : red[18] + red[19]) * (1.0f / (8 * R));
+                const float shift = valid ? (q < 2 ? red[16] + red[17] : red[18] + red[19]) * (1.0f / (8 * R)) : 0.f;
                 if (valid) {
                     P.lb.new_prio[(size_t)e * R + (row & 63)] = fabsf(nq - qa);
                     if ((row & 63) == 0) P.lb.loss[e] = loss;
                 }
                 float d[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) d[j] = j < 8 ? ((j == a ? g : 0.f) - (valid ? shift : 0.f)) : (j == 8 ? g : 0.f);
+                for (int j = 0; j < 16; ++j) d[j] = j < 8 ? ((j == a ? g : 0.f) - shift) : (j == 8 ? g : 0.f);
                 uint32_t w[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) w[j] = pk(sat(d[2 * j] * H_SCALE), sat(d[2 * j + 1] * H_SCALE));
                 *reinterpret_cast<uint4*>(sDout + himg(row, 0, 16)) = make_uint4(w[0], w[1], w[2], w[3]);
                 *reinterpret_cast<uint4*>(sDout + himg(row, 8, 16)) = make_uint4(w[4], w[5], w[6], w[7]);
-                // dbh[j] = sum over the rows of dOut[b][j]
 #pragma unroll
                 for (int j = 0; j < 9; ++j) {
                     float s = d[j];
 #pragma unroll
                     for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
-                    if (lane == 0) red_add(G + L::OFF_BH + j, s);
+                    dbh = lane == j ? s : dbh;
                 }
-                head_bar();
             }
             go_signal();                                            // -> dH2 half 0 + dWh
+            // (global reds are issued AFTER the arrive they would otherwise delay: an mbarrier arrive has release semantics and
+            //  waits for the thread's outstanding reds)
+            if (hh == 0 && lane < 9) red_add(G + L::OFF_BH + lane, dbh);
             wait_done();
-            {   // head weight gradients: row n2 = 128 hh + this thread's TMEM lane, 9 columns
-                float wv[16];
-                tmem_ld16(T0 + t_lane + 16 * hh, wv);
-                tmem_wait_ld();
+            float wv[16];
+            tmem_ld16(T0 + t_lane + 16 * hh, wv);                   // head weight gradients: row n2 = 128 hh + this thread's TMEM lane
+            tmem_wait_ld();
+            go_signal();                                            // -> dH2 half 1 (its accumulator overwrites the dWh columns)
+            {
                 const int n2 = hh * 128 + row;
 #pragma unroll
                 for (int j = 0; j < 9; ++j) red_add(G + L::OFF_WH + n2 * 9 + j, wv[j] * (1.0f / H_SCALE));
             }
-            fence_before();
-            go_signal();                                            // -> dH2 half 1 (its accumulator overwrites the dWh columns)
             // ---- dH2 epilogue, two halves of 128 features: mask by H2 > 0, dH2 in place of H2, db2 by warp reduce-scatter ----
-#pragma unroll 1
+            float cs[4];
+#pragma unroll
             for (int half = 0; half < 2; ++half) {
                 if (half == 1) wait_done();
                 const uint32_t tcol = half == 0 ? 128u : 0u;
-#pragma unroll 1
+#pragma unroll
                 for (int cb = 0; cb < 2; ++cb) {
                     const int c0 = hh * 64 + cb * 32;                 // column within the half
                     const int n0 = half * 128 + c0;                   // feature n2 of v[0]
@@ -507,58 +542,54 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                         }
                         *ph = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                     }
-                    const float cs = warp_colsum32(v, lane);
-                    red_add(G + L::OFF_B2 + n0 + lane, cs * (1.0f / H_SCALE));
+                    cs[half * 2 + cb] = warp_colsum32(v, lane);
                 }
             }
             go_signal();                                            // -> dH1, dW2
+#pragma unroll
+            for (int k = 0; k < 4; ++k) red_add(G + L::OFF_B2 + (k >> 1) * 128 + hh * 64 + (k & 1) * 32 + lane, cs[k] * (1.0f / H_SCALE));
             if (more) {
-                epi_bar();                                          // the next pair's ring positions (threads 0-127) are visible to every warp
+                epi_bar();                                          // the next pair's metadata (threads 0-127) is visible to every warp
                 gather_load(P.rp.next_obs, buf ^ 1);                // next pair's target rows, in flight behind dH1 / dW1
             }
             wait_done();
             {   // dH1 epilogue: this thread's row, columns [64 hh, +64): mask by H1 > 0, dH1 in place of H1
-#pragma unroll 1
-                for (int cb = 0; cb < 2; ++cb) {
-                    const int c0 = hh * 64 + cb * 32;
-                    float v[32];
-                    tmem_ld32(T0 + t_lane + c0, v);
-                    tmem_wait_ld();
+                const int c0 = hh * 64;
+                float v0[32], v1[32];
+                tmem_ld32(T0 + t_lane + c0, v0);
+                tmem_ld32(T0 + t_lane + c0 + 32, v1);
+                tmem_wait_ld();
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        uint4* ph = reinterpret_cast<uint4*>(sH1 + himg(row, c0 + j8 * 8, 128));
-                        const uint4 h4 = *ph;
-                        const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w};
-                        uint32_t ow[4];
+                for (int j8 = 0; j8 < 8; ++j8) {
+                    uint4* ph = reinterpret_cast<uint4*>(sH1 + himg(row, c0 + j8 * 8, 128));
+                    const uint4 h4 = *ph;
+                    const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w};
+                    uint32_t ow[4];
 #pragma unroll
-                        for (int p2 = 0; p2 < 4; ++p2) {
-                            const int j = j8 * 8 + p2 * 2;
-                            ow[p2] = pk(hlo(hw[p2]) > 0.f ? sat(v[j]) : 0.f, hhi(hw[p2]) > 0.f ? sat(v[j + 1]) : 0.f);
-                        }
-                        *ph = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    for (int p2 = 0; p2 < 4; ++p2) {
+                        const int j = (j8 & 3) * 8 + p2 * 2;
+                        const float x0 = j8 < 4 ? v0[j] : v1[j], x1 = j8 < 4 ? v0[j + 1] : v1[j + 1];
+                        ow[p2] = pk(hlo(hw[p2]) > 0.f ? sat(x0) : 0.f, hhi(hw[p2]) > 0.f ? sat(x1) : 0.f);
                     }
+                    *ph = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                 }
             }
             go_signal();                                            // -> dW1
             wait_done();
-            {   // dW1 flush: TMEM lane = k1 = row, columns [80 hh, +80) of the 160 inputs; column 159 carries db1
+            if (more) gather_store();                               // X image <- next pair's target rows (dW1 is done with X)
+            {   // dW1 flush: TMEM lane = k1 = row, columns [80 hh, +80) of the 160 inputs; column 159 carries db1.  All 80 values
+                // are pulled into registers first so that the next pair's target L1 can start before the reds are issued.
+                float v[80];
+#pragma unroll
+                for (int cb = 0; cb < 5; ++cb) tmem_ld16(T0 + t_lane + hh * 80 + cb * 16, v + cb * 16);
+                tmem_wait_ld();
+                if (more) go_signal();                              // -> next pair's target L1
                 float* gw = G + L::OFF_W1T + row * RL_K1 + hh * 80;
-#pragma unroll 1
-                for (int cb = 0; cb < 5; ++cb) {
-                    float v[16];
-                    tmem_ld16(T0 + t_lane + hh * 80 + cb * 16, v);
-                    tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] *= (1.0f / H_SCALE);
-                    if (hh == 1 && cb == 4) { red_add(G + L::OFF_B1 + row, v[15]); v[15] = 0.f; }
+                for (int j = 0; j < 80; ++j) v[j] *= (1.0f / H_SCALE);
+                if (hh == 1) { red_add(G + L::OFF_B1 + row, v[79]); v[79] = 0.f; }
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) red_add4(gw + cb * 16 + j4 * 4, v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-                }
-            }
-            if (more) {
-                gather_store();                                     // X image <- next pair's target rows (dW1 is done with X)
-                fence_before();
-                go_signal();                                        // -> next pair's target L1
+                for (int j4 = 0; j4 < 20; ++j4) red_add4(gw + j4 * 4, v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
             }
         }
         if (n_pairs > 0) {     // flush the TMEM-resident dW2 accumulator once: lane = k1, columns [128 hh, +128) of n2
@@ -595,10 +626,26 @@ extern "C" int rl_brain_learn_p(const rl_world_cfg* cfg, const rl_rows_bufs* row
     P.ev_total = rows->total + gene * RL_N_ROW_KINDS + RL_ROWS_EVENT;
     P.rp = *replay; P.sample_idx = sample_idx; P.lb = *learn;
     P.wimg_e = reinterpret_cast<const __half*>(wimg_eval_h); P.wimg_t = reinterpret_cast<const __half*>(wimg_target_h);
+    P.trace = nullptr;
+    static long long* trace_dev = nullptr;
+    const bool tracing = getenv("RL_TC_TRACE") != nullptr;
+    if (tracing) {
+        if (!trace_dev) RL_CUDA_CHECK(cudaMalloc(&trace_dev, 64 * sizeof(long long)));
+        RL_CUDA_CHECK(cudaMemset(trace_dev, 0, 64 * sizeof(long long)));
+        P.trace = trace_dev;
+    }
     static PerDeviceOnce attr;
     if (attr.need()) RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dueling_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM));
     cudaStream_t st = (cudaStream_t)stream;
     k_learn_dueling_p<<<rl_learn_grid(), NTH, PAIR_SMEM, st>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
+    if (tracing) {
+        long long h[64];
+        RL_CUDA_CHECK(cudaStreamSynchronize(st));
+        RL_CUDA_CHECK(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[pair trace] deltas (cycles) between stamps of pair 3:");
+        for (int i = 1; i < 40 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[i - 1]);
+        fprintf(stderr, "\n");
+    }
     return rl_learn_reduce(learn, P.ev_total, 1, (void*)st);
 }
