@@ -72,8 +72,10 @@ __device__ __forceinline__ uint32_t pk(float a, float b) {
 __device__ __forceinline__ float sat(float x) { return fminf(fmaxf(x, -60000.f), 60000.f); }
 __device__ __forceinline__ float hlo(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xFFFFu))); }
 __device__ __forceinline__ float hhi(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }
-__device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ int g_no_red;   // RL_PAIR_DBG & 4
+__device__ __forceinline__ void red_add(float* p, float v) { if (g_no_red) return; asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+    if (g_no_red) return;
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -107,6 +109,7 @@ struct PairParams {
     const __half* wimg_e;
     const __half* wimg_t;
     long long* trace;      // debug: clock64 stamps of CTA 0, pair 3 (RL_TC_TRACE=1), else nullptr
+    int dbg;               // timing experiments only (RL_PAIR_DBG): 1 gathers read ring row 0, 2 no db2 reduce-scatter, 4 no global reds
 };
 
 __device__ __forceinline__ void sched_pair(int i, int& net, int& chunk) {
@@ -346,7 +349,7 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 const int rr = v & 7, o4 = (v >> 3) & 3, blk = v >> 5;
                 const int rg = blk / 5, og = blk - rg * 5;
                 const int r = rg * 8 + rr, oct = og * 4 + o4;
-                const float4* g = reinterpret_cast<const float4*>(src + ((size_t)ringb[buf * 2 + (r >> 6)] + ids[r]) * RL_K1) + oct * 2;
+                const float4* g = reinterpret_cast<const float4*>(src + ((size_t)ringb[buf * 2 + (r >> 6)] + ((P.dbg & 1) ? 0 : ids[r])) * RL_K1) + oct * 2;
                 const float4 a = __ldg(g), b = __ldg(g + 1);
                 xh[u] = make_uint4(pk(a.x, a.y), pk(a.z, a.w), pk(b.x, b.y), oct == 19 ? pk(b.z, 1.0f) : pk(b.z, b.w));   // column 159 := 1 (db1)
             }
@@ -414,6 +417,11 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
             return m;
         };
 
+        // gradients whose owner (thread, element) is the same in every pair are summed in registers and leave once per CTA:
+        // dWh row n2 = 128 hh + row (9), db2 of the four columns this lane receives from the reduce-scatters, dbh[lane], db1[row]
+        float acc_wh[9], acc_b2[4] = {0.f, 0.f, 0.f, 0.f}, acc_bh = 0.f, acc_b1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) acc_wh[j] = 0.f;
         if (n_pairs > 0) {
             meta_a(0); meta_b(); meta_c(0);
             epi_bar();
@@ -501,36 +509,33 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 }
             }
             go_signal();                                            // -> dH2 half 0 + dWh
-            // (global reds are issued AFTER the arrive they would otherwise delay: an mbarrier arrive has release semantics and
-            //  waits for the thread's outstanding reds)
-            if (hh == 0 && lane < 9) red_add(G + L::OFF_BH + lane, dbh);
+            acc_bh += dbh;
             wait_done();
             float wv[16];
             tmem_ld16(T0 + t_lane + 16 * hh, wv);                   // head weight gradients: row n2 = 128 hh + this thread's TMEM lane
             tmem_wait_ld();
             go_signal();                                            // -> dH2 half 1 (its accumulator overwrites the dWh columns)
-            {
-                const int n2 = hh * 128 + row;
 #pragma unroll
-                for (int j = 0; j < 9; ++j) red_add(G + L::OFF_WH + n2 * 9 + j, wv[j] * (1.0f / H_SCALE));
-            }
+            for (int j = 0; j < 9; ++j) acc_wh[j] += wv[j];
             // ---- dH2 epilogue, two halves of 128 features: mask by H2 > 0, dH2 in place of H2, db2 by warp reduce-scatter ----
             float cs[4];
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 if (half == 1) wait_done();
                 const uint32_t tcol = half == 0 ? 128u : 0u;
+                const int c0 = hh * 64;                               // first column within the half
+                const int n0 = half * 128 + c0;                       // feature n2 of va[0]
+                float va[32], vb[32];
+                tmem_ld32(T0 + t_lane + tcol + c0, va);
+                tmem_ld32(T0 + t_lane + tcol + c0 + 32, vb);
+                uint4 hm[8];
 #pragma unroll
-                for (int cb = 0; cb < 2; ++cb) {
-                    const int c0 = hh * 64 + cb * 32;                 // column within the half
-                    const int n0 = half * 128 + c0;                   // feature n2 of v[0]
-                    float v[32];
-                    tmem_ld32(T0 + t_lane + tcol + c0, v);
-                    tmem_wait_ld();
+                for (int j8 = 0; j8 < 8; ++j8) hm[j8] = *reinterpret_cast<const uint4*>(sH2 + himg(row, n0 + j8 * 8, 256));
+                tmem_wait_ld();
+                auto mask_store = [&](float (&v)[32], const int hb, int nb) {      // 32 columns: dH2 = H2 > 0 ? acc : 0, in place
 #pragma unroll
                     for (int j8 = 0; j8 < 4; ++j8) {
-                        uint4* ph = reinterpret_cast<uint4*>(sH2 + himg(row, n0 + j8 * 8, 256));
-                        const uint4 h4 = *ph;
+                        const uint4 h4 = hm[hb + j8];
                         const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w};
                         uint32_t ow[4];
 #pragma unroll
@@ -540,14 +545,17 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                             v[j + 1] = hhi(hw[p2]) > 0.f ? sat(v[j + 1]) : 0.f;
                             ow[p2] = pk(v[j], v[j + 1]);
                         }
-                        *ph = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                        *reinterpret_cast<uint4*>(sH2 + himg(row, nb + j8 * 8, 256)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                     }
-                    cs[half * 2 + cb] = warp_colsum32(v, lane);
-                }
+                };
+                mask_store(va, 0, n0);
+                mask_store(vb, 4, n0 + 32);
+                cs[half * 2] = (P.dbg & 2) ? va[0] : warp_colsum32(va, lane);
+                cs[half * 2 + 1] = (P.dbg & 2) ? vb[0] : warp_colsum32(vb, lane);
             }
             go_signal();                                            // -> dH1, dW2
 #pragma unroll
-            for (int k = 0; k < 4; ++k) red_add(G + L::OFF_B2 + (k >> 1) * 128 + hh * 64 + (k & 1) * 32 + lane, cs[k] * (1.0f / H_SCALE));
+            for (int k = 0; k < 4; ++k) acc_b2[k] += cs[k];
             if (more) {
                 epi_bar();                                          // the next pair's metadata (threads 0-127) is visible to every warp
                 gather_load(P.rp.next_obs, buf ^ 1);                // next pair's target rows, in flight behind dH1 / dW1
@@ -587,10 +595,21 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 float* gw = G + L::OFF_W1T + row * RL_K1 + hh * 80;
 #pragma unroll
                 for (int j = 0; j < 80; ++j) v[j] *= (1.0f / H_SCALE);
-                if (hh == 1) { red_add(G + L::OFF_B1 + row, v[79]); v[79] = 0.f; }
+                if (hh == 1) { acc_b1 += v[79]; v[79] = 0.f; }                  // (already unscaled)
 #pragma unroll
                 for (int j4 = 0; j4 < 20; ++j4) red_add4(gw + j4 * 4, v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
             }
+        }
+        if (n_pairs > 0) {
+            // (global reds are kept off the per-pair path: an mbarrier arrive has release semantics and waits for the thread's
+            //  outstanding reds, and scattered reds share the LSU with the epilogue's shared-memory traffic)
+            const int n2 = hh * 128 + row;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) G[L::OFF_WH + n2 * 9 + j] = acc_wh[j] * (1.0f / H_SCALE);          // sole owner of the row
+#pragma unroll
+            for (int k = 0; k < 4; ++k) red_add(G + L::OFF_B2 + (k >> 1) * 128 + hh * 64 + (k & 1) * 32 + lane, acc_b2[k] * (1.0f / H_SCALE));
+            if (hh == 0 && lane < 9) red_add(G + L::OFF_BH + lane, acc_bh);
+            if (hh == 1) G[L::OFF_B1 + row] = acc_b1;
         }
         if (n_pairs > 0) {     // flush the TMEM-resident dW2 accumulator once: lane = k1, columns [128 hh, +128) of n2
 #pragma unroll 1
@@ -627,6 +646,7 @@ extern "C" int rl_brain_learn_p(const rl_world_cfg* cfg, const rl_rows_bufs* row
     P.rp = *replay; P.sample_idx = sample_idx; P.lb = *learn;
     P.wimg_e = reinterpret_cast<const __half*>(wimg_eval_h); P.wimg_t = reinterpret_cast<const __half*>(wimg_target_h);
     P.trace = nullptr;
+    { const char* d = getenv("RL_PAIR_DBG"); P.dbg = d ? atoi(d) : 0; const int nr = (P.dbg & 4) ? 1 : 0; RL_CUDA_CHECK(cudaMemcpyToSymbol(g_no_red, &nr, sizeof(int))); }
     static long long* trace_dev = nullptr;
     const bool tracing = getenv("RL_TC_TRACE") != nullptr;
     if (tracing) {
