@@ -172,7 +172,7 @@ def parity_check(env, brains, precision):
                     _lib.check(lib.rl_brain_learn(C.byref(w.cfg), C.byref(env.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
                                                   C.c_void_p(dev.sample_idx.data_ptr()), C.byref(dev.learn_bufs), st))
                 elif mode == "fp16":
-                    _lib.check(lib.rl_brain_learn_h(C.byref(w.cfg), C.byref(env.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
+                    _lib.check(lib.rl_brain_learn_p(C.byref(w.cfg), C.byref(env.rows.bufs), C.c_int32(g), C.byref(b._replay.bufs),
                                                     C.c_void_p(dev.sample_idx.data_ptr()), C.byref(dev.learn_bufs),
                                                     C.c_void_p(dev.wimg_eh.data_ptr()), C.c_void_p(dev.wimg_th.data_ptr()), st))
                 else:
@@ -306,7 +306,7 @@ def run_b200(args):
     env.kernel_events = None
     learn_kernel_ms = sum(k_ms) / max(1, len(k_ms))
     ev_per_launch = ev_avg / len(brains)
-    learn_kernel_name = {"fp16": "k_learn_dueling_h", "tf32": "k_learn_dueling_tc2", "fp32": "k_learn_dueling"}[args.precision]
+    learn_kernel_name = {"fp16": "k_learn_dueling_p", "tf32": "k_learn_dueling_tc2", "fp32": "k_learn_dueling"}[args.precision]
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01_final.json"))).get(learn_kernel_name + "_bytes_per_launch")

@@ -118,6 +118,7 @@ class Environment:
         self.sequential_events = bool(sequential_events)
         if self.sequential_events and (self.n_worlds != 1 or self.world_size != 1):
             raise ValueError("sequential_events=True is the exact single-world mode: n_worlds must be 1 (one rank)")
+        self._learn_single = os.environ.get("RL_LEARN_SINGLE") is not None   # A/B: the one-event-per-iteration fp16 kernel
         self._act_tc = os.environ.get("RL_ACT_FP32") is None    # tf32 runs: get_action of dueling brains on the tensor cores too
         self._grad_all = None
         # Multi-GPU: the "did this brain act / store / trigger this step" conditions of the epsilon schedules and target
@@ -337,8 +338,9 @@ class Environment:
                     self.gpu_launches += 2
                 if ev0 is not None:
                     ev0.record()
-                if self._learn_fp16:
-                    _lib.check(lib.rl_brain_learn_h(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
+                if self._learn_fp16:                                  # two events per CTA iteration (csrc/tc_pair_kernels.cu)
+                    fn = lib.rl_brain_learn_h if self._learn_single else lib.rl_brain_learn_p
+                    _lib.check(fn(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
                                                     C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs),
                                                     C.c_void_p(b._dev.wimg_eh.data_ptr()), C.c_void_p(b._dev.wimg_th.data_ptr()), st))
                 else:

@@ -195,7 +195,9 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
         // that touches 128..255.
         if (lane == 0) {
             uint32_t consumed = 0, go_no = 0, stage = 0;
-            auto wait_go = [&]() { mbar_wait(go, go_no & 1); ++go_no; fence_after(); };
+            int itr_n = 0, itr_p = -1;
+            auto istamp = [&]() { if (P.trace && blockIdx.x == 0 && itr_p == 3 && itr_n < 40) P.trace[64 + itr_n++] = clock64(); };
+            auto wait_go = [&]() { mbar_wait(go, go_no & 1); ++go_no; fence_after(); istamp(); };
             auto chunk_wait = [&]() -> uint32_t {
                 const uint32_t slot = consumed % NSP;
                 mbar_wait(&full[slot], (consumed / NSP) & 1);
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 ++consumed;
                 return smem_u32(sStg + slot * HCH);
             };
-            auto stage_free = [&]() { mma_commit(&sfree[stage % NSTG]); ++stage; };
+            auto stage_free = [&]() { istamp(); mma_commit(&sfree[stage % NSTG]); ++stage; };
             // L1: D[128 b][128 k1] = X[128][160] W1[128][160]^T -- 5 chunks [128 n][32 k], 2 k-steps each
             auto l1 = [&]() {
                 const uint32_t id = idesc_h(128, 128, 0, 0);
@@ -240,6 +242,7 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 mma_commit(done);
             };
             for (int p = 0; p < n_pairs; ++p) {
+                itr_p = p;
                 wait_go(); l1();                                   // target net
                 wait_go(); l2();
                 wait_go(); head(); l1();                           // target head, then the eval L1 (runs under the target head epilogue)
@@ -650,8 +653,8 @@ extern "C" int rl_brain_learn_p(const rl_world_cfg* cfg, const rl_rows_bufs* row
     static long long* trace_dev = nullptr;
     const bool tracing = getenv("RL_TC_TRACE") != nullptr;
     if (tracing) {
-        if (!trace_dev) RL_CUDA_CHECK(cudaMalloc(&trace_dev, 64 * sizeof(long long)));
-        RL_CUDA_CHECK(cudaMemset(trace_dev, 0, 64 * sizeof(long long)));
+        if (!trace_dev) RL_CUDA_CHECK(cudaMalloc(&trace_dev, 128 * sizeof(long long)));
+        RL_CUDA_CHECK(cudaMemset(trace_dev, 0, 128 * sizeof(long long)));
         P.trace = trace_dev;
     }
     static PerDeviceOnce attr;
@@ -660,11 +663,13 @@ extern "C" int rl_brain_learn_p(const rl_world_cfg* cfg, const rl_rows_bufs* row
     k_learn_dueling_p<<<rl_learn_grid(), NTH, PAIR_SMEM, st>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
     if (tracing) {
-        long long h[64];
+        long long h[128];
         RL_CUDA_CHECK(cudaStreamSynchronize(st));
         RL_CUDA_CHECK(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[pair trace] deltas (cycles) between stamps of pair 3:");
-        for (int i = 1; i < 40 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[i - 1]);
+        fprintf(stderr, "[pair trace] epilogue stamps (cycles since the pair's start):");
+        for (int i = 1; i < 40 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
+        fprintf(stderr, "\n[pair trace] issuer stamps (go seen / last MMA of a chunk stage issued):");
+        for (int i = 0; i < 40 && h[64 + i]; ++i) fprintf(stderr, " %lld", h[64 + i] - h[0]);
         fprintf(stderr, "\n");
     }
     return rl_learn_reduce(learn, P.ev_total, 1, (void*)st);

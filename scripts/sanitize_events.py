@@ -35,9 +35,9 @@ def events(n_per_cta=3):
     rp.reward.copy_(torch.randn_like(rp.reward)); rp.len[:] = 128
     n_ev = _fake_events(vw, rows, per_world)
     sidx = torch.from_numpy(rng.integers(0, 128, size=(n_ev, 64)).astype(np.int32)).cuda()
-    for mode in ("fp16", "tf32", "fp32"):
+    for mode in ("fp16p", "fp16", "tf32", "fp32"):
         brain = DeviceBrain(0, packing.default_init(0), "cuda")
-        brain.use_fp16 = mode == "fp16"
+        brain.use_fp16 = mode in ("fp16", "fp16p")
         brain.alloc_learn(rows.row_cap)
         brain.sample_idx[:n_ev] = sidx
         st = vw._stream()
@@ -46,8 +46,8 @@ def events(n_per_cta=3):
                                              C.c_void_p(brain.sample_idx.data_ptr()), C.byref(brain.learn_bufs), st))
         else:
             brain.build_wimg(st)
-            fn = vw.lib.rl_brain_learn_h if mode == "fp16" else vw.lib.rl_brain_learn_tc
-            we, wt = (brain.wimg_eh, brain.wimg_th) if mode == "fp16" else (brain.wimg_e, brain.wimg_t)
+            fn = {"fp16": vw.lib.rl_brain_learn_h, "fp16p": vw.lib.rl_brain_learn_p}.get(mode, vw.lib.rl_brain_learn_tc)
+            we, wt = (brain.wimg_eh, brain.wimg_th) if mode in ("fp16", "fp16p") else (brain.wimg_e, brain.wimg_t)
             _lib.check(fn(C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(rp.bufs), C.c_void_p(brain.sample_idx.data_ptr()),
                           C.byref(brain.learn_bufs), C.c_void_p(we.data_ptr()), C.c_void_p(wt.data_ptr()), st))
         torch.cuda.synchronize()

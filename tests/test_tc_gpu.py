@@ -67,9 +67,9 @@ def test_tensor_core_learn_matches_fp32_learn():
     n_ev = _fake_events(vw, rows, per_world)
     sidx = torch.from_numpy(rng.integers(0, 200, size=(n_ev, 64)).astype(np.int32)).cuda()
     out = {}
-    for mode in ("fp32", "tf32", "fp16"):
+    for mode in ("fp32", "tf32", "fp16", "fp16p"):       # fp16p = rl_brain_learn_p (two events per CTA iteration)
         brain = DeviceBrain(0, w0, "cuda", lr=1e-3, gamma=0.99)
-        brain.use_fp16 = mode == "fp16"
+        brain.use_fp16 = mode in ("fp16", "fp16p")
         brain.load_state_dict(tgt, target=True)
         brain.alloc_learn(rows.row_cap)
         brain.sample_idx[:n_ev] = sidx
@@ -83,9 +83,10 @@ def test_tensor_core_learn_matches_fp32_learn():
                                                 C.c_void_p(brain.wimg_e.data_ptr()), C.c_void_p(brain.wimg_t.data_ptr()), vw._stream()))
         else:
             brain.build_wimg(vw._stream())
-            _lib.check(vw.lib.rl_brain_learn_h(C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(rp.bufs),
-                                               C.c_void_p(brain.sample_idx.data_ptr()), C.byref(brain.learn_bufs),
-                                               C.c_void_p(brain.wimg_eh.data_ptr()), C.c_void_p(brain.wimg_th.data_ptr()), vw._stream()))
+            fn = vw.lib.rl_brain_learn_p if mode == "fp16p" else vw.lib.rl_brain_learn_h
+            _lib.check(fn(C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(rp.bufs),
+                          C.c_void_p(brain.sample_idx.data_ptr()), C.byref(brain.learn_bufs),
+                          C.c_void_p(brain.wimg_eh.data_ptr()), C.c_void_p(brain.wimg_th.data_ptr()), vw._stream()))
         torch.cuda.synchronize()
         out[mode] = (brain.grad.cpu().numpy().copy(), brain.loss[:n_ev].cpu().numpy().copy(), brain.new_prio[:n_ev].cpu().numpy().copy())
     g32, l32, p32 = out["fp32"]
@@ -93,7 +94,7 @@ def test_tensor_core_learn_matches_fp32_learn():
     d = packing.dims(0)
     m = packing.grad_mask(0)
     nt = len(g32) - 4
-    for mode in ("tf32", "fp16"):       # both carry 11 significant bits per operand, fp32 accumulation
+    for mode in ("tf32", "fp16", "fp16p"):       # all carry 11 significant bits per operand, fp32 accumulation
         gtc, ltc, ptc = out[mode]
         assert gtc[nt] == n_ev
         for name, lo, hi in (("W1", 0, d.off_b1), ("b1", d.off_b1, d.off_w2t), ("W2", d.off_w2t, d.off_b2), ("b2", d.off_b2, d.off_wh),
