@@ -256,12 +256,12 @@ def test_act_kernels_600_tiles_per_brain():
         q32 = out["fp32"][0][i, :n]
         np.testing.assert_allclose(q32[pick], q_or, rtol=1e-4, atol=1e-4)
         scale = np.abs(q32).max()
-        for mode in ("tf32", "fp16", "fp16p"):
+        for mode in ("tf32", "fp16"):
             qtc = out[mode][0][i, :n]
             assert np.abs(qtc[pick] - q_or).max() < 2e-2 * scale, (mode, "vs oracle")
             assert np.abs(q32 - qtc).max() < 2e-2 * scale, mode
             assert (q32.argmax(1) == qtc.argmax(1)).mean() >= 0.99, mode
-    for mode in ("tf32", "fp16", "fp16p"):
+    for mode in ("tf32", "fp16"):
         atc = out[mode][1]
         assert ((atc != -1) == listed).all(), mode
         assert (a32[listed] == atc[listed]).mean() >= 0.99, mode
