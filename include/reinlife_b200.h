@@ -199,8 +199,8 @@ int rl_brain_act_all(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const r
  * only the brains' weights (so at N=1 the buffer is exactly Models/PERD3QN.py:133-182).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct rl_replay_bufs {             /* per brain; ring index = local world */
-    float*   obs;        /* [n_worlds, capacity, obs_ld]  state        */
-    float*   next_obs;   /* [n_worlds, capacity, obs_ld]  state_prime  */
+    float*   obs;        /* [n_worlds, capacity, obs_ld]  state        (float32, or float16 when obs_fp16 = 1) */
+    float*   next_obs;   /* [n_worlds, capacity, obs_ld]  state_prime  (same element type as obs)               */
     int8_t*  action;     /* [n_worlds, capacity] */
     float*   reward;     /* [n_worlds, capacity] float32(reward) (PPO: reward/100, PPO.py:73) */
     uint8_t* done;       /* [n_worlds, capacity] */
@@ -210,6 +210,11 @@ typedef struct rl_replay_bufs {             /* per brain; ring index = local wor
     int32_t* pos;        /* [n_worlds] */
     int32_t  capacity;
     int32_t  prioritized;/* 1: proportional PER (PERD3QN); 0: uniform (D3QN, DQN) */
+    int32_t  obs_fp16;   /* 1: obs / next_obs rows are stored as float16 (obs_ld halves per row, column obs_ld-1 = 1.0): the ring
+                            of the dueling brains under precision="fp16" -- the tensor-core event kernel consumes fp16 operands, so the
+                            rows are rounded once at store time instead of at every gather; half the ring memory and traffic.
+                            Readers: rl_replay_store (writes), rl_brain_learn_p, rl_brain_learn (fp32 arithmetic on the rounded rows). */
+    int32_t  _pad;
 } rl_replay_bufs;
 
 /* brain.memorize for every STORE row of `gene` (PERD3QN.py:91-92,143-155): state = obs_state[prev_slot],

@@ -66,12 +66,14 @@ class DeviceBrainBase(BasicBrain):
         self._env, self._gene = env, gene
         if env.training and self._trains():
             if self._replay is None:
-                need = ReplayRings.bytes_needed(env.n_worlds, self._capacity())
+                # the dueling brains' rings hold float16 rows when their events run on fp16 tensor-core operands
+                fp16 = bool(getattr(env, "_learn_fp16", False)) and self.KIND == packing.DUELING and not getattr(env, "_learn_single", False)
+                need = ReplayRings.bytes_needed(env.n_worlds, self._capacity(), fp16=fp16)
                 free, _ = torch.cuda.mem_get_info(env.device)
                 if need > 0.9 * free:
                     raise MemoryError(f"replay rings for {env.n_worlds} worlds x capacity {self._capacity()} need "
                                       f"{need / 2**30:.1f} GiB, {free / 2**30:.1f} GiB free; lower `capacity`")
-                self._replay = ReplayRings(env.n_worlds, self._capacity(), env.device, prioritized=self.PRIORITIZED)
+                self._replay = ReplayRings(env.n_worlds, self._capacity(), env.device, prioritized=self.PRIORITIZED, fp16=fp16)
             self._dev.alloc_learn(env.rows.row_cap)
 
     def _trains(self):

@@ -87,10 +87,20 @@ class Environment:
                               incentivize_killing=incentivize_killing, device=self.device)
         self.rows = RowLists(self.world)
         G = len(brains)
+        # "tf32": train() events on the tensor cores (tcgen05 kind::tf32, fp32 accumulate); "fp32": CUDA-core FMA path
+        if precision not in ("tf32", "fp16", "fp32"):
+            raise ValueError("precision must be 'tf32', 'fp16' or 'fp32'")
+        # "fp16": train() events with fp16 operands (tcgen05 kind::f16, fp32 accumulate); get_action stays on the tf32 forward
+        self._learn_fp16 = precision == "fp16"
+        self.precision = "tf32" if precision == "fp16" else precision
+        self._learn_single = os.environ.get("RL_LEARN_SINGLE") is not None   # A/B: the one-event-per-iteration fp16 kernel
         for g, b in enumerate(brains):
             if not hasattr(b, "_bind"):
                 raise TypeError(f"brain {g} ({type(b).__name__}) is not a reinlife_b200.Models brain")
             b._bind(self, g)
+        for b in brains:
+            if getattr(b, "_dev", None) is not None:
+                b._dev.use_fp16 = self._learn_fp16
         self._eps = torch.tensor([float(b.epsilon) if hasattr(b, "epsilon") else 0.0 for b in brains],
                                  dtype=torch.float64, device=self.device)
         self._seen = torch.tensor([int(getattr(b, "n_epi", 0)) for b in brains], dtype=torch.int64, device=self.device)
@@ -102,15 +112,6 @@ class Environment:
                 torch.distributed.broadcast(b._dev.params, 0)
                 if b._dev.target is not None:
                     torch.distributed.broadcast(b._dev.target, 0)
-        # "tf32": train() events on the tensor cores (tcgen05 kind::tf32, fp32 accumulate); "fp32": CUDA-core FMA path
-        if precision not in ("tf32", "fp16", "fp32"):
-            raise ValueError("precision must be 'tf32', 'fp16' or 'fp32'")
-        # "fp16": train() events with fp16 operands (tcgen05 kind::f16, fp32 accumulate); get_action stays on the tf32 forward
-        self._learn_fp16 = precision == "fp16"
-        self.precision = "tf32" if precision == "fp16" else precision
-        for b in brains:
-            if getattr(b, "_dev", None) is not None:
-                b._dev.use_fp16 = self._learn_fp16
         # sequential_events=True (one world, one rank): learn() walks the agents in the reference's order and runs
         # store -> train -> priorities -> Adam -> target sync PER AGENT, so that every train() sees the weights and the ring
         # the previous agent's train() left (Helpers/trainer.py:95-96, PERD3QN.py:117-125) -- the reference's exact N = 1
@@ -118,7 +119,6 @@ class Environment:
         self.sequential_events = bool(sequential_events)
         if self.sequential_events and (self.n_worlds != 1 or self.world_size != 1):
             raise ValueError("sequential_events=True is the exact single-world mode: n_worlds must be 1 (one rank)")
-        self._learn_single = os.environ.get("RL_LEARN_SINGLE") is not None   # A/B: the one-event-per-iteration fp16 kernel
         self._act_tc = os.environ.get("RL_ACT_FP32") is None    # tf32 runs: get_action of dueling brains on the tensor cores too
         self._grad_all = None
         # Multi-GPU: the "did this brain act / store / trigger this step" conditions of the epsilon schedules and target

@@ -90,11 +90,14 @@ class DeviceBrain:
 class ReplayRings:
     """One ring per local world for one brain (rl_replay_bufs)."""
 
-    def __init__(self, n_worlds, capacity, device, prioritized=True, ld=_lib.OBS_LD):
+    def __init__(self, n_worlds, capacity, device, prioritized=True, ld=_lib.OBS_LD, fp16=False):
         dev = torch.device(device)
-        self.n_worlds, self.capacity, self.prioritized = n_worlds, int(capacity), bool(prioritized)
-        self.obs = torch.empty((n_worlds, capacity, ld), device=dev)
-        self.next_obs = torch.empty((n_worlds, capacity, ld), device=dev)
+        self.n_worlds, self.capacity, self.prioritized, self.fp16 = n_worlds, int(capacity), bool(prioritized), bool(fp16)
+        # fp16=True: rows rounded to float16 once, at store time (rl_replay_bufs.obs_fp16) -- the ring of the dueling brains
+        # under precision="fp16", whose tensor-core event kernel consumes fp16 operands anyway
+        dt = torch.float16 if fp16 else torch.float32
+        self.obs = torch.empty((n_worlds, capacity, ld), dtype=dt, device=dev)
+        self.next_obs = torch.empty((n_worlds, capacity, ld), dtype=dt, device=dev)
         self.action = torch.zeros((n_worlds, capacity), dtype=torch.int8, device=dev)
         self.reward = torch.zeros((n_worlds, capacity), device=dev)
         self.done = torch.zeros((n_worlds, capacity), dtype=torch.uint8, device=dev)
@@ -104,11 +107,12 @@ class ReplayRings:
         self.pos = torch.zeros(n_worlds, dtype=torch.int32, device=dev)
         self.bufs = _lib.ReplayBufs(self.obs.data_ptr(), self.next_obs.data_ptr(), self.action.data_ptr(),
                                     self.reward.data_ptr(), self.done.data_ptr(), self.prio.data_ptr(), self.pw.data_ptr(),
-                                    self.len.data_ptr(), self.pos.data_ptr(), self.capacity, int(self.prioritized))
+                                    self.len.data_ptr(), self.pos.data_ptr(), self.capacity, int(self.prioritized),
+                                    int(self.fp16), 0)
 
     @staticmethod
-    def bytes_needed(n_worlds, capacity, ld=_lib.OBS_LD):
-        return n_worlds * capacity * (2 * ld * 4 + 1 + 4 + 1 + 4 + 4)
+    def bytes_needed(n_worlds, capacity, ld=_lib.OBS_LD, fp16=False):
+        return n_worlds * capacity * (2 * ld * (2 if fp16 else 4) + 1 + 4 + 1 + 4 + 4)
 
 
 class SumTrees:

@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(NT, 1) k_learn_dueling(const LearnParams P) {
         }
         __syncthreads();
         // ---- target forward on next_obs (PERD3QN.py:104-105) ----
-        gather64(bufX, LDX, P.rp.next_obs + ring * RL_K1, idx);
+        if (P.rp.obs_fp16) gather64_h(bufX, LDX, reinterpret_cast<const __half*>(P.rp.next_obs) + ring * RL_K1, idx);
+        else gather64(bufX, LDX, P.rp.next_obs + ring * RL_K1, idx);
         __syncthreads();
         gemm_stage<RL_K1, M::N1, 1, true>(bufX, LDX, Pt + L::OFF_W1T, Pt + L::OFF_B1, bufH1, LDH1, pp);
         gemm_stage<M::N1, M::N2, 1, true>(bufH1, LDH1, Pt + L::OFF_W2T, Pt + L::OFF_B2, bufH2, LDH2, pp);
@@ -96,7 +97,8 @@ __global__ void __launch_bounds__(NT, 1) k_learn_dueling(const LearnParams P) {
         }
         __syncthreads();
         // ---- eval forward on obs (:103), activations kept for the backward ----
-        gather64(bufX, LDX, P.rp.obs + ring * RL_K1, idx);
+        if (P.rp.obs_fp16) gather64_h(bufX, LDX, reinterpret_cast<const __half*>(P.rp.obs) + ring * RL_K1, idx);
+        else gather64(bufX, LDX, P.rp.obs + ring * RL_K1, idx);
         __syncthreads();
         gemm_stage<RL_K1, M::N1, 1, true>(bufX, LDX, Pe + L::OFF_W1T, Pe + L::OFF_B1, bufH1, LDH1, pp);
         gemm_stage<M::N1, M::N2, 1, true>(bufH1, LDH1, Pe + L::OFF_W2T, Pe + L::OFF_B2, bufH2, LDH2, pp);

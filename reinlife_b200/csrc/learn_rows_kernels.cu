@@ -210,6 +210,7 @@ extern "C" {
 
 int rl_brain_learn_dqn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
                        const int32_t* sample_idx, const rl_learn_bufs* learn, void* stream) {
+    if (replay && replay->obs_fp16) return rl_set_err(RL_ERR_UNSUPPORTED, "rl_brain_learn_dqn: float16 replay rows are not supported");
     RL_ARG_CHECK(cfg && rows && replay && sample_idx && learn);
     RL_ARG_CHECK(gene >= 0 && gene < cfg->n_genes && cfg->obs_ld == RL_K1);
     RL_ARG_CHECK(learn->kind == RL_MODEL_DQN && learn->batch == 32);
@@ -236,6 +237,7 @@ int rl_brain_learn_dqn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_
 
 int rl_brain_learn_perdqn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
                           const int32_t* sample_idx, const float* ev_weight, const rl_learn_bufs* learn, void* stream) {
+    if (replay && replay->obs_fp16) return rl_set_err(RL_ERR_UNSUPPORTED, "rl_brain_learn_perdqn: float16 replay rows are not supported");
     RL_ARG_CHECK(cfg && rows && replay && sample_idx && ev_weight && learn);
     RL_ARG_CHECK(gene >= 0 && gene < cfg->n_genes && cfg->obs_ld == RL_K1);
     RL_ARG_CHECK(learn->kind == RL_MODEL_DQN && learn->batch == 64);

@@ -2,6 +2,7 @@
 // learn_rows_kernels.cu: DQN and PPO row tiles): block reductions, weight-gradient outer products into the CTA-private
 // slab, column sums, replay-row gathers and the small head GEMV.
 #pragma once
+#include <cuda_fp16.h>
 #include "mlp_tile.cuh"
 #include "models.cuh"
 
@@ -68,6 +69,17 @@ __device__ __forceinline__ void colsum_accum(const float* __restrict__ B, int ld
 #pragma unroll 8
         for (int b = 0; b < R; ++b) s += B[(size_t)b * ldb + n];
         G[n] += s;
+    }
+}
+
+// the same gather from a float16 ring (rl_replay_bufs.obs_fp16): fp32 arithmetic on the rows as they were rounded at store time
+__device__ __forceinline__ void gather64_h(float* dst, int ldd, const void* __restrict__ src, const int* ids) {
+    const uint2* s2 = reinterpret_cast<const uint2*>(src);
+    for (int v = threadIdx.x; v < R * (RL_K1 / 4); v += NT) {
+        const int r = v / (RL_K1 / 4), c4 = v - r * (RL_K1 / 4);
+        const uint2 h = __ldg(s2 + (size_t)ids[r] * (RL_K1 / 4) + c4);
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+        *reinterpret_cast<float4*>(dst + (size_t)r * ldd + c4 * 4) = make_float4(lo.x, lo.y, hi.x, hi.y);
     }
 }
 

@@ -4,9 +4,15 @@
 // priorities initialised to 0, new items stored with max(priorities) (1.0 while empty), proportional sampling
 // prio^0.6 with replacement (np.random.choice = cumsum + searchsorted), update_priorities by sequential
 // overwrite.  The unused importance weights / beta bookkeeping (:168-172) are not materialised.
+#include <cuda_fp16.h>
 #include "rl_common.cuh"
 
 namespace {
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    return (uint32_t)__half_as_ushort(__float2half_rn(a)) | ((uint32_t)__half_as_ushort(__float2half_rn(b)) << 16);
+}
+
 
 constexpr int RT = 256;
 
@@ -65,9 +71,20 @@ __global__ void __launch_bounds__(RT) k_replay_store(const ReplayParams P) {
         const int p = (pos + tr) % cap;
         const float4* s0 = reinterpret_cast<const float4*>(P.wb.obs_state + ((size_t)w * S + prev) * ld);
         const float4* s1 = reinterpret_cast<const float4*>(P.wb.obs_prime + (size_t)row * ld);
-        float4* d0 = reinterpret_cast<float4*>(P.rp.obs + ((size_t)w * cap + p) * ld);
-        float4* d1 = reinterpret_cast<float4*>(P.rp.next_obs + ((size_t)w * cap + p) * ld);
-        for (int v = lane; v < ld / 4; v += 32) { d0[v] = __ldg(s0 + v); d1[v] = __ldg(s1 + v); }
+        if (P.rp.obs_fp16) {        // float16 ring: rows rounded once here; the last (padding) column carries 1.0 (db1 rides the dW1 GEMM)
+            uint2* h0 = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(P.rp.obs) + ((size_t)w * cap + p) * ld);
+            uint2* h1 = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(P.rp.next_obs) + ((size_t)w * cap + p) * ld);
+            for (int v = lane; v < ld / 4; v += 32) {
+                float4 a = __ldg(s0 + v), b = __ldg(s1 + v);
+                if (v == ld / 4 - 1) { a.w = 1.0f; b.w = 1.0f; }
+                h0[v] = make_uint2(pack_half2(a.x, a.y), pack_half2(a.z, a.w));
+                h1[v] = make_uint2(pack_half2(b.x, b.y), pack_half2(b.z, b.w));
+            }
+        } else {
+            float4* d0 = reinterpret_cast<float4*>(P.rp.obs + ((size_t)w * cap + p) * ld);
+            float4* d1 = reinterpret_cast<float4*>(P.rp.next_obs + ((size_t)w * cap + p) * ld);
+            for (int v = lane; v < ld / 4; v += 32) { d0[v] = __ldg(s0 + v); d1[v] = __ldg(s1 + v); }
+        }
         if (lane == 0) {
             const size_t q = (size_t)w * cap + p;
             P.rp.action[q] = (int8_t)((rv.w >> 8) & 0xFF);

@@ -1696,6 +1696,7 @@ int rl_brain_build_wimg_h(int32_t kind, const float* params, void* wimg_h, void*
 int rl_brain_learn_h(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
                      const int32_t* sample_idx, const rl_learn_bufs* learn, const void* wimg_eval_h, const void* wimg_target_h,
                      void* stream) {
+    if (replay && replay->obs_fp16) return rl_set_err(RL_ERR_UNSUPPORTED, "rl_brain_learn_h: float16 replay rows are read by rl_brain_learn_p / rl_brain_learn only");
     RL_ARG_CHECK(cfg && rows && replay && sample_idx && learn && wimg_eval_h && wimg_target_h);
     RL_ARG_CHECK(gene >= 0 && gene < cfg->n_genes && cfg->obs_ld == RL_K1 && learn->batch == R);
     RL_ARG_CHECK(learn->params && learn->target && learn->grad_scratch && learn->grad && learn->new_prio && learn->loss);
@@ -1766,6 +1767,7 @@ int rl_brain_act_h(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_
 int rl_brain_learn_tc(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
                       const int32_t* sample_idx, const rl_learn_bufs* learn, const float* wimg_eval, const float* wimg_target,
                       void* stream) {
+    if (replay && replay->obs_fp16) return rl_set_err(RL_ERR_UNSUPPORTED, "rl_brain_learn_tc: float16 replay rows are read by rl_brain_learn_p / rl_brain_learn only");
     RL_ARG_CHECK(cfg && rows && replay && sample_idx && learn && wimg_eval && wimg_target);
     RL_ARG_CHECK(gene >= 0 && gene < cfg->n_genes && cfg->obs_ld == RL_K1 && learn->batch == R);
     RL_ARG_CHECK(learn->params && learn->target && learn->grad_scratch && learn->grad && learn->new_prio && learn->loss);

@@ -72,10 +72,8 @@ __device__ __forceinline__ uint32_t pk(float a, float b) {
 __device__ __forceinline__ float sat(float x) { return fminf(fmaxf(x, -60000.f), 60000.f); }
 __device__ __forceinline__ float hlo(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xFFFFu))); }
 __device__ __forceinline__ float hhi(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }
-__device__ int g_no_red;   // RL_PAIR_DBG & 4
-__device__ __forceinline__ void red_add(float* p, float v) { if (g_no_red) return; asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
-    if (g_no_red) return;
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -109,7 +107,7 @@ struct PairParams {
     const __half* wimg_e;
     const __half* wimg_t;
     long long* trace;      // debug: clock64 stamps of CTA 0, pair 3 (RL_TC_TRACE=1), else nullptr
-    int dbg;               // timing experiments only (RL_PAIR_DBG): 1 gathers read ring row 0, 2 no db2 reduce-scatter, 4 no global reds
+    int dbg;               // reserved
 };
 
 __device__ __forceinline__ void sched_pair(int i, int& net, int& chunk) {
@@ -325,11 +323,12 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 m_ring = (size_t)(m_row / S) * cap; m_i = max(m_i, 0);
                 m_act = P.rp.action[m_ring + m_i]; m_rew = P.rp.reward[m_ring + m_i]; m_dn = (float)P.rp.done[m_ring + m_i];
                 // pull the two 640-byte rows of this sample towards L2 now: the gathers of the next pair then hit L2, not HBM
-                const float* r0 = P.rp.next_obs + (m_ring + m_i) * RL_K1; const float* r1 = P.rp.obs + (m_ring + m_i) * RL_K1;
-#pragma unroll
-                for (int ln = 0; ln < 5; ++ln) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + ln * 32));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + ln * 32));
+                const size_t rb = (m_ring + m_i) * RL_K1 * (P.rp.obs_fp16 ? 2 : 4);                  // byte offset of the sample's row
+                const char* r0 = reinterpret_cast<const char*>(P.rp.next_obs) + rb; const char* r1 = reinterpret_cast<const char*>(P.rp.obs) + rb;
+                const int nl = P.rp.obs_fp16 ? 3 : 5;
+                for (int ln = 0; ln < nl; ++ln) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + ln * 128));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + ln * 128));
                 }
             }
         };
@@ -344,15 +343,30 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
         };
         // ---- 128 rows x 160 floats from the replay ring -> packed fp16 in registers (unit = 8 consecutive columns) ----
         uint4 xh[10];
+        const bool ring16 = P.rp.obs_fp16 != 0;
         auto gather_load = [&](const float* __restrict__ src, int buf) {
             const int* ids = meta + buf * 4 * PB;
+            if (ring16) {
+                // float16 ring: one 16-byte load per unit, straight into the packed registers -- nothing depends on the data
+                // until gather_store, so the loads stay in flight behind whatever the thread does next
+                const uint4* src16 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+                for (int u = 0; u < 10; ++u) {
+                    const int v = threadIdx.x + u * NEPI;
+                    const int rr = v & 7, o4 = (v >> 3) & 3, blk = v >> 5;
+                    const int rg = blk / 5, og = blk - rg * 5;
+                    const int r = rg * 8 + rr, oct = og * 4 + o4;
+                    xh[u] = __ldg(src16 + ((size_t)ringb[buf * 2 + (r >> 6)] + ids[r]) * (RL_K1 / 8) + oct);
+                }
+                return;
+            }
 #pragma unroll
             for (int u = 0; u < 10; ++u) {
                 const int v = threadIdx.x + u * NEPI;
                 const int rr = v & 7, o4 = (v >> 3) & 3, blk = v >> 5;
                 const int rg = blk / 5, og = blk - rg * 5;
                 const int r = rg * 8 + rr, oct = og * 4 + o4;
-                const float4* g = reinterpret_cast<const float4*>(src + ((size_t)ringb[buf * 2 + (r >> 6)] + ((P.dbg & 1) ? 0 : ids[r])) * RL_K1) + oct * 2;
+                const float4* g = reinterpret_cast<const float4*>(src + ((size_t)ringb[buf * 2 + (r >> 6)] + ids[r]) * RL_K1) + oct * 2;
                 const float4 a = __ldg(g), b = __ldg(g + 1);
                 xh[u] = make_uint4(pk(a.x, a.y), pk(a.z, a.w), pk(b.x, b.y), oct == 19 ? pk(b.z, 1.0f) : pk(b.z, b.w));   // column 159 := 1 (db1)
             }
@@ -553,8 +567,8 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 };
                 mask_store(va, 0, n0);
                 mask_store(vb, 4, n0 + 32);
-                cs[half * 2] = (P.dbg & 2) ? va[0] : warp_colsum32(va, lane);
-                cs[half * 2 + 1] = (P.dbg & 2) ? vb[0] : warp_colsum32(vb, lane);
+                cs[half * 2] = warp_colsum32(va, lane);
+                cs[half * 2 + 1] = warp_colsum32(vb, lane);
             }
             go_signal();                                            // -> dH1, dW2
 #pragma unroll
@@ -649,7 +663,7 @@ extern "C" int rl_brain_learn_p(const rl_world_cfg* cfg, const rl_rows_bufs* row
     P.rp = *replay; P.sample_idx = sample_idx; P.lb = *learn;
     P.wimg_e = reinterpret_cast<const __half*>(wimg_eval_h); P.wimg_t = reinterpret_cast<const __half*>(wimg_target_h);
     P.trace = nullptr;
-    { const char* d = getenv("RL_PAIR_DBG"); P.dbg = d ? atoi(d) : 0; const int nr = (P.dbg & 4) ? 1 : 0; RL_CUDA_CHECK(cudaMemcpyToSymbol(g_no_red, &nr, sizeof(int))); }
+    P.dbg = 0;
     static long long* trace_dev = nullptr;
     const bool tracing = getenv("RL_TC_TRACE") != nullptr;
     if (tracing) {

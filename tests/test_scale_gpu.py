@@ -364,3 +364,67 @@ def test_ppo_tile_kernels_many_tiles_vs_oracle():
     for k in acc:
         ref = acc[k] / n_ev
         np.testing.assert_allclose(got[k].numpy(), ref, rtol=1e-3, atol=2e-6 + 5e-5 * np.abs(ref).max(), err_msg=k)
+
+
+def _half_copy(rp):
+    """float16 twin of a float32 ring (what rl_replay_store writes when obs_fp16 = 1: rounded rows, last column = 1)."""
+    from reinlife_b200.brains import ReplayRings
+    r16 = ReplayRings(rp.n_worlds, rp.capacity, "cuda", prioritized=rp.prioritized, fp16=True)
+    r16.obs.copy_(rp.obs.half()); r16.next_obs.copy_(rp.next_obs.half())
+    r16.obs[..., -1] = 1.0; r16.next_obs[..., -1] = 1.0
+    for name in ("action", "reward", "done", "prio", "pw", "len", "pos"):
+        getattr(r16, name).copy_(getattr(rp, name))
+    return r16
+
+
+def test_float16_ring_pair_kernel_and_fp32_kernel():
+    """precision="fp16" keeps the dueling brains' replay rows as float16 (rl_replay_bufs.obs_fp16).  The paired event kernel
+    must give the SAME results from the float16 ring as from the float32 ring (it rounds the same rows to the same halves
+    at gather time), and the fp32 kernel reading the float16 ring (bench.py's parity_check) stays within the tensor-core
+    tolerance of the fp32 kernel on the float32 ring."""
+    from reinlife_b200.Models import packing
+    NW = 48
+    per_world = [13] * NW
+    per_world[5] = 0
+    z, vw, rows, rp, ring, n_ev, sidx = _events_setup(NW, per_world, seed=31)
+    r16 = _half_copy(rp)
+    w0, tgt = state_dict("train_perd3qn/w0"), state_dict("train_perd3qn/target")
+    sd = torch.from_numpy(sidx).cuda()
+    ref32 = _run_event_kernel("fp32", vw, rows, rp, w0, tgt, sd, n_ev)
+    p32 = _run_event_kernel("fp16p", vw, rows, rp, w0, tgt, sd, n_ev)
+    p16 = _run_event_kernel("fp16p", vw, rows, r16, w0, tgt, sd, n_ev)
+    f16 = _run_event_kernel("fp32", vw, rows, r16, w0, tgt, sd, n_ev)
+    assert (p32[1] == p16[1]).all() and (p32[2] == p16[2]).all()                  # per-event loss / priorities: identical
+    assert np.abs(p32[0] - p16[0]).max() <= 1e-4 * np.abs(p32[0]).max()           # gradients: red.add order only
+    d, m = packing.dims(0), packing.grad_mask(0)
+    _check_tc_vs(ref32, p16, m, d, n_ev, "pair kernel, float16 ring vs fp32 kernel, float32 ring")
+    _check_tc_vs(ref32, f16, m, d, n_ev, "fp32 kernel, float16 ring vs float32 ring")
+    _check_tc_vs(f16, p16, m, d, n_ev, "pair kernel vs fp32 kernel, both on the float16 ring")
+
+
+def test_replay_store_writes_float16_rows():
+    """rl_replay_store into a float16 ring == float16(row) of what it writes into a float32 ring, last column = 1."""
+    from reinlife_b200 import _lib
+    from reinlife_b200.brains import ReplayRings
+    from reinlife_b200.World.vecworld import VecWorld
+    from reinlife_b200.rows import RowLists
+    NW, cap = 5, 64
+    vw = VecWorld(NW, 12, 12, 2, max_agents=40, seed=3)
+    rows = RowLists(vw)
+    vw.reset(); vw.top_up(40)
+    a, b = ReplayRings(NW, cap, "cuda"), ReplayRings(NW, cap, "cuda", fp16=True)
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    for _ in range(4):
+        vw.set_actions(torch.randint(0, 8, (NW, vw.S), device="cuda", dtype=torch.int8, generator=g))
+        vw.step()
+        rows.build(kinds_mask=6, train_freq=[3, 3], event_on=[1, 1])
+        for rp in (a, b):
+            _lib.check(vw.lib.rl_replay_store(C.byref(vw.cfg), C.byref(vw.bufs), C.byref(rows.bufs), 0, C.byref(rp.bufs), vw._stream()))
+        vw.update(); vw.top_up(40)
+    torch.cuda.synchronize()
+    assert (a.len == b.len).all() and (a.pos == b.pos).all() and int(a.len.max()) == cap
+    for x, y in ((a.obs, b.obs), (a.next_obs, b.next_obs)):
+        want = x.half().clone(); want[..., -1] = 1.0
+        filled = torch.arange(cap, device="cuda")[None, :] < a.len[:, None]
+        assert torch.equal(y[filled], want[filled])
+    assert torch.equal(a.prio, b.prio) and torch.equal(a.action, b.action) and torch.equal(a.reward, b.reward)
