@@ -48,7 +48,7 @@ constexpr int PO_RED = PO_BIAS + 4 * 800;                 // reduction scratch f
 constexpr int PO_META = PO_RED + 4 * 64;                  // [2] x { idx[128] act[128] rew[128] dn[128] } int / float
 constexpr int PO_RING = PO_META + 2 * 4 * 4 * PB;         // [2][2] ring base (elements) per buffer / event, 64-bit
 constexpr int PO_BARS = PO_RING + 2 * 2 * 8;
-constexpr int NSTG = 8;                  // chunk-consuming stages per pair: tL1 tL2 thead eL1 eL2 ehead dH2 dH1
+constexpr int NSTG = 11;                 // ring release groups per pair: tL1 tL2a tL2b thead eL1 eL2a eL2b ehead dH2 dH1a dH1b
 constexpr size_t PAIR_SMEM = PO_BARS + 8 * (NSP + NSTG + 3) + 16;
 static_assert(PAIR_SMEM <= 227 * 1024 && PO_BARS % 8 == 0 && PO_RING % 8 == 0, "shared memory budget");
 
@@ -135,8 +135,9 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
     int* meta = reinterpret_cast<int*>(smem + PO_META);
     unsigned long long* ringb = reinterpret_cast<unsigned long long*>(smem + PO_RING);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PO_BARS);
-    // full[slot]: chunk landed; sfree[stage]: every MMA of that chunk-consuming stage has completed (its ring slots are free
-    // again -- one tcgen05.commit per STAGE instead of one per chunk: a commit between MMAs costs the issuer ~200 cycles)
+    // full[slot]: chunk landed; sfree[group]: every MMA that reads the chunks of that release group has completed (its ring
+    // slots are free again -- one tcgen05.commit per GROUP of 4-5 chunks instead of one per chunk: a commit between MMAs costs
+    // the issuer ~200 cycles; the 8-chunk stages are released in two halves so that the ring refills behind them)
     uint64_t* full = bars; uint64_t* sfree = bars + NSP; uint64_t* done = sfree + NSTG; uint64_t* doneL1 = done + 1; uint64_t* go = done + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(go + 1);
 
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 while (produced - freed >= (uint32_t)NSP) {
                     const uint32_t k = stage % NSTG;
                     mbar_wait(&sfree[k], (stage / NSTG) & 1);
-                    freed += (k == 0 || k == 3) ? 5u : (k == 1 || k == 4 || k == 7) ? 8u : 1u;
+                    freed += (k == 0 || k == 4) ? 5u : (k == 3 || k == 7 || k == 8) ? 1u : 4u;
                     ++stage;
                 }
                 int net, ch; sched_pair(produced % SCHED_P, net, ch);
@@ -226,6 +227,7 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 for (int c = 0; c < 8; ++c) {
                     mma_h(T0, a, dk(chunk_wait(), 16), id, c != 0);
                     a += 16u;
+                    if (c == 3) stage_free();
                 }
                 stage_free();
                 mma_commit(done);
@@ -274,6 +276,7 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                         mma_h(T0, a, b, id, c != 0);
                         mma_h(T0, a + 16u, b + 16u, id, 1u);
                         a += 32u;
+                        if (c == 3) stage_free();
                     }
                     stage_free();
                     // dW2[k1][n2] += sum_b H1[b][k1] dH2[b][n2]: both images read MN-major, accumulator resident in TMEM
