@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--worlds-per-gpu", type=int, default=4096)
     ap.add_argument("--capacity", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the additional fixed-4096-worlds (strong scaling) measurement")
     ap.add_argument("--precision", default="fp16", choices=["tf32", "fp16", "fp32"],
                     help="train() events: tcgen05 with fp16 operands (default) or tf32 operands (both 11 significant bits, fp32 accumulate), or fp32 CUDA-core FMA")
     ap.add_argument("--cpu-worlds-per-core", type=int, default=2)
@@ -196,6 +197,65 @@ def parity_check(env, brains, precision):
     return out
 
 
+# ----------------------------------------------------------------------------------------------- multi-GPU extras
+def replicas_identical(env, brains, world_size):
+    """Are the replicated brains bit-identical on every rank after the timed loops?  Integer checksum of the raw bits of
+    eval parameters, target parameters, Adam moments, step counters and epsilons, all-reduced with MIN and MAX."""
+    import torch
+    import torch.distributed as dist
+    parts = []
+    for b in brains:
+        d = b._dev
+        for t in (d.params, d.target, d.adam_m, d.adam_v):
+            if t is not None:
+                parts.append(t.view(torch.int32).to(torch.int64).sum().reshape(1))
+        parts.append(d.adam_step.to(torch.int64).reshape(1))
+    parts.append(env._eps.view(torch.int64).sum().reshape(1))
+    chk = torch.cat(parts)
+    if world_size == 1:
+        return True
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return bool(torch.equal(lo, hi))
+
+
+def strong_scaling_point(args, rl, PERD3QN, torch, dist, world_size, local, total_worlds=4096):
+    """BASELINE.json configs[3] as stated: a FIXED total of 4096 worlds sharded over the N GPUs (512 per GPU at N = 8), same
+    loop body, device-timed like `value`.  Printed as `strong`; the driver's own scaling numbers stay the weak ones."""
+    torch.manual_seed(0)
+    brains = [PERD3QN(exploration=0, capacity=args.capacity), PERD3QN(exploration=0, capacity=args.capacity)]
+    env = rl.Environment(width=W, height=H, brains=brains, max_agents=TARGET, update_interval=500, print_results=False,
+                         training=True, n_worlds=total_worlds, seed=0, device=torch.device("cuda", local), precision=args.precision)
+    env.reset(); env.top_up(TARGET)
+    count = torch.zeros(1, dtype=torch.int64, device=env.device)
+
+    def body(n_epi):
+        count.add_(env.world.n_agents.sum())
+        env.act(n_epi); env.step(); env.learn(n_epi); env.update_env(n_epi); env.top_up(TARGET)
+
+    n_epi = 1
+    for _ in range(max(3, args.warmup)):
+        body(n_epi); n_epi += 1
+    dist.barrier(); torch.cuda.synchronize()
+    count.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        body(n_epi); n_epi += 1
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=env.device)
+    agents = count.clone()
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    dist.all_reduce(agents, op=dist.ReduceOp.SUM)
+    same = replicas_identical(env, brains, world_size)
+    return {"scaling": "strong", "worlds_total": total_worlds, "worlds_per_gpu": env.n_worlds, "value": int(agents) / (float(ms) / 1e3),
+            "unit": UNIT, "ms_per_step": float(ms) / args.steps, "steps": args.steps, "replicas_identical": same,
+            "note": "fixed 4096 worlds over N GPUs; per-step device work shrinks with N while ~60 launches + the gradient / gate "
+                    "all-reduces per step do not: launch latency and all-reduce latency bound this point at large N"}
+
+
 # ----------------------------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     import torch
@@ -301,6 +361,7 @@ def run_b200(args):
     n_avg = n_agents_meas / n_meas / NW
     ev_avg = ev_meas / n_meas
     parity = parity_check(env, brains, args.precision) if rank == 0 else None
+    same = replicas_identical(env, brains, world_size)          # before parity_check's re-runs matter: they touch grad / loss only
     # the event kernel alone (one launch per brain per step): CUDA events recorded around rl_brain_learn(_tc)
     k_ms = [a.elapsed_time(b) for (_, _, a, b) in env.kernel_events]
     env.kernel_events = None
@@ -356,7 +417,9 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "public Environment API; per step: pinned control block H2D, tracker record + event counts D2H (host sync)"},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "roofline_kernels": roof_k,
-            "phase_ms": phases, "parity_check": parity}
+            "phase_ms": phases, "parity_check": parity, "replicas_identical": same}
+    if world_size > 1 and not args.no_strong:
+        line["strong"] = strong_scaling_point(args, rl, PERD3QN, torch, dist, world_size, local)
     if rank == 0:
         if world_size == 1 and not args.no_cpu_baseline:
             try:
