@@ -61,7 +61,7 @@ typedef struct rl_world_cfg {
     int32_t  max_agents;        /* Environment(max_agents) -- a soft cap */
     int32_t  slot_cap;          /* rows per world in rec/reward/obs buffers (<= height*width) */
     int32_t  obs_ld;            /* floats per observation row, >= 153, multiple of 4; pad is zero-filled */
-    int32_t  static_families;   /* only 1 is implemented */
+    int32_t  static_families;   /* 0: the *_ns entry points (rl_world_ns_bufs) */
     int32_t  limit_reproduction;
     int32_t  incentivize_killing;
     uint64_t seed;
@@ -102,6 +102,36 @@ int rl_world_step(const rl_world_cfg* cfg, const rl_world_bufs* bufs, uint64_t t
  * _remove_dead_agents :795, _get_observations :313, _update_agents_state :784).  Same `t` as the step
  * it follows.  Writes type/rec/n_agents/obs_state. */
 int rl_world_update(const rl_world_cfg* cfg, const rl_world_bufs* bufs, uint64_t t, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Non-static families (static_families = False): World/environment.py:149 (ten deep-copied best agents), :506-507
+ * (offspring share the parent's brain), :541-547 (_produce: gene = ++max_gene with a deep copy of a random best agent's
+ * brain), :728-739 (_update_best_agents on Agent.fitness with object identity).  The World side: per-agent float64
+ * fitness and a serial number (object identity, handed out in row-major order to agents that are new at the end of
+ * reset / update_env), and per world max_gene, the ten best agents and the _produce event of the last update_env --
+ * the event (new gene, source brain id) is what a brain pool executes.  Layouts equal oracle/rl_oracle.c (rlo_ns).
+ * A brain id is the gene of a lineage, or -1-k for the private copy of initial best agent k.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rl_ns_best { int64_t serial; double fitness; int32_t brain; int32_t _pad; } rl_ns_best;
+typedef struct rl_ns_state {
+    int32_t max_gene;            /* Environment.max_gene */
+    int32_t produced_gene;       /* gene created by the last update_env, -1 if none (set even when the grid was full) */
+    int32_t produced_src_best;   /* index into best[] that random.choice picked (:543) */
+    int32_t produced_src_brain;  /* brain id that is deep-copied */
+    int64_t next_serial;
+    rl_ns_best best[10];
+} rl_ns_state;
+typedef struct rl_world_ns_bufs {
+    double*      fitness;        /* [n_worlds, slot_cap] Agent.fitness of the listed agents */
+    int64_t*     serial;         /* [n_worlds, slot_cap] object identity of the listed agents */
+    rl_ns_state* state;          /* [n_worlds] */
+    int32_t*     n_lineages;     /* [n_worlds] distinct genes in the current list (tracker: Helpers/tracker.py:178-186), may be NULL */
+} rl_world_ns_bufs;
+/* reset / step / update_env with cfg->static_families = 0 (same contracts as the static entry points; status bit 2 = more
+ * than 256 distinct lineages alive in one world). */
+int rl_world_reset_ns(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_world_ns_bufs* ns, void* stream);
+int rl_world_step_ns(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_world_ns_bufs* ns, uint64_t t, void* stream);
+int rl_world_update_ns(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_world_ns_bufs* ns, uint64_t t, void* stream);
 
 /* Saturated-world generator of the benchmark: add agents on random empty cells until
  * `target` are on the grid (gene U{0..G-1}, health 10*U{1..20}, age U{0..max_age-1}), then observe. */

@@ -46,6 +46,21 @@ class VecWorld:
                                    self.gene_count.data_ptr(), self.status.data_ptr(),
                                    self.stats.data_ptr() if with_stats else None, None)
         self.t = 0
+        # non-static families (rl_world_ns_bufs): Agent.fitness, object identity, max_gene / best agents / _produce event
+        self.static_families = bool(static_families)
+        self.ns = None
+        if not self.static_families:
+            self.fitness = torch.zeros((n_worlds, self.S), dtype=torch.float64, device=dev)
+            self.serial = torch.zeros((n_worlds, self.S), dtype=torch.int64, device=dev)
+            self.ns_state = torch.zeros((n_worlds, C.sizeof(_lib.NsState)), dtype=torch.uint8, device=dev)
+            self.n_lineages = torch.zeros(n_worlds, dtype=torch.int32, device=dev)
+            self.ns = _lib.WorldNsBufs(self.fitness.data_ptr(), self.serial.data_ptr(), self.ns_state.data_ptr(),
+                                       self.n_lineages.data_ptr())
+
+    def ns_host(self):
+        """Host copy of the per-world non-static state as an array of _lib.NsState."""
+        raw = self.ns_state.cpu().numpy().tobytes()
+        return (_lib.NsState * self.n_worlds).from_buffer_copy(raw)
 
     def enable_reward_div100(self):
         """Have rl_world_step also write float32(reward / 100.0), the value PPOAgent.learn stores (Models/PPO.py:73)."""
@@ -59,17 +74,26 @@ class VecWorld:
     # --- the reference's Environment phases -------------------------------------------------------
     def reset(self):
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.rl_world_reset(C.byref(self.cfg), C.byref(self.bufs), self._stream()))
+            if self.ns is not None:
+                _lib.check(self.lib.rl_world_reset_ns(C.byref(self.cfg), C.byref(self.bufs), C.byref(self.ns), self._stream()))
+            else:
+                _lib.check(self.lib.rl_world_reset(C.byref(self.cfg), C.byref(self.bufs), self._stream()))
         self.t = 0
 
     def step(self):
         self.t += 1
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.rl_world_step(C.byref(self.cfg), C.byref(self.bufs), C.c_uint64(self.t), self._stream()))
+            if self.ns is not None:
+                _lib.check(self.lib.rl_world_step_ns(C.byref(self.cfg), C.byref(self.bufs), C.byref(self.ns), C.c_uint64(self.t), self._stream()))
+            else:
+                _lib.check(self.lib.rl_world_step(C.byref(self.cfg), C.byref(self.bufs), C.c_uint64(self.t), self._stream()))
 
     def update(self):
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.rl_world_update(C.byref(self.cfg), C.byref(self.bufs), C.c_uint64(self.t), self._stream()))
+            if self.ns is not None:
+                _lib.check(self.lib.rl_world_update_ns(C.byref(self.cfg), C.byref(self.bufs), C.byref(self.ns), C.c_uint64(self.t), self._stream()))
+            else:
+                _lib.check(self.lib.rl_world_update(C.byref(self.cfg), C.byref(self.bufs), C.c_uint64(self.t), self._stream()))
 
     def top_up(self, target, max_age=50):
         with torch.cuda.device(self.device):

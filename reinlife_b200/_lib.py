@@ -36,6 +36,19 @@ class WorldBufs(C.Structure):
                 ("status", C.c_void_p), ("stats", C.c_void_p), ("reward_div100", C.c_void_p)]
 
 
+class NsBest(C.Structure):          # rl_ns_best
+    _fields_ = [("serial", C.c_int64), ("fitness", C.c_double), ("brain", C.c_int32), ("_pad", C.c_int32)]
+
+
+class NsState(C.Structure):         # rl_ns_state: max_gene, the last _produce event, the ten best agents (non-static families)
+    _fields_ = [("max_gene", C.c_int32), ("produced_gene", C.c_int32), ("produced_src_best", C.c_int32),
+                ("produced_src_brain", C.c_int32), ("next_serial", C.c_int64), ("best", NsBest * 10)]
+
+
+class WorldNsBufs(C.Structure):     # rl_world_ns_bufs
+    _fields_ = [("fitness", C.c_void_p), ("serial", C.c_void_p), ("state", C.c_void_p), ("n_lineages", C.c_void_p)]
+
+
 _lib = None
 
 

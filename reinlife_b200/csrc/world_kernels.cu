@@ -25,10 +25,17 @@ constexpr int WNW = WT / 32;    // warps per world
 enum { M_ALIVE = 0, M_NFOOD, M_NPOISON, M_NSUPER, M_NB, M_PRESENT, M_ANY, M_PALL, M_ALIVE_G = 8,
        M_CNT_G = M_ALIVE_G + RL_MAX_GENES, M_PG = M_CNT_G + RL_MAX_GENES, M_WORDS = M_PG + RL_MAX_GENES };
 
+// non-static families (static_families = False; environment.py:149,506-507,541-547,728-739): genes are unbounded lineage
+// numbers, so inside a kernel every distinct gene of the world gets a compact id < NS_IDS (shared-memory hash table, ids by
+// table position: deterministic); per-gene tables are indexed by that id and rec[].gene carries the real gene.
+constexpr int NS_IDS = 256;     // distinct lineages alive in one world at a time (status bit 2 when exceeded)
+constexpr int NS_HASH = 1024;
+
 struct WParams {
     long long* trace;
     rl_world_cfg cfg;
     rl_world_bufs b;
+    rl_world_ns_bufs ns;
     uint64_t t;
     int32_t target, max_age, which;
     int32_t dbg;        // RL_WORLD_DEBUG bits (timing experiments only): 1 skip row stores, 2 skip observe, 4 early exit after sim
@@ -51,13 +58,50 @@ struct WS {
     uint16_t *aslot, *tgt, *src, *cellof;
     uint8_t *type, *ntype, *flags, *gene;
     int8_t* action;
+    int32_t *alive_g, *cnt_g, *pg;   // per-gene (static) / per-lineage-id (non-static) tables: alive count, listed count, count / n (float bits)
+    // ---- non-static families only ----
+    double* rtab64;     // [NS_IDS][4] float64 reward by (id, dead, killed): Agent.fitness accumulates it (entities.py:187-192)
+    double* fit;        // [slot_cap] Agent.fitness by OLD slot
+    long long* ser;     // [slot_cap] object identity by OLD slot
+    int32_t* hkey;      // [NS_HASH] gene keys of the id hash table (-1 = empty)
+    int32_t* id2gene;   // [NS_IDS]
+    uint8_t* hid;       // [NS_HASH] id of a table entry
+    uint32_t* nbmask;   // [Cw] cells holding a newborn agent (serial not handed out yet)
+    uint32_t* nbpre;    // [Cw] exclusive popc prefix of nbmask
+    rl_ns_state* st;    // the world's max_gene / best_agents / last _produce event
 };
+
+__host__ __device__ inline size_t ws_bytes_ns(int H, int W, int S) {
+    const size_t C = (size_t)H * W, Cw = ((C + 31) / 32 + 3) & ~(size_t)3;
+    const size_t Sp = ((size_t)S + 1) & ~(size_t)1;
+    return 4 * (size_t)NS_IDS * 8 + 8 * (size_t)NS_IDS * 4 + 16 * Sp + 4 * NS_HASH + 4 * NS_IDS + NS_HASH + 4 * 3 * NS_IDS + 4 * Cw * 2 + sizeof(rl_ns_state) + 64;
+}
 
 __host__ __device__ inline size_t ws_bytes(int H, int W) {
     const size_t C = (size_t)H * W, Cw = (C + 31) / 32, Cp = (C + 15) & ~(size_t)15;
     const size_t PADN = ((size_t)(H + 6) * (W + 6) + 3) & ~(size_t)3;
     const size_t TAB = 160 + (((size_t)H + 6 + 3) & ~(size_t)3) + (((size_t)W + 6 + 3) & ~(size_t)3) + RL_MAX_GENES * 8;
     return 4 * 2 * PADN + 4 * WNW * 16 * 8 + 4 * ((Cw + 3) & ~(size_t)3) * 3 + 4 * M_WORDS + 4 * TAB + 2 * Cp * 7 + Cp * 5;
+}
+
+// the non-static additions sit behind the static carve-up (8-byte aligned)
+__device__ inline void ws_carve_ns(WS& s, unsigned char* base, int H, int W, int S) {
+    const size_t C = (size_t)H * W, Cw = ((C + 31) / 32 + 3) & ~(size_t)3;
+    const size_t Sp = ((size_t)S + 1) & ~(size_t)1;
+    unsigned char* p = base + ((ws_bytes(H, W) + 15) & ~(size_t)15);
+    s.rtab64 = (double*)p; p += 8 * (size_t)NS_IDS * 4;
+    s.fit = (double*)p; p += 8 * Sp;
+    s.ser = (long long*)p; p += 8 * Sp;
+    s.st = (rl_ns_state*)p; p += (sizeof(rl_ns_state) + 15) & ~(size_t)15;
+    s.rtab = (float*)p; p += 4 * (size_t)NS_IDS * 8;
+    s.hkey = (int32_t*)p; p += 4 * NS_HASH;
+    s.id2gene = (int32_t*)p; p += 4 * NS_IDS;
+    s.alive_g = (int32_t*)p; p += 4 * NS_IDS;
+    s.cnt_g = (int32_t*)p; p += 4 * NS_IDS;
+    s.pg = (int32_t*)p; p += 4 * NS_IDS;
+    s.nbmask = (uint32_t*)p; p += 4 * Cw;
+    s.nbpre = (uint32_t*)p; p += 4 * Cw;
+    s.hid = p;
 }
 
 __device__ inline void ws_carve(WS& s, unsigned char* base, int H, int W) {
@@ -88,6 +132,7 @@ __device__ inline void ws_carve(WS& s, unsigned char* base, int H, int W) {
     s.flags = p; p += Cp;
     s.gene = p; p += Cp;
     s.action = (int8_t*)p;
+    s.alive_g = s.misc + M_ALIVE_G; s.cnt_g = s.misc + M_CNT_G; s.pg = s.misc + M_PG;
 }
 
 // toroidal neighbour: 0 up (i-1), 1 right (j+1), 2 down (i+1), 3 left (j-1) -- environment.py:601-623
@@ -169,8 +214,19 @@ __device__ __forceinline__ void init_tables(const WParams& P, WS& s) {
     for (int k = t; k < W + 6; k += WT) { int sj = k - 3; sj += sj < 0 ? W : 0; sj -= sj >= W ? W : 0; s.colmap[k] = sj; }
 }
 
+constexpr int M_NIDS = M_PRESENT;      // non-static: number of lineage ids in use (M_PRESENT is a static-families scratch word)
+constexpr int M_NLIN = M_ALIVE_G;      // non-static: distinct lineages in the final list (the per-gene words of misc are unused)
+constexpr int M_NNEW = M_ANY;          // non-static: newborn agents of this phase
+
+__device__ __forceinline__ uint32_t ns_hash(int gene) { return ((uint32_t)gene * 2654435761u) >> 22; }      // 10 bits = NS_HASH
+__device__ __forceinline__ int ns_lookup(const WS& s, int gene) {
+    uint32_t h = ns_hash(gene);
+    while (s.hkey[h] != gene) h = (h + 1) & (NS_HASH - 1);
+    return s.hid[h];
+}
+
 // load cell types + the agent list into the cell-indexed shared arrays
-template <bool DECAY>
+template <bool DECAY, bool NS>
 __device__ __forceinline__ int load_world(const WParams& P, WS& s, int w) {
     const int C = P.cfg.height * P.cfg.width;
     const uint8_t* tg = P.b.type + (size_t)w * C;
@@ -186,8 +242,48 @@ __device__ __forceinline__ int load_world(const WParams& P, WS& s, int w) {
     for (int k = threadIdx.x; k < M_WORDS; k += WT) s.misc[k] = 0;
     init_tables(P, s);
     const int n = min(P.b.n_agents[w], P.cfg.slot_cap);
-    __syncthreads();
     const int4* rg = reinterpret_cast<const int4*>(P.b.rec + (size_t)w * P.cfg.slot_cap);
+    if (NS) {
+        for (int k = threadIdx.x; k < NS_HASH; k += WT) s.hkey[k] = -1;
+        for (int k = threadIdx.x; k < NS_IDS; k += WT) { s.alive_g[k] = 0; s.cnt_g[k] = 0; s.id2gene[k] = -1; }
+        for (int k = threadIdx.x; k < (int)(sizeof(rl_ns_state) / 8); k += WT)
+            reinterpret_cast<long long*>(s.st)[k] = reinterpret_cast<const long long*>(P.ns.state + w)[k];
+        __syncthreads();
+        for (int sl = threadIdx.x; sl < n; sl += WT) {     // phase 1: the distinct genes of the list
+            const int gene = rg[sl].z;
+            uint32_t h = ns_hash(gene);
+            for (;;) {
+                const int old = atomicCAS(&s.hkey[h], -1, gene);
+                if (old == -1 || old == gene) break;
+                h = (h + 1) & (NS_HASH - 1);
+            }
+        }
+        __syncthreads();
+        {                                                  // phase 2: ids by table position (deterministic)
+            constexpr int PER = NS_HASH / WT;
+            int cnt = 0;
+#pragma unroll
+            for (int k = 0; k < PER; ++k) cnt += s.hkey[threadIdx.x * PER + k] != -1;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane_id() >= o) incl += v; }
+            int* wsum = reinterpret_cast<int*>(s.rtab64);                // (scratch: the reward table is built later)
+            if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
+            __syncthreads();
+            int base = incl - cnt;
+            for (int k = 0; k < (int)(threadIdx.x >> 5); ++k) base += wsum[k];
+            for (int k = 0; k < PER; ++k) {
+                const int e = threadIdx.x * PER + k;
+                if (s.hkey[e] != -1) {
+                    if (base < NS_IDS) { s.hid[e] = (uint8_t)base; s.id2gene[base] = s.hkey[e]; }
+                    else { s.hid[e] = (uint8_t)(NS_IDS - 1); if (P.b.status) atomicOr(&P.b.status[w], 4); }
+                    ++base;
+                }
+            }
+            if (threadIdx.x == WT - 1) s.misc[M_NIDS] = min(base, NS_IDS);
+        }
+    }
+    __syncthreads();
     for (int sl = threadIdx.x; sl < n; sl += WT) {
         int4 v = ld_stream_i4(rg + sl);
         int c = v.x & 0xFFFF;
@@ -199,8 +295,12 @@ __device__ __forceinline__ int load_world(const WParams& P, WS& s, int w) {
             fl &= ~(RL_F_KILLED | RL_F_INTER_KILLED | RL_F_INTRA_KILLED);
         }
         s.health[c] = (int16_t)h; s.age[c] = (int16_t)age; s.maxage[c] = (int16_t)ma;
-        s.gene[c] = (uint8_t)v.z; s.flags[c] = (uint8_t)fl; s.action[c] = (int8_t)act;
+        s.gene[c] = NS ? (uint8_t)ns_lookup(s, v.z) : (uint8_t)v.z; s.flags[c] = (uint8_t)fl; s.action[c] = (int8_t)act;
         s.aslot[c] = (uint16_t)sl; s.cellof[sl] = (uint16_t)c;
+        if (NS) {
+            s.fit[sl] = P.ns.fitness[(size_t)w * P.cfg.slot_cap + sl];
+            s.ser[sl] = P.ns.serial[(size_t)w * P.cfg.slot_cap + sl];
+        }
     }
     __syncthreads();
     return n;
@@ -218,8 +318,8 @@ __device__ __forceinline__ float hratio(int h) { return __fdiv_rn((float)h, 200.
 // grid (what Grid.fov's np.concatenate builds, grid.py:99-115), so a window element is one shared-memory load at
 // base(i,j) + constant(lane): each lane owns row elements e = lane + 32k (k < 5) of the 160-float row and
 // the warp writes the row as five fully coalesced, 128-byte aligned stores straight to HBM.
-template <bool STEP>
-__device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t* ft, float* obs_out) {
+template <bool STEP, bool NS>
+__device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t* ft, float* obs_out, int n_prev) {
     const int H = P.cfg.height, W = P.cfg.width, C = H * W, Cw = (C + 31) / 32;
     const int S = P.cfg.slot_cap, ld = P.cfg.obs_ld, G = P.cfg.n_genes;
     const int PW = W + 6, PADN = (((H + 6) * PW) + 3) & ~3;
@@ -232,19 +332,43 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
         uint8_t t = in ? ft[c] : (uint8_t)0;
         unsigned m = __ballot_sync(0xffffffffu, in && t == RL_AGENT);
         if (lane == 0) s.amask[ch] = m;
+        if (NS) {                                          // newborn = no slot in the previous list: its serial is handed out below
+            const unsigned nb = __ballot_sync(0xffffffffu, in && t == RL_AGENT && s.aslot[s.src[c]] == RL_NONE16);
+            if (lane == 0) s.nbmask[ch] = nb;
+        }
         if ((C & 3) != 0 && in) tg[c] = t;
     }
     if ((C & 3) == 0)
         for (int q = threadIdx.x; q < C / 4; q += WT) reinterpret_cast<uint32_t*>(tg)[q] = reinterpret_cast<const uint32_t*>(ft)[q];
-    if (STEP && threadIdx.x < P.cfg.n_genes) {           // _get_rewards (environment.py:291-311) by (gene, dead, killed)
-        const int g = threadIdx.x, alive_ = s.misc[M_ALIVE], kin = max(0, s.misc[M_ALIVE_G + g] - 1);
-        const double ra = alive_ == 1 ? 0.0 : (double)kin / (double)max(alive_, 1), rd = (double)(kin - alive_);
-        const double bonus = P.cfg.incentivize_killing ? 0.2 : 0.0;
-        const double r4[4] = {ra, ra + bonus, rd, rd + bonus};
+    const int n_tab = NS ? s.misc[M_NIDS] : P.cfg.n_genes;
+    if (STEP) {                                          // _get_rewards (environment.py:291-311) by (gene, dead, killed)
+        for (int g = threadIdx.x; g < n_tab; g += WT) {
+            const int alive_ = s.misc[M_ALIVE], kin = max(0, s.alive_g[g] - 1);
+            const double ra = alive_ == 1 ? 0.0 : (double)kin / (double)max(alive_, 1), rd = (double)(kin - alive_);
+            const double bonus = P.cfg.incentivize_killing ? 0.2 : 0.0;
+            const double r4[4] = {ra, ra + bonus, rd, rd + bonus};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { s.rtab[g * 8 + k] = (float)r4[k]; s.rtab[g * 8 + 4 + k] = (float)(r4[k] / 100.0); }
+            for (int k = 0; k < 4; ++k) {
+                s.rtab[g * 8 + k] = (float)r4[k]; s.rtab[g * 8 + 4 + k] = (float)(r4[k] / 100.0);
+                if (NS) s.rtab64[g * 4 + k] = r4[k];
+            }
+        }
     }
     __syncthreads();
+    if (STEP && NS) {
+        // Agent.fitness += reward for every agent of the _act list, vanished ones included (entities.py:187-192); best_agents
+        // holds live objects, so an entry that is one of these agents sees the new fitness (environment.py:149,728-739)
+        for (int sl = threadIdx.x; sl < n_prev; sl += WT) {
+            const int c0 = s.cellof[sl];
+            const unsigned fl = s.flags[c0];
+            const double f = s.fit[sl] + s.rtab64[s.gene[c0] * 4 + ((fl & RL_F_DEAD) ? 2 : 0) + ((fl & RL_F_KILLED) ? 1 : 0)];
+            s.fit[sl] = f;
+            const long long id = s.ser[sl];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) if (s.st->best[k].serial == id) s.st->best[k].fitness = f;
+        }
+        __syncthreads();
+    }
     if (warp == 0) {
         const int wpl = (Cw + 31) / 32;
         const int w0 = lane * wpl, w1 = min(Cw, w0 + wpl);
@@ -259,7 +383,20 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
         int run = incl - cnt;
         for (int wd = w0; wd < w1; ++wd) { s.wpre[wd] = run; run += __popc(s.amask[wd]); }
         if (lane == 31) s.misc[M_NB] = incl;
-        for (int g = lane; g < RL_MAX_GENES; g += 32) s.misc[M_CNT_G + g] = 0;
+        if (!NS) for (int g = lane; g < RL_MAX_GENES; g += 32) s.cnt_g[g] = 0;
+        if (NS) {                                          // ranks of the newborns in row-major order + the serials they take
+            int cnb = 0;
+            for (int wd = w0; wd < w1; ++wd) cnb += __popc(s.nbmask[wd]);
+            int inb = cnb;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, inb, o);
+                if (lane >= o) inb += v;
+            }
+            int rnb = inb - cnb;
+            for (int wd = w0; wd < w1; ++wd) { s.nbpre[wd] = rnb; rnb += __popc(s.nbmask[wd]); }
+            if (lane == 31) s.misc[M_NNEW] = inb;
+        }
     }
     __syncthreads();
     const int nB = s.misc[M_NB];
@@ -270,13 +407,21 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
         const int sc = s.src[c];
         const int h = s.health[sc], g = s.gene[sc];
         const unsigned fl = s.flags[sc] & 0x3Fu;
-        atomicAdd(&s.misc[M_CNT_G + (g & (RL_MAX_GENES - 1))], 1);
+        atomicAdd(&s.cnt_g[NS ? g : (g & (RL_MAX_GENES - 1))], 1);
         if (slot < S) {
             s.cellof[slot] = (uint16_t)c;
             int4 v;
             v.x = (c & 0xFFFF) | ((int)(uint16_t)(int16_t)h << 16);
             v.y = ((int)(uint16_t)s.age[sc]) | ((int)(uint16_t)s.maxage[sc] << 16);
-            v.z = g;
+            v.z = NS ? s.id2gene[g] : g;
+            if (NS) {
+                const unsigned old = s.aslot[sc];
+                double f = 0.0; long long id;
+                if (old != RL_NONE16) { f = s.fit[old]; id = s.ser[old]; }
+                else id = s.st->next_serial + s.nbpre[c >> 5] + __popc(s.nbmask[c >> 5] & ((1u << (c & 31)) - 1u));
+                P.ns.fitness[(size_t)w * S + slot] = f;
+                P.ns.serial[(size_t)w * S + slot] = id;
+            }
             const unsigned prev = STEP ? (unsigned)s.aslot[sc] : (unsigned)slot;
             v.w = (int)(fl | (((unsigned)(uint8_t)s.action[sc]) << 8) | (prev << 16));
             reinterpret_cast<int4*>(rg)[slot] = v;
@@ -313,11 +458,12 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
         }
     }
     __syncthreads();
-    if (threadIdx.x < G) {
-        int cg = s.misc[M_CNT_G + threadIdx.x];
+    for (int g = threadIdx.x; g < (NS ? s.misc[M_NIDS] : G); g += WT) {
+        int cg = s.cnt_g[g];
         // :357 -- float32(cg / nB); for counts <= 4096 the correctly rounded f32 quotient equals the double-rounded one
-        reinterpret_cast<float*>(s.misc)[M_PG + threadIdx.x] = nB <= 4096 ? __fdiv_rn((float)cg, (float)nB) : (float)((double)cg / (double)nB);
-        if (P.b.gene_count) P.b.gene_count[(size_t)w * G + threadIdx.x] = cg;
+        reinterpret_cast<float*>(s.pg)[g] = nB <= 4096 ? __fdiv_rn((float)cg, (float)nB) : (float)((double)cg / (double)nB);
+        if (!NS && P.b.gene_count) P.b.gene_count[(size_t)w * G + g] = cg;
+        if (NS && cg > 0) atomicAdd(&s.misc[M_NLIN], 1);
     }
     if (threadIdx.x == RL_MAX_GENES) {
         reinterpret_cast<float*>(s.misc)[M_PALL] = (nB <= 4096 && P.cfg.max_agents <= 4096)                     // :358
@@ -326,6 +472,15 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
         if (nB > S && P.b.status) atomicOr(&P.b.status[w], 1);
     }
     __syncthreads();
+    if (NS) {                                              // hand the world's non-static state back
+        if (threadIdx.x == 0) {
+            s.st->next_serial += s.misc[M_NNEW];
+            if (P.ns.n_lineages) P.ns.n_lineages[w] = s.misc[M_NLIN];
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < (int)(sizeof(rl_ns_state) / 8); k += WT)
+            reinterpret_cast<long long*>(P.ns.state + w)[k] = reinterpret_cast<const long long*>(s.st)[k];
+    }
     if (STEP && P.trace && blockIdx.x == 77 && threadIdx.x == 0) P.trace[6] = clock64();
 
     // ---- observation rows: one warp per agent ----
@@ -359,7 +514,7 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
             float4 lo, hi;
             lo.x = hratio(s.health[sc]);                                        // :365
             lo.y = (fl & RL_F_REPRODUCED) ? 1.f : 0.f;                           // :359
-            lo.z = reinterpret_cast<const float*>(s.misc)[M_PG + g];            // :357
+            lo.z = reinterpret_cast<const float*>(s.pg)[g];                     // :357
             lo.w = pall;                                                         // :358
             hi.x = (fl & RL_F_KILLED) ? 1.f : 0.f;                               // :369
             hi.y = (fl & RL_F_ATE_SUPER) ? 1.f : -1.f;                           // :370
@@ -402,17 +557,19 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
 // =====================================================================================================
 // Environment.step -- environment.py:160-186
 // =====================================================================================================
-__global__ void __launch_bounds__(WT, RL_WORLD_MINB) k_world_step(const WParams P) {
+template <bool NS>
+__global__ void __launch_bounds__(WT, NS ? 1 : RL_WORLD_MINB) k_world_step(const WParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int w = blockIdx.x;
     const int H = P.cfg.height, W = P.cfg.width, C = H * W, Cw = (C + 31) / 32;
     WS s; ws_carve(s, smem, P.cfg.height, P.cfg.width);
+    if (NS) ws_carve_ns(s, smem, P.cfg.height, P.cfg.width, P.cfg.slot_cap);
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
 
 #define WSTAMP(k) do { if (P.trace && blockIdx.x == 77 && threadIdx.x == 0) P.trace[k] = clock64(); } while (0)
     WSTAMP(0);
-    const int n = load_world<true>(P, s, w);
+    const int n = load_world<true, NS>(P, s, w);
     WSTAMP(1);
 
     // ---- _attack (environment.py:652-699) in closed form + _prepare_movement (:591-625) ----
@@ -510,7 +667,7 @@ __global__ void __launch_bounds__(WT, RL_WORLD_MINB) k_world_step(const WParams 
     for (int sl = threadIdx.x; sl < n; sl += WT) {
         const int c = s.cellof[sl];
         if (s.health[c] <= 0 || s.age[c] == s.maxage[c]) s.flags[c] |= RL_F_DEAD;
-        else { atomicAdd(&s.misc[M_ALIVE], 1); atomicAdd(&s.misc[M_ALIVE_G + s.gene[c]], 1); }
+        else { atomicAdd(&s.misc[M_ALIVE], 1); atomicAdd(&s.alive_g[s.gene[c]], 1); }
     }
     __syncthreads();
 
@@ -558,22 +715,54 @@ __global__ void __launch_bounds__(WT, RL_WORLD_MINB) k_world_step(const WParams 
     __syncthreads();
     WSTAMP(5);
     if (P.dbg & 4) { if (threadIdx.x < C) P.b.type[(size_t)w * C + threadIdx.x] = s.ntype[threadIdx.x]; return; }
-    finish_and_observe<true>(P, s, w, s.ntype, P.b.obs_prime);
+    finish_and_observe<true, NS>(P, s, w, s.ntype, P.b.obs_prime, n);
     WSTAMP(9);
 }
 
 // =====================================================================================================
 // Environment.update_env -- environment.py:188-215 (static families)
 // =====================================================================================================
-__global__ void __launch_bounds__(WT, RL_WORLD_MINB) k_world_update(const WParams P) {
+template <bool NS>
+__global__ void __launch_bounds__(WT, NS ? 1 : RL_WORLD_MINB) k_world_update(const WParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int w = blockIdx.x;
     const int C = P.cfg.height * P.cfg.width, Cw = (C + 31) / 32, G = P.cfg.n_genes;
     WS s; ws_carve(s, smem, P.cfg.height, P.cfg.width);
+    if (NS) ws_carve_ns(s, smem, P.cfg.height, P.cfg.width, P.cfg.slot_cap);
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
 
-    const int n_list = load_world<false>(P, s, w);   // :210 (frozen for the whole phase)
+    const int n_list = load_world<false, NS>(P, s, w);   // :210 (frozen for the whole phase)
+
+    if (NS && warp == 0) {
+        // _update_best_agents (environment.py:728-739): the listed agent with the highest fitness (np.argmax: first maximum
+        // in list order) replaces the best-table entry with the lowest fitness (np.argmin: first minimum) if it is fitter
+        // and not already in the table (object identity = serial)
+        double bv = -1.0e300; int bi = 0x7fffffff;
+        for (int sl = lane; sl < n_list; sl += 32) { const double v = s.fit[sl]; if (v > bv) { bv = v; bi = sl; } }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) {
+            rl_ns_state* st = s.st;
+            if (n_list > 0) {
+                int mi = 0;
+                for (int k = 1; k < 10; ++k) if (st->best[k].fitness < st->best[mi].fitness) mi = k;
+                const long long id = s.ser[bi];
+                bool present = false;
+                for (int k = 0; k < 10; ++k) present |= st->best[k].serial == id;
+                if (!present && s.fit[bi] > st->best[mi].fitness) {
+                    st->best[mi].serial = id; st->best[mi].fitness = s.fit[bi];
+                    st->best[mi].brain = s.id2gene[s.gene[s.cellof[bi]]];
+                }
+            }
+            st->produced_gene = -1; st->produced_src_best = -1; st->produced_src_brain = 0;
+        }
+        __syncwarp();
+    }
 
     for (int ch = warp; ch < Cw; ch += WNW) {
         const int c = ch * 32 + lane;
@@ -585,7 +774,7 @@ __global__ void __launch_bounds__(WT, RL_WORLD_MINB) k_world_update(const WParam
         const unsigned me = __ballot_sync(0xffffffffu, t == RL_EMPTY);
         const unsigned ma = __ballot_sync(0xffffffffu, elig);
         if (lane == 0) { s.mask[ch] = me; s.amask[ch] = ma; }
-        if (ag) { atomicOr(&s.misc[M_PRESENT], 1 << s.gene[c]); s.src[c] = (uint16_t)c; }
+        if (ag) { if (!NS) atomicOr(&s.misc[M_PRESENT], 1 << s.gene[c]); s.src[c] = (uint16_t)c; }
     }
     __syncthreads();
     if (warp == 0 && n_list <= P.cfg.max_agents) {
@@ -617,7 +806,31 @@ __global__ void __launch_bounds__(WT, RL_WORLD_MINB) k_world_update(const WParam
             }
         }
         // _produce (:521-547)
-        if (rl_uniform(rl_draw(key, P.t, RL_SITE_PRODUCE_TRIAL, 0)) > 0.95) {
+        if (NS) {
+            // _produce, non-static (:541-547): gene = ++max_gene (before the placement can fail), brain = deep copy of a random
+            // best agent's brain -- the (new gene, source brain id) event is left in the state for the brain pool
+            if (rl_uniform(rl_draw(key, P.t, RL_SITE_PRODUCE_TRIAL, 0)) > 0.95) {
+                int id = 0;
+                if (lane == 0) {
+                    rl_ns_state* st = s.st;
+                    st->max_gene += 1;
+                    const int k = (int)rl_below(rl_draw(key, P.t, RL_SITE_PRODUCE_GENE, 0), 10u);
+                    st->produced_gene = st->max_gene; st->produced_src_best = k; st->produced_src_brain = st->best[k].brain;
+                }
+                const int cell = warp_place(s.mask, Cw, rl_draw(key, P.t, RL_SITE_BIRTH_PLACE, birth));
+                if (cell >= 0) {
+                    if (lane == 0) {
+                        id = s.misc[M_NIDS];
+                        if (id < NS_IDS) { s.id2gene[id] = s.st->max_gene; s.misc[M_NIDS] = id + 1; }
+                        else { id = NS_IDS - 1; if (P.b.status) atomicOr(&P.b.status[w], 4); }
+                    }
+                    id = __shfl_sync(0xffffffffu, id, 0);
+                    spawn_agent(s, cell, id, 200, 0);
+                    if (lane == 0) s.src[cell] = (uint16_t)cell;
+                    warp_mask_clear(s.mask, cell);
+                }
+            }
+        } else if (rl_uniform(rl_draw(key, P.t, RL_SITE_PRODUCE_TRIAL, 0)) > 0.95) {
             const uint32_t all = G >= 32 ? 0xffffffffu : ((1u << G) - 1u);
             uint32_t cand = all & ~(uint32_t)s.misc[M_PRESENT];
             if (!cand) cand = all;
@@ -636,23 +849,36 @@ __global__ void __launch_bounds__(WT, RL_WORLD_MINB) k_world_update(const WParam
     for (int c = threadIdx.x; c < C; c += WT)
         if (s.type[c] == RL_AGENT && (s.flags[c] & RL_F_DEAD)) s.type[c] = RL_FOOD;
     __syncthreads();
-    finish_and_observe<false>(P, s, w, s.type, P.b.obs_state);
+    finish_and_observe<false, NS>(P, s, w, s.type, P.b.obs_state, 0);
 }
 
 // =====================================================================================================
 // Environment.reset -- environment.py:133-158
 // =====================================================================================================
+template <bool NS>
 __global__ void __launch_bounds__(WT) k_world_reset(const WParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int w = blockIdx.x;
     const int C = P.cfg.height * P.cfg.width, Cw = (C + 31) / 32, G = P.cfg.n_genes;
     WS s; ws_carve(s, smem, P.cfg.height, P.cfg.width);
+    if (NS) ws_carve_ns(s, smem, P.cfg.height, P.cfg.width, P.cfg.slot_cap);
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
     for (int c = threadIdx.x; c < C; c += WT) { s.type[c] = RL_EMPTY; s.src[c] = (uint16_t)c; s.aslot[c] = RL_NONE16; }
     for (int k = threadIdx.x; k < M_WORDS; k += WT) s.misc[k] = 0;
     init_tables(P, s);
+    if (NS) {
+        // the first agents carry gene i = lineage id i; the ten initial best agents are deep copies of agent 0 (:149): serials
+        // -1..-10, fitness 0, private brain copies -1..-10; max_gene = len(brains) (:108)
+        for (int k = threadIdx.x; k < NS_IDS; k += WT) { s.cnt_g[k] = 0; s.alive_g[k] = 0; s.id2gene[k] = k < G ? k : -1; }
+        if (threadIdx.x == 0) {
+            rl_ns_state* st = s.st;
+            st->max_gene = G; st->produced_gene = -1; st->produced_src_best = -1; st->produced_src_brain = 0; st->next_serial = 0;
+            for (int k = 0; k < 10; ++k) { st->best[k].serial = -1 - k; st->best[k].fitness = 0.0; st->best[k].brain = -1 - k; st->best[k]._pad = 0; }
+        }
+    }
     __syncthreads();
+    if (NS && threadIdx.x == 0) s.misc[M_NIDS] = G;
     build_empty_mask(s.type, s.mask, C);
     __syncthreads();
     if (warp == 0) {
@@ -682,7 +908,7 @@ __global__ void __launch_bounds__(WT) k_world_reset(const WParams P) {
         if (cell >= 0) { if (lane == 0) s.type[cell] = RL_SUPER_FOOD; warp_mask_clear(s.mask, cell); }
     }
     __syncthreads();
-    finish_and_observe<false>(P, s, w, s.type, P.b.obs_state);
+    finish_and_observe<false, NS>(P, s, w, s.type, P.b.obs_state, 0);
 }
 
 // =====================================================================================================
@@ -695,7 +921,7 @@ __global__ void __launch_bounds__(WT, RL_WORLD_MINB) k_world_topup(const WParams
     WS s; ws_carve(s, smem, P.cfg.height, P.cfg.width);
     const int warp = threadIdx.x >> 5;
     const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
-    const int n = load_world<false>(P, s, w);
+    const int n = load_world<false, false>(P, s, w);
     for (int c = threadIdx.x; c < C; c += WT) s.src[c] = (uint16_t)c;
     build_empty_mask(s.type, s.mask, C);
     __syncthreads();
@@ -712,7 +938,7 @@ __global__ void __launch_bounds__(WT, RL_WORLD_MINB) k_world_topup(const WParams
         }
     }
     __syncthreads();
-    finish_and_observe<false>(P, s, w, s.type, P.b.obs_state);
+    finish_and_observe<false, false>(P, s, w, s.type, P.b.obs_state, 0);
 }
 
 __global__ void __launch_bounds__(WT) k_world_observe(const WParams P) {
@@ -720,15 +946,15 @@ __global__ void __launch_bounds__(WT) k_world_observe(const WParams P) {
     const int w = blockIdx.x;
     const int C = P.cfg.height * P.cfg.width;
     WS s; ws_carve(s, smem, P.cfg.height, P.cfg.width);
-    load_world<false>(P, s, w);
+    load_world<false, false>(P, s, w);
     for (int c = threadIdx.x; c < C; c += WT) s.src[c] = (uint16_t)c;
     __syncthreads();
-    finish_and_observe<false>(P, s, w, s.type, P.which ? P.b.obs_prime : P.b.obs_state);
+    finish_and_observe<false, false>(P, s, w, s.type, P.which ? P.b.obs_prime : P.b.obs_state, 0);
 }
 
-size_t g_world_smem_max = 0;
+size_t g_world_smem_max = 0, g_world_smem_max_ns = 0;
 
-int world_prepare(const rl_world_cfg* cfg, const rl_world_bufs* b, WParams& P, size_t& smem) {
+int world_prepare(const rl_world_cfg* cfg, const rl_world_bufs* b, WParams& P, size_t& smem, const rl_world_ns_bufs* ns = nullptr) {
     RL_ARG_CHECK(cfg && b);
     RL_ARG_CHECK(cfg->height >= 3 && cfg->width >= 3);          // World/grid.py:23-24
     RL_ARG_CHECK((int64_t)cfg->height * cfg->width <= 65535);
@@ -736,21 +962,39 @@ int world_prepare(const rl_world_cfg* cfg, const rl_world_bufs* b, WParams& P, s
     RL_ARG_CHECK(cfg->slot_cap > 0 && cfg->slot_cap <= cfg->height * cfg->width);
     RL_ARG_CHECK(cfg->obs_ld >= 160 && cfg->obs_ld % 32 == 0 && cfg->obs_ld <= 192);
     RL_ARG_CHECK(cfg->max_agents > 0);
-    if (!cfg->static_families) return rl_set_err(RL_ERR_UNSUPPORTED, "static_families=False is not implemented yet");
+    if (!cfg->static_families && !ns)
+        return rl_set_err(RL_ERR_UNSUPPORTED, "static_families=False goes through rl_world_reset_ns / rl_world_step_ns / rl_world_update_ns");
+    if (ns) {
+        RL_ARG_CHECK(!cfg->static_families && ns->fitness && ns->serial && ns->state);
+        P.ns = *ns;
+    } else {
+        P.ns.fitness = nullptr; P.ns.serial = nullptr; P.ns.state = nullptr; P.ns.n_lineages = nullptr;
+    }
     RL_ARG_CHECK(b->type && b->rec && b->n_agents && b->reward && b->obs_state && b->obs_prime);
     P.trace = nullptr; P.cfg = *cfg; P.b = *b; P.t = 0; P.target = 0; P.max_age = 50; P.which = 0;
     { const char* d = getenv("RL_WORLD_DEBUG"); P.dbg = d ? atoi(d) : 0; }
     P.magicW = (uint32_t)(0x100000000ull / (uint64_t)cfg->width) + 1u;
     smem = ws_bytes(cfg->height, cfg->width);
-    if (smem > 227 * 1024) return rl_set_err(RL_ERR_UNSUPPORTED, "world of %d cells needs %zu B shared memory", cfg->height * cfg->width, smem);
+    if (ns) smem = ((smem + 15) & ~(size_t)15) + ws_bytes_ns(cfg->height, cfg->width, cfg->slot_cap);
+    if (smem > 227 * 1024) return rl_set_err(RL_ERR_UNSUPPORTED, "world of %d cells (slot_cap %d) needs %zu B shared memory", cfg->height * cfg->width, cfg->slot_cap, smem);
+    if (ns) {
+        if (smem > g_world_smem_max_ns) {
+            const int v = (int)smem;
+            RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+            RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+            RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_reset<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+            g_world_smem_max_ns = smem;
+        }
+        return RL_OK;
+    }
     if (smem > g_world_smem_max) {
         const int v = (int)smem;
-        RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_step, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
-        RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_step, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_update, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_step<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_update<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_topup, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_update, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
-        RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_reset<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_topup, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_world_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
         g_world_smem_max = smem;
@@ -766,7 +1010,7 @@ int rl_world_reset(const rl_world_cfg* cfg, const rl_world_bufs* bufs, void* str
     WParams P; size_t smem;
     int rc = world_prepare(cfg, bufs, P, smem);
     if (rc) return rc;
-    k_world_reset<<<cfg->n_worlds, WT, smem, (cudaStream_t)stream>>>(P);
+    k_world_reset<false><<<cfg->n_worlds, WT, smem, (cudaStream_t)stream>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
     return RL_OK;
 }
@@ -782,7 +1026,7 @@ int rl_world_step(const rl_world_cfg* cfg, const rl_world_bufs* bufs, uint64_t t
         if (!trace_dev) RL_CUDA_CHECK(cudaMalloc(&trace_dev, 16 * sizeof(long long)));
         P.trace = trace_dev;
     }
-    k_world_step<<<cfg->n_worlds, WT, smem, (cudaStream_t)stream>>>(P);
+    k_world_step<false><<<cfg->n_worlds, WT, smem, (cudaStream_t)stream>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
     if (tracing) {
         long long h[16];
@@ -799,7 +1043,7 @@ int rl_world_update(const rl_world_cfg* cfg, const rl_world_bufs* bufs, uint64_t
     int rc = world_prepare(cfg, bufs, P, smem);
     if (rc) return rc;
     P.t = t;
-    k_world_update<<<cfg->n_worlds, WT, smem, (cudaStream_t)stream>>>(P);
+    k_world_update<false><<<cfg->n_worlds, WT, smem, (cudaStream_t)stream>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
     return RL_OK;
 }
@@ -822,6 +1066,38 @@ int rl_world_observe(const rl_world_cfg* cfg, const rl_world_bufs* bufs, int32_t
     if (rc) return rc;
     P.which = which;
     k_world_observe<<<cfg->n_worlds, WT, smem, (cudaStream_t)stream>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_world_reset_ns(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_world_ns_bufs* ns, void* stream) {
+    WParams P; size_t smem;
+    RL_ARG_CHECK(ns);
+    int rc = world_prepare(cfg, bufs, P, smem, ns);
+    if (rc) return rc;
+    k_world_reset<true><<<cfg->n_worlds, WT, smem, (cudaStream_t)stream>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_world_step_ns(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_world_ns_bufs* ns, uint64_t t, void* stream) {
+    WParams P; size_t smem;
+    RL_ARG_CHECK(ns);
+    int rc = world_prepare(cfg, bufs, P, smem, ns);
+    if (rc) return rc;
+    P.t = t;
+    k_world_step<true><<<cfg->n_worlds, WT, smem, (cudaStream_t)stream>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_world_update_ns(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_world_ns_bufs* ns, uint64_t t, void* stream) {
+    WParams P; size_t smem;
+    RL_ARG_CHECK(ns);
+    int rc = world_prepare(cfg, bufs, P, smem, ns);
+    if (rc) return rc;
+    P.t = t;
+    k_world_update<true><<<cfg->n_worlds, WT, smem, (cudaStream_t)stream>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
     return RL_OK;
 }

@@ -38,10 +38,11 @@ def test_struct_layouts_match_the_header():
     from reinlife_b200.World.vecworld import REC_DTYPE
     assert REC_DTYPE.itemsize == 16
     pairs = [("rl_world_cfg", _lib.WorldCfg, "world_id0"), ("rl_world_bufs", _lib.WorldBufs, "reward_div100"),
-             ("rl_rows_bufs", _lib.RowsBufs, "row_cap"), ("rl_replay_bufs", _lib.ReplayBufs, "prioritized"),
+             ("rl_rows_bufs", _lib.RowsBufs, "row_cap"), ("rl_replay_bufs", _lib.ReplayBufs, "obs_fp16"),
              ("rl_learn_bufs", _lib.LearnBufs, "lr"), ("rl_brain_act", _lib.BrainAct, "epsilon"),
              ("rl_brain_sched", _lib.BrainSched, "max_epi"), ("rl_ppo_bufs", _lib.PpoBufs, "eps_clip"),
-             ("rl_sumtree_bufs", _lib.SumTreeBufs, "p_new"),
+             ("rl_sumtree_bufs", _lib.SumTreeBufs, "p_new"), ("rl_ns_best", _lib.NsBest, "brain"),
+             ("rl_ns_state", _lib.NsState, "best"), ("rl_world_ns_bufs", _lib.WorldNsBufs, "n_lineages"),
              ("rl_agent_rec", None, "prev_slot")]
     body = "".join(f'printf("%s %zu %zu\\n", "{c}", sizeof({c}), offsetof({c}, {m}));' for c, _, m in pairs)
     src = f'#include <stdio.h>\n#include <stddef.h>\n#include "{os.path.join(ROOT, "include", "reinlife_b200.h")}"\nint main(void){{{body}return 0;}}\n'
