@@ -39,6 +39,18 @@ class _NetHandle:
         return list(self.state_dict().values())
 
 
+def _copy_tensors(dst, src):
+    """dst.<tensor attributes> <- src's, recursively through helper objects (ReplayRings / SumTrees / PpoData)."""
+    if dst is None or src is None:
+        return
+    for name, val in src.__dict__.items():
+        if isinstance(val, torch.Tensor):
+            getattr(dst, name).copy_(val)
+        elif hasattr(val, "__dict__") and not isinstance(val, (type, torch.device)) and hasattr(getattr(dst, name, None), "__dict__") \
+                and type(val).__module__.startswith("reinlife_b200"):
+            _copy_tensors(getattr(dst, name), val)
+
+
 class DeviceBrainBase(BasicBrain):
     KIND = None          # packing.DUELING / DQN / PPO
     RULE = None          # _lib.ACT_*
@@ -90,6 +102,43 @@ class DeviceBrainBase(BasicBrain):
             self.epsilon = float(eps)
         if hasattr(self, "n_epi"):
             self.n_epi = int(seen)
+
+    # ---- copy.deepcopy(brain) of the reference (World/environment.py:149,544) --------------------------------
+    def clone(self):
+        """Deep copy of this brain the way `copy.deepcopy` copies a reference brain: networks, optimizer state, replay
+        memory, schedule scalars -- device-to-device tensor copies.  The copy is an independent plugin-mode brain."""
+        import copy
+        from ..brains import DeviceBrain
+        new = copy.copy(self)                                   # hyper-parameters and schedule scalars (epsilon, n_epi, ...)
+        new._dev = new._replay = new._env = new._plugin_host = None
+        if hasattr(new, "memory"):
+            new.memory = None
+        src_sd = self._dev.state_dict() if self._dev is not None else self._host_sd
+        new._host_sd = {k: torch.as_tensor(v).clone() for k, v in src_sd.items()}
+        if self.HAS_TARGET:
+            tgt = self._dev.state_dict(target=True) if self._dev is not None else self._host_sd_target
+            new._host_sd_target = {k: torch.as_tensor(v).clone() for k, v in tgt.items()}
+        for name, val in list(self.__dict__.items()):
+            if isinstance(val, _NetHandle):
+                setattr(new, name, _NetHandle(new, target=val._target))
+        if self._dev is not None:
+            d = self._dev
+            new._dev = DeviceBrain(self.KIND, self._host_sd, d.device, lr=self._lr(), gamma=self._gamma(), batch=self._batch(),
+                                   has_target=self.HAS_TARGET)
+            for name in ("params", "target", "adam_m", "adam_v", "adam_step"):
+                if getattr(d, name) is not None:
+                    getattr(new._dev, name).copy_(getattr(d, name))
+            new._dev.wimg_stale = True
+        if self._plugin_host is not None:                       # the replay memory / data list / SumTree and the device schedule state
+            from ..plugin import PluginHost
+            new._plugin_host = PluginHost(new, device=self._plugin_host.env.device)
+            _copy_tensors(new._replay, self._replay)
+            if getattr(self, "memory", None) is not None:
+                _copy_tensors(new.memory, self.memory)
+            new._plugin_host.env._eps.copy_(self._plugin_host.env._eps)
+            new._plugin_host.env._seen.copy_(self._plugin_host.env._seen)
+            new._plugin_host.calls = self._plugin_host.calls
+        return new
 
     # ---- plugin surface for single observations (the reference's per-agent calls) ------------------
     def _plugin_learn(self, **kw):

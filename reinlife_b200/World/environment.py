@@ -48,6 +48,15 @@ class _GridView:
 
 
 class Environment:
+    def __new__(cls, *args, **kwargs):
+        # static_families=False (8th positional argument of the reference's constructor, environment.py:74-89) is the
+        # evolving-lineage mode: reinlife_b200.World.nonstatic.NonStaticEnvironment (device World + per-world brain pools)
+        static = kwargs.get("static_families", args[7] if len(args) > 7 else True)
+        if cls is Environment and not static:
+            from .nonstatic import NonStaticEnvironment
+            return NonStaticEnvironment(*args, **kwargs)
+        return super().__new__(cls)
+
     def __init__(self, width: int = 30, height: int = 30, brains=None, grid_size: int = 16, max_agents: int = 50,
                  update_interval: int = 500, print_results: bool = True, static_families: bool = True,
                  interactive_results: bool = False, google_colab: bool = False, training: bool = True,
@@ -66,8 +75,6 @@ class Environment:
         self.update_interval, self.print_results = update_interval, print_results
         if interactive_results:
             raise NotImplementedError("interactive matplotlib results are out of scope (SURVEY.md 2, #16)")
-        if not static_families:
-            raise NotImplementedError("static_families=False (per-lineage brain pool) is not implemented yet")
 
         self.dist = torch.distributed.is_available() and torch.distributed.is_initialized()
         self.rank = torch.distributed.get_rank() if self.dist else 0

@@ -60,8 +60,6 @@ def test_unimplemented_paths_fail_loudly():
     from reinlife_b200.Models import DQN
     with pytest.raises(ZeroDivisionError):
         rl.trainer([DQN()], n_episodes=1, save=False, n_worlds=2)           # DQN(max_epi=0) while training (DQN.py:69)
-    with pytest.raises(NotImplementedError):                                # per-lineage brain pools (a21) are not built
-        rl.Environment(brains=[DQN(training=False)], training=False, static_families=False, n_worlds=1)
     env = rl.Environment(brains=[DQN(training=False)], training=False, n_worlds=1)
     with pytest.raises(NotImplementedError):
         env.render()
