@@ -136,12 +136,8 @@ class NonStaticEnvironment:
     def act(self, n_epi=0):
         """for agent in env.agents: agent.get_action(n_epi)   (Helpers/trainer.py:88-89, World/entities.py:215-222)"""
         w = self.world
-        torch.cuda.synchronize(self.device)
-        n = w.n_agents.cpu().numpy()
-        rec = w.rec_host()
-        self._state = w.obs_state.cpu().numpy()
+        n, rec = self.snapshot_state()
         acts = np.zeros((self.n_worlds, w.S), np.int8)
-        self._probs = {}
         for wi in range(self.n_worlds):
             for s in range(int(n[wi])):
                 brain = self.pools[wi][int(rec[wi, s]["gene"])]
@@ -156,6 +152,14 @@ class NonStaticEnvironment:
                     a = brain.get_action(state, n_epi)
                 acts[wi, s] = a
         w.set_actions(acts)
+
+    def snapshot_state(self):
+        """Host copy of `agent.state` of every listed agent (the `state` of the transitions this step will produce)."""
+        w = self.world
+        torch.cuda.synchronize(self.device)
+        self._state = w.obs_state.cpu().numpy()
+        self._probs = {}
+        return w.n_agents.cpu().numpy(), w.rec_host()
 
     def step(self):
         self.world.step()

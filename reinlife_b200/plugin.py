@@ -14,6 +14,12 @@ import torch
 from . import _lib
 
 
+# test hooks (tests/test_nonstatic_gpu.py): callables taking the brain -- ring positions used instead of the sampler's,
+# and a callback after every train() event.  Module-level so that brains cloned mid-run are covered too.
+SAMPLE_OVERRIDE = None
+EVENT_HOOK = None
+
+
 class PluginHost:
     def __init__(self, brain, device=None):
         from .World.environment import Environment
@@ -75,6 +81,10 @@ class PluginHost:
         self._gate[_lib.ROWS_EVENT] = 1 if trigger else 0
         env._gate_base = self._gate.data_ptr()
         env._t_key = self.calls
+        if SAMPLE_OVERRIDE is not None:
+            env.sample_override = lambda _g, _k: SAMPLE_OVERRIDE(b)
+        if EVENT_HOOK is not None:
+            env.event_hook = lambda _g, _k: EVENT_HOOK(b)
         env._seq_event = (0, 0) if trigger else None
         env._learn_lists([0], tf, on, n_epi)
         env._seq_event = None

@@ -85,3 +85,69 @@ def test_non_static_checkpoint_layout(tmp_path, monkeypatch):
     assert len(files) == 10
     sd = torch.load(files[0])
     assert sd["fc.weight"].shape == (128, 153)
+
+
+def test_non_static_learning_run_matches_reference():
+    """260 steps of ONE reference world with static_families=False and learning on (tests/golden/ns_learn_golden.npz,
+    oracle/make_ns_learn_golden.py: 336 train() events, 15 _produce deep copies incl. replay memory and Adam state,
+    mutate_brain, best-agent bookkeeping) replayed through NonStaticEnvironment: the same lineage triggers every event,
+    per-event loss, and at the end every referenced brain's weights, target, Adam step count and ring fill."""
+    import json
+    import os
+    import reinlife_b200 as rl
+    from reinlife_b200 import plugin
+    from reinlife_b200.Models import PERD3QN
+    from test_seq_cpu import KEYS, assert_weights_close
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ns_learn_golden.npz"))
+    m = json.loads(bytes(z["meta"]).decode())
+    brains = []
+    for g in range(2):
+        b = PERD3QN(exploration=m["exploration"], train_freq=m["train_freq"], capacity=m["capacity"],
+                    soft_update_freq=m["soft_update_freq"], learning_rate=m["lr"], gamma=m["gamma"])
+        sd = {k: z[f"w0/{g}/{k}"] for k in KEYS}
+        b.eval_net.load_state_dict(sd); b.target_net.load_state_dict(sd)
+        brains.append(b)
+    env = rl.Environment(width=m["width"], height=m["height"], brains=brains, max_agents=m["max_agents"], print_results=False,
+                         static_families=False, training=False, n_worlds=1, seed=m["seed"], world_id0=m["world"])
+    env.training = True            # (training=False above only keeps the tracker out, like the minting run)
+    cur = {"e": 0, "n_epi": 0}
+    gene_of = lambda brain: next(g for g, b in env.pools[0].items() if b is brain)   # noqa: E731
+
+    def override(brain):
+        e = cur["e"]
+        assert int(z["ev_gene"][e]) == gene_of(brain) and int(z["ev_step"][e]) == cur["n_epi"], (e, gene_of(brain))
+        return z["ev_idx"][e]
+
+    def hook(brain):
+        e = cur["e"]
+        np.testing.assert_allclose(float(brain._dev.loss[0]), z["ev_loss"][e], rtol=2e-3, atol=1e-5, err_msg=f"event {e}")
+        cur["e"] += 1
+    plugin.SAMPLE_OVERRIDE, plugin.EVENT_HOOK = override, hook
+    try:
+        env.reset()
+        pos, produced = 0, []
+        for n_epi in range(m["steps"] + 1):
+            cur["n_epi"] = n_epi
+            n, _ = env.snapshot_state()
+            assert int(n[0]) == z["counts"][n_epi], n_epi
+            a = np.zeros((1, env.world.S), np.int8)
+            a[0, :n[0]] = z["actions"][pos:pos + n[0]]; pos += int(n[0])
+            env.world.set_actions(a)
+            env.step()
+            env.learn(n_epi)
+            mg = env.max_gene
+            env.tracker.update_interval = 10 ** 9
+            env.update_env(n_epi)
+            if env.max_gene > mg:
+                produced.append((n_epi, env.max_gene, env.world.ns_host()[0].produced_src_best))
+    finally:
+        plugin.SAMPLE_OVERRIDE = plugin.EVENT_HOOK = None
+    assert cur["e"] == m["n_events"] and env.max_gene == m["max_gene"]
+    assert produced == [tuple(int(x) for x in r) for r in z["produced"]]
+    for g, steps, ring_len, ring_pos in m["final"]:
+        b = env.pools[0][g]
+        assert (int(b._dev.adam_step), int(b._replay.len[0]), int(b._replay.pos[0])) == (steps, ring_len, ring_pos), g
+        got, tgt = b.eval_net.state_dict(), b.target_net.state_dict()
+        for k in KEYS:
+            assert_weights_close(got[k].numpy(), z[f"final/{g}/{k}"], f"final gene {g} {k}")
+            assert_weights_close(tgt[k].numpy(), z[f"final_target/{g}/{k}"], f"final target gene {g} {k}")
