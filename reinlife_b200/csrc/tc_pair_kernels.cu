@@ -28,7 +28,7 @@ using mlp::mbar_init; using mlp::mbar_wait; using mlp::fence_mbar_init; using ml
 constexpr int R = 64;                    // rows per event
 constexpr int PB = 128;                  // rows per pair
 constexpr int NEPI = 256;                // epilogue threads (warps 0-7)
-constexpr int NTH = NEPI + 64;           // + producer warp (8) + MMA issuer warp (9)
+constexpr int NTH = NEPI + 96;           // + producer warp (8) + two MMA issuer warps (9, 10)
 constexpr int NSP = 8;                   // weight-chunk ring slots of 8 KB
 constexpr int HCH = 4096;                // halves per weight chunk
 constexpr float H_SCALE = 256.0f;        // backward operands are scaled by 2^8 (exact), removed when gradients leave TMEM
@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSP; ++i) mbar_init(&full[i], 1);
-        for (int i = 0; i < NSTG; ++i) mbar_init(&sfree[i], 1);
-        mbar_init(done, 1); mbar_init(doneL1, 1); mbar_init(go, NEPI);
+        for (int i = 0; i < NSTG; ++i) mbar_init(&sfree[i], 2);     // both issuers commit
+        mbar_init(done, 2); mbar_init(doneL1, 2); mbar_init(go, NEPI);
         fence_mbar_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -187,15 +187,21 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 bulk_load(sStg + slot * HCH, (net ? P.wimg_e : P.wimg_t) + (size_t)ch * HCH, HCH * 2, &full[slot]);
             }
         }
-    } else if (warp == 9) {
-        // =================================== MMA issuer ===================================
-        // TMEM columns of the work area: L1 accumulators 128..255, L2 / dH2 0..255, heads 0..15, dWh 0..31, dH1 0..127,
-        // dW1 0..159 -- the L1 of the eval net runs under the target head epilogue, the next pair's target L1 under nothing
-        // that touches 128..255.
+    } else if (warp == 9 || warp == 10) {
+        // =================================== MMA issuers (two warps) ===================================
+        // A tcgen05.mma costs its issuing thread 100-300 cycles whatever its size and two threads issue concurrently at ~1.4x
+        // the rate (scripts/tc_mma_bench.py), so every stage is split between two issuers by OUTPUT COLUMNS: issuer r takes
+        // the N-half r of L1 / L2 / dH1 / dW2 / dW1 (same A, rows [r N/2, (r+1) N/2) of B, accumulator columns shifted by
+        // r N/2 -- no extra TMEM, nothing for the epilogue to add), the M-half r of dWh and the dH2 half r; the heads
+        // (N = 16) are split over K into two accumulators the epilogue adds.  Both walk the same go sequence and chunk
+        // stream; ring groups, `done` and `doneL1` complete on two commits.
+        // TMEM columns of the work area: L1 accumulators 128..255, L2 / dH2 0..255, heads 0..31, dWh 0..31, dH1 0..127,
+        // dW1 0..159 -- the L1 of the eval net runs under the target head epilogue.
         if (lane == 0) {
+            const uint32_t r = (uint32_t)(warp - 9);
             uint32_t consumed = 0, go_no = 0, stage = 0;
             int itr_n = 0, itr_p = -1;
-            auto istamp = [&]() { if (P.trace && blockIdx.x == 0 && itr_p == 3 && itr_n < 40) P.trace[64 + itr_n++] = clock64(); };
+            auto istamp = [&]() { if (P.trace && blockIdx.x == 0 && r == 0 && itr_p == 3 && itr_n < 40) P.trace[64 + itr_n++] = clock64(); };
             auto wait_go = [&]() { mbar_wait(go, go_no & 1); ++go_no; fence_after(); istamp(); };
             auto chunk_wait = [&]() -> uint32_t {
                 const uint32_t slot = consumed % NSP;
@@ -205,39 +211,39 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 return smem_u32(sStg + slot * HCH);
             };
             auto stage_free = [&]() { istamp(); mma_commit(&sfree[stage % NSTG]); ++stage; };
-            // L1: D[128 b][128 k1] = X[128][160] W1[128][160]^T -- 5 chunks [128 n][32 k], 2 k-steps each
+            // L1: D[128 b][128 k1] = X[128][160] W1[128][160]^T -- 5 chunks [128 n][32 k], 2 k-steps each; issuer r: k1 in [64 r, +64)
             auto l1 = [&]() {
-                const uint32_t id = idesc_h(128, 128, 0, 0);
+                const uint32_t id = idesc_h(128, 64, 0, 0);
                 uint64_t a = dk(aX, 160);
 #pragma unroll 1
                 for (int c = 0; c < 5; ++c) {
-                    const uint64_t b = dk(chunk_wait(), 32);
-                    mma_h(T0 + 128, a, b, id, c != 0);
-                    mma_h(T0 + 128, a + 16u, b + 16u, id, 1u);
+                    const uint64_t b = dk(chunk_wait() + r * 4096u, 32);          // rows 64 r.. of the [128][32] chunk: 8 row groups x 512 B
+                    mma_h(T0 + 128 + 64 * r, a, b, id, c != 0);
+                    mma_h(T0 + 128 + 64 * r, a + 16u, b + 16u, id, 1u);
                     a += 32u;
                 }
                 stage_free();
                 mma_commit(doneL1);
             };
-            // L2: D[128 b][256 n2] = H1[128][128] W2[256][128]^T -- 8 chunks [256 n][16 k], one k-step each
+            // L2: D[128 b][256 n2] = H1[128][128] W2[256][128]^T -- 8 chunks [256 n][16 k]; issuer r: n2 in [128 r, +128)
             auto l2 = [&]() {
-                const uint32_t id = idesc_h(128, 256, 0, 0);
+                const uint32_t id = idesc_h(128, 128, 0, 0);
                 uint64_t a = dk(aH1, 128);
 #pragma unroll 1
                 for (int c = 0; c < 8; ++c) {
-                    mma_h(T0, a, dk(chunk_wait(), 16), id, c != 0);
+                    mma_h(T0 + 128 * r, a, dk(chunk_wait() + r * 4096u, 16), id, c != 0);   // rows 128 r..: 16 row groups x 256 B
                     a += 16u;
                     if (c == 3) stage_free();
                 }
                 stage_free();
                 mma_commit(done);
             };
-            // head: D[128 b][16] = H2[128][256] Wh[16][256]^T -- one chunk, 16 k-steps
+            // head: D[128 b][16] = H2[128][256] Wh[16][256]^T -- one chunk; issuer r: k-steps [8 r, +8) into columns 16 r..
             auto head = [&]() {
                 const uint32_t id = idesc_h(128, 16, 0, 0);
-                uint64_t a = dk(aH2, 256), b = dk(chunk_wait(), 256);
+                uint64_t a = dk(aH2, 256) + 128u * r, b = dk(chunk_wait(), 256) + 128u * r;
 #pragma unroll 1
-                for (int ks = 0; ks < 16; ++ks) { mma_h(T0, a, b, id, ks != 0); a += 16u; b += 16u; }
+                for (int ks = 0; ks < 8; ++ks) { mma_h(T0 + 16 * r, a, b, id, ks != 0); a += 16u; b += 16u; }
                 stage_free();
                 mma_commit(done);
             };
@@ -249,49 +255,46 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 wait_go(); l2();
                 wait_go(); head();
                 wait_go();
-                {   // dH2 half 0 (n2 < 128) -> columns 128..255: A = dOut [128][16], B = Wh^T chunk rows 0..127 [256 n2][16 j]
+                {   // issuer 0: dH2 half 0 (n2 < 128) -> columns 128..255: A = dOut [128][16], B = Wh^T chunk rows 0..127 [256 n2][16 j];
+                    // issuer r: dWh rows n2 in [128 r, +128): A = H2 read MN-major (M = n2 half), B = dOut read MN-major, K = 128 rows
                     const uint32_t wht = chunk_wait();
-                    mma_h(T0 + 128, dk(aD, 16), dk(wht, 16), idesc_h(128, 128, 0, 0), 0u);
-                    // dWh[n2][j] = sum_b H2[b][n2] dOut[b][j]: A = H2 read MN-major (M = n2 half), B = dOut read MN-major, K = 128 rows
+                    if (r == 0) mma_h(T0 + 128, dk(aD, 16), dk(wht, 16), idesc_h(128, 128, 0, 0), 0u);
                     const uint32_t id = idesc_h(128, 16, 1, 1);
+                    uint64_t a = dm(aH2 + r * 2048u, 256), b = dm(aD, 16);
 #pragma unroll 1
-                    for (int mh = 0; mh < 2; ++mh) {
-                        uint64_t a = dm(aH2 + mh * 2048u, 256), b = dm(aD, 16);
-#pragma unroll 1
-                        for (int ks = 0; ks < 8; ++ks) { mma_h(T0 + 16 * mh, a, b, id, ks != 0); a += 512u; b += 32u; }
-                    }
+                    for (int ks = 0; ks < 8; ++ks) { mma_h(T0 + 16 * r, a, b, id, ks != 0); a += 512u; b += 32u; }
                     mma_commit(done);
-                    wait_go();                                     // dWh drained: dH2 half 1 (n2 >= 128) -> columns 0..127
-                    mma_h(T0, dk(aD, 16), dk(wht + 4096u, 16), idesc_h(128, 128, 0, 0), 0u);
+                    wait_go();                                     // dWh drained: dH2 half 1 (n2 >= 128) -> columns 0..127, 64 each
+                    mma_h(T0 + 64 * r, dk(aD, 16), dk(wht + 4096u + r * 2048u, 16), idesc_h(128, 64, 0, 0), 0u);
                     stage_free();
                     mma_commit(done);
                 }
                 wait_go();
-                {   // dH1[128 b][128 k1] = dH2[128][256] W2^T[128 k1][256 n2]^T: 8 chunks [128][32], 2 k-steps each
-                    const uint32_t id = idesc_h(128, 128, 0, 0);
+                {   // dH1[128 b][128 k1] = dH2[128][256] W2^T[128 k1][256 n2]^T: 8 chunks [128][32], 2 k-steps each; issuer r: k1 in [64 r, +64)
+                    const uint32_t id = idesc_h(128, 64, 0, 0);
                     uint64_t a = dk(aH2, 256);
 #pragma unroll 1
                     for (int c = 0; c < 8; ++c) {
-                        const uint64_t b = dk(chunk_wait(), 32);
-                        mma_h(T0, a, b, id, c != 0);
-                        mma_h(T0, a + 16u, b + 16u, id, 1u);
+                        const uint64_t b = dk(chunk_wait() + r * 4096u, 32);
+                        mma_h(T0 + 64 * r, a, b, id, c != 0);
+                        mma_h(T0 + 64 * r, a + 16u, b + 16u, id, 1u);
                         a += 32u;
                         if (c == 3) stage_free();
                     }
                     stage_free();
-                    // dW2[k1][n2] += sum_b H1[b][k1] dH2[b][n2]: both images read MN-major, accumulator resident in TMEM
-                    const uint32_t id2 = idesc_h(128, 256, 1, 1);
-                    uint64_t a2 = dm(aH1, 128), b2 = dm(aH2, 256);
+                    // dW2[k1][n2] += sum_b H1[b][k1] dH2[b][n2]: both images read MN-major, accumulator resident in TMEM; issuer r: n2 half r
+                    const uint32_t id2 = idesc_h(128, 128, 1, 1);
+                    uint64_t a2 = dm(aH1, 128), b2 = dm(aH2 + r * 2048u, 256);
 #pragma unroll 1
-                    for (int ks = 0; ks < 8; ++ks) { mma_h(T_DW2, a2, b2, id2, (p != 0 || ks != 0) ? 1u : 0u); a2 += 256u; b2 += 512u; }
+                    for (int ks = 0; ks < 8; ++ks) { mma_h(T_DW2 + 128 * r, a2, b2, id2, (p != 0 || ks != 0) ? 1u : 0u); a2 += 256u; b2 += 512u; }
                     mma_commit(done);
                 }
                 wait_go();
-                {   // dW1[k1][x] = sum_b dH1[b][k1] X[b][x]: dH1 (in the H1 region) and X read MN-major, N = 160
-                    const uint32_t id = idesc_h(128, 160, 1, 1);
-                    uint64_t a = dm(aH1, 128), b = dm(aX, 160);
+                {   // dW1[k1][x] = sum_b dH1[b][k1] X[b][x]: dH1 (in the H1 region) and X read MN-major; issuer r: inputs x in [80 r, +80)
+                    const uint32_t id = idesc_h(128, 80, 1, 1);
+                    uint64_t a = dm(aH1, 128), b = dm(aX + r * 1280u, 160);
 #pragma unroll 1
-                    for (int ks = 0; ks < 8; ++ks) { mma_h(T0, a, b, id, ks != 0); a += 256u; b += 320u; }
+                    for (int ks = 0; ks < 8; ++ks) { mma_h(T0 + 80 * r, a, b, id, ks != 0); a += 256u; b += 320u; }
                     mma_commit(done);
                 }
             }
@@ -422,12 +425,13 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
         // ---- head epilogue (warps 0-3: one row each): out[0..8] of the row, mean of the advantages over the row's EVENT
         //      (PERD3QN.py:202: advantage.mean() over the whole [64, 8] tensor) ----
         auto head_epilogue = [&](const float* bias, float (&out)[9]) -> float {
-            float v[16];
+            float v[16], v2[16];
             tmem_ld16(T0 + t_lane, v);
+            tmem_ld16(T0 + t_lane + 16, v2);                        // second K half (issuer 1)
             tmem_wait_ld();
             float s = 0.f;
 #pragma unroll
-            for (int j = 0; j < 9; ++j) { out[j] = v[j] + bias[384 + j]; if (j < 8) s += out[j]; }
+            for (int j = 0; j < 9; ++j) { out[j] = (v[j] + v2[j]) + bias[384 + j]; if (j < 8) s += out[j]; }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0) red[q] = s;
