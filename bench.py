@@ -35,6 +35,10 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--worlds-per-gpu", type=int, default=4096)
     ap.add_argument("--capacity", type=int, default=10000)
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c5"],
+                    help="c3 = BASELINE.json configs[2]/[3] (the metric's configuration, default); c2 = configs[1] (256 worlds, DQN x1 "
+                         "inference, tester loop); c5 = configs[4] brain mix and grid with static_families=False at the scale the "
+                         "exact per-lineage brain pools serve (secondary lines, single GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the additional fixed-4096-worlds (strong scaling) measurement")
     ap.add_argument("--precision", default="fp16", choices=["tf32", "fp16", "fp32"],
@@ -442,10 +446,64 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_secondary(args):
+    """Secondary workloads (single GPU, device-timed with CUDA events, same metric): printed as ONE JSON line each."""
+    import torch
+    import reinlife_b200 as rl
+    from reinlife_b200.Models import DQN, PERD3QN, PPO
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: reinlife_b200 has no CPU fallback")
+    torch.manual_seed(0)
+    if args.workload == "c2":
+        import numpy as np
+        z = np.load(os.path.join(ROOT, "tests", "golden", "brain_golden.npz"))
+        b = DQN(training=False)
+        b.agent.load_state_dict({k[4:]: z[k] for k in z.files if k.startswith("dqn/")})      # pretrained/DQN/DQN/brain_gene_0.pt
+        env = rl.Environment(width=30, height=30, brains=[b], max_agents=100, print_results=False, training=False, n_worlds=256, seed=0)
+        env.reset(); env.top_up(100)
+        name = "BASELINE configs[1]: 256 worlds, 30x30, saturated to 100 agents, DQN x1 pretrained weights, inference only (tester loop body)"
+
+        def body(n_epi):
+            env.act(n_epi); env.step(); env.update_env(n_epi); env.top_up(100)
+        warm, steps = 20, max(args.steps, 100)
+    else:
+        brains = [PPO(), PERD3QN(exploration=20, capacity=1000)]
+        env = rl.Environment(width=60, height=60, brains=brains, max_agents=400, print_results=False, training=True,
+                             static_families=False, n_worlds=4, seed=0, slot_cap=1024, update_interval=10 ** 9)
+        env.reset()
+        name = ("BASELINE configs[4] brain mix and grid (60x60, max_agents=400, [PPO, PERD3QN], static_families=False) at REDUCED scale: "
+                "4 natural worlds, exact per-lineage brain pools driven per agent from the host (the batched pool for 1024 worlds is not built)")
+
+        def body(n_epi):
+            env.act(n_epi); env.step(); env.learn(n_epi); env.update_env(n_epi)
+        warm, steps = 150, max(args.steps, 50)
+    count = 0
+    n_epi = 1
+    for _ in range(warm):
+        body(n_epi); n_epi += 1
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cnt = torch.zeros(1, dtype=torch.int64, device=env.device)
+    e0.record()
+    for _ in range(steps):
+        cnt.add_(env.world.n_agents.sum())
+        body(n_epi); n_epi += 1
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    env.check_status()
+    print(json.dumps({"metric": METRIC, "value": int(cnt) / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warm,
+                      "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "fp32" if args.workload == "c5" else "fp32 (DQN forward on CUDA cores)", "data": "synthetic",
+                      "config": {"workload": name, "agents_per_world": int(cnt) / steps / env.n_worlds,
+                                 "max_gene": getattr(env, "max_gene", None)}, "secondary": True}))
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "c3":
+        run_secondary(args)
     else:
         run_b200(args)
 

@@ -51,6 +51,7 @@ class DeviceBrain:
                 if which in ("both", "target") and self.target is not None:
                     _lib.check(self.lib.rl_brain_build_wimg_h(C.c_int32(self.kind), C.c_void_p(self.target.data_ptr()),
                                                               C.c_void_p(self.wimg_th.data_ptr()), stream_ptr))
+                return                                      # fp16 mode: get_action and the events read the fp16 images only
             if which in ("both", "eval"):
                 _lib.check(self.lib.rl_brain_build_wimg(C.c_int32(self.kind), C.c_void_p(self.params.data_ptr()),
                                                         C.c_void_p(self.wimg_e.data_ptr()), stream_ptr))
