@@ -374,7 +374,9 @@ def run_b200(args):
     learn_kernel_name = {"fp16": "k_learn_dueling_p", "tf32": "k_learn_dueling_tc2", "fp32": "k_learn_dueling"}[args.precision]
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01_final.json"))).get(learn_kernel_name + "_bytes_per_launch")
+        # static number: dram__bytes_read + dram__bytes_write of ONE launch from the committed `ncu --set full` capture of this
+        # same command (profiles/ncu_full_r02_summary.md), not measured in this run
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json"))).get(learn_kernel_name + "_bytes_per_launch")
     except Exception:
         pass
     peaks = {}
@@ -407,7 +409,8 @@ def run_b200(args):
     for v in roof_k.values():
         v["frac"] = v["achieved"] / v["peak"]
     dominant = max(roof_k, key=lambda k: roof_k[k]["ms"] * roof_k[k].get("launches_per_step", 1))
-    roofline = dict(roof_k[dominant], kernel=dominant, traffic=traffic if dominant == learn_kernel_name else None, peak_source=peak_src,
+    roofline = dict(roof_k[dominant], kernel=dominant, traffic=traffic if dominant == learn_kernel_name else None,
+                    traffic_source="profiles/traffic_r02.json (static: one launch under ncu --set full, same command)", peak_source=peak_src,
                     step_share=roof_k[dominant]["ms"] * roof_k[dominant].get("launches_per_step", 1) / sum(phases.values()))
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(3, args.warmup),
