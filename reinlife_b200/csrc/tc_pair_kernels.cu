@@ -210,14 +210,25 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 ++consumed;
                 return smem_u32(sStg + slot * HCH);
             };
+            // all `n` chunks of a stage have landed (they are normally prefetched long before): the MMAs of the stage are then
+            // issued back to back -- a try_wait + fence + descriptor build between two MMAs costs the issuer more than the MMA
+            auto chunks_wait = [&](int n) -> uint32_t {
+                const uint32_t first = consumed;
+                for (int c = 0; c < n; ++c) { const uint32_t k = consumed + c; mbar_wait(&full[k % NSP], (k / NSP) & 1); }
+                fence_after();
+                consumed += n;
+                return first;
+            };
+            auto chunk_addr = [&](uint32_t k) -> uint32_t { return smem_u32(sStg) + (k % NSP) * (HCH * 2); };
             auto stage_free = [&]() { istamp(); mma_commit(&sfree[stage % NSTG]); ++stage; };
             // L1: D[128 b][128 k1] = X[128][160] W1[128][160]^T -- 5 chunks [128 n][32 k], 2 k-steps each; issuer r: k1 in [64 r, +64)
             auto l1 = [&]() {
                 const uint32_t id = idesc_h(128, 64, 0, 0);
                 uint64_t a = dk(aX, 160);
+                const uint32_t k0 = chunks_wait(5);
 #pragma unroll 1
                 for (int c = 0; c < 5; ++c) {
-                    const uint64_t b = dk(chunk_wait() + r * 4096u, 32);          // rows 64 r.. of the [128][32] chunk: 8 row groups x 512 B
+                    const uint64_t b = dk(chunk_addr(k0 + c) + r * 4096u, 32);    // rows 64 r.. of the [128][32] chunk: 8 row groups x 512 B
                     mma_h(T0 + 128 + 64 * r, a, b, id, c != 0);
                     mma_h(T0 + 128 + 64 * r, a + 16u, b + 16u, id, 1u);
                     a += 32u;
@@ -229,9 +240,10 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
             auto l2 = [&]() {
                 const uint32_t id = idesc_h(128, 128, 0, 0);
                 uint64_t a = dk(aH1, 128);
+                const uint32_t k0 = chunks_wait(8);
 #pragma unroll 1
                 for (int c = 0; c < 8; ++c) {
-                    mma_h(T0 + 128 * r, a, dk(chunk_wait() + r * 4096u, 16), id, c != 0);   // rows 128 r..: 16 row groups x 256 B
+                    mma_h(T0 + 128 * r, a, dk(chunk_addr(k0 + c) + r * 4096u, 16), id, c != 0);   // rows 128 r..: 16 row groups x 256 B
                     a += 16u;
                     if (c == 3) stage_free();
                 }
@@ -273,9 +285,10 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 {   // dH1[128 b][128 k1] = dH2[128][256] W2^T[128 k1][256 n2]^T: 8 chunks [128][32], 2 k-steps each; issuer r: k1 in [64 r, +64)
                     const uint32_t id = idesc_h(128, 64, 0, 0);
                     uint64_t a = dk(aH2, 256);
+                    const uint32_t k0 = chunks_wait(8);
 #pragma unroll 1
                     for (int c = 0; c < 8; ++c) {
-                        const uint64_t b = dk(chunk_wait() + r * 4096u, 32);
+                        const uint64_t b = dk(chunk_addr(k0 + c) + r * 4096u, 32);
                         mma_h(T0 + 64 * r, a, b, id, c != 0);
                         mma_h(T0 + 64 * r, a + 16u, b + 16u, id, 1u);
                         a += 32u;
