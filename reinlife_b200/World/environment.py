@@ -20,6 +20,23 @@ from .vecworld import VecWorld
 from .utils import Actions, EntityTypes
 
 
+def _nvtx(name):
+    """Decorator: an NVTX range around a phase when RL_NVTX is set (nsys / ncu --nvtx timelines)."""
+    def wrap(fn):
+        if os.environ.get("RL_NVTX") is None:
+            return fn
+
+        def inner(*a, **kw):
+            torch.cuda.nvtx.range_push(name)
+            try:
+                return fn(*a, **kw)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        inner.__doc__ = fn.__doc__
+        return inner
+    return wrap
+
+
 class AgentView:
     """Read-only host snapshot of one agent (the fields of World/entities.py:145-170 that live on the device)."""
     __slots__ = ("i", "j", "health", "max_health", "age", "max_age", "gene", "action", "killed", "inter_killed",
@@ -153,15 +170,18 @@ class Environment:
         self.kernel_events = None       # set to a list to collect (name, gene, start, end) CUDA events of the hot kernels
 
     # ------------------------------------------------------------------ reference phases
+    @_nvtx("reinlife.reset")
     def reset(self):
         self.world.reset()
         self.grid = _GridView(self)
         self.gpu_launches += 1
 
+    @_nvtx("reinlife.step")
     def step(self):
         self.world.step()
         self.gpu_launches += 1
 
+    @_nvtx("reinlife.update_env")
     def update_env(self, n_epi: int = 0):
         if self.training:                                  # environment.py:206-207
             self.tracker.update_results(None, n_epi)
@@ -169,6 +189,7 @@ class Environment:
         self.world.update()
         self.gpu_launches += 1
 
+    @_nvtx("reinlife.top_up")
     def top_up(self, target, max_age=50):
         """Benchmark-only saturated-world generator."""
         self.world.top_up(target, max_age)
@@ -182,6 +203,7 @@ class Environment:
         return save_brains(self)
 
     # ------------------------------------------------------------------ batched stand-ins for the per-agent loops
+    @_nvtx("reinlife.act")
     def act(self, n_epi: int = 0, q_out=None):
         """for agent in env.agents: agent.get_action(n_epi)   (Helpers/trainer.py:88-89, Helpers/tester.py:58-68)"""
         w = self.world
@@ -217,6 +239,7 @@ class Environment:
                                                      C.c_uint64(w.t + 1), C.c_void_p(q_out), w._stream()))
         self.gpu_launches += 4 + G
 
+    @_nvtx("reinlife.learn")
     def learn(self, n_epi: int = 0):
         """for agent in env.agents: agent.learn(n_epi=n_epi)   (Helpers/trainer.py:95-96), batched:
         all stores of the step, then every train() trigger of every world as one event against the same pre-step

@@ -240,14 +240,16 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
             auto l2 = [&]() {
                 const uint32_t id = idesc_h(128, 128, 0, 0);
                 uint64_t a = dk(aH1, 128);
-                const uint32_t k0 = chunks_wait(8);
 #pragma unroll 1
-                for (int c = 0; c < 8; ++c) {
-                    mma_h(T0 + 128 * r, a, dk(chunk_addr(k0 + c) + r * 4096u, 16), id, c != 0);   // rows 128 r..: 16 row groups x 256 B
-                    a += 16u;
-                    if (c == 3) stage_free();
+                for (int hf = 0; hf < 2; ++hf) {
+                    const uint32_t k0 = chunks_wait(4);
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        mma_h(T0 + 128 * r, a, dk(chunk_addr(k0 + c) + r * 4096u, 16), id, (hf | c) != 0);   // rows 128 r..: 16 row groups x 256 B
+                        a += 16u;
+                    }
+                    stage_free();
                 }
-                stage_free();
                 mma_commit(done);
             };
             // head: D[128 b][16] = H2[128][256] Wh[16][256]^T -- one chunk; issuer r: k-steps [8 r, +8) into columns 16 r..
@@ -282,24 +284,27 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                     mma_commit(done);
                 }
                 wait_go();
-                {   // dH1[128 b][128 k1] = dH2[128][256] W2^T[128 k1][256 n2]^T: 8 chunks [128][32], 2 k-steps each; issuer r: k1 in [64 r, +64)
-                    const uint32_t id = idesc_h(128, 64, 0, 0);
-                    uint64_t a = dk(aH2, 256);
-                    const uint32_t k0 = chunks_wait(8);
-#pragma unroll 1
-                    for (int c = 0; c < 8; ++c) {
-                        const uint64_t b = dk(chunk_addr(k0 + c) + r * 4096u, 32);
-                        mma_h(T0 + 64 * r, a, b, id, c != 0);
-                        mma_h(T0 + 64 * r, a + 16u, b + 16u, id, 1u);
-                        a += 32u;
-                        if (c == 3) stage_free();
-                    }
-                    stage_free();
-                    // dW2[k1][n2] += sum_b H1[b][k1] dH2[b][n2]: both images read MN-major, accumulator resident in TMEM; issuer r: n2 half r
+                {   // dW2[k1][n2] += sum_b H1[b][k1] dH2[b][n2] first (no weights: the last W2^T chunks get more time to land): both
+                    // images read MN-major, accumulator resident in TMEM; issuer r: n2 half r
                     const uint32_t id2 = idesc_h(128, 128, 1, 1);
                     uint64_t a2 = dm(aH1, 128), b2 = dm(aH2 + r * 2048u, 256);
 #pragma unroll 1
                     for (int ks = 0; ks < 8; ++ks) { mma_h(T_DW2 + 128 * r, a2, b2, id2, (p != 0 || ks != 0) ? 1u : 0u); a2 += 256u; b2 += 512u; }
+                    // dH1[128 b][128 k1] = dH2[128][256] W2^T[128 k1][256 n2]^T: 8 chunks [128][32], 2 k-steps each; issuer r: k1 in [64 r, +64)
+                    const uint32_t id = idesc_h(128, 64, 0, 0);
+                    uint64_t a = dk(aH2, 256);
+#pragma unroll 1
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const uint32_t k0 = chunks_wait(4);
+#pragma unroll 1
+                        for (int c = 0; c < 4; ++c) {
+                            const uint64_t b = dk(chunk_addr(k0 + c) + r * 4096u, 32);
+                            mma_h(T0 + 64 * r, a, b, id, (hf | c) != 0);
+                            mma_h(T0 + 64 * r, a + 16u, b + 16u, id, 1u);
+                            a += 32u;
+                        }
+                        stage_free();
+                    }
                     mma_commit(done);
                 }
                 wait_go();
