@@ -421,6 +421,18 @@ int rl_world_stats_scratch_doubles(const rl_world_cfg* cfg);   /* size of scratc
 /* Timing probe (scripts/tc_mma_bench.py): average cycles to issue / to complete `ksteps` back-to-back tcgen05.mma
  * kind::tf32 (K = 8 each) for operand layout `mode` (0 no-swizzle, 1 no-swizzle with padded chunk stride, 2 SWIZZLE_128B). */
 int rl_tc_mma_bench(int M, int N, int ksteps, int mode, int iters, long long* out_host);
+/* Timing probe (scripts/tc_issue_probe.py): cycles to issue / complete `nmma` back-to-back M = 128 tcgen05.mma kind::f16 of
+ * width N from `n_warps` warps; layout 0 K-major no-swizzle, 1 MN-major no-swizzle, 2 K-major SWIZZLE_128B; style 0 = issuing
+ * thread picked by `lane == 0` (descriptors in vector registers), style 1 = warp-uniform loop + elect.sync (uniform registers). */
+int rl_tc_issue_probe(int N, int nmma, int layout, int style, int n_warps, int iters, long long* out_host);
+/* Test hook: rl_tc_gemm_test_h with a swizzle layout type per operand (descriptor bits 61-63: 0 none, 2 SWIZZLE_128B) and, when
+ * a_kblk / b_kblk != 0, k-step addresses of the form (ks / 4) * kblk + (ks % 4) * kstep (four K = 16 steps per 128-byte atom). */
+int rl_tc_gemm_test_hx(const void* a_img, const void* b_img, float* d, int M, int N, int K, int a_halves, int b_halves,
+                       uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kstep, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep,
+                       int a_mn, int b_mn, uint32_t a_kblk, uint32_t b_kblk, int a_layout, int b_layout, void* stream);
+/* Test hook: TMA tile::gather4 of rows idx[0..127] of the fp16 tensor [n_rows][160] at `ring` into three [128 rows][128 B]
+ * SWIZZLE_128B K blocks; `out` receives the 48 KB shared-memory image (tests/test_tc_gpu.py pins the layout). */
+int rl_tma_gather_test(const void* ring, long long n_rows, const int32_t* idx, void* out, int box_rows);
 
 int rl_tc_gemm_test(const float* a_img, const float* b_img, float* d, int M, int N, int K, int a_mn, int b_mn, void* stream);
 /* Test hook: one-tile tcgen05 kind::f16 GEMM  D[M,N] = A * B^T  on fp16 operand images with caller-supplied descriptor

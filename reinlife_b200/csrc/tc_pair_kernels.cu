@@ -1,23 +1,37 @@
 // tc_pair_kernels.cu -- k_learn_dueling_p: the train() events of the dueling brains (PERD3QN.py:94-115, D3QN.py:97-116)
 // on the 5th-gen tensor cores, TWO events (2 x 64 rows) per CTA iteration in BATCH-MAJOR form.
 //
-// Why a second design next to tc_kernels.cu::k_learn_dueling_h.  tcgen05.mma costs its issuing thread ~100-230 cycles
-// whatever its N (scripts/tc_mma_bench.py), so an event processed alone (batch 64) is issue-bound: the transposed-output
-// form of k_learn_dueling_h reaches M = 128 but every MMA is N = 64, every operand needs a batch-major AND a
+// Why a second design next to tc_kernels.cu::k_learn_dueling_h.  An event processed alone (batch 64) is issue-bound: the
+// transposed-output form of k_learn_dueling_h reaches M = 128 but every MMA is N = 64, every operand needs a batch-major AND a
 // feature-major image (scalar scatter stores), and every stage is handed over once per 64 rows.  Here
-//   * a pair of events is one M = 128 tile: D[batch 128][features] = Act[128][K] * W[features][K]^T, N = 128 / 256 per MMA
-//     -- the same ~117 MMA instructions now cover two events;
+//   * a pair of events is one M = 128 tile: D[batch 128][features] = Act[128][K] * W[features][K]^T, N = 128 / 256 per MMA;
 //   * fp16 operands may be MN-major (scripts/tc_probe_h.py pins it): the weight-gradient GEMMs dW2 = H1^T dH2,
-//     dW1 = dH1^T X, dWh = H2^T dOut read the SAME batch-major images the forward wrote (core matrix = 8 rows x 16 B in
-//     both readings), so no transposed image exists any more: X, H1, H2, dOut only, dH2 / dH1 written in place;
+//     dW1 = dH1^T X, dWh = H2^T dOut read the SAME batch-major images the forward wrote, so no transposed image exists:
+//     X, H1, H2, dOut only, dH2 / dH1 written in place;
 //   * an epilogue thread owns one batch ROW: activations leave as 16-byte vector stores, the dueling combine / TD
 //     error / dOut of a row are thread-local, bias gradients are warp reduce-scatters (db2, dbh) or ride a GEMM for free
-//     (db1 = column 159 of dW1, whose X column is set to 1 -- the matching W1 rows are structural zeros);
+//     (db1 = column 159 of dW1, whose X column is 1 -- the matching W1 rows are structural zeros);
 //   * dW2 stays resident in TMEM across all pairs of the CTA, dW1 is flushed once per pair with 16-byte vector reds.
+// Round-2 rework (what scripts/tc_issue_probe.py, scripts/tc_probe_sw128.py and the RL_TC_TRACE stamps showed):
+//   * ONE issuer warp in warp-uniform control flow + elect.sync: descriptors stay in uniform registers and UTCHMMA issues
+//     directly (48-69 cycles per N = 64-128 MMA, the math time at N = 256).  Picking the issuing thread with `lane == 0` makes
+//     ptxas wrap every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (92 cycles per MMA whatever its N), and two such
+//     issuers only shared the tensor pipe;
+//   * the sampled replay rows are gathered by the TMA (cp.async.bulk.tensor tile::gather4, four ring rows per instruction)
+//     straight into SWIZZLE_128B operand images: 128 rows x 160 halves = three [128][128 B] K blocks.  The same image is the
+//     K-major A operand of L1 and the MN-major B operand of dW1 (the XOR pattern is the same in both readings).  The LSU
+//     gather it replaces (2560 16-byte loads per image, 8 rows per quarter-warp) took 3-6 k cycles to drain and stalled the
+//     MMA stages it was meant to hide behind (tL2 6.5 k -> 2.2 k cycles, dH1 8.3 k -> 3.3 k without it);
+//   * the target rows X' of the NEXT pair land in the H2 region (dead once dW2 / dH1 have completed), the eval rows X in the X
+//     region (dead once dW1 has completed): both gathers are off the epilogue's critical path and need no registers.
+// float32 rings (rl_replay_bufs.obs_fp16 = 0) cannot be gathered by the TMA (it does not convert): they keep a register gather
+// that writes the same swizzled images (template parameter TMA = false).
 // Same contract, outputs and tolerance as rl_brain_learn_h (tests/test_scale_gpu.py, tests/test_tc_gpu.py).
 #include <stdlib.h>
+#include <string.h>
 #include <cuda_fp16.h>
 #include "tc_tile.cuh"
+#include "tma_util.cuh"
 #include "models.cuh"
 
 namespace {
@@ -28,20 +42,22 @@ using mlp::mbar_init; using mlp::mbar_wait; using mlp::fence_mbar_init; using ml
 constexpr int R = 64;                    // rows per event
 constexpr int PB = 128;                  // rows per pair
 constexpr int NEPI = 256;                // epilogue threads (warps 0-7)
-constexpr int NTH = NEPI + 96;           // + producer warp (8) + two MMA issuer warps (9, 10)
+constexpr int NTH = NEPI + 96;           // + weight producer (warp 8) + MMA issuer (warp 9) + row gatherer (warp 10)
 constexpr int NSP = 8;                   // weight-chunk ring slots of 8 KB
 constexpr int HCH = 4096;                // halves per weight chunk
 constexpr float H_SCALE = 256.0f;        // backward operands are scaled by 2^8 (exact), removed when gradients leave TMEM
+constexpr int XBLK = PB * 128;           // bytes of one SWIZZLE_128B K block: 128 rows x 64 halves
+constexpr int XIMG = 3 * XBLK;           // 160 halves = 2.5 blocks; the upper half of block 2 is never read
 
 // weight image chunk ids (tc_kernels.cu::k_build_wimg_dueling_h)
 constexpr int WI_W1 = 0, WI_W2K = 5, WI_WH = 13, WI_WHT = 14, WI_W2T = 15;
 constexpr int SCHED_P = 37;              // chunks per pair: t W1[5] W2K[8] WH | e W1[5] W2K[8] WH WHT W2T[8]
 
-// ---- shared memory (bytes) ----
-constexpr int PO_X = 0;                                   // X' / X [128][160] halves
-constexpr int PO_H1 = PO_X + PB * 160 * 2;                // H1 -> dH1 [128][128]
-constexpr int PO_H2 = PO_H1 + PB * 128 * 2;               // H2 -> dH2 [128][256]
-constexpr int PO_STG = PO_H2 + PB * 256 * 2;              // weight ring
+// ---- shared memory (bytes, from a 1024-byte aligned base) ----
+constexpr int PO_X = 0;                                   // X (eval rows), SWIZZLE_128B
+constexpr int PO_H2 = PO_X + XIMG;                        // H2 -> dH2 [128][256] no swizzle; between pairs: X' (target rows), SWIZZLE_128B
+constexpr int PO_H1 = PO_H2 + PB * 256 * 2;               // H1 -> dH1 [128][128]
+constexpr int PO_STG = PO_H1 + PB * 128 * 2;              // weight ring
 constexpr int PO_DOUT = PO_STG + NSP * HCH * 2;           // dOut [128][16] halves
 constexpr int PO_BIAS = PO_DOUT + PB * 16 * 2;            // b1[128] b2[256] bh[16] x {target, eval} floats
 constexpr int PO_RED = PO_BIAS + 4 * 800;                 // reduction scratch floats [64]
@@ -49,22 +65,38 @@ constexpr int PO_META = PO_RED + 4 * 64;                  // [2] x { idx[128] ac
 constexpr int PO_RING = PO_META + 2 * 4 * 4 * PB;         // [2][2] ring base (elements) per buffer / event, 64-bit
 constexpr int PO_BARS = PO_RING + 2 * 2 * 8;
 constexpr int NSTG = 11;                 // ring release groups per pair: tL1 tL2a tL2b thead eL1 eL2a eL2b ehead dH2 dH1a dH1b
-constexpr size_t PAIR_SMEM = PO_BARS + 8 * (NSP + NSTG + 3) + 16;
-static_assert(PAIR_SMEM <= 227 * 1024 && PO_BARS % 8 == 0 && PO_RING % 8 == 0, "shared memory budget");
+constexpr int NBAR = NSP + NSTG + 8;     // + done doneL1 go xfull xpfull h2free xfree metaready
+constexpr size_t PAIR_SMEM = PO_BARS + 8 * NBAR + 16 + 1024;     // + alignment slack
+static_assert(PAIR_SMEM <= 227 * 1024 && PO_BARS % 8 == 0 && PO_RING % 8 == 0 && PO_H2 % 1024 == 0, "shared memory budget");
 
 // interleaved no-swizzle fp16 image of width K: 8 rows x 16 bytes core matrices
 __device__ __forceinline__ int himg(int r, int c, int K) { return (r >> 3) * (K * 8) + (c >> 3) * 64 + (r & 7) * 8 + (c & 7); }
-// K-major reading (rows = M / N index): LBO = next 8 k (128 B), SBO = next 8 rows (K * 16 B); one K = 16 step = +256 B
+// byte offset of 16-byte unit `u` (8 halves) of row r in a SWIZZLE_128B image of [128][64-half] K blocks
+__device__ __forceinline__ int ximg(int r, int u) { return (u >> 3) * XBLK + r * 128 + (((u & 7) ^ (r & 7)) << 4); }
+// K-major no-swizzle reading (rows = M / N index): LBO = next 8 k (128 B), SBO = next 8 rows (K * 16 B); one K = 16 step = +256 B
 __device__ __forceinline__ uint64_t dk(uint32_t addr, int K) { return make_desc(addr, 128u, (uint32_t)K * 16u); }
-// MN-major reading (rows = k index, columns = M / N index): SBO = next 8 columns (128 B), LBO = next 8 rows (W * 16 B);
+// MN-major no-swizzle reading (rows = k index, columns = M / N index): SBO = next 8 columns (128 B), LBO = next 8 rows (W * 16 B);
 // one K = 16 step = +2 * W * 16 B
 __device__ __forceinline__ uint64_t dm(uint32_t addr, int W) { return make_desc(addr, (uint32_t)W * 16u, 128u); }
+// SWIZZLE_128B image, K-major reading (A of L1): 8-row groups 1024 B apart; a K = 16 step is +32 B inside the 128-byte row,
+// the next 64 halves are the next K block
+__device__ __forceinline__ uint64_t dxk(uint32_t addr, int ks) {
+    return make_desc(addr + (uint32_t)(ks >> 2) * XBLK + (uint32_t)(ks & 3) * 32u, 16u, 1024u) | (2ull << 61);
+}
+// SWIZZLE_128B image, MN-major reading (B of dW1: N = image columns, K = image rows): LBO = next 64 columns (one K block),
+// SBO = next 8 rows; a K = 16 step is +2048 B
+__device__ __forceinline__ uint64_t dxm(uint32_t addr, int ks) { return make_desc(addr + (uint32_t)ks * 2048u, (uint32_t)XBLK, 1024u) | (2ull << 61); }
 __host__ __device__ constexpr uint32_t idesc_h(int M, int N, int a_mn, int b_mn) {      // kind::f16: fp16 A/B, fp32 D
     return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void mma_h(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ uint32_t pk(float a, float b) {
     return (uint32_t)__half_as_ushort(__float2half_rn(a)) | ((uint32_t)__half_as_ushort(__float2half_rn(b)) << 16);
@@ -78,6 +110,9 @@ __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, fl
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void head_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
@@ -98,6 +133,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 }
 
 struct PairParams {
+    CUtensorMap map_obs, map_next;       // float16 rings as [n_worlds * capacity][160] tensors (TMA = true only)
     rl_world_cfg cfg;
     const int32_t* ev_rows;
     const int32_t* ev_total;
@@ -107,7 +143,6 @@ struct PairParams {
     const __half* wimg_e;
     const __half* wimg_t;
     long long* trace;      // debug: clock64 stamps of CTA 0, pair 3 (RL_TC_TRACE=1), else nullptr
-    int dbg;               // reserved
 };
 
 __device__ __forceinline__ void sched_pair(int i, int& net, int& chunk) {
@@ -121,10 +156,11 @@ __device__ __forceinline__ void sched_pair(int i, int& net, int& chunk) {
     else { net = 1; chunk = WI_W2T + (i - 29); }
 }
 
-__global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) {
+template <bool TMA>
+__global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constant__ PairParams P) {
     using L = Layout<RL_MODEL_DUELING>;
-    extern __shared__ __align__(128) unsigned char smem[];
-    __half* sX = reinterpret_cast<__half*>(smem + PO_X);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // SWIZZLE_128B atoms are 1024-byte aligned
     __half* sH1 = reinterpret_cast<__half*>(smem + PO_H1);
     __half* sH2 = reinterpret_cast<__half*>(smem + PO_H2);
     __half* sStg = reinterpret_cast<__half*>(smem + PO_STG);
@@ -135,11 +171,13 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
     int* meta = reinterpret_cast<int*>(smem + PO_META);
     unsigned long long* ringb = reinterpret_cast<unsigned long long*>(smem + PO_RING);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PO_BARS);
-    // full[slot]: chunk landed; sfree[group]: every MMA that reads the chunks of that release group has completed (its ring
-    // slots are free again -- one tcgen05.commit per GROUP of 4-5 chunks instead of one per chunk: a commit between MMAs costs
-    // the issuer ~200 cycles; the 8-chunk stages are released in two halves so that the ring refills behind them)
+    // full[slot]: chunk landed; sfree[group]: every MMA that reads the chunks of that release group has completed (one
+    // tcgen05.commit per GROUP of 4-5 chunks; the 8-chunk stages are released in two halves so that the ring refills behind them)
     uint64_t* full = bars; uint64_t* sfree = bars + NSP; uint64_t* done = sfree + NSTG; uint64_t* doneL1 = done + 1; uint64_t* go = done + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(go + 1);
+    // xfull / xpfull: the gathered eval / target rows of a pair have landed; h2free / xfree: the MMAs that read the H2 / X region
+    // have completed (tcgen05.commit): the next pair's rows may be gathered into it; metaready: the ring positions of a pair are in `meta`
+    uint64_t* xfull = done + 3; uint64_t* xpfull = done + 4; uint64_t* h2free = done + 5; uint64_t* xfree = done + 6; uint64_t* metaready = done + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* G = P.lb.grad_scratch + (size_t)blockIdx.x * L::N_TRAIN;
@@ -149,8 +187,9 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSP; ++i) mbar_init(&full[i], 1);
-        for (int i = 0; i < NSTG; ++i) mbar_init(&sfree[i], 2);     // both issuers commit
-        mbar_init(done, 2); mbar_init(doneL1, 2); mbar_init(go, NEPI);
+        for (int i = 0; i < NSTG; ++i) mbar_init(&sfree[i], 1);
+        mbar_init(done, 1); mbar_init(doneL1, 1); mbar_init(go, NEPI);
+        mbar_init(xfull, 1); mbar_init(xpfull, 1); mbar_init(h2free, 1); mbar_init(xfree, 1); mbar_init(metaready, PB);
         fence_mbar_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -166,9 +205,7 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
     fence_before();
     __syncthreads();
     fence_after();
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t T0 = tmem, T_DW2 = tmem + 256;
-    const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH2 = smem_u32(sH2), aD = smem_u32(sDout);
+    const uint32_t aX = smem_u32(smem + PO_X), aH1 = smem_u32(sH1), aH2 = smem_u32(sH2), aD = smem_u32(sDout), aStg = smem_u32(sStg);
 
     if (warp == 8) {
         // =================================== weight-stream producer ===================================
@@ -187,138 +224,188 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 bulk_load(sStg + slot * HCH, (net ? P.wimg_e : P.wimg_t) + (size_t)ch * HCH, HCH * 2, &full[slot]);
             }
         }
-    } else if (warp == 9 || warp == 10) {
-        // =================================== MMA issuers (two warps) ===================================
-        // A tcgen05.mma costs its issuing thread 100-300 cycles whatever its size and two threads issue concurrently at ~1.4x
-        // the rate (scripts/tc_mma_bench.py), so every stage is split between two issuers by OUTPUT COLUMNS: issuer r takes
-        // the N-half r of L1 / L2 / dH1 / dW2 / dW1 (same A, rows [r N/2, (r+1) N/2) of B, accumulator columns shifted by
-        // r N/2 -- no extra TMEM, nothing for the epilogue to add), the M-half r of dWh and the dH2 half r; the heads
-        // (N = 16) are split over K into two accumulators the epilogue adds.  Both walk the same go sequence and chunk
-        // stream; ring groups, `done` and `doneL1` complete on two commits.
-        // TMEM columns of the work area: L1 accumulators 128..255, L2 / dH2 0..255, heads 0..31, dWh 0..31, dH1 0..127,
-        // dW1 0..159 -- the L1 of the eval net runs under the target head epilogue.
-        if (lane == 0) {
-            const uint32_t r = (uint32_t)(warp - 9);
-            uint32_t consumed = 0, go_no = 0, stage = 0;
-            int itr_n = 0, itr_p = -1;
-            auto istamp = [&]() { if (P.trace && blockIdx.x == 0 && r == 0 && itr_p == 3 && itr_n < 40) P.trace[64 + itr_n++] = clock64(); };
-            auto wait_go = [&]() { mbar_wait(go, go_no & 1); ++go_no; fence_after(); istamp(); };
-            auto chunk_wait = [&]() -> uint32_t {
-                const uint32_t slot = consumed % NSP;
-                mbar_wait(&full[slot], (consumed / NSP) & 1);
-                fence_after();
-                ++consumed;
-                return smem_u32(sStg + slot * HCH);
-            };
-            // all `n` chunks of a stage have landed (they are normally prefetched long before): the MMAs of the stage are then
-            // issued back to back -- a try_wait + fence + descriptor build between two MMAs costs the issuer more than the MMA
-            auto chunks_wait = [&](int n) -> uint32_t {
-                const uint32_t first = consumed;
-                for (int c = 0; c < n; ++c) { const uint32_t k = consumed + c; mbar_wait(&full[k % NSP], (k / NSP) & 1); }
-                fence_after();
-                consumed += n;
-                return first;
-            };
-            auto chunk_addr = [&](uint32_t k) -> uint32_t { return smem_u32(sStg) + (k % NSP) * (HCH * 2); };
-            auto stage_free = [&]() { istamp(); mma_commit(&sfree[stage % NSTG]); ++stage; };
-            // L1: D[128 b][128 k1] = X[128][160] W1[128][160]^T -- 5 chunks [128 n][32 k], 2 k-steps each; issuer r: k1 in [64 r, +64)
-            auto l1 = [&]() {
-                const uint32_t id = idesc_h(128, 64, 0, 0);
-                uint64_t a = dk(aX, 160);
-                const uint32_t k0 = chunks_wait(5);
+    } else if (warp == 10) {
+        // =================================== row gatherer (TMA tile::gather4) ===================================
+        // Lane l owns rows 4 l .. 4 l + 3 of the pair (event l / 16): three gather4 per image (K blocks 0-2; columns 160-191 are
+        // out of bounds and land as zeros).  X' of pair p goes to the H2 region once pair p-1's dW2 / dH1 have completed, X of
+        // pair p to the X region once pair p-1's dW1 has completed.
+        if (TMA) {
+            if (lane == 0) { tma::prefetch_map(&P.map_obs); tma::prefetch_map(&P.map_next); }
+            for (int p = 0; p < n_pairs; ++p) {
+                const int buf = p & 1;
+                mbar_wait(metaready, p & 1);
+                const int* ids = meta + buf * 4 * PB;
+                const int rb = (int)ringb[buf * 2 + (lane >> 4)];
+                const int4 i4 = *reinterpret_cast<const int4*>(ids + 4 * lane);
+                const int r0 = rb + i4.x, r1 = rb + i4.y, r2 = rb + i4.z, r3 = rb + i4.w;
+                if (p > 0) mbar_wait(h2free, (p - 1) & 1);
+                if (lane == 0) mbar_expect_tx(xpfull, XIMG);
+                __syncwarp();
+#pragma unroll
+                for (int kb = 0; kb < 3; ++kb) tma::gather4(aH2 + kb * XBLK + lane * 512, &P.map_next, smem_u32(xpfull), kb * 64, r0, r1, r2, r3);
+                if (p > 0) mbar_wait(xfree, (p - 1) & 1);
+                if (lane == 0) mbar_expect_tx(xfull, XIMG);
+                __syncwarp();
+#pragma unroll
+                for (int kb = 0; kb < 3; ++kb) tma::gather4(aX + kb * XBLK + lane * 512, &P.map_obs, smem_u32(xfull), kb * 64, r0, r1, r2, r3);
+            }
+        }
+    } else if (warp == 9) {
+        // =================================== MMA issuer (one warp, warp-uniform) ===================================
+        // The whole warp walks the stage sequence; every value an MMA consumes is built from uniform values only and the MMA
+        // itself is guarded by elect.sync, so descriptors stay in uniform registers and UTCHMMA issues without a convergence loop.
+        // TMEM columns of the work area: L1 accumulators 128..255, L2 0..255, heads 0..15, dWh 0..31, dH2 half 0 128..255 /
+        // half 1 0..127, dH1 0..127, dW1 0..159 -- the L1 of the eval net runs under the target head epilogue.
+        const bool me = elect_one();
+        const uint32_t T0 = __shfl_sync(0xffffffffu, *tmem_slot, 0), T_DW2 = T0 + 256;
+        const int np_u = __shfl_sync(0xffffffffu, n_pairs, 0);
+        uint32_t consumed = 0, go_no = 0, stage = 0;
+        int itr_n = 0, itr_p = -1;
+        auto istamp = [&]() { if (P.trace && blockIdx.x == 0 && me && itr_p == 3 && itr_n < 40) P.trace[64 + itr_n++] = clock64(); };
+        auto wait_go = [&]() { mbar_wait(go, go_no & 1); ++go_no; fence_after(); istamp(); };
+        // all `n` chunks of a stage have landed (they are normally prefetched long before): its MMAs are then issued back to back
+        auto chunks_wait = [&](int n) -> uint32_t {
+            const uint32_t first = consumed;
+            for (int c = 0; c < n; ++c) { const uint32_t k = consumed + c; mbar_wait(&full[k % NSP], (k / NSP) & 1); }
+            fence_after();
+            consumed += n;
+            istamp();
+            return first;
+        };
+        auto chunk_addr = [&](uint32_t k) -> uint32_t { return aStg + (k % NSP) * (HCH * 2); };
+        auto commit = [&](uint64_t* bar) { if (me) mma_commit(bar); };
+        auto stage_free = [&]() { istamp(); commit(&sfree[stage % NSTG]); ++stage; };
+        // L1: D[128 b][128 k1] = X[128][160] W1[128][160]^T -- 5 chunks [128 n][32 k], 2 k-steps each; X is a SWIZZLE_128B image
+        auto l1 = [&](uint32_t ax) {
+            const uint32_t id = idesc_h(128, 128, 0, 0);
+            const uint32_t k0 = chunks_wait(5);
 #pragma unroll 1
-                for (int c = 0; c < 5; ++c) {
-                    const uint64_t b = dk(chunk_addr(k0 + c) + r * 4096u, 32);    // rows 64 r.. of the [128][32] chunk: 8 row groups x 512 B
-                    mma_h(T0 + 128 + 64 * r, a, b, id, c != 0);
-                    mma_h(T0 + 128 + 64 * r, a + 16u, b + 16u, id, 1u);
-                    a += 32u;
+            for (int c = 0; c < 5; ++c) {
+                const uint64_t b = dk(chunk_addr(k0 + c), 32);
+                if (me) {
+                    mma_h(T0 + 128, dxk(ax, 2 * c), b, id, c != 0);
+                    mma_h(T0 + 128, dxk(ax, 2 * c + 1), b + 16u, id, 1u);
+                }
+            }
+            stage_free();
+            commit(doneL1);
+        };
+        // L2: D[128 b][256 n2] = H1[128][128] W2[256][128]^T -- 8 chunks [256 n][16 k]
+        auto l2 = [&]() {
+            const uint32_t id = idesc_h(128, 256, 0, 0);
+            uint64_t a = dk(aH1, 128);
+#pragma unroll 1
+            for (int hf = 0; hf < 2; ++hf) {
+                const uint32_t k0 = chunks_wait(4);
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    if (me) mma_h(T0, a, dk(chunk_addr(k0 + c), 16), id, (hf | c) != 0);
+                    a += 16u;
                 }
                 stage_free();
-                mma_commit(doneL1);
-            };
-            // L2: D[128 b][256 n2] = H1[128][128] W2[256][128]^T -- 8 chunks [256 n][16 k]; issuer r: n2 in [128 r, +128)
-            auto l2 = [&]() {
+            }
+            commit(done);
+        };
+        // head: D[128 b][16] = H2[128][256] Wh[16][256]^T -- one chunk, 16 k-steps
+        auto head = [&]() {
+            const uint32_t id = idesc_h(128, 16, 0, 0);
+            const uint32_t k0 = chunks_wait(1);
+            uint64_t a = dk(aH2, 256), b = dk(chunk_addr(k0), 256);
+#pragma unroll 1
+            for (int ks = 0; ks < 16; ks += 4) {
+                if (me) {
+                    mma_h(T0, a, b, id, ks != 0); mma_h(T0, a + 16u, b + 16u, id, 1u);
+                    mma_h(T0, a + 32u, b + 32u, id, 1u); mma_h(T0, a + 48u, b + 48u, id, 1u);
+                }
+                a += 64u; b += 64u;
+            }
+            stage_free();
+            commit(done);
+        };
+        for (int p = 0; p < np_u; ++p) {
+            itr_p = p;
+            wait_go();
+            if (TMA) { mbar_wait(xpfull, p & 1); fence_after(); }
+            l1(aH2);                                           // target net: X' sits in the H2 region
+            wait_go(); l2();
+            wait_go(); head();                                 // target head, then the eval L1 (runs under the target head epilogue)
+            if (TMA) { mbar_wait(xfull, p & 1); fence_after(); }
+            l1(aX);
+            wait_go(); l2();
+            wait_go(); head();
+            wait_go();
+            {   // dH2 half 0 (n2 < 128) -> columns 128..255: A = dOut [128][16], B = Wh^T chunk rows 0..127 [256 n2][16 j];
+                // dWh rows n2 in [128 m, +128) -> columns 16 m..: A = H2 read MN-major (M = n2 half), B = dOut read MN-major, K = 128 rows
+                const uint32_t wht = chunk_addr(chunks_wait(1));
+                const uint32_t id = idesc_h(128, 16, 1, 1);
+                if (me) mma_h(T0 + 128, dk(aD, 16), dk(wht, 16), idesc_h(128, 128, 0, 0), 0u);
+#pragma unroll 1
+                for (int m = 0; m < 2; ++m) {
+                    uint64_t a = dm(aH2 + m * 2048u, 256), b = dm(aD, 16);
+#pragma unroll 1
+                    for (int ks = 0; ks < 8; ks += 4) {
+                        if (me) {
+                            mma_h(T0 + 16 * m, a, b, id, ks != 0); mma_h(T0 + 16 * m, a + 512u, b + 32u, id, 1u);
+                            mma_h(T0 + 16 * m, a + 1024u, b + 64u, id, 1u); mma_h(T0 + 16 * m, a + 1536u, b + 96u, id, 1u);
+                        }
+                        a += 2048u; b += 128u;
+                    }
+                }
+                commit(done);
+                wait_go();                                     // dWh drained: dH2 half 1 (n2 >= 128) -> columns 0..127
+                if (me) mma_h(T0, dk(aD, 16), dk(wht + 4096u, 16), idesc_h(128, 128, 0, 0), 0u);
+                stage_free();
+                commit(done);
+            }
+            wait_go();
+            {   // dW2[k1][n2] += sum_b H1[b][k1] dH2[b][n2] first (no weights: the last W2^T chunks get more time to land): both
+                // images read MN-major, accumulator resident in TMEM
+                const uint32_t id2 = idesc_h(128, 256, 1, 1);
+                uint64_t a2 = dm(aH1, 128), b2 = dm(aH2, 256);
+#pragma unroll 1
+                for (int ks = 0; ks < 8; ks += 4) {
+                    if (me) {
+                        mma_h(T_DW2, a2, b2, id2, (p != 0 || ks != 0) ? 1u : 0u); mma_h(T_DW2, a2 + 256u, b2 + 512u, id2, 1u);
+                        mma_h(T_DW2, a2 + 512u, b2 + 1024u, id2, 1u); mma_h(T_DW2, a2 + 768u, b2 + 1536u, id2, 1u);
+                    }
+                    a2 += 1024u; b2 += 2048u;
+                }
+                // dH1[128 b][128 k1] = dH2[128][256] W2^T[128 k1][256 n2]^T: 8 chunks [128][32], 2 k-steps each
                 const uint32_t id = idesc_h(128, 128, 0, 0);
-                uint64_t a = dk(aH1, 128);
+                uint64_t a = dk(aH2, 256);
 #pragma unroll 1
                 for (int hf = 0; hf < 2; ++hf) {
                     const uint32_t k0 = chunks_wait(4);
 #pragma unroll 1
                     for (int c = 0; c < 4; ++c) {
-                        mma_h(T0 + 128 * r, a, dk(chunk_addr(k0 + c) + r * 4096u, 16), id, (hf | c) != 0);   // rows 128 r..: 16 row groups x 256 B
-                        a += 16u;
+                        const uint64_t b = dk(chunk_addr(k0 + c), 32);
+                        if (me) { mma_h(T0, a, b, id, (hf | c) != 0); mma_h(T0, a + 16u, b + 16u, id, 1u); }
+                        a += 32u;
                     }
                     stage_free();
                 }
-                mma_commit(done);
-            };
-            // head: D[128 b][16] = H2[128][256] Wh[16][256]^T -- one chunk; issuer r: k-steps [8 r, +8) into columns 16 r..
-            auto head = [&]() {
-                const uint32_t id = idesc_h(128, 16, 0, 0);
-                uint64_t a = dk(aH2, 256) + 128u * r, b = dk(chunk_wait(), 256) + 128u * r;
+                commit(done);
+                if (TMA) commit(h2free);                       // dH2 is dead: the next pair's target rows may land in the H2 region
+            }
+            wait_go();
+            {   // dW1[k1][x] = sum_b dH1[b][k1] X[b][x]: dH1 (in the H1 region) read MN-major, X (SWIZZLE_128B) read MN-major, N = 160
+                const uint32_t id = idesc_h(128, 160, 1, 1);
+                uint64_t a = dm(aH1, 128);
 #pragma unroll 1
-                for (int ks = 0; ks < 8; ++ks) { mma_h(T0 + 16 * r, a, b, id, ks != 0); a += 16u; b += 16u; }
-                stage_free();
-                mma_commit(done);
-            };
-            for (int p = 0; p < n_pairs; ++p) {
-                itr_p = p;
-                wait_go(); l1();                                   // target net
-                wait_go(); l2();
-                wait_go(); head(); l1();                           // target head, then the eval L1 (runs under the target head epilogue)
-                wait_go(); l2();
-                wait_go(); head();
-                wait_go();
-                {   // issuer 0: dH2 half 0 (n2 < 128) -> columns 128..255: A = dOut [128][16], B = Wh^T chunk rows 0..127 [256 n2][16 j];
-                    // issuer r: dWh rows n2 in [128 r, +128): A = H2 read MN-major (M = n2 half), B = dOut read MN-major, K = 128 rows
-                    const uint32_t wht = chunk_wait();
-                    if (r == 0) mma_h(T0 + 128, dk(aD, 16), dk(wht, 16), idesc_h(128, 128, 0, 0), 0u);
-                    const uint32_t id = idesc_h(128, 16, 1, 1);
-                    uint64_t a = dm(aH2 + r * 2048u, 256), b = dm(aD, 16);
-#pragma unroll 1
-                    for (int ks = 0; ks < 8; ++ks) { mma_h(T0 + 16 * r, a, b, id, ks != 0); a += 512u; b += 32u; }
-                    mma_commit(done);
-                    wait_go();                                     // dWh drained: dH2 half 1 (n2 >= 128) -> columns 0..127, 64 each
-                    mma_h(T0 + 64 * r, dk(aD, 16), dk(wht + 4096u + r * 2048u, 16), idesc_h(128, 64, 0, 0), 0u);
-                    stage_free();
-                    mma_commit(done);
-                }
-                wait_go();
-                {   // dW2[k1][n2] += sum_b H1[b][k1] dH2[b][n2] first (no weights: the last W2^T chunks get more time to land): both
-                    // images read MN-major, accumulator resident in TMEM; issuer r: n2 half r
-                    const uint32_t id2 = idesc_h(128, 128, 1, 1);
-                    uint64_t a2 = dm(aH1, 128), b2 = dm(aH2 + r * 2048u, 256);
-#pragma unroll 1
-                    for (int ks = 0; ks < 8; ++ks) { mma_h(T_DW2 + 128 * r, a2, b2, id2, (p != 0 || ks != 0) ? 1u : 0u); a2 += 256u; b2 += 512u; }
-                    // dH1[128 b][128 k1] = dH2[128][256] W2^T[128 k1][256 n2]^T: 8 chunks [128][32], 2 k-steps each; issuer r: k1 in [64 r, +64)
-                    const uint32_t id = idesc_h(128, 64, 0, 0);
-                    uint64_t a = dk(aH2, 256);
-#pragma unroll 1
-                    for (int hf = 0; hf < 2; ++hf) {
-                        const uint32_t k0 = chunks_wait(4);
-#pragma unroll 1
-                        for (int c = 0; c < 4; ++c) {
-                            const uint64_t b = dk(chunk_addr(k0 + c) + r * 4096u, 32);
-                            mma_h(T0 + 64 * r, a, b, id, (hf | c) != 0);
-                            mma_h(T0 + 64 * r, a + 16u, b + 16u, id, 1u);
-                            a += 32u;
-                        }
-                        stage_free();
+                for (int ks = 0; ks < 8; ks += 4) {
+                    if (me) {
+                        mma_h(T0, a, dxm(aX, ks), id, ks != 0); mma_h(T0, a + 256u, dxm(aX, ks + 1), id, 1u);
+                        mma_h(T0, a + 512u, dxm(aX, ks + 2), id, 1u); mma_h(T0, a + 768u, dxm(aX, ks + 3), id, 1u);
                     }
-                    mma_commit(done);
+                    a += 1024u;
                 }
-                wait_go();
-                {   // dW1[k1][x] = sum_b dH1[b][k1] X[b][x]: dH1 (in the H1 region) and X read MN-major; issuer r: inputs x in [80 r, +80)
-                    const uint32_t id = idesc_h(128, 80, 1, 1);
-                    uint64_t a = dm(aH1, 128), b = dm(aX + r * 1280u, 160);
-#pragma unroll 1
-                    for (int ks = 0; ks < 8; ++ks) { mma_h(T0 + 80 * r, a, b, id, ks != 0); a += 256u; b += 320u; }
-                    mma_commit(done);
-                }
+                commit(done);
+                if (TMA) commit(xfree);                        // X is dead: the next pair's eval rows may land in the X region
             }
         }
     } else {
         // =================================== epilogue warps ===================================
+        const uint32_t T0 = *tmem_slot, T_DW2 = T0 + 256;
         uint32_t done_no = 0, l1_no = 0;
         const int q = warp & 3, hh = warp >> 2;
         const int row = q * 32 + lane;                    // batch row of the pair == TMEM lane
@@ -331,7 +418,7 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
         auto wait_l1 = [&]() { mbar_wait(doneL1, l1_no & 1); ++l1_no; fence_after(); stamp(); };
         // ---- metadata of a pair (threads 0-127, one sampled row each) in three phases so that no global-load latency
         //      sits on the critical path: A event row + ring position, B action / reward / done (+ L2 prefetch of the
-        //      sample's two rows), C to shared memory ----
+        //      sample's two rows), C to shared memory (+ metaready for the row gatherer) ----
         size_t m_ring = 0; int m_row = 0, m_i = 0, m_act = 0; float m_rew = 0.f, m_dn = 0.f;
         auto meta_a = [&](int p) {
             if (threadIdx.x < PB) {
@@ -346,7 +433,7 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
             if (threadIdx.x < PB) {
                 m_ring = (size_t)(m_row / S) * cap; m_i = max(m_i, 0);
                 m_act = P.rp.action[m_ring + m_i]; m_rew = P.rp.reward[m_ring + m_i]; m_dn = (float)P.rp.done[m_ring + m_i];
-                // pull the two 640-byte rows of this sample towards L2 now: the gathers of the next pair then hit L2, not HBM
+                // pull the two rows of this sample towards L2 now: the gathers of the next pair then hit L2, not HBM
                 const size_t rb = (m_ring + m_i) * RL_K1 * (P.rp.obs_fp16 ? 2 : 4);                  // byte offset of the sample's row
                 const char* r0 = reinterpret_cast<const char*>(P.rp.next_obs) + rb; const char* r1 = reinterpret_cast<const char*>(P.rp.obs) + rb;
                 const int nl = P.rp.obs_fp16 ? 3 : 5;
@@ -363,45 +450,37 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                 m[r] = m_i; m[PB + r] = m_act;
                 reinterpret_cast<float*>(m)[2 * PB + r] = m_rew; reinterpret_cast<float*>(m)[3 * PB + r] = m_dn;
                 if ((r & 63) == 0) ringb[buf * 2 + (r >> 6)] = (unsigned long long)m_ring;
+                if (TMA) mbar_arrive(metaready);
             }
         };
-        // ---- 128 rows x 160 floats from the replay ring -> packed fp16 in registers (unit = 8 consecutive columns) ----
-        uint4 xh[10];
-        const bool ring16 = P.rp.obs_fp16 != 0;
+        // ---- register gather (float32 rings only, TMA = false): 128 rows x 20 units of 8 columns -> packed fp16; a quarter-warp
+        //      takes 8 consecutive units of a row (contiguous loads, conflict-free swizzled stores) ----
+        uint4 xh[TMA ? 1 : 10];
         auto gather_load = [&](const float* __restrict__ src, int buf) {
+            if (TMA) return;
             const int* ids = meta + buf * 4 * PB;
-            if (ring16) {
-                // float16 ring: one 16-byte load per unit, straight into the packed registers -- nothing depends on the data
-                // until gather_store, so the loads stay in flight behind whatever the thread does next
-                const uint4* src16 = reinterpret_cast<const uint4*>(src);
+            const bool ring16 = P.rp.obs_fp16 != 0;
 #pragma unroll
-                for (int u = 0; u < 10; ++u) {
-                    const int v = threadIdx.x + u * NEPI;
-                    const int rr = v & 7, o4 = (v >> 3) & 3, blk = v >> 5;
-                    const int rg = blk / 5, og = blk - rg * 5;
-                    const int r = rg * 8 + rr, oct = og * 4 + o4;
-                    xh[u] = __ldg(src16 + ((size_t)ringb[buf * 2 + (r >> 6)] + ids[r]) * (RL_K1 / 8) + oct);
-                }
-                return;
-            }
-#pragma unroll
-            for (int u = 0; u < 10; ++u) {
+            for (int u = 0; u < (TMA ? 0 : 10); ++u) {
                 const int v = threadIdx.x + u * NEPI;
-                const int rr = v & 7, o4 = (v >> 3) & 3, blk = v >> 5;
-                const int rg = blk / 5, og = blk - rg * 5;
-                const int r = rg * 8 + rr, oct = og * 4 + o4;
-                const float4* g = reinterpret_cast<const float4*>(src + ((size_t)ringb[buf * 2 + (r >> 6)] + ids[r]) * RL_K1) + oct * 2;
-                const float4 a = __ldg(g), b = __ldg(g + 1);
-                xh[u] = make_uint4(pk(a.x, a.y), pk(a.z, a.w), pk(b.x, b.y), oct == 19 ? pk(b.z, 1.0f) : pk(b.z, b.w));   // column 159 := 1 (db1)
+                const int r = v / 20, oct = v - r * 20;
+                const size_t ro = (size_t)ringb[buf * 2 + (r >> 6)] + ids[r];
+                if (ring16) {
+                    xh[u] = __ldg(reinterpret_cast<const uint4*>(src) + ro * (RL_K1 / 8) + oct);
+                } else {
+                    const float4* g = reinterpret_cast<const float4*>(src + ro * RL_K1) + oct * 2;
+                    const float4 a = __ldg(g), b = __ldg(g + 1);
+                    xh[u] = make_uint4(pk(a.x, a.y), pk(a.z, a.w), pk(b.x, b.y), oct == 19 ? pk(b.z, 1.0f) : pk(b.z, b.w));   // column 159 := 1 (db1)
+                }
             }
         };
-        auto gather_store = [&]() {
+        auto gather_store = [&](int region) {
+            if (TMA) return;
 #pragma unroll
-            for (int u = 0; u < 10; ++u) {
+            for (int u = 0; u < (TMA ? 0 : 10); ++u) {
                 const int v = threadIdx.x + u * NEPI;
-                const int rr = v & 7, o4 = (v >> 3) & 3, blk = v >> 5;
-                const int rg = blk / 5, og = blk - rg * 5;
-                *reinterpret_cast<uint4*>(sX + himg(rg * 8 + rr, (og * 4 + o4) * 8, 160)) = xh[u];
+                const int r = v / 20, oct = v - r * 20;
+                *reinterpret_cast<uint4*>(smem + region + ximg(r, oct)) = xh[u];
             }
         };
         // relu(D + bias) of 32 accumulator columns -> 4 x 16-byte stores into a batch-major image of width K
@@ -443,13 +522,12 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
         // ---- head epilogue (warps 0-3: one row each): out[0..8] of the row, mean of the advantages over the row's EVENT
         //      (PERD3QN.py:202: advantage.mean() over the whole [64, 8] tensor) ----
         auto head_epilogue = [&](const float* bias, float (&out)[9]) -> float {
-            float v[16], v2[16];
+            float v[16];
             tmem_ld16(T0 + t_lane, v);
-            tmem_ld16(T0 + t_lane + 16, v2);                        // second K half (issuer 1)
             tmem_wait_ld();
             float s = 0.f;
 #pragma unroll
-            for (int j = 0; j < 9; ++j) { out[j] = (v[j] + v2[j]) + bias[384 + j]; if (j < 8) s += out[j]; }
+            for (int j = 0; j < 9; ++j) { out[j] = v[j] + bias[384 + j]; if (j < 8) s += out[j]; }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0) red[q] = s;
@@ -468,7 +546,7 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
             meta_a(0); meta_b(); meta_c(0);
             epi_bar();
             gather_load(P.rp.next_obs, 0);
-            gather_store();
+            gather_store(PO_H2);
             go_signal();                                            // -> target L1 of pair 0
         }
         for (int p = 0; p < n_pairs; ++p) {
@@ -485,11 +563,11 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
             wait_l1();
             l1_epilogue(bias_t);
             go_signal();                                            // -> target L2
-            gather_load(P.rp.obs, buf);                             // eval rows of this pair: their latency sits behind the target L2
             if (more) meta_b();
             wait_done();
+            gather_load(P.rp.obs, buf);                             // (float32 rings: eval rows of this pair, in flight behind the L2 epilogue)
             l2_epilogue(bias_t);
-            gather_store();                                         // X image <- eval rows (the target L1 is done with X')
+            gather_store(PO_X);
             go_signal();                                            // -> target head, eval L1
             if (more) meta_c(buf ^ 1);
             wait_done();
@@ -598,11 +676,9 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
             go_signal();                                            // -> dH1, dW2
 #pragma unroll
             for (int k = 0; k < 4; ++k) acc_b2[k] += cs[k];
-            if (more) {
-                epi_bar();                                          // the next pair's metadata (threads 0-127) is visible to every warp
-                gather_load(P.rp.next_obs, buf ^ 1);                // next pair's target rows, in flight behind dH1 / dW1
-            }
+            if (!TMA && more) epi_bar();                            // the next pair's metadata (threads 0-127) is visible to every warp
             wait_done();
+            if (more) gather_load(P.rp.next_obs, buf ^ 1);          // (float32 rings: next pair's target rows, in flight behind the dH1 epilogue)
             {   // dH1 epilogue: this thread's row, columns [64 hh, +64): mask by H1 > 0, dH1 in place of H1
                 const int c0 = hh * 64;
                 float v0[32], v1[32];
@@ -624,9 +700,9 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
                     *ph = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                 }
             }
+            if (more) gather_store(PO_H2);                          // (float32 rings) X' of the next pair -> H2 region: dH2 is dead (dW2 / dH1 done)
             go_signal();                                            // -> dW1
             wait_done();
-            if (more) gather_store();                               // X image <- next pair's target rows (dW1 is done with X)
             {   // dW1 flush: TMEM lane = k1 = row, columns [80 hh, +80) of the 160 inputs; column 159 carries db1.  All 80 values
                 // are pulled into registers first so that the next pair's target L1 can start before the reds are issued.
                 float v[80];
@@ -669,7 +745,7 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const PairParams P) 
     }
     fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem, 512);
+    if (warp == 8) tmem_dealloc(*tmem_slot, 512);
 }
 
 }  // namespace
@@ -682,13 +758,21 @@ extern "C" int rl_brain_learn_p(const rl_world_cfg* cfg, const rl_rows_bufs* row
     RL_ARG_CHECK(learn->params && learn->target && learn->grad_scratch && learn->grad && learn->new_prio && learn->loss);
     if (learn->kind != RL_MODEL_DUELING) return rl_set_err(RL_ERR_UNSUPPORTED, "rl_brain_learn_p: dueling networks only");
     PairParams P;
+    memset(&P, 0, sizeof(P));
     P.cfg = *cfg;
     P.ev_rows = rows->rows + (size_t)(gene * RL_N_ROW_KINDS + RL_ROWS_EVENT) * rows->row_cap;
     P.ev_total = rows->total + gene * RL_N_ROW_KINDS + RL_ROWS_EVENT;
     P.rp = *replay; P.sample_idx = sample_idx; P.lb = *learn;
     P.wimg_e = reinterpret_cast<const __half*>(wimg_eval_h); P.wimg_t = reinterpret_cast<const __half*>(wimg_target_h);
     P.trace = nullptr;
-    P.dbg = 0;
+    const bool use_tma = replay->obs_fp16 != 0 && getenv("RL_PAIR_NO_TMA") == nullptr;     // (A/B switch: register gather from the float16 ring)
+    if (use_tma) {
+        const long long n_rows = (long long)cfg->n_worlds * replay->capacity;
+        RL_ARG_CHECK(n_rows > 0 && n_rows < (1ll << 31));
+        if (tma::make_rows_map(&P.map_obs, replay->obs, (uint64_t)n_rows, RL_K1, 1) != 0 ||
+            tma::make_rows_map(&P.map_next, replay->next_obs, (uint64_t)n_rows, RL_K1, 1) != 0)
+            return rl_set_err(RL_ERR_CUDA, "rl_brain_learn_p: cuTensorMapEncodeTiled failed");
+    }
     static long long* trace_dev = nullptr;
     const bool tracing = getenv("RL_TC_TRACE") != nullptr;
     if (tracing) {
@@ -697,9 +781,13 @@ extern "C" int rl_brain_learn_p(const rl_world_cfg* cfg, const rl_rows_bufs* row
         P.trace = trace_dev;
     }
     static PerDeviceOnce attr;
-    if (attr.need()) RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dueling_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM));
+    if (attr.need()) {
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dueling_p<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM));
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dueling_p<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM));
+    }
     cudaStream_t st = (cudaStream_t)stream;
-    k_learn_dueling_p<<<rl_learn_grid(), NTH, PAIR_SMEM, st>>>(P);
+    if (use_tma) k_learn_dueling_p<true><<<rl_learn_grid(), NTH, PAIR_SMEM, st>>>(P);
+    else k_learn_dueling_p<false><<<rl_learn_grid(), NTH, PAIR_SMEM, st>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
     if (tracing) {
         long long h[128];
@@ -707,7 +795,7 @@ extern "C" int rl_brain_learn_p(const rl_world_cfg* cfg, const rl_rows_bufs* row
         RL_CUDA_CHECK(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
         fprintf(stderr, "[pair trace] epilogue stamps (cycles since the pair's start):");
         for (int i = 1; i < 40 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
-        fprintf(stderr, "\n[pair trace] issuer stamps (go seen / last MMA of a chunk stage issued):");
+        fprintf(stderr, "\n[pair trace] issuer stamps (go seen / chunks landed / last MMA of a chunk stage issued):");
         for (int i = 0; i < 40 && h[64 + i]; ++i) fprintf(stderr, " %lld", h[64 + i] - h[0]);
         fprintf(stderr, "\n");
     }

@@ -72,12 +72,12 @@ extern "C" int rl_tc_gemm_test(const float* a_img, const float* b_img, float* d,
 namespace {
 using namespace tc;
 struct TcTestParamsH { const uint16_t* a; const uint16_t* b; float* d; int M, N, K, a_halves, b_halves;
-                       uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep; int a_mn, b_mn; };
+                       uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep; int a_mn, b_mn; uint32_t a_kblk, b_kblk; int a_layout, b_layout; };
 
 __global__ void __launch_bounds__(128) k_tc_gemm_test_h(const TcTestParamsH P) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint16_t* sa = reinterpret_cast<uint16_t*>(smem_raw);
-    uint16_t* sb = sa + ((P.a_halves + 63) & ~63);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    uint16_t* sa = reinterpret_cast<uint16_t*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    uint16_t* sb = sa + ((P.a_halves + 511) & ~511);        // 1024-byte aligned (SWIZZLE_128B atoms)
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     for (int i = threadIdx.x; i < P.a_halves; i += blockDim.x) sa[i] = P.a[i];
@@ -92,8 +92,11 @@ __global__ void __launch_bounds__(128) k_tc_gemm_test_h(const TcTestParamsH P) {
     if (threadIdx.x == 0) {
         const uint32_t idesc = (1u << 4) | ((uint32_t)P.a_mn << 15) | ((uint32_t)P.b_mn << 16) | ((uint32_t)(P.N >> 3) << 17) | ((uint32_t)(P.M >> 4) << 24);
         for (int ks = 0; ks < P.K / 16; ++ks) {
-            const uint64_t ad = make_desc(smem_u32(sa) + ks * P.a_kstep, P.a_lbo, P.a_sbo);
-            const uint64_t bd = make_desc(smem_u32(sb) + ks * P.b_kstep, P.b_lbo, P.b_sbo);
+            // k-step address: linear, or (a_kblk != 0) four steps inside a swizzle atom, then the next K block
+            const uint32_t ao = P.a_kblk ? (ks >> 2) * P.a_kblk + (ks & 3) * P.a_kstep : ks * P.a_kstep;
+            const uint32_t bo = P.b_kblk ? (ks >> 2) * P.b_kblk + (ks & 3) * P.b_kstep : ks * P.b_kstep;
+            const uint64_t ad = make_desc(smem_u32(sa) + ao, P.a_lbo, P.a_sbo) | ((uint64_t)P.a_layout << 61);
+            const uint64_t bd = make_desc(smem_u32(sb) + bo, P.b_lbo, P.b_sbo) | ((uint64_t)P.b_layout << 61);
             const uint32_t acc = ks > 0;
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                          "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -120,13 +123,21 @@ __global__ void __launch_bounds__(128) k_tc_gemm_test_h(const TcTestParamsH P) {
 }
 }  // namespace
 
+extern "C" int rl_tc_gemm_test_hx(const void* a_img, const void* b_img, float* d, int M, int N, int K, int a_halves, int b_halves,
+                                  uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kstep, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep,
+                                  int a_mn, int b_mn, uint32_t a_kblk, uint32_t b_kblk, int a_layout, int b_layout, void* stream);
 extern "C" int rl_tc_gemm_test_h(const void* a_img, const void* b_img, float* d, int M, int N, int K, int a_halves, int b_halves,
                                  uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kstep, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep,
                                  int a_mn, int b_mn, void* stream) {
+    return rl_tc_gemm_test_hx(a_img, b_img, d, M, N, K, a_halves, b_halves, a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep, a_mn, b_mn, 0, 0, 0, 0, stream);
+}
+extern "C" int rl_tc_gemm_test_hx(const void* a_img, const void* b_img, float* d, int M, int N, int K, int a_halves, int b_halves,
+                                  uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kstep, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep,
+                                  int a_mn, int b_mn, uint32_t a_kblk, uint32_t b_kblk, int a_layout, int b_layout, void* stream) {
     RL_ARG_CHECK(a_img && b_img && d && (M == 64 || M == 128) && N % 16 == 0 && N <= 256 && K % 16 == 0);
     TcTestParamsH P{reinterpret_cast<const uint16_t*>(a_img), reinterpret_cast<const uint16_t*>(b_img), d, M, N, K, a_halves, b_halves,
-                    a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep, a_mn, b_mn};
-    const size_t smem = 2 * (size_t)(((a_halves + 63) & ~63) + b_halves) + 256;
+                    a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep, a_mn, b_mn, a_kblk, b_kblk, a_layout, b_layout};
+    const size_t smem = 2 * (size_t)(((a_halves + 511) & ~511) + b_halves) + 2048;
     RL_ARG_CHECK(smem <= 200 * 1024);
     RL_CUDA_CHECK(cudaFuncSetAttribute(k_tc_gemm_test_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_tc_gemm_test_h<<<1, 128, smem, (cudaStream_t)stream>>>(P);

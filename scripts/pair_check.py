@@ -4,7 +4,7 @@ import numpy as np
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-from test_scale_gpu import _events_setup, _run_event_kernel, _check_tc_vs
+from test_scale_gpu import _events_setup, _run_event_kernel, _check_tc_vs, _half_copy
 from brain_golden_util import state_dict
 from reinlife_b200.Models import packing
 import ctypes as C
@@ -20,14 +20,16 @@ for name, NW, per_world in cases:
     z, vw, rows, rp, ring, n_ev, sidx = _events_setup(NW, per_world, seed=5)
     sd = torch.from_numpy(sidx).cuda()
     ref = _run_event_kernel("fp32", vw, rows, rp, w0, tgt, sd, n_ev)
-    got = _run_event_kernel("fp16p", vw, rows, rp, w0, tgt, sd, n_ev)
-    try:
-        _check_tc_vs(ref, got, m, d, n_ev, name)
-        print(name, "OK", flush=True)
-    except AssertionError as e:
-        print(name, "FAIL", str(e)[:600], flush=True)
+    r16 = _half_copy(rp)
+    for ring_name, ring_used in (("float32 ring (register gather)", rp), ("float16 ring (TMA gather4)", r16)):
+        got = _run_event_kernel("fp16p", vw, rows, ring_used, w0, tgt, sd, n_ev)
+        try:
+            _check_tc_vs(ref, got, m, d, n_ev, name)
+            print(name, ring_name, "OK", flush=True)
+        except AssertionError as e:
+            print(name, ring_name, "FAIL", str(e)[:600], flush=True)
     if n_ev > 10000:
-        for mode in ("fp16", "fp16p"):
+        for mode, rp in (("fp16", rp), ("fp16p", rp), ("fp16p", r16)):
             brain = DeviceBrain(0, w0, "cuda"); brain.use_fp16 = True
             brain.load_state_dict(tgt, target=True); brain.alloc_learn(rows.row_cap); brain.sample_idx[:n_ev] = sd
             st = vw._stream(); brain.build_wimg(st)
@@ -42,4 +44,4 @@ for name, NW, per_world in cases:
             for _ in range(10): run()
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 10
-            print(f"{mode}: {ms:.3f} ms per launch for {n_ev} events -> {n_ev * 24.89e6 / ms / 1e9:.1f} TFLOP/s", flush=True)
+            print(f"{mode} ({'float16' if rp.fp16 else 'float32'} ring): {ms:.3f} ms per launch for {n_ev} events -> {n_ev * 24.89e6 / ms / 1e9:.1f} TFLOP/s", flush=True)
