@@ -177,7 +177,10 @@ __global__ void k_grad_reduce(const float* __restrict__ scratch, int n_cta, int 
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < n_train) {
         int src = p;
-        if (w1_rowmajor && p < RL_K1 * n1) { const int kx = p / n1, k1 = p - kx * n1; src = k1 * RL_K1 + kx; }
+        if (w1_rowmajor && p < RL_K1 * n1) {      // W1 slab layouts of the tensor-core kernels: 1 = [k1][kx], 2 = [kx / 4][k1][kx % 4]
+            const int kx = p / n1, k1 = p - kx * n1;
+            src = w1_rowmajor == 2 ? ((kx >> 2) * n1 + k1) * 4 + (kx & 3) : k1 * RL_K1 + kx;
+        }
         float s = 0.f;
         for (int c = 0; c < n_cta; ++c) s += scratch[(size_t)c * n_train + src];
         grad[p] = s;

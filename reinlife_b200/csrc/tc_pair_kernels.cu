@@ -42,7 +42,7 @@ using mlp::mbar_init; using mlp::mbar_wait; using mlp::fence_mbar_init; using ml
 constexpr int R = 64;                    // rows per event
 constexpr int PB = 128;                  // rows per pair
 constexpr int NEPI = 256;                // epilogue threads (warps 0-7)
-constexpr int NTH = NEPI + 96;           // + weight producer (warp 8) + MMA issuer (warp 9) + row gatherer (warp 10)
+constexpr int NTH = NEPI + 128;          // + weight producer (warp 8) + MMA issuer (warp 9) + two row gatherers (warps 10, 11)
 constexpr int NSP = 8;                   // weight-chunk ring slots of 8 KB
 constexpr int HCH = 4096;                // halves per weight chunk
 constexpr float H_SCALE = 256.0f;        // backward operands are scaled by 2^8 (exact), removed when gradients leave TMEM
@@ -65,7 +65,7 @@ constexpr int PO_META = PO_RED + 4 * 64;                  // [2] x { idx[128] ac
 constexpr int PO_RING = PO_META + 2 * 4 * 4 * PB;         // [2][2] ring base (elements) per buffer / event, 64-bit
 constexpr int PO_BARS = PO_RING + 2 * 2 * 8;
 constexpr int NSTG = 11;                 // ring release groups per pair: tL1 tL2a tL2b thead eL1 eL2a eL2b ehead dH2 dH1a dH1b
-constexpr int NBAR = NSP + NSTG + 8;     // + done doneL1 go xfull xpfull h2free xfree metaready
+constexpr int NBAR = 2 * NSTG + 8;       // gfull[NSTG] sfree[NSTG] + done doneL1 go xfull xpfull h2free xfree metaready
 constexpr size_t PAIR_SMEM = PO_BARS + 8 * NBAR + 16 + 1024;     // + alignment slack
 static_assert(PAIR_SMEM <= 227 * 1024 && PO_BARS % 8 == 0 && PO_RING % 8 == 0 && PO_H2 % 1024 == 0, "shared memory budget");
 
@@ -116,6 +116,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void bulk_copy(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {      // (barrier armed by the caller)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t group_chunks(uint32_t g) { return (g == 0 || g == 4) ? 5u : (g == 3 || g == 7 || g == 8) ? 1u : 4u; }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void head_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 
@@ -173,9 +178,10 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
     int* meta = reinterpret_cast<int*>(smem + PO_META);
     unsigned long long* ringb = reinterpret_cast<unsigned long long*>(smem + PO_RING);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PO_BARS);
-    // full[slot]: chunk landed; sfree[group]: every MMA that reads the chunks of that release group has completed (one
-    // tcgen05.commit per GROUP of 4-5 chunks; the 8-chunk stages are released in two halves so that the ring refills behind them)
-    uint64_t* full = bars; uint64_t* sfree = bars + NSP; uint64_t* done = sfree + NSTG; uint64_t* doneL1 = done + 1; uint64_t* go = done + 2;
+    // gfull[group]: all chunks of a release group have landed (one expect_tx per group: one mbarrier wait per stage on the issuer's
+    // path); sfree[group]: every MMA that reads the chunks of that group has completed (one tcgen05.commit per GROUP of 4-5 chunks;
+    // the 8-chunk stages are released in two halves so that the ring refills behind them)
+    uint64_t* gfull = bars; uint64_t* sfree = bars + NSTG; uint64_t* done = sfree + NSTG; uint64_t* doneL1 = done + 1; uint64_t* go = done + 2;
     // xfull / xpfull: the gathered eval / target rows of a pair have landed; h2free / xfree: the MMAs that read the H2 / X region
     // have completed (tcgen05.commit): the next pair's rows may be gathered into it; metaready: the ring positions of a pair are in `meta`
     uint64_t* xfull = done + 3; uint64_t* xpfull = done + 4; uint64_t* h2free = done + 5; uint64_t* xfree = done + 6; uint64_t* metaready = done + 7;
@@ -188,10 +194,10 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
     const int n_pairs = (n_my + 1) >> 1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NSP; ++i) mbar_init(&full[i], 1);
+        for (int i = 0; i < NSTG; ++i) mbar_init(&gfull[i], 1);
         for (int i = 0; i < NSTG; ++i) mbar_init(&sfree[i], 1);
         mbar_init(done, 1); mbar_init(doneL1, 1); mbar_init(go, NEPI);
-        mbar_init(xfull, 1); mbar_init(xpfull, 1); mbar_init(h2free, 1); mbar_init(xfree, 1); mbar_init(metaready, PB);
+        mbar_init(xfull, 2); mbar_init(xpfull, 2); mbar_init(h2free, 1); mbar_init(xfree, 1); mbar_init(metaready, PB);
         fence_mbar_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -214,25 +220,35 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
         if (lane == 0) {
             const uint32_t n_chunks = (uint32_t)n_pairs * SCHED_P;
             uint32_t freed = 0, stage = 0;                          // chunks of completed stages / next stage to wait for
+            uint32_t grp = 0, left = 0;                             // release group of the chunk being produced / chunks left in it
             for (uint32_t produced = 0; produced < n_chunks; ++produced) {
                 while (produced - freed >= (uint32_t)NSP) {
                     const uint32_t k = stage % NSTG;
                     mbar_wait(&sfree[k], (stage / NSTG) & 1);
-                    freed += (k == 0 || k == 4) ? 5u : (k == 3 || k == 7 || k == 8) ? 1u : 4u;
+                    freed += group_chunks(k);
                     ++stage;
+                }
+                if (left == 0) {                                    // first chunk of a group: arm its barrier with the group's bytes
+                    left = group_chunks(grp);
+                    fence_proxy_async();                            // earlier generic-proxy reads of the ring slots precede the async-proxy overwrite
+                    mbar_expect_tx(&gfull[grp], left * (uint32_t)(HCH * 2));
                 }
                 int net, ch; sched_pair(produced % SCHED_P, net, ch);
                 const uint32_t slot = produced % NSP;
-                bulk_load(sStg + slot * HCH, (net ? P.wimg_e : P.wimg_t) + (size_t)ch * HCH, HCH * 2, &full[slot]);
+                bulk_copy(sStg + slot * HCH, (net ? P.wimg_e : P.wimg_t) + (size_t)ch * HCH, HCH * 2, &gfull[grp]);
+                if (--left == 0) grp = grp + 1 == NSTG ? 0 : grp + 1;
             }
         }
-    } else if (warp == 10) {
-        // =================================== row gatherer (TMA tile::gather4) ===================================
-        // Lane l owns rows 4 l .. 4 l + 3 of the pair (event l / 16): three gather4 per image (K blocks 0-2; columns 160-191 are
-        // out of bounds and land as zeros).  X' of pair p goes to the H2 region once pair p-1's dW2 / dH1 have completed, X of
-        // pair p to the X region once pair p-1's dW1 has completed.
+    } else if (warp >= 10) {
+        // =================================== row gatherers (TMA tile::gather4), two warps ===================================
+        // Lane l stands for rows 4 l .. 4 l + 3 of the pair (event l / 16).  An image is three K blocks x 32 row groups = 96 gather4
+        // (columns 160-191 are out of bounds and land as zeros); ptxas serialises the per-lane instructions of a warp, so the 96 are
+        // split over two warps: warp w takes K block w of every row group and K block 2 of the row groups (l / 16) == w.
+        // X' of pair p goes to the H2 region once pair p-1's dW2 / dH1 have completed, X of pair p to the X region once pair
+        // p-1's dW1 has completed.
         if (TMA) {
-            if (lane == 0) { tma::prefetch_map(&P.map_obs); tma::prefetch_map(&P.map_next); }
+            const int w = warp - 10;
+            if (lane == 0) tma::prefetch_map(w ? &P.map_obs : &P.map_next);
             for (int p = 0; p < n_pairs; ++p) {
                 const int buf = p & 1;
                 mbar_wait(metaready, p & 1);
@@ -240,16 +256,17 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
                 const int rb = (int)ringb[buf * 2 + (lane >> 4)];
                 const int4 i4 = *reinterpret_cast<const int4*>(ids + 4 * lane);
                 const int r0 = rb + i4.x, r1 = rb + i4.y, r2 = rb + i4.z, r3 = rb + i4.w;
+                const bool third = (lane >> 4) == w;
                 if (p > 0) mbar_wait(h2free, (p - 1) & 1);
-                if (lane == 0) mbar_expect_tx(xpfull, XIMG);
+                if (lane == 0) mbar_expect_tx(xpfull, XIMG / 2);
                 __syncwarp();
-#pragma unroll
-                for (int kb = 0; kb < 3; ++kb) tma::gather4(aH2 + kb * XBLK + lane * 512, &P.map_next, smem_u32(xpfull), kb * 64, r0, r1, r2, r3);
+                tma::gather4(aH2 + w * XBLK + lane * 512, &P.map_next, smem_u32(xpfull), w * 64, r0, r1, r2, r3);
+                if (third) tma::gather4(aH2 + 2 * XBLK + lane * 512, &P.map_next, smem_u32(xpfull), 128, r0, r1, r2, r3);
                 if (p > 0) mbar_wait(xfree, (p - 1) & 1);
-                if (lane == 0) mbar_expect_tx(xfull, XIMG);
+                if (lane == 0) mbar_expect_tx(xfull, XIMG / 2);
                 __syncwarp();
-#pragma unroll
-                for (int kb = 0; kb < 3; ++kb) tma::gather4(aX + kb * XBLK + lane * 512, &P.map_obs, smem_u32(xfull), kb * 64, r0, r1, r2, r3);
+                tma::gather4(aX + w * XBLK + lane * 512, &P.map_obs, smem_u32(xfull), w * 64, r0, r1, r2, r3);
+                if (third) tma::gather4(aX + 2 * XBLK + lane * 512, &P.map_obs, smem_u32(xfull), 128, r0, r1, r2, r3);
             }
         }
     } else if (warp == 9) {
@@ -261,15 +278,16 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
         const bool me = elect_one();
         const uint32_t T0 = __shfl_sync(0xffffffffu, *tmem_slot, 0), T_DW2 = T0 + 256;
         const int np_u = __shfl_sync(0xffffffffu, n_pairs, 0);
-        uint32_t consumed = 0, go_no = 0, stage = 0;
+        uint32_t consumed = 0, go_no = 0, stage = 0, wstage = 0;
         int itr_n = 0, itr_p = -1;
         auto istamp = [&]() { if (P.trace && blockIdx.x == 0 && me && itr_p == 3 && itr_n < 40) P.trace[64 + itr_n++] = clock64(); };
         auto wait_go = [&]() { mbar_wait(go, go_no & 1); ++go_no; fence_after(); istamp(); };
-        // all `n` chunks of a stage have landed (they are normally prefetched long before): its MMAs are then issued back to back
+        // all `n` chunks of the next release group have landed (one barrier per group; they are normally prefetched long before).
+        // The wait for a stage's first group is placed BEFORE the stage's wait_go, off the hand-over path.
         auto chunks_wait = [&](int n) -> uint32_t {
             const uint32_t first = consumed;
-            for (int c = 0; c < n; ++c) { const uint32_t k = consumed + c; mbar_wait(&full[k % NSP], (k / NSP) & 1); }
-            fence_after();
+            mbar_wait(&gfull[wstage % NSTG], (wstage / NSTG) & 1);
+            ++wstage;
             consumed += n;
             istamp();
             return first;
@@ -278,9 +296,8 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
         auto commit = [&](uint64_t* bar) { if (me) mma_commit(bar); };
         auto stage_free = [&]() { istamp(); commit(&sfree[stage % NSTG]); ++stage; };
         // L1: D[128 b][128 k1] = X[128][160] W1[128][160]^T -- 5 chunks [128 n][32 k], 2 k-steps each; X is a SWIZZLE_128B image
-        auto l1 = [&](uint32_t ax) {
+        auto l1 = [&](uint32_t ax, uint32_t k0) {
             const uint32_t id = idesc_h(128, 128, 0, 0);
-            const uint32_t k0 = chunks_wait(5);
 #pragma unroll 1
             for (int c = 0; c < 5; ++c) {
                 const uint64_t b = dk(chunk_addr(k0 + c), 32);
@@ -293,12 +310,12 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
             commit(doneL1);
         };
         // L2: D[128 b][256 n2] = H1[128][128] W2[256][128]^T -- 8 chunks [256 n][16 k]
-        auto l2 = [&]() {
+        auto l2 = [&](uint32_t k0) {
             const uint32_t id = idesc_h(128, 256, 0, 0);
             uint64_t a = dk(aH1, 128);
 #pragma unroll 1
             for (int hf = 0; hf < 2; ++hf) {
-                const uint32_t k0 = chunks_wait(4);
+                if (hf) k0 = chunks_wait(4);
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     if (me) mma_h(T0, a, dk(chunk_addr(k0 + c), 16), id, (hf | c) != 0);
@@ -309,9 +326,8 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
             commit(done);
         };
         // head: D[128 b][16] = H2[128][256] Wh[16][256]^T -- one chunk, 16 k-steps
-        auto head = [&]() {
+        auto head = [&](uint32_t k0) {
             const uint32_t id = idesc_h(128, 16, 0, 0);
-            const uint32_t k0 = chunks_wait(1);
             uint64_t a = dk(aH2, 256), b = dk(chunk_addr(k0), 256);
 #pragma unroll 1
             for (int ks = 0; ks < 16; ks += 4) {
@@ -326,19 +342,22 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
         };
         for (int p = 0; p < np_u; ++p) {
             itr_p = p;
+            uint32_t k0 = chunks_wait(5);                      // (the chunks of a stage are waited for BEFORE its go: off the hand-over path)
             wait_go();
             if (TMA) { mbar_wait(xpfull, p & 1); fence_after(); }
-            l1(aH2);                                           // target net: X' sits in the H2 region
-            wait_go(); l2();
-            wait_go(); head();                                 // target head, then the eval L1 (runs under the target head epilogue)
+            l1(aH2, k0);                                       // target net: X' sits in the H2 region
+            k0 = chunks_wait(4); wait_go(); l2(k0);
+            k0 = chunks_wait(1); wait_go(); head(k0);          // target head, then the eval L1 (runs under the target head epilogue)
+            k0 = chunks_wait(5);
             if (TMA) { mbar_wait(xfull, p & 1); fence_after(); }
-            l1(aX);
-            wait_go(); l2();
-            wait_go(); head();
+            l1(aX, k0);
+            k0 = chunks_wait(4); wait_go(); l2(k0);
+            k0 = chunks_wait(1); wait_go(); head(k0);
+            k0 = chunks_wait(1);
             wait_go();
             {   // dH2 half 0 (n2 < 128) -> columns 128..255: A = dOut [128][16], B = Wh^T chunk rows 0..127 [256 n2][16 j];
                 // dWh rows n2 in [128 m, +128) -> columns 16 m..: A = H2 read MN-major (M = n2 half), B = dOut read MN-major, K = 128 rows
-                const uint32_t wht = chunk_addr(chunks_wait(1));
+                const uint32_t wht = chunk_addr(k0);
                 const uint32_t id = idesc_h(128, 16, 1, 1);
                 if (me) mma_h(T0 + 128, dk(aD, 16), dk(wht, 16), idesc_h(128, 128, 0, 0), 0u);
 #pragma unroll 1
@@ -712,12 +731,13 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
                 for (int cb = 0; cb < 5; ++cb) tmem_ld16(T0 + t_lane + hh * 80 + cb * 16, v + cb * 16);
                 tmem_wait_ld();
                 if (more) go_signal();                              // -> next pair's target L1
-                float* gw = G + L::OFF_W1T + row * RL_K1 + hh * 80;
+                // slab layout [x / 4][k1][x % 4]: the 32 lanes of a red.v4 cover 512 contiguous bytes (16 sectors instead of 32)
+                float* gw = G + L::OFF_W1T + ((hh * 20) * 128 + row) * 4;
 #pragma unroll
                 for (int j = 0; j < 80; ++j) v[j] *= (1.0f / H_SCALE);
                 if (hh == 1) { acc_b1 += v[79]; v[79] = 0.f; }                  // (already unscaled)
 #pragma unroll
-                for (int j4 = 0; j4 < 20; ++j4) red_add4(gw + j4 * 4, v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                for (int j4 = 0; j4 < 20; ++j4) red_add4(gw + j4 * 512, v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
             }
         }
         if (n_pairs > 0) {
@@ -801,5 +821,5 @@ extern "C" int rl_brain_learn_p(const rl_world_cfg* cfg, const rl_rows_bufs* row
         for (int i = 0; i < 40 && h[64 + i]; ++i) fprintf(stderr, " %lld", h[64 + i] - h[0]);
         fprintf(stderr, "\n");
     }
-    return rl_learn_reduce(learn, P.ev_total, 1, (void*)st);
+    return rl_learn_reduce(learn, P.ev_total, 2, (void*)st);
 }
