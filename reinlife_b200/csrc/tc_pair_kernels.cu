@@ -66,7 +66,8 @@ constexpr int PO_RING = PO_META + 2 * 4 * 4 * PB;         // [2][2] ring base (e
 constexpr int PO_BARS = PO_RING + 2 * 2 * 8;
 constexpr int NSTG = 11;                 // ring release groups per pair: tL1 tL2a tL2b thead eL1 eL2a eL2b ehead dH2 dH1a dH1b
 constexpr int NBAR = 2 * NSTG + 8;       // gfull[NSTG] sfree[NSTG] + done doneL1 go xfull xpfull h2free xfree metaready
-constexpr size_t PAIR_SMEM = PO_BARS + 8 * NBAR + 16 + 1024;     // + alignment slack
+constexpr int PO_ONES = (PO_BARS + 8 * NBAR + 16 + 127) & ~127;   // [16 k][16] halves of 1.0: B operand of the db2 GEMM (every k-step reads it)
+constexpr size_t PAIR_SMEM = PO_ONES + 512 + 1024;               // + alignment slack
 static_assert(PAIR_SMEM <= 227 * 1024 && PO_BARS % 8 == 0 && PO_RING % 8 == 0 && PO_H2 % 1024 == 0, "shared memory budget");
 
 // interleaved no-swizzle fp16 image of width K: 8 rows x 16 bytes core matrices
@@ -103,9 +104,23 @@ __device__ __forceinline__ uint32_t pk(float a, float b) {      // one F2FP.PACK
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));     // upper half <- b, lower half <- a
     return r;
 }
-__device__ __forceinline__ float sat(float x) { return fminf(fmaxf(x, -60000.f), 60000.f); }
-__device__ __forceinline__ float hlo(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xFFFFu))); }
-__device__ __forceinline__ float hhi(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }
+// relu(a), relu(b) -> packed halves (F2FP.RELU); finite-saturating pack for the scaled backward operands (F2FP.SATFINITE)
+__device__ __forceinline__ uint32_t pk_relu(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ uint32_t pk_sat(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+// per half: v where h > 0, else 0 (ReLU derivative applied to a packed pair: HSET2.BF.GT + HMUL2)
+__device__ __forceinline__ uint32_t mask_pos(uint32_t v, uint32_t h) {
+    const __half2 m = __hgt2(*reinterpret_cast<const __half2*>(&h), __float2half2_rn(0.f));
+    const __half2 r = __hmul2(*reinterpret_cast<const __half2*>(&v), m);
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
 __device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -123,21 +138,6 @@ __device__ __forceinline__ void bulk_copy(void* dst, const void* src, uint32_t b
 __device__ __forceinline__ uint32_t group_chunks(uint32_t g) { return (g == 0 || g == 4) ? 5u : (g == 3 || g == 7 || g == 8) ? 1u : 4u; }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void head_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
-
-// Sum v[0..31] over the 32 lanes of the warp; lane L returns the total of element L (reduce-scatter, 31 shuffles).
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
-#pragma unroll
-    for (int w = 16; w >= 1; w >>= 1) {
-        const bool up = (lane & w) != 0;
-#pragma unroll
-        for (int k = 0; k < w; ++k) {
-            const float send = up ? v[k] : v[k + w];
-            const float keep = up ? v[k + w] : v[k];
-            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, w);
-        }
-    }
-    return v[0];
-}
 
 struct PairParams {
     CUtensorMap map_obs, map_next;       // float16 rings as [n_worlds * capacity][160] tensors (TMA = true only)
@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
     }
     if (warp == 8) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x < NEPI) {
+        reinterpret_cast<__half*>(smem + PO_ONES)[threadIdx.x] = __float2half_rn(1.0f);
         const float* Pe = P.lb.params; const float* Pt = P.lb.target;
         for (int i = threadIdx.x; i < 400; i += NEPI) {
             const int o = i < 128 ? L::OFF_B1 + i : i < 384 ? L::OFF_B2 + (i - 128) : L::OFF_BH + (i - 384);
@@ -210,10 +211,11 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
         }
         for (int i = threadIdx.x; i < L::N_TRAIN / 4; i += NEPI) reinterpret_cast<float4*>(G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    fence_proxy_async();
     fence_before();
     __syncthreads();
     fence_after();
-    const uint32_t aX = smem_u32(smem + PO_X), aH1 = smem_u32(sH1), aH2 = smem_u32(sH2), aD = smem_u32(sDout), aStg = smem_u32(sStg);
+    const uint32_t aX = smem_u32(smem + PO_X), aH1 = smem_u32(sH1), aH2 = smem_u32(sH2), aD = smem_u32(sDout), aStg = smem_u32(sStg), aOnes = smem_u32(smem + PO_ONES);
 
     if (warp == 8) {
         // =================================== weight-stream producer ===================================
@@ -355,11 +357,13 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
             k0 = chunks_wait(1); wait_go(); head(k0);
             k0 = chunks_wait(1);
             wait_go();
-            {   // dH2 half 0 (n2 < 128) -> columns 128..255: A = dOut [128][16], B = Wh^T chunk rows 0..127 [256 n2][16 j];
-                // dWh rows n2 in [128 m, +128) -> columns 16 m..: A = H2 read MN-major (M = n2 half), B = dOut read MN-major, K = 128 rows
+            {   // dH2 half 0 (n2 < 128) -> columns 128..255: A = dOut [128][16], B = Wh^T chunk rows 0..127 [256 n2][16 j]; handed
+                // over on its own so that its epilogue starts at once.  dWh (rows n2 in [128 m, +128) -> columns 16 m..: A = H2 read
+                // MN-major, B = dOut read MN-major, K = 128 rows) runs under that epilogue.
                 const uint32_t wht = chunk_addr(k0);
                 const uint32_t id = idesc_h(128, 16, 1, 1);
                 if (me) mma_h(T0 + 128, dk(aD, 16), dk(wht, 16), idesc_h(128, 128, 0, 0), 0u);
+                commit(done);
 #pragma unroll 1
                 for (int m = 0; m < 2; ++m) {
                     uint64_t a = dm(aH2 + m * 2048u, 256), b = dm(aD, 16);
@@ -373,37 +377,53 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
                     }
                 }
                 commit(done);
-                wait_go();                                     // dWh drained: dH2 half 1 (n2 >= 128) -> columns 0..127
+                wait_go();                                     // dH2[:, :128] stored, dWh drained: dH2 half 1 (n2 >= 128) -> columns 0..127
                 if (me) mma_h(T0, dk(aD, 16), dk(wht + 4096u, 16), idesc_h(128, 128, 0, 0), 0u);
                 stage_free();
                 commit(done);
             }
-            wait_go();
-            {   // dW2[k1][n2] += sum_b H1[b][k1] dH2[b][n2] first (no weights: the last W2^T chunks get more time to land): both
-                // images read MN-major, accumulator resident in TMEM
-                const uint32_t id2 = idesc_h(128, 256, 1, 1);
-                uint64_t a2 = dm(aH1, 128), b2 = dm(aH2, 256);
+            const uint32_t id_w2 = idesc_h(128, 128, 1, 1), id_h1 = idesc_h(128, 128, 0, 0);
+            uint64_t a_h1 = dk(aH2, 256);
+#pragma unroll 1
+            for (int hf = 0; hf < 2; ++hf) {
+                // The n2 half `hf` of dH2 is in place.  Under the epilogue of the other half (hf = 0) / at the end (hf = 1):
+                // dW2[k1][n2 half] += sum_b H1[b][k1] dH2[b][n2] (both images MN-major, accumulator resident in TMEM) and the k-steps
+                // n2 in [128 hf, +128) of dH1[128 b][128 k1] = dH2[128][256] W2^T[128 k1][256 n2]^T (4 chunks [128][32], 2 k-steps each,
+                // accumulator columns 128..255: dH2 half 0 has been drained from them)
+                if (hf) wait_go();
+                uint64_t a2 = dm(aH1, 128), b2 = dm(aH2 + hf * 2048u, 256);
 #pragma unroll 1
                 for (int ks = 0; ks < 8; ks += 4) {
                     if (me) {
-                        mma_h(T_DW2, a2, b2, id2, (p != 0 || ks != 0) ? 1u : 0u); mma_h(T_DW2, a2 + 256u, b2 + 512u, id2, 1u);
-                        mma_h(T_DW2, a2 + 512u, b2 + 1024u, id2, 1u); mma_h(T_DW2, a2 + 768u, b2 + 1536u, id2, 1u);
+                        mma_h(T_DW2 + 128 * hf, a2, b2, id_w2, (p != 0 || ks != 0) ? 1u : 0u); mma_h(T_DW2 + 128 * hf, a2 + 256u, b2 + 512u, id_w2, 1u);
+                        mma_h(T_DW2 + 128 * hf, a2 + 512u, b2 + 1024u, id_w2, 1u); mma_h(T_DW2 + 128 * hf, a2 + 768u, b2 + 1536u, id_w2, 1u);
                     }
                     a2 += 1024u; b2 += 2048u;
                 }
-                // dH1[128 b][128 k1] = dH2[128][256] W2^T[128 k1][256 n2]^T: 8 chunks [128][32], 2 k-steps each
-                const uint32_t id = idesc_h(128, 128, 0, 0);
-                uint64_t a = dk(aH2, 256);
+                const uint32_t kc = chunks_wait(4);
 #pragma unroll 1
-                for (int hf = 0; hf < 2; ++hf) {
-                    const uint32_t k0 = chunks_wait(4);
+                for (int c = 0; c < 4; ++c) {
+                    const uint64_t b = dk(chunk_addr(kc + c), 32);
+                    if (me) { mma_h(T0 + 128, a_h1, b, id_h1, (hf | c) != 0); mma_h(T0 + 128, a_h1 + 16u, b + 16u, id_h1, 1u); }
+                    a_h1 += 32u;
+                }
+                stage_free();
+            }
+            {   // db2[n2] = sum_b dH2[b][n2] as a GEMM with a block of ones: A = dH2 read MN-major (M = n2 half m), B = ones [16 k][16]
+                // (the same 512 bytes for every k-step) -> columns 16 m.. (all 16 equal); replaces 62 shuffles per 64 columns
+                const uint32_t id = idesc_h(128, 16, 1, 1);
+                const uint64_t b = dm(aOnes, 16);
 #pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {
-                        const uint64_t b = dk(chunk_addr(k0 + c), 32);
-                        if (me) { mma_h(T0, a, b, id, (hf | c) != 0); mma_h(T0, a + 16u, b + 16u, id, 1u); }
-                        a += 32u;
+                for (int m = 0; m < 2; ++m) {
+                    uint64_t a = dm(aH2 + m * 2048u, 256);
+#pragma unroll 1
+                    for (int ks = 0; ks < 8; ks += 4) {
+                        if (me) {
+                            mma_h(T0 + 16 * m, a, b, id, ks != 0); mma_h(T0 + 16 * m, a + 512u, b, id, 1u);
+                            mma_h(T0 + 16 * m, a + 1024u, b, id, 1u); mma_h(T0 + 16 * m, a + 1536u, b, id, 1u);
+                        }
+                        a += 2048u;
                     }
-                    stage_free();
                 }
                 commit(done);
                 if (TMA) commit(h2free);                       // dH2 is dead: the next pair's target rows may land in the H2 region
@@ -507,15 +527,12 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
         // relu(D + bias) of 32 accumulator columns -> 4 x 16-byte stores into a batch-major image of width K
         auto relu_store32 = [&](float (&v)[32], const float* bias, __half* img, int c0, int K) {
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 b = *reinterpret_cast<const float4*>(bias + j4 * 4);
-                v[j4 * 4] = fmaxf(v[j4 * 4] + b.x, 0.f); v[j4 * 4 + 1] = fmaxf(v[j4 * 4 + 1] + b.y, 0.f);
-                v[j4 * 4 + 2] = fmaxf(v[j4 * 4 + 2] + b.z, 0.f); v[j4 * 4 + 3] = fmaxf(v[j4 * 4 + 3] + b.w, 0.f);
-            }
-#pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8)
+            for (int j8 = 0; j8 < 4; ++j8) {
+                const float4 b0 = *reinterpret_cast<const float4*>(bias + j8 * 8), b1 = *reinterpret_cast<const float4*>(bias + j8 * 8 + 4);
                 *reinterpret_cast<uint4*>(img + himg(row, c0 + j8 * 8, K)) =
-                    make_uint4(pk(v[j8 * 8], v[j8 * 8 + 1]), pk(v[j8 * 8 + 2], v[j8 * 8 + 3]), pk(v[j8 * 8 + 4], v[j8 * 8 + 5]), pk(v[j8 * 8 + 6], v[j8 * 8 + 7]));
+                    make_uint4(pk_relu(v[j8 * 8] + b0.x, v[j8 * 8 + 1] + b0.y), pk_relu(v[j8 * 8 + 2] + b0.z, v[j8 * 8 + 3] + b0.w),
+                               pk_relu(v[j8 * 8 + 4] + b1.x, v[j8 * 8 + 5] + b1.y), pk_relu(v[j8 * 8 + 6] + b1.z, v[j8 * 8 + 7] + b1.w));
+            }
         };
         // ---- L1 epilogue: this thread's row, columns [64 hh, 64 hh + 64) of the accumulator at TMEM columns 128..255 ----
         auto l1_epilogue = [&](const float* bias) {
@@ -559,8 +576,8 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
         };
 
         // gradients whose owner (thread, element) is the same in every pair are summed in registers and leave once per CTA:
-        // dWh row n2 = 128 hh + row (9), db2 of the four columns this lane receives from the reduce-scatters, dbh[lane], db1[row]
-        float acc_wh[9], acc_b2[4] = {0.f, 0.f, 0.f, 0.f}, acc_bh = 0.f, acc_b1 = 0.f;
+        // dWh row n2 = 128 hh + row (9), db2[n2] of the same row (column 0 of the ones GEMM), dbh[lane], db1[row]
+        float acc_wh[9], acc_b2 = 0.f, acc_bh = 0.f, acc_b1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 9; ++j) acc_wh[j] = 0.f;
         if (n_pairs > 0) {
@@ -638,7 +655,7 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
                 for (int j = 0; j < 16; ++j) d[j] = j < 8 ? ((j == a ? g : 0.f) - shift) : (j == 8 ? g : 0.f);
                 uint32_t w[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) w[j] = pk(sat(d[2 * j] * H_SCALE), sat(d[2 * j + 1] * H_SCALE));
+                for (int j = 0; j < 8; ++j) w[j] = pk_sat(d[2 * j] * H_SCALE, d[2 * j + 1] * H_SCALE);
                 *reinterpret_cast<uint4*>(sDout + himg(row, 0, 16)) = make_uint4(w[0], w[1], w[2], w[3]);
                 *reinterpret_cast<uint4*>(sDout + himg(row, 8, 16)) = make_uint4(w[4], w[5], w[6], w[7]);
 #pragma unroll
@@ -649,76 +666,58 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
                     dbh = lane == j ? s : dbh;
                 }
             }
-            go_signal();                                            // -> dH2 half 0 + dWh
+            go_signal();                                            // -> dH2 half 0, dWh
             acc_bh += dbh;
-            wait_done();
-            float wv[16];
-            tmem_ld16(T0 + t_lane + 16 * hh, wv);                   // head weight gradients: row n2 = 128 hh + this thread's TMEM lane
-            tmem_wait_ld();
-            go_signal();                                            // -> dH2 half 1 (its accumulator overwrites the dWh columns)
-#pragma unroll
-            for (int j = 0; j < 9; ++j) acc_wh[j] += wv[j];
-            // ---- dH2 epilogue, two halves of 128 features: mask by H2 > 0, dH2 in place of H2, db2 by warp reduce-scatter ----
-            float cs[4];
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                if (half == 1) wait_done();
-                const uint32_t tcol = half == 0 ? 128u : 0u;
-                const int c0 = hh * 64;                               // first column within the half
-                const int n0 = half * 128 + c0;                       // feature n2 of va[0]
+            // ---- dH2 epilogue, two halves of 128 features: dH2 = H2 > 0 ? acc : 0 (packed: F2FP.SATFINITE, HSET2, HMUL2), in place of H2 ----
+            auto dh2_epilogue = [&](uint32_t tcol, int n0) {           // this thread's row, 64 columns: accumulator tcol.., features n0..
                 float va[32], vb[32];
-                tmem_ld32(T0 + t_lane + tcol + c0, va);
-                tmem_ld32(T0 + t_lane + tcol + c0 + 32, vb);
+                tmem_ld32(T0 + t_lane + tcol, va);
+                tmem_ld32(T0 + t_lane + tcol + 32, vb);
                 uint4 hm[8];
 #pragma unroll
                 for (int j8 = 0; j8 < 8; ++j8) hm[j8] = *reinterpret_cast<const uint4*>(sH2 + himg(row, n0 + j8 * 8, 256));
                 tmem_wait_ld();
-                auto mask_store = [&](float (&v)[32], const int hb, int nb) {      // 32 columns: dH2 = H2 > 0 ? acc : 0, in place
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        const uint4 h4 = hm[hb + j8];
-                        const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w};
-                        uint32_t ow[4];
+                for (int j8 = 0; j8 < 8; ++j8) {
+                    const float* v = j8 < 4 ? va + j8 * 8 : vb + (j8 - 4) * 8;
+                    *reinterpret_cast<uint4*>(sH2 + himg(row, n0 + j8 * 8, 256)) =
+                        make_uint4(mask_pos(pk_sat(v[0], v[1]), hm[j8].x), mask_pos(pk_sat(v[2], v[3]), hm[j8].y),
+                                   mask_pos(pk_sat(v[4], v[5]), hm[j8].z), mask_pos(pk_sat(v[6], v[7]), hm[j8].w));
+                }
+            };
+            wait_done();                                            // dH2 half 0
+            dh2_epilogue(128u + hh * 64, hh * 64);
+            wait_done();                                            // dWh (ran under the epilogue above)
+            float wv[16];
+            tmem_ld16(T0 + t_lane + 16 * hh, wv);                   // head weight gradients: row n2 = 128 hh + this thread's TMEM lane
+            tmem_wait_ld();
+            go_signal();                                            // -> dH2 half 1 (its accumulator overwrites the dWh columns); dW2 / dH1 over n2 < 128
 #pragma unroll
-                        for (int p2 = 0; p2 < 4; ++p2) {
-                            const int j = j8 * 8 + p2 * 2;
-                            v[j] = hlo(hw[p2]) > 0.f ? sat(v[j]) : 0.f;
-                            v[j + 1] = hhi(hw[p2]) > 0.f ? sat(v[j + 1]) : 0.f;
-                            ow[p2] = pk(v[j], v[j + 1]);
-                        }
-                        *reinterpret_cast<uint4*>(sH2 + himg(row, nb + j8 * 8, 256)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                    }
-                };
-                mask_store(va, 0, n0);
-                mask_store(vb, 4, n0 + 32);
-                cs[half * 2] = warp_colsum32(va, lane);
-                cs[half * 2 + 1] = warp_colsum32(vb, lane);
-            }
-            go_signal();                                            // -> dH1, dW2
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc_b2[k] += cs[k];
+            for (int j = 0; j < 9; ++j) acc_wh[j] += wv[j];
+            wait_done();                                            // dH2 half 1
+            dh2_epilogue(hh * 64, 128 + hh * 64);
+            go_signal();                                            // -> dW2 / dH1 over n2 >= 128, db2
             if (!TMA && more) epi_bar();                            // the next pair's metadata (threads 0-127) is visible to every warp
             wait_done();
             if (more) gather_load(P.rp.next_obs, buf ^ 1);          // (float32 rings: next pair's target rows, in flight behind the dH1 epilogue)
-            {   // dH1 epilogue: this thread's row, columns [64 hh, +64): mask by H1 > 0, dH1 in place of H1
+            {   // db2 of feature n2 = 128 hh + row, then the dH1 epilogue: this thread's row, columns [64 hh, +64) of the accumulator at
+                // TMEM columns 128..255: dH1 = H1 > 0 ? acc : 0 in place of H1
                 const int c0 = hh * 64;
-                float v0[32], v1[32];
-                tmem_ld32(T0 + t_lane + c0, v0);
-                tmem_ld32(T0 + t_lane + c0 + 32, v1);
+                float v0[32], v1[32], b2v[16];
+                tmem_ld16(T0 + t_lane + 16 * hh, b2v);
+                tmem_ld32(T0 + t_lane + 128 + c0, v0);
+                tmem_ld32(T0 + t_lane + 128 + c0 + 32, v1);
+                uint4 hm[8];
+#pragma unroll
+                for (int j8 = 0; j8 < 8; ++j8) hm[j8] = *reinterpret_cast<const uint4*>(sH1 + himg(row, c0 + j8 * 8, 128));
                 tmem_wait_ld();
+                acc_b2 += b2v[0];
 #pragma unroll
                 for (int j8 = 0; j8 < 8; ++j8) {
-                    uint4* ph = reinterpret_cast<uint4*>(sH1 + himg(row, c0 + j8 * 8, 128));
-                    const uint4 h4 = *ph;
-                    const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w};
-                    uint32_t ow[4];
-#pragma unroll
-                    for (int p2 = 0; p2 < 4; ++p2) {
-                        const int j = (j8 & 3) * 8 + p2 * 2;
-                        const float x0 = j8 < 4 ? v0[j] : v1[j], x1 = j8 < 4 ? v0[j + 1] : v1[j + 1];
-                        ow[p2] = pk(hlo(hw[p2]) > 0.f ? sat(x0) : 0.f, hhi(hw[p2]) > 0.f ? sat(x1) : 0.f);
-                    }
-                    *ph = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    const float* v = j8 < 4 ? v0 + j8 * 8 : v1 + (j8 - 4) * 8;
+                    *reinterpret_cast<uint4*>(sH1 + himg(row, c0 + j8 * 8, 128)) =
+                        make_uint4(mask_pos(pk_sat(v[0], v[1]), hm[j8].x), mask_pos(pk_sat(v[2], v[3]), hm[j8].y),
+                                   mask_pos(pk_sat(v[4], v[5]), hm[j8].z), mask_pos(pk_sat(v[6], v[7]), hm[j8].w));
                 }
             }
             if (more) gather_store(PO_H2);                          // (float32 rings) X' of the next pair -> H2 region: dH2 is dead (dW2 / dH1 done)
@@ -746,8 +745,7 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
             const int n2 = hh * 128 + row;
 #pragma unroll
             for (int j = 0; j < 9; ++j) G[L::OFF_WH + n2 * 9 + j] = acc_wh[j] * (1.0f / H_SCALE);          // sole owner of the row
-#pragma unroll
-            for (int k = 0; k < 4; ++k) red_add(G + L::OFF_B2 + (k >> 1) * 128 + hh * 64 + (k & 1) * 32 + lane, acc_b2[k] * (1.0f / H_SCALE));
+            G[L::OFF_B2 + n2] = acc_b2 * (1.0f / H_SCALE);                                               // sole owner
             if (hh == 0 && lane < 9) red_add(G + L::OFF_BH + lane, acc_bh);
             if (hh == 1) G[L::OFF_B1 + row] = acc_b1;
         }
