@@ -42,7 +42,8 @@ using mlp::mbar_init; using mlp::mbar_wait; using mlp::fence_mbar_init; using ml
 constexpr int R = 64;                    // rows per event
 constexpr int PB = 128;                  // rows per pair
 constexpr int NEPI = 256;                // epilogue threads (warps 0-7)
-constexpr int NTH = NEPI + 128;          // + weight producer (warp 8) + MMA issuer (warp 9) + two row gatherers (warps 10, 11)
+constexpr int NTH = NEPI + 64;           // + weight producer (warp 8) + MMA issuer (warp 9)
+constexpr int NGW = 4;                   // + row gatherer warps 10.. (TMA = true only)
 constexpr int NSP = 8;                   // weight-chunk ring slots of 8 KB
 constexpr int HCH = 4096;                // halves per weight chunk
 constexpr float H_SCALE = 256.0f;        // backward operands are scaled by 2^8 (exact), removed when gradients leave TMEM
@@ -164,7 +165,7 @@ __device__ __forceinline__ void sched_pair(int i, int& net, int& chunk) {
 }
 
 template <bool TMA>
-__global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constant__ PairParams P) {
+__global__ void __launch_bounds__(NTH + (TMA ? 32 * NGW : 0), 1) k_learn_dueling_p(const __grid_constant__ PairParams P) {
     using L = Layout<RL_MODEL_DUELING>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // SWIZZLE_128B atoms are 1024-byte aligned
@@ -192,12 +193,13 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
     const int total = *P.ev_total;
     const int n_my = total > (int)blockIdx.x ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int n_pairs = (n_my + 1) >> 1;
+    const long long t_cta0 = clock64();
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTG; ++i) mbar_init(&gfull[i], 1);
         for (int i = 0; i < NSTG; ++i) mbar_init(&sfree[i], 1);
         mbar_init(done, 1); mbar_init(doneL1, 1); mbar_init(go, NEPI);
-        mbar_init(xfull, 2); mbar_init(xpfull, 2); mbar_init(h2free, 1); mbar_init(xfree, 1); mbar_init(metaready, PB);
+        mbar_init(xfull, NGW); mbar_init(xpfull, NGW); mbar_init(h2free, 1); mbar_init(xfree, 1); mbar_init(metaready, PB);
         fence_mbar_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -242,33 +244,42 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
             }
         }
     } else if (warp >= 10) {
-        // =================================== row gatherers (TMA tile::gather4), two warps ===================================
-        // Lane l stands for rows 4 l .. 4 l + 3 of the pair (event l / 16).  An image is three K blocks x 32 row groups = 96 gather4
-        // (columns 160-191 are out of bounds and land as zeros); ptxas serialises the per-lane instructions of a warp, so the 96 are
-        // split over two warps: warp w takes K block w of every row group and K block 2 of the row groups (l / 16) == w.
-        // X' of pair p goes to the H2 region once pair p-1's dW2 / dH1 have completed, X of pair p to the X region once pair
-        // p-1's dW1 has completed.
+        // =================================== row gatherers (TMA tile::gather4), NGW warps ===================================
+        // An image is 32 row groups (4 rows each) x three K blocks = 96 gather4 (columns 160-191 are out of bounds and land as
+        // zeros).  A gather4 costs its issuing warp ~100 cycles (scripts trace: 48 per warp took 5 k cycles, the rows land ~350
+        // cycles after the last one is issued), so the 96 are spread over NGW warps: warp w takes the row groups g = w (mod NGW),
+        // lanes 0..23 of it one (row group, K block) each.  X' of pair p goes to the H2 region once pair p-1's dW2 / dH1 / db2
+        // have completed, X of pair p to the X region once pair p-1's dW1 has completed.
         if (TMA) {
             const int w = warp - 10;
-            if (lane == 0) tma::prefetch_map(w ? &P.map_obs : &P.map_next);
+            const int g = (lane >> 2) * NGW + w, kb = lane & 3;        // lanes with kb == 3 or g >= 32 idle
+            const bool act = kb < 3 && g < 32;
+            if (lane == 0) tma::prefetch_map(w & 1 ? &P.map_obs : &P.map_next);
             for (int p = 0; p < n_pairs; ++p) {
                 const int buf = p & 1;
                 mbar_wait(metaready, p & 1);
                 const int* ids = meta + buf * 4 * PB;
-                const int rb = (int)ringb[buf * 2 + (lane >> 4)];
-                const int4 i4 = *reinterpret_cast<const int4*>(ids + 4 * lane);
-                const int r0 = rb + i4.x, r1 = rb + i4.y, r2 = rb + i4.z, r3 = rb + i4.w;
-                const bool third = (lane >> 4) == w;
+                int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+                if (act) {
+                    const int rb = (int)ringb[buf * 2 + (g >> 4)];
+                    const int4 i4 = *reinterpret_cast<const int4*>(ids + 4 * g);
+                    r0 = rb + i4.x; r1 = rb + i4.y; r2 = rb + i4.z; r3 = rb + i4.w;
+                }
                 if (p > 0) mbar_wait(h2free, (p - 1) & 1);
-                if (lane == 0) mbar_expect_tx(xpfull, XIMG / 2);
+                const long long tg0 = clock64();
+                if (lane == 0) mbar_expect_tx(xpfull, XIMG / NGW);
                 __syncwarp();
-                tma::gather4(aH2 + w * XBLK + lane * 512, &P.map_next, smem_u32(xpfull), w * 64, r0, r1, r2, r3);
-                if (third) tma::gather4(aH2 + 2 * XBLK + lane * 512, &P.map_next, smem_u32(xpfull), 128, r0, r1, r2, r3);
+                if (act) tma::gather4(aH2 + kb * XBLK + g * 512, &P.map_next, smem_u32(xpfull), kb * 64, r0, r1, r2, r3);
+                __syncwarp();
+                if (P.trace && blockIdx.x == 0 && p == 4 && lane == 0 && w < 2) {       // (pair 4's rows are gathered during pair 3)
+                    P.trace[110 + 4 * w] = tg0; P.trace[111 + 4 * w] = clock64();
+                    mbar_wait(xpfull, p & 1);
+                    P.trace[112 + 4 * w] = clock64();
+                }
                 if (p > 0) mbar_wait(xfree, (p - 1) & 1);
-                if (lane == 0) mbar_expect_tx(xfull, XIMG / 2);
+                if (lane == 0) mbar_expect_tx(xfull, XIMG / NGW);
                 __syncwarp();
-                tma::gather4(aX + w * XBLK + lane * 512, &P.map_obs, smem_u32(xfull), w * 64, r0, r1, r2, r3);
-                if (third) tma::gather4(aX + 2 * XBLK + lane * 512, &P.map_obs, smem_u32(xfull), 128, r0, r1, r2, r3);
+                if (act) tma::gather4(aX + kb * XBLK + g * 512, &P.map_obs, smem_u32(xfull), kb * 64, r0, r1, r2, r3);
             }
         }
     } else if (warp == 9) {
@@ -765,6 +776,7 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dueling_p(const __grid_constan
     }
     fence_before();
     __syncthreads();
+    if (P.trace && threadIdx.x == 0 && blockIdx.x < 160) { P.trace[128 + 2 * blockIdx.x] = clock64() - t_cta0; P.trace[129 + 2 * blockIdx.x] = n_pairs; }
     if (warp == 8) tmem_dealloc(*tmem_slot, 512);
 }
 
@@ -796,8 +808,8 @@ extern "C" int rl_brain_learn_p(const rl_world_cfg* cfg, const rl_rows_bufs* row
     static long long* trace_dev = nullptr;
     const bool tracing = getenv("RL_TC_TRACE") != nullptr;
     if (tracing) {
-        if (!trace_dev) RL_CUDA_CHECK(cudaMalloc(&trace_dev, 128 * sizeof(long long)));
-        RL_CUDA_CHECK(cudaMemset(trace_dev, 0, 128 * sizeof(long long)));
+        if (!trace_dev) RL_CUDA_CHECK(cudaMalloc(&trace_dev, 512 * sizeof(long long)));
+        RL_CUDA_CHECK(cudaMemset(trace_dev, 0, 512 * sizeof(long long)));
         P.trace = trace_dev;
     }
     static PerDeviceOnce attr;
@@ -806,18 +818,21 @@ extern "C" int rl_brain_learn_p(const rl_world_cfg* cfg, const rl_rows_bufs* row
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dueling_p<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM));
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (use_tma) k_learn_dueling_p<true><<<rl_learn_grid(), NTH, PAIR_SMEM, st>>>(P);
+    if (use_tma) k_learn_dueling_p<true><<<rl_learn_grid(), NTH + 32 * NGW, PAIR_SMEM, st>>>(P);
     else k_learn_dueling_p<false><<<rl_learn_grid(), NTH, PAIR_SMEM, st>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
     if (tracing) {
-        long long h[128];
+        long long h[512];
         RL_CUDA_CHECK(cudaStreamSynchronize(st));
         RL_CUDA_CHECK(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
         fprintf(stderr, "[pair trace] epilogue stamps (cycles since the pair's start):");
         for (int i = 1; i < 40 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
         fprintf(stderr, "\n[pair trace] issuer stamps (go seen / chunks landed / last MMA of a chunk stage issued):");
         for (int i = 0; i < 40 && h[64 + i]; ++i) fprintf(stderr, " %lld", h[64 + i] - h[0]);
-        fprintf(stderr, "\n");
+        long long cmin = 1ll << 60, cmax = 0, csum = 0; int nc = 0;
+        for (int c = 0; c < 160; ++c) if (h[128 + 2 * c]) { const long long v = h[128 + 2 * c]; cmin = v < cmin ? v : cmin; cmax = v > cmax ? v : cmax; csum += v; ++nc; }
+        fprintf(stderr, "\n[pair trace] cycles per CTA: min %lld avg %lld max %lld over %d CTAs; CTA 0: %lld cycles, %lld pairs\n", cmin, nc ? csum / nc : 0, cmax, nc,
+                h[128], h[129]);
     }
     return rl_learn_reduce(learn, P.ev_total, 2, (void*)st);
 }
