@@ -43,7 +43,13 @@ constexpr int R = 64;                    // rows per event
 constexpr int PB = 128;                  // rows per pair
 constexpr int NEPI = 256;                // epilogue threads (warps 0-7)
 constexpr int NTH = NEPI + 64;           // + weight producer (warp 8) + MMA issuer (warp 9)
-constexpr int NGW = 4;                   // + row gatherer warps 10.. (TMA = true only)
+constexpr int NGW = 4;                   // TMA = true: + warps 10, 11 (idle: they complete warpgroup 2) + NGW accumulator / row-gatherer warps 12..
+constexpr int NTH_TMA = NEPI + 128 + 32 * NGW;
+// register budget of the TMA variant (setmaxnreg, per warpgroup of 4 warps): 512 threads are launched with 128 registers each (the pool
+// setmaxnreg redistributes is the CTA's launch allocation); the epilogue warpgroups 0-1 keep them, warpgroup 2 (producer, issuer) shrinks
+// to REG_AUX, the accumulator warpgroup 3 grows to REG_ACC
+constexpr int REG_EPI = 128, REG_AUX = 40, REG_ACC = 216;
+static_assert(256 * REG_EPI + 128 * REG_AUX + 32 * NGW * REG_ACC <= NTH_TMA * 128, "register pool of the launch");
 constexpr int NSP = 8;                   // weight-chunk ring slots of 8 KB
 constexpr int HCH = 4096;                // halves per weight chunk
 constexpr float H_SCALE = 256.0f;        // backward operands are scaled by 2^8 (exact), removed when gradients leave TMEM
@@ -66,7 +72,7 @@ constexpr int PO_META = PO_RED + 4 * 64;                  // [2] x { idx[128] ac
 constexpr int PO_RING = PO_META + 2 * 4 * 4 * PB;         // [2][2] ring base (elements) per buffer / event, 64-bit
 constexpr int PO_BARS = PO_RING + 2 * 2 * 8;
 constexpr int NSTG = 11;                 // ring release groups per pair: tL1 tL2a tL2b thead eL1 eL2a eL2b ehead dH2 dH1a dH1b
-constexpr int NBAR = 2 * NSTG + 8;       // gfull[NSTG] sfree[NSTG] + done doneL1 go xfull xpfull h2free xfree metaready
+constexpr int NBAR = 2 * NSTG + 10;      // gfull[NSTG] sfree[NSTG] + done doneL1 go xfull xpfull h2free xfree metaready w1a w1b
 constexpr int PO_ONES = (PO_BARS + 8 * NBAR + 16 + 127) & ~127;   // [16 k][16] halves of 1.0: B operand of the db2 GEMM (every k-step reads it)
 constexpr size_t PAIR_SMEM = PO_ONES + 512 + 1024;               // + alignment slack
 static_assert(PAIR_SMEM <= 227 * 1024 && PO_BARS % 8 == 0 && PO_RING % 8 == 0 && PO_H2 % 1024 == 0, "shared memory budget");
@@ -165,7 +171,7 @@ __device__ __forceinline__ void sched_pair(int i, int& net, int& chunk) {
 }
 
 template <bool TMA>
-__global__ void __launch_bounds__(NTH + (TMA ? 32 * NGW : 0), 1) k_learn_dueling_p(const __grid_constant__ PairParams P) {
+__global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(const __grid_constant__ PairParams P) {
     using L = Layout<RL_MODEL_DUELING>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // SWIZZLE_128B atoms are 1024-byte aligned
@@ -186,6 +192,8 @@ __global__ void __launch_bounds__(NTH + (TMA ? 32 * NGW : 0), 1) k_learn_dueling
     // xfull / xpfull: the gathered eval / target rows of a pair have landed; h2free / xfree: the MMAs that read the H2 / X region
     // have completed (tcgen05.commit): the next pair's rows may be gathered into it; metaready: the ring positions of a pair are in `meta`
     uint64_t* xfull = done + 3; uint64_t* xpfull = done + 4; uint64_t* h2free = done + 5; uint64_t* xfree = done + 6; uint64_t* metaready = done + 7;
+    // w1a / w1b: the accumulator warps have taken columns 128..159 / 0..127 of the dW1 accumulator out of TMEM (gate the next target L1 / L2)
+    uint64_t* w1a = done + 8; uint64_t* w1b = done + 9;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -199,7 +207,7 @@ __global__ void __launch_bounds__(NTH + (TMA ? 32 * NGW : 0), 1) k_learn_dueling
         for (int i = 0; i < NSTG; ++i) mbar_init(&gfull[i], 1);
         for (int i = 0; i < NSTG; ++i) mbar_init(&sfree[i], 1);
         mbar_init(done, 1); mbar_init(doneL1, 1); mbar_init(go, NEPI);
-        mbar_init(xfull, NGW); mbar_init(xpfull, NGW); mbar_init(h2free, 1); mbar_init(xfree, 1); mbar_init(metaready, PB);
+        mbar_init(xfull, NGW); mbar_init(xpfull, NGW); mbar_init(h2free, 1); mbar_init(xfree, 1); mbar_init(metaready, PB); mbar_init(w1a, 32 * NGW); mbar_init(w1b, 32 * NGW);
         fence_mbar_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -219,7 +227,11 @@ __global__ void __launch_bounds__(NTH + (TMA ? 32 * NGW : 0), 1) k_learn_dueling
     fence_after();
     const uint32_t aX = smem_u32(smem + PO_X), aH1 = smem_u32(sH1), aH2 = smem_u32(sH2), aD = smem_u32(sDout), aStg = smem_u32(sStg), aOnes = smem_u32(smem + PO_ONES);
 
-    if (warp == 8) {
+    // (setmaxnreg is the first instruction of each role branch -- one per warpgroup, no control-flow merge behind it -- so that ptxas
+    //  allocates each role's code against its own budget)
+    if (warp >= 8 && warp < 12) {
+      if (TMA) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_AUX));
+      if (warp == 8) {
         // =================================== weight-stream producer ===================================
         if (lane == 0) {
             const uint32_t n_chunks = (uint32_t)n_pairs * SCHED_P;
@@ -243,46 +255,7 @@ __global__ void __launch_bounds__(NTH + (TMA ? 32 * NGW : 0), 1) k_learn_dueling
                 if (--left == 0) grp = grp + 1 == NSTG ? 0 : grp + 1;
             }
         }
-    } else if (warp >= 10) {
-        // =================================== row gatherers (TMA tile::gather4), NGW warps ===================================
-        // An image is 32 row groups (4 rows each) x three K blocks = 96 gather4 (columns 160-191 are out of bounds and land as
-        // zeros).  A gather4 costs its issuing warp ~100 cycles (scripts trace: 48 per warp took 5 k cycles, the rows land ~350
-        // cycles after the last one is issued), so the 96 are spread over NGW warps: warp w takes the row groups g = w (mod NGW),
-        // lanes 0..23 of it one (row group, K block) each.  X' of pair p goes to the H2 region once pair p-1's dW2 / dH1 / db2
-        // have completed, X of pair p to the X region once pair p-1's dW1 has completed.
-        if (TMA) {
-            const int w = warp - 10;
-            const int g = (lane >> 2) * NGW + w, kb = lane & 3;        // lanes with kb == 3 or g >= 32 idle
-            const bool act = kb < 3 && g < 32;
-            if (lane == 0) tma::prefetch_map(w & 1 ? &P.map_obs : &P.map_next);
-            for (int p = 0; p < n_pairs; ++p) {
-                const int buf = p & 1;
-                mbar_wait(metaready, p & 1);
-                const int* ids = meta + buf * 4 * PB;
-                int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-                if (act) {
-                    const int rb = (int)ringb[buf * 2 + (g >> 4)];
-                    const int4 i4 = *reinterpret_cast<const int4*>(ids + 4 * g);
-                    r0 = rb + i4.x; r1 = rb + i4.y; r2 = rb + i4.z; r3 = rb + i4.w;
-                }
-                if (p > 0) mbar_wait(h2free, (p - 1) & 1);
-                const long long tg0 = clock64();
-                if (lane == 0) mbar_expect_tx(xpfull, XIMG / NGW);
-                __syncwarp();
-                if (act) tma::gather4(aH2 + kb * XBLK + g * 512, &P.map_next, smem_u32(xpfull), kb * 64, r0, r1, r2, r3);
-                __syncwarp();
-                if (P.trace && blockIdx.x == 0 && p == 4 && lane == 0 && w < 2) {       // (pair 4's rows are gathered during pair 3)
-                    P.trace[110 + 4 * w] = tg0; P.trace[111 + 4 * w] = clock64();
-                    mbar_wait(xpfull, p & 1);
-                    P.trace[112 + 4 * w] = clock64();
-                }
-                if (p > 0) mbar_wait(xfree, (p - 1) & 1);
-                if (lane == 0) mbar_expect_tx(xfull, XIMG / NGW);
-                __syncwarp();
-                if (act) tma::gather4(aX + kb * XBLK + g * 512, &P.map_obs, smem_u32(xfull), kb * 64, r0, r1, r2, r3);
-            }
-        }
-    } else if (warp == 9) {
+      } else if (warp == 9) {
         // =================================== MMA issuer (one warp, warp-uniform) ===================================
         // The whole warp walks the stage sequence; every value an MMA consumes is built from uniform values only and the MMA
         // itself is guarded by elect.sync, so descriptors stay in uniform registers and UTCHMMA issues without a convergence loop.
@@ -357,9 +330,11 @@ __global__ void __launch_bounds__(NTH + (TMA ? 32 * NGW : 0), 1) k_learn_dueling
             itr_p = p;
             uint32_t k0 = chunks_wait(5);                      // (the chunks of a stage are waited for BEFORE its go: off the hand-over path)
             wait_go();
-            if (TMA) { mbar_wait(xpfull, p & 1); fence_after(); }
+            if (TMA) { if (p > 0) mbar_wait(w1a, (p - 1) & 1); mbar_wait(xpfull, p & 1); fence_after(); }
             l1(aH2, k0);                                       // target net: X' sits in the H2 region
-            k0 = chunks_wait(4); wait_go(); l2(k0);
+            k0 = chunks_wait(4); wait_go();
+            if (TMA && p > 0) { mbar_wait(w1b, (p - 1) & 1); fence_after(); }
+            l2(k0);
             k0 = chunks_wait(1); wait_go(); head(k0);          // target head, then the eval L1 (runs under the target head epilogue)
             k0 = chunks_wait(5);
             if (TMA) { mbar_wait(xfull, p & 1); fence_after(); }
@@ -368,13 +343,13 @@ __global__ void __launch_bounds__(NTH + (TMA ? 32 * NGW : 0), 1) k_learn_dueling
             k0 = chunks_wait(1); wait_go(); head(k0);
             k0 = chunks_wait(1);
             wait_go();
-            {   // dH2 half 0 (n2 < 128) -> columns 128..255: A = dOut [128][16], B = Wh^T chunk rows 0..127 [256 n2][16 j]; handed
-                // over on its own so that its epilogue starts at once.  dWh (rows n2 in [128 m, +128) -> columns 16 m..: A = H2 read
-                // MN-major, B = dOut read MN-major, K = 128 rows) runs under that epilogue.
+            {   // dH2 half 0 (n2 < 128) -> columns 128..255: A = dOut [128][16], B = Wh^T chunk rows 0..127 [256 n2][16 j], and the half
+                // n2 < 128 of dWh (rows n2 in [128 m, +128) -> columns 16 m..: A = H2 read MN-major, B = dOut read MN-major, K = 128 rows) are
+                // handed over together: the dH2 epilogue overwrites H2[:, :128], which that half of dWh reads.  The half n2 >= 128 of dWh
+                // runs under that epilogue.
                 const uint32_t wht = chunk_addr(k0);
                 const uint32_t id = idesc_h(128, 16, 1, 1);
                 if (me) mma_h(T0 + 128, dk(aD, 16), dk(wht, 16), idesc_h(128, 128, 0, 0), 0u);
-                commit(done);
 #pragma unroll 1
                 for (int m = 0; m < 2; ++m) {
                     uint64_t a = dm(aH2 + m * 2048u, 256), b = dm(aD, 16);
@@ -386,8 +361,8 @@ __global__ void __launch_bounds__(NTH + (TMA ? 32 * NGW : 0), 1) k_learn_dueling
                         }
                         a += 2048u; b += 128u;
                     }
+                    commit(done);
                 }
-                commit(done);
                 wait_go();                                     // dH2[:, :128] stored, dWh drained: dH2 half 1 (n2 >= 128) -> columns 0..127
                 if (me) mma_h(T0, dk(aD, 16), dk(wht + 4096u, 16), idesc_h(128, 128, 0, 0), 0u);
                 stage_free();
@@ -453,6 +428,76 @@ __global__ void __launch_bounds__(NTH + (TMA ? 32 * NGW : 0), 1) k_learn_dueling
                 }
                 commit(done);
                 if (TMA) commit(xfree);                        // X is dead: the next pair's eval rows may land in the X region
+            }
+        }
+      }
+    } else if (warp >= 12) {
+        if (TMA) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_ACC));
+        // =================================== dW1 accumulators + row gatherers (TMA = true), NGW = 4 warps ===================================
+        // (a) dW1 lives in REGISTERS across the pairs of the CTA.  Flushing it with reds cost 80 KB of L2 atomics per pair (830 MB per
+        //     launch, ~4 k cycles of LSU time per pair that also slowed the MMA stages running beside them).  Warp 12 + i covers the
+        //     TMEM lane quarter i (= its warp id % 4): as soon as the dW1 MMAs of a pair have completed (xfree) each thread adds the 160
+        //     accumulator columns of its row k1 to its registers -- columns 128..159 first (w1a: the next target L1 writes TMEM columns
+        //     128..255), then 0..127 (w1b: the next target L2 writes 0..255); column 159 carries db1.  One plain store per element when
+        //     the CTA is done.
+        // (b) Row gathers: an image is 32 row groups (4 rows each) x three K blocks = 96 tile::gather4 (columns 160-191 are out of
+        //     bounds and land as zeros).  A gather4 costs its issuing warp ~100 cycles and the rows land ~350 cycles after the last one
+        //     is issued, so the 96 are spread over the NGW warps: warp i takes the row groups g = i (mod 4), lanes 0..23 of it one
+        //     (row group, K block) each.  X' of pair p goes to the H2 region once pair p-1's dW2 / dH1 / db2 have completed (h2free),
+        //     X of pair p to the X region once pair p-1's dW1 has completed (xfree).
+        if (TMA) {
+            const int w = warp - 12;
+            const int g = (lane / 3) * NGW + w, kb = lane - (lane / 3) * 3;
+            const bool act = lane < 24;
+            if (lane == 0) tma::prefetch_map(w & 1 ? &P.map_obs : &P.map_next);
+            const uint32_t T0 = *tmem_slot;
+            const int k1 = (warp & 3) * 32 + lane;
+            const uint32_t t_acc = T0 + ((uint32_t)((warp & 3) * 32) << 16);
+            float acc[160];
+#pragma unroll
+            for (int j = 0; j < 160; ++j) acc[j] = 0.f;
+            auto w1_add = [&]() {
+#pragma unroll
+                for (int i = 0; i < 10; ++i) {
+                    const int cb = i < 2 ? 8 + i : i - 2;              // columns 128..159 first
+                    float v[16];
+                    tmem_ld16(t_acc + cb * 16, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[cb * 16 + j] += v[j];
+                    if (i == 1) { fence_before(); mbar_arrive(w1a); }
+                }
+                fence_before();
+                mbar_arrive(w1b);
+            };
+            for (int p = 0; p < n_pairs; ++p) {
+                const int buf = p & 1;
+                mbar_wait(metaready, p & 1);
+                const int* ids = meta + buf * 4 * PB;
+                int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+                if (act) {
+                    const int rb = (int)ringb[buf * 2 + (g >> 4)];
+                    const int4 i4 = *reinterpret_cast<const int4*>(ids + 4 * g);
+                    r0 = rb + i4.x; r1 = rb + i4.y; r2 = rb + i4.z; r3 = rb + i4.w;
+                }
+                if (p > 0) mbar_wait(h2free, (p - 1) & 1);
+                if (lane == 0) mbar_expect_tx(xpfull, XIMG / NGW);
+                __syncwarp();
+                if (act) tma::gather4(aH2 + kb * XBLK + g * 512, &P.map_next, smem_u32(xpfull), kb * 64, r0, r1, r2, r3);
+                if (p > 0) { mbar_wait(xfree, (p - 1) & 1); fence_after(); w1_add(); }
+                if (lane == 0) mbar_expect_tx(xfull, XIMG / NGW);
+                __syncwarp();
+                if (act) tma::gather4(aX + kb * XBLK + g * 512, &P.map_obs, smem_u32(xfull), kb * 64, r0, r1, r2, r3);
+            }
+            if (n_pairs > 0) {
+                mbar_wait(xfree, (n_pairs - 1) & 1); fence_after();
+                w1_add();
+                G[L::OFF_B1 + k1] = acc[159] * (1.0f / H_SCALE); acc[159] = 0.f;                      // column 159 = db1
+                float* gw = G + L::OFF_W1T + k1 * 4;                                                   // slab layout [x / 4][k1][x % 4]
+#pragma unroll
+                for (int j4 = 0; j4 < 40; ++j4)
+                    *reinterpret_cast<float4*>(gw + j4 * 512) = make_float4(acc[j4 * 4] * (1.0f / H_SCALE), acc[j4 * 4 + 1] * (1.0f / H_SCALE),
+                                                                             acc[j4 * 4 + 2] * (1.0f / H_SCALE), acc[j4 * 4 + 3] * (1.0f / H_SCALE));
             }
         }
     } else {
@@ -734,8 +779,10 @@ __global__ void __launch_bounds__(NTH + (TMA ? 32 * NGW : 0), 1) k_learn_dueling
             if (more) gather_store(PO_H2);                          // (float32 rings) X' of the next pair -> H2 region: dH2 is dead (dW2 / dH1 done)
             go_signal();                                            // -> dW1
             wait_done();
-            {   // dW1 flush: TMEM lane = k1 = row, columns [80 hh, +80) of the 160 inputs; column 159 carries db1.  All 80 values
-                // are pulled into registers first so that the next pair's target L1 can start before the reds are issued.
+            if (TMA) {   // the accumulator warps take dW1 out of TMEM (w1a, w1b gate the next pair's target L1, L2)
+                if (more) go_signal();
+            } else {     // float32 rings (no gather warps): columns [80 hh, +80); column 159 carries db1.  All 80 values are pulled into
+                // registers first so that the next pair's target L1 can start before the reds are issued.
                 float v[80];
 #pragma unroll
                 for (int cb = 0; cb < 5; ++cb) tmem_ld16(T0 + t_lane + hh * 80 + cb * 16, v + cb * 16);
@@ -758,7 +805,7 @@ __global__ void __launch_bounds__(NTH + (TMA ? 32 * NGW : 0), 1) k_learn_dueling
             for (int j = 0; j < 9; ++j) G[L::OFF_WH + n2 * 9 + j] = acc_wh[j] * (1.0f / H_SCALE);          // sole owner of the row
             G[L::OFF_B2 + n2] = acc_b2 * (1.0f / H_SCALE);                                               // sole owner
             if (hh == 0 && lane < 9) red_add(G + L::OFF_BH + lane, acc_bh);
-            if (hh == 1) G[L::OFF_B1 + row] = acc_b1;
+            if (!TMA && hh == 1) G[L::OFF_B1 + row] = acc_b1;      // (TMA: the accumulator warps own db1)
         }
         if (n_pairs > 0) {     // flush the TMEM-resident dW2 accumulator once: lane = k1, columns [128 hh, +128) of n2
 #pragma unroll 1
@@ -818,7 +865,7 @@ extern "C" int rl_brain_learn_p(const rl_world_cfg* cfg, const rl_rows_bufs* row
         RL_CUDA_CHECK(cudaFuncSetAttribute(k_learn_dueling_p<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM));
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (use_tma) k_learn_dueling_p<true><<<rl_learn_grid(), NTH + 32 * NGW, PAIR_SMEM, st>>>(P);
+    if (use_tma) k_learn_dueling_p<true><<<rl_learn_grid(), NTH_TMA, PAIR_SMEM, st>>>(P);
     else k_learn_dueling_p<false><<<rl_learn_grid(), NTH, PAIR_SMEM, st>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
     if (tracing) {
