@@ -465,6 +465,11 @@ int rl_brain_build_wimg_h(int32_t kind, const float* params, void* wimg_h, void*
 /* get_action of ONE dueling brain with fp16 operands (same contract as rl_brain_act_tc, fp16 weight image) */
 int rl_brain_act_h(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_rows_bufs* rows, int32_t gene,
                    const rl_brain_act* brain, const void* wimg_eval_h, uint64_t t_act, float* q_out, void* stream);
+/* get_action of the dueling brains in the batch-major form of rl_brain_learn_p (csrc/tc_act_kernels.cu: 128-row tiles, one warp-uniform
+ * MMA issuer, rows gathered float32 -> fp16 into a SWIZZLE_128B image by dedicated warps).  Same contract as rl_brain_act_h; the
+ * Environment's default under precision="fp16". */
+int rl_brain_act_p(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_rows_bufs* rows, int32_t gene,
+                   const rl_brain_act* brain, const void* wimg_eval_h, uint64_t t_act, float* q_out, void* stream);
 int rl_brain_learn_h(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
                      const int32_t* sample_idx, const rl_learn_bufs* learn, const void* wimg_eval_h, const void* wimg_target_h,
                      void* stream);

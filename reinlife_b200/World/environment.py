@@ -229,8 +229,9 @@ class Environment:
                     b._dev.build_wimg(w._stream())
                     b._dev.wimg_stale = False
                     self.gpu_launches += 2
-                if self._learn_fp16:                     # fp16 operands, issuer-warp pipeline (k_act_dueling_h)
-                    _lib.check(w.lib.rl_brain_act_h(C.byref(w.cfg), C.byref(w.bufs), C.byref(self.rows.bufs), C.c_int32(g),
+                if self._learn_fp16:                     # fp16 operands: batch-major 128-row tiles (k_act_dueling_p); RL_LEARN_SINGLE: k_act_dueling_h
+                    fn = w.lib.rl_brain_act_h if self._learn_single else w.lib.rl_brain_act_p
+                    _lib.check(fn(C.byref(w.cfg), C.byref(w.bufs), C.byref(self.rows.bufs), C.c_int32(g),
                                                     C.byref(self._act_descs[g]), C.c_void_p(b._dev.wimg_eh.data_ptr()),
                                                     C.c_uint64(w.t + 1), C.c_void_p(q_out), w._stream()))
                 else:

@@ -226,7 +226,7 @@ def test_act_kernels_600_tiles_per_brain():
     eps = torch.tensor([0.3, 0.0], dtype=torch.float64, device="cuda")
     descs = (_lib.BrainAct * 2)(*[b.act_desc(_lib.ACT_DUELING, eps.data_ptr() + 8 * i) for i, b in enumerate(brains)])
     out = {}
-    for mode in ("fp32", "tf32", "fp16"):
+    for mode in ("fp32", "tf32", "fp16", "fp16p"):       # fp16p = rl_brain_act_p (batch-major 128-row tiles, the default)
         q = torch.zeros((2, rows.row_cap, 8), device="cuda")
         vw.rec[:, :, 13] = 255
         if mode == "fp32":
@@ -234,9 +234,9 @@ def test_act_kernels_600_tiles_per_brain():
                                                C.c_void_p(q.data_ptr()), None, vw._stream()))
         else:
             for i, b in enumerate(brains):
-                b.use_fp16 = mode == "fp16"
+                b.use_fp16 = mode != "tf32"
                 b.build_wimg(vw._stream())
-                fn = vw.lib.rl_brain_act_tc if mode == "tf32" else vw.lib.rl_brain_act_h
+                fn = vw.lib.rl_brain_act_tc if mode == "tf32" else vw.lib.rl_brain_act_p if mode == "fp16p" else vw.lib.rl_brain_act_h
                 img = b.wimg_e if mode == "tf32" else b.wimg_eh
                 _lib.check(fn(C.byref(vw.cfg), C.byref(vw.bufs), C.byref(rows.bufs), i, C.byref(descs[i]),
                               C.c_void_p(img.data_ptr()), C.c_uint64(7), C.c_void_p(q.data_ptr()), vw._stream()))
@@ -256,12 +256,12 @@ def test_act_kernels_600_tiles_per_brain():
         q32 = out["fp32"][0][i, :n]
         np.testing.assert_allclose(q32[pick], q_or, rtol=1e-4, atol=1e-4)
         scale = np.abs(q32).max()
-        for mode in ("tf32", "fp16"):
+        for mode in ("tf32", "fp16", "fp16p"):
             qtc = out[mode][0][i, :n]
             assert np.abs(qtc[pick] - q_or).max() < 2e-2 * scale, (mode, "vs oracle")
             assert np.abs(q32 - qtc).max() < 2e-2 * scale, mode
             assert (q32.argmax(1) == qtc.argmax(1)).mean() >= 0.99, mode
-    for mode in ("tf32", "fp16"):
+    for mode in ("tf32", "fp16", "fp16p"):
         atc = out[mode][1]
         assert ((atc != -1) == listed).all(), mode
         assert (a32[listed] == atc[listed]).mean() >= 0.99, mode

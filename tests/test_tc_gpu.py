@@ -129,7 +129,7 @@ def test_tensor_core_act_matches_fp32_act():
     eps = torch.tensor([0.3, 0.0], dtype=torch.float64, device="cuda")
     descs = (_lib.BrainAct * 2)(*[b.act_desc(_lib.ACT_DUELING, eps.data_ptr() + 8 * i) for i, b in enumerate(brains)])
     out = {}
-    for mode in ("fp32", "tf32", "fp16"):
+    for mode in ("fp32", "tf32", "fp16", "fp16p"):       # fp16p = rl_brain_act_p (batch-major 128-row tiles, the default)
         q = torch.zeros((2, rows.row_cap, 8), device="cuda")
         vw.rec[:, :, 13] = 255
         if mode == "fp32":
@@ -137,19 +137,20 @@ def test_tensor_core_act_matches_fp32_act():
                                                C.c_void_p(q.data_ptr()), None, vw._stream()))
         else:
             for i, b in enumerate(brains):
-                b.use_fp16 = mode == "fp16"
+                b.use_fp16 = mode != "tf32"
                 b.build_wimg(vw._stream())
                 if mode == "tf32":
                     _lib.check(vw.lib.rl_brain_act_tc(C.byref(vw.cfg), C.byref(vw.bufs), C.byref(rows.bufs), i, C.byref(descs[i]),
                                                       C.c_void_p(b.wimg_e.data_ptr()), C.c_uint64(7), C.c_void_p(q.data_ptr()), vw._stream()))
                 else:
-                    _lib.check(vw.lib.rl_brain_act_h(C.byref(vw.cfg), C.byref(vw.bufs), C.byref(rows.bufs), i, C.byref(descs[i]),
-                                                     C.c_void_p(b.wimg_eh.data_ptr()), C.c_uint64(7), C.c_void_p(q.data_ptr()), vw._stream()))
+                    fn = vw.lib.rl_brain_act_p if mode == "fp16p" else vw.lib.rl_brain_act_h
+                    _lib.check(fn(C.byref(vw.cfg), C.byref(vw.bufs), C.byref(rows.bufs), i, C.byref(descs[i]),
+                                  C.c_void_p(b.wimg_eh.data_ptr()), C.c_uint64(7), C.c_void_p(q.data_ptr()), vw._stream()))
         torch.cuda.synchronize()
         out[mode] = (q.cpu().numpy(), vw.rec[:, :, 13].cpu().numpy().view(np.int8).copy())
     a32 = out["fp32"][1]
     listed = a32 != -1
-    for mode in ("tf32", "fp16"):
+    for mode in ("tf32", "fp16", "fp16p"):
         n_tot = 0
         for i in range(2):
             n = int(rows.total[i * 3])
