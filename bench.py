@@ -236,7 +236,7 @@ def strong_scaling_point(args, rl, PERD3QN, torch, dist, world_size, local, tota
 
     def body(n_epi):
         count.add_(env.world.n_agents.sum())
-        env.act(n_epi); env.step(); env.learn(n_epi); env.update_env(n_epi); env.top_up(TARGET)
+        env.act(n_epi); env.step(); env.learn(n_epi); env.update_env(n_epi, top_up=TARGET)
 
     n_epi = 1
     for _ in range(max(3, args.warmup)):
@@ -290,8 +290,7 @@ def run_b200(args):
         env.act(n_epi)
         env.step()
         env.learn(n_epi)
-        env.update_env(n_epi)
-        env.top_up(TARGET)
+        env.update_env(n_epi, top_up=TARGET)     # update_env + the saturated-world generator in one launch (rl_world_update_top_up)
 
     def barrier():
         if world_size > 1:
@@ -347,16 +346,16 @@ def run_b200(args):
     e2e_value = int(agents2) / float(sec2)
 
     # ---- per-phase device times (CUDA events on the launching stream) for the roofline
-    phases = {"act": 0.0, "step": 0.0, "learn": 0.0, "update": 0.0, "top_up": 0.0}
+    phases = {"act": 0.0, "step": 0.0, "learn": 0.0, "update": 0.0}
     n_meas = 5
     n_agents_meas = 0
     ev_meas = 0.0
     env.kernel_events = []
     for _ in range(n_meas):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         n_agents_meas += int(env.world.n_agents.sum())
         ev[0].record(); env.act(n_epi); ev[1].record(); env.step(); ev[2].record(); env.learn(n_epi); ev[3].record()
-        env.update_env(n_epi); ev[4].record(); env.top_up(TARGET); ev[5].record()
+        env.update_env(n_epi, top_up=TARGET); ev[4].record()
         torch.cuda.synchronize()
         ev_meas += sum(float(b._dev.grad[nt]) for b in brains) / world_size    # grad[nt] is all-reduced: events per GPU
         for k, name in enumerate(phases):
@@ -393,8 +392,8 @@ def run_b200(args):
     flop_event = 2.0 * 64 * (2 * 53504 + 2 * 53504) - 2.0 * 64 * (153 * 128)   # 2 forwards + backward (dX of layer 1 not needed)
     roof_k = {
         "k_world_step": {"bound": "hbm", "ms": phases["step"], "achieved": b_step / phases["step"] / 1e6, "peak": hbm_peak, "unit": "GB/s"},
-        "k_world_update": {"bound": "hbm", "ms": phases["update"], "achieved": b_obs / phases["update"] / 1e6, "peak": hbm_peak, "unit": "GB/s"},
-        "k_world_topup": {"bound": "hbm", "ms": phases["top_up"], "achieved": b_obs / phases["top_up"] / 1e6, "peak": hbm_peak, "unit": "GB/s"},
+        "k_world_update": {"bound": "hbm", "ms": phases["update"], "achieved": b_obs / phases["update"] / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                           "note": "update_env + the benchmark's saturated-world top-up fused in one launch (rl_world_update_top_up): one list rebuild, one observation pass"},
         learn_kernel_name: {"bound": "tensor", "ms": learn_kernel_ms, "launches_per_step": len(brains),
                                 "achieved": ev_per_launch * flop_event / max(learn_kernel_ms, 1e-9) / 1e9, "peak": bf16_peak, "unit": "TFLOP/s",
                                 "note": ("one launch = all train() events of one brain (25.6 MFLOP per 64-row event), timed alone with CUDA events; "
@@ -467,7 +466,7 @@ def run_secondary(args):
         name = "BASELINE configs[1]: 256 worlds, 30x30, saturated to 100 agents, DQN x1 pretrained weights, inference only (tester loop body)"
 
         def body(n_epi):
-            env.act(n_epi); env.step(); env.update_env(n_epi); env.top_up(100)
+            env.act(n_epi); env.step(); env.update_env(n_epi, top_up=100)
         warm, steps = 20, max(args.steps, 100)
     else:
         brains = [PPO(), PERD3QN(exploration=20, capacity=1000)]

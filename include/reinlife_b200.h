@@ -137,6 +137,10 @@ int rl_world_update_ns(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const
  * `target` are on the grid (gene U{0..G-1}, health 10*U{1..20}, age U{0..max_age-1}), then observe. */
 int rl_world_top_up(const rl_world_cfg* cfg, const rl_world_bufs* bufs, uint64_t t, int32_t target,
                     int32_t max_age, void* stream);
+/* rl_world_update followed by rl_world_top_up in ONE launch (the benchmark loop's update_env + saturate): the same draws and the same
+ * final state, bit for bit (tests/test_world_gpu.py), with one agent-list rebuild and one observation pass instead of two. */
+int rl_world_update_top_up(const rl_world_cfg* cfg, const rl_world_bufs* bufs, uint64_t t, int32_t target, int32_t max_age,
+                           void* stream);
 
 /* Environment._get_observations() alone -- World/environment.py:313-375, Grid.fov World/grid.py:90-117.
  * Writes obs_state (which=0) or obs_prime (which=1) for the current list; does not change the world. */

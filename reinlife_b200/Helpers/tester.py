@@ -18,8 +18,6 @@ def tester(brains: List, width: int = 30, height: int = 30, max_agents: int = 10
     while n_steps is None or k < n_steps:
         env.act(0)                # agent.action = agent.brain.get_action(agent.state[, 0])   tester.py:58-68
         env.step()
-        env.update_env()
-        if saturate_to:
-            env.top_up(saturate_to)
+        env.update_env(top_up=saturate_to or None)
         k += 1
     return env

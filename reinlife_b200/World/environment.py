@@ -182,11 +182,13 @@ class Environment:
         self.gpu_launches += 1
 
     @_nvtx("reinlife.update_env")
-    def update_env(self, n_epi: int = 0):
+    def update_env(self, n_epi: int = 0, top_up=None, max_age=50):
+        """environment.py:188-215.  top_up=N (benchmark loops, static families): the saturated-world generator runs in the same
+        launch -- identical to update_env() followed by top_up(N)."""
         if self.training:                                  # environment.py:206-207
             self.tracker.update_results(None, n_epi)
             self.gpu_launches += 1
-        self.world.update()
+        self.world.update(top_up=top_up, max_age=max_age)
         self.gpu_launches += 1
 
     @_nvtx("reinlife.top_up")

@@ -88,8 +88,13 @@ class VecWorld:
             else:
                 _lib.check(self.lib.rl_world_step(C.byref(self.cfg), C.byref(self.bufs), C.c_uint64(self.t), self._stream()))
 
-    def update(self):
+    def update(self, top_up=None, max_age=50):
+        """update_env; top_up=N additionally saturates the world to N agents in the same launch (static families only)."""
         with torch.cuda.device(self.device):
+            if top_up and self.ns is None:
+                _lib.check(self.lib.rl_world_update_top_up(C.byref(self.cfg), C.byref(self.bufs), C.c_uint64(self.t),
+                                                           C.c_int32(top_up), C.c_int32(max_age), self._stream()))
+                return
             if self.ns is not None:
                 _lib.check(self.lib.rl_world_update_ns(C.byref(self.cfg), C.byref(self.bufs), C.byref(self.ns), C.c_uint64(self.t), self._stream()))
             else:

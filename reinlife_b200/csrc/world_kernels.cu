@@ -849,6 +849,31 @@ __global__ void __launch_bounds__(WT, NS ? 1 : RL_WORLD_MINB) k_world_update(con
     for (int c = threadIdx.x; c < C; c += WT)
         if (s.type[c] == RL_AGENT && (s.flags[c] & RL_F_DEAD)) s.type[c] = RL_FOOD;
     __syncthreads();
+    if (!NS && P.target > 0) {
+        // fused saturated-world generator (rl_world_update_top_up): exactly what k_world_topup does on the state this kernel would
+        // have written -- the same draws (keyed by t and the placement counter), one list rebuild and one observation pass instead of two
+        build_empty_mask(s.type, s.mask, C);
+        __syncthreads();
+        if (warp == 0) {
+            int cur = 0;
+            for (int base = 0; base < C; base += 32) {
+                const int c = base + lane;
+                cur += __popc(__ballot_sync(0xffffffffu, c < C && s.type[c] == RL_AGENT));
+            }
+            cur = min(cur, P.cfg.slot_cap);
+            for (uint32_t k = 0; cur < P.target; ++k, ++cur) {
+                const int cell = warp_place(s.mask, Cw, rl_draw(key, P.t, RL_SITE_TOPUP_PLACE, k));
+                if (cell < 0) break;
+                const int gene = (int)rl_below(rl_draw(key, P.t, RL_SITE_TOPUP_GENE, k), (uint32_t)P.cfg.n_genes);
+                const int health = 10 * (1 + (int)rl_below(rl_draw(key, P.t, RL_SITE_TOPUP_HEALTH, k), 20));
+                const int age = (int)rl_below(rl_draw(key, P.t, RL_SITE_TOPUP_AGE, k), (uint32_t)P.max_age);
+                spawn_agent(s, cell, gene, health, age);
+                if (lane == 0) s.src[cell] = (uint16_t)cell;
+                warp_mask_clear(s.mask, cell);
+            }
+        }
+        __syncthreads();
+    }
     finish_and_observe<false, NS>(P, s, w, s.type, P.b.obs_state, 0);
 }
 
@@ -1043,6 +1068,18 @@ int rl_world_update(const rl_world_cfg* cfg, const rl_world_bufs* bufs, uint64_t
     int rc = world_prepare(cfg, bufs, P, smem);
     if (rc) return rc;
     P.t = t;
+    k_world_update<false><<<cfg->n_worlds, WT, smem, (cudaStream_t)stream>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_world_update_top_up(const rl_world_cfg* cfg, const rl_world_bufs* bufs, uint64_t t, int32_t target, int32_t max_age,
+                           void* stream) {
+    WParams P; size_t smem;
+    int rc = world_prepare(cfg, bufs, P, smem);
+    if (rc) return rc;
+    RL_ARG_CHECK(max_age > 0 && target >= 0);
+    P.t = t; P.target = target; P.max_age = max_age;
     k_world_update<false><<<cfg->n_worlds, WT, smem, (cudaStream_t)stream>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
     return RL_OK;

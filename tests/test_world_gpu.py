@@ -169,3 +169,31 @@ def test_full_size_world_batch_properties_and_oracle_spot_checks():
     a = run()
     b = run()
     assert a == b                                                                    # bit-reproducible run to run
+
+
+def test_fused_update_top_up_equals_update_then_top_up():
+    """rl_world_update_top_up (one launch: the benchmark loops' update_env + saturate) leaves exactly the state that
+    rl_world_update followed by rl_world_top_up leaves: cell types, agent records, counts, observations -- bit for bit,
+    over a run with deaths, births and a moving saturation target."""
+    from reinlife_b200.World.vecworld import VecWorld
+    for (H, W, G, NW, target) in ((30, 30, 2, 40, 100), (9, 7, 3, 24, 20), (12, 17, 5, 16, 60)):
+        a = VecWorld(NW, H, W, G, max_agents=target, seed=21)
+        b = VecWorld(NW, H, W, G, max_agents=target, seed=21)
+        g = torch.Generator(device="cuda"); g.manual_seed(3)
+        for vw in (a, b):
+            vw.reset(); vw.top_up(target)
+        for t in range(25):
+            act = torch.randint(0, 8, (NW, a.S), device="cuda", dtype=torch.int8, generator=g)
+            tgt = target if t % 3 else max(1, target // 2)          # below the current count on some steps: no placement
+            for vw in (a, b):
+                vw.set_actions(act); vw.step()
+            a.update(); a.top_up(tgt)
+            b.update(top_up=tgt)
+            torch.cuda.synchronize()
+            assert torch.equal(a.type, b.type) and torch.equal(a.n_agents, b.n_agents), (H, W, t)
+            n = a.n_agents.cpu().numpy()
+            ra, rb = a.rec.cpu().numpy(), b.rec.cpu().numpy()
+            oa, ob = a.obs_state.view(torch.int32).cpu().numpy(), b.obs_state.view(torch.int32).cpu().numpy()
+            for w in range(NW):
+                assert (ra[w, :n[w]] == rb[w, :n[w]]).all(), (H, W, t, w)
+                assert (oa[w, :n[w]] == ob[w, :n[w]]).all(), (H, W, t, w)
