@@ -374,8 +374,8 @@ def run_b200(args):
     traffic = None
     try:
         # static number: dram__bytes_read + dram__bytes_write of ONE launch from the committed `ncu --set full` capture of this
-        # same command (profiles/ncu_full_r02_summary.md), not measured in this run
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json"))).get(learn_kernel_name + "_bytes_per_launch")
+        # same command (profiles/ncu_full_r02b_summary.md), not measured in this run
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02b.json"))).get(learn_kernel_name + "_bytes_per_launch")
     except Exception:
         pass
     peaks = {}
@@ -402,14 +402,14 @@ def run_b200(args):
                                             "fp32": "fp32 FMA on CUDA cores (reference precision); peak shown is the bf16 tensor peak"}[args.precision])},
         "act(get_action kernels x2 + row lists)": {"bound": "tensor", "ms": phases["act"], "achieved": NW * n_avg * 107008 / phases["act"] / 1e9,
                                                    "peak": bf16_peak, "unit": "TFLOP/s",
-                                                   "note": {"fp16": "k_act_dueling_h, tcgen05 kind::f16", "tf32": "k_act_dueling_tc, tcgen05 kind::tf32",
+                                                   "note": {"fp16": "k_act_dueling_p, tcgen05 kind::f16", "tf32": "k_act_dueling_tc, tcgen05 kind::tf32",
                                                             "fp32": "k_brain_act, fp32 FMA on CUDA cores"}[args.precision]},
     }
     for v in roof_k.values():
         v["frac"] = v["achieved"] / v["peak"]
     dominant = max(roof_k, key=lambda k: roof_k[k]["ms"] * roof_k[k].get("launches_per_step", 1))
     roofline = dict(roof_k[dominant], kernel=dominant, traffic=traffic if dominant == learn_kernel_name else None,
-                    traffic_source="profiles/traffic_r02.json (static: one launch under ncu --set full, same command)", peak_source=peak_src,
+                    traffic_source="profiles/traffic_r02b.json (static: one launch under ncu --set full, same command)", peak_source=peak_src,
                     step_share=roof_k[dominant]["ms"] * roof_k[dominant].get("launches_per_step", 1) / sum(phases.values()))
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(3, args.warmup),

@@ -18,6 +18,9 @@ def tester(brains: List, width: int = 30, height: int = 30, max_agents: int = 10
     while n_steps is None or k < n_steps:
         env.act(0)                # agent.action = agent.brain.get_action(agent.state[, 0])   tester.py:58-68
         env.step()
-        env.update_env(top_up=saturate_to or None)
+        if saturate_to:
+            env.update_env(top_up=saturate_to)
+        else:
+            env.update_env()
         k += 1
     return env

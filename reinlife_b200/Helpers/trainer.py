@@ -32,7 +32,10 @@ def trainer(brains: List, n_episodes: int = 10_000, width: int = 30, height: int
         env.act(n_epi)            # for agent in env.agents: agent.get_action(n_epi)      trainer.py:88-89
         env.step()                #                                                        trainer.py:92
         env.learn(n_epi)          # for agent in env.agents: agent.learn(n_epi=n_epi)     trainer.py:95-96
-        env.update_env(n_epi, top_up=saturate_to or None)     # trainer.py:99 (+ the benchmark's saturated-world generator, same launch)
+        if saturate_to:           # trainer.py:99 + the benchmark's saturated-world generator in the same launch
+            env.update_env(n_epi, top_up=saturate_to)
+        else:
+            env.update_env(n_epi)
 
     env.check_status()
     if save:

@@ -860,6 +860,7 @@ __global__ void __launch_bounds__(WT, NS ? 1 : RL_WORLD_MINB) k_world_update(con
                 const int c = base + lane;
                 cur += __popc(__ballot_sync(0xffffffffu, c < C && s.type[c] == RL_AGENT));
             }
+            __syncwarp();                                  // the reads above precede lane 0's s.type writes in spawn_agent
             cur = min(cur, P.cfg.slot_cap);
             for (uint32_t k = 0; cur < P.target; ++k, ++cur) {
                 const int cell = warp_place(s.mask, Cw, rl_draw(key, P.t, RL_SITE_TOPUP_PLACE, k));

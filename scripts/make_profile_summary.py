@@ -53,7 +53,7 @@ seen, lines, traffic = set(), [], {}
 cols = [c for c in hdr if c in metrics]
 for row in r[2:]:
     d = dict(zip(hdr, row))
-    name = d["Kernel Name"].replace("<unnamed>::", "").split("(")[0]
+    name = d["Kernel Name"].replace("<unnamed>::", "").replace("void ", "").split("(")[0].split("<")[0]
     if name in seen:
         continue
     seen.add(name)
@@ -64,7 +64,7 @@ for row in r[2:]:
                                               float(d["dram__bytes_write.sum"]) * scale[u["dram__bytes_write.sum"]])
 with open(os.path.join(out_dir, f"ncu_full_{tag}_summary.md"), "w") as f:
     f.write(f"# ncu --set full, {tag} (one row per kernel; first captured launch)\n\n"
-            "Command: `ncu --set full --clock-control none --import-source on -k regex:\"k_learn_dueling_p|k_world_step|k_world_update|k_replay_store|k_act_dueling_h|k_world_topup\" -s 27 -c 9 "
+            "Command: `ncu --set full --clock-control none --import-source on -k regex:\"k_learn_dueling_p|k_world_step|k_world_update|k_replay_store|k_act_dueling_p|k_replay_sample\" -s 30 -c 10 "
             "python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (the event kernel's name is k_learn_dueling_h in the round-1 captures)\n\n| kernel | " + " | ".join(cols) + " |\n|" + "---|" * (len(cols) + 1) + "\n"
             "| (unit) | " + " | ".join(dict(zip(hdr, units))[c] for c in cols) + " |\n" + "\n".join(lines) + "\n")
 json.dump(traffic, open(os.path.join(out_dir, f"traffic_{tag}.json"), "w"), indent=1)

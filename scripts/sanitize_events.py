@@ -52,6 +52,22 @@ def events(n_per_cta=3):
                           C.byref(brain.learn_bufs), C.c_void_p(we.data_ptr()), C.c_void_p(wt.data_ptr()), st))
         torch.cuda.synchronize()
         print(f"event kernel {mode}: {n_ev} events over {grid} CTAs, grad[n]={float(brain.grad[brain.dims.n_train])}", flush=True)
+    # the paired kernel's TMA variant: float16 ring -> tile::gather4 row gathers, accumulator warps (setmaxnreg)
+    r16 = ReplayRings(NW, 128, "cuda", fp16=True)
+    r16.obs.copy_(rp.obs.half()); r16.next_obs.copy_(rp.next_obs.half())
+    r16.obs[..., -1] = 1.0; r16.next_obs[..., -1] = 1.0
+    for name in ("action", "reward", "done", "prio", "pw", "len", "pos"):
+        getattr(r16, name).copy_(getattr(rp, name))
+    brain = DeviceBrain(0, packing.default_init(0), "cuda")
+    brain.use_fp16 = True
+    brain.alloc_learn(rows.row_cap)
+    brain.sample_idx[:n_ev] = sidx
+    st = vw._stream()
+    brain.build_wimg(st)
+    _lib.check(vw.lib.rl_brain_learn_p(C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(r16.bufs), C.c_void_p(brain.sample_idx.data_ptr()),
+                                       C.byref(brain.learn_bufs), C.c_void_p(brain.wimg_eh.data_ptr()), C.c_void_p(brain.wimg_th.data_ptr()), st))
+    torch.cuda.synchronize()
+    print(f"event kernel fp16p, float16 ring (TMA gather4): {n_ev} events, grad[n]={float(brain.grad[brain.dims.n_train])}", flush=True)
 
 
 def env_steps():
@@ -64,7 +80,7 @@ def env_steps():
                              n_worlds=384, seed=3, device="cuda:0", precision=precision)
         env.reset(); env.top_up(100)
         for n_epi in range(1, 4):
-            env.act(n_epi); env.step(); env.learn(n_epi); env.update_env(n_epi); env.top_up(100)
+            env.act(n_epi); env.step(); env.learn(n_epi); env.update_env(n_epi, top_up=100)
         torch.cuda.synchronize()
         print(f"Environment x3 steps ({precision}): adam steps", [int(b._dev.adam_step) for b in brains], flush=True)
 

@@ -162,3 +162,63 @@ def test_tensor_core_act_matches_fp32_act():
         atc = out[mode][1]
         assert listed.sum() == n_tot and ((atc != -1) == listed).all(), mode
         assert (a32[listed] == atc[listed]).mean() >= 0.99, mode
+
+
+def _himg16(mat):
+    """fp16 [R][W] -> interleaved no-swizzle image (8 rows x 16 B core matrices), csrc/tc_bm.cuh::himg."""
+    R, W = mat.shape
+    out = np.zeros(R * W, np.float16)
+    r, c = np.meshgrid(np.arange(R), np.arange(W), indexing="ij")
+    out[((r >> 3) * (W * 8) + (c >> 3) * 64 + (r & 7) * 8 + (c & 7)).reshape(-1)] = mat.reshape(-1)
+    return out
+
+
+def _sw128(mat):
+    """fp16 [R][W] -> ceil(W / 64) K blocks of [R][128 B], 16-byte unit index ^= (row & 7): csrc/tc_bm.cuh::ximg, what a TMA
+    tile::gather4 with CU_TENSOR_MAP_SWIZZLE_128B writes."""
+    R, W = mat.shape
+    out = np.zeros(((W + 63) // 64) * R * 64, np.float16)
+    r, c = np.meshgrid(np.arange(R), np.arange(W), indexing="ij")
+    out[((c // 64) * (R * 64) + r * 64 + ((((c % 64) // 8) ^ (r & 7)) * 8) + (c % 8)).reshape(-1)] = mat.reshape(-1)
+    return out
+
+
+def _gemm_hx(a_img, b_img, M, N, K, ageo, bgeo, a_mn, b_mn, akblk, bkblk, alay, blay):
+    from reinlife_b200 import _lib
+    lib = _lib.load()
+    ta, tb = torch.from_numpy(a_img).cuda(), torch.from_numpy(b_img).cuda()
+    d = torch.zeros((M, N), device="cuda")
+    _lib.check(lib.rl_tc_gemm_test_hx(C.c_void_p(ta.data_ptr()), C.c_void_p(tb.data_ptr()), C.c_void_p(d.data_ptr()), M, N, K,
+                                      a_img.size, b_img.size, *ageo, *bgeo, a_mn, b_mn, akblk, bkblk, alay, blay, None))
+    torch.cuda.synchronize()
+    return d.cpu().numpy()
+
+
+def test_swizzle128_operand_conventions_and_tma_gather4():
+    """What k_learn_dueling_p / k_act_dueling_p rely on for their gathered input rows (csrc/tc_bm.cuh):
+    (1) a SWIZZLE_128B image [128 rows][160 halves] (three K blocks) is a valid K-major A operand (L1: X W1^T, W1 no-swizzle);
+    (2) the SAME image is a valid MN-major B operand with N = image columns, K = image rows (dW1 = dH1^T X, N = 160 / 80 / 64);
+    (3) cp.async.bulk.tensor tile::gather4 of 128 ring rows by index (box {64 columns, 1 row}, SWIZZLE_128B) lands exactly that
+        image, columns >= 160 as zeros."""
+    from reinlife_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    M, N, K = 128, 128, 160
+    X = rng.standard_normal((M, K)).astype(np.float16); W = rng.standard_normal((N, K)).astype(np.float16)
+    got = _gemm_hx(_sw128(X), _himg16(W), M, N, K, (16, 1024, 32), (128, K * 16, 256), 0, 0, M * 128, 0, 2, 0)
+    want = X.astype(np.float64) @ W.astype(np.float64).T
+    assert np.abs(got - want).max() < 1e-5 * np.abs(want).max()
+    dH1 = rng.standard_normal((128, 128)).astype(np.float16)
+    want = dH1.astype(np.float64).T @ X.astype(np.float64)
+    for Nx in (160, 80, 64, 128):
+        got = _gemm_hx(_himg16(dH1), _sw128(X), 128, Nx, 128, (128 * 16, 128, 2 * 128 * 16), (16384, 1024, 2048), 1, 1, 0, 0, 0, 2)
+        assert np.abs(got - want[:, :Nx]).max() < 1e-5 * np.abs(want).max(), Nx
+    n_rows = 5000
+    ring = rng.standard_normal((n_rows, 160)).astype(np.float16)
+    idx = rng.integers(0, n_rows, 128).astype(np.int32)
+    idx[:4] = (0, n_rows - 1, 17, 17)                                       # first / last row, a duplicate
+    tr, ti = torch.from_numpy(ring).cuda(), torch.from_numpy(idx).cuda()
+    out = torch.zeros(3 * 16384 // 2, dtype=torch.float16, device="cuda")
+    _lib.check(lib.rl_tma_gather_test(C.c_void_p(tr.data_ptr()), C.c_longlong(n_rows), C.c_void_p(ti.data_ptr()), C.c_void_p(out.data_ptr()), 1))
+    want = _sw128(np.concatenate([ring[idx], np.zeros((128, 32), np.float16)], axis=1))
+    assert np.array_equal(out.cpu().numpy().view(np.uint16), want.view(np.uint16))
