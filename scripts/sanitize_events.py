@@ -86,6 +86,9 @@ def env_steps():
 
 
 if __name__ == "__main__":
-    events()
-    env_steps()
+    part = os.environ.get("RL_SAN_PART", "all")
+    if part in ("all", "events"):
+        events()
+    if part in ("all", "env"):
+        env_steps()
     print("sanitize target done")
