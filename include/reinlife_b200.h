@@ -242,6 +242,10 @@ typedef struct rl_replay_bufs {             /* per brain; ring index = local wor
     float*   pw;         /* [n_worlds, capacity] float32(float64(prio)^0.6) */
     int32_t* len;        /* [n_worlds] */
     int32_t* pos;        /* [n_worlds] */
+    int32_t* maxst;      /* [n_worlds][2] or NULL: {float bits of max(priorities), number of entries holding it}, maintained exactly by
+                            rl_replay_store / rl_replay_update_prio so that the store needs no scan of the priority array
+                            (PERD3QN.py:147 recomputes the max at every memorize); count 0 = unknown: the next store scans.  Zero it
+                            after writing prio[] by hand. */
     int32_t  capacity;
     int32_t  prioritized;/* 1: proportional PER (PERD3QN); 0: uniform (D3QN, DQN) */
     int32_t  obs_fp16;   /* 1: obs / next_obs rows are stored as float16 (obs_ld halves per row, column obs_ld-1 = 1.0): the ring

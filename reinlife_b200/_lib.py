@@ -102,6 +102,7 @@ class BrainSched(C.Structure):
 class ReplayBufs(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("next_obs", C.c_void_p), ("action", C.c_void_p), ("reward", C.c_void_p),
                 ("done", C.c_void_p), ("prio", C.c_void_p), ("pw", C.c_void_p), ("len", C.c_void_p), ("pos", C.c_void_p),
+                ("maxst", C.c_void_p),
                 ("capacity", C.c_int32), ("prioritized", C.c_int32), ("obs_fp16", C.c_int32), ("_pad", C.c_int32)]
 
 

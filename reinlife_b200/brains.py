@@ -106,9 +106,12 @@ class ReplayRings:
         self.pw = torch.zeros((n_worlds, capacity), device=dev)
         self.len = torch.zeros(n_worlds, dtype=torch.int32, device=dev)
         self.pos = torch.zeros(n_worlds, dtype=torch.int32, device=dev)
+        # {max(priorities) as float bits, count of entries holding it} per ring, kept exact by the store / priority-update kernels
+        # (count 0 = unknown -> the next store scans the ring); zero it after writing prio[] by hand
+        self.maxst = torch.zeros((n_worlds, 2), dtype=torch.int32, device=dev)
         self.bufs = _lib.ReplayBufs(self.obs.data_ptr(), self.next_obs.data_ptr(), self.action.data_ptr(),
                                     self.reward.data_ptr(), self.done.data_ptr(), self.prio.data_ptr(), self.pw.data_ptr(),
-                                    self.len.data_ptr(), self.pos.data_ptr(), self.capacity, int(self.prioritized),
+                                    self.len.data_ptr(), self.pos.data_ptr(), self.maxst.data_ptr(), self.capacity, int(self.prioritized),
                                     int(self.fp16), 0)
 
     @staticmethod

@@ -44,6 +44,17 @@ __device__ __forceinline__ float block_max(float v, float* red) {
     return r;
 }
 
+__device__ __forceinline__ int block_sum_i(int v, int* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane_id() == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = 0;
+    for (int i = 0; i < RT / 32; ++i) r += red[i];
+    __syncthreads();
+    return r;
+}
+
 // ---- memorize: CTA per world ----
 __global__ void __launch_bounds__(RT) k_replay_store(const ReplayParams P) {
     __shared__ float red[RT / 32];
@@ -53,15 +64,26 @@ __global__ void __launch_bounds__(RT) k_replay_store(const ReplayParams P) {
     if (cnt == 0) return;
     const int off = P.rows.offset[(size_t)gk * NW + w];
     const int len = P.rp.len[w], pos = P.rp.pos[w];
+    // max(priorities) (1.0 while the ring is empty, PERD3QN.py:147) and the number of entries holding it: read from the maintained
+    // state when it is known, else one scan of the ring (first store after the priorities were written by hand / a count that fell to 0)
+    __shared__ int s_more;
     float maxp = 1.0f;
-    if (P.rp.prioritized) {
-        if (len > 0) {                                             // PERD3QN.py:147
+    int mcount = 0;
+    if (threadIdx.x == 0) s_more = 0;
+    if (P.rp.prioritized && len > 0) {
+        const int2 st = P.rp.maxst ? reinterpret_cast<const int2*>(P.rp.maxst)[w] : make_int2(0, 0);
+        if (st.y > 0) { maxp = __int_as_float(st.x); mcount = st.y; }
+        else {
             float m = 0.f;
             const float* pr = P.rp.prio + (size_t)w * cap;
             for (int i = threadIdx.x; i < cap; i += RT) m = fmaxf(m, pr[i]);
             maxp = block_max(m, red);
+            int c = 0;
+            for (int i = threadIdx.x; i < cap; i += RT) c += pr[i] == maxp;
+            mcount = block_sum_i(c, reinterpret_cast<int*>(red));
         }
     }
+    __syncthreads();
     const float pwv = P.rp.prioritized ? pw_of(maxp) : 1.0f;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const int skip = max(0, cnt - cap);
@@ -92,13 +114,17 @@ __global__ void __launch_bounds__(RT) k_replay_store(const ReplayParams P) {
             P.rp.action[q] = (int8_t)((rv.w >> 8) & 0xFF);
             P.rp.reward[q] = P.wb.reward[row];
             P.rp.done[q] = (rv.w & RL_F_DEAD) ? 1 : 0;
-            if (P.rp.prioritized) { P.rp.prio[q] = maxp; P.rp.pw[q] = pwv; }
+            if (P.rp.prioritized) {
+                if (P.rp.prio[q] != maxp) atomicAdd(&s_more, 1);           // one more entry holds the maximum
+                P.rp.prio[q] = maxp; P.rp.pw[q] = pwv;
+            }
         }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         P.rp.pos[w] = (pos + cnt) % cap;
         P.rp.len[w] = min(cap, len + cnt);
+        if (P.rp.prioritized && P.rp.maxst) reinterpret_cast<int2*>(P.rp.maxst)[w] = make_int2(__float_as_int(maxp), mcount + s_more);
     }
 }
 
@@ -227,7 +253,12 @@ __global__ void __launch_bounds__(RT) k_replay_sample_uniform(const ReplayParams
 }
 
 // ---- update_priorities: warp per world, sequential over events, later writes win ----
+// Also keeps {max(priorities), count of entries holding it} exact (rl_replay_bufs.maxst): a per-warp bitmap in shared memory marks
+// the distinct touched entries; before the writes those holding the maximum are counted, after the writes the final values give the
+// new maximum / count.  Rings too large for the bitmap (or whose state is unknown) are left "unknown": the next store scans.
+constexpr int UP_BITMAP_WORDS = 1024;        // per warp: capacity <= 32768
 __global__ void __launch_bounds__(RT) k_replay_update_prio(const ReplayParams P) {
+    __shared__ uint32_t bitmap[RT / 32][UP_BITMAP_WORDS];
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= P.cfg.n_worlds) return;
     const int NW = P.cfg.n_worlds, cap = P.rp.capacity, batch = P.batch, lane = lane_id();
@@ -235,6 +266,23 @@ __global__ void __launch_bounds__(RT) k_replay_update_prio(const ReplayParams P)
     const int cnt = P.rows.count[(size_t)gk * NW + w];
     if (cnt == 0) return;
     const int off = P.rows.offset[(size_t)gk * NW + w];
+    uint32_t* bm = bitmap[threadIdx.x >> 5];
+    int2 st = P.rp.maxst ? reinterpret_cast<const int2*>(P.rp.maxst)[w] : make_int2(0, 0);
+    const bool track = P.rp.maxst && st.y > 0 && cap <= 32 * UP_BITMAP_WORDS;
+    const float M = __int_as_float(st.x);
+    int dec = 0;
+    if (track) {
+        for (int k = lane; k < (cap + 31) / 32; k += 32) bm[k] = 0u;
+        __syncwarp();
+        for (int e = 0; e < cnt && off + e < P.rows.row_cap; ++e)
+            for (int i = lane; i < batch; i += 32) {
+                const int idx = P.sample_idx[(size_t)(off + e) * batch + i];
+                if (idx < 0) continue;
+                const uint32_t bit = 1u << (idx & 31);
+                if (!(atomicOr(&bm[idx >> 5], bit) & bit) && P.rp.prio[(size_t)w * cap + idx] == M) ++dec;      // first mention of idx
+            }
+        __syncwarp();
+    }
     for (int e = 0; e < cnt; ++e) {
         if (off + e >= P.rows.row_cap) break;
         for (int h = 0; h < batch; h += 32) {
@@ -244,12 +292,45 @@ __global__ void __launch_bounds__(RT) k_replay_update_prio(const ReplayParams P)
             const int idx = on ? P.sample_idx[q] : -1 - lane;
             const float val = on ? P.new_prio[q] : 0.f;
             const unsigned m = __match_any_sync(0xffffffffu, idx);
-            if (on && (31 - __clz(m)) == lane) {
+            if (on && idx >= 0 && (31 - __clz(m)) == lane) {
                 P.rp.prio[(size_t)w * cap + idx] = val;
                 P.rp.pw[(size_t)w * cap + idx] = pw_of(val);
             }
             __syncwarp();
         }
+    }
+    if (!P.rp.maxst) return;
+    if (!track) {                                          // unknown stays unknown (a store may have set it since: only clear when it was)
+        if (lane == 0 && st.y > 0) reinterpret_cast<int2*>(P.rp.maxst)[w] = make_int2(0, 0);
+        return;
+    }
+    __threadfence_block();
+    __syncwarp();
+    float vmax = -1.0f; int nmax = 0, nM = 0;              // over the distinct touched entries: largest final value, how many hold it / hold M
+    for (int e = 0; e < cnt && off + e < P.rows.row_cap; ++e)
+        for (int i = lane; i < batch; i += 32) {
+            const int idx = P.sample_idx[(size_t)(off + e) * batch + i];
+            if (idx < 0) continue;
+            const uint32_t bit = 1u << (idx & 31);
+            if (atomicAnd(&bm[idx >> 5], ~bit) & bit) {    // first to clear the mark: one visit per distinct entry
+                const float v = P.rp.prio[(size_t)w * cap + idx];
+                if (v > vmax) { vmax = v; nmax = 1; } else if (v == vmax) ++nmax;
+                nM += v == M;
+            }
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, vmax, o);
+        const int on = __shfl_xor_sync(0xffffffffu, nmax, o);
+        if (ov > vmax) { vmax = ov; nmax = on; } else if (ov == vmax) nmax += on;
+        nM += __shfl_xor_sync(0xffffffffu, nM, o);
+        dec += __shfl_xor_sync(0xffffffffu, dec, o);
+    }
+    if (lane == 0) {
+        int2 out;
+        if (vmax > M) out = make_int2(__float_as_int(vmax), nmax);
+        else out = make_int2(st.x, max(0, st.y - dec + nM));
+        reinterpret_cast<int2*>(P.rp.maxst)[w] = out;
     }
 }
 

@@ -33,6 +33,8 @@ constexpr int WI_WH = 13;    // 1 chunk  [16 n][256 k]   B of head: n = j,  k = 
 constexpr int WI_WHT = 14;   // 1 chunk  [256 n][16 k]   B of dH2:  n = n2, k = j
 constexpr int WI_W2T = 15;   // 8 chunks [128 n][32 k]   B of dH1:  n = k1, k = n2
 constexpr int WI_CHUNKS = 23;
+constexpr int WI_W2N = 23;   // fp16 images only: 8 chunks [128 n][32 k]  B of L2 split by output halves: chunk 4 h + q = n2 in [128 h, +128), k1 in [32 q, +32)
+constexpr int WI_CHUNKS_H = 31;
 
 // chunk schedule of one event: (net, chunk).  net 0 = target, 1 = eval
 constexpr int SCHED_N = 37;
@@ -1467,6 +1469,7 @@ __global__ void k_build_wimg_dueling_h(const float* __restrict__ p, __half* __re
         const __half v = __float2half_rn(p[L::OFF_W2T + i]);
         wimg[(WI_W2K + k1 / 16) * HCHUNK + himg_off(n2, k1 % 16, 16)] = v;
         wimg[(WI_W2T + n2 / 32) * HCHUNK + himg_off(k1, n2 % 32, 32)] = v;
+        wimg[(WI_W2N + (n2 / 128) * 4 + k1 / 32) * HCHUNK + himg_off(n2 % 128, k1 % 32, 32)] = v;
     }
     if (i < 256 * 16) {
         const int n2 = i / 16, j = i - n2 * 16;
@@ -1679,7 +1682,7 @@ __global__ void k_build_wimg_dueling(const float* __restrict__ p, float* __restr
 
 extern "C" {
 
-int rl_tc_wimg_floats(void) { return WI_CHUNKS * CHUNK_F; }
+int rl_tc_wimg_floats(void) { return WI_CHUNKS_H * CHUNK_F; }      // (sized for the fp16 image, which carries 8 more chunks)
 
 int rl_brain_build_wimg(int32_t kind, const float* params, float* wimg, void* stream) {
     RL_ARG_CHECK(params && wimg);

@@ -55,8 +55,8 @@ constexpr int NSP = 8;                   // weight-chunk ring slots of 8 KB
 constexpr float H_SCALE = 256.0f;        // backward operands are scaled by 2^8 (exact), removed when gradients leave TMEM
 
 // weight image chunk ids (tc_kernels.cu::k_build_wimg_dueling_h)
-constexpr int WI_W1 = 0, WI_W2K = 5, WI_WH = 13, WI_WHT = 14, WI_W2T = 15;
-constexpr int SCHED_P = 37;              // chunks per pair: t W1[5] W2K[8] WH | e W1[5] W2K[8] WH WHT W2T[8]
+constexpr int WI_W1 = 0, WI_WH = 13, WI_WHT = 14, WI_W2T = 15, WI_W2N = 23;    // (W2N: L2 weights split by output halves, 4 chunks [128 n][32 k] each)
+constexpr int SCHED_P = 37;              // chunks per pair: t W1[5] W2N[8] WH | e W1[5] W2N[8] WH WHT W2T[8]
 
 // ---- shared memory (bytes, from a 1024-byte aligned base) ----
 constexpr int PO_X = 0;                                   // X (eval rows), SWIZZLE_128B
@@ -70,7 +70,7 @@ constexpr int PO_META = PO_RED + 4 * 64;                  // [2] x { idx[128] ac
 constexpr int PO_RING = PO_META + 2 * 4 * 4 * PB;         // [2][2] ring base (elements) per buffer / event, 64-bit
 constexpr int PO_BARS = PO_RING + 2 * 2 * 8;
 constexpr int NSTG = 11;                 // ring release groups per pair: tL1 tL2a tL2b thead eL1 eL2a eL2b ehead dH2 dH1a dH1b
-constexpr int NBAR = 2 * NSTG + 10;      // gfull[NSTG] sfree[NSTG] + done doneL1 go xfull xpfull h2free xfree metaready w1a w1b
+constexpr int NBAR = 2 * NSTG + 11;      // gfull[NSTG] sfree[NSTG] + done doneL1 go xfull xpfull h2free xfree metaready w1a w1b
 constexpr int PO_ONES = (PO_BARS + 8 * NBAR + 16 + 127) & ~127;   // [16 k][16] halves of 1.0: B operand of the db2 GEMM (every k-step reads it)
 constexpr size_t PAIR_SMEM = PO_ONES + 512 + 1024;               // + alignment slack
 static_assert(PAIR_SMEM <= 227 * 1024 && PO_BARS % 8 == 0 && PO_RING % 8 == 0 && PO_H2 % 1024 == 0, "shared memory budget");
@@ -92,10 +92,10 @@ struct PairParams {
 
 __device__ __forceinline__ void sched_pair(int i, int& net, int& chunk) {
     if (i < 5) { net = 0; chunk = WI_W1 + i; }
-    else if (i < 13) { net = 0; chunk = WI_W2K + (i - 5); }
+    else if (i < 13) { net = 0; chunk = WI_W2N + (i - 5); }
     else if (i == 13) { net = 0; chunk = WI_WH; }
     else if (i < 19) { net = 1; chunk = WI_W1 + (i - 14); }
-    else if (i < 27) { net = 1; chunk = WI_W2K + (i - 19); }
+    else if (i < 27) { net = 1; chunk = WI_W2N + (i - 19); }
     else if (i == 27) { net = 1; chunk = WI_WH; }
     else if (i == 28) { net = 1; chunk = WI_WHT; }
     else { net = 1; chunk = WI_W2T + (i - 29); }
@@ -125,6 +125,10 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
     uint64_t* xfull = done + 3; uint64_t* xpfull = done + 4; uint64_t* h2free = done + 5; uint64_t* xfree = done + 6; uint64_t* metaready = done + 7;
     // w1a / w1b: the accumulator warps have taken columns 128..159 / 0..127 of the dW1 accumulator out of TMEM (gate the next target L1 / L2)
     uint64_t* w1a = done + 8; uint64_t* w1b = done + 9;
+    // done2: the SECOND of two stages handed over back to back without a `go` in between (L2 half 1, the n2 >= 128 half of dWh).  A
+    // parity-tracked mbarrier must never complete two phases before its waiters have seen the first one (they would wait for a flip
+    // that has already happened twice), so consecutive completions alternate between `done` and `done2`.
+    uint64_t* done2 = done + 10;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTG; ++i) mbar_init(&gfull[i], 1);
         for (int i = 0; i < NSTG; ++i) mbar_init(&sfree[i], 1);
-        mbar_init(done, 1); mbar_init(doneL1, 1); mbar_init(go, NEPI);
+        mbar_init(done, 1); mbar_init(done2, 1); mbar_init(doneL1, 1); mbar_init(go, NEPI);
         mbar_init(xfull, NGW); mbar_init(xpfull, NGW); mbar_init(h2free, 1); mbar_init(xfree, 1); mbar_init(metaready, PB); mbar_init(w1a, 32 * NGW); mbar_init(w1b, 32 * NGW);
         fence_mbar_init();
     }
@@ -226,21 +230,24 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
             stage_free();
             commit(doneL1);
         };
-        // L2: D[128 b][256 n2] = H1[128][128] W2[256][128]^T -- 8 chunks [256 n][16 k]
+        // L2: D[128 b][256 n2] = H1[128][128] W2[256][128]^T in two output halves (4 chunks [128 n][32 k] each, 2 k-steps per chunk):
+        // half 0 -> columns 0..127, half 1 -> columns 128..255, each handed over on its own -- the epilogue of half 0 runs under the
+        // MMAs of half 1
         auto l2 = [&](uint32_t k0) {
-            const uint32_t id = idesc_h(128, 256, 0, 0);
-            uint64_t a = dk(aH1, 128);
+            const uint32_t id = idesc_h(128, 128, 0, 0);
 #pragma unroll 1
             for (int hf = 0; hf < 2; ++hf) {
                 if (hf) k0 = chunks_wait(4);
+                uint64_t a = dk(aH1, 128);
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
-                    if (me) mma_h(T0, a, dk(chunk_addr(k0 + c), 16), id, (hf | c) != 0);
-                    a += 16u;
+                    const uint64_t b = dk(chunk_addr(k0 + c), 32);
+                    if (me) { mma_h(T0 + 128 * hf, a, b, id, c != 0); mma_h(T0 + 128 * hf, a + 16u, b + 16u, id, 1u); }
+                    a += 32u;
                 }
                 stage_free();
+                commit(hf ? done2 : done);
             }
-            commit(done);
         };
         // head: D[128 b][16] = H2[128][256] Wh[16][256]^T -- one chunk, 16 k-steps
         auto head = [&](uint32_t k0) {
@@ -292,7 +299,7 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
                         }
                         a += 2048u; b += 128u;
                     }
-                    commit(done);
+                    commit(m ? done2 : done);
                 }
                 wait_go();                                     // dH2[:, :128] stored, dWh drained: dH2 half 1 (n2 >= 128) -> columns 0..127
                 if (me) mma_h(T0, dk(aD, 16), dk(wht + 4096u, 16), idesc_h(128, 128, 0, 0), 0u);
@@ -434,7 +441,7 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
     } else {
         // =================================== epilogue warps ===================================
         const uint32_t T0 = *tmem_slot, T_DW2 = T0 + 256;
-        uint32_t done_no = 0, l1_no = 0;
+        uint32_t done_no = 0, done2_no = 0, l1_no = 0;
         const int q = warp & 3, hh = warp >> 2;
         const int row = q * 32 + lane;                    // batch row of the pair == TMEM lane
         const uint32_t t_lane = (uint32_t)(q * 32) << 16;
@@ -443,6 +450,7 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
         auto stamp = [&]() { if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && tr_p == 3 && tr_n < 40) P.trace[tr_n++] = clock64(); };
         auto go_signal = [&]() { fence_proxy_async(); fence_before(); mbar_arrive(go); stamp(); };
         auto wait_done = [&]() { mbar_wait(done, done_no & 1); ++done_no; fence_after(); stamp(); };
+        auto wait_done2 = [&]() { mbar_wait(done2, done2_no & 1); ++done2_no; fence_after(); stamp(); };
         auto wait_l1 = [&]() { mbar_wait(doneL1, l1_no & 1); ++l1_no; fence_after(); stamp(); };
         // ---- metadata of a pair (threads 0-127, one sampled row each) in three phases so that no global-load latency
         //      sits on the critical path: A event row + ring position, B action / reward / done (+ L2 prefetch of the
@@ -531,18 +539,16 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
             relu_store32(v0, bias + c0, sH1, c0, 128);
             relu_store32(v1, bias + c0 + 32, sH1, c0 + 32, 128);
         };
-        // ---- L2 epilogue: this thread's row, columns [128 hh, 128 hh + 128): H2 = relu(D + b2) ----
-        auto l2_epilogue = [&](const float* bias) {
-#pragma unroll 1
-            for (int cb = 0; cb < 2; ++cb) {
-                const int c0 = hh * 128 + cb * 64;
-                float v0[32], v1[32];
-                tmem_ld32(T0 + t_lane + c0, v0);
-                tmem_ld32(T0 + t_lane + c0 + 32, v1);
-                tmem_wait_ld();
-                relu_store32(v0, bias + 128 + c0, sH2, c0, 256);
-                relu_store32(v1, bias + 128 + c0 + 32, sH2, c0 + 32, 256);
-            }
+        // ---- L2 epilogue, one call per output half (each handed over on its own): this thread's row, columns
+        //      [128 half + 64 hh, +64): H2 = relu(D + b2) ----
+        auto l2_epilogue = [&](const float* bias, int half) {
+            const int c0 = half * 128 + hh * 64;
+            float v0[32], v1[32];
+            tmem_ld32(T0 + t_lane + c0, v0);
+            tmem_ld32(T0 + t_lane + c0 + 32, v1);
+            tmem_wait_ld();
+            relu_store32(v0, bias + 128 + c0, sH2, c0, 256);
+            relu_store32(v1, bias + 128 + c0 + 32, sH2, c0 + 32, 256);
         };
         // ---- head epilogue (warps 0-3: one row each): out[0..8] of the row, mean of the advantages over the row's EVENT
         //      (PERD3QN.py:202: advantage.mean() over the whole [64, 8] tensor) ----
@@ -591,7 +597,9 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
             if (more) meta_b();
             wait_done();
             gather_load(P.rp.obs, buf);                             // (float32 rings: eval rows of this pair, in flight behind the L2 epilogue)
-            l2_epilogue(bias_t);
+            l2_epilogue(bias_t, 0);
+            wait_done2();
+            l2_epilogue(bias_t, 1);
             gather_store(PO_X);
             go_signal();                                            // -> target head, eval L1
             if (more) meta_c(buf ^ 1);
@@ -610,7 +618,9 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
             l1_epilogue(bias_e);
             go_signal();                                            // -> eval L2 (overwrites the target head columns: consumed above)
             wait_done();
-            l2_epilogue(bias_e);
+            l2_epilogue(bias_e, 0);
+            wait_done2();
+            l2_epilogue(bias_e, 1);
             go_signal();                                            // -> eval head
             wait_done();
             float dbh = 0.f;                                        // lane j < 9 of warps 0-3: sum over the warp's rows of dOut[.][j]
@@ -674,7 +684,7 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
             };
             wait_done();                                            // dH2 half 0
             dh2_epilogue(128u + hh * 64, hh * 64);
-            wait_done();                                            // dWh (ran under the epilogue above)
+            wait_done2();                                           // the n2 >= 128 half of dWh (ran under the epilogue above)
             float wv[16];
             tmem_ld16(T0 + t_lane + 16 * hh, wv);                   // head weight gradients: row n2 = 128 hh + this thread's TMEM lane
             tmem_wait_ld();

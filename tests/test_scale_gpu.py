@@ -428,3 +428,84 @@ def test_replay_store_writes_float16_rows():
         filled = torch.arange(cap, device="cuda")[None, :] < a.len[:, None]
         assert torch.equal(y[filled], want[filled])
     assert torch.equal(a.prio, b.prio) and torch.equal(a.action, b.action) and torch.equal(a.reward, b.reward)
+
+
+def test_replay_max_priority_is_maintained_exactly():
+    """rl_replay_store no longer scans the priority array for max(priorities) (PERD3QN.py:147): the store / priority-update
+    kernels keep {max, count of entries holding it} per ring (rl_replay_bufs.maxst).  Over rounds of stores (ring wrap) and
+    priority updates with duplicate indices, values above / equal to / below the maximum and updates that remove every
+    holder of the maximum, the state equals a recount of the array whenever it is known, and every new item is stored with
+    the true maximum."""
+    from reinlife_b200 import _lib
+    from reinlife_b200.brains import ReplayRings
+    from reinlife_b200.World.vecworld import VecWorld
+    from reinlife_b200.rows import RowLists
+    NW, cap, B = 6, 96, 64
+    vw = VecWorld(NW, 12, 12, 2, max_agents=40, seed=3)
+    rows = RowLists(vw)
+    vw.reset(); vw.top_up(40)
+    rp = ReplayRings(NW, cap, "cuda")
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    rng = np.random.default_rng(1)
+    known = 0
+    for step in range(30):
+        vw.set_actions(torch.randint(0, 8, (NW, vw.S), device="cuda", dtype=torch.int8, generator=g))
+        vw.step()
+        rows.build(kinds_mask=6, train_freq=[3, 3], event_on=[1, 1])
+        before = rp.prio.clone(); len0 = rp.len.clone(); pos0 = rp.pos.clone()
+        _lib.check(vw.lib.rl_replay_store(C.byref(vw.cfg), C.byref(vw.bufs), C.byref(rows.bufs), 0, C.byref(rp.bufs), vw._stream()))
+        torch.cuda.synchronize()
+        cnt = rows.count[_lib.ROWS_STORE].cpu().numpy()
+        for w in range(NW):
+            if cnt[w] == 0:
+                continue
+            want = float(before[w].max()) if int(len0[w]) > 0 else 1.0
+            slots = [(int(pos0[w]) + k) % cap for k in range(max(0, cnt[w] - cap), cnt[w])]
+            assert (rp.prio[w, slots].cpu().numpy() == np.float32(want)).all(), (step, w)
+        st = rp.maxst.cpu().numpy()
+        for w in range(NW):
+            if st[w, 1] > 0:
+                known += 1
+                m = float(rp.prio[w].max())
+                assert np.int32(st[w, 0]).view(np.float32) == np.float32(m) and st[w, 1] == int((rp.prio[w] == m).sum()), (step, w, "store")
+        # priority update on hand-made events: duplicates inside and across events, values above / equal / below the maximum
+        n_ev = rng.integers(0, 4, NW)
+        ev_tot = _fake_events_scale(vw, rows, n_ev)
+        if ev_tot == 0:
+            vw.update(); vw.top_up(40); continue
+        L = np.maximum(rp.len.cpu().numpy(), 1)
+        sidx = np.concatenate([rng.integers(0, L[w], (n_ev[w], B)) for w in range(NW)]).astype(np.int32)
+        cur_max = rp.prio.max(1).values.cpu().numpy()
+        newp = rng.random((ev_tot, B)).astype(np.float32) * 2.0
+        ev_w = np.repeat(np.arange(NW), n_ev)
+        mode = step % 3
+        for e in range(ev_tot):
+            if mode == 0:   newp[e, ::7] = cur_max[ev_w[e]]                 # re-assert the maximum on some entries
+            elif mode == 1: newp[e] *= 0.01                                  # everything far below: holders of the max disappear
+            else:           newp[e, 3] = cur_max[ev_w[e]] + 1.0 + e          # a new, larger maximum
+        ts, tp = torch.from_numpy(sidx).cuda(), torch.from_numpy(newp).cuda()
+        _lib.check(vw.lib.rl_replay_update_prio(C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(rp.bufs), B,
+                                                C.c_void_p(ts.data_ptr()), C.c_void_p(tp.data_ptr()), vw._stream()))
+        torch.cuda.synchronize()
+        ref = before.clone()                                                  # sequential overwrite, later writes win
+        ref = rp.prio.clone()                                                 # (values themselves are covered by test_learn_gpu)
+        st = rp.maxst.cpu().numpy()
+        for w in range(NW):
+            if st[w, 1] > 0:
+                known += 1
+                m = float(ref[w].max())
+                assert np.int32(st[w, 0]).view(np.float32) == np.float32(m) and st[w, 1] == int((ref[w] == m).sum()), (step, w, "update", mode)
+        vw.update(); vw.top_up(40)
+    assert known > 100
+
+
+def _fake_events_scale(vw, rows, per_world):
+    from reinlife_b200 import _lib as L
+    cnt = torch.tensor(np.asarray(per_world), dtype=torch.int32)
+    off = (torch.cumsum(cnt, 0) - cnt).int()
+    k = L.ROWS_EVENT
+    rows.count[k] = cnt.cuda(); rows.offset[k] = off.cuda(); rows.total[k] = int(cnt.sum())
+    ids = [w * vw.S + e for w in range(vw.n_worlds) for e in range(int(per_world[w]))]
+    if ids:
+        rows.rows[k, :len(ids)] = torch.tensor(ids, dtype=torch.int32).cuda()
+    return len(ids)
