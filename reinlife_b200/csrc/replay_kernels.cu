@@ -257,67 +257,86 @@ __global__ void __launch_bounds__(RT) k_replay_sample_uniform(const ReplayParams
 // the distinct touched entries; before the writes those holding the maximum are counted, after the writes the final values give the
 // new maximum / count.  Rings too large for the bitmap (or whose state is unknown) are left "unknown": the next store scans.
 constexpr int UP_BITMAP_WORDS = 1024;        // per warp: capacity <= 32768
+constexpr int UP_K = 10;                     // entries per lane and chunk: 320 = five 64-row events, all their loads in flight at once
 __global__ void __launch_bounds__(RT) k_replay_update_prio(const ReplayParams P) {
     __shared__ uint32_t bitmap[RT / 32][UP_BITMAP_WORDS];
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= P.cfg.n_worlds) return;
     const int NW = P.cfg.n_worlds, cap = P.rp.capacity, batch = P.batch, lane = lane_id();
     const int gk = P.gene * RL_N_ROW_KINDS + RL_ROWS_EVENT;
-    const int cnt = P.rows.count[(size_t)gk * NW + w];
+    int cnt = P.rows.count[(size_t)gk * NW + w];
     if (cnt == 0) return;
     const int off = P.rows.offset[(size_t)gk * NW + w];
+    cnt = min(cnt, P.rows.row_cap - off);
+    const int n_all = cnt * batch;                       // entries of this world, in event order (later writes win)
+    const int32_t* sidx = P.sample_idx + (size_t)off * batch;
+    const float* nprio = P.new_prio + (size_t)off * batch;
+    float* prio = P.rp.prio + (size_t)w * cap;
+    float* pw = P.rp.pw + (size_t)w * cap;
     uint32_t* bm = bitmap[threadIdx.x >> 5];
-    int2 st = P.rp.maxst ? reinterpret_cast<const int2*>(P.rp.maxst)[w] : make_int2(0, 0);
+    const int2 st = P.rp.maxst ? reinterpret_cast<const int2*>(P.rp.maxst)[w] : make_int2(0, 0);
     const bool track = P.rp.maxst && st.y > 0 && cap <= 32 * UP_BITMAP_WORDS;
     const float M = __int_as_float(st.x);
     int dec = 0;
-    if (track) {
+    if (track) {     // pass A: the distinct entries about to be overwritten that hold the maximum (old values, before any write)
         for (int k = lane; k < (cap + 31) / 32; k += 32) bm[k] = 0u;
         __syncwarp();
-        for (int e = 0; e < cnt && off + e < P.rows.row_cap; ++e)
-            for (int i = lane; i < batch; i += 32) {
-                const int idx = P.sample_idx[(size_t)(off + e) * batch + i];
-                if (idx < 0) continue;
-                const uint32_t bit = 1u << (idx & 31);
-                if (!(atomicOr(&bm[idx >> 5], bit) & bit) && P.rp.prio[(size_t)w * cap + idx] == M) ++dec;      // first mention of idx
-            }
+        for (int c0 = 0; c0 < n_all; c0 += 32 * UP_K) {
+            int idx[UP_K]; float old[UP_K];
+#pragma unroll
+            for (int k = 0; k < UP_K; ++k) { const int j = c0 + k * 32 + lane; idx[k] = j < n_all ? sidx[j] : -1; }
+#pragma unroll
+            for (int k = 0; k < UP_K; ++k) old[k] = idx[k] >= 0 ? prio[idx[k]] : 0.f;
+#pragma unroll
+            for (int k = 0; k < UP_K; ++k)
+                if (idx[k] >= 0) {
+                    const uint32_t bit = 1u << (idx[k] & 31);
+                    if (!(atomicOr(&bm[idx[k] >> 5], bit) & bit) && old[k] == M) ++dec;      // first mention of the entry
+                }
+        }
         __syncwarp();
     }
-    for (int e = 0; e < cnt; ++e) {
-        if (off + e >= P.rows.row_cap) break;
-        for (int h = 0; h < batch; h += 32) {
-            const int i = h + lane;
-            const bool on = i < batch;
-            const size_t q = (size_t)(off + e) * batch + i;
-            const int idx = on ? P.sample_idx[q] : -1 - lane;
-            const float val = on ? P.new_prio[q] : 0.f;
-            const unsigned m = __match_any_sync(0xffffffffu, idx);
-            if (on && idx >= 0 && (31 - __clz(m)) == lane) {
-                P.rp.prio[(size_t)w * cap + idx] = val;
-                P.rp.pw[(size_t)w * cap + idx] = pw_of(val);
-            }
+    for (int c0 = 0; c0 < n_all; c0 += 32 * UP_K) {      // the writes, 32 entries at a time in order; inside a group the last lane wins
+        int idx[UP_K]; float val[UP_K];
+#pragma unroll
+        for (int k = 0; k < UP_K; ++k) {
+            const int j = c0 + k * 32 + lane;
+            idx[k] = j < n_all ? sidx[j] : -1;
+            val[k] = j < n_all ? nprio[j] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < UP_K; ++k) {
+            if (c0 + k * 32 >= n_all) break;                                                  // (warp-uniform)
+            const unsigned m = __match_any_sync(0xffffffffu, idx[k] >= 0 ? idx[k] : -1 - lane);
+            if (idx[k] >= 0 && (31 - __clz(m)) == lane) { prio[idx[k]] = val[k]; pw[idx[k]] = pw_of(val[k]); }
             __syncwarp();
         }
     }
     if (!P.rp.maxst) return;
-    if (!track) {                                          // unknown stays unknown (a store may have set it since: only clear when it was)
+    if (!track) {                                          // unknown stays unknown; a known state this kernel could not follow is dropped
         if (lane == 0 && st.y > 0) reinterpret_cast<int2*>(P.rp.maxst)[w] = make_int2(0, 0);
         return;
     }
     __threadfence_block();
     __syncwarp();
-    float vmax = -1.0f; int nmax = 0, nM = 0;              // over the distinct touched entries: largest final value, how many hold it / hold M
-    for (int e = 0; e < cnt && off + e < P.rows.row_cap; ++e)
-        for (int i = lane; i < batch; i += 32) {
-            const int idx = P.sample_idx[(size_t)(off + e) * batch + i];
-            if (idx < 0) continue;
-            const uint32_t bit = 1u << (idx & 31);
-            if (atomicAnd(&bm[idx >> 5], ~bit) & bit) {    // first to clear the mark: one visit per distinct entry
-                const float v = P.rp.prio[(size_t)w * cap + idx];
-                if (v > vmax) { vmax = v; nmax = 1; } else if (v == vmax) ++nmax;
-                nM += v == M;
+    float vmax = -1.0f; int nmax = 0, nM = 0;              // pass C, over the distinct touched entries: largest final value, how many hold it / hold M
+    for (int c0 = 0; c0 < n_all; c0 += 32 * UP_K) {
+        int idx[UP_K]; float fin[UP_K];
+#pragma unroll
+        for (int k = 0; k < UP_K; ++k) { const int j = c0 + k * 32 + lane; idx[k] = j < n_all ? sidx[j] : -1; }
+#pragma unroll
+        for (int k = 0; k < UP_K; ++k) fin[k] = idx[k] >= 0 ? prio[idx[k]] : 0.f;
+#pragma unroll
+        for (int k = 0; k < UP_K; ++k)
+            if (idx[k] >= 0) {
+                const uint32_t bit = 1u << (idx[k] & 31);
+                if (atomicAnd(&bm[idx[k] >> 5], ~bit) & bit) {    // first to clear the mark: one visit per distinct entry
+                    const float v = fin[k];
+                    if (v > vmax) { vmax = v; nmax = 1; } else if (v == vmax) ++nmax;
+                    nM += v == M;
+                }
             }
-        }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, vmax, o);
