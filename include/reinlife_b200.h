@@ -350,6 +350,13 @@ int rl_sumtree_sample(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t
  * events into learn->grad, grad[n_train] = events that trained.  learn->kind = RL_MODEL_DQN, learn->batch = 64. */
 int rl_brain_learn_perdqn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
                           const int32_t* sample_idx, const float* ev_weight, const rl_learn_bufs* learn, void* stream);
+/* rl_brain_learn_dqn / rl_brain_learn_perdqn on the tensor cores (csrc/tc_dqn_kernels.cu: 128-row batch-major tiles, fp16 operands /
+ * fp32 accumulation, both nets' operand images resident in shared memory, all weight gradients resident in TMEM).  Same contract and
+ * outputs at the tolerance of the dueling tensor-core kernels; the Environment's choice for DQN / PERDQN under precision="fp16". */
+int rl_brain_learn_dqn_p(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                         const int32_t* sample_idx, const rl_learn_bufs* learn, void* stream);
+int rl_brain_learn_perdqn_p(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
+                            const int32_t* sample_idx, const float* ev_weight, const rl_learn_bufs* learn, void* stream);
 
 /* Memory.update (:305-308) for the 64 sampled leaves of every trained event: event order, batch order, duplicates
  * included, priority = powf(|error| + 0.01, 0.6), float64 propagation. */

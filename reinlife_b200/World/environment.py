@@ -419,7 +419,9 @@ class Environment:
             _lib.check(lib.rl_replay_sample_uniform(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
                                                     C.c_int32(32), C.c_uint64(self._t_key), C.c_int32(it), C.c_int32(5), C.c_int32(b.min_buffer),
                                                     C.c_void_p(b._dev.sample_idx.data_ptr()), None, st))
-            _lib.check(lib.rl_brain_learn_dqn(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
+            # precision="fp16": the tensor-core iteration kernel (csrc/tc_dqn_kernels.cu); "tf32" / "fp32": the fp32 tile kernel
+            fn = lib.rl_brain_learn_dqn_p if self._learn_fp16 else lib.rl_brain_learn_dqn
+            _lib.check(fn(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
                                               C.c_void_p(b._dev.sample_idx.data_ptr()), C.byref(b._dev.learn_bufs), st))
             if self.dist:
                 self._allreduce_grads([g])
@@ -438,7 +440,8 @@ class Environment:
         _lib.check(lib.rl_sumtree_sample(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
                                          C.byref(tr.bufs), C.c_int32(64), C.c_uint64(self._t_key), C.c_void_p(dev.sample_idx.data_ptr()),
                                          C.c_void_p(tr.ev_weight.data_ptr()), st))
-        _lib.check(lib.rl_brain_learn_perdqn(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
+        fn = lib.rl_brain_learn_perdqn_p if self._learn_fp16 else lib.rl_brain_learn_perdqn
+        _lib.check(fn(C.byref(w.cfg), C.byref(self._rb_event), C.c_int32(g), C.byref(b._replay.bufs),
                                              C.c_void_p(dev.sample_idx.data_ptr()), C.c_void_p(tr.ev_weight.data_ptr()),
                                              C.byref(dev.learn_bufs), st))
         if self.dist:

@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["c_api.cu", "world_kernels.cu", "stats_kernels.cu", "rows_kernels.cu", "brain_kernels.cu", "replay_kernels.cu", "learn_kernels.cu", "learn_rows_kernels.cu", "ppo_kernels.cu", "sumtree_kernels.cu", "tc_selftest.cu", "tc_issue_probe.cu", "tc_kernels.cu", "tc_pair_kernels.cu", "tc_act_kernels.cu"]
+SOURCES = ["c_api.cu", "world_kernels.cu", "stats_kernels.cu", "rows_kernels.cu", "brain_kernels.cu", "replay_kernels.cu", "learn_kernels.cu", "learn_rows_kernels.cu", "ppo_kernels.cu", "sumtree_kernels.cu", "tc_selftest.cu", "tc_issue_probe.cu", "tc_kernels.cu", "tc_pair_kernels.cu", "tc_act_kernels.cu", "tc_dqn_kernels.cu"]
 OUT = os.path.join(os.path.dirname(HERE), "libreinlife_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -206,6 +206,13 @@ __global__ void k_count_valid(const int32_t* __restrict__ sample_idx, int batch,
 
 }  // namespace
 
+// (shared with tc_dqn_kernels.cu)
+int rl_count_valid_launch(const int32_t* sample_idx, int batch, const int32_t* ev_total, float* out, void* stream) {
+    k_count_valid<<<1, 256, 0, (cudaStream_t)stream>>>(sample_idx, batch, ev_total, out);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
+}
+
 extern "C" {
 
 int rl_brain_learn_dqn(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,

@@ -509,3 +509,65 @@ def _fake_events_scale(vw, rows, per_world):
     if ids:
         rows.rows[k, :len(ids)] = torch.tensor(ids, dtype=torch.int32).cuda()
     return len(ids)
+
+
+def _dqn_parts(d):
+    return (("W1", 0, d.off_b1), ("b1", d.off_b1, d.off_w2t), ("W2", d.off_w2t, d.off_b2), ("b2", d.off_b2, d.off_wh),
+            ("Wh", d.off_wh, d.off_bh), ("bh", d.off_bh, d.off_bh + 8))
+
+
+@pytest.mark.parametrize("mode", ["dqn", "perdqn"])
+def test_dqn_tensor_core_kernel_matches_fp32_kernel(mode):
+    """k_learn_dqn_p<MODE> (tcgen05, fp16 operands, batch-major 128-row tiles, resident weight images and gradients) vs
+    k_learn_dqn<MODE> (fp32 FMA, itself checked against the oracle above) at >= 5 tiles per persistent CTA, with skipped
+    events, done rows and -- PERDQN -- per-event importance weights: summed gradients within 1 % of each tensor's gradient
+    scale, per-event losses / errors within 2 %, the same event count."""
+    from reinlife_b200 import _lib
+    from reinlife_b200.brains import DeviceBrain, ReplayRings
+    from reinlife_b200.Models import packing
+    z, z1 = _golden2(), golden()
+    rng = np.random.default_rng(23)
+    B = 32 if mode == "dqn" else 64
+    NW, cap, n_items = 64, 128, 100
+    per_world = [48] * NW if mode == "dqn" else [24] * NW
+    per_world[7] = 0
+    vw, rows = _mk(NW)
+    w0, tgt = _sd2(z, "train_dqn/w0"), _sd2(z, "train_dqn/target")
+    rp = ReplayRings(NW, cap, "cuda", prioritized=False)
+    _fill_rings(rp, rng, z1["obs"], n_items)
+    n_ev = _fake_events(vw, rows, per_world)
+    assert n_ev * B >= 5 * 128 * vw.lib.rl_learn_grid()
+    sidx = rng.integers(0, n_items, size=(n_ev, B)).astype(np.int32)
+    for e in rng.integers(0, n_ev, 25):
+        sidx[e] = -1
+    evw = torch.from_numpy(rng.uniform(0.2, 1.0, n_ev).astype(np.float32)).cuda()
+    out = {}
+    for kern in ("fp32", "tc"):
+        brain = DeviceBrain(1, w0, "cuda", lr=5e-4, gamma=0.98, batch=B)
+        brain.load_state_dict(tgt, target=True)
+        brain.alloc_learn(rows.row_cap)
+        brain.sample_idx[:n_ev] = torch.from_numpy(sidx).cuda()
+        args = [C.byref(vw.cfg), C.byref(rows.bufs), 0, C.byref(rp.bufs), C.c_void_p(brain.sample_idx.data_ptr())]
+        if mode == "perdqn":
+            args.append(C.c_void_p(evw.data_ptr()))
+        args += [C.byref(brain.learn_bufs), vw._stream()]
+        fn = {("dqn", "fp32"): vw.lib.rl_brain_learn_dqn, ("dqn", "tc"): vw.lib.rl_brain_learn_dqn_p,
+              ("perdqn", "fp32"): vw.lib.rl_brain_learn_perdqn, ("perdqn", "tc"): vw.lib.rl_brain_learn_perdqn_p}[(mode, kern)]
+        _lib.check(fn(*args))
+        torch.cuda.synchronize()
+        out[kern] = (brain.grad.cpu().numpy().copy(), brain.loss[:n_ev].cpu().numpy().copy(),
+                     brain.new_prio.reshape(-1)[:n_ev * B].cpu().numpy().copy())
+    d, m = packing.dims(1), packing.grad_mask(1)
+    g32, l32, p32 = out["fp32"]
+    gtc, ltc, ptc = out["tc"]
+    nt = d.n_train
+    assert g32[nt] == gtc[nt] == n_ev - len({int(e) for e in np.where(sidx[:, 0] < 0)[0]})
+    for name, lo, hi in _dqn_parts(d):
+        a, b = g32[lo:hi] * m[lo:hi], gtc[lo:hi] * m[lo:hi]
+        scale = np.abs(a).max()
+        assert scale > 0 and np.abs(a - b).max() / scale < 1e-2, (mode, name, np.abs(a - b).max() / scale, scale)
+    valid = sidx[:, 0] >= 0
+    np.testing.assert_allclose(ltc[valid], l32[valid], rtol=2e-2, atol=1e-3)
+    if mode == "perdqn":
+        v = np.repeat(valid, B)
+        np.testing.assert_allclose(ptc[v], p32[v], rtol=2e-2, atol=2e-2)
