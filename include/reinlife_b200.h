@@ -357,6 +357,10 @@ int rl_brain_learn_dqn_p(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int3
                          const int32_t* sample_idx, const rl_learn_bufs* learn, void* stream);
 int rl_brain_learn_perdqn_p(const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
                             const int32_t* sample_idx, const float* ev_weight, const rl_learn_bufs* learn, void* stream);
+/* get_action of the DQN-layout brains (DQN, PERDQN) on the tensor cores (csrc/tc_dqn_kernels.cu::k_act_dqn_p): as rl_brain_act_all for
+ * one gene, operand images built in the kernel from brain->params. */
+int rl_brain_act_dqn_p(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_rows_bufs* rows, int32_t gene,
+                       const rl_brain_act* brain, uint64_t t_act, float* q_out, void* stream);
 
 /* Memory.update (:305-308) for the 64 sampled leaves of every trained event: event order, batch order, duplicates
  * included, priority = powf(|error| + 0.01, 0.6), float64 propagation. */

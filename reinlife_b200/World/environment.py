@@ -218,11 +218,16 @@ class Environment:
                                                      C.c_void_p(self._eps.data_ptr()), C.c_void_p(self._seen.data_ptr()),
                                                      w._stream()))
             tc = [g for g, b in enumerate(self.brains) if self.precision == "tf32" and b.KIND == _lib.MODEL_DUELING and self._act_tc]
+            # DQN-layout brains (DQN, PERDQN) under precision="fp16": k_act_dqn_p (q_out is not produced on this path)
+            tcq = [g for g, d in enumerate(self._act_descs) if self._learn_fp16 and d.kind == _lib.MODEL_DQN and self._act_tc and q_out is None]
             descs = self._act_descs
-            if tc:                                   # dueling brains act on the tensor cores; the others on the fp32 path
-                descs = (_lib.BrainAct * G)(*[_lib.BrainAct(-1 if g in tc else d.kind, d.rule, d.params, d.epsilon)
+            if tc or tcq:                            # these brains act on the tensor cores; the others on the fp32 path
+                descs = (_lib.BrainAct * G)(*[_lib.BrainAct(-1 if (g in tc or g in tcq) else d.kind, d.rule, d.params, d.epsilon)
                                               for g, d in enumerate(self._act_descs)])
-            if len(tc) < G:
+            for g in tcq:
+                _lib.check(w.lib.rl_brain_act_dqn_p(C.byref(w.cfg), C.byref(w.bufs), C.byref(self.rows.bufs), C.c_int32(g),
+                                                    C.byref(self._act_descs[g]), C.c_uint64(w.t + 1), None, w._stream()))
+            if len(tc) + len(tcq) < G:
                 _lib.check(w.lib.rl_brain_act_all(C.byref(w.cfg), C.byref(w.bufs), C.byref(self.rows.bufs), descs, G,
                                                   C.c_uint64(w.t + 1), C.c_void_p(q_out), C.c_void_p(self._prob.data_ptr()), w._stream()))
             for g in tc:

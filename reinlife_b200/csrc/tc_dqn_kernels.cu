@@ -458,6 +458,216 @@ __global__ void __launch_bounds__(NTH, 1) k_learn_dqn_p(const DqnParams P) {
     if (warp == 8) tmem_dealloc(*tmem_slot, 512);
 }
 
+// =====================================================================================================
+// k_act_dqn_p -- brain.get_action of the DQN-layout brains (DQN.py:126-139, PERDQN.py:101-111) in the same form: 128-row tiles of
+// the brain's ALL row list, the net's operand images resident in shared memory, L1 / L2 / head accumulators in disjoint TMEM
+// columns (the next tile's L1 runs under this tile's head epilogue), rows gathered float32 -> fp16 by eight warps.  Epilogue =
+// k_brain_act's: first-max argmax, exploration draws keyed (t_act, slot) with the family's comparison (coin < eps / u <= eps).
+// =====================================================================================================
+constexpr int QO_X = 0, QO_H1 = QO_X + XIMG, QO_H2 = QO_H1 + PB * N1 * 2, QO_W = QO_H2 + PB * N2 * 2, QO_BIAS = QO_W + WNET;
+constexpr int QO_BARS = QO_BIAS + 4 * 208;
+constexpr size_t QACT_SMEM = QO_BARS + 8 * 8 + 16 + 1024;
+static_assert(QO_W % 128 == 0 && QO_BARS % 8 == 0, "layout");
+
+struct DqnActParams {
+    rl_world_cfg cfg;
+    rl_agent_rec* rec;
+    const float* obs;          // obs_state
+    const int32_t* rows;       // row list of this brain, kind ALL
+    const int32_t* total;      // device scalar
+    const float* params;
+    const double* epsilon;
+    uint64_t t_act;
+    float* q_out;              // [row_cap][8] or null
+    int32_t rule;              // RL_ACT_DQN / RL_ACT_PERDQN
+};
+
+__global__ void __launch_bounds__(NTH, 1) k_act_dqn_p(const DqnActParams P) {
+    using L = Layout<RL_MODEL_DQN>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __half* sH1 = reinterpret_cast<__half*>(smem + QO_H1);
+    __half* sH2 = reinterpret_cast<__half*>(smem + QO_H2);
+    float* bias = reinterpret_cast<float*>(smem + QO_BIAS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + QO_BARS);
+    uint64_t* done = bars; uint64_t* doneL1 = bars + 1; uint64_t* go = bars + 2; uint64_t* xfull = bars + 3; uint64_t* xfree = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = *P.total;
+    const int n_tiles = (total + PB - 1) / PB;
+    const int n_my = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (threadIdx.x == 0) {
+        mbar_init(done, 1); mbar_init(doneL1, 1); mbar_init(go, NEPI); mbar_init(xfull, 32 * NGA); mbar_init(xfree, 1);
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 512);
+    {
+        const float* p = P.params;
+        __half* w1 = reinterpret_cast<__half*>(smem + QO_W);
+        __half* w2 = reinterpret_cast<__half*>(smem + QO_W + WO_W2);
+        __half* wh = reinterpret_cast<__half*>(smem + QO_W + WO_WH);
+        for (int i = threadIdx.x; i < 160 * N1; i += NTH) { const int k = i / N1, n = i - k * N1; w1[himg(n, k, 160)] = __float2half_rn(p[L::OFF_W1T + i]); }
+        for (int i = threadIdx.x; i < N1 * N2; i += NTH) { const int k = i / N2, n = i - k * N2; w2[himg(n, k, N1)] = __float2half_rn(p[L::OFF_W2T + i]); }
+        for (int i = threadIdx.x; i < N2 * 16; i += NTH) {
+            const int k = i >> 4, j = i & 15;
+            wh[himg(j, k, N2)] = __float2half_rn(j < 8 ? p[L::OFF_WH + k * 8 + j] : 0.f);
+        }
+        for (int i = threadIdx.x; i < 208; i += NTH)
+            bias[i] = i < 128 ? p[L::OFF_B1 + i] : i < 192 ? p[L::OFF_B2 + (i - 128)] : i < 200 ? p[L::OFF_BH + (i - 192)] : 0.f;
+    }
+    fence_proxy_async();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t aX = smem_u32(smem + QO_X), aH1 = smem_u32(sH1), aH2 = smem_u32(sH2), aW = smem_u32(smem + QO_W);
+    constexpr int TA_L2 = 0, TA_L1 = 256, TA_HD = 384;
+
+    if (warp == 9) {
+        const bool me = elect_one();
+        const uint32_t T0 = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+        const int n_u = __shfl_sync(0xffffffffu, n_my, 0);
+        uint32_t go_no = 0;
+        auto wait_go = [&]() { mbar_wait(go, go_no & 1); ++go_no; fence_after(); };
+        auto commit = [&](uint64_t* bar) { if (me) mma_commit(bar); };
+        for (int t = 0; t < n_u; ++t) {
+            mbar_wait(xfull, t & 1); fence_after();
+            {
+                const uint32_t id = idesc_h(128, 128, 0, 0);
+                uint64_t b = dk(aW, 160);
+#pragma unroll 1
+                for (int ks = 0; ks < 10; ks += 2) {
+                    if (me) { mma_h(T0 + TA_L1, dxk(aX, ks), b, id, ks != 0); mma_h(T0 + TA_L1, dxk(aX, ks + 1), b + 16u, id, 1u); }
+                    b += 32u;
+                }
+                commit(doneL1);
+                commit(xfree);
+            }
+            wait_go();
+            {
+                const uint32_t id = idesc_h(128, N2, 0, 0);
+                uint64_t a = dk(aH1, N1), b = dk(aW + WO_W2, N1);
+#pragma unroll 1
+                for (int ks = 0; ks < 8; ks += 4) {
+                    if (me) {
+                        mma_h(T0 + TA_L2, a, b, id, ks != 0); mma_h(T0 + TA_L2, a + 16u, b + 16u, id, 1u);
+                        mma_h(T0 + TA_L2, a + 32u, b + 32u, id, 1u); mma_h(T0 + TA_L2, a + 48u, b + 48u, id, 1u);
+                    }
+                    a += 64u; b += 64u;
+                }
+                commit(done);
+            }
+            wait_go();
+            {
+                const uint32_t id = idesc_h(128, 16, 0, 0);
+                const uint64_t a = dk(aH2, N2), b = dk(aW + WO_WH, N2);
+                if (me) {
+                    mma_h(T0 + TA_HD, a, b, id, 0u); mma_h(T0 + TA_HD, a + 16u, b + 16u, id, 1u);
+                    mma_h(T0 + TA_HD, a + 32u, b + 32u, id, 1u); mma_h(T0 + TA_HD, a + 48u, b + 48u, id, 1u);
+                }
+                commit(done);
+            }
+        }
+    } else if (warp >= 10) {
+        const int gt = threadIdx.x - 320;
+        for (int t = 0; t < n_my; ++t) {
+            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+            float4 xa[10], xb[10];
+#pragma unroll
+            for (int u = 0; u < 10; ++u) {
+                const int v = gt + u * (32 * NGA);
+                const int r = v / 20, oct = v - r * 20;
+                const int i = tile * PB + r;
+                const int rid = i < total ? __ldg(P.rows + i) : 0;
+                const float4* g = reinterpret_cast<const float4*>(P.obs + (size_t)rid * RL_K1) + oct * 2;
+                xa[u] = ld_stream_f4(g); xb[u] = ld_stream_f4(g + 1);
+            }
+            if (t > 0) mbar_wait(xfree, (t - 1) & 1);
+#pragma unroll
+            for (int u = 0; u < 10; ++u) {
+                const int v = gt + u * (32 * NGA);
+                const int r = v / 20, oct = v - r * 20;
+                *reinterpret_cast<uint4*>(smem + QO_X + ximg(r, oct)) =
+                    make_uint4(pk(xa[u].x, xa[u].y), pk(xa[u].z, xa[u].w), pk(xb[u].x, xb[u].y), pk(xb[u].z, xb[u].w));
+            }
+            fence_proxy_async();
+            mbar_arrive(xfull);
+        }
+    } else if (warp < 8) {
+        const uint32_t T0 = *tmem_slot;
+        uint32_t done_no = 0, l1_no = 0;
+        const int q = warp & 3, hh = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+        const int S = P.cfg.slot_cap;
+        auto go_signal = [&]() { fence_proxy_async(); fence_before(); mbar_arrive(go); };
+        auto wait_done = [&]() { mbar_wait(done, done_no & 1); ++done_no; fence_after(); };
+        auto relu_store32 = [&](float (&v)[32], const float* b, __half* img, int c0, int K) {
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+                const float4 b0 = *reinterpret_cast<const float4*>(b + j8 * 8), b1 = *reinterpret_cast<const float4*>(b + j8 * 8 + 4);
+                *reinterpret_cast<uint4*>(img + himg(row, c0 + j8 * 8, K)) =
+                    make_uint4(pk_relu(v[j8 * 8] + b0.x, v[j8 * 8 + 1] + b0.y), pk_relu(v[j8 * 8 + 2] + b0.z, v[j8 * 8 + 3] + b0.w),
+                               pk_relu(v[j8 * 8 + 4] + b1.x, v[j8 * 8 + 5] + b1.y), pk_relu(v[j8 * 8 + 6] + b1.z, v[j8 * 8 + 7] + b1.w));
+            }
+        };
+        const double epsilon = *P.epsilon;
+        for (int t = 0; t < n_my; ++t) {
+            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+            const int i = tile * PB + row;
+            const int rid = (hh == 0 && i < total) ? __ldg(P.rows + i) : 0;
+            mbar_wait(doneL1, l1_no & 1); ++l1_no; fence_after();
+            {
+                const int c0 = hh * 64;
+                float v0[32], v1[32];
+                tmem_ld32(T0 + t_lane + TA_L1 + c0, v0);
+                tmem_ld32(T0 + t_lane + TA_L1 + c0 + 32, v1);
+                tmem_wait_ld();
+                relu_store32(v0, bias + c0, sH1, c0, N1);
+                relu_store32(v1, bias + c0 + 32, sH1, c0 + 32, N1);
+            }
+            go_signal();
+            wait_done();
+            {
+                const int c0 = hh * 32;
+                float v0[32];
+                tmem_ld32(T0 + t_lane + TA_L2 + c0, v0);
+                tmem_wait_ld();
+                relu_store32(v0, bias + 128 + c0, sH2, c0, N2);
+            }
+            go_signal();
+            wait_done();
+            if (hh == 0) {
+                float v[16];
+                tmem_ld16(T0 + t_lane + TA_HD, v);
+                tmem_wait_ld();
+                if (i < total) {
+                    float qv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) qv[j] = v[j] + bias[192 + j];
+                    int best = 0;
+#pragma unroll
+                    for (int j = 1; j < 8; ++j) if (qv[j] > qv[best]) best = j;                   // first maximum
+                    const int w = rid / S, slot = rid - w * S;
+                    const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
+                    int a = best;
+                    const double u = rl_uniform(rl_draw(key, P.t_act, RL_SITE_ACT_EXPLORE, (uint32_t)slot));
+                    const bool explore = P.rule == RL_ACT_DQN ? (u < epsilon) : (u <= epsilon);    // DQN.py:135-139 / PERDQN.py:101-111
+                    if (explore) a = (int)rl_below(rl_draw(key, P.t_act, RL_SITE_ACT_RANDOM, (uint32_t)slot), 8);
+                    reinterpret_cast<int8_t*>(P.rec + rid)[13] = (int8_t)a;
+                    if (P.q_out) {
+                        float4* qo = reinterpret_cast<float4*>(P.q_out + (size_t)i * 8);
+                        qo[0] = make_float4(qv[0], qv[1], qv[2], qv[3]);
+                        qo[1] = make_float4(qv[4], qv[5], qv[6], qv[7]);
+                    }
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(*tmem_slot, 512);
+}
+
 int launch(int mode, const rl_world_cfg* cfg, const rl_rows_bufs* rows, int32_t gene, const rl_replay_bufs* replay,
            const int32_t* sample_idx, const float* ev_weight, const rl_learn_bufs* learn, void* stream) {
     DqnParams P;
@@ -502,4 +712,25 @@ extern "C" int rl_brain_learn_perdqn_p(const rl_world_cfg* cfg, const rl_rows_bu
     RL_ARG_CHECK(learn->params && learn->target && learn->grad_scratch && learn->grad && learn->loss && learn->new_prio);
     RL_ARG_CHECK((int64_t)cfg->n_worlds * replay->capacity < (1ll << 31));
     return launch(1, cfg, rows, gene, replay, sample_idx, ev_weight, learn, stream);
+}
+
+extern "C" int rl_brain_act_dqn_p(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl_rows_bufs* rows, int32_t gene,
+                                  const rl_brain_act* brain, uint64_t t_act, float* q_out, void* stream) {
+    RL_ARG_CHECK(cfg && bufs && rows && brain);
+    RL_ARG_CHECK(gene >= 0 && gene < cfg->n_genes && cfg->obs_ld == RL_K1);
+    RL_ARG_CHECK(bufs->rec && bufs->obs_state && brain->params && brain->epsilon);
+    if (brain->kind != RL_MODEL_DQN || (brain->rule != RL_ACT_DQN && brain->rule != RL_ACT_PERDQN))
+        return rl_set_err(RL_ERR_UNSUPPORTED, "rl_brain_act_dqn_p: DQN-layout networks (DQN, PERDQN) only");
+    DqnActParams P;
+    memset(&P, 0, sizeof(P));
+    P.cfg = *cfg; P.rec = bufs->rec; P.obs = bufs->obs_state;
+    P.rows = rows->rows + (size_t)(gene * RL_N_ROW_KINDS + RL_ROWS_ALL) * rows->row_cap;
+    P.total = rows->total + gene * RL_N_ROW_KINDS + RL_ROWS_ALL;
+    P.params = brain->params; P.epsilon = brain->epsilon; P.t_act = t_act; P.rule = brain->rule;
+    P.q_out = q_out ? q_out + (size_t)gene * rows->row_cap * 8 : nullptr;
+    static PerDeviceOnce attr;
+    if (attr.need()) RL_CUDA_CHECK(cudaFuncSetAttribute(k_act_dqn_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QACT_SMEM));
+    k_act_dqn_p<<<rl_learn_grid(), NTH, QACT_SMEM, (cudaStream_t)stream>>>(P);
+    RL_CUDA_CHECK(cudaGetLastError());
+    return RL_OK;
 }

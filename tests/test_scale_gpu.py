@@ -571,3 +571,50 @@ def test_dqn_tensor_core_kernel_matches_fp32_kernel(mode):
     if mode == "perdqn":
         v = np.repeat(valid, B)
         np.testing.assert_allclose(ptc[v], p32[v], rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("rule", ["dqn", "perdqn"])
+def test_dqn_layout_act_tensor_core_matches_fp32_act(rule):
+    """k_act_dqn_p (tcgen05 get_action of the DQN-layout brains, >= 3 tiles of 128 rows per persistent CTA) vs
+    rl_brain_act_all (fp32 FMA, checked against the oracle in test_brain_gpu / test_perdqn_gpu): Q within 2e-2 of the Q scale,
+    >= 99 % identical greedy actions, the same set of listed rows written, identical exploration draws and comparison rule."""
+    from reinlife_b200 import _lib
+    from reinlife_b200.Models import packing
+    from reinlife_b200.World.vecworld import VecWorld
+    from reinlife_b200.rows import RowLists
+    z = _golden2()
+    NW = 620
+    vw = VecWorld(NW, 30, 30, 1, max_agents=100, seed=12)
+    rows = RowLists(vw)
+    vw.reset(); vw.top_up(100)
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    for _ in range(2):
+        vw.set_actions(torch.randint(0, 8, (NW, vw.S), device="cuda", dtype=torch.int8, generator=g))
+        vw.step(); vw.update(); vw.top_up(100)
+    rows.build(kinds_mask=1)
+    n = int(rows.total[0])
+    assert n >= 3 * 128 * vw.lib.rl_learn_grid()
+    sd = _sd2(z, "train_dqn/w0")
+    flat = torch.from_numpy(packing.pack(1, sd)).cuda()
+    eps = torch.tensor([0.25], dtype=torch.float64, device="cuda")
+    desc = (_lib.BrainAct * 1)(_lib.BrainAct(_lib.MODEL_DQN, _lib.ACT_DQN if rule == "dqn" else _lib.ACT_PERDQN, flat.data_ptr(), eps.data_ptr()))
+    out = {}
+    for kern in ("fp32", "tc"):
+        q = torch.zeros((1, rows.row_cap, 8), device="cuda")
+        vw.rec[:, :, 13] = 255
+        if kern == "fp32":
+            _lib.check(vw.lib.rl_brain_act_all(C.byref(vw.cfg), C.byref(vw.bufs), C.byref(rows.bufs), desc, 1, C.c_uint64(7),
+                                               C.c_void_p(q.data_ptr()), None, vw._stream()))
+        else:
+            _lib.check(vw.lib.rl_brain_act_dqn_p(C.byref(vw.cfg), C.byref(vw.bufs), C.byref(rows.bufs), 0, C.byref(desc[0]), C.c_uint64(7),
+                                                 C.c_void_p(q.data_ptr()), vw._stream()))
+        torch.cuda.synchronize()
+        out[kern] = (q[0, :n].cpu().numpy(), vw.rec[:, :, 13].cpu().numpy().view(np.int8).copy())
+    q32, a32 = out["fp32"]
+    qtc, atc = out["tc"]
+    scale = np.abs(q32).max()
+    assert scale > 0.1 and np.abs(q32 - qtc).max() < 2e-2 * scale
+    assert (q32.argmax(1) == qtc.argmax(1)).mean() >= 0.99
+    listed = a32 != -1
+    assert listed.sum() == n and ((atc != -1) == listed).all()
+    assert (a32[listed] == atc[listed]).mean() >= 0.99
