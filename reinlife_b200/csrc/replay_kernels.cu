@@ -85,39 +85,42 @@ __global__ void __launch_bounds__(RT) k_replay_store(const ReplayParams P) {
     }
     __syncthreads();
     const float pwv = P.rp.prioritized ? pw_of(maxp) : 1.0f;
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
     const int skip = max(0, cnt - cap);
-    for (int tr = skip + warp; tr < cnt; tr += RT / 32) {
-        if (off + tr >= P.rows.row_cap) break;
+    const int n_tr = min(cnt, P.rows.row_cap - off) - skip;        // transitions this launch writes
+    // Phase 1: one thread per transition resolves the chain row id -> agent record (previous slot) and writes the scalars; the two
+    // source rows and the ring slot go to shared memory.  Phase 2: the whole CTA copies the 2 x 40 float4 of every transition as one
+    // flat loop of independent loads (the warp-per-transition chain of dependent loads left the kernel latency-bound at 0.15 ms).
+    extern __shared__ int tr_src[];                                  // [3][slot_cap]: obs_state row, obs_prime row, ring slot
+    int* src0 = tr_src; int* src1 = tr_src + S; int* dstq = tr_src + 2 * S;
+    for (int k = threadIdx.x; k < n_tr; k += RT) {
+        const int tr = skip + k;
         const int row = P.rows.rows[(size_t)gk * P.rows.row_cap + off + tr];
         const int4 rv = reinterpret_cast<const int4*>(P.wb.rec)[row];
-        const int prev = (rv.w >> 16) & 0xFFFF;
         const int p = (pos + tr) % cap;
-        const float4* s0 = reinterpret_cast<const float4*>(P.wb.obs_state + ((size_t)w * S + prev) * ld);
-        const float4* s1 = reinterpret_cast<const float4*>(P.wb.obs_prime + (size_t)row * ld);
-        if (P.rp.obs_fp16) {        // float16 ring: rows rounded once here; the last (padding) column carries 1.0 (db1 rides the dW1 GEMM)
-            uint2* h0 = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(P.rp.obs) + ((size_t)w * cap + p) * ld);
-            uint2* h1 = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(P.rp.next_obs) + ((size_t)w * cap + p) * ld);
-            for (int v = lane; v < ld / 4; v += 32) {
-                float4 a = __ldg(s0 + v), b = __ldg(s1 + v);
-                if (v == ld / 4 - 1) { a.w = 1.0f; b.w = 1.0f; }
-                h0[v] = make_uint2(pack_half2(a.x, a.y), pack_half2(a.z, a.w));
-                h1[v] = make_uint2(pack_half2(b.x, b.y), pack_half2(b.z, b.w));
-            }
-        } else {
-            float4* d0 = reinterpret_cast<float4*>(P.rp.obs + ((size_t)w * cap + p) * ld);
-            float4* d1 = reinterpret_cast<float4*>(P.rp.next_obs + ((size_t)w * cap + p) * ld);
-            for (int v = lane; v < ld / 4; v += 32) { d0[v] = __ldg(s0 + v); d1[v] = __ldg(s1 + v); }
+        src0[k] = w * S + ((rv.w >> 16) & 0xFFFF); src1[k] = row; dstq[k] = p;
+        const size_t q = (size_t)w * cap + p;
+        P.rp.action[q] = (int8_t)((rv.w >> 8) & 0xFF);
+        P.rp.reward[q] = P.wb.reward[row];
+        P.rp.done[q] = (rv.w & RL_F_DEAD) ? 1 : 0;
+        if (P.rp.prioritized) {
+            if (P.rp.prio[q] != maxp) atomicAdd(&s_more, 1);               // one more entry holds the maximum
+            P.rp.prio[q] = maxp; P.rp.pw[q] = pwv;
         }
-        if (lane == 0) {
-            const size_t q = (size_t)w * cap + p;
-            P.rp.action[q] = (int8_t)((rv.w >> 8) & 0xFF);
-            P.rp.reward[q] = P.wb.reward[row];
-            P.rp.done[q] = (rv.w & RL_F_DEAD) ? 1 : 0;
-            if (P.rp.prioritized) {
-                if (P.rp.prio[q] != maxp) atomicAdd(&s_more, 1);           // one more entry holds the maximum
-                P.rp.prio[q] = maxp; P.rp.pw[q] = pwv;
-            }
+    }
+    __syncthreads();
+    const int nv = ld / 4;                                           // float4 per row
+    for (int i = threadIdx.x; i < n_tr * 2 * nv; i += RT) {
+        const int k = i / (2 * nv), rem = i - k * 2 * nv;
+        const int which = rem >= nv, v = rem - which * nv;
+        const float4* sp = reinterpret_cast<const float4*>((which ? P.wb.obs_prime : P.wb.obs_state) + (size_t)(which ? src1[k] : src0[k]) * ld);
+        float4 x = __ldg(sp + v);
+        const size_t q = (size_t)w * cap + dstq[k];
+        if (P.rp.obs_fp16) {        // float16 ring: rows rounded once here; the last (padding) column carries 1.0 (db1 rides the dW1 GEMM)
+            if (v == nv - 1) x.w = 1.0f;
+            uint2* h = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(which ? P.rp.next_obs : P.rp.obs) + q * ld);
+            h[v] = make_uint2(pack_half2(x.x, x.y), pack_half2(x.z, x.w));
+        } else {
+            reinterpret_cast<float4*>((which ? P.rp.next_obs : P.rp.obs) + q * ld)[v] = x;
         }
     }
     __syncthreads();
@@ -376,7 +379,7 @@ int rl_replay_store(const rl_world_cfg* cfg, const rl_world_bufs* bufs, const rl
     if (rc) return rc;
     RL_ARG_CHECK(replay->obs && replay->next_obs && replay->action && replay->reward && replay->done);
     RL_ARG_CHECK(!replay->prioritized || (replay->prio && replay->pw));
-    k_replay_store<<<cfg->n_worlds, RT, 0, (cudaStream_t)stream>>>(P);
+    k_replay_store<<<cfg->n_worlds, RT, 3 * sizeof(int) * (size_t)cfg->slot_cap, (cudaStream_t)stream>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
     return RL_OK;
 }
