@@ -8,6 +8,7 @@
 // tile's head epilogue; the next tile's rows are in the gather warps' registers while this tile computes (their loads are issued
 // before the X image is free).  Replaces k_act_dueling_h (transposed-output form, N = 64 MMAs, scalar F2F conversions and 2-byte
 // scatter stores: 0.12 ms per 200 k rows) -- same contract, outputs and tolerance (tests/test_tc_gpu.py, tests/test_scale_gpu.py).
+#include <stdlib.h>
 #include <string.h>
 #include "tc_bm.cuh"
 #include "models.cuh"
@@ -49,6 +50,7 @@ struct ActParams {
     const double* epsilon;
     uint64_t t_act;
     float* q_out;              // [row_cap][8] or null
+    long long* trace;          // RL_TC_TRACE: clock64 stamps of CTA 0, tile 3
 };
 
 __global__ void __launch_bounds__(NTH, 1) k_act_dueling_p(const ActParams P) {
@@ -114,7 +116,9 @@ __global__ void __launch_bounds__(NTH, 1) k_act_dueling_p(const ActParams P) {
         const uint32_t T0 = __shfl_sync(0xffffffffu, *tmem_slot, 0);
         const int n_u = __shfl_sync(0xffffffffu, n_my, 0);
         uint32_t consumed = 0, go_no = 0, stage = 0, wstage = 0;
-        auto wait_go = [&]() { mbar_wait(go, go_no & 1); ++go_no; fence_after(); };
+        int itr_n = 0, itr_t = -1;
+        auto istamp = [&]() { if (P.trace && blockIdx.x == 0 && me && itr_t == 3 && itr_n < 30) P.trace[32 + itr_n++] = clock64(); };
+        auto wait_go = [&]() { mbar_wait(go, go_no & 1); ++go_no; fence_after(); istamp(); };
         auto chunks_wait = [&](int n) -> uint32_t {
             const uint32_t first = consumed;
             mbar_wait(&gfull[wstage % NSTG], (wstage / NSTG) & 1);
@@ -126,9 +130,12 @@ __global__ void __launch_bounds__(NTH, 1) k_act_dueling_p(const ActParams P) {
         auto commit = [&](uint64_t* bar) { if (me) mma_commit(bar); };
         auto stage_free = [&]() { commit(&sfree[stage % NSTG]); ++stage; };
         for (int t = 0; t < n_u; ++t) {
+            itr_t = t; istamp();
             uint32_t k0 = chunks_wait(5);
+            istamp();
             mbar_wait(xfull, t & 1);
             fence_after();
+            istamp();
             {   // L1: 5 chunks [128 n][32 k], 2 k-steps each -> columns 256..383
                 const uint32_t id = idesc_h(128, 128, 0, 0);
 #pragma unroll 1
@@ -139,6 +146,7 @@ __global__ void __launch_bounds__(NTH, 1) k_act_dueling_p(const ActParams P) {
                         mma_h(T0 + 256, dxk(aX, 2 * c + 1), b + 16u, id, 1u);
                     }
                 }
+                istamp();
                 stage_free();
                 commit(doneL1);
                 commit(xfree);                                 // the X image may be overwritten with the next tile's rows
@@ -156,6 +164,7 @@ __global__ void __launch_bounds__(NTH, 1) k_act_dueling_p(const ActParams P) {
                         if (me) mma_h(T0, a, dk(chunk_addr(k0 + c), 16), id, (hf | c) != 0);
                         a += 16u;
                     }
+                    istamp();
                     stage_free();
                 }
                 commit(done);
@@ -173,6 +182,7 @@ __global__ void __launch_bounds__(NTH, 1) k_act_dueling_p(const ActParams P) {
                     }
                     a += 64u; b += 64u;
                 }
+                istamp();
                 stage_free();
                 commit(done);
             }
@@ -195,7 +205,9 @@ __global__ void __launch_bounds__(NTH, 1) k_act_dueling_p(const ActParams P) {
                 const float4* g = reinterpret_cast<const float4*>(P.obs + (size_t)rid * RL_K1) + oct * 2;
                 xa[u] = ld_stream_f4(g); xb[u] = ld_stream_f4(g + 1);
             }
+            if (P.trace && blockIdx.x == 0 && gt == 0 && t == 4) P.trace[64] = clock64();
             if (t > 0) mbar_wait(xfree, (t - 1) & 1);
+            if (P.trace && blockIdx.x == 0 && gt == 0 && t == 4) P.trace[65] = clock64();
 #pragma unroll
             for (int u = 0; u < 10; ++u) {
                 const int v = gt + u * (32 * NGA);
@@ -205,6 +217,7 @@ __global__ void __launch_bounds__(NTH, 1) k_act_dueling_p(const ActParams P) {
             }
             fence_proxy_async();
             mbar_arrive(xfull);
+            if (P.trace && blockIdx.x == 0 && gt == 0 && t == 4) P.trace[66] = clock64();
         }
     } else {
         // =================================== epilogue warps ===================================
@@ -214,9 +227,11 @@ __global__ void __launch_bounds__(NTH, 1) k_act_dueling_p(const ActParams P) {
         const int row = q * 32 + lane;                    // batch row of the tile == TMEM lane
         const uint32_t t_lane = (uint32_t)(q * 32) << 16;
         const int S = P.cfg.slot_cap;
-        auto go_signal = [&]() { fence_proxy_async(); fence_before(); mbar_arrive(go); };
-        auto wait_done = [&]() { mbar_wait(done, done_no & 1); ++done_no; fence_after(); };
-        auto wait_l1 = [&]() { mbar_wait(doneL1, l1_no & 1); ++l1_no; fence_after(); };
+        int tr_n = 0, tr_t = -1;
+        auto stamp = [&]() { if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && tr_t == 3 && tr_n < 30) P.trace[tr_n++] = clock64(); };
+        auto go_signal = [&]() { fence_proxy_async(); fence_before(); mbar_arrive(go); stamp(); };
+        auto wait_done = [&]() { mbar_wait(done, done_no & 1); ++done_no; fence_after(); stamp(); };
+        auto wait_l1 = [&]() { mbar_wait(doneL1, l1_no & 1); ++l1_no; fence_after(); stamp(); };
         auto relu_store32 = [&](float (&v)[32], const float* b, __half* img, int c0, int K) {
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
@@ -231,6 +246,7 @@ __global__ void __launch_bounds__(NTH, 1) k_act_dueling_p(const ActParams P) {
             const int tile = (int)blockIdx.x + t * (int)gridDim.x;
             const int i = tile * PB + row;
             const int rid = (hh == 0 && i < total) ? __ldg(P.rows + i) : 0;
+            tr_t = t; stamp();
             wait_l1();
             {   // L1 epilogue: this thread's row, columns [64 hh, +64) of the accumulator at TMEM columns 256..383
                 const int c0 = hh * 64;
@@ -305,9 +321,28 @@ extern "C" int rl_brain_act_p(const rl_world_cfg* cfg, const rl_world_bufs* bufs
     P.total = rows->total + gene * RL_N_ROW_KINDS + RL_ROWS_ALL;
     P.params = brain->params; P.wimg = reinterpret_cast<const __half*>(wimg_eval_h); P.epsilon = brain->epsilon; P.t_act = t_act;
     P.q_out = q_out ? q_out + (size_t)gene * rows->row_cap * 8 : nullptr;
+    static long long* trace_dev = nullptr;
+    const bool tracing = getenv("RL_TC_TRACE") != nullptr;
+    if (tracing) {
+        if (!trace_dev) RL_CUDA_CHECK(cudaMalloc(&trace_dev, 128 * sizeof(long long)));
+        RL_CUDA_CHECK(cudaMemset(trace_dev, 0, 128 * sizeof(long long)));
+        P.trace = trace_dev;
+    }
     static PerDeviceOnce attr;
     if (attr.need()) RL_CUDA_CHECK(cudaFuncSetAttribute(k_act_dueling_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACT_SMEM));
     k_act_dueling_p<<<rl_learn_grid(), NTH, ACT_SMEM, (cudaStream_t)stream>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
+    if (tracing) {
+        long long h[128];
+        RL_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+        RL_CUDA_CHECK(cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[act trace] epilogue stamps (tile start, L1 done, ->L2, L2 done, ->head, head done):");
+        for (int i = 1; i < 30 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
+        fprintf(stderr, "\n[act trace] issuer stamps (tile start, W1 chunks, xfull, L1 issued, go, L2a issued, L2b issued, go, head issued):");
+        for (int i = 0; i < 30 && h[32 + i]; ++i) fprintf(stderr, " %lld", h[32 + i] - h[0]);
+        fprintf(stderr, "\n[act trace] gather warps, tile 4 (loads issued, xfree seen, stored):");
+        for (int i = 0; i < 3; ++i) fprintf(stderr, " %lld", h[64 + i] - h[0]);
+        fprintf(stderr, "\n");
+    }
     return RL_OK;
 }
