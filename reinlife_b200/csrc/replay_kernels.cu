@@ -108,19 +108,21 @@ __global__ void __launch_bounds__(RT) k_replay_store(const ReplayParams P) {
         }
     }
     __syncthreads();
-    const int nv = ld / 4;                                           // float4 per row
-    for (int i = threadIdx.x; i < n_tr * 2 * nv; i += RT) {
-        const int k = i / (2 * nv), rem = i - k * 2 * nv;
-        const int which = rem >= nv, v = rem - which * nv;
-        const float4* sp = reinterpret_cast<const float4*>((which ? P.wb.obs_prime : P.wb.obs_state) + (size_t)(which ? src1[k] : src0[k]) * ld);
-        float4 x = __ldg(sp + v);
+    const int nu = ld / 8;                                           // 32-byte units per row (ld = 160: 20)
+    for (int i = threadIdx.x; i < n_tr * 2 * nu; i += RT) {
+        const int k = i / (2 * nu), rem = i - k * 2 * nu;
+        const int which = rem >= nu, u = rem - which * nu;
+        const float4* sp = reinterpret_cast<const float4*>((which ? P.wb.obs_prime : P.wb.obs_state) + (size_t)(which ? src1[k] : src0[k]) * ld) + 2 * u;
+        const float4 x = __ldg(sp);
+        float4 y = __ldg(sp + 1);
         const size_t q = (size_t)w * cap + dstq[k];
         if (P.rp.obs_fp16) {        // float16 ring: rows rounded once here; the last (padding) column carries 1.0 (db1 rides the dW1 GEMM)
-            if (v == nv - 1) x.w = 1.0f;
-            uint2* h = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(which ? P.rp.next_obs : P.rp.obs) + q * ld);
-            h[v] = make_uint2(pack_half2(x.x, x.y), pack_half2(x.z, x.w));
+            if (u == nu - 1) y.w = 1.0f;
+            uint4* h = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(which ? P.rp.next_obs : P.rp.obs) + q * ld);
+            h[u] = make_uint4(pack_half2(x.x, x.y), pack_half2(x.z, x.w), pack_half2(y.x, y.y), pack_half2(y.z, y.w));
         } else {
-            reinterpret_cast<float4*>((which ? P.rp.next_obs : P.rp.obs) + q * ld)[v] = x;
+            float4* d = reinterpret_cast<float4*>((which ? P.rp.next_obs : P.rp.obs) + q * ld) + 2 * u;
+            d[0] = x; d[1] = y;
         }
     }
     __syncthreads();
