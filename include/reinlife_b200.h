@@ -80,6 +80,9 @@ typedef struct rl_world_bufs {
     float*        stats;        /* [n_worlds, n_genes, RL_N_STATS] tracker partials of the last step, may be NULL */
     float*        reward_div100;/* [n_worlds, slot_cap] float32(reference reward / 100.0) -- what PPOAgent.learn stores
                                    (Models/PPO.py:73); written by step, may be NULL (needed only with PPO brains) */
+    void*         obs_state_h;  /* optional float16 copies of obs_state / obs_prime ([n_worlds, slot_cap, 160] halves, column 159 = 1.0),
+                                   written by the same kernels next to the float32 rows (obs_ld must be 160): what the tensor-core   */
+    void*         obs_prime_h;  /* consumers read (TMA row gathers of rl_brain_act_p, float16 replay rows of rl_replay_store); NULL = off */
 } rl_world_bufs;
 
 /* per world x gene partial sums over the post-step agent list (Helpers/tracker.py:178-266) */

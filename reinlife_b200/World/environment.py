@@ -125,6 +125,11 @@ class Environment:
         for b in brains:
             if getattr(b, "_dev", None) is not None:
                 b._dev.use_fp16 = self._learn_fp16
+        # fp16 events of the dueling brains: the World kernels also emit float16 rows, which get_action gathers by TMA
+        # (k_act_dueling_p<true>) and rl_replay_store copies into the float16 rings (RL_NO_OBS16: A/B switch)
+        if (self._learn_fp16 and not self._learn_single and os.environ.get("RL_NO_OBS16") is None
+                and any(getattr(b, "KIND", None) == _lib.MODEL_DUELING for b in brains)):
+            self.world.enable_obs_fp16()
         self._eps = torch.tensor([float(b.epsilon) if hasattr(b, "epsilon") else 0.0 for b in brains],
                                  dtype=torch.float64, device=self.device)
         self._seen = torch.tensor([int(getattr(b, "n_epi", 0)) for b in brains], dtype=torch.int64, device=self.device)

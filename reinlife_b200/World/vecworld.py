@@ -62,6 +62,17 @@ class VecWorld:
         raw = self.ns_state.cpu().numpy().tobytes()
         return (_lib.NsState * self.n_worlds).from_buffer_copy(raw)
 
+    def enable_obs_fp16(self):
+        """Have the World kernels also write float16 copies of obs_state / obs_prime (column 159 = 1.0): the rows the tensor-core
+        get_action kernel gathers by TMA and rl_replay_store copies into float16 rings."""
+        if getattr(self, "obs_state_h", None) is None:
+            if self.ld != 160:
+                raise _lib.RLError("float16 observation copies need obs_ld = 160")
+            self.obs_state_h = torch.zeros((self.n_worlds, self.S, 160), dtype=torch.float16, device=self.device)
+            self.obs_prime_h = torch.zeros((self.n_worlds, self.S, 160), dtype=torch.float16, device=self.device)
+            self.bufs.obs_state_h = self.obs_state_h.data_ptr()
+            self.bufs.obs_prime_h = self.obs_prime_h.data_ptr()
+
     def enable_reward_div100(self):
         """Have rl_world_step also write float32(reward / 100.0), the value PPOAgent.learn stores (Models/PPO.py:73)."""
         if self.reward_div100 is None:

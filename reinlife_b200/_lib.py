@@ -33,7 +33,8 @@ class WorldCfg(C.Structure):
 class WorldBufs(C.Structure):
     _fields_ = [("type", C.c_void_p), ("rec", C.c_void_p), ("n_agents", C.c_void_p), ("reward", C.c_void_p),
                 ("obs_state", C.c_void_p), ("obs_prime", C.c_void_p), ("gene_count", C.c_void_p),
-                ("status", C.c_void_p), ("stats", C.c_void_p), ("reward_div100", C.c_void_p)]
+                ("status", C.c_void_p), ("stats", C.c_void_p), ("reward_div100", C.c_void_p),
+                ("obs_state_h", C.c_void_p), ("obs_prime_h", C.c_void_p)]
 
 
 class NsBest(C.Structure):          # rl_ns_best

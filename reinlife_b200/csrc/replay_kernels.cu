@@ -109,6 +109,17 @@ __global__ void __launch_bounds__(RT) k_replay_store(const ReplayParams P) {
     }
     __syncthreads();
     const int nu = ld / 8;                                           // 32-byte units per row (ld = 160: 20)
+    if (P.rp.obs_fp16 && P.wb.obs_state_h && P.wb.obs_prime_h) {
+        // the World kernels wrote float16 copies of the rows (column 159 = 1.0 already): plain 16-byte copies, half the read traffic
+        for (int i = threadIdx.x; i < n_tr * 2 * nu; i += RT) {
+            const int k = i / (2 * nu), rem = i - k * 2 * nu;
+            const int which = rem >= nu, u = rem - which * nu;
+            const uint4* sp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(which ? P.wb.obs_prime_h : P.wb.obs_state_h) +
+                                                             (size_t)(which ? src1[k] : src0[k]) * ld) + u;
+            const size_t q = (size_t)w * cap + dstq[k];
+            reinterpret_cast<uint4*>(reinterpret_cast<__half*>(which ? P.rp.next_obs : P.rp.obs) + q * ld)[u] = __ldg(sp);
+        }
+    } else
     for (int i = threadIdx.x; i < n_tr * 2 * nu; i += RT) {
         const int k = i / (2 * nu), rem = i - k * 2 * nu;
         const int which = rem >= nu, u = rem - which * nu;

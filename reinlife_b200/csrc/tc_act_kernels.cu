@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "tc_bm.cuh"
+#include "tma_util.cuh"
 #include "models.cuh"
 
 namespace {
@@ -40,6 +41,7 @@ static_assert(ACT_SMEM <= 227 * 1024 && AO_BARS % 8 == 0 && AO_H2 % 1024 == 0, "
 __device__ __forceinline__ uint32_t group_chunks(uint32_t g) { return g == 0 ? 5u : g == 3 ? 1u : 4u; }
 
 struct ActParams {
+    CUtensorMap map_obs;       // TMA = true: obs_state_h as a [n_worlds * slot_cap][160] float16 tensor
     rl_world_cfg cfg;
     rl_agent_rec* rec;
     const float* obs;          // obs_state
@@ -53,7 +55,8 @@ struct ActParams {
     long long* trace;          // RL_TC_TRACE: clock64 stamps of CTA 0, tile 3
 };
 
-__global__ void __launch_bounds__(NTH, 1) k_act_dueling_p(const ActParams P) {
+template <bool TMA>
+__global__ void __launch_bounds__(NTH, 1) k_act_dueling_p(const __grid_constant__ ActParams P) {
     using L = Layout<RL_MODEL_DUELING>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(NTH, 1) k_act_dueling_p(const ActParams P) {
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTG; ++i) { mbar_init(&gfull[i], 1); mbar_init(&sfree[i], 1); }
-        mbar_init(done, 1); mbar_init(doneL1, 1); mbar_init(go, NEPI); mbar_init(xfull, 32 * NGA); mbar_init(xfree, 1);
+        mbar_init(done, 1); mbar_init(doneL1, 1); mbar_init(go, NEPI); mbar_init(xfull, TMA ? 4 : 32 * NGA); mbar_init(xfree, 1);
         fence_mbar_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -193,6 +196,29 @@ __global__ void __launch_bounds__(NTH, 1) k_act_dueling_p(const ActParams P) {
         // a row (256 contiguous bytes, conflict-free swizzled stores).  The loads of tile t + 1 are issued before the X image is
         // free (xfree: the L1 MMAs of tile t have completed), so their latency sits behind tile t.  Rows past `total` read row 0.
         const int gt = threadIdx.x - 320;
+        if (TMA) {
+            // float16 copies of the rows exist (rl_world_bufs.obs_state_h): the TMA gathers them by row id straight into the
+            // SWIZZLE_128B image -- 32 row groups x 3 K blocks = 96 tile::gather4 over four warps, no LSU traffic beside the MMAs
+            const int gw = warp - 10;
+            if (gw < 4) {
+                const int g = (lane / 3) * 4 + gw, kb = lane - (lane / 3) * 3;
+                const bool act = lane < 24;
+                if (lane == 0) tma::prefetch_map(&P.map_obs);
+                for (int t = 0; t < n_my; ++t) {
+                    const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+                    int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+                    if (act) {
+                        const int i = tile * PB + 4 * g;
+                        r0 = i < total ? __ldg(P.rows + i) : 0; r1 = i + 1 < total ? __ldg(P.rows + i + 1) : 0;
+                        r2 = i + 2 < total ? __ldg(P.rows + i + 2) : 0; r3 = i + 3 < total ? __ldg(P.rows + i + 3) : 0;
+                    }
+                    if (t > 0) mbar_wait(xfree, (t - 1) & 1);
+                    if (lane == 0) mbar_expect_tx(xfull, XIMG / 4);
+                    __syncwarp();
+                    if (act) tma::gather4(smem_u32(smem + AO_X) + kb * XBLK + g * 512, &P.map_obs, smem_u32(xfull), kb * 64, r0, r1, r2, r3);
+                }
+            }
+        } else
         for (int t = 0; t < n_my; ++t) {
             const int tile = (int)blockIdx.x + t * (int)gridDim.x;
             float4 xa[10], xb[10];
@@ -328,9 +354,20 @@ extern "C" int rl_brain_act_p(const rl_world_cfg* cfg, const rl_world_bufs* bufs
         RL_CUDA_CHECK(cudaMemset(trace_dev, 0, 128 * sizeof(long long)));
         P.trace = trace_dev;
     }
+    const bool use_tma = bufs->obs_state_h != nullptr && getenv("RL_ACT_NO_TMA") == nullptr;
+    if (use_tma) {
+        const long long n_rows = (long long)cfg->n_worlds * cfg->slot_cap;
+        RL_ARG_CHECK(n_rows < (1ll << 31));
+        if (tma::make_rows_map(&P.map_obs, bufs->obs_state_h, (uint64_t)n_rows, RL_K1, 1) != 0)
+            return rl_set_err(RL_ERR_CUDA, "rl_brain_act_p: cuTensorMapEncodeTiled failed");
+    }
     static PerDeviceOnce attr;
-    if (attr.need()) RL_CUDA_CHECK(cudaFuncSetAttribute(k_act_dueling_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACT_SMEM));
-    k_act_dueling_p<<<rl_learn_grid(), NTH, ACT_SMEM, (cudaStream_t)stream>>>(P);
+    if (attr.need()) {
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_act_dueling_p<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACT_SMEM));
+        RL_CUDA_CHECK(cudaFuncSetAttribute(k_act_dueling_p<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ACT_SMEM));
+    }
+    if (use_tma) k_act_dueling_p<true><<<rl_learn_grid(), NTH, ACT_SMEM, (cudaStream_t)stream>>>(P);
+    else k_act_dueling_p<false><<<rl_learn_grid(), NTH, ACT_SMEM, (cudaStream_t)stream>>>(P);
     RL_CUDA_CHECK(cudaGetLastError());
     if (tracing) {
         long long h[128];

@@ -306,6 +306,12 @@ __device__ __forceinline__ int load_world(const WParams& P, WS& s, int w) {
     return n;
 }
 
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {      // one F2FP.PACK_AB
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 // float32(health / max_health), environment.py:365,397.  The correctly rounded float32 quotient equals
 // float32(float64(h) / 200.0) for every int16 h (no double-rounding case exists; checked exhaustively), so no f64 here.
 __device__ __forceinline__ float hratio(int h) { return __fdiv_rn((float)h, 200.0f); }
@@ -486,6 +492,7 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
     // ---- observation rows: one warp per agent ----
     // per-lane constants: element e = lane + 32k of the row -> offset into the padded planes (window elements only)
     if (P.dbg & 2) return;
+    __half* obs16 = reinterpret_cast<__half*>(obs_out == P.b.obs_prime ? P.b.obs_prime_h : P.b.obs_state_h);
     int off[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) off[k] = s.offtab[lane + 32 * k];
@@ -525,6 +532,7 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
         __syncwarp();
         const int cnt = min(16, a1 - b0);
         float* orow = obs_out + ((size_t)w * S + b0) * ld;
+        uint32_t* orow16 = obs16 ? reinterpret_cast<uint32_t*>(obs16 + ((size_t)w * S + b0) * 160) : nullptr;
         const int sidx = lane >= 19 ? min(lane - 19, 7) : 0;   // lanes 19-24: scalars, 25-31: zero pad (slots 6,7 are zero)
         const bool wide = ld > 160;
 #pragma unroll 2
@@ -549,6 +557,19 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
             __stcs(orow + lane, v0); __stcs(orow + 32 + lane, v1); __stcs(orow + 64 + lane, v2);
             __stcs(orow + 96 + lane, v3); __stcs(orow + 128 + lane, v4);
             if (wide) for (int e = 160 + lane; e < ld; e += 32) __stcs(orow + e, 0.f);
+            if (orow16) {
+                // float16 copy of the row (320 bytes; element 159 := 1.0): lane l holds elements 32 k + l; neighbours are exchanged so that
+                // even lanes pack a pair of block k and odd lanes a pair of block k + 1 -- one 4-byte store per lane and two blocks
+                const float n0 = __shfl_xor_sync(0xffffffffu, v0, 1), n1 = __shfl_xor_sync(0xffffffffu, v1, 1);
+                const float n2 = __shfl_xor_sync(0xffffffffu, v2, 1), n3 = __shfl_xor_sync(0xffffffffu, v3, 1);
+                const float n4 = __shfl_xor_sync(0xffffffffu, v4, 1);
+                const bool odd = lane & 1;
+                const int hw = lane >> 1;
+                __stcs(orow16 + (odd ? 16 : 0) + hw, pack_h2(odd ? n1 : v0, odd ? v1 : n0));
+                __stcs(orow16 + (odd ? 48 : 32) + hw, pack_h2(odd ? n3 : v2, odd ? v3 : n2));
+                if (!odd) __stcs(orow16 + 64 + hw, pack_h2(v4, lane == 30 ? 1.0f : n4));
+                orow16 += 80;
+            }
         }
         __syncwarp();
     }
@@ -987,6 +1008,7 @@ int world_prepare(const rl_world_cfg* cfg, const rl_world_bufs* b, WParams& P, s
     RL_ARG_CHECK(cfg->n_worlds > 0 && cfg->n_genes > 0 && cfg->n_genes <= RL_MAX_GENES);
     RL_ARG_CHECK(cfg->slot_cap > 0 && cfg->slot_cap <= cfg->height * cfg->width);
     RL_ARG_CHECK(cfg->obs_ld >= 160 && cfg->obs_ld % 32 == 0 && cfg->obs_ld <= 192);
+    RL_ARG_CHECK((!b->obs_state_h && !b->obs_prime_h) || (cfg->obs_ld == 160 && b->obs_state_h && b->obs_prime_h));
     RL_ARG_CHECK(cfg->max_agents > 0);
     if (!cfg->static_families && !ns)
         return rl_set_err(RL_ERR_UNSUPPORTED, "static_families=False goes through rl_world_reset_ns / rl_world_step_ns / rl_world_update_ns");

@@ -411,23 +411,27 @@ def test_replay_store_writes_float16_rows():
     NW, cap = 5, 64
     vw = VecWorld(NW, 12, 12, 2, max_agents=40, seed=3)
     rows = RowLists(vw)
+    vw.enable_obs_fp16()                      # ring c: copied from the float16 rows the World kernels emit
+    hs, hp = vw.obs_state_h.data_ptr(), vw.obs_prime_h.data_ptr()
     vw.reset(); vw.top_up(40)
-    a, b = ReplayRings(NW, cap, "cuda"), ReplayRings(NW, cap, "cuda", fp16=True)
+    a, b, c = ReplayRings(NW, cap, "cuda"), ReplayRings(NW, cap, "cuda", fp16=True), ReplayRings(NW, cap, "cuda", fp16=True)
     g = torch.Generator(device="cuda"); g.manual_seed(5)
     for _ in range(4):
         vw.set_actions(torch.randint(0, 8, (NW, vw.S), device="cuda", dtype=torch.int8, generator=g))
         vw.step()
         rows.build(kinds_mask=6, train_freq=[3, 3], event_on=[1, 1])
-        for rp in (a, b):
+        for rp in (a, b, c):
+            vw.bufs.obs_state_h, vw.bufs.obs_prime_h = (hs, hp) if rp is c else (None, None)
             _lib.check(vw.lib.rl_replay_store(C.byref(vw.cfg), C.byref(vw.bufs), C.byref(rows.bufs), 0, C.byref(rp.bufs), vw._stream()))
         vw.update(); vw.top_up(40)
     torch.cuda.synchronize()
     assert (a.len == b.len).all() and (a.pos == b.pos).all() and int(a.len.max()) == cap
-    for x, y in ((a.obs, b.obs), (a.next_obs, b.next_obs)):
+    for x, y, z in ((a.obs, b.obs, c.obs), (a.next_obs, b.next_obs, c.next_obs)):
         want = x.half().clone(); want[..., -1] = 1.0
         filled = torch.arange(cap, device="cuda")[None, :] < a.len[:, None]
-        assert torch.equal(y[filled], want[filled])
-    assert torch.equal(a.prio, b.prio) and torch.equal(a.action, b.action) and torch.equal(a.reward, b.reward)
+        assert torch.equal(y[filled], want[filled]) and torch.equal(z[filled], want[filled])
+    for r in (b, c):
+        assert torch.equal(a.prio, r.prio) and torch.equal(a.action, r.action) and torch.equal(a.reward, r.reward)
 
 
 def test_replay_max_priority_is_maintained_exactly():

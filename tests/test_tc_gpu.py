@@ -119,6 +119,7 @@ def test_tensor_core_act_matches_fp32_act():
     NW = 24
     vw = VecWorld(NW, 30, 30, 2, max_agents=100, seed=12)
     rows = RowLists(vw)
+    vw.enable_obs_fp16()                     # "fp16t": rows gathered by TMA from the float16 copies the World kernels emit
     vw.reset(); vw.top_up(100)
     g = torch.Generator(device="cuda"); g.manual_seed(1)
     for _ in range(3):                       # a few steps so that observations are not the reset ones
@@ -129,7 +130,11 @@ def test_tensor_core_act_matches_fp32_act():
     eps = torch.tensor([0.3, 0.0], dtype=torch.float64, device="cuda")
     descs = (_lib.BrainAct * 2)(*[b.act_desc(_lib.ACT_DUELING, eps.data_ptr() + 8 * i) for i, b in enumerate(brains)])
     out = {}
-    for mode in ("fp32", "tf32", "fp16", "fp16p"):       # fp16p = rl_brain_act_p (batch-major 128-row tiles, the default)
+    import os
+    for mode in ("fp32", "tf32", "fp16", "fp16p", "fp16t"):       # fp16p / fp16t = rl_brain_act_p (batch-major 128-row tiles, the default)
+        os.environ.pop("RL_ACT_NO_TMA", None)
+        if mode == "fp16p":
+            os.environ["RL_ACT_NO_TMA"] = "1"                     # rows converted from obs_state by the gather warps
         q = torch.zeros((2, rows.row_cap, 8), device="cuda")
         vw.rec[:, :, 13] = 255
         if mode == "fp32":
@@ -143,14 +148,19 @@ def test_tensor_core_act_matches_fp32_act():
                     _lib.check(vw.lib.rl_brain_act_tc(C.byref(vw.cfg), C.byref(vw.bufs), C.byref(rows.bufs), i, C.byref(descs[i]),
                                                       C.c_void_p(b.wimg_e.data_ptr()), C.c_uint64(7), C.c_void_p(q.data_ptr()), vw._stream()))
                 else:
-                    fn = vw.lib.rl_brain_act_p if mode == "fp16p" else vw.lib.rl_brain_act_h
+                    fn = vw.lib.rl_brain_act_p if mode in ("fp16p", "fp16t") else vw.lib.rl_brain_act_h
                     _lib.check(fn(C.byref(vw.cfg), C.byref(vw.bufs), C.byref(rows.bufs), i, C.byref(descs[i]),
                                   C.c_void_p(b.wimg_eh.data_ptr()), C.c_uint64(7), C.c_void_p(q.data_ptr()), vw._stream()))
         torch.cuda.synchronize()
         out[mode] = (q.cpu().numpy(), vw.rec[:, :, 13].cpu().numpy().view(np.int8).copy())
+    os.environ.pop("RL_ACT_NO_TMA", None)
     a32 = out["fp32"][1]
     listed = a32 != -1
-    for mode in ("tf32", "fp16", "fp16p"):
+    for i in range(2):                         # same float16 operands either way: bit-identical Q values and actions
+        n = int(rows.total[i * 3])
+        assert np.array_equal(out["fp16p"][0][i, :n], out["fp16t"][0][i, :n])
+    assert np.array_equal(out["fp16p"][1], out["fp16t"][1])
+    for mode in ("tf32", "fp16", "fp16p", "fp16t"):
         n_tot = 0
         for i in range(2):
             n = int(rows.total[i * 3])

@@ -197,3 +197,37 @@ def test_fused_update_top_up_equals_update_then_top_up():
             for w in range(NW):
                 assert (ra[w, :n[w]] == rb[w, :n[w]]).all(), (H, W, t, w)
                 assert (oa[w, :n[w]] == ob[w, :n[w]]).all(), (H, W, t, w)
+
+
+def test_float16_observation_copies():
+    """enable_obs_fp16(): reset / step / update / top-up also write float16 copies of the rows they write in float32 -- exactly
+    float16(row) with element 159 = 1.0 for every listed agent -- and change nothing else (same float32 rows, records, cells)."""
+    from reinlife_b200.World.vecworld import VecWorld
+    NW, H, W, G, target = 24, 30, 30, 2, 100
+    a = VecWorld(NW, H, W, G, max_agents=target, seed=4)
+    b = VecWorld(NW, H, W, G, max_agents=target, seed=4)
+    b.enable_obs_fp16()
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    for vw in (a, b):
+        vw.reset(); vw.top_up(target)
+
+    def check(which):
+        torch.cuda.synchronize()
+        assert torch.equal(a.type, b.type) and torch.equal(a.n_agents, b.n_agents) and torch.equal(a.rec, b.rec)
+        f32, f16 = (b.obs_prime, b.obs_prime_h) if which else (b.obs_state, b.obs_state_h)
+        assert torch.equal(f32, a.obs_prime if which else a.obs_state)
+        listed = torch.arange(b.S, device="cuda")[None, :] < b.n_agents[:, None]
+        want = f32.half().clone(); want[..., 159] = 1.0
+        assert torch.equal(f16[listed], want[listed]), which
+
+    check(0)
+    for t in range(8):
+        act = torch.randint(0, 8, (NW, a.S), device="cuda", dtype=torch.int8, generator=g)
+        for vw in (a, b):
+            vw.set_actions(act); vw.step()
+        check(1)
+        a.update(); b.update(); check(0)
+        a.top_up(target); b.top_up(target); check(0)
+        for vw in (a, b):
+            vw.set_actions(act); vw.step()
+        a.update(top_up=target); b.update(top_up=target); check(0)
