@@ -182,6 +182,52 @@ __device__ __forceinline__ void warp_mask_clear(uint32_t* mask, int cell) {
     __syncwarp();
 }
 
+// The same placement with the popc prefix kept in registers between calls (the hot kernels place several entities per phase):
+// lane l owns the words [l * wpl, (l + 1) * wpl); a placement takes one empty cell out of its owner's count and out of the
+// inclusive prefixes of the lanes behind it, and clears the cell's bit in `mask`.  Same k, same cell as warp_place.
+struct Placer { int cnt, incl; };
+__device__ __forceinline__ Placer placer_init(const uint32_t* mask, int nwords) {
+    const int lane = lane_id();
+    const int wpl = (nwords + 31) / 32;
+    const int w0 = lane * wpl, w1 = min(nwords, w0 + wpl);
+    Placer pl; pl.cnt = 0;
+    for (int wd = w0; wd < w1; ++wd) pl.cnt += __popc(mask[wd]);
+    pl.incl = pl.cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, pl.incl, o);
+        if (lane >= o) pl.incl += v;
+    }
+    return pl;
+}
+__device__ __forceinline__ int placer_take(Placer& pl, uint32_t* mask, int nwords, uint64_t bits) {
+    const int lane = lane_id();
+    const int total = __shfl_sync(0xffffffffu, pl.incl, 31);
+    if (total == 0) return -1;
+    const int k = (int)rl_below(bits, (uint32_t)total);
+    const int owner = __ffs(__ballot_sync(0xffffffffu, pl.incl > k)) - 1;
+    int cell = -1;
+    if (lane == owner) {
+        const int wpl = (nwords + 31) / 32;
+        int kk = k - (pl.incl - pl.cnt);
+        for (int wd = lane * wpl; ; ++wd) {
+            const uint32_t m = mask[wd];
+            const int p = __popc(m);
+            if (kk < p) {
+                const int b = (int)__fns(m, 0, kk + 1);
+                mask[wd] = m & ~(1u << b);
+                cell = wd * 32 + b;
+                break;
+            }
+            kk -= p;
+        }
+        --pl.cnt;
+    }
+    if (lane >= owner) --pl.incl;
+    cell = __shfl_sync(0xffffffffu, cell, owner);
+    return cell;
+}
+
 __device__ __forceinline__ void spawn_agent(WS& s, int cell, int gene, int health, int age) {   // entities.py:145-160
     if (lane_id() == 0) {
         s.type[cell] = RL_AGENT;
@@ -798,32 +844,46 @@ __global__ void __launch_bounds__(WT, NS ? 1 : RL_WORLD_MINB) k_world_update(con
         if (ag) { if (!NS) atomicOr(&s.misc[M_PRESENT], 1 << s.gene[c]); s.src[c] = (uint16_t)c; }
     }
     __syncthreads();
+    // _reproduce (:488-519), the 0.95 trials: trial index = rank among the eligible parents in row-major order, exactly the order
+    // of the reference's short-circuited random.random() calls -- a pure function of the eligible mask, so all warps draw them
+    // (one 32-cell word each) and leave the successful parents of word ch in s.wpre[ch] (free until finish_and_observe)
+    for (int ch = warp; ch < Cw; ch += WNW) {
+        const uint32_t m = s.amask[ch];
+        int before = 0;
+        for (int i = lane; i < ch; i += 32) before += __popc(s.amask[i]);
+        before = __reduce_add_sync(0xffffffffu, before);
+        const bool el = (m >> lane) & 1u;
+        const uint32_t rank = (uint32_t)before + __popc(m & lanemask_lt());
+        const bool succ = el && rl_uniform(rl_draw(key, P.t, RL_SITE_REPRO_TRIAL, rank)) > 0.95;
+        const uint32_t sm = __ballot_sync(0xffffffffu, succ);
+        if (lane == 0) s.wpre[ch] = sm;
+    }
+    __syncthreads();
+    Placer pl = {0, 0};
+    if (warp == 0) pl = placer_init(s.mask, Cw);
     if (warp == 0 && n_list <= P.cfg.max_agents) {
-        uint32_t trial = 0, birth = 0;
-        // _reproduce (:488-519): parents in row-major order; offspring on a uniformly random empty cell (A.9)
-        for (int wd = 0; wd < Cw; ++wd) {
-            const uint32_t m = s.amask[wd];
-            if (!m) continue;
-            // the 0.95 trials of one 32-cell word are drawn in parallel (trial index = rank among eligible parents,
-            // exactly the order of the reference's short-circuited random.random() calls); births stay sequential
-            const bool el = (m >> lane) & 1u;
-            const uint32_t rank = trial + __popc(m & lanemask_lt());
-            const bool succ = el && rl_uniform(rl_draw(key, P.t, RL_SITE_REPRO_TRIAL, rank)) > 0.95;
-            trial += __popc(m);
-            uint32_t sm = __ballot_sync(0xffffffffu, succ);
-            while (sm) {
-                const int bpos = __ffs(sm) - 1;
-                sm &= sm - 1;
-                const int pc = wd * 32 + bpos;
-                const int cell = warp_place(s.mask, Cw, rl_draw(key, P.t, RL_SITE_BIRTH_PLACE, birth));
-                if (cell >= 0) {
-                    ++birth;
-                    spawn_agent(s, cell, s.gene[pc], 200, 0);
-                    if (lane == 0) s.src[cell] = (uint16_t)cell;
-                    warp_mask_clear(s.mask, cell);
+        uint32_t birth = 0;
+        // births stay sequential: offspring on a uniformly random empty cell (A.9)
+        for (int wb = 0; wb < Cw; wb += 32) {
+            const uint32_t mine = wb + lane < Cw ? s.wpre[wb + lane] : 0u;
+            unsigned has = __ballot_sync(0xffffffffu, mine != 0u);
+            while (has) {
+                const int wl = __ffs(has) - 1;
+                has &= has - 1;
+                uint32_t sm = __shfl_sync(0xffffffffu, mine, wl);
+                while (sm) {
+                    const int bpos = __ffs(sm) - 1;
+                    sm &= sm - 1;
+                    const int pc = (wb + wl) * 32 + bpos;
+                    const int cell = placer_take(pl, s.mask, Cw, rl_draw(key, P.t, RL_SITE_BIRTH_PLACE, birth));
+                    if (cell >= 0) {
+                        ++birth;
+                        spawn_agent(s, cell, s.gene[pc], 200, 0);
+                        if (lane == 0) s.src[cell] = (uint16_t)cell;
+                    }
+                    if (P.cfg.limit_reproduction && lane == 0) s.flags[pc] |= RL_F_REPRODUCED;   // :518-519
+                    __syncwarp();
                 }
-                if (P.cfg.limit_reproduction && lane == 0) s.flags[pc] |= RL_F_REPRODUCED;   // :518-519
-                __syncwarp();
             }
         }
         // _produce (:521-547)
@@ -838,7 +898,7 @@ __global__ void __launch_bounds__(WT, NS ? 1 : RL_WORLD_MINB) k_world_update(con
                     const int k = (int)rl_below(rl_draw(key, P.t, RL_SITE_PRODUCE_GENE, 0), 10u);
                     st->produced_gene = st->max_gene; st->produced_src_best = k; st->produced_src_brain = st->best[k].brain;
                 }
-                const int cell = warp_place(s.mask, Cw, rl_draw(key, P.t, RL_SITE_BIRTH_PLACE, birth));
+                const int cell = placer_take(pl, s.mask, Cw, rl_draw(key, P.t, RL_SITE_BIRTH_PLACE, birth));
                 if (cell >= 0) {
                     if (lane == 0) {
                         id = s.misc[M_NIDS];
@@ -848,7 +908,6 @@ __global__ void __launch_bounds__(WT, NS ? 1 : RL_WORLD_MINB) k_world_update(con
                     id = __shfl_sync(0xffffffffu, id, 0);
                     spawn_agent(s, cell, id, 200, 0);
                     if (lane == 0) s.src[cell] = (uint16_t)cell;
-                    warp_mask_clear(s.mask, cell);
                 }
             }
         } else if (rl_uniform(rl_draw(key, P.t, RL_SITE_PRODUCE_TRIAL, 0)) > 0.95) {
@@ -857,41 +916,40 @@ __global__ void __launch_bounds__(WT, NS ? 1 : RL_WORLD_MINB) k_world_update(con
             if (!cand) cand = all;
             const int pick = (int)rl_below(rl_draw(key, P.t, RL_SITE_PRODUCE_GENE, 0), (uint32_t)__popc(cand));
             const int gene = (int)__fns(cand, 0, pick + 1);
-            const int cell = warp_place(s.mask, Cw, rl_draw(key, P.t, RL_SITE_BIRTH_PLACE, birth));
+            const int cell = placer_take(pl, s.mask, Cw, rl_draw(key, P.t, RL_SITE_BIRTH_PLACE, birth));
             if (cell >= 0) {
                 spawn_agent(s, cell, gene, 200, 0);
                 if (lane == 0) s.src[cell] = (uint16_t)cell;
-                warp_mask_clear(s.mask, cell);
             }
         }
     }
     __syncthreads();
-    // _remove_dead_agents (:795-799)
-    for (int c = threadIdx.x; c < C; c += WT)
-        if (s.type[c] == RL_AGENT && (s.flags[c] & RL_F_DEAD)) s.type[c] = RL_FOOD;
+    // _remove_dead_agents (:795-799); a dead agent's cell becomes food, so the empty-cell mask (and warp 0's Placer) stay valid.
+    // The surviving agents of word ch are left in s.amask[ch] for the top-up's head count.
+    for (int ch = warp; ch < Cw; ch += WNW) {
+        const int c = ch * 32 + lane;
+        const bool ag = c < C && s.type[c] == RL_AGENT;
+        const bool dead = ag && (s.flags[c] & RL_F_DEAD);
+        if (dead) s.type[c] = RL_FOOD;
+        const unsigned m = __ballot_sync(0xffffffffu, ag && !dead);
+        if (lane == 0) s.amask[ch] = m;
+    }
     __syncthreads();
     if (!NS && P.target > 0) {
         // fused saturated-world generator (rl_world_update_top_up): exactly what k_world_topup does on the state this kernel would
         // have written -- the same draws (keyed by t and the placement counter), one list rebuild and one observation pass instead of two
-        build_empty_mask(s.type, s.mask, C);
-        __syncthreads();
         if (warp == 0) {
             int cur = 0;
-            for (int base = 0; base < C; base += 32) {
-                const int c = base + lane;
-                cur += __popc(__ballot_sync(0xffffffffu, c < C && s.type[c] == RL_AGENT));
-            }
-            __syncwarp();                                  // the reads above precede lane 0's s.type writes in spawn_agent
-            cur = min(cur, P.cfg.slot_cap);
+            for (int i = lane; i < Cw; i += 32) cur += __popc(s.amask[i]);
+            cur = min(__reduce_add_sync(0xffffffffu, cur), P.cfg.slot_cap);
             for (uint32_t k = 0; cur < P.target; ++k, ++cur) {
-                const int cell = warp_place(s.mask, Cw, rl_draw(key, P.t, RL_SITE_TOPUP_PLACE, k));
+                const int cell = placer_take(pl, s.mask, Cw, rl_draw(key, P.t, RL_SITE_TOPUP_PLACE, k));
                 if (cell < 0) break;
                 const int gene = (int)rl_below(rl_draw(key, P.t, RL_SITE_TOPUP_GENE, k), (uint32_t)P.cfg.n_genes);
                 const int health = 10 * (1 + (int)rl_below(rl_draw(key, P.t, RL_SITE_TOPUP_HEALTH, k), 20));
                 const int age = (int)rl_below(rl_draw(key, P.t, RL_SITE_TOPUP_AGE, k), (uint32_t)P.max_age);
                 spawn_agent(s, cell, gene, health, age);
                 if (lane == 0) s.src[cell] = (uint16_t)cell;
-                warp_mask_clear(s.mask, cell);
             }
         }
         __syncthreads();
