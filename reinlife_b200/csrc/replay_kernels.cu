@@ -111,13 +111,24 @@ __global__ void __launch_bounds__(RT) k_replay_store(const ReplayParams P) {
     const int nu = ld / 8;                                           // 32-byte units per row (ld = 160: 20)
     if (P.rp.obs_fp16 && P.wb.obs_state_h && P.wb.obs_prime_h) {
         // the World kernels wrote float16 copies of the rows (column 159 = 1.0 already): plain 16-byte copies, half the read traffic
-        for (int i = threadIdx.x; i < n_tr * 2 * nu; i += RT) {
-            const int k = i / (2 * nu), rem = i - k * 2 * nu;
-            const int which = rem >= nu, u = rem - which * nu;
-            const uint4* sp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(which ? P.wb.obs_prime_h : P.wb.obs_state_h) +
-                                                             (size_t)(which ? src1[k] : src0[k]) * ld) + u;
-            const size_t q = (size_t)w * cap + dstq[k];
-            reinterpret_cast<uint4*>(reinterpret_cast<__half*>(which ? P.rp.next_obs : P.rp.obs) + q * ld)[u] = __ldg(sp);
+        // (four independent loads in flight per thread before the first store)
+        const int n_u = n_tr * 2 * nu;
+        for (int i0 = threadIdx.x; i0 < n_u; i0 += 4 * RT) {
+            uint4 v[4]; uint4* d[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j * RT;
+                if (i < n_u) {
+                    const int k = i / (2 * nu), rem = i - k * 2 * nu;
+                    const int which = rem >= nu, u = rem - which * nu;
+                    v[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(which ? P.wb.obs_prime_h : P.wb.obs_state_h) +
+                                                                (size_t)(which ? src1[k] : src0[k]) * ld) + u);
+                    d[j] = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(which ? P.rp.next_obs : P.rp.obs) + ((size_t)w * cap + dstq[k]) * ld) + u;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i0 + j * RT < n_u) *d[j] = v[j];
         }
     } else
     for (int i = threadIdx.x; i < n_tr * 2 * nu; i += RT) {
