@@ -366,7 +366,9 @@ def run_b200(args):
     parity = parity_check(env, brains, args.precision) if rank == 0 else None
     same = replicas_identical(env, brains, world_size)          # before parity_check's re-runs matter: they touch grad / loss only
     # the event kernel alone (one launch per brain per step): CUDA events recorded around rl_brain_learn(_tc)
-    k_ms = [a.elapsed_time(b) for (_, _, a, b) in env.kernel_events]
+    k_ms = [a.elapsed_time(b) for (nm, _, a, b) in env.kernel_events if nm == "learn_events"]
+    u_ms = [a.elapsed_time(b) for (nm, _, a, b) in env.kernel_events if nm == "world_update"]
+    update_kernel_ms = sum(u_ms) / max(1, len(u_ms)) if u_ms else phases["update"]
     env.kernel_events = None
     learn_kernel_ms = sum(k_ms) / max(1, len(k_ms))
     ev_per_launch = ev_avg / len(brains)
@@ -387,13 +389,16 @@ def run_b200(args):
     bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     # algorithmic bytes per world: step 2C+30n, observe C+12n+612n
-    b_step = NW * ((2 * C + 30 * n_avg) + (C + 12 * n_avg + 612 * n_avg))
-    b_obs = NW * (C + 12 * n_avg + 612 * n_avg)
+    # + 306 n when the World kernels also emit the float16 rows get_action / the replay store consume (precision="fp16", dueling brains)
+    row_b = 612 + (306 if getattr(env.world, "obs_state_h", None) is not None else 0)
+    b_step = NW * ((2 * C + 30 * n_avg) + (C + 12 * n_avg + row_b * n_avg))
+    b_obs = NW * (C + 12 * n_avg + row_b * n_avg)
     flop_event = 2.0 * 64 * (2 * 53504 + 2 * 53504) - 2.0 * 64 * (153 * 128)   # 2 forwards + backward (dX of layer 1 not needed)
     roof_k = {
         "k_world_step": {"bound": "hbm", "ms": phases["step"], "achieved": b_step / phases["step"] / 1e6, "peak": hbm_peak, "unit": "GB/s"},
-        "k_world_update": {"bound": "hbm", "ms": phases["update"], "achieved": b_obs / phases["update"] / 1e6, "peak": hbm_peak, "unit": "GB/s",
-                           "note": "update_env + the benchmark's saturated-world top-up fused in one launch (rl_world_update_top_up): one list rebuild, one observation pass"},
+        "k_world_update": {"bound": "hbm", "ms": update_kernel_ms, "achieved": b_obs / update_kernel_ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                           "note": "update_env + the benchmark's saturated-world top-up fused in one launch (rl_world_update_top_up): one list rebuild, one "
+                                   "observation pass; CUDA events around the launch (phase_ms.update also holds the tracker statistics kernel)"},
         learn_kernel_name: {"bound": "tensor", "ms": learn_kernel_ms, "launches_per_step": len(brains),
                                 "achieved": ev_per_launch * flop_event / max(learn_kernel_ms, 1e-9) / 1e9, "peak": bf16_peak, "unit": "TFLOP/s",
                                 "note": ("one launch = all train() events of one brain (25.6 MFLOP per 64-row event), timed alone with CUDA events; "
@@ -419,7 +424,7 @@ def run_b200(args):
             "config": {"workload": workload_name(args), "grid": [H, W], "worlds_total": n_worlds, "agents_per_world": n_avg,
                        "train_events_per_step_per_gpu": ev_avg, "parallelism": f"worlds sharded x{world_size}, brains replicated, "
                        "1 NCCL all-reduce of summed gradients per step" if world_size > 1 else "single GPU",
-                       "l2": "per-step working set (2 x 262 MB observation tensors + replay rows) exceeds the 126 MB L2"},
+                       "l2": "per-step working set (2 x 262 MB float32 + 2 x 131 MB float16 observation tensors + replay rows) exceeds the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "public Environment API; per step: pinned control block H2D, tracker record + event counts D2H (host sync)"},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "roofline_kernels": roof_k,

@@ -193,7 +193,14 @@ class Environment:
         if self.training:                                  # environment.py:206-207
             self.tracker.update_results(None, n_epi)
             self.gpu_launches += 1
+        ev0 = None
+        if self.kernel_events is not None:                 # bench.py: CUDA-event time of the update (+ top-up) kernel alone (roofline)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         self.world.update(top_up=top_up, max_age=max_age)
+        if ev0 is not None:
+            ev1.record()
+            self.kernel_events.append(("world_update", -1, ev0, ev1))
         self.gpu_launches += 1
 
     @_nvtx("reinlife.top_up")

@@ -169,7 +169,52 @@ __global__ void __launch_bounds__(RT) k_replay_sample(const ReplayParams P) {
     const int len = P.rp.len[w];
     const uint64_t key = rl_world_key(P.cfg.seed, (uint64_t)(P.cfg.world_id0 + w));
     unsigned long long total = 0;
-    if (P.rp.prioritized) {
+    constexpr int ST = 10;                                  // tiles of 4 * RT weights held in registers (capacity <= 10240: the default 10000)
+    if (P.rp.prioritized && (cap & 3) == 0 && len <= 4 * RT * ST) {
+        // coalesced form: every thread loads its float4 of all tiles first (independent 16-byte loads), then the tiles are scanned
+        // from registers -- thread-local prefix of 4, warp scan, running carry over the tiles.  Same integer sums, same cum[].
+        const float4* pw4 = reinterpret_cast<const float4*>(P.rp.pw + (size_t)w * cap);
+        const int lane = lane_id(), warp = threadIdx.x >> 5;
+        float4 v[ST];
+#pragma unroll
+        for (int t = 0; t < ST; ++t) {
+            const int i = (t * RT + (int)threadIdx.x) * 4;
+            v[t] = i < len ? __ldg(pw4 + (i >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        unsigned long long carry = 0;
+#pragma unroll
+        for (int t = 0; t < ST; ++t) {
+            if (t * RT * 4 >= len) break;                   // uniform
+            const int i = (t * RT + (int)threadIdx.x) * 4;
+            const unsigned long long f0 = i < len ? fix_of(v[t].x) : 0ull, f1 = i + 1 < len ? fix_of(v[t].y) : 0ull;
+            const unsigned long long f2 = i + 2 < len ? fix_of(v[t].z) : 0ull, f3 = i + 3 < len ? fix_of(v[t].w) : 0ull;
+            const unsigned long long local = f0 + f1 + f2 + f3;
+            unsigned long long incl = local;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long x = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += x;
+            }
+            if (lane == 31) wsum[warp] = incl;
+            __syncthreads();
+            unsigned long long base = carry, tile = 0;
+#pragma unroll
+            for (int k = 0; k < RT / 32; ++k) { const unsigned long long x = wsum[k]; tile += x; if (k < warp) base += x; }
+            unsigned long long run = base + incl - local;
+            if (i + 3 < len) {
+                const unsigned long long c0 = run + f0, c1 = c0 + f1, c2 = c1 + f2;
+                reinterpret_cast<ulonglong2*>(cum + i)[0] = make_ulonglong2(c0, c1);
+                reinterpret_cast<ulonglong2*>(cum + i)[1] = make_ulonglong2(c2, c2 + f3);
+            } else {
+                if (i < len) { run += f0; cum[i] = run; }
+                if (i + 1 < len) { run += f1; cum[i + 1] = run; }
+                if (i + 2 < len) { run += f2; cum[i + 2] = run; }
+            }
+            carry += tile;
+            __syncthreads();
+        }
+        total = carry;
+    } else if (P.rp.prioritized) {
         const float* pw = P.rp.pw + (size_t)w * cap;
         const int per = (len + RT - 1) / RT;
         const int i0 = min(len, (int)threadIdx.x * per), i1 = min(len, i0 + per);

@@ -4,7 +4,7 @@
 namespace {
 
 constexpr int ST = 256;
-constexpr int MAXB = 148;
+constexpr int MAXB = 148 * 4;      // one to two worlds per warp at 4096 worlds (a warp walks its worlds serially: latency-bound)
 
 struct StatsParams {
     rl_world_cfg cfg;

@@ -520,3 +520,38 @@ def test_ppo_store_plan_and_compaction_follow_the_reference_data_list():
         assert (r100[nz] != 0).all()
         vw.update(); vw.top_up(30)
     assert sum(len(d) for g_ in mirror for d in g_) >= 0
+
+
+def test_prioritized_sampler_tiles_match_oracle():
+    """rl_replay_sample at the default capacity: the coalesced register-tile scan (several tiles of 1024 weights, ragged lengths,
+    a length of 1, a full ring) and the chunked fallback (capacity not a multiple of 4) draw exactly the oracle's indices."""
+    from reinlife_b200 import _lib
+    from reinlife_b200.brains import ReplayRings
+    from oracle import brain_oracle as bo
+    from oracle import ref_harness as rh
+    for cap, lens in ((10000, [10000, 1, 1023, 1024, 1025, 4097, 9999, 3]), (1003, [1003, 7, 512, 1000])):
+        NW = len(lens)
+        vw, rows = _mk(NW)
+        rp = ReplayRings(NW, cap, "cuda")
+        rng = np.random.default_rng(cap)
+        prio = (rng.random((NW, cap)) ** 4 * 3.0).astype(np.float32)
+        prio[0, ::7] = 0.0                                     # zero-weight entries are never drawn
+        pw = np.stack([bo.per_weight(p) for p in prio])
+        rp.prio.copy_(torch.from_numpy(prio)); rp.pw.copy_(torch.from_numpy(pw))
+        rp.len.copy_(torch.tensor(lens, dtype=torch.int32))
+        per_world = [2, 1, 1, 1, 2, 1, 1, 1][:NW]
+        n_ev = _fake_events(vw, rows, per_world)
+        sidx = torch.full((rows.row_cap, 64), -7, dtype=torch.int32, device="cuda")
+        t = 5
+        _lib.check(vw.lib.rl_replay_sample(C.byref(vw.cfg), C.byref(rows.bufs), C.c_int32(0), C.byref(rp.bufs), C.c_int32(64),
+                                           C.c_uint64(t), C.c_void_p(sidx.data_ptr()), vw._stream()))
+        torch.cuda.synchronize()
+        got = sidx.cpu().numpy()
+        ev = 0
+        for w in range(NW):
+            key = rh.world_key(9, w)
+            for k_ev in range(per_world[w]):
+                u53 = [rh.draw(key, t, rh.SITE["REPLAY_SAMPLE"], k_ev * 64 + i) >> 11 for i in range(64)]
+                assert got[ev].tolist() == bo.per_sample(pw[w, :lens[w]], u53), (cap, w, k_ev)
+                ev += 1
+        assert ev == n_ev
