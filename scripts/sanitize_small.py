@@ -18,7 +18,8 @@ from test_scale_gpu import _events_setup, _run_event_kernel, _half_copy      # n
 from brain_golden_util import state_dict                                     # noqa: E402
 
 w0, tgt = state_dict("train_perd3qn/w0"), state_dict("train_perd3qn/target")
-for name, NW, per_world in (("1 event", 1, [1]), ("21 events", 7, [3, 1, 0, 5, 2, 4, 6])):
+PART = os.environ.get("RL_SAN_PART", "all")          # "env": only the Environment steps (World kernels with float16 rows, TMA get_action, store, sampler)
+for name, NW, per_world in (("1 event", 1, [1]), ("21 events", 7, [3, 1, 0, 5, 2, 4, 6])) if PART != "env" else ():
     z, vw, rows, rp, ring, n_ev, sidx = _events_setup(NW, per_world, seed=5)
     sd = torch.from_numpy(sidx).cuda()
     for ring_name, r in (("float32 ring", rp), ("float16 ring / TMA", _half_copy(rp))):
