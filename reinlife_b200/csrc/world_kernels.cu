@@ -7,6 +7,7 @@
 // entities.py:145-248; closed forms: SURVEY.md Appendix A.3-A.6 (validated against the reference
 // through oracle/rl_oracle.c, which keeps the sequential formulation).
 #include <stdlib.h>
+#include <type_traits>
 #include <cuda_fp16.h>
 #include "rl_common.cuh"
 
@@ -580,43 +581,49 @@ __device__ void finish_and_observe(const WParams& P, WS& s, int w, const uint8_t
         float* orow = obs_out + ((size_t)w * S + b0) * ld;
         uint32_t* orow16 = obs16 ? reinterpret_cast<uint32_t*>(obs16 + ((size_t)w * S + b0) * 160) : nullptr;
         const int sidx = lane >= 19 ? min(lane - 19, 7) : 0;   // lanes 19-24: scalars, 25-31: zero pad (slots 6,7 are zero)
-        const bool wide = ld > 160;
+        // float16 copy of a row (320 bytes; element 159 := 1.0): lane l holds elements 32 k + l.  Each lane packs its elements of two
+        // blocks into one word, swaps words with its neighbour and picks {mine.lo, other.lo} (even lanes: a pair of block k) or
+        // {other.hi, mine.hi} (odd lanes: a pair of block k + 1) with one PRMT -- three packs, three shuffles, three 4-byte stores
+        const uint32_t hsel = (lane & 1) ? 0x3276u : 0x5410u;
+        const int hidx = ((lane & 1) ? 16 : 0) + (lane >> 1);
+        // the row loop is instantiated per (padded row, float16 copy) so that nothing uniform is tested per row
+        auto emit = [&](auto wide_c, auto h16_c) {
+            constexpr bool WIDE = decltype(wide_c)::value, H16 = decltype(h16_c)::value;
 #pragma unroll 2
-        for (int a = 0; a < cnt; ++a, orow += ld) {
-            const int base = __shfl_sync(0xffffffffu, base_l, a);
-            const float mygene = __shfl_sync(0xffffffffu, gene_l, a);
-            const uint32_t w0 = planes[base + off[0]];      // e  0..31 : food
-            const uint32_t w1 = planes[base + off[1]];      // e 32..48 : food, 49..63: health
-            const uint32_t w2 = planes[base + off[2]];      // e 64..95 : health
-            const uint32_t w3 = planes[base + off[3]];      // e 96,97  : health, 98..127: dead-agent gene
-            const uint32_t w4 = planes[base + off[4]];      // e 128..146: dead-agent gene, 147..: scalars / pad
-            const float sv = scr[a * 8 + sidx];
-            const float v0 = lo_f(w0);
-            const float v1 = lane < 17 ? lo_f(w1) : __uint_as_float(w1);
-            const float v2 = __uint_as_float(w2);
-            const float q3 = hi_f(w3), q4 = hi_f(w4);
-            const float g3 = q3 == -2.f ? 0.f : (q3 == mygene ? 1.f : -1.f);             // :424-428
-            const float g4 = q4 == -2.f ? 0.f : (q4 == mygene ? 1.f : -1.f);
-            const float v3 = lane >= 2 ? g3 : __uint_as_float(w3);
-            const float v4 = lane < 19 ? g4 : sv;
-            if (P.dbg & 1) { if (v0 + v1 + v2 + v3 + v4 == 12345.678f) __stcs(orow, v0); continue; }
-            __stcs(orow + lane, v0); __stcs(orow + 32 + lane, v1); __stcs(orow + 64 + lane, v2);
-            __stcs(orow + 96 + lane, v3); __stcs(orow + 128 + lane, v4);
-            if (wide) for (int e = 160 + lane; e < ld; e += 32) __stcs(orow + e, 0.f);
-            if (orow16) {
-                // float16 copy of the row (320 bytes; element 159 := 1.0): lane l holds elements 32 k + l; neighbours are exchanged so that
-                // even lanes pack a pair of block k and odd lanes a pair of block k + 1 -- one 4-byte store per lane and two blocks
-                const float n0 = __shfl_xor_sync(0xffffffffu, v0, 1), n1 = __shfl_xor_sync(0xffffffffu, v1, 1);
-                const float n2 = __shfl_xor_sync(0xffffffffu, v2, 1), n3 = __shfl_xor_sync(0xffffffffu, v3, 1);
-                const float n4 = __shfl_xor_sync(0xffffffffu, v4, 1);
-                const bool odd = lane & 1;
-                const int hw = lane >> 1;
-                __stcs(orow16 + (odd ? 16 : 0) + hw, pack_h2(odd ? n1 : v0, odd ? v1 : n0));
-                __stcs(orow16 + (odd ? 48 : 32) + hw, pack_h2(odd ? n3 : v2, odd ? v3 : n2));
-                if (!odd) __stcs(orow16 + 64 + hw, pack_h2(v4, lane == 30 ? 1.0f : n4));
-                orow16 += 80;
+            for (int a = 0; a < cnt; ++a, orow += ld) {
+                const int base = __shfl_sync(0xffffffffu, base_l, a);
+                const float mygene = __shfl_sync(0xffffffffu, gene_l, a);
+                const uint32_t w0 = planes[base + off[0]];      // e  0..31 : food
+                const uint32_t w1 = planes[base + off[1]];      // e 32..48 : food, 49..63: health
+                const uint32_t w2 = planes[base + off[2]];      // e 64..95 : health
+                const uint32_t w3 = planes[base + off[3]];      // e 96,97  : health, 98..127: dead-agent gene
+                const uint32_t w4 = planes[base + off[4]];      // e 128..146: dead-agent gene, 147..: scalars / pad
+                const float sv = scr[a * 8 + sidx];
+                const float v0 = lo_f(w0);
+                const float v1 = lane < 17 ? lo_f(w1) : __uint_as_float(w1);
+                const float v2 = __uint_as_float(w2);
+                const float q3 = hi_f(w3), q4 = hi_f(w4);
+                const float g3 = q3 == -2.f ? 0.f : (q3 == mygene ? 1.f : -1.f);             // :424-428
+                const float g4 = q4 == -2.f ? 0.f : (q4 == mygene ? 1.f : -1.f);
+                const float v3 = lane >= 2 ? g3 : __uint_as_float(w3);
+                const float v4 = lane < 19 ? g4 : sv;
+                __stcs(orow + lane, v0); __stcs(orow + 32 + lane, v1); __stcs(orow + 64 + lane, v2);
+                __stcs(orow + 96 + lane, v3); __stcs(orow + 128 + lane, v4);
+                if (WIDE) for (int e = 160 + lane; e < ld; e += 32) __stcs(orow + e, 0.f);
+                if (H16) {
+                    const uint32_t p01 = pack_h2(v0, v1), p23 = pack_h2(v2, v3), p4 = pack_h2(lane == 31 ? 1.0f : v4, 0.f);
+                    const uint32_t n01 = __shfl_xor_sync(0xffffffffu, p01, 1), n23 = __shfl_xor_sync(0xffffffffu, p23, 1);
+                    const uint32_t n4 = __shfl_xor_sync(0xffffffffu, p4, 1);
+                    __stcs(orow16 + hidx, __byte_perm(p01, n01, hsel));
+                    __stcs(orow16 + 32 + hidx, __byte_perm(p23, n23, hsel));
+                    if (!(lane & 1)) __stcs(orow16 + 64 + hidx, __byte_perm(p4, n4, 0x5410u));
+                    orow16 += 80;
+                }
             }
-        }
+        };
+        using T = std::true_type; using F = std::false_type;
+        if (ld > 160) { if (orow16) emit(T{}, T{}); else emit(T{}, F{}); }
+        else { if (orow16) emit(F{}, T{}); else emit(F{}, F{}); }
         __syncwarp();
     }
 }
