@@ -70,7 +70,7 @@ constexpr int PO_META = PO_RED + 4 * 64;                  // [2] x { idx[128] ac
 constexpr int PO_RING = PO_META + 2 * 4 * 4 * PB;         // [2][2] ring base (elements) per buffer / event, 64-bit
 constexpr int PO_BARS = PO_RING + 2 * 2 * 8;
 constexpr int NSTG = 11;                 // ring release groups per pair: tL1 tL2a tL2b thead eL1 eL2a eL2b ehead dH2 dH1a dH1b
-constexpr int NBAR = 2 * NSTG + 11;      // gfull[NSTG] sfree[NSTG] + done doneL1 go xfull xpfull h2free xfree metaready w1a w1b
+constexpr int NBAR = 2 * NSTG + 12;      // gfull[NSTG] sfree[NSTG] + done doneL1 go xfull xpfull h2free xfree metaready w1a w1b done2 go2
 constexpr int PO_ONES = (PO_BARS + 8 * NBAR + 16 + 127) & ~127;   // [16 k][16] halves of 1.0: B operand of the db2 GEMM (every k-step reads it)
 constexpr size_t PAIR_SMEM = PO_ONES + 512 + 1024;               // + alignment slack
 static_assert(PAIR_SMEM <= 227 * 1024 && PO_BARS % 8 == 0 && PO_RING % 8 == 0 && PO_H2 % 1024 == 0, "shared memory budget");
@@ -129,6 +129,10 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
     // parity-tracked mbarrier must never complete two phases before its waiters have seen the first one (they would wait for a flip
     // that has already happened twice), so consecutive completions alternate between `done` and `done2`.
     uint64_t* done2 = done + 10;
+    // go2: H2[:, :128] of a forward pass is stored (epilogue of L2 half 0) -- the head's k-steps over those columns are issued behind
+    // the MMAs of L2 half 1 instead of after the whole L2 epilogue.  Its own barrier for the same reason as done2: the next `go`
+    // (L2 half 1 stored) may complete before the issuer has looked at this one.
+    uint64_t* go2 = done + 11;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTG; ++i) mbar_init(&gfull[i], 1);
         for (int i = 0; i < NSTG; ++i) mbar_init(&sfree[i], 1);
-        mbar_init(done, 1); mbar_init(done2, 1); mbar_init(doneL1, 1); mbar_init(go, NEPI);
+        mbar_init(done, 1); mbar_init(done2, 1); mbar_init(doneL1, 1); mbar_init(go, NEPI); mbar_init(go2, NEPI);
         mbar_init(xfull, NGW); mbar_init(xpfull, NGW); mbar_init(h2free, 1); mbar_init(xfree, 1); mbar_init(metaready, PB); mbar_init(w1a, 32 * NGW); mbar_init(w1b, 32 * NGW);
         fence_mbar_init();
     }
@@ -199,10 +203,11 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
         const bool me = elect_one();
         const uint32_t T0 = __shfl_sync(0xffffffffu, *tmem_slot, 0), T_DW2 = T0 + 256;
         const int np_u = __shfl_sync(0xffffffffu, n_pairs, 0);
-        uint32_t consumed = 0, go_no = 0, stage = 0, wstage = 0;
+        uint32_t consumed = 0, go_no = 0, go2_no = 0, stage = 0, wstage = 0;
         int itr_n = 0, itr_p = -1;
         auto istamp = [&]() { if (P.trace && blockIdx.x == 0 && me && itr_p == 3 && itr_n < 40) P.trace[64 + itr_n++] = clock64(); };
         auto wait_go = [&]() { mbar_wait(go, go_no & 1); ++go_no; fence_after(); istamp(); };
+        auto wait_go2 = [&]() { mbar_wait(go2, go2_no & 1); ++go2_no; fence_after(); };
         // all `n` chunks of the next release group have landed (one barrier per group; they are normally prefetched long before).
         // The wait for a stage's first group is placed BEFORE the stage's wait_go, off the hand-over path.
         auto chunks_wait = [&](int n) -> uint32_t {
@@ -249,12 +254,16 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
                 commit(hf ? done2 : done);
             }
         };
-        // head: D[128 b][16] = H2[128][256] Wh[16][256]^T -- one chunk, 16 k-steps
+        // head: D[128 b][16] = H2[128][256] Wh[16][256]^T -- one chunk, 16 k-steps in two halves: k-steps 0..7 read H2[:, :128] and are
+        // issued once the epilogue of L2 half 0 has stored those columns (go2; they queue behind the MMAs of L2 half 1, whose accumulator
+        // columns 128..255 they do not touch -- columns 0..15 have been drained by that epilogue), k-steps 8..15 after the whole L2 epilogue
         auto head = [&](uint32_t k0) {
             const uint32_t id = idesc_h(128, 16, 0, 0);
             uint64_t a = dk(aH2, 256), b = dk(chunk_addr(k0), 256);
+            wait_go2();
 #pragma unroll 1
             for (int ks = 0; ks < 16; ks += 4) {
+                if (ks == 8) wait_go();
                 if (me) {
                     mma_h(T0, a, b, id, ks != 0); mma_h(T0, a + 16u, b + 16u, id, 1u);
                     mma_h(T0, a + 32u, b + 32u, id, 1u); mma_h(T0, a + 48u, b + 48u, id, 1u);
@@ -273,12 +282,12 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
             k0 = chunks_wait(4); wait_go();
             if (TMA && p > 0) { mbar_wait(w1b, (p - 1) & 1); fence_after(); }
             l2(k0);
-            k0 = chunks_wait(1); wait_go(); head(k0);          // target head, then the eval L1 (runs under the target head epilogue)
+            k0 = chunks_wait(1); head(k0);                     // target head (waits go2 / go inside), then the eval L1 (runs under the target head epilogue)
             k0 = chunks_wait(5);
             if (TMA) { mbar_wait(xfull, p & 1); fence_after(); }
             l1(aX, k0);
             k0 = chunks_wait(4); wait_go(); l2(k0);
-            k0 = chunks_wait(1); wait_go(); head(k0);
+            k0 = chunks_wait(1); head(k0);
             k0 = chunks_wait(1);
             wait_go();
             {   // dH2 half 0 (n2 < 128) -> columns 128..255: A = dOut [128][16], B = Wh^T chunk rows 0..127 [256 n2][16 j], and the half
@@ -449,6 +458,7 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
         int tr_n = 0, tr_p = -1;
         auto stamp = [&]() { if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && tr_p == 3 && tr_n < 40) P.trace[tr_n++] = clock64(); };
         auto go_signal = [&]() { fence_proxy_async(); fence_before(); mbar_arrive(go); stamp(); };
+        auto go2_signal = [&]() { fence_proxy_async(); fence_before(); mbar_arrive(go2); };
         auto wait_done = [&]() { mbar_wait(done, done_no & 1); ++done_no; fence_after(); stamp(); };
         auto wait_done2 = [&]() { mbar_wait(done2, done2_no & 1); ++done2_no; fence_after(); stamp(); };
         auto wait_l1 = [&]() { mbar_wait(doneL1, l1_no & 1); ++l1_no; fence_after(); stamp(); };
@@ -598,6 +608,7 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
             wait_done();
             gather_load(P.rp.obs, buf);                             // (float32 rings: eval rows of this pair, in flight behind the L2 epilogue)
             l2_epilogue(bias_t, 0);
+            go2_signal();                                           // -> first half of the target head's k-steps
             wait_done2();
             l2_epilogue(bias_t, 1);
             gather_store(PO_X);
@@ -619,6 +630,7 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
             go_signal();                                            // -> eval L2 (overwrites the target head columns: consumed above)
             wait_done();
             l2_epilogue(bias_e, 0);
+            go2_signal();                                           // -> first half of the eval head's k-steps
             wait_done2();
             l2_epilogue(bias_e, 1);
             go_signal();                                            // -> eval head
