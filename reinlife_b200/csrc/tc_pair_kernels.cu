@@ -342,8 +342,10 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
                 }
                 stage_free();
             }
+            commit(done);                                      // dW2 (reads H1) and dH1 are complete: the dH1 epilogue may overwrite H1
             {   // db2[n2] = sum_b dH2[b][n2] as a GEMM with a block of ones: A = dH2 read MN-major (M = n2 half m), B = ones [16 k][16]
-                // (the same 512 bytes for every k-step) -> columns 16 m.. (all 16 equal); replaces 62 shuffles per 64 columns
+                // (the same 512 bytes for every k-step) -> columns 16 m.. (all 16 equal); replaces 62 shuffles per 64 columns.  Its 16
+                // issue-bound N = 16 MMAs run under the dH1 epilogue (handed over on done2)
                 const uint32_t id = idesc_h(128, 16, 1, 1);
                 const uint64_t b = dm(aOnes, 16);
 #pragma unroll 1
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
                         a += 2048u;
                     }
                 }
-                commit(done);
+                commit(done2);
                 if (TMA) commit(h2free);                       // dH2 is dead: the next pair's target rows may land in the H2 region
             }
             wait_go();
@@ -709,18 +711,16 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
             if (!TMA && more) epi_bar();                            // the next pair's metadata (threads 0-127) is visible to every warp
             wait_done();
             if (more) gather_load(P.rp.next_obs, buf ^ 1);          // (float32 rings: next pair's target rows, in flight behind the dH1 epilogue)
-            {   // db2 of feature n2 = 128 hh + row, then the dH1 epilogue: this thread's row, columns [64 hh, +64) of the accumulator at
-                // TMEM columns 128..255: dH1 = H1 > 0 ? acc : 0 in place of H1
+            {   // the dH1 epilogue: this thread's row, columns [64 hh, +64) of the accumulator at TMEM columns 128..255:
+                // dH1 = H1 > 0 ? acc : 0 in place of H1
                 const int c0 = hh * 64;
-                float v0[32], v1[32], b2v[16];
-                tmem_ld16(T0 + t_lane + 16 * hh, b2v);
+                float v0[32], v1[32];
                 tmem_ld32(T0 + t_lane + 128 + c0, v0);
                 tmem_ld32(T0 + t_lane + 128 + c0 + 32, v1);
                 uint4 hm[8];
 #pragma unroll
                 for (int j8 = 0; j8 < 8; ++j8) hm[j8] = *reinterpret_cast<const uint4*>(sH1 + himg(row, c0 + j8 * 8, 128));
                 tmem_wait_ld();
-                acc_b2 += b2v[0];
 #pragma unroll
                 for (int j8 = 0; j8 < 8; ++j8) {
                     const float* v = j8 < 4 ? v0 + j8 * 8 : v1 + (j8 - 4) * 8;
@@ -729,7 +729,14 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
                                    mask_pos(pk_sat(v[4], v[5]), hm[j8].z), mask_pos(pk_sat(v[6], v[7]), hm[j8].w));
                 }
             }
-            if (more) gather_store(PO_H2);                          // (float32 rings) X' of the next pair -> H2 region: dH2 is dead (dW2 / dH1 done)
+            wait_done2();                                           // db2 (ran under the epilogue above): feature n2 = 128 hh + row, before dW1 overwrites its columns
+            {
+                float b2v[16];
+                tmem_ld16(T0 + t_lane + 16 * hh, b2v);
+                tmem_wait_ld();
+                acc_b2 += b2v[0];
+            }
+            if (more) gather_store(PO_H2);                          // (float32 rings) X' of the next pair -> H2 region: dH2 is dead (dW2 / dH1 / db2 done)
             go_signal();                                            // -> dW1
             wait_done();
             if (TMA) {   // the accumulator warps take dW1 out of TMEM (w1a, w1b gate the next pair's target L1, L2)
