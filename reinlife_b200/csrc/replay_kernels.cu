@@ -156,7 +156,9 @@ __global__ void __launch_bounds__(RT) k_replay_store(const ReplayParams P) {
 }
 
 // ---- sample: CTA per world, exact-integer CDF in shared memory ----
-__device__ __forceinline__ unsigned long long fix_of(float w) { return __double2ull_rz((double)w * 16777216.0); }
+// floor(w * 2^24) of a non-negative float32 weight: the product is a pure exponent shift (exact in float32, weights are far below 2^39), so the
+// single-precision conversion returns exactly what the float64 formulation of the oracle (int(float64(w) * 2^24)) does, without the FP64 pipe
+__device__ __forceinline__ unsigned long long fix_of(float w) { return __float2ull_rz(w * 16777216.0f); }
 
 __global__ void __launch_bounds__(RT) k_replay_sample(const ReplayParams P) {
     extern __shared__ __align__(16) unsigned long long cum[];

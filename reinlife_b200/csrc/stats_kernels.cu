@@ -87,14 +87,21 @@ __global__ void __launch_bounds__(ST) k_world_stats(const StatsParams P) {
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    for (int i = threadIdx.x; i < NV; i += ST) {
+    // one warp per value: lane l folds blocks l, l + 32, ... in order, then a fixed xor tree -- deterministic, and the loads of a lane are
+    // independent (a single thread walking all blocks of a value was a chain of ~nblocks / 4 L2 round trips: most of the kernel's time)
+    for (int i = warp; i < NV; i += ST / 32) {
         const bool is_max = i < G * RL_N_STATS && (i % RL_N_STATS) == RL_STAT_AGE_MAX;
         double s = 0.0;
-        for (int b = 0; b < P.nblocks; ++b) {
-            const double v = P.scratch[(size_t)b * NV + i];
+        for (int b = lane; b < P.nblocks; b += 32) {
+            const double v = __ldcg(P.scratch + (size_t)b * NV + i);
             s = is_max ? fmax(s, v) : s + v;
         }
-        P.out[i] = s;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double t = __shfl_xor_sync(0xffffffffu, s, o);
+            s = is_max ? fmax(s, t) : s + t;
+        }
+        if (lane == 0) P.out[i] = s;
     }
     if (threadIdx.x == 0) {
         P.out[G * RL_N_STATS + 3] = P.ctrl ? (double)P.ctrl[0] : 0.0;
