@@ -376,8 +376,8 @@ def run_b200(args):
     traffic = None
     try:
         # static number: dram__bytes_read + dram__bytes_write of ONE launch from the committed `ncu --set full` capture of this
-        # same command (profiles/ncu_full_r02b_summary.md), not measured in this run
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02b.json"))).get(learn_kernel_name + "_bytes_per_launch")
+        # same command (profiles/ncu_full_r02c_summary.md), not measured in this run
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02c.json"))).get(learn_kernel_name + "_bytes_per_launch")
     except Exception:
         pass
     peaks = {}
@@ -414,7 +414,7 @@ def run_b200(args):
         v["frac"] = v["achieved"] / v["peak"]
     dominant = max(roof_k, key=lambda k: roof_k[k]["ms"] * roof_k[k].get("launches_per_step", 1))
     roofline = dict(roof_k[dominant], kernel=dominant, traffic=traffic if dominant == learn_kernel_name else None,
-                    traffic_source="profiles/traffic_r02b.json (static: one launch under ncu --set full, same command)", peak_source=peak_src,
+                    traffic_source="profiles/traffic_r02c.json (static: one launch under ncu --set full, same command)", peak_source=peak_src,
                     step_share=roof_k[dominant]["ms"] * roof_k[dominant].get("launches_per_step", 1) / sum(phases.values()))
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(3, args.warmup),
