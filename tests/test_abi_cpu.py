@@ -37,7 +37,7 @@ def test_struct_layouts_match_the_header():
     from reinlife_b200 import _lib
     from reinlife_b200.World.vecworld import REC_DTYPE
     assert REC_DTYPE.itemsize == 16
-    pairs = [("rl_world_cfg", _lib.WorldCfg, "world_id0"), ("rl_world_bufs", _lib.WorldBufs, "reward_div100"),
+    pairs = [("rl_world_cfg", _lib.WorldCfg, "world_id0"), ("rl_world_bufs", _lib.WorldBufs, "obs_prime_h"),
              ("rl_rows_bufs", _lib.RowsBufs, "row_cap"), ("rl_replay_bufs", _lib.ReplayBufs, "obs_fp16"),
              ("rl_learn_bufs", _lib.LearnBufs, "lr"), ("rl_brain_act", _lib.BrainAct, "epsilon"),
              ("rl_brain_sched", _lib.BrainSched, "max_epi"), ("rl_ppo_bufs", _lib.PpoBufs, "eps_clip"),
