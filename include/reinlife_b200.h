@@ -457,6 +457,10 @@ int rl_tc_gemm_test_hx(const void* a_img, const void* b_img, float* d, int M, in
 int rl_tma_gather_test(const void* ring, long long n_rows, const int32_t* idx, void* out, int box_rows);
 
 int rl_tc_gemm_test(const float* a_img, const float* b_img, float* d, int M, int N, int K, int a_mn, int b_mn, void* stream);
+/* Probe hook behind it (scripts/tc_probe.py): the same tf32 tile GEMM with caller-supplied B descriptor geometry
+ * (leading / stride byte offsets, byte advance per k-step; 0 = the defaults of rl_tc_gemm_test). */
+int rl_tc_gemm_test_ex(const float* a_img, const float* b_img, float* d, int M, int N, int K, int a_mn, int b_mn,
+                       int b_lbo, int b_sbo, int b_kstep, void* stream);
 /* Test hook: one-tile tcgen05 kind::f16 GEMM  D[M,N] = A * B^T  on fp16 operand images with caller-supplied descriptor
  * geometry (leading / stride byte offsets, byte advance per K = 16 step) and major-ness (a_mn / b_mn = 1: MN-major). */
 int rl_tc_gemm_test_h(const void* a_img, const void* b_img, float* d, int M, int N, int K, int a_halves, int b_halves,
