@@ -10,6 +10,9 @@ import subprocess
 import sys
 
 launch_csv, rep, tag = sys.argv[1], sys.argv[2], sys.argv[3]
+# the ncu selection of the full capture (4th argument), as written into the summary header
+FULL_SEL = sys.argv[4] if len(sys.argv) > 4 else ('-k regex:"k_learn_dueling_p|k_world_step|k_world_update|k_replay_store|k_act_dueling_p|k_replay_sample|'
+                                                  'k_replay_update_prio|k_world_stats" -s 40 -c 12')
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out_dir = os.path.join(ROOT, "profiles")
 
@@ -64,7 +67,7 @@ for row in r[2:]:
                                               float(d["dram__bytes_write.sum"]) * scale[u["dram__bytes_write.sum"]])
 with open(os.path.join(out_dir, f"ncu_full_{tag}_summary.md"), "w") as f:
     f.write(f"# ncu --set full, {tag} (one row per kernel; first captured launch)\n\n"
-            "Command: `ncu --set full --clock-control none --import-source on -k regex:\"k_learn_dueling_p|k_world_step|k_world_update|k_replay_store|k_act_dueling_p|k_replay_sample\" -s 30 -c 10 "
+            f"Command: `ncu --set full --clock-control none --import-source on {FULL_SEL} "
             "python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (the event kernel's name is k_learn_dueling_h in the round-1 captures)\n\n| kernel | " + " | ".join(cols) + " |\n|" + "---|" * (len(cols) + 1) + "\n"
             "| (unit) | " + " | ".join(dict(zip(hdr, units))[c] for c in cols) + " |\n" + "\n".join(lines) + "\n")
 json.dump(traffic, open(os.path.join(out_dir, f"traffic_{tag}.json"), "w"), indent=1)
