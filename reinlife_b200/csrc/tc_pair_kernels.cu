@@ -44,7 +44,8 @@ using mlp::mbar_init; using mlp::mbar_wait; using mlp::fence_mbar_init; using ml
 constexpr int R = 64;                    // rows per event
 constexpr int NEPI = 256;                // epilogue threads (warps 0-7)
 constexpr int NTH = NEPI + 64;           // + weight producer (warp 8) + MMA issuer (warp 9)
-constexpr int NGW = 4;                   // TMA = true: + warps 10, 11 (idle: they complete warpgroup 2) + NGW accumulator / row-gatherer warps 12..
+constexpr int NGW = 4;                   // TMA = true: + warps 10, 11 (row gatherers: they complete warpgroup 2) + NGW accumulator / row-gatherer warps 12..
+constexpr int NGI = NGW + 2;             // warps that issue the row gathers of an image: 96 tile::gather4 = NGI x 16 lanes
 constexpr int NTH_TMA = NEPI + 128 + 32 * NGW;
 // register budget of the TMA variant (setmaxnreg, per warpgroup of 4 warps): 512 threads are launched with 128 registers each (the pool
 // setmaxnreg redistributes is the CTA's launch allocation); the epilogue warpgroups 0-1 keep them, warpgroup 2 (producer, issuer) shrinks
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
         for (int i = 0; i < NSTG; ++i) mbar_init(&gfull[i], 1);
         for (int i = 0; i < NSTG; ++i) mbar_init(&sfree[i], 1);
         mbar_init(done, 1); mbar_init(done2, 1); mbar_init(doneL1, 1); mbar_init(go, NEPI); mbar_init(go2, NEPI);
-        mbar_init(xfull, NGW); mbar_init(xpfull, NGW); mbar_init(h2free, 1); mbar_init(xfree, 1); mbar_init(metaready, PB); mbar_init(w1a, 32 * NGW); mbar_init(w1b, 32 * NGW);
+        mbar_init(xfull, NGI); mbar_init(xpfull, NGI); mbar_init(h2free, 1); mbar_init(xfree, 1); mbar_init(metaready, PB); mbar_init(w1a, 32 * NGW); mbar_init(w1b, 32 * NGW);
         fence_mbar_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -379,6 +380,33 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
                 if (TMA) commit(xfree);                        // X is dead: the next pair's eval rows may land in the X region
             }
         }
+      } else if (TMA) {
+        // =================================== warps 10, 11: row gatherers only ===================================
+        // They take a sixth each of the 96 gathers of an image (gather op o = 6 l + j of lane l < 16, j = warp's gather index): the
+        // accumulator warps then need ~1.6 k instead of ~2.4 k cycles to issue X' before they turn to the dW1 accumulator (w1a gates
+        // the next target L1).
+        const int j = NGW + (warp - 10);
+        const int o = lane * NGI + j, g = o / 3, kb = o - g * 3;
+        const bool act = lane < 16;
+        for (int p = 0; p < n_pairs; ++p) {
+            const int buf = p & 1;
+            mbar_wait(metaready, p & 1);
+            const int* ids = meta + buf * 4 * PB;
+            int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+            if (act) {
+                const int rb = (int)ringb[buf * 2 + (g >> 4)];
+                const int4 i4 = *reinterpret_cast<const int4*>(ids + 4 * g);
+                r0 = rb + i4.x; r1 = rb + i4.y; r2 = rb + i4.z; r3 = rb + i4.w;
+            }
+            if (p > 0) mbar_wait(h2free, (p - 1) & 1);
+            if (lane == 0) mbar_expect_tx(xpfull, XIMG / NGI);
+            __syncwarp();
+            if (act) tma::gather4(aH2 + kb * XBLK + g * 512, &P.map_next, smem_u32(xpfull), kb * 64, r0, r1, r2, r3);
+            if (p > 0) mbar_wait(xfree, (p - 1) & 1);
+            if (lane == 0) mbar_expect_tx(xfull, XIMG / NGI);
+            __syncwarp();
+            if (act) tma::gather4(aX + kb * XBLK + g * 512, &P.map_obs, smem_u32(xfull), kb * 64, r0, r1, r2, r3);
+        }
       }
     } else if (warp >= 12) {
         if (TMA) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_ACC));
@@ -396,8 +424,8 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
         //     X of pair p to the X region once pair p-1's dW1 has completed (xfree).
         if (TMA) {
             const int w = warp - 12;
-            const int g = (lane / 3) * NGW + w, kb = lane - (lane / 3) * 3;
-            const bool act = lane < 24;
+            const int o = lane * NGI + w, g = o / 3, kb = o - g * 3;       // gather op o of 96: row group g (4 rows), K block kb
+            const bool act = lane < 16;
             if (lane == 0) tma::prefetch_map(w & 1 ? &P.map_obs : &P.map_next);
             const uint32_t T0 = *tmem_slot;
             const int k1 = (warp & 3) * 32 + lane;
@@ -430,11 +458,11 @@ __global__ void __launch_bounds__(TMA ? NTH_TMA : NTH, 1) k_learn_dueling_p(cons
                     r0 = rb + i4.x; r1 = rb + i4.y; r2 = rb + i4.z; r3 = rb + i4.w;
                 }
                 if (p > 0) mbar_wait(h2free, (p - 1) & 1);
-                if (lane == 0) mbar_expect_tx(xpfull, XIMG / NGW);
+                if (lane == 0) mbar_expect_tx(xpfull, XIMG / NGI);
                 __syncwarp();
                 if (act) tma::gather4(aH2 + kb * XBLK + g * 512, &P.map_next, smem_u32(xpfull), kb * 64, r0, r1, r2, r3);
                 if (p > 0) { mbar_wait(xfree, (p - 1) & 1); fence_after(); w1_add(); }
-                if (lane == 0) mbar_expect_tx(xfull, XIMG / NGW);
+                if (lane == 0) mbar_expect_tx(xfull, XIMG / NGI);
                 __syncwarp();
                 if (act) tma::gather4(aX + kb * XBLK + g * 512, &P.map_obs, smem_u32(xfull), kb * 64, r0, r1, r2, r3);
             }
